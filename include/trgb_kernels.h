@@ -1,0 +1,138 @@
+/* trgb_kernels.h — thin C ABI over the hand-written sm_100a CUDA kernels of the TRG hot path.
+ *
+ * This is the seam that replaces the reference's per-call C kd-tree API
+ *   cpp/trg_planner/core/trg_planner/include/kdtree/kdtree.h:30-115   (kd_create / kd_insert2 /
+ *   kd_nearest2 / kd_nearest_range2 / kd_res_*), which trg.cpp drives one point at a time,
+ * with batched, pure functions of (queries, static map, params). Plain pointers and sizes,
+ * `int` status (0 ok, <0 error; text via trgb_last_error()), no exceptions, no torch types.
+ * Caller-owned host buffers, library-owned device memory, one CUDA stream per map handle;
+ * a handle may be used by one thread at a time (the reference serialises on TRG::mtx.graph).
+ *
+ * Two tiers:
+ *   *_batch   host buffers in/out, synchronous (what a cgo/ctypes/pybind stub binds);
+ *   *_launch  device pointers, asynchronous on the handle's stream (what the C++ host
+ *             library trg-planner_b200/host uses inside TRG::expandGraph, and what bench.py
+ *             uses for the "inputs already resident in HBM" number).
+ * There is no CPU fallback: every entry point fails with TRGB_E_CUDA when no device is usable.
+ */
+#ifndef TRGB_KERNELS_H_
+#define TRGB_KERNELS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { TRGB_OK = 0, TRGB_E_ARG = -1, TRGB_E_CUDA = -2, TRGB_E_NOMEM = -3, TRGB_E_STATE = -4 };
+
+/* stage at which TRG::wireEdge's geometric part stops (trg.cpp:269-329). The slope gate
+ * (:269-274, glibc atan2f) is applied on the host side of the boundary. */
+enum { TRGB_EDGE_OK = 0, TRGB_EDGE_SLOPE = 1, TRGB_EDGE_COLLISION = 2, TRGB_EDGE_EMPTY = 3, TRGB_EDGE_FEWPTS = 4 };
+
+typedef struct trgb_map trgb_map;     /* device-resident cell index over one point cloud  */
+typedef struct trgb_graph trgb_graph; /* device-resident CSR graph + node kd-tree arrays  */
+
+typedef struct TrgbMapInfo {
+  int64_t n_points;
+  int32_t grid_w, grid_h;
+  float   origin_x, origin_y, cell_size;
+  int64_t device_bytes;
+} TrgbMapInfo;
+
+/* TRG::Param subset the edge kernel needs (trg.h:132-142) */
+typedef struct TrgbEdgeParams {
+  float robot_size;
+  float height_threshold;
+  float collision_threshold;
+} TrgbEdgeParams;
+
+const char* trgb_last_error(void);
+int trgb_device_count(void);
+int trgb_set_device(int device);
+
+/* ---- K1: map index build — replaces the kd_insert2 loop of TRG::setGlobalMap / setLocalMap
+ *      (trg.cpp:185-188, 203-206; kdtree.c:167-209). Points: n records of `stride_floats`
+ *      floats (3 = packed xyz, 4 = pcl::PointXYZ). cell_size <= 0 picks robot_size/2 semantics
+ *      left to the caller; must be > 0. */
+int  trgb_map_create(trgb_map** out, const float* host_pts, int64_t n, int stride_floats, float cell_size);
+int  trgb_map_create_dev(trgb_map** out, const float* dev_pts, int64_t n, int stride_floats, float cell_size);
+void trgb_map_destroy(trgb_map* m);
+int  trgb_map_info(const trgb_map* m, TrgbMapInfo* info);
+void* trgb_map_stream(const trgb_map* m); /* cudaStream_t */
+int  trgb_map_sync(const trgb_map* m);
+
+/* ---- tier 1: host-buffer batches (synchronous) ---------------------------------------- */
+/* K2 — TRG::isCollision (trg.cpp:746-778) for n query points xy[2n]; out[i] in {0,1} */
+int trgb_collision_batch(trgb_map* m, const float* xy, int64_t n, float radius, float height_thr,
+                         float ratio_thr, uint8_t* out);
+/* kd_nearest_range2 result size (kdtree.c:479-501) */
+int trgb_range_count_batch(trgb_map* m, const float* xy, int64_t n, float radius, int32_t* out);
+/* K3 — kd_nearest2 on the map tree + payload z (trg.cpp:244-246). tie[i]=1 when another
+ * point has the identical float dist^2 (the reference resolves by kd-tree visit order; this
+ * library by lowest original point index). */
+int trgb_nearest_z_batch(trgb_map* m, const float* xy, int64_t n, float* z, int64_t* idx, uint8_t* tie);
+/* K4 — geometric part of TRG::wireEdge (trg.cpp:269-363) incl. the host-side slope gate */
+int trgb_edge_eval_batch(trgb_map* m, const float* p1_xyz, const float* p2_xyz, int64_t n,
+                         const TrgbEdgeParams* prm, uint8_t* stage, float* weight, float* dist,
+                         int32_t* npts);
+
+/* ---- tier 2: device-pointer launches (asynchronous on trgb_map_stream(m)) -------------- */
+int trgb_collision_launch(const trgb_map* m, const float* d_xy, int64_t n, float radius,
+                          float height_thr, float ratio_thr, uint8_t* d_out);
+int trgb_range_count_launch(const trgb_map* m, const float* d_xy, int64_t n, float radius, int32_t* d_out);
+/* sampling windows of TRG::expandGraph (trg.cpp:387-403): for node i and j < window, test
+ * isCollision(node_xy[i] + draw_xy[first_draw[i] + j]); bit j of d_mask[i] = collision.
+ * Each node owns (window+63)/64 consecutive 64-bit words of d_mask, which the caller zeroes;
+ * window <= 256. */
+int trgb_sample_window_launch(const trgb_map* m, const float* d_node_xy, const int32_t* d_first_draw,
+                              const float* d_draw_xy, int64_t n_nodes, int window, float radius,
+                              float height_thr, float ratio_thr, unsigned long long* d_mask);
+int trgb_nearest_z_launch(const trgb_map* m, const float* d_xy, int64_t n, float* d_z, int64_t* d_idx,
+                          uint8_t* d_tie);
+/* p1: (x,y,z) start node; p2: (x,y) end point (its z only enters the host-side slope gate).
+ * d_stage gets OK/COLLISION/EMPTY/FEWPTS. */
+int trgb_edge_eval_launch(const trgb_map* m, const float* d_p1_xyz, const float* d_p2_xy, int64_t n,
+                          const TrgbEdgeParams* prm, uint8_t* d_stage, float* d_weight, float* d_dist,
+                          int32_t* d_npts);
+
+/* ---- K7: graph upload + batched risk-aware shortest path (TRG::planSafePath, trg.cpp:618-688).
+ *      CSR rows = node id 0..n-1, columns in `edges_` order. Start/goal snapping
+ *      (TRG::setGoal trg.cpp:537-565, kd_nearest2 :615) is order-dependent host logic and stays
+ *      in the C++ host library; this layer takes node ids. */
+typedef struct TrgbGraphDesc {
+  int32_t n_nodes;
+  int64_t n_edges;
+  const int64_t* row_ptr;   /* n_nodes+1 */
+  const int32_t* col;       /* n_edges */
+  const float*   weight;    /* n_edges */
+  const float*   dist;      /* n_edges */
+  const float*   pos_xyz;   /* 3*n_nodes */
+  const int32_t* state;     /* n_nodes: 0 valid, -1 invalid, 1 frontier */
+} TrgbGraphDesc;
+
+int  trgb_graph_upload(trgb_graph** out, const TrgbGraphDesc* g);
+void trgb_graph_destroy(trgb_graph* g);
+/* n (start, goal) node-id pairs. Outputs per query: found; cost = float-accumulated
+ * g(goal) = sum (sf*w+1)*dist in the reference's evaluation order (trg.cpp:674);
+ * path_length = sum dist and avg_risk = sum w / #path nodes accumulated goal->start like
+ * trg.cpp:641-659; node id sequences start..goal concatenated in path_ids, path_offsets[n+1].
+ * Returns TRGB_E_NOMEM (and the needed size in path_offsets[n]) when path_ids_capacity is
+ * too small. */
+int trgb_sssp_batch(trgb_graph* g, const int32_t* start_ids, const int32_t* goal_ids, int64_t n,
+                    float safety_factor, uint8_t* found, float* cost, float* path_length,
+                    float* avg_risk, int64_t* path_offsets, int32_t* path_ids,
+                    int64_t path_ids_capacity);
+
+/* ---- profiling: CUDA-event timing of every kernel launched by this library ------------- */
+int trgb_prof_enable(int on);
+int trgb_prof_reset(void);
+/* fills up to cap entries; returns the number of distinct kernels seen */
+typedef struct TrgbProfEntry { char name[48]; int64_t launches; double total_ms; double bytes; } TrgbProfEntry;
+int trgb_prof_collect(TrgbProfEntry* out, int cap);
+int64_t trgb_launch_count(void); /* kernels launched by this library since load / reset */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRGB_KERNELS_H_ */

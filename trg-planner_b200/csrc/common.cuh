@@ -1,0 +1,284 @@
+// Shared device/host helpers of the sm_100a TRG kernels.
+//
+// Parity-critical arithmetic (set membership, segment sample positions, medians) is written
+// with explicit round-to-nearest intrinsics (__fadd_rn/__fmul_rn/__fsub_rn/__fdiv_rn/
+// __fsqrt_rn): they are never contracted into FMAs, so results are bit-identical to the
+// reference's baseline-x86-64 float arithmetic (SURVEY.md hard part 2). The whole library is
+// additionally compiled with --fmad=false.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdio>
+#include <mutex>
+#include <string>
+
+#include "trgb_kernels.h"
+
+namespace trgb {
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define TRGB_CUDA(expr)                                                        \
+  do {                                                                         \
+    cudaError_t _e = (expr);                                                   \
+    if (_e != cudaSuccess) return ::trgb::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define TRGB_ARG(cond, msg)                                   \
+  do {                                                        \
+    if (!(cond)) {                                            \
+      ::trgb::set_error(std::string("bad argument: ") + msg); \
+      return TRGB_E_ARG;                                      \
+    }                                                         \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// profiling (CUDA events on the launching stream) + launch counter
+// ------------------------------------------------------------------------------------------
+struct ProfScope {
+  ProfScope(const char* name, cudaStream_t s, double bytes);
+  ~ProfScope();
+  const char* name_;
+  cudaStream_t s_;
+  double bytes_;
+  cudaEvent_t start_ = nullptr, stop_ = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------
+// map view (HBM layout)
+//   pts        float4[n]  (x, y, z, bit-cast original index), sorted by row-major cell id,
+//                         ascending original index inside a cell (deterministic)
+//   cell_start uint32[W*H+1]  exclusive prefix of points per cell; the cells of one grid row
+//                         are consecutive, so a query's cell span in a row is ONE contiguous run
+// ------------------------------------------------------------------------------------------
+struct MapView {
+  const float4* pts;
+  const uint32_t* cell_start;
+  float x0, y0, inv_cell, cell;
+  int W, H;
+  int64_t n;
+};
+
+#ifdef __CUDACC__
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ int cell_coord(float v, float origin, float inv_cell, int dim) {
+  // monotone non-decreasing in v: float sub, float mul, floor, clamp
+  float f = floorf(__fmul_rn(__fsub_rn(v, origin), inv_cell));
+  if (!(f > 0.0f)) return 0;  // also catches NaN
+  if (f >= (float)dim) return dim - 1;
+  return (int)f;
+}
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+__device__ __forceinline__ float4 ld_pt(const float4* p) { return __ldg(p); }
+
+// order-preserving float -> uint key (ascending)
+__device__ __forceinline__ uint32_t fkey(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(uint32_t k) {
+  uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(u);
+}
+
+// Inflated search half-width for a radius-r membership test `fl(dx^2+dy^2) <= fl(r^2)`:
+// any point passing the float test has |dx| <= r*(1+4eps); the cell span is computed from
+// q -+ rr with rr larger than r by more than the rounding of q -+ rr itself (which scales with
+// |q|), and cell_coord is monotone, so no hit can be missed.
+__device__ __forceinline__ float inflate(float r, float qx, float qy) {
+  return r * 1.00001f + 1e-6f + 1e-6f * (fabsf(qx) + fabsf(qy));
+}
+
+// Warp-cooperative iteration over every point stored in the cell block [cx0..cx1] x [cy0..cy1].
+// f(valid, p) is called by ALL lanes each round (so it may use warp collectives); `valid` is
+// false on padding lanes. Per grid row the block is one contiguous run of `pts`.
+template <class F>
+__device__ __forceinline__ void warp_for_each_in_cells(const MapView& m, int cx0, int cx1, int cy0,
+                                                       int cy1, F&& f) {
+  const int lane = threadIdx.x & 31;
+  for (int rbase = cy0; rbase <= cy1; rbase += 32) {
+    const int row = rbase + lane;
+    uint32_t s = 0, e = 0;
+    if (row <= cy1) {
+      const size_t b = (size_t)row * (size_t)m.W;
+      s = __ldg(m.cell_start + b + cx0);
+      e = __ldg(m.cell_start + b + cx1 + 1);
+    }
+    const uint32_t cnt = e - s;
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t t = __shfl_up_sync(FULL, inc, d);
+      if (lane >= d) inc += t;
+    }
+    const uint32_t total = __shfl_sync(FULL, inc, 31);
+    const uint32_t exc = inc - cnt;
+    const int nr = min(32, cy1 - rbase + 1);
+    for (uint32_t j0 = 0; j0 < total; j0 += 32) {
+      const uint32_t j = j0 + lane;
+      uint32_t addr = 0;
+      for (int r = 0; r < nr; ++r) {
+        const uint32_t er = __shfl_sync(FULL, exc, r);
+        const uint32_t ir = __shfl_sync(FULL, inc, r);
+        const uint32_t sr = __shfl_sync(FULL, s, r);
+        if (j >= er && j < ir) addr = sr + (j - er);
+      }
+      const bool valid = j < total;
+      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) p = ld_pt(m.pts + addr);
+      f(valid, p);
+    }
+  }
+}
+
+// ... over the cells intersecting the square [qx-rr, qx+rr] x [qy-rr, qy+rr]
+template <class F>
+__device__ __forceinline__ void warp_for_each_candidate(const MapView& m, float qx, float qy,
+                                                        float rr, F&& f) {
+  const int cx0 = cell_coord(qx - rr, m.x0, m.inv_cell, m.W);
+  const int cx1 = cell_coord(qx + rr, m.x0, m.inv_cell, m.W);
+  const int cy0 = cell_coord(qy - rr, m.y0, m.inv_cell, m.H);
+  const int cy1 = cell_coord(qy + rr, m.y0, m.inv_cell, m.H);
+  warp_for_each_in_cells(m, cx0, cx1, cy0, cy1, f);
+}
+
+// rank-select on a warp-private buffer: value with 0-based ascending rank `k` among zbuf[0..n)
+__device__ __forceinline__ float warp_select_smem(const float* zbuf, int n, int k) {
+  const int lane = threadIdx.x & 31;
+  if (n <= 32) {
+    const float z = lane < n ? zbuf[lane] : 0.f;
+    int less = 0, leq = 0;
+    for (int i = 0; i < n; ++i) {
+      const float zi = __shfl_sync(FULL, z, i);
+      less += (zi < z);
+      leq += (zi <= z);
+    }
+    const unsigned b = __ballot_sync(FULL, lane < n && less <= k && k < leq);
+    return __shfl_sync(FULL, z, __ffs(b) - 1);
+  }
+  // bitwise radix select on order-preserving keys, MSB first
+  uint32_t prefix = 0, mask = 0;
+  int kk = k;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t bm = 1u << bit;
+    int c0 = 0;
+    for (int i = lane; i < n; i += 32) {
+      const uint32_t key = fkey(zbuf[i]);
+      c0 += ((key & mask) == prefix && !(key & bm));
+    }
+    c0 = __reduce_add_sync(FULL, c0);
+    if (kk >= c0) {
+      kk -= c0;
+      prefix |= bm;
+    }
+    mask |= bm;
+  }
+  return fkey_inv(prefix);
+}
+
+// TRG::isCollision (trg.cpp:746-778) for one query, executed by one warp.
+// zbuf: warp-private shared buffer of `cap` floats. Returns a warp-uniform result;
+// *nhits_out receives the number of points in the cylinder.
+__device__ __forceinline__ bool warp_is_collision(const MapView& m, float qx, float qy, float r,
+                                                  float hthr, float rthr, float* zbuf, int cap,
+                                                  int* nhits_out) {
+  const int lane = threadIdx.x & 31;
+  const float r2 = __fmul_rn(r, r);
+  const float rr = inflate(r, qx, qy);
+  const unsigned lt = lanemask_lt();
+  int nhits = 0;
+  warp_for_each_candidate(m, qx, qy, rr, [&](bool valid, const float4& p) {
+    const float dx = __fsub_rn(p.x, qx), dy = __fsub_rn(p.y, qy);
+    const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+    const bool hit = valid && (d2 <= r2);
+    const unsigned b = __ballot_sync(FULL, hit);
+    if (hit) {
+      const int pos = nhits + __popc(b & lt);
+      if (pos < cap) zbuf[pos] = p.z;
+    }
+    nhits += __popc(b);
+  });
+  if (nhits_out) *nhits_out = nhits;
+  if (nhits == 0) return true;  // :749-752 empty cylinder => collision
+  __syncwarp();
+  const int mid = nhits / 2;  // :764 upper median
+  int cnt = 0;
+  if (nhits <= cap) {
+    const float zmed = warp_select_smem(zbuf, nhits, mid);
+    for (int i = lane; i < nhits; i += 32) cnt += (fabsf(__fsub_rn(zbuf[i], zmed)) > hthr);
+    cnt = __reduce_add_sync(FULL, cnt);
+  } else {
+    // overflow path (cylinder holds more points than the shared buffer): radix select by
+    // re-scanning the candidates from L2/HBM, 32 passes. Correct for any density.
+    uint32_t prefix = 0, mask = 0;
+    int kk = mid;
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t bm = 1u << bit;
+      int c0 = 0;
+      warp_for_each_candidate(m, qx, qy, rr, [&](bool valid, const float4& p) {
+        const float dx = __fsub_rn(p.x, qx), dy = __fsub_rn(p.y, qy);
+        const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        const uint32_t key = fkey(p.z);
+        c0 += (valid && d2 <= r2 && (key & mask) == prefix && !(key & bm));
+      });
+      c0 = __reduce_add_sync(FULL, c0);
+      if (kk >= c0) {
+        kk -= c0;
+        prefix |= bm;
+      }
+      mask |= bm;
+    }
+    const float zmed = fkey_inv(prefix);
+    warp_for_each_candidate(m, qx, qy, rr, [&](bool valid, const float4& p) {
+      const float dx = __fsub_rn(p.x, qx), dy = __fsub_rn(p.y, qy);
+      const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+      cnt += (valid && d2 <= r2 && fabsf(__fsub_rn(p.z, zmed)) > hthr);
+    });
+    cnt = __reduce_add_sync(FULL, cnt);
+  }
+  __syncwarp();
+  const float ratio = __fdiv_rn((float)cnt, (float)nhits);  // :773
+  return ratio > rthr;
+}
+
+#endif  // __CUDACC__
+
+// shared launch geometry: 8 warps per CTA, one query per warp at a time, grid sized to a
+// multiple of the SM count (persistent-style grid-stride loop)
+constexpr int kWarpsPerCta = 8;
+constexpr int kThreads = kWarpsPerCta * 32;
+int sm_count();
+int grid_for_warps(int64_t n_warps, int ctas_per_sm);
+
+}  // namespace trgb
+
+// opaque handle bodies
+struct trgb_map {
+  trgb::MapView view{};
+  float4* d_pts = nullptr;
+  uint32_t* d_cell_start = nullptr;
+  int64_t n = 0;
+  int64_t device_bytes = 0;
+  cudaStream_t stream = nullptr;
+  int zcap = 128;  // per-warp shared z buffer (floats) for the collision kernels
+  // pinned/device staging for the host-buffer tier
+  void* h_stage = nullptr;
+  size_t h_stage_bytes = 0;
+  void* d_stage = nullptr;
+  size_t d_stage_bytes = 0;
+};

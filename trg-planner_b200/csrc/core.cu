@@ -1,0 +1,152 @@
+// Error state, device selection, launch geometry and the CUDA-event profiler shared by all
+// kernels of libtrgb_kernels.so.
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "common.cuh"
+
+namespace trgb {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file,
+           line, what);
+  g_err = buf;
+  cudaGetLastError();  // clear sticky-less errors
+  return e == cudaErrorMemoryAllocation ? TRGB_E_NOMEM : TRGB_E_CUDA;
+}
+
+int sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;  // B200
+  }
+  return sms;
+}
+
+int grid_for_warps(int64_t n_warps, int ctas_per_sm) {
+  const int64_t need = (n_warps + kWarpsPerCta - 1) / kWarpsPerCta;
+  const int64_t cap = (int64_t)sm_count() * ctas_per_sm;
+  int64_t g = need < cap ? need : cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ---- profiler ---------------------------------------------------------------------------
+struct Pending {
+  const char* name;
+  cudaEvent_t a, b;
+  double bytes;
+};
+struct Acc {
+  int64_t launches = 0;
+  double ms = 0, bytes = 0;
+};
+static std::mutex g_pmx;
+static bool g_prof_on = false;
+static std::vector<Pending> g_pending;
+static std::vector<cudaEvent_t> g_pool;
+static std::map<std::string, Acc> g_acc;
+static std::atomic<int64_t> g_launches{0};
+
+static cudaEvent_t get_event() {
+  if (!g_pool.empty()) {
+    cudaEvent_t e = g_pool.back();
+    g_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+static void drain_locked() {
+  for (auto& p : g_pending) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+      Acc& a = g_acc[p.name];
+      a.launches++;
+      a.ms += ms;
+      a.bytes += p.bytes;
+    }
+    g_pool.push_back(p.a);
+    g_pool.push_back(p.b);
+  }
+  g_pending.clear();
+}
+
+ProfScope::ProfScope(const char* name, cudaStream_t s, double bytes) : name_(name), s_(s), bytes_(bytes) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_pmx);
+  start_ = get_event();
+  stop_ = get_event();
+  cudaEventRecord(start_, s_);
+}
+ProfScope::~ProfScope() {
+  if (!start_) return;
+  std::lock_guard<std::mutex> lk(g_pmx);
+  cudaEventRecord(stop_, s_);
+  g_pending.push_back({name_, start_, stop_, bytes_});
+  if (g_pending.size() >= 2048) drain_locked();
+}
+
+}  // namespace trgb
+
+using namespace trgb;
+
+extern "C" const char* trgb_last_error(void) { return g_err.c_str(); }
+
+extern "C" int trgb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+extern "C" int trgb_set_device(int device) {
+  TRGB_CUDA(cudaSetDevice(device));
+  return TRGB_OK;
+}
+
+extern "C" int trgb_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_pmx);
+  g_prof_on = on != 0;
+  return TRGB_OK;
+}
+
+extern "C" int trgb_prof_reset(void) {
+  std::lock_guard<std::mutex> lk(g_pmx);
+  drain_locked();
+  g_acc.clear();
+  g_launches.store(0);
+  return TRGB_OK;
+}
+
+extern "C" int trgb_prof_collect(TrgbProfEntry* out, int cap) {
+  std::lock_guard<std::mutex> lk(g_pmx);
+  drain_locked();
+  int i = 0;
+  for (auto& kv : g_acc) {
+    if (out && i < cap) {
+      memset(&out[i], 0, sizeof(TrgbProfEntry));
+      strncpy(out[i].name, kv.first.c_str(), sizeof(out[i].name) - 1);
+      out[i].launches = kv.second.launches;
+      out[i].total_ms = kv.second.ms;
+      out[i].bytes = kv.second.bytes;
+    }
+    ++i;
+  }
+  return i;
+}
+
+extern "C" int64_t trgb_launch_count(void) { return g_launches.load(); }

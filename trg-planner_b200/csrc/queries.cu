@@ -1,0 +1,545 @@
+// K2 / K3 / K4 and the sampling-window kernel: batched, pure functions of
+// (query, static map index, params). One warp per query; the cells a query touches are
+// contiguous float4 runs (one per grid row), loaded coalesced through the read-only path.
+//
+//   k_collision      TRG::isCollision                      trg.cpp:746-778 (+ kdtree.c:270-301)
+//   k_range_count    kd_nearest_range2 result size         kdtree.c:479-501
+//   k_sample_window  sampling loop of TRG::expandGraph     trg.cpp:387-403 (collision bits only)
+//   k_nearest_z      kd_nearest2 on the map tree + z       trg.cpp:244-246 (+ kdtree.c:303-417)
+//   k_edge_eval      geometric part of TRG::wireEdge       trg.cpp:276-363
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+
+namespace trgb {
+
+// ------------------------------------------------------------------------------------------
+// K2
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_collision(MapView m, const float2* __restrict__ q,
+                                                        int64_t n, float r, float hthr, float rthr,
+                                                        int cap, uint8_t* __restrict__ out) {
+  extern __shared__ float zsm[];
+  float* zbuf = zsm + (threadIdx.x >> 5) * cap;
+  const int lane = threadIdx.x & 31;
+  const int64_t wstride = (int64_t)gridDim.x * kWarpsPerCta;
+  for (int64_t i = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); i < n; i += wstride) {
+    const float2 p = __ldg(q + i);
+    const bool c = warp_is_collision(m, p.x, p.y, r, hthr, rthr, zbuf, cap, nullptr);
+    if (lane == 0) out[i] = c ? 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_range_count(MapView m, const float2* __restrict__ q,
+                                                          int64_t n, float r, int32_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const float r2 = __fmul_rn(r, r);
+  const int64_t wstride = (int64_t)gridDim.x * kWarpsPerCta;
+  for (int64_t i = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); i < n; i += wstride) {
+    const float2 p = __ldg(q + i);
+    int cnt = 0;
+    warp_for_each_candidate(m, p.x, p.y, inflate(r, p.x, p.y), [&](bool valid, const float4& c) {
+      const float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y);
+      const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+      cnt += (valid && d2 <= r2);
+    });
+    cnt = __reduce_add_sync(FULL, cnt);
+    if (lane == 0) out[i] = cnt;
+  }
+}
+
+// one warp per (node, draw) pair; bit j of mask[node] = isCollision(node + draw[first+j])
+__global__ void __launch_bounds__(kThreads) k_sample_window(
+    MapView m, const float2* __restrict__ node_xy, const int32_t* __restrict__ first_draw,
+    const float2* __restrict__ draw_xy, int64_t n_nodes, int window, float r, float hthr, float rthr,
+    int cap, unsigned long long* __restrict__ mask) {
+  extern __shared__ float zsm[];
+  float* zbuf = zsm + (threadIdx.x >> 5) * cap;
+  const int lane = threadIdx.x & 31;
+  const int64_t items = n_nodes * window;
+  const int64_t wstride = (int64_t)gridDim.x * kWarpsPerCta;
+  for (int64_t it = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); it < items; it += wstride) {
+    const int64_t node = it / window;
+    const int j = (int)(it - node * window);
+    const float2 np = __ldg(node_xy + node);
+    const float2 d = __ldg(draw_xy + (__ldg(first_draw + node) + j));
+    // sample = node->pos_.head(2) + Vector2f(e*cos, e*sin)   (trg.cpp:396-397); d = (e*cos, e*sin)
+    const float sx = __fadd_rn(np.x, d.x), sy = __fadd_rn(np.y, d.y);
+    const bool c = warp_is_collision(m, sx, sy, r, hthr, rthr, zbuf, cap, nullptr);
+    if (lane == 0 && c) atomicOr(mask + node * ((window + 63) >> 6) + (j >> 6), 1ull << (j & 63));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 — nearest map point in 2-D (strict `<` on float dist^2; ties -> lowest original index,
+// flagged). Ring search over cell blocks until the best distance is provably final.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_nearest_z(MapView m, const float2* __restrict__ q,
+                                                        int64_t n, float* __restrict__ z_out,
+                                                        int64_t* __restrict__ idx_out,
+                                                        uint8_t* __restrict__ tie_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wstride = (int64_t)gridDim.x * kWarpsPerCta;
+  const float extent = (float)m.W * m.cell + (float)m.H * m.cell;
+  for (int64_t i = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); i < n; i += wstride) {
+    const float2 p = __ldg(q + i);
+    const int qcx = cell_coord(p.x, m.x0, m.inv_cell, m.W);
+    const int qcy = cell_coord(p.y, m.y0, m.inv_cell, m.H);
+    const float fuzz = 2e-6f * (fabsf(p.x) + fabsf(p.y) + extent);
+    float best = INFINITY, bz = 0.f;
+    int bidx = 0x7fffffff;
+    int tie = 0;
+    for (int R = 1;; R *= 2) {
+      const int bx0 = max(qcx - R, 0), bx1 = min(qcx + R, m.W - 1);
+      const int by0 = max(qcy - R, 0), by1 = min(qcy + R, m.H - 1);
+      best = INFINITY; bidx = 0x7fffffff; tie = 0;
+      warp_for_each_in_cells(m, bx0, bx1, by0, by1, [&](bool valid, const float4& c) {
+        if (!valid) return;
+        const float dx = __fsub_rn(c.x, p.x), dy = __fsub_rn(c.y, p.y);
+        const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        const int ci = __float_as_int(c.w);
+        if (d2 < best) { best = d2; bidx = ci; bz = c.z; tie = 0; }
+        else if (d2 == best) { tie = 1; if (ci < bidx) { bidx = ci; bz = c.z; } }
+      });
+      // warp arg-min (d2, idx) with tie tracking
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        const float ob = __shfl_xor_sync(FULL, best, d);
+        const int oi = __shfl_xor_sync(FULL, bidx, d);
+        const float oz = __shfl_xor_sync(FULL, bz, d);
+        const int ot = __shfl_xor_sync(FULL, tie, d);
+        if (ob < best) { best = ob; bidx = oi; bz = oz; tie = ot; }
+        else if (ob == best && ob != INFINITY) {
+          tie = (oi != bidx) ? 1 : (tie | ot);
+          if (oi < bidx) { bidx = oi; bz = oz; }
+        }
+      }
+      const bool whole = bx0 == 0 && by0 == 0 && bx1 == m.W - 1 && by1 == m.H - 1;
+      if (whole) break;
+      // distance from the query to the nearest side of the searched block that has cells beyond it
+      float g = INFINITY;
+      if (bx0 > 0) g = fminf(g, p.x - (m.x0 + (float)bx0 * m.cell));
+      if (bx1 < m.W - 1) g = fminf(g, (m.x0 + (float)(bx1 + 1) * m.cell) - p.x);
+      if (by0 > 0) g = fminf(g, p.y - (m.y0 + (float)by0 * m.cell));
+      if (by1 < m.H - 1) g = fminf(g, (m.y0 + (float)(by1 + 1) * m.cell) - p.y);
+      g = g * 0.9999f - fuzz;
+      if (best < INFINITY && g > 0.f && best <= g * g) break;
+    }
+    if (lane == 0) {
+      if (z_out) z_out[i] = bz;
+      if (idx_out) idx_out[i] = best < INFINITY ? (int64_t)bidx : -1;
+      if (tie_out) tie_out[i] = (uint8_t)tie;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4 — edge evaluation
+// ------------------------------------------------------------------------------------------
+// One-sided Jacobi SVD of a real 3x3 (row-major), the algorithm Eigen::JacobiSVD runs for a
+// square matrix (trg.cpp:339): 2x2 real SVD steps over the pairs (1,0),(2,0),(2,1), left
+// rotations accumulated into U, negative diagonals flipped, columns sorted descending.
+struct Rot { float c, s; };
+__device__ __forceinline__ Rot rot_mul(Rot a, Rot b) { return {a.c * b.c - a.s * b.s, a.c * b.s + a.s * b.c}; }
+__device__ __forceinline__ void rot_plane(float* x, int incx, float* y, int incy, int n, Rot j) {
+  if (j.c == 1.f && j.s == 0.f) return;
+  for (int i = 0; i < n; ++i) {
+    const float xi = x[i * incx], yi = y[i * incy];
+    x[i * incx] = j.c * xi + j.s * yi;
+    y[i * incy] = -j.s * xi + j.c * yi;
+  }
+}
+__device__ __forceinline__ Rot make_jacobi(float x, float y, float z) {
+  const float deno = 2.f * fabsf(y);
+  if (deno < 1.17549435e-38f) return {1.f, 0.f};
+  const float tau = __fdiv_rn(x - z, deno);
+  const float w = __fsqrt_rn(tau * tau + 1.f);
+  const float t = tau > 0.f ? __fdiv_rn(1.f, tau + w) : __fdiv_rn(1.f, tau - w);
+  const float sign_t = t > 0.f ? 1.f : -1.f;
+  const float nn = __fdiv_rn(1.f, __fsqrt_rn(t * t + 1.f));
+  Rot r;
+  r.s = -sign_t * __fdiv_rn(y, fabsf(y)) * fabsf(t) * nn;
+  r.c = nn;
+  return r;
+}
+__device__ void jacobi_svd3(const float* A, float* U, float* sv) {
+  const float precision = 2.f * 1.1920929e-07f;
+  const float tiny = 1.17549435e-38f;
+  float scale = 0.f;
+  for (int i = 0; i < 9; ++i) scale = fmaxf(scale, fabsf(A[i]));
+  for (int i = 0; i < 9; ++i) U[i] = (i % 4 == 0) ? 1.f : 0.f;
+  if (!isfinite(scale)) { sv[0] = sv[1] = sv[2] = NAN; return; }
+  if (scale == 0.f) scale = 1.f;
+  float W[9];
+  for (int i = 0; i < 9; ++i) W[i] = __fdiv_rn(A[i], scale);
+  float maxDiag = fmaxf(fabsf(W[0]), fmaxf(fabsf(W[4]), fabsf(W[8])));
+  bool finished = false;
+  for (int guard = 0; !finished && guard < 1000; ++guard) {
+    finished = true;
+    for (int p = 1; p < 3; ++p)
+      for (int q = 0; q < p; ++q) {
+        const float thr = fmaxf(tiny, precision * maxDiag);
+        if (fabsf(W[p * 3 + q]) > thr || fabsf(W[q * 3 + p]) > thr) {
+          finished = false;
+          float mm[4] = {W[p * 3 + p], W[p * 3 + q], W[q * 3 + p], W[q * 3 + q]};
+          Rot rot1;
+          const float t = mm[0] + mm[3], d = mm[2] - mm[1];
+          if (fabsf(d) < tiny) { rot1.s = 0.f; rot1.c = 1.f; }
+          else {
+            const float u = __fdiv_rn(t, d);
+            const float tmp = __fsqrt_rn(1.f + u * u);
+            rot1.s = __fdiv_rn(1.f, tmp);
+            rot1.c = __fdiv_rn(u, tmp);
+          }
+          rot_plane(mm + 0, 1, mm + 2, 1, 2, rot1);
+          const Rot jr = make_jacobi(mm[0], mm[1], mm[3]);
+          const Rot jl = rot_mul(rot1, Rot{jr.c, -jr.s});
+          rot_plane(W + p * 3, 1, W + q * 3, 1, 3, jl);  // applyOnTheLeft(p,q,j_left)
+          rot_plane(U + p, 3, U + q, 3, 3, jl);          // U.applyOnTheRight(p,q,j_left^T)
+          rot_plane(W + p, 3, W + q, 3, 3, Rot{jr.c, -jr.s});  // applyOnTheRight(p,q,j_right)
+          maxDiag = fmaxf(maxDiag, fmaxf(fabsf(W[p * 3 + p]), fabsf(W[q * 3 + q])));
+        }
+      }
+  }
+  for (int i = 0; i < 3; ++i) {
+    const float a = W[i * 3 + i];
+    sv[i] = fabsf(a);
+    if (a < 0.f) for (int r = 0; r < 3; ++r) U[r * 3 + i] = -U[r * 3 + i];
+  }
+  for (int i = 0; i < 3; ++i) sv[i] *= scale;
+  for (int i = 0; i < 3; ++i) {
+    int pos = 0;
+    float best = sv[i];
+    for (int k = i + 1; k < 3; ++k) if (sv[k] > best) { best = sv[k]; pos = k - i; }
+    if (best == 0.f) break;
+    if (pos) {
+      pos += i;
+      float ts = sv[i]; sv[i] = sv[pos]; sv[pos] = ts;
+      for (int r = 0; r < 3; ++r) { float tu = U[r * 3 + i]; U[r * 3 + i] = U[r * 3 + pos]; U[r * 3 + pos] = tu; }
+    }
+  }
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+  return v;
+}
+
+__global__ void __launch_bounds__(kThreads) k_edge_eval(MapView m, const float* __restrict__ p1_xyz,
+                                                        const float2* __restrict__ p2_xy, int64_t n,
+                                                        float rs, float hthr, float cthr, int cap,
+                                                        uint8_t* __restrict__ stage_out,
+                                                        float* __restrict__ w_out,
+                                                        float* __restrict__ dist_out,
+                                                        int32_t* __restrict__ npts_out) {
+  extern __shared__ float zsm[];
+  float* zbuf = zsm + (threadIdx.x >> 5) * cap;
+  const int lane = threadIdx.x & 31;
+  const int64_t wstride = (int64_t)gridDim.x * kWarpsPerCta;
+  for (int64_t i = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); i < n; i += wstride) {
+    const float p1x = __ldg(p1_xyz + 3 * i), p1y = __ldg(p1_xyz + 3 * i + 1), p1z = __ldg(p1_xyz + 3 * i + 2);
+    const float2 p2 = __ldg(p2_xy + i);
+    // :276 dist = (node1 - node2).norm() ; :277 dir = (node2 - node1).normalized()
+    const float ax = __fsub_rn(p1x, p2.x), ay = __fsub_rn(p1y, p2.y);
+    const float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)));
+    const float ex = __fsub_rn(p2.x, p1x), ey = __fsub_rn(p2.y, p1y);
+    const float sq = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+    float dirx = ex, diry = ey;
+    if (sq > 0.f) {
+      const float s = __fsqrt_rn(sq);
+      dirx = __fdiv_rn(ex, s);
+      diry = __fdiv_rn(ey, s);
+    }
+    int stage = TRGB_EDGE_OK;
+    float weight = 0.f;
+    int npts = 0;
+    // :282-288 collision samples every robot_size/2 along the segment (float accumulator)
+    const float ds = 0.5f * rs;
+    for (float t = 0.f; t < dist; t = __fadd_rn(t, ds)) {
+      const float sx = __fadd_rn(p1x, __fmul_rn(t, dirx)), sy = __fadd_rn(p1y, __fmul_rn(t, diry));
+      if (warp_is_collision(m, sx, sy, rs, hthr, cthr, zbuf, cap, nullptr)) {
+        stage = TRGB_EDGE_COLLISION;
+        break;
+      }
+    }
+    if (stage == TRGB_EDGE_OK) {
+      // :291-297 ellipse with foci at the two nodes (circle when the nodes are close)
+      const float c = 0.5f * dist;
+      const float b = rs;
+      float a = b;
+      if (c >= b) a = __fsqrt_rn(__fadd_rn(__fmul_rn(c, c), __fmul_rn(b, b)));
+      const bool circle = (a == b);
+      const float cx = __fadd_rn(p1x, __fmul_rn(c, dirx)), cy = __fadd_rn(p1y, __fmul_rn(c, diry));
+      const float a2 = __fmul_rn(a, a), b2 = __fmul_rn(b, b);
+      const float rhs = __fmul_rn(__fmul_rn(a2, b), b);  // a*a*b*b, left to right
+      const float ndiry = -diry;
+      int nrange = 0;
+      double sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
+      warp_for_each_candidate(m, cx, cy, inflate(a, cx, cy), [&](bool valid, const float4& p) {
+        const float qx = __fsub_rn(p.x, cx), qy = __fsub_rn(p.y, cy);
+        const float d2 = __fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy));
+        const bool in_range = valid && d2 <= a2;  // kd_nearest_range2(center, a)
+        nrange += in_range;
+        // :312-316 p2d = R * (pt - center), R = [dir.x -dir.y; dir.y dir.x]
+        const float px = __fadd_rn(__fmul_rn(dirx, qx), __fmul_rn(ndiry, qy));
+        const float py = __fadd_rn(__fmul_rn(diry, qx), __fmul_rn(dirx, qy));
+        bool keep = in_range;
+        if (!circle)  // :320
+          keep = keep && (__fadd_rn(__fmul_rn(__fmul_rn(px, px), b2), __fmul_rn(__fmul_rn(py, py), a2)) < rhs);
+        if (keep) {
+          // covariance sums in double about the pivot z = p1.z: order-independent to ~1e-16,
+          // i.e. at least as close to the reference's float result as any float ordering
+          const double X = px, Y = py, Z = (double)p.z - (double)p1z;
+          npts += 1;
+          sx += X; sy += Y; sz += Z;
+          sxx += X * X; sxy += X * Y; sxz += X * Z; syy += Y * Y; syz += Y * Z; szz += Z * Z;
+        }
+      });
+      nrange = __reduce_add_sync(FULL, nrange);
+      npts = __reduce_add_sync(FULL, npts);
+      if (nrange == 0) stage = TRGB_EDGE_EMPTY;       // :305
+      else if (npts < 3) stage = TRGB_EDGE_FEWPTS;    // :327
+      else {
+        sx = warp_sum_d(sx); sy = warp_sum_d(sy); sz = warp_sum_d(sz);
+        sxx = warp_sum_d(sxx); sxy = warp_sum_d(sxy); sxz = warp_sum_d(sxz);
+        syy = warp_sum_d(syy); syz = warp_sum_d(syz); szz = warp_sum_d(szz);
+        // :337-338 cov = centered^T centered / (n-1)
+        const double nn = (double)npts, dn = (double)(npts - 1);
+        float cov[9];
+        cov[0] = (float)((sxx - sx * sx / nn) / dn);
+        cov[1] = cov[3] = (float)((sxy - sx * sy / nn) / dn);
+        cov[2] = cov[6] = (float)((sxz - sx * sz / nn) / dn);
+        cov[4] = (float)((syy - sy * sy / nn) / dn);
+        cov[5] = cov[7] = (float)((syz - sy * sz / nn) / dn);
+        cov[8] = (float)((szz - sz * sz / nn) / dn);
+        float U[9], sv[3];
+        jacobi_svd3(cov, U, sv);
+        // :340 matrixU().normalized(): Frobenius norm of the 3x3
+        float fro = 0.f;
+        for (int k = 0; k < 9; ++k) fro += U[k] * U[k];
+        float e20 = U[6], e21 = U[7];
+        if (fro > 0.f) {
+          const float nrm = __fsqrt_rn(fro);
+          e20 = __fdiv_rn(e20, nrm);
+          e21 = __fdiv_rn(e21, nrm);
+        }
+        const float hor = fabsf(e20), ver = fabsf(e21);  // :347-354
+        const float ratio = 0.8f;
+        weight = __fadd_rn(__fmul_rn(ratio, hor), __fmul_rn(__fsub_rn(1.f, ratio), ver));  // :360
+        if ((double)weight < 0.1) weight = 0.f;  // :361-363
+      }
+    }
+    if (lane == 0) {
+      stage_out[i] = (uint8_t)stage;
+      w_out[i] = weight;
+      dist_out[i] = dist;
+      if (npts_out) npts_out[i] = npts;
+    }
+  }
+}
+
+// per-warp shared z-buffer capacity for a radius-r cylinder on this map
+static int pick_cap(const trgb_map* m, float r) {
+  const double area = (double)m->view.W * m->view.H * (double)m->view.cell * m->view.cell;
+  const double density = (double)m->n / std::max(area, 1e-9);
+  const double side = 2.0 * r + m->view.cell;
+  double cand = 4.0 * density * side * side + 64.0;
+  int cap = 64;
+  while (cap < cand && cap < 4096) cap <<= 1;
+  return cap;
+}
+
+static int launch_cfg(const trgb_map* m, float r, int64_t n_items, int* grid, int* cap, size_t* smem,
+                      const void* kernel) {
+  *cap = pick_cap(m, r);
+  *smem = (size_t)kWarpsPerCta * (*cap) * sizeof(float);
+  if (*smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(smem)", __FILE__, __LINE__);
+  }
+  const int per_sm = *smem > 64 * 1024 ? 1 : (*smem > 24 * 1024 ? 2 : 8);
+  *grid = grid_for_warps(n_items, per_sm);
+  return TRGB_OK;
+}
+
+}  // namespace trgb
+
+using namespace trgb;
+
+// ---- tier 2 -------------------------------------------------------------------------------
+extern "C" int trgb_collision_launch(const trgb_map* m, const float* d_xy, int64_t n, float radius,
+                                     float height_thr, float ratio_thr, uint8_t* d_out) {
+  TRGB_ARG(m && d_xy && d_out, "null pointer");
+  TRGB_ARG(radius > 0.f, "radius must be > 0");
+  if (n <= 0) return TRGB_OK;
+  int grid, cap; size_t smem;
+  int rc = launch_cfg(m, radius, n, &grid, &cap, &smem, (const void*)k_collision);
+  if (rc) return rc;
+  ProfScope ps("k_collision", m->stream, 0.0);
+  k_collision<<<grid, kThreads, smem, m->stream>>>(m->view, reinterpret_cast<const float2*>(d_xy), n, radius,
+                                                   height_thr, ratio_thr, cap, d_out);
+  TRGB_CUDA(cudaGetLastError());
+  return TRGB_OK;
+}
+
+extern "C" int trgb_range_count_launch(const trgb_map* m, const float* d_xy, int64_t n, float radius,
+                                       int32_t* d_out) {
+  TRGB_ARG(m && d_xy && d_out, "null pointer");
+  TRGB_ARG(radius > 0.f, "radius must be > 0");
+  if (n <= 0) return TRGB_OK;
+  ProfScope ps("k_range_count", m->stream, 0.0);
+  k_range_count<<<grid_for_warps(n, 8), kThreads, 0, m->stream>>>(m->view, reinterpret_cast<const float2*>(d_xy),
+                                                                   n, radius, d_out);
+  TRGB_CUDA(cudaGetLastError());
+  return TRGB_OK;
+}
+
+extern "C" int trgb_sample_window_launch(const trgb_map* m, const float* d_node_xy,
+                                         const int32_t* d_first_draw, const float* d_draw_xy,
+                                         int64_t n_nodes, int window, float radius, float height_thr,
+                                         float ratio_thr, unsigned long long* d_mask) {
+  TRGB_ARG(m && d_node_xy && d_first_draw && d_draw_xy && d_mask, "null pointer");
+  TRGB_ARG(window >= 1 && window <= 256, "window must be in [1,256]");
+  TRGB_ARG(radius > 0.f, "radius must be > 0");
+  if (n_nodes <= 0) return TRGB_OK;
+  int grid, cap; size_t smem;
+  int rc = launch_cfg(m, radius, n_nodes * window, &grid, &cap, &smem, (const void*)k_sample_window);
+  if (rc) return rc;
+  ProfScope ps("k_sample_window", m->stream, 0.0);
+  k_sample_window<<<grid, kThreads, smem, m->stream>>>(
+      m->view, reinterpret_cast<const float2*>(d_node_xy), d_first_draw,
+      reinterpret_cast<const float2*>(d_draw_xy), n_nodes, window, radius, height_thr, ratio_thr, cap, d_mask);
+  TRGB_CUDA(cudaGetLastError());
+  return TRGB_OK;
+}
+
+extern "C" int trgb_nearest_z_launch(const trgb_map* m, const float* d_xy, int64_t n, float* d_z,
+                                     int64_t* d_idx, uint8_t* d_tie) {
+  TRGB_ARG(m && d_xy, "null pointer");
+  if (n <= 0) return TRGB_OK;
+  ProfScope ps("k_nearest_z", m->stream, 0.0);
+  k_nearest_z<<<grid_for_warps(n, 8), kThreads, 0, m->stream>>>(m->view, reinterpret_cast<const float2*>(d_xy), n,
+                                                                 d_z, d_idx, d_tie);
+  TRGB_CUDA(cudaGetLastError());
+  return TRGB_OK;
+}
+
+extern "C" int trgb_edge_eval_launch(const trgb_map* m, const float* d_p1_xyz, const float* d_p2_xy,
+                                     int64_t n, const TrgbEdgeParams* prm, uint8_t* d_stage,
+                                     float* d_weight, float* d_dist, int32_t* d_npts) {
+  TRGB_ARG(m && d_p1_xyz && d_p2_xy && prm && d_stage && d_weight && d_dist, "null pointer");
+  TRGB_ARG(prm->robot_size > 0.f, "robot_size must be > 0");
+  if (n <= 0) return TRGB_OK;
+  int grid, cap; size_t smem;
+  // the ellipse gather reaches sqrt((1.25*expand)^2 + r^2) but keeps nothing in shared memory;
+  // the shared buffer only serves the radius-robot_size collision samples
+  int rc = launch_cfg(m, prm->robot_size, n, &grid, &cap, &smem, (const void*)k_edge_eval);
+  if (rc) return rc;
+  ProfScope ps("k_edge_eval", m->stream, 0.0);
+  k_edge_eval<<<grid, kThreads, smem, m->stream>>>(m->view, d_p1_xyz, reinterpret_cast<const float2*>(d_p2_xy), n,
+                                                   prm->robot_size, prm->height_threshold,
+                                                   prm->collision_threshold, cap, d_stage, d_weight, d_dist, d_npts);
+  TRGB_CUDA(cudaGetLastError());
+  return TRGB_OK;
+}
+
+// ---- tier 1: host buffers ------------------------------------------------------------------
+namespace {
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1) == cudaSuccess ? 0 : -1; }
+  template <class T> T* as() { return static_cast<T*>(p); }
+};
+#define TRGB_ALLOC(buf, bytes) \
+  if ((buf).alloc(bytes)) return cuda_fail(cudaErrorMemoryAllocation, "cudaMalloc(staging)", __FILE__, __LINE__)
+}  // namespace
+
+extern "C" int trgb_collision_batch(trgb_map* m, const float* xy, int64_t n, float radius, float height_thr,
+                                    float ratio_thr, uint8_t* out) {
+  TRGB_ARG(m && (n == 0 || (xy && out)), "null pointer");
+  if (n <= 0) return TRGB_OK;
+  DevBuf dq, dout;
+  TRGB_ALLOC(dq, n * 2 * sizeof(float));
+  TRGB_ALLOC(dout, n);
+  TRGB_CUDA(cudaMemcpyAsync(dq.p, xy, n * 2 * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+  int rc = trgb_collision_launch(m, dq.as<float>(), n, radius, height_thr, ratio_thr, dout.as<uint8_t>());
+  if (rc) return rc;
+  TRGB_CUDA(cudaMemcpyAsync(out, dout.p, n, cudaMemcpyDeviceToHost, m->stream));
+  TRGB_CUDA(cudaStreamSynchronize(m->stream));
+  return TRGB_OK;
+}
+
+extern "C" int trgb_range_count_batch(trgb_map* m, const float* xy, int64_t n, float radius, int32_t* out) {
+  TRGB_ARG(m && (n == 0 || (xy && out)), "null pointer");
+  if (n <= 0) return TRGB_OK;
+  DevBuf dq, dout;
+  TRGB_ALLOC(dq, n * 2 * sizeof(float));
+  TRGB_ALLOC(dout, n * sizeof(int32_t));
+  TRGB_CUDA(cudaMemcpyAsync(dq.p, xy, n * 2 * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+  int rc = trgb_range_count_launch(m, dq.as<float>(), n, radius, dout.as<int32_t>());
+  if (rc) return rc;
+  TRGB_CUDA(cudaMemcpyAsync(out, dout.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
+  TRGB_CUDA(cudaStreamSynchronize(m->stream));
+  return TRGB_OK;
+}
+
+extern "C" int trgb_nearest_z_batch(trgb_map* m, const float* xy, int64_t n, float* z, int64_t* idx, uint8_t* tie) {
+  TRGB_ARG(m && (n == 0 || xy), "null pointer");
+  if (n <= 0) return TRGB_OK;
+  DevBuf dq, dz, di, dt;
+  TRGB_ALLOC(dq, n * 2 * sizeof(float));
+  TRGB_ALLOC(dz, n * sizeof(float));
+  TRGB_ALLOC(di, n * sizeof(int64_t));
+  TRGB_ALLOC(dt, n);
+  TRGB_CUDA(cudaMemcpyAsync(dq.p, xy, n * 2 * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+  int rc = trgb_nearest_z_launch(m, dq.as<float>(), n, dz.as<float>(), di.as<int64_t>(), dt.as<uint8_t>());
+  if (rc) return rc;
+  if (z) TRGB_CUDA(cudaMemcpyAsync(z, dz.p, n * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+  if (idx) TRGB_CUDA(cudaMemcpyAsync(idx, di.p, n * sizeof(int64_t), cudaMemcpyDeviceToHost, m->stream));
+  if (tie) TRGB_CUDA(cudaMemcpyAsync(tie, dt.p, n, cudaMemcpyDeviceToHost, m->stream));
+  TRGB_CUDA(cudaStreamSynchronize(m->stream));
+  return TRGB_OK;
+}
+
+extern "C" int trgb_edge_eval_batch(trgb_map* m, const float* p1_xyz, const float* p2_xyz, int64_t n,
+                                    const TrgbEdgeParams* prm, uint8_t* stage, float* weight, float* dist,
+                                    int32_t* npts) {
+  TRGB_ARG(m && prm && (n == 0 || (p1_xyz && p2_xyz && stage && weight && dist)), "null pointer");
+  if (n <= 0) return TRGB_OK;
+  std::vector<float> p2xy((size_t)n * 2);
+  for (int64_t i = 0; i < n; ++i) { p2xy[2 * i] = p2_xyz[3 * i]; p2xy[2 * i + 1] = p2_xyz[3 * i + 1]; }
+  DevBuf d1, d2, ds, dw, dd, dn;
+  TRGB_ALLOC(d1, n * 3 * sizeof(float));
+  TRGB_ALLOC(d2, n * 2 * sizeof(float));
+  TRGB_ALLOC(ds, n);
+  TRGB_ALLOC(dw, n * sizeof(float));
+  TRGB_ALLOC(dd, n * sizeof(float));
+  TRGB_ALLOC(dn, n * sizeof(int32_t));
+  TRGB_CUDA(cudaMemcpyAsync(d1.p, p1_xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+  TRGB_CUDA(cudaMemcpyAsync(d2.p, p2xy.data(), n * 2 * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+  int rc = trgb_edge_eval_launch(m, d1.as<float>(), d2.as<float>(), n, prm, ds.as<uint8_t>(), dw.as<float>(),
+                                 dd.as<float>(), dn.as<int32_t>());
+  if (rc) return rc;
+  TRGB_CUDA(cudaMemcpyAsync(stage, ds.p, n, cudaMemcpyDeviceToHost, m->stream));
+  TRGB_CUDA(cudaMemcpyAsync(weight, dw.p, n * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+  TRGB_CUDA(cudaMemcpyAsync(dist, dd.p, n * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+  if (npts) TRGB_CUDA(cudaMemcpyAsync(npts, dn.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
+  TRGB_CUDA(cudaStreamSynchronize(m->stream));
+  // host-side slope gate (trg.cpp:269-274): glibc atan2f, float overloads
+  const float max_slope = atan2f(prm->height_threshold, prm->robot_size);
+  for (int64_t i = 0; i < n; ++i) {
+    const float dx = p1_xyz[3 * i] - p2_xyz[3 * i], dy = p1_xyz[3 * i + 1] - p2_xyz[3 * i + 1];
+    const float nrm = sqrtf(dx * dx + dy * dy);
+    const float slope = atan2f(fabsf(p1_xyz[3 * i + 2] - p2_xyz[3 * i + 2]), nrm);
+    if (slope > max_slope) {
+      stage[i] = TRGB_EDGE_SLOPE;
+      weight[i] = 0.f;
+      if (npts) npts[i] = 0;
+    }
+  }
+  return TRGB_OK;
+}

@@ -1,0 +1,305 @@
+// Host-side index over graph nodes. Replaces the reference's `kdtree* node_tree`
+// (trg.h:106) with two cooperating structures:
+//
+//   NodeGrid     uniform hash grid -> exact nearest / in-range sets in O(1) expected time,
+//                using the same float arithmetic as kdtree.c (dist^2 = fl(fl(dx*dx)+fl(dy*dy)),
+//                strict `<` for nearest, inclusive `<=` for range);
+//   OrderTree2D  an insertion-order 2-D tree kept ONLY for the order-dependent semantics the
+//                reference leaks through its kd-tree: which of several exactly
+//                equidistant nodes kd_nearest2 returns, and the order in which
+//                kd_nearest_range2 results are iterated (head of list = last node visited;
+//                kdtree.c:270-301, 759-777). It is built lazily from the insertion sequence.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <limits>
+#include <vector>
+
+namespace trg_b200 {
+
+class OrderTree2D {
+ public:
+  void clear() {
+    x_.clear(); y_.clear(); lo_.clear(); hi_.clear(); axis_.clear(); payload_.clear();
+    have_box_ = false;
+  }
+  size_t size() const { return x_.size(); }
+  void reserve(size_t n) {
+    x_.reserve(n); y_.reserve(n); lo_.reserve(n); hi_.reserve(n); axis_.reserve(n); payload_.reserve(n);
+  }
+
+  // descend from the root: smaller coordinate on the split axis goes to the low child, ties and
+  // larger go to the high child; the split axis alternates x, y with depth (kdtree.c:167-194)
+  void insert(float x, float y, int payload) {
+    const int self = static_cast<int>(x_.size());
+    uint8_t axis = 0;
+    if (self > 0) {
+      int at = 0;
+      while (true) {
+        const bool low = axis_[at] ? (y < y_[at]) : (x < x_[at]);
+        int& slot = low ? lo_[at] : hi_[at];
+        if (slot < 0) {
+          slot = self;
+          axis = axis_[at] ^ 1;
+          break;
+        }
+        at = slot;
+      }
+    }
+    x_.push_back(x); y_.push_back(y); lo_.push_back(-1); hi_.push_back(-1);
+    axis_.push_back(axis); payload_.push_back(payload);
+    if (!have_box_) {
+      bmin_[0] = bmax_[0] = x; bmin_[1] = bmax_[1] = y; have_box_ = true;
+    } else {
+      bmin_[0] = std::fmin(bmin_[0], x); bmax_[0] = std::fmax(bmax_[0], x);
+      bmin_[1] = std::fmin(bmin_[1], y); bmax_[1] = std::fmax(bmax_[1], y);
+    }
+  }
+
+  // In-range payloads in the order the reference's result iterator yields them: the traversal
+  // is pre-order, query side first, far side only if |delta| < r; results are prepended, so
+  // the iteration order is the reverse of the visit order.
+  void range(float qx, float qy, float r, std::vector<int>& out) const {
+    out.clear();
+    if (x_.empty()) return;
+    const float r2 = r * r;
+    walk_.clear();
+    walk_.push_back({0, 0.f, false});
+    while (!walk_.empty()) {
+      Step s = walk_.back();
+      walk_.pop_back();
+      if (s.second_half) {
+        if (std::fabs(s.delta) < r) {
+          const int far = s.delta <= 0.0f ? hi_[s.node] : lo_[s.node];
+          if (far >= 0) walk_.push_back({far, 0.f, false});
+        }
+        continue;
+      }
+      const int n = s.node;
+      const float dx = x_[n] - qx, dy = y_[n] - qy;
+      float d2 = 0.f;
+      d2 += dx * dx;
+      d2 += dy * dy;
+      if (d2 <= r2) out.push_back(payload_[n]);
+      const float delta = axis_[n] ? (qy - y_[n]) : (qx - x_[n]);
+      walk_.push_back({n, delta, true});
+      const int near = delta <= 0.0f ? lo_[n] : hi_[n];
+      if (near >= 0) walk_.push_back({near, 0.f, false});
+    }
+    for (size_t a = 0, b = out.size(); a + 1 < b; ++a, --b) std::swap(out[a], out[b - 1]);
+  }
+
+  // kd_nearest semantics (kdtree.c:303-417): best starts at the root; visit nearer subtree,
+  // then the node (strict <), then the farther subtree if its bounding box can still win.
+  int nearest(float qx, float qy) const {
+    if (x_.empty()) return -1;
+    float mn[2] = {bmin_[0], bmin_[1]}, mx[2] = {bmax_[0], bmax_[1]};
+    const float q[2] = {qx, qy};
+    int best = 0;
+    float best_d2 = 0.f;
+    best_d2 += (x_[0] - qx) * (x_[0] - qx);
+    best_d2 += (y_[0] - qy) * (y_[0] - qy);
+    frames_.clear();
+    frames_.push_back({0, 0, 0.f, false});
+    while (!frames_.empty()) {
+      Frame& f = frames_.back();
+      const int n = f.node;
+      const int ax = axis_[n];
+      const float split = ax ? y_[n] : x_[n];
+      if (f.stage == 0) {
+        f.low_side = (q[ax] - split) <= 0.f;
+        f.stage = 1;
+        const int near = f.low_side ? lo_[n] : hi_[n];
+        if (near >= 0) {
+          float* edge = f.low_side ? &mx[ax] : &mn[ax];
+          f.saved = *edge;
+          *edge = split;
+          frames_.push_back({near, 0, 0.f, false});
+        }
+        continue;
+      }
+      if (f.stage == 1) {
+        const int near = f.low_side ? lo_[n] : hi_[n];
+        if (near >= 0) *(f.low_side ? &mx[ax] : &mn[ax]) = f.saved;
+        float d2 = 0.f;
+        d2 += (x_[n] - qx) * (x_[n] - qx);
+        d2 += (y_[n] - qy) * (y_[n] - qy);
+        if (d2 < best_d2) {
+          best = n;
+          best_d2 = d2;
+        }
+        f.stage = 2;
+        const int far = f.low_side ? hi_[n] : lo_[n];
+        if (far >= 0) {
+          float* edge = f.low_side ? &mn[ax] : &mx[ax];
+          f.saved = *edge;
+          *edge = split;
+          float bd = 0.f;
+          for (int k = 0; k < 2; ++k) {
+            if (q[k] < mn[k]) bd += (mn[k] - q[k]) * (mn[k] - q[k]);
+            else if (q[k] > mx[k]) bd += (mx[k] - q[k]) * (mx[k] - q[k]);
+          }
+          if (bd < best_d2) {
+            frames_.push_back({far, 0, 0.f, false});
+            continue;
+          }
+          *edge = f.saved;  // pruned: undo the slice right away
+          f.stage = 3;
+        } else {
+          f.stage = 3;
+        }
+        continue;
+      }
+      if (f.stage == 2) {  // back from the far subtree
+        *(f.low_side ? &mn[ax] : &mx[ax]) = f.saved;
+      }
+      frames_.pop_back();
+    }
+    return payload_[best];
+  }
+
+  // raw arrays (device upload for batched goal/start snapping)
+  const std::vector<int>& low() const { return lo_; }
+  const std::vector<int>& high() const { return hi_; }
+  const std::vector<uint8_t>& axis() const { return axis_; }
+  const std::vector<int>& payload() const { return payload_; }
+
+ private:
+  struct Step { int node; float delta; bool second_half; };
+  struct Frame { int node; int stage; float saved; bool low_side; };
+  std::vector<float> x_, y_;
+  std::vector<int> lo_, hi_;
+  std::vector<uint8_t> axis_;
+  std::vector<int> payload_;
+  float bmin_[2] = {0, 0}, bmax_[2] = {0, 0};
+  bool have_box_ = false;
+  mutable std::vector<Step> walk_;
+  mutable std::vector<Frame> frames_;
+};
+
+// Uniform grid over node positions; intrusive singly linked lists per cell.
+class NodeGrid {
+ public:
+  void configure(float x0, float y0, float x1, float y1, float cell) {
+    cell_ = cell;
+    inv_ = 1.0f / cell;
+    x0_ = x0 - 2.f * cell;
+    y0_ = y0 - 2.f * cell;
+    w_ = static_cast<int>(std::floor((x1 - x0_) * inv_)) + 4;
+    h_ = static_cast<int>(std::floor((y1 - y0_) * inv_)) + 4;
+    head_.assign(static_cast<size_t>(w_) * h_, -1);
+    next_.clear(); px_.clear(); py_.clear();
+  }
+  bool configured() const { return w_ > 0; }
+  void clear() {
+    std::fill(head_.begin(), head_.end(), -1);
+    next_.clear(); px_.clear(); py_.clear();
+  }
+  size_t size() const { return px_.size(); }
+  void reserve(size_t n) { next_.reserve(n); px_.reserve(n); py_.reserve(n); }
+
+  // entries are numbered in insertion order (0, 1, 2, ...)
+  int insert(float x, float y) {
+    const int id = static_cast<int>(px_.size());
+    const size_t c = static_cast<size_t>(cy(y)) * w_ + cx(x);
+    px_.push_back(x); py_.push_back(y);
+    next_.push_back(head_[c]);
+    head_[c] = id;
+    return id;
+  }
+
+  struct Nearest { int entry; float d2; bool tie; };
+  // exact global nearest (float dist^2, strict <). `tie` = some other entry has the identical
+  // dist^2 — the caller then asks the OrderTree2D which one the reference would return.
+  Nearest nearest(float qx, float qy) const {
+    Nearest best{-1, std::numeric_limits<float>::infinity(), false};
+    if (px_.empty()) return best;
+    const int qcx = cx(qx), qcy = cy(qy);
+    const int maxr = std::max(w_, h_);
+    const float fuzz = 4e-6f * (std::fabs(qx) + std::fabs(qy) + cell_ * static_cast<float>(w_ + h_));
+    for (int R = 1; R <= maxr; ++R) {
+      // scan the ring of cells at Chebyshev distance R-1.. (first pass scans the 3x3 block)
+      const int lo = (R == 1) ? 0 : R;
+      for (int ring = lo; ring <= R; ++ring) scan_ring(qcx, qcy, ring, qx, qy, best);
+      const float g = static_cast<float>(R) * cell_ * 0.9999f - fuzz;
+      // cells outside the scanned block are at least R whole cells away from the query's cell
+      if (best.entry >= 0 && g > 0.f && best.d2 <= g * g) break;
+      if (qcx - R <= 0 && qcy - R <= 0 && qcx + R >= w_ - 1 && qcy + R >= h_ - 1) break;
+    }
+    return best;
+  }
+
+  // all entries with fl(dx^2+dy^2) <= fl(r^2), unordered
+  template <class F>
+  void for_each_in_range(float qx, float qy, float r, F&& f) const {
+    if (px_.empty()) return;
+    const float r2 = r * r;
+    const float rr = r * 1.0001f + 1e-5f + 4e-6f * (std::fabs(qx) + std::fabs(qy));
+    const int cx0 = cx(qx - rr), cx1 = cx(qx + rr), cy0 = cy(qy - rr), cy1 = cy(qy + rr);
+    for (int yy = cy0; yy <= cy1; ++yy)
+      for (int xx = cx0; xx <= cx1; ++xx)
+        for (int e = head_[static_cast<size_t>(yy) * w_ + xx]; e >= 0; e = next_[e]) {
+          const float dx = px_[e] - qx, dy = py_[e] - qy;
+          float d2 = 0.f;
+          d2 += dx * dx;
+          d2 += dy * dy;
+          if (d2 <= r2) f(e);
+        }
+  }
+  int count_in_range(float qx, float qy, float r) const {
+    int c = 0;
+    for_each_in_range(qx, qy, r, [&](int) { ++c; });
+    return c;
+  }
+
+ private:
+  int cx(float x) const {
+    const float f = std::floor((x - x0_) * inv_);
+    if (!(f > 0.f)) return 0;
+    if (f >= static_cast<float>(w_)) return w_ - 1;
+    return static_cast<int>(f);
+  }
+  int cy(float y) const {
+    const float f = std::floor((y - y0_) * inv_);
+    if (!(f > 0.f)) return 0;
+    if (f >= static_cast<float>(h_)) return h_ - 1;
+    return static_cast<int>(f);
+  }
+  void scan_cell(int xx, int yy, float qx, float qy, Nearest& best) const {
+    if (xx < 0 || yy < 0 || xx >= w_ || yy >= h_) return;
+    for (int e = head_[static_cast<size_t>(yy) * w_ + xx]; e >= 0; e = next_[e]) {
+      const float dx = px_[e] - qx, dy = py_[e] - qy;
+      float d2 = 0.f;
+      d2 += dx * dx;
+      d2 += dy * dy;
+      if (d2 < best.d2) {
+        best.d2 = d2;
+        best.entry = e;
+        best.tie = false;
+      } else if (d2 == best.d2 && e != best.entry) {
+        best.tie = true;
+      }
+    }
+  }
+  void scan_ring(int qcx, int qcy, int ring, float qx, float qy, Nearest& best) const {
+    if (ring == 0) {
+      scan_cell(qcx, qcy, qx, qy, best);
+      return;
+    }
+    for (int xx = qcx - ring; xx <= qcx + ring; ++xx) {
+      scan_cell(xx, qcy - ring, qx, qy, best);
+      scan_cell(xx, qcy + ring, qx, qy, best);
+    }
+    for (int yy = qcy - ring + 1; yy <= qcy + ring - 1; ++yy) {
+      scan_cell(qcx - ring, yy, qx, qy, best);
+      scan_cell(qcx + ring, yy, qx, qy, best);
+    }
+  }
+
+  float cell_ = 1.f, inv_ = 1.f, x0_ = 0.f, y0_ = 0.f;
+  int w_ = 0, h_ = 0;
+  std::vector<int> head_, next_;
+  std::vector<float> px_, py_;
+};
+
+}  // namespace trg_b200

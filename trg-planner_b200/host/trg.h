@@ -1,0 +1,234 @@
+// TRG — traversal risk graph, B200-native drop-in for the reference class
+//   cpp/trg_planner/core/trg_planner/include/graph/trg.h:18-147.
+//
+// The public interface (nested types with their field names, the 9-argument constructor and
+// the 24 public methods) is source-compatible with the reference, so TRGPlanner
+// (planner.cpp:23-31,47,187-190,198,205,212-213,222,263-292), the pybind module
+// (trg_planner_pybind.cpp:19-78) and the ROS nodes compile against it unchanged. What changed
+// is everything behind it: the two kd-trees per graph (trg.h:106,110) are gone — the map lives
+// in HBM as a cell index (include/trgb_kernels.h) and graph construction runs as a
+// wavefront scheduler that batches the pure-function work (collision tests, nearest-z,
+// edge PCA) of one BFS generation into a few kernel launches while committing decisions in
+// the reference's exact sequential order.
+//
+// Additions to the reference API are marked [+]. There is no CPU fallback: methods that need
+// the device throw std::runtime_error when no usable GPU / kernel library is present.
+#ifndef TRG_PLANNER_B200_HOST_TRG_H_
+#define TRG_PLANNER_B200_HOST_TRG_H_
+
+#include <cstdint>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <random>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "node_index.h"
+#include "trg_types.h"
+
+#define EPS 1e-6
+
+struct trgb_map;
+struct trgb_graph;
+
+namespace trg_b200 {
+class DeviceSession;
+class Expander;
+}  // namespace trg_b200
+
+class TRG {
+ public:
+  struct Edge {
+    Edge(int dst_id, float weight, float dist) : dst_id_(dst_id), weight_(weight), dist_(dist) {}
+    int   dst_id_;
+    float weight_;
+    float dist_;
+  };
+
+  enum struct NodeState {
+    Valid    = 0,
+    Invalid  = -1,
+    Frontier = 1,
+  };
+
+  struct Node {
+    Node(int id, Eigen::Vector2f& pos2d, float z, NodeState state)
+        : id_(id), pos_(Eigen::Vector3f(pos2d.x(), pos2d.y(), z)), state_(state) {}
+    int                id_;
+    Eigen::Vector3f    pos_;
+    NodeState          state_;
+    std::vector<Edge*> edges_;
+  };
+
+  struct OptimizeNode {
+    OptimizeNode(int i, float f, float g) : id_(i), f_(f), g_(g) {}
+    int           id_;
+    OptimizeNode* parent_;
+    float         f_;
+    float         g_;
+  };
+
+ public:
+  TRG(bool  isVerbose,
+      float expand_dist,
+      float robot_size,
+      int   sample_num,
+      float height_threshold,
+      float collision_threshold,
+      float update_collision_threshold,
+      float safety_factor,
+      float goal_tolerance);
+  virtual ~TRG();
+
+  void initGraph(bool isPreMap, Eigen::Vector3f start3d = Eigen::Vector3f::Zero());
+  void loadPrebuiltGraph(const std::string& filepath);
+  void saveGraph(const std::string& filepath);
+
+  void setGlobalMap(PointCloudPtr& map);
+  void setLocalMap(Eigen::Vector2f start2d, PointCloudPtr& map);
+  void setLocalGraph(bool useMutex = false);
+
+  bool addNode(int node_id, Eigen::Vector2f& node_pos, NodeState state, std::string type);
+  void wireEdge(Node* node1, Node* node2, std::string type);
+
+  void expandGraph(int node_id, std::string type);
+  void cleanGraph(bool updateLocal = true);
+  void updateGraph();
+
+  void setGoal(Eigen::Vector3f& goal);
+  bool checkReadched(Eigen::Vector2f& pos2d);
+  bool checkReplan(Eigen::Vector2f& pos2d, std::vector<Eigen::Vector3f>& path);
+
+  bool planSafePath(Eigen::Vector2f&              start2d,
+                    Eigen::Vector3f&              goal_pose,
+                    std::vector<Eigen::Vector3f>& out_path,
+                    float&                        direct_dist,
+                    float&                        path_length,
+                    float&                        avg_risk);
+  void refinePath(std::vector<Eigen::Vector3f>& in_path, std::vector<Eigen::Vector3f>& out_path);
+
+  void resetGraph(std::string type);
+  void resetMap(std::string type);
+
+  bool isCollision(Eigen::Vector2f& pos2d, std::string type, float threshold = 0.1);
+  bool isFrontier(Eigen::Vector2f& pos2d);
+
+  std::unordered_map<int, Node*> getGraph(std::string type = "global");
+  std::unordered_map<int, Node*> getGraphCopy(std::string type = "global");
+  void                           lockGraph();
+  void                           unlockGraph();
+
+  // ---- [+] additions --------------------------------------------------------------------
+  // Reseed the sampling stream (the reference seeds gen_ from std::random_device, trg.cpp:20,
+  // and is therefore not reproducible). Also drops the look-ahead buffer of generated draws.
+  void reseed(uint32_t seed);
+  // Raw-pointer map ingest: n records of `stride_floats` floats (3 = xyz, 4 = pcl::PointXYZ).
+  // `device` != 0 means `xyz` already lives in HBM (bench "inputs resident" path).
+  void setGlobalMapRaw(const float* xyz, int64_t n, int stride_floats, bool device = false);
+  void setLocalMapRaw(Eigen::Vector2f start2d, const float* xyz, int64_t n, int stride_floats);
+  // Batched planSafePath: queries rows (sx, sy, gx, gy, gz); one GPU launch sequence for all.
+  struct PathBatch {
+    std::vector<uint8_t> found, goal_known;
+    std::vector<float>   cost, path_length, avg_risk, direct_dist;
+    std::vector<int64_t> offsets;   // n+1
+    std::vector<int32_t> node_ids;  // concatenated start..goal id sequences
+  };
+  void planSafePathBatch(const float* queries, int64_t n, PathBatch& out);
+  // Pure batched evaluations (kernel-level parity / benchmarking)
+  void isCollisionBatch(const float* xy, int64_t n, const std::string& type, float threshold,
+                        uint8_t* out);
+  // wall-clock seconds of the last call at the reference's timer sites (planner.cpp:185-270)
+  double lastSeconds(const std::string& what) const;
+  int64_t stat(const std::string& what) const;
+  trgb_map* deviceMap(const std::string& type);
+  const std::vector<int32_t>& lastPathIds() const { return last_path_ids_; }
+  bool goalKnown() const { return goal_.isKnown; }
+
+ protected:
+  struct trgStruct {
+    explicit trgStruct(std::string type) : type(type), node_id(0) {}
+    std::string type;
+
+    std::unordered_map<int, Node*> nodes;
+    int                            node_id;
+    Eigen::Vector2f                root_pos = Eigen::Vector2f::Zero();
+    PointCloudPtr                  cloud_map = nullptr;
+
+    // replaces `kdtree* node_tree` (trg.h:106): insertion sequence + grid + lazy order tree
+    std::vector<Node*>      node_seq;
+    trg_b200::NodeGrid      node_grid;
+    trg_b200::OrderTree2D   node_tree;
+    size_t                  tree_built = 0;  // prefix of node_seq already in node_tree
+    // replaces `kdtree* map_tree` (trg.h:110): device cell index
+    trgb_map*               map_index = nullptr;
+    int64_t                 map_points = 0;
+    float                   bbox[4] = {0, 0, 0, 0};
+  };
+  trgStruct prebuilt_trg_ = trgStruct("prebuilt");
+  trgStruct global_trg_   = trgStruct("global");
+  trgStruct local_trg_    = trgStruct("local");
+
+  std::unordered_map<std::string, trgStruct*> trgMap_ = {{"prebuilt", &prebuilt_trg_},
+                                                         {"global", &global_trg_},
+                                                         {"local", &local_trg_}};
+
+  struct goalStruct {
+    Eigen::Vector3f pose3d;
+    Eigen::Vector2f pose2d;
+    Node*           node    = nullptr;
+    bool            isKnown = false;
+  } goal_;
+
+  std::random_device                    rd_;
+  std::mt19937                          gen_;
+  std::uniform_real_distribution<float> distr_;
+
+  struct Param {
+    bool  isVerbose                  = true;
+    float expand_dist                = 0.5;
+    float robot_size                 = 0.5;
+    int   sample_num                 = 20;
+    float height_threshold           = 0.5;
+    float collision_threshold        = 0.5;
+    float update_collision_threshold = 0.5;
+    float safety_factor              = 3.0;
+    float goal_tolerance             = 0.2;
+  } param_;
+
+  struct Mutex {
+    std::mutex graph;
+  } mtx;
+
+ private:
+  friend class trg_b200::Expander;
+  // buffered view of (gen_, distr_): draw k of the stream, generated on demand, consumed in order
+  float nextUniform();
+  void  ensureDraws(size_t upto);
+  std::vector<float> draw_u_;          // u_k for k >= draw_base_
+  std::vector<float> draw_cx_, draw_cy_;  // expand_dist*cosf(angle_k), expand_dist*sinf(angle_k)
+  size_t draw_base_ = 0;               // stream index of draw_u_[0]
+  size_t draw_next_ = 0;               // next unconsumed stream index
+
+  void nodeIndexInsert(trgStruct& g, Node* n);
+  void nodeIndexReset(trgStruct& g);
+  void ensureTree(trgStruct& g);
+  Node* nearestNode(trgStruct& g, float x, float y);
+  void rangeNodesOrdered(trgStruct& g, float x, float y, float r, std::vector<Node*>& out);
+  void buildMapIndex(trgStruct& g, const float* xyz, int64_t n, int stride, bool device);
+  void invalidateDeviceGraph();
+  void ensureDeviceGraph();
+  Node* newNode(int id, Eigen::Vector2f& p, float z, NodeState s);
+  Edge* newEdge(int dst, float w, float d);
+
+  std::unique_ptr<trg_b200::DeviceSession> dev_;
+  trgb_graph* dev_graph_ = nullptr;
+  std::deque<Node> node_pool_;
+  std::deque<Edge> edge_pool_;
+  std::unordered_map<std::string, double>  secs_;
+  std::unordered_map<std::string, int64_t> stat_;
+  std::vector<int32_t> last_path_ids_;
+};
+
+#endif  // TRG_PLANNER_B200_HOST_TRG_H_
