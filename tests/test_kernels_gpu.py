@@ -1,0 +1,183 @@
+"""-m gpu: kernel-level parity of the CUDA path (through the tier-1 C ABI of
+include/trgb_kernels.h) against the CPU oracle on the same seeded inputs.
+Bit-exact for sets / booleans / indices; edge weights within 1e-5 relative (north_star), with the
+ill-conditioned classification of SURVEY.md A.4."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K(pkg, built):
+    from trg_planner_b200 import kernels
+    if kernels.device_count() < 1:
+        pytest.fail("no CUDA device: the product has no CPU fallback")
+    return kernels
+
+
+def _queries(pts, n, seed, margin=0.5):
+    rng = np.random.default_rng(seed)
+    lo = pts[:, :2].min(0) - margin
+    hi = pts[:, :2].max(0) + margin
+    return rng.uniform(lo, hi, size=(n, 2)).astype(np.float32)
+
+
+@pytest.mark.parametrize("which,prm", [("mountain", "MOUNTAIN"), ("indoor", "INDOOR")])
+def test_collision_and_count_parity(pkg, K, which, prm, small_mountain, small_indoor):
+    pts = small_mountain if which == "mountain" else small_indoor
+    P = getattr(pkg, prm)
+    o = pkg.oracle(P)
+    o.set_global_map(pts)
+    dm = K.DeviceMap(pts, P.robot_size)
+    q = _queries(pts, 200_000, 11)
+    for r in (0.15, 0.3, 0.61):
+        np.testing.assert_array_equal(dm.range_count(q[:50_000], r), o.range_count(q[:50_000], r))
+    got = dm.collision(q, P.robot_size, P.height_threshold, P.collision_threshold)
+    want = o.is_collision(q, P.collision_threshold)
+    assert got.shape == want.shape
+    np.testing.assert_array_equal(got, want)
+    assert 0 < want.mean() < 1  # both outcomes exercised
+
+
+def test_collision_cell_size_independent(pkg, K, small_mountain):
+    P = pkg.MOUNTAIN
+    q = _queries(small_mountain, 50_000, 12)
+    ref = None
+    for cell in (0.1, 0.3, 0.45, 1.0):
+        dm = K.DeviceMap(small_mountain, cell)
+        got = dm.collision(q, P.robot_size, P.height_threshold, P.collision_threshold)
+        if ref is None:
+            ref = got
+        np.testing.assert_array_equal(got, ref)
+
+
+def test_collision_large_radius_overflow_path(pkg, K, small_mountain):
+    """radius 2.4 m on a 0.1 m lattice => ~1800 points per cylinder (shared buffer overflow path)."""
+    import dataclasses
+    P = dataclasses.replace(pkg.MOUNTAIN, robot_size=2.4)
+    o = pkg.oracle(P)
+    o.set_global_map(small_mountain)
+    dm = K.DeviceMap(small_mountain, 0.3)
+    q = _queries(small_mountain, 3_000, 13)
+    np.testing.assert_array_equal(dm.collision(q, 2.4, P.height_threshold, P.collision_threshold),
+                                  o.is_collision(q, P.collision_threshold))
+    # force the tiny-buffer path too: 4-point cells, many points
+    dm2 = K.DeviceMap(small_mountain, 5.0)
+    np.testing.assert_array_equal(dm2.collision(q, 2.4, P.height_threshold, P.collision_threshold),
+                                  o.is_collision(q, P.collision_threshold))
+
+
+def test_nearest_z_parity(pkg, K, small_mountain, small_indoor):
+    for pts, P in ((small_mountain, pkg.MOUNTAIN), (small_indoor, pkg.INDOOR)):
+        o = pkg.oracle(P)
+        o.set_global_map(pts)
+        dm = K.DeviceMap(pts, P.robot_size)
+        q = _queries(pts, 100_000, 14, margin=3.0)
+        z, idx, tie = dm.nearest_z(q)
+        oz, oidx, otie = o.nearest_z(q)
+        np.testing.assert_array_equal(tie, otie)
+        ok = tie == 0
+        np.testing.assert_array_equal(idx[ok], oidx[ok])
+        np.testing.assert_array_equal(z[ok], oz[ok])
+        assert ok.mean() > 0.999
+
+
+def _edge_pairs(pts, o, n, seed, e):
+    rng = np.random.default_rng(seed)
+    a = _queries(pts, n, seed, margin=-1.0)
+    ang = rng.uniform(0, 2 * np.pi, n)
+    d = rng.uniform(0.1, 1.45 * e, n)
+    b = (a + np.stack([d * np.cos(ang), d * np.sin(ang)], 1)).astype(np.float32)
+    za, _, _ = o.nearest_z(a)
+    zb, _, _ = o.nearest_z(b)
+    return np.column_stack([a, za]).astype(np.float32), np.column_stack([b, zb]).astype(np.float32)
+
+
+@pytest.mark.parametrize("which,prm", [("mountain", "MOUNTAIN"), ("indoor", "INDOOR")])
+def test_edge_eval_parity(pkg, K, which, prm, small_mountain, small_indoor):
+    pts = small_mountain if which == "mountain" else small_indoor
+    P = getattr(pkg, prm)
+    o = pkg.oracle(P)
+    o.set_global_map(pts)
+    dm = K.DeviceMap(pts, P.robot_size)
+    p1, p2 = _edge_pairs(pts, o, 60_000, 15, P.expand_dist)
+    got = dm.edge_eval(p1, p2, P.robot_size, P.height_threshold, P.collision_threshold)
+    want = o.edge_eval(p1, p2)
+    np.testing.assert_array_equal(got["stage"], want["stage"])
+    np.testing.assert_array_equal(got["dist"], want["dist"])
+    ok = want["stage"] == 0
+    assert ok.sum() > 1000
+    np.testing.assert_array_equal(got["npts"][ok], want["npts"][ok])
+    gw, ww, w64 = got["weight"][ok], want["weight"][ok], want["weight64"][ok]
+    tol = 1e-5  # north_star: edge risks within 1e-5 relative
+    rel = np.abs(gw - ww) / np.maximum(np.abs(ww), 1e-12)
+    rel[(gw == 0) & (ww == 0)] = 0
+    bad = rel > tol
+    # SURVEY A.4 protocol: a mismatch is a real failure only if the float oracle agrees with its
+    # own float64 evaluation (i.e. the case is well-conditioned)
+    rel_o = np.abs(ww - w64) / np.maximum(np.abs(w64), 1e-12)
+    rel_o[(ww == 0) & (w64 == 0)] = 0
+    ill = bad & (rel_o > tol)
+    real = bad & ~ill
+    # GPU (double accumulation) must match the float64 oracle everywhere it is defined
+    rel64 = np.abs(gw - w64) / np.maximum(np.abs(w64), 1e-12)
+    rel64[(gw == 0) & (w64 < 0.1)] = 0
+    thr_cross = (gw == 0) != (w64 < 0.1)
+    print(f"{which}: ok={ok.sum()} bad={bad.sum()} ill={ill.sum()} real={real.sum()} "
+          f"max_rel64={rel64[~thr_cross].max():.3g} thr_cross={thr_cross.sum()}")
+    # the kernel accumulates the covariance in double and runs the reference's float Jacobi on the
+    # rounded result: well-conditioned edges must agree with BOTH oracle pipelines; ill-conditioned
+    # ones (float vs float64 oracle already apart) are counted, not asserted
+    assert real.sum() == 0
+    assert ill.sum() <= 0.01 * ok.sum()
+    well = (rel_o <= 0.1 * tol) & ~thr_cross
+    assert rel64[well].max() <= tol
+    assert thr_cross.sum() <= 3
+
+
+def test_sssp_parity(pkg, K, small_mountain):
+    P = pkg.MOUNTAIN
+    o = pkg.oracle(P)
+    o.seed(42)
+    o.set_global_map(small_mountain)
+    assert o.init_graph((15.0, 15.0, 0.0)) == 0
+    g = o.export()
+    assert np.array_equal(g.ids, np.arange(g.n_nodes))
+    dg = K.DeviceGraph(g.row_ptr, g.col, g.weight, g.dist, g.pos, g.state)
+    q = pkg.terrain.query_pairs(pkg.terrain.bbox(small_mountain), 300, seed=7)
+    starts, goals, ocost, opaths = [], [], [], []
+    sf = np.float32(P.safety_factor)
+    for row in q:
+        r = o.plan(row[:2], row[2:5])
+        assert r["found"]
+        ids = r["ids"]
+        starts.append(ids[0]); goals.append(ids[-1]); opaths.append(ids)
+        c = np.float32(0)
+        for a, b in zip(ids[:-1], ids[1:]):
+            e = g.row_ptr[a] + np.nonzero(g.col[g.row_ptr[a]:g.row_ptr[a + 1]] == b)[0][0]
+            c = np.float32(c + np.float32(np.float32(np.float32(sf * g.weight[e]) + np.float32(1)) * g.dist[e]))
+        ocost.append(c)
+    res = dg.sssp(starts, goals, P.safety_factor)
+    assert res["found"].all()
+    ocost = np.array(ocost, np.float32)
+    rel = np.abs(res["cost"] - ocost) / np.maximum(ocost, 1e-9)
+    assert rel.max() <= 1e-5, rel.max()
+    same = 0
+    for i, ids in enumerate(opaths):
+        mine = res["ids"][res["offsets"][i]:res["offsets"][i + 1]]
+        assert mine[0] == starts[i] and mine[-1] == goals[i]
+        same += int(len(mine) == len(ids) and np.array_equal(mine, ids))
+        # path_length / avg_risk follow from the node sequence; compare when it is identical
+        if len(mine) == len(ids) and np.array_equal(mine, ids):
+            assert abs(res["path_length"][i] - r_len(g, ids)) <= 1e-5 * max(1.0, r_len(g, ids))
+    print(f"identical node sequences: {same}/{len(opaths)}")
+    assert same >= 0.9 * len(opaths)
+
+
+def r_len(g, ids):
+    s = np.float32(0)
+    for a, b in zip(ids[::-1][:-1], ids[::-1][1:]):  # goal -> start accumulation (trg.cpp:641-659)
+        e = g.row_ptr[a] + np.nonzero(g.col[g.row_ptr[a]:g.row_ptr[a + 1]] == b)[0][0]
+        s = np.float32(s + g.dist[e])
+    return float(s)

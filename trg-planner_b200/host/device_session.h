@@ -1,5 +1,8 @@
-// Pinned-host / device buffer pairs used by the wavefront scheduler. Memory management only
+// Pinned-host / device staging arenas used by the wavefront scheduler. Memory management only
 // (CUDA runtime); every kernel is reached through the C ABI in include/trgb_kernels.h.
+//
+// One batch = one H2D copy of the whole input arena, a few kernel launches on sub-ranges of it,
+// one D2H copy of the whole output arena, one stream synchronise.
 #pragma once
 #include <cuda_runtime_api.h>
 
@@ -15,62 +18,92 @@ inline void cuda_check(cudaError_t e, const char* what) {
     throw std::runtime_error(std::string("trg_b200: CUDA failure in ") + what + ": " + cudaGetErrorString(e));
 }
 
-template <class T>
-struct Mirror {
-  T* h = nullptr;
-  T* d = nullptr;
-  size_t cap = 0;
-  ~Mirror() { release(); }
+// Bump allocator over a pinned host buffer and a device buffer of the same size.
+class Arena {
+ public:
+  ~Arena() { release(); }
   void release() {
-    if (h) cudaFreeHost(h);
-    if (d) cudaFree(d);
-    h = nullptr; d = nullptr; cap = 0;
+    if (h_) cudaFreeHost(h_);
+    if (d_) cudaFree(d_);
+    h_ = nullptr; d_ = nullptr; cap_ = 0; used_ = 0;
   }
-  void ensure(size_t n) {
-    if (n <= cap) return;
-    size_t want = cap ? cap : 1024;
-    while (want < n) want *= 2;
+  // Drop the contents and make sure `bytes` fit. Invalidates earlier offsets.
+  void reset(size_t bytes) {
+    used_ = 0;
+    if (bytes <= cap_) return;
+    size_t want = cap_ ? cap_ : (size_t)1 << 16;
+    while (want < bytes) want *= 2;
     release();
-    cuda_check(cudaMallocHost(reinterpret_cast<void**>(&h), want * sizeof(T)), "cudaMallocHost");
-    cuda_check(cudaMalloc(reinterpret_cast<void**>(&d), want * sizeof(T)), "cudaMalloc");
-    cap = want;
+    cuda_check(cudaMallocHost(reinterpret_cast<void**>(&h_), want), "cudaMallocHost(arena)");
+    cuda_check(cudaMalloc(reinterpret_cast<void**>(&d_), want), "cudaMalloc(arena)");
+    cap_ = want;
   }
-  void h2d(size_t n, cudaStream_t s) {
-    if (n) cuda_check(cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, s), "H2D");
+  static size_t padded(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+  size_t take(size_t bytes) {
+    const size_t off = used_;
+    used_ += padded(bytes);
+    if (used_ > cap_) throw std::logic_error("trg_b200: arena overflow (reset() sized too small)");
+    return off;
   }
-  void d2h(size_t n, cudaStream_t s) {
-    if (n) cuda_check(cudaMemcpyAsync(h, d, n * sizeof(T), cudaMemcpyDeviceToHost, s), "D2H");
+  template <class T> T* h(size_t off) { return reinterpret_cast<T*>(h_ + off); }
+  template <class T> T* d(size_t off) { return reinterpret_cast<T*>(d_ + off); }
+  size_t used() const { return used_; }
+  void h2d(cudaStream_t s) {
+    if (used_) cuda_check(cudaMemcpyAsync(d_, h_, used_, cudaMemcpyHostToDevice, s), "H2D(arena)");
   }
-  void zero_d(size_t n, cudaStream_t s) {
-    if (n) cuda_check(cudaMemsetAsync(d, 0, n * sizeof(T), s), "memset");
+  void d2h(cudaStream_t s) {
+    if (used_) cuda_check(cudaMemcpyAsync(h_, d_, used_, cudaMemcpyDeviceToHost, s), "D2H(arena)");
   }
+  void zero_d(size_t off, size_t bytes, cudaStream_t s) {
+    if (bytes) cuda_check(cudaMemsetAsync(d_ + off, 0, bytes, s), "memset(arena)");
+  }
+
+ private:
+  uint8_t* h_ = nullptr;
+  uint8_t* d_ = nullptr;
+  size_t cap_ = 0, used_ = 0;
 };
 
-// All staging buffers of one TRG instance.
+// Device-resident copy of the sampling-draw offsets (expand_dist*cosf(angle), expand_dist*sinf(angle))
+// for stream positions [base, base+count): uploaded once per generated block, indexed by the
+// sampling-window kernel.
+class DrawBuffer {
+ public:
+  ~DrawBuffer() { if (d_) cudaFree(d_); }
+  void clear() { count_ = 0; base_ = 0; }
+  size_t base() const { return base_; }
+  size_t end() const { return base_ + count_; }
+  const float* dev() const { return d_; }
+  void set_base(size_t b) { base_ = b; count_ = 0; }
+  // append n (x,y) pairs that follow the current end
+  void append(const float* xy, size_t n, cudaStream_t s) {
+    if (count_ + n > cap_) {
+      size_t want = cap_ ? cap_ : (size_t)1 << 16;
+      while (want < count_ + n) want *= 2;
+      float* nd = nullptr;
+      cuda_check(cudaMalloc(reinterpret_cast<void**>(&nd), want * 2 * sizeof(float)), "cudaMalloc(draws)");
+      if (count_) cuda_check(cudaMemcpyAsync(nd, d_, count_ * 2 * sizeof(float), cudaMemcpyDeviceToDevice, s), "D2D(draws)");
+      cuda_check(cudaStreamSynchronize(s), "sync(draws)");
+      if (d_) cudaFree(d_);
+      d_ = nd;
+      cap_ = want;
+    }
+    // source is pageable host memory: the runtime stages it before returning
+    cuda_check(cudaMemcpyAsync(d_ + count_ * 2, xy, n * 2 * sizeof(float), cudaMemcpyHostToDevice, s), "H2D(draws)");
+    count_ += n;
+  }
+
+ private:
+  float* d_ = nullptr;
+  size_t cap_ = 0, count_ = 0, base_ = 0;
+};
+
+// All staging state of one TRG instance.
 class DeviceSession {
  public:
-  // sampling windows
-  Mirror<float> node_xy;                 // 2 per node
-  Mirror<int32_t> first_draw;            // per node, relative to the uploaded draw slice
-  Mirror<float> draw_xy;                 // 2 per draw
-  Mirror<unsigned long long> mask;       // words per node
-  // sample / edge evaluation
-  Mirror<float> p1;                      // 3 per item
-  Mirror<float> p2;                      // 2 per item
-  Mirror<float> z;                       // per item
-  Mirror<uint8_t> stage;
-  Mirror<float> weight;
-  Mirror<float> dist;
-  Mirror<uint8_t> tie;
-  // deferred edge evaluations
-  Mirror<float> dp1, dp2, dweight, ddist;
-  Mirror<uint8_t> dstage;
-  // generic queries
-  Mirror<float> qxy;
-  Mirror<uint8_t> qout;
-  Mirror<int32_t> qcount;
-
-  uint64_t bytes_h2d = 0, bytes_d2h = 0;
+  Arena in, out;
+  DrawBuffer draws;
+  uint64_t bytes_h2d = 0, bytes_d2h = 0, batches = 0;
 };
 
 }  // namespace trg_b200
