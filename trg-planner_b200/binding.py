@@ -92,6 +92,12 @@ class TrgFacade:
             f("last_error").restype = C.c_char_p
             f("last_error").argtypes = []
             f("plan_batch").argtypes = [_vp, _vp, C.c_int64] + [_vp] * 8 + [C.c_int64]
+            f("save_graph").argtypes = [_vp, C.c_char_p]
+            f("load_graph").argtypes = [_vp, C.c_char_p]
+            f("set_tuning").argtypes = [_vp, C.c_char_p, C.c_double]
+            f("set_global_map_dev").argtypes = [_vp, _vp, C.c_int64, C.c_int]
+            f("check_reached").argtypes = [_vp, C.c_float, C.c_float]
+            f("check_replan").argtypes = [_vp, C.c_float, C.c_float, _vp, C.c_int]
 
     def last_error(self) -> str:
         if self.p != "trg":
@@ -186,6 +192,19 @@ class TrgFacade:
         return dict(found=found.astype(bool), cost=cost, path_length=length, avg_risk=risk,
                     direct_dist=direct, goal_known=known.astype(bool), offsets=offs,
                     ids=ids[:int(offs[-1])].copy())
+
+    def save_graph(self, path: str):
+        self._chk(self._f("save_graph")(self.h, str(path).encode()), "save_graph")
+
+    def load_graph(self, path: str):
+        self._chk(self._f("load_graph")(self.h, str(path).encode()), "load_graph")
+
+    def set_tuning(self, key: str, value: float):
+        self._chk(self._f("set_tuning")(self.h, key.encode(), float(value)), "set_tuning")
+
+    def set_global_map_dev(self, dev_ptr: int, n: int, stride: int = 3):
+        """Map cloud already resident in HBM (bench `value` leg)."""
+        self._chk(self._f("set_global_map_dev")(self.h, C.c_void_p(dev_ptr), n, stride), "set_global_map_dev")
 
     def refine_path(self, path: np.ndarray):
         p = np.ascontiguousarray(path, dtype=np.float32)

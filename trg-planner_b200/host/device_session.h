@@ -90,6 +90,7 @@ class DrawBuffer {
     }
     // source is pageable host memory: the runtime stages it before returning
     cuda_check(cudaMemcpyAsync(d_ + count_ * 2, xy, n * 2 * sizeof(float), cudaMemcpyHostToDevice, s), "H2D(draws)");
+    cuda_check(cudaStreamSynchronize(s), "sync(draws)");  // visible to every stream launched after this returns
     count_ += n;
   }
 
@@ -101,9 +102,18 @@ class DrawBuffer {
 // All staging state of one TRG instance.
 class DeviceSession {
  public:
-  Arena in, out;
+  ~DeviceSession() { if (copy_) cudaStreamDestroy(copy_); }
+  Arena in, out;    // batch staging (windows, speculative evaluation)
+  Arena in2, out2;  // mid-commit flushes: must not disturb the results `out` still holds
   DrawBuffer draws;
-  uint64_t bytes_h2d = 0, bytes_d2h = 0, batches = 0;
+  uint64_t batches = 0;
+  cudaStream_t copyStream() {
+    if (!copy_) cuda_check(cudaStreamCreateWithFlags(&copy_, cudaStreamNonBlocking), "cudaStreamCreate");
+    return copy_;
+  }
+
+ private:
+  cudaStream_t copy_ = nullptr;
 };
 
 }  // namespace trg_b200

@@ -1,0 +1,1114 @@
+// TRG — B200-native implementation of the reference graph core
+//   cpp/trg_planner/core/trg_planner/src/graph/trg.cpp   (cited below as trg.cpp:LINE).
+//
+// Same public behaviour, different machinery: every map query (the reference's kd_nearest_range2 /
+// kd_nearest2 on `map_tree`) is a batched kernel launch through include/trgb_kernels.h; graph
+// expansion is a wavefront scheduler (class Expander) that evaluates the pure-function work of
+// many queue pops at once and then commits decisions in the reference's exact sequential order.
+// Nothing here touches oracle/; without a CUDA device every map-dependent call throws.
+#include "trg.h"
+
+#include <math.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <limits>
+#include <stdexcept>
+
+#include "device_session.h"
+#include "trgb_kernels.h"
+
+namespace {
+using Clock = std::chrono::steady_clock;
+inline double since(Clock::time_point t0) { return std::chrono::duration<double>(Clock::now() - t0).count(); }
+
+[[noreturn]] void fail(const std::string& what) {
+  throw std::runtime_error("trg_b200: " + what + ": " + trgb_last_error());
+}
+inline void K(int rc, const char* what) {
+  if (rc != TRGB_OK) fail(what);
+}
+inline float norm2(float dx, float dy) { return sqrtf(dx * dx + dy * dy); }  // Vector2f::norm()
+}  // namespace
+
+// ================================================================================================
+// construction / reset
+// ================================================================================================
+TRG::TRG(bool isVerbose, float expand_dist, float robot_size, int sample_num, float height_threshold,
+         float collision_threshold, float update_collision_threshold, float safety_factor,
+         float goal_tolerance)
+    : gen_(rd_()), distr_(0.0, 1.0), dev_(new trg_b200::DeviceSession()) {  // trg.cpp:11-34
+  param_.isVerbose                  = isVerbose;
+  param_.expand_dist                = expand_dist;
+  param_.robot_size                 = robot_size;
+  param_.sample_num                 = sample_num;
+  param_.height_threshold           = height_threshold;
+  param_.collision_threshold        = collision_threshold;
+  param_.update_collision_threshold = update_collision_threshold;
+  param_.safety_factor              = safety_factor;
+  param_.goal_tolerance             = goal_tolerance;
+  this->resetGraph("global");
+  this->resetGraph("local");
+  this->resetMap("global");
+  this->resetMap("local");
+}
+
+TRG::~TRG() {
+  for (auto& kv : trgMap_) {
+    if (kv.second->map_index) trgb_map_destroy(kv.second->map_index);
+    kv.second->map_index = nullptr;
+  }
+  if (dev_graph_) trgb_graph_destroy(dev_graph_);
+}
+
+void TRG::resetGraph(std::string type) {  // trg.cpp:732-737
+  trgStruct& graph = *trgMap_.at(type);
+  graph.nodes.clear();
+  nodeIndexReset(graph);
+  graph.node_id = 0;
+  if (type == "global") invalidateDeviceGraph();
+}
+
+void TRG::resetMap(std::string type) {  // trg.cpp:739-744
+  trgStruct& graph = *trgMap_.at(type);
+  if (graph.map_index) trgb_map_destroy(graph.map_index);
+  graph.map_index  = nullptr;
+  graph.map_points = 0;
+  graph.cloud_map.reset(new pcl::PointCloud<PtsDefault>());
+}
+
+void TRG::reseed(uint32_t seed) {
+  gen_.seed(seed);
+  distr_.reset();
+  draw_u_.clear();
+  draw_xy_.clear();
+  draw_base_ = draw_next_ = 0;
+  dev_->draws.set_base(0);
+}
+
+TRG::Node* TRG::newNode(int id, Eigen::Vector2f& p, float z, NodeState s) {
+  node_pool_.emplace_back(id, p, z, s);
+  return &node_pool_.back();
+}
+TRG::Edge* TRG::newEdge(int dst, float w, float d) {
+  edge_pool_.emplace_back(dst, w, d);
+  return &edge_pool_.back();
+}
+
+// ================================================================================================
+// sampling stream
+// ================================================================================================
+void TRG::ensureDraws(size_t upto) {
+  const size_t have = draw_base_ + draw_u_.size();
+  if (upto <= have) return;
+  size_t want = std::max(upto, have + (size_t)(1 << 15));  // generate in blocks
+  const size_t first = draw_u_.size();
+  draw_u_.resize(want - draw_base_);
+  draw_xy_.resize(2 * (want - draw_base_));
+  const float e = param_.expand_dist;
+  for (size_t k = first; k < draw_u_.size(); ++k) {
+    const float u = distr_(gen_);
+    draw_u_[k]    = u;
+    // trg.cpp:395-397: float angle = distr_(gen_) * 2 * M_PI; Vector2f(e * cos(angle), e * sin(angle))
+    const float angle   = u * 2 * M_PI;
+    draw_xy_[2 * k]     = e * cosf(angle);
+    draw_xy_[2 * k + 1] = e * sinf(angle);
+  }
+}
+
+// make the device copy cover exactly the host buffer [draw_base_, draw_base_ + size)
+void TRG::syncDraws() {
+  trg_b200::DrawBuffer& db = dev_->draws;
+  const size_t host_end = draw_base_ + draw_u_.size();
+  if (db.base() != draw_base_ || db.end() > host_end) db.set_base(draw_base_);
+  if (db.end() < host_end)
+    db.append(draw_xy_.data() + 2 * (db.end() - draw_base_), host_end - db.end(), dev_->copyStream());
+}
+
+float TRG::nextUniform() {
+  ensureDraws(draw_next_ + 1);
+  return draw_u_[draw_next_++ - draw_base_];
+}
+
+void TRG::compactDraws() {
+  const size_t used = draw_next_ - draw_base_;
+  if (used < ((size_t)1 << 20)) return;
+  draw_u_.erase(draw_u_.begin(), draw_u_.begin() + used);
+  draw_xy_.erase(draw_xy_.begin(), draw_xy_.begin() + 2 * used);
+  draw_base_ = draw_next_;
+  dev_->draws.set_base(draw_base_);  // dropped: syncDraws() re-uploads the remainder
+}
+
+// ================================================================================================
+// maps
+// ================================================================================================
+void TRG::buildMapIndex(trgStruct& g, const float* xyz, int64_t n, int stride, bool device) {
+  if (g.map_index) trgb_map_destroy(g.map_index);
+  g.map_index  = nullptr;
+  g.map_points = 0;
+  if (n <= 0) return;
+  const float cell = tuning_.map_cell_scale * param_.robot_size;
+  if (device) K(trgb_map_create_dev(&g.map_index, xyz, n, stride, cell), "trgb_map_create_dev");
+  else K(trgb_map_create(&g.map_index, xyz, n, stride, cell), "trgb_map_create");
+  g.map_points = n;
+  TrgbMapInfo mi;
+  K(trgb_map_info(g.map_index, &mi), "trgb_map_info");
+  g.bbox[0] = mi.origin_x;
+  g.bbox[1] = mi.origin_y;
+  g.bbox[2] = mi.origin_x + mi.grid_w * mi.cell_size;
+  g.bbox[3] = mi.origin_y + mi.grid_h * mi.cell_size;
+}
+
+trgb_map* TRG::requireMap(trgStruct& g, const char* who) {
+  if (!g.map_index) throw std::runtime_error(std::string("trg_b200: ") + who + ": no " + g.type + " map loaded");
+  return g.map_index;
+}
+
+void TRG::setGlobalMap(PointCloudPtr& map) {  // trg.cpp:179-193
+  auto t0 = Clock::now();
+  trgStruct& g = *trgMap_["global"];
+  this->resetMap("global");
+  *g.cloud_map = *map;
+  const int64_t n = (int64_t)g.cloud_map->size();
+  if (n > 0) buildMapIndex(g, reinterpret_cast<const float*>(g.cloud_map->points.data()), n, 4, false);
+  secs_["set_global_map"] = since(t0);
+}
+
+void TRG::setGlobalMapRaw(const float* xyz, int64_t n, int stride_floats, bool device) {
+  auto t0 = Clock::now();
+  trgStruct& g = *trgMap_["global"];
+  this->resetMap("global");
+  buildMapIndex(g, xyz, n, stride_floats, device);
+  secs_["set_global_map"] = since(t0);
+}
+
+void TRG::setLocalMap(Eigen::Vector2f start2d, PointCloudPtr& map) {  // trg.cpp:195-209
+  std::lock_guard<std::mutex> lock(mtx.graph);
+  auto t0 = Clock::now();
+  trgStruct& l = *trgMap_["local"];
+  this->resetMap("local");
+  l.root_pos   = start2d;
+  *l.cloud_map = *map;
+  const int64_t n = (int64_t)l.cloud_map->size();
+  if (n > 0) buildMapIndex(l, reinterpret_cast<const float*>(l.cloud_map->points.data()), n, 4, false);
+  this->setLocalGraph(false);
+  secs_["set_local_map"] = since(t0);
+}
+
+void TRG::setLocalMapRaw(Eigen::Vector2f start2d, const float* xyz, int64_t n, int stride_floats) {
+  std::lock_guard<std::mutex> lock(mtx.graph);
+  auto t0 = Clock::now();
+  trgStruct& l = *trgMap_["local"];
+  this->resetMap("local");
+  l.root_pos = start2d;
+  buildMapIndex(l, xyz, n, stride_floats, false);
+  this->setLocalGraph(false);
+  secs_["set_local_map"] = since(t0);
+}
+
+void TRG::setLocalGraph(bool useMutex) {  // trg.cpp:211-231
+  if (useMutex) {
+    std::lock_guard<std::mutex> lock(mtx.graph);  // (sic) the reference's guard dies here too
+  }
+  trgStruct& g = *trgMap_["global"];
+  trgStruct& l = *trgMap_["local"];
+  this->resetGraph("local");
+  if (g.nodes.empty()) return;
+  // one batched range-count over every global node, in the map's iteration order
+  std::vector<Node*> order;
+  order.reserve(g.nodes.size());
+  std::vector<float> xy;
+  xy.reserve(2 * g.nodes.size());
+  for (auto& node : g.nodes) {
+    order.push_back(node.second);
+    xy.push_back(node.second->pos_.x());
+    xy.push_back(node.second->pos_.y());
+  }
+  std::vector<int32_t> cnt(order.size(), 0);
+  if (l.map_index)
+    K(trgb_range_count_batch(l.map_index, xy.data(), (int64_t)order.size(), (float)(param_.robot_size * 0.5), cnt.data()),
+      "trgb_range_count_batch");
+  size_t k = 0;
+  for (auto& node : g.nodes) {
+    if (cnt[k++] == 0) continue;
+    l.nodes[node.first] = node.second;
+    nodeIndexInsert(l, node.second);
+  }
+}
+
+// ================================================================================================
+// node index (replaces kdtree* node_tree)
+// ================================================================================================
+void TRG::nodeIndexReset(trgStruct& g) {
+  g.node_seq.clear();
+  g.node_grid.clear();
+  g.node_tree.clear();
+  g.tree_built = 0;
+}
+
+void TRG::ensureGrid(trgStruct& g) {
+  if (g.node_grid.configured()) return;
+  // nodes live within robot_size of a map point; pad generously (positions are clamped anyway)
+  const trgStruct& m = global_trg_.map_index ? global_trg_ : g;
+  float x0 = m.bbox[0], y0 = m.bbox[1], x1 = m.bbox[2], y1 = m.bbox[3];
+  if (!(x1 > x0) || !(y1 > y0)) { x0 = y0 = -64.f; x1 = y1 = 64.f; }
+  const float cell = std::max(param_.expand_dist, param_.robot_size);
+  g.node_grid.configure(x0 - 2.f, y0 - 2.f, x1 + 2.f, y1 + 2.f, cell);
+}
+
+void TRG::nodeIndexInsert(trgStruct& g, Node* n) {
+  ensureGrid(g);
+  g.node_grid.insert(n->pos_.x(), n->pos_.y());
+  g.node_seq.push_back(n);
+}
+
+void TRG::ensureTree(trgStruct& g) {
+  for (; g.tree_built < g.node_seq.size(); ++g.tree_built) {
+    Node* n = g.node_seq[g.tree_built];
+    g.node_tree.insert(n->pos_.x(), n->pos_.y(), (int)g.tree_built);
+  }
+}
+
+// kd_nearest2 on node_tree (kdtree.c:364-417): exact float argmin; exact ties by tree visit order
+TRG::Node* TRG::nearestNode(trgStruct& g, float x, float y) {
+  if (g.node_seq.empty()) return nullptr;
+  auto nn = g.node_grid.nearest(x, y);
+  if (nn.entry >= 0 && !nn.tie) return g.node_seq[nn.entry];
+  ensureTree(g);
+  stat_["node_ties"]++;
+  return g.node_seq[g.node_tree.nearest(x, y)];
+}
+
+// kd_nearest_range2 on node_tree in the reference's result-iteration order
+void TRG::rangeNodesOrdered(trgStruct& g, float x, float y, float r, std::vector<Node*>& out) {
+  out.clear();
+  if (g.node_seq.empty()) return;
+  ensureTree(g);
+  static thread_local std::vector<int> idx;
+  g.node_tree.range(x, y, r, idx);
+  for (int i : idx) out.push_back(g.node_seq[i]);
+}
+
+int TRG::countNodesInRange(trgStruct& g, float x, float y, float r) {
+  if (g.node_seq.empty()) return 0;
+  return g.node_grid.count_in_range(x, y, r);
+}
+
+// ================================================================================================
+// single-shot primitives of the public API (each is one tiny batch on the device)
+// ================================================================================================
+bool TRG::isCollision(Eigen::Vector2f& pos, std::string type, float threshold) {  // trg.cpp:746-778
+  trgStruct& g = *trgMap_.at(type);
+  uint8_t out = 1;
+  const float xy[2] = {pos.x(), pos.y()};
+  K(trgb_collision_batch(requireMap(g, "isCollision"), xy, 1, param_.robot_size, param_.height_threshold, threshold, &out),
+    "trgb_collision_batch");
+  stat_["collision_calls"]++;
+  return out != 0;
+}
+
+void TRG::isCollisionBatch(const float* xy, int64_t n, const std::string& type, float threshold, uint8_t* out) {
+  trgStruct& g = *trgMap_.at(type);
+  K(trgb_collision_batch(requireMap(g, "isCollisionBatch"), xy, n, param_.robot_size, param_.height_threshold, threshold, out),
+    "trgb_collision_batch");
+  stat_["collision_calls"] += n;
+}
+
+bool TRG::isFrontier(Eigen::Vector2f& pos) {  // trg.cpp:780-803
+  trgStruct& g = *trgMap_["global"];
+  trgStruct& l = *trgMap_["local"];
+  Eigen::Vector2f dir = pos - l.root_pos;
+  dir.normalize();
+  Eigen::Vector2f check = pos + 2 * param_.robot_size * dir;
+  if (countNodesInRange(g, check.x(), check.y(), param_.robot_size) > 0) return false;
+  int32_t cnt = 0;
+  const float xy[2] = {check.x(), check.y()};
+  if (l.map_index)
+    K(trgb_range_count_batch(l.map_index, xy, 1, (float)(0.5 * param_.robot_size), &cnt), "trgb_range_count_batch");
+  return cnt == 0;
+}
+
+bool TRG::addNode(int node_id, Eigen::Vector2f& node_pos, NodeState state, std::string type) {  // trg.cpp:233-252
+  trgStruct& graph = *trgMap_.at(type);
+  if (node_id == 0) {
+    if (this->isCollision(node_pos, graph.type, param_.collision_threshold)) return false;
+  }
+  float z = 0.f;
+  uint8_t tie = 0;
+  const float xy[2] = {node_pos.x(), node_pos.y()};
+  K(trgb_nearest_z_batch(requireMap(graph, "addNode"), xy, 1, &z, nullptr, &tie), "trgb_nearest_z_batch");
+  stat_["nearest_map"]++;
+  if (tie) stat_["z_ties"]++;
+  Node* node           = newNode(node_id, node_pos, z, state);
+  graph.nodes[node_id] = node;
+  nodeIndexInsert(graph, node);
+  graph.node_id++;
+  if (&graph == &global_trg_) invalidateDeviceGraph();
+  return true;
+}
+
+namespace {
+// trg.cpp:269-274 — slope gate, float overloads (SURVEY.md hard part 2)
+inline bool slope_rejects(const Eigen::Vector3f& a, const Eigen::Vector3f& b, float height_thr, float robot_size) {
+  const float max_slope = atan2f(height_thr, robot_size);
+  const float slope     = atan2f(fabsf(a.z() - b.z()), norm2(a.x() - b.x(), a.y() - b.y()));
+  return slope > max_slope;
+}
+inline bool has_edge_to(const TRG::Node* n, int id) {
+  for (auto* e : n->edges_)
+    if (e->dst_id_ == id) return true;
+  return false;
+}
+}  // namespace
+
+void TRG::wireEdge(Node* node1, Node* node2, std::string type) {  // trg.cpp:254-370
+  if (node1->id_ == node2->id_) return;
+  if (has_edge_to(node1, node2->id_) || has_edge_to(node2, node1->id_)) return;
+  trgStruct& graph = *trgMap_.at(type);
+  const float p1[3] = {node1->pos_.x(), node1->pos_.y(), node1->pos_.z()};
+  const float p2[3] = {node2->pos_.x(), node2->pos_.y(), node2->pos_.z()};
+  TrgbEdgeParams prm{param_.robot_size, param_.height_threshold, param_.collision_threshold};
+  uint8_t stage = 0;
+  float w = 0.f, d = 0.f;
+  K(trgb_edge_eval_batch(requireMap(graph, "wireEdge"), p1, p2, 1, &prm, &stage, &w, &d, nullptr), "trgb_edge_eval_batch");
+  stat_["edge_evals"]++;
+  if (stage != TRGB_EDGE_OK) return;
+  node1->edges_.push_back(newEdge(node2->id_, w, d));
+  node2->edges_.push_back(newEdge(node1->id_, w, d));
+  if (&graph == &global_trg_) invalidateDeviceGraph();
+}
+
+// ================================================================================================
+// Expander — wavefront scheduler for TRG::expandGraph (trg.cpp:372-454)
+//
+// The reference pops one node at a time: draw angles until sample_num collision-free samples, then
+// for each sample look up the nearest existing node and wire / insert. Three facts make it
+// batchable without changing a single decision:
+//   (1) sampling never looks at the graph: the draw positions consumed by successive pops form a
+//       chain o_{i+1} = o_i + consumed_i that depends only on (node position, map, stream);
+//   (2) the z of a would-be new node and the geometric part of wireEdge(node, new) are pure
+//       functions of (node, sample, map) -> evaluated speculatively for every accepted sample;
+//   (3) wireEdge to an *existing* node only appends edges; nothing decided later in the same
+//       expansion depends on its outcome except the emptiness of a brand-new node's edge list,
+//       so those evaluations are deferred (placeholder edges keep the reference's edge order and
+//       duplicate suppression) and resolved in the next batch.
+// Per batch of pops: [windows kernel] -> host chain scan -> [nearest-z + edge kernels] -> host
+// commit in (pop, sample) order.
+// ================================================================================================
+namespace trg_b200 {
+
+class Expander {
+ public:
+  Expander(TRG& t, TRG::trgStruct& g) : t_(t), g_(g), P_(t.param_) {
+    map_ = t.requireMap(g, "expandGraph");
+    st_  = (cudaStream_t)trgb_map_stream(map_);
+    // trg.cpp:429 — `float - float < double * float`
+    step3_ = (P_.expand_dist - P_.robot_size < 0.25 * P_.expand_dist);
+    mean_  = 1.15 * P_.sample_num;
+  }
+
+  void run(const std::vector<TRG::Node*>& roots) {
+    t_.compactDraws();
+    size_t root_i = 0;
+    std::deque<TRG::Node*> bfs;
+    int cur_ref = -1;
+    const size_t C = (size_t)std::max(1, t_.tuning_.chunk_nodes);
+    while (true) {
+      chunk_.clear();
+      for (size_t k = 0; k < bfs.size() && chunk_.size() < C; ++k) chunk_.push_back({bfs[k], cur_ref, false});
+      if (chunk_.size() == bfs.size())
+        for (size_t r = root_i; r < roots.size() && chunk_.size() < C; ++r)
+          chunk_.push_back({roots[r], roots[r]->id_, true});
+      if (chunk_.empty()) break;
+      sampleChunk();
+      evalChunk();
+      for (size_t i = 0; i < chunk_.size(); ++i) {
+        Pop& p = chunk_[i];
+        if (p.is_root) {
+          if (!bfs.empty()) break;  // the previous root's BFS is still running: speculation is stale
+        }
+        if (p.draw_start != t_.draw_next_) break;
+        if (p.is_root) {
+          cur_ref = p.ref_id;
+          ++root_i;
+        } else {
+          bfs.pop_front();
+        }
+        commitPop(p, bfs);
+      }
+    }
+    flushDeferred();
+  }
+
+ private:
+  struct Pop {
+    TRG::Node* node;
+    int ref_id;
+    bool is_root;
+    size_t draw_start = 0;
+    int consumed = 0;
+    uint32_t acc_begin = 0, acc_count = 0;
+  };
+  struct Sample { float x, y; };
+  struct Deferred { TRG::Node *a, *b; TRG::Edge *ea, *eb; int primary; bool ok; };
+
+  // ---- phase A: sampling windows (trg.cpp:384-403) ------------------------------------------
+  void sampleChunk() {
+    const int S = P_.sample_num;
+    const size_t m = chunk_.size();
+    acc_.clear();
+    size_t done = 0;
+    size_t pos = t_.draw_next_;  // stream position reached by the chain
+    int part_acc = 0, part_trials = 0;
+    bool part_open = false;
+    int W = std::min(256, std::max(8, t_.tuning_.window));
+    guess_.resize(m);
+    int stuck = 0;
+    while (done < m) {
+      const int words = (W + 63) >> 6;
+      // window start guesses: exact for the first open node, extrapolated with the running mean
+      // draws/pop minus a lead that grows like a random walk for the others
+      const size_t n_live = m - done;
+      size_t hi = 0;
+      for (size_t i = done; i < m; ++i) {
+        const size_t k = i - done;
+        size_t gpos = pos;
+        if (k > 0) {
+          // every pop consumes at least min(S, 1001) draws (trg.cpp:389-392)
+          const size_t smin = (size_t)std::min(S, 1001);
+          const size_t lb   = pos + (size_t)std::max(0, (int)smin - part_acc) + (k - 1) * smin;
+          double lead = 2.0 + 2.0 * std::sqrt((double)k * var_);
+          lead = std::min(lead, std::max(2.0, 0.5 * ((double)W - 2.0 * mean_)));
+          const double rem0 = (double)(S - part_acc) * (mean_ / (double)S);
+          const double ex   = (double)pos + rem0 + (double)(k - 1) * mean_ - lead;
+          gpos = (size_t)std::max((double)lb, std::floor(ex));
+        }
+        guess_[i] = gpos;
+        hi = std::max(hi, gpos + (size_t)W);
+      }
+      t_.ensureDraws(hi);
+      t_.syncDraws();
+      DrawBuffer& db = t_.dev_->draws;
+      Arena& in  = t_.dev_->in;
+      Arena& out = t_.dev_->out;
+      in.reset(Arena::padded(n_live * 2 * sizeof(float)) + Arena::padded(n_live * sizeof(int32_t)));
+      out.reset(Arena::padded(n_live * words * sizeof(unsigned long long)));
+      const size_t o_xy = in.take(n_live * 2 * sizeof(float));
+      const size_t o_fd = in.take(n_live * sizeof(int32_t));
+      const size_t o_mk = out.take(n_live * words * sizeof(unsigned long long));
+      float* xy   = in.h<float>(o_xy);
+      int32_t* fd = in.h<int32_t>(o_fd);
+      for (size_t i = done; i < m; ++i) {
+        xy[2 * (i - done)]     = chunk_[i].node->pos_.x();
+        xy[2 * (i - done) + 1] = chunk_[i].node->pos_.y();
+        fd[i - done]           = (int32_t)(guess_[i] - db.base());
+      }
+      in.h2d(st_);
+      out.zero_d(o_mk, n_live * words * sizeof(unsigned long long), st_);
+      K(trgb_sample_window_launch(map_, in.d<float>(o_xy), in.d<int32_t>(o_fd), db.dev(), (int64_t)n_live, W,
+                                  P_.robot_size, P_.height_threshold, P_.collision_threshold,
+                                  out.d<unsigned long long>(o_mk)),
+        "trgb_sample_window_launch");
+      out.d2h(st_);
+      cuda_check(cudaStreamSynchronize(st_), "sync(windows)");
+      t_.dev_->batches++;
+      t_.stat_["window_launches"]++;
+      t_.stat_["window_tests"] += (int64_t)n_live * W;
+      const unsigned long long* mk = out.h<unsigned long long>(o_mk);
+      // host chain scan
+      const size_t done_before = done;
+      const size_t pos_before  = pos;
+      for (size_t i = done; i < m; ++i) {
+        Pop& p = chunk_[i];
+        if (!part_open) {
+          p.draw_start = pos;
+          p.acc_begin  = (uint32_t)acc_.size();
+          part_acc = 0;
+          part_trials = 0;
+          part_open = true;
+        }
+        if (pos < guess_[i]) break;  // the window starts past the chain position: re-plan from here
+        const unsigned long long* w = mk + (i - done_before) * words;
+        bool miss = false;
+        const float nx = p.node->pos_.x(), ny = p.node->pos_.y();
+        while (part_acc < S) {
+          if (part_trials > 1000) break;  // trg.cpp:390-392 (checked before every draw)
+          const size_t rel = pos - guess_[i];
+          if (rel >= (size_t)W) { miss = true; break; }
+          const bool coll = (w[rel >> 6] >> (rel & 63)) & 1ull;
+          const size_t d  = pos - t_.draw_base_;
+          ++pos;
+          if (coll) { ++part_trials; continue; }
+          acc_.push_back({nx + t_.draw_xy_[2 * d], ny + t_.draw_xy_[2 * d + 1]});  // trg.cpp:396-397
+          ++part_acc;
+        }
+        if (miss) break;
+        p.consumed  = (int)(pos - p.draw_start);
+        p.acc_count = (uint32_t)acc_.size() - p.acc_begin;
+        part_open   = false;
+        ++done;
+        const double c = (double)p.consumed;
+        mean_ += 0.02 * (c - mean_);
+        var_  += 0.02 * ((c - mean_) * (c - mean_) - var_);
+        if (var_ < 0.25) var_ = 0.25;
+      }
+      if (done == done_before && pos == pos_before) {
+        if (++stuck > 64) throw std::logic_error("trg_b200: sampling windows make no progress");
+      } else {
+        stuck = 0;
+      }
+      if (done == done_before) W = std::min(256, W * 2);  // a single pop needs a longer window
+    }
+  }
+
+  // ---- phase B: speculative z + parent edge per accepted sample, plus deferred edges -------
+  void evalChunk() {
+    const size_t ns = acc_.size();
+    const size_t nd = deferred_.size();
+    spec_.n = ns;
+    if (ns + nd == 0) return;
+    Arena& in  = t_.dev_->in;
+    Arena& out = t_.dev_->out;
+    const size_t ne = ns + nd;
+    in.reset(Arena::padded(ne * 3 * sizeof(float)) + Arena::padded(ne * 2 * sizeof(float)));
+    out.reset(Arena::padded(ns * sizeof(float)) + Arena::padded(ns) + Arena::padded(ne) + 2 * Arena::padded(ne * sizeof(float)));
+    const size_t o_p1 = in.take(ne * 3 * sizeof(float));
+    const size_t o_p2 = in.take(ne * 2 * sizeof(float));
+    const size_t o_z  = out.take(ns * sizeof(float));
+    const size_t o_t  = out.take(ns);
+    const size_t o_s  = out.take(ne);
+    const size_t o_w  = out.take(ne * sizeof(float));
+    const size_t o_d  = out.take(ne * sizeof(float));
+    float* p1 = in.h<float>(o_p1);
+    float* p2 = in.h<float>(o_p2);
+    size_t k = 0;
+    for (const Pop& p : chunk_) {
+      for (uint32_t j = 0; j < p.acc_count; ++j, ++k) {
+        p1[3 * k] = p.node->pos_.x(); p1[3 * k + 1] = p.node->pos_.y(); p1[3 * k + 2] = p.node->pos_.z();
+        p2[2 * k] = acc_[p.acc_begin + j].x; p2[2 * k + 1] = acc_[p.acc_begin + j].y;
+      }
+    }
+    for (const Deferred& d : deferred_) {
+      p1[3 * k] = d.a->pos_.x(); p1[3 * k + 1] = d.a->pos_.y(); p1[3 * k + 2] = d.a->pos_.z();
+      p2[2 * k] = d.b->pos_.x(); p2[2 * k + 1] = d.b->pos_.y();
+      ++k;
+    }
+    in.h2d(st_);
+    if (ns)
+      K(trgb_nearest_z_launch(map_, in.d<float>(o_p2), (int64_t)ns, out.d<float>(o_z), nullptr, out.d<uint8_t>(o_t)),
+        "trgb_nearest_z_launch");
+    TrgbEdgeParams prm{P_.robot_size, P_.height_threshold, P_.collision_threshold};
+    K(trgb_edge_eval_launch(map_, in.d<float>(o_p1), in.d<float>(o_p2), (int64_t)ne, &prm, out.d<uint8_t>(o_s),
+                            out.d<float>(o_w), out.d<float>(o_d), nullptr),
+      "trgb_edge_eval_launch");
+    out.d2h(st_);
+    cuda_check(cudaStreamSynchronize(st_), "sync(eval)");
+    t_.dev_->batches++;
+    t_.stat_["eval_launches"]++;
+    t_.stat_["nearest_map"] += (int64_t)ns;
+    t_.stat_["edge_evals"] += (int64_t)ne;
+    spec_.z = out.h<float>(o_z);
+    spec_.tie = out.h<uint8_t>(o_t);
+    spec_.stage = out.h<uint8_t>(o_s);
+    spec_.w = out.h<float>(o_w);
+    spec_.d = out.h<float>(o_d);
+    resolveDeferred(spec_.stage + ns, spec_.w + ns, spec_.d + ns);
+  }
+
+  // Resolve every deferred evaluation in call order. An entry with `primary >= 0` is the
+  // opposite-orientation retry of an earlier pending entry: it only counts if that one failed.
+  void resolveDeferred(const uint8_t* stage, const float* w, const float* d) {
+    auto drop = [](TRG::Node* n, TRG::Edge* x) {
+      auto it = std::find(n->edges_.begin(), n->edges_.end(), x);
+      if (it != n->edges_.end()) n->edges_.erase(it);
+    };
+    for (size_t i = 0; i < deferred_.size(); ++i) {
+      Deferred& e = deferred_[i];
+      bool ok = stage[i] == TRGB_EDGE_OK;
+      if (e.primary >= 0 && deferred_[e.primary].ok) ok = false;  // duplicate of an edge that exists
+      e.ok = ok;
+      if (ok) {
+        e.ea->weight_ = e.eb->weight_ = w[i];
+        e.ea->dist_ = e.eb->dist_ = d[i];
+      } else {
+        drop(e.a, e.ea);
+        drop(e.b, e.eb);
+      }
+    }
+    deferred_.clear();
+  }
+
+  // synchronous resolution of everything deferred so far (end of expansion / validity stall)
+  void flushDeferred() {
+    const size_t nd = deferred_.size();
+    if (!nd) return;
+    Arena& in  = t_.dev_->in2;
+    Arena& out = t_.dev_->out2;
+    in.reset(Arena::padded(nd * 3 * sizeof(float)) + Arena::padded(nd * 2 * sizeof(float)));
+    out.reset(Arena::padded(nd) + 2 * Arena::padded(nd * sizeof(float)));
+    const size_t o_p1 = in.take(nd * 3 * sizeof(float));
+    const size_t o_p2 = in.take(nd * 2 * sizeof(float));
+    const size_t o_s  = out.take(nd);
+    const size_t o_w  = out.take(nd * sizeof(float));
+    const size_t o_d  = out.take(nd * sizeof(float));
+    float* p1 = in.h<float>(o_p1);
+    float* p2 = in.h<float>(o_p2);
+    for (size_t k = 0; k < nd; ++k) {
+      const Deferred& d = deferred_[k];
+      p1[3 * k] = d.a->pos_.x(); p1[3 * k + 1] = d.a->pos_.y(); p1[3 * k + 2] = d.a->pos_.z();
+      p2[2 * k] = d.b->pos_.x(); p2[2 * k + 1] = d.b->pos_.y();
+    }
+    in.h2d(st_);
+    TrgbEdgeParams prm{P_.robot_size, P_.height_threshold, P_.collision_threshold};
+    K(trgb_edge_eval_launch(map_, in.d<float>(o_p1), in.d<float>(o_p2), (int64_t)nd, &prm, out.d<uint8_t>(o_s),
+                            out.d<float>(o_w), out.d<float>(o_d), nullptr),
+      "trgb_edge_eval_launch");
+    out.d2h(st_);
+    cuda_check(cudaStreamSynchronize(st_), "sync(flush)");
+    t_.dev_->batches++;
+    t_.stat_["flush_launches"]++;
+    t_.stat_["edge_evals"] += (int64_t)nd;
+    resolveDeferred(out.h<uint8_t>(o_s), out.h<float>(o_w), out.h<float>(o_d));
+  }
+
+  // wireEdge(a, b) against an existing node (trg.cpp:254-370): duplicate check + slope gate now,
+  // geometry in the next batch. Placeholder edges (dist_ < 0 encodes the deferred index,
+  // weight_ -1 on the origin side / -2 on the far side) keep the reference's edge order.
+  // Evaluation is a pure function of the ORIENTED pair, so while (b, a) is pending a call
+  // (a, b) must be kept as a conditional retry: the reference would run it if (b, a) failed.
+  void wireDeferred(TRG::Node* a, TRG::Node* b) {
+    if (a->id_ == b->id_) return;
+    int primary = -1;
+    for (TRG::Edge* e : a->edges_) {
+      if (e->dst_id_ != b->id_) continue;
+      if (e->dist_ >= 0.f) return;          // resolved edge exists
+      if (e->weight_ == -1.f) return;       // same orientation already pending: same outcome
+      primary = (int)(-e->dist_) - 1;       // opposite orientation pending
+    }
+    if (primary < 0) {
+      for (TRG::Edge* e : b->edges_)
+        if (e->dst_id_ == a->id_ && e->dist_ >= 0.f) return;
+    }
+    if (slope_rejects(a->pos_, b->pos_, P_.height_threshold, P_.robot_size)) return;
+    const float tag = -(float)(deferred_.size() + 1);
+    TRG::Edge* ea = t_.newEdge(b->id_, -1.f, tag);
+    TRG::Edge* eb = t_.newEdge(a->id_, -2.f, tag);
+    a->edges_.push_back(ea);
+    b->edges_.push_back(eb);
+    deferred_.push_back({a, b, ea, eb, primary, false});
+  }
+
+  // ---- phase C: commit one pop in the reference's order (trg.cpp:406-452) ------------------
+  void commitPop(const Pop& p, std::deque<TRG::Node*>& bfs) {
+    TRG::Node* node = p.node;
+    t_.draw_next_ = p.draw_start + (size_t)p.consumed;
+    t_.stat_["pops"]++;
+    const TRG::NodeState new_state = (p.ref_id == 0) ? TRG::NodeState::Valid : TRG::NodeState::Frontier;
+    // index of this pop's first sample inside the speculative arrays
+    const size_t s0 = p.acc_begin;
+    for (uint32_t j = 0; j < p.acc_count; ++j) {
+      const Sample& s = acc_[s0 + j];
+      t_.stat_["nearest_node"]++;
+      TRG::Node* ex = t_.nearestNode(g_, s.x, s.y);
+      if (ex->state_ == TRG::NodeState::Invalid) continue;
+      if (norm2(ex->pos_.x() - s.x, ex->pos_.y() - s.y) < P_.robot_size) {
+        wireDeferred(node, ex);
+        continue;
+      }
+      // 2. new node (addNode never fails for id != 0)
+      const size_t si = s0 + j;
+      if (spec_.tie[si]) t_.stat_["z_ties"]++;
+      Eigen::Vector2f pos2(s.x, s.y);
+      TRG::Node* nn = t_.newNode(g_.node_id, pos2, spec_.z[si], new_state);
+      g_.nodes[g_.node_id] = nn;
+      t_.nodeIndexInsert(g_, nn);
+      g_.node_id++;
+      // 2.1 wireEdge(node, new): slope gate on the host, geometry from the speculative batch
+      bool parent_ok = false;
+      if (!slope_rejects(node->pos_, nn->pos_, P_.height_threshold, P_.robot_size) && spec_.stage[si] == TRGB_EDGE_OK) {
+        node->edges_.push_back(t_.newEdge(nn->id_, spec_.w[si], spec_.d[si]));
+        nn->edges_.push_back(t_.newEdge(node->id_, spec_.w[si], spec_.d[si]));
+        parent_ok = true;
+      }
+      // 3. wire to the neighbours within expand_dist, in kd result order
+      if (step3_) {
+        t_.rangeNodesOrdered(g_, nn->pos_.x(), nn->pos_.y(), P_.expand_dist, cand_);
+        for (TRG::Node* en : cand_) {
+          if (en->state_ == TRG::NodeState::Invalid) continue;
+          wireDeferred(nn, en);
+        }
+        if (!parent_ok && !nn->edges_.empty()) {
+          // the node survives only if one of its pending edges does: resolve them now
+          t_.stat_["stalls"]++;
+          flushDeferred();
+        }
+      }
+      // 4.
+      if (nn->edges_.size() < 1) {
+        nn->state_ = TRG::NodeState::Invalid;
+        continue;
+      }
+      bfs.push_back(nn);
+    }
+  }
+
+  struct Spec {
+    size_t n = 0;
+    const float* z = nullptr;
+    const uint8_t* tie = nullptr;
+    const uint8_t* stage = nullptr;
+    const float* w = nullptr;
+    const float* d = nullptr;
+  } spec_;
+
+  TRG& t_;
+  TRG::trgStruct& g_;
+  const decltype(TRG::param_)& P_;
+  trgb_map* map_ = nullptr;
+  cudaStream_t st_ = nullptr;
+  bool step3_ = false;
+  double mean_ = 8.0, var_ = 2.0;
+  std::vector<Pop> chunk_;
+  std::vector<Sample> acc_;
+  std::vector<size_t> guess_;
+  std::vector<Deferred> deferred_;
+  std::vector<TRG::Node*> cand_;
+};
+
+}  // namespace trg_b200
+
+void TRG::runExpansion(const std::vector<Node*>& roots, trgStruct& g) {
+  if (roots.empty()) return;
+  // the device copy of the draw stream is keyed to the global map's stream; make sure it exists
+  trg_b200::Expander ex(*this, g);
+  ex.run(roots);
+  if (&g == &global_trg_) invalidateDeviceGraph();
+}
+
+void TRG::expandGraph(int ref_id, std::string type) {  // trg.cpp:372-454
+  trgStruct& graph = *trgMap_.at(type);
+  std::vector<Node*> roots{graph.nodes.at(ref_id)};
+  runExpansion(roots, graph);
+}
+
+// ================================================================================================
+// build / update / clean
+// ================================================================================================
+void TRG::initGraph(bool /*isPreMap*/, Eigen::Vector3f start3d) {  // trg.cpp:36-64
+  std::lock_guard<std::mutex> lock(mtx.graph);
+  auto t0 = Clock::now();
+  trgStruct& graph = *trgMap_["global"];
+  this->resetGraph(graph.type);
+  requireMap(graph, "initGraph");
+
+  graph.root_pos           = start3d.head(2);
+  Eigen::Vector2f root_pos = graph.root_pos;
+  root_pos.x()             = root_pos.x() + param_.expand_dist;
+  int cnt                  = 0;
+  while (!this->addNode(graph.node_id, root_pos, NodeState::Valid, graph.type)) {
+    if (cnt > 100) throw std::runtime_error("trg_b200: Failed to generate root node");  // reference: exit(1)
+    // g++ evaluates the two constructor arguments right-to-left: y takes the first draw
+    const float ry = param_.expand_dist * nextUniform();
+    const float rx = param_.expand_dist * nextUniform();
+    root_pos = root_pos + Eigen::Vector2f(rx, ry);
+    cnt++;
+  }
+  this->expandGraph(graph.node_id - 1, graph.type);
+  this->cleanGraph(false);
+  secs_["init_graph"] = since(t0);
+}
+
+void TRG::cleanGraph(bool updateLocal) {  // trg.cpp:491-535
+  trgStruct&                     g = *trgMap_["global"];
+  std::unordered_map<int, int>   old2new;
+  std::unordered_map<int, Node*> new_nodes;
+  int                            new_id = 0;
+  for (auto& node : g.nodes) {
+    if (node.second->state_ == NodeState::Invalid || node.second->edges_.size() < 1) continue;
+    new_nodes[new_id]   = node.second;
+    old2new[node.first] = new_id;
+    new_id++;
+  }
+  // the reference collects the ids of Invalid edge targets in a vector and std::find()s every edge
+  // against it (:515); the same predicate is "target node is Invalid", evaluated directly here
+  for (auto& node : new_nodes) {
+    std::vector<Edge*> new_edges;
+    new_edges.reserve(node.second->edges_.size());
+    for (auto& edge : node.second->edges_) {
+      if (g.nodes.at(edge->dst_id_)->state_ == NodeState::Invalid) continue;
+      new_edges.push_back(newEdge(old2new[edge->dst_id_], edge->weight_, edge->dist_));
+    }
+    node.second->edges_ = std::move(new_edges);
+  }
+  for (auto& node : new_nodes) node.second->id_ = node.first;
+  this->resetGraph(g.type);
+  g.nodes   = new_nodes;
+  g.node_id = new_id;
+  for (auto& node : g.nodes) nodeIndexInsert(g, node.second);
+  invalidateDeviceGraph();
+  if (updateLocal) this->setLocalGraph(false);
+}
+
+void TRG::updateGraph() {  // trg.cpp:456-489
+  std::lock_guard<std::mutex> lock(mtx.graph);
+  auto t0 = Clock::now();
+  trgStruct& g = *trgMap_["global"];
+  trgStruct& l = *trgMap_["local"];
+  // the per-node tests are pure functions of (node, local map, node set at entry): batch them
+  std::vector<Node*> order;
+  std::vector<float> xy, chk;
+  std::vector<uint8_t> far;
+  for (auto& node : l.nodes) {
+    Node* n = node.second;
+    order.push_back(n);
+    xy.push_back(n->pos_.x());
+    xy.push_back(n->pos_.y());
+    Eigen::Vector2f npos2d = n->pos_.head(2);
+    far.push_back((npos2d - l.root_pos).norm() > 2.0 * param_.expand_dist ? 1 : 0);
+    Eigen::Vector2f dir = npos2d - l.root_pos;  // isFrontier probe (trg.cpp:783-787)
+    dir.normalize();
+    Eigen::Vector2f check = npos2d + 2 * param_.robot_size * dir;
+    chk.push_back(check.x());
+    chk.push_back(check.y());
+  }
+  const int64_t n = (int64_t)order.size();
+  std::vector<uint8_t> coll(n, 1);
+  std::vector<int32_t> lcnt(n, 0);
+  if (n > 0 && l.map_index) {
+    K(trgb_collision_batch(l.map_index, xy.data(), n, param_.robot_size, param_.height_threshold,
+                           param_.update_collision_threshold, coll.data()), "trgb_collision_batch");
+    K(trgb_range_count_batch(l.map_index, chk.data(), n, (float)(0.5 * param_.robot_size), lcnt.data()),
+      "trgb_range_count_batch");
+  }
+  std::vector<Node*> expand_queue;
+  for (int64_t i = 0; i < n; ++i) {
+    Node* node = order[i];
+    if (far[i]) {
+      if (coll[i] || node->edges_.size() < 1) {
+        node->state_ = NodeState::Invalid;
+        continue;
+      }
+    }
+    const bool frontier = countNodesInRange(g, chk[2 * i], chk[2 * i + 1], param_.robot_size) == 0 && lcnt[i] == 0;
+    if (frontier && node->state_ == NodeState::Frontier) {
+      node->state_ = NodeState::Frontier;
+      expand_queue.push_back(node);
+      continue;
+    }
+    expand_queue.push_back(node);
+    node->state_ = NodeState::Valid;
+  }
+  runExpansion(expand_queue, g);  // == expandGraph(node->id_, "global") for each, in order
+  this->cleanGraph(true);
+  secs_["update_graph"] = since(t0);
+}
+
+// ================================================================================================
+// path queries
+// ================================================================================================
+void TRG::invalidateDeviceGraph() {
+  if (dev_graph_) trgb_graph_destroy(dev_graph_);
+  dev_graph_ = nullptr;
+  dev_graph_nodes_.clear();
+}
+
+void TRG::ensureDeviceGraph() {
+  if (dev_graph_) return;
+  trgStruct& g = *trgMap_["global"];
+  int max_id = -1;
+  for (auto& kv : g.nodes) max_id = std::max(max_id, kv.first);
+  const int n = max_id + 1;
+  if (n <= 0) throw std::runtime_error("trg_b200: planSafePath on an empty graph");
+  dev_graph_nodes_.assign(n, nullptr);
+  for (auto& kv : g.nodes) dev_graph_nodes_[kv.first] = kv.second;
+  std::vector<int64_t> row(n + 1, 0);
+  for (int i = 0; i < n; ++i) row[i + 1] = row[i] + (dev_graph_nodes_[i] ? (int64_t)dev_graph_nodes_[i]->edges_.size() : 0);
+  const int64_t e = row[n];
+  std::vector<int32_t> col(e), state(n, -1);
+  std::vector<float> w(e), d(e), pos(3 * (size_t)n, 0.f);
+  for (int i = 0; i < n; ++i) {
+    Node* nd = dev_graph_nodes_[i];
+    if (!nd) continue;
+    state[i] = (int32_t)nd->state_;
+    pos[3 * i] = nd->pos_.x(); pos[3 * i + 1] = nd->pos_.y(); pos[3 * i + 2] = nd->pos_.z();
+    int64_t k = row[i];
+    for (Edge* ed : nd->edges_) {
+      col[k] = ed->dst_id_; w[k] = ed->weight_; d[k] = ed->dist_;
+      ++k;
+    }
+  }
+  TrgbGraphDesc desc{n, e, row.data(), col.data(), w.data(), d.data(), pos.data(), state.data()};
+  K(trgb_graph_upload(&dev_graph_, &desc), "trgb_graph_upload");
+}
+
+void TRG::setGoalUnlocked(Eigen::Vector3f& goal) {  // trg.cpp:537-565
+  trgStruct& g = *trgMap_["global"];
+  goal_.pose3d = goal;
+  goal_.pose2d = goal.head(2);
+  static thread_local std::vector<Node*> res;
+  rangeNodesOrdered(g, goal.x(), goal.y(), param_.robot_size, res);
+  if (res.empty()) {
+    float min_dist = std::numeric_limits<float>::max();
+    for (auto& node : g.nodes) {
+      float dist = norm2(node.second->pos_.x() - goal.x(), node.second->pos_.y() - goal.y());
+      if (dist < min_dist) {
+        min_dist   = dist;
+        goal_.node = node.second;
+      }
+    }
+    goal_.isKnown = false;
+  } else {
+    goal_.node    = res[0];  // head of the kd result list = last node the traversal visited
+    goal_.isKnown = true;
+  }
+}
+
+void TRG::setGoal(Eigen::Vector3f& goal) { setGoalUnlocked(goal); }
+
+bool TRG::checkReadched(Eigen::Vector2f& pos2d) {  // trg.cpp:567-574
+  float dist = (goal_.pose2d - pos2d).norm();
+  return dist < param_.goal_tolerance;
+}
+
+bool TRG::checkReplan(Eigen::Vector2f& pos2d, std::vector<Eigen::Vector3f>& path) {  // trg.cpp:576-601
+  if (goal_.node == nullptr) return false;
+  float dist2subgoal = norm2(goal_.node->pos_.x() - pos2d.x(), goal_.node->pos_.y() - pos2d.y());
+  if (!goal_.isKnown && dist2subgoal < param_.goal_tolerance) return true;
+  if (!goal_.isKnown && goal_.node->state_ != NodeState::Frontier) return true;
+  trgStruct& g = *trgMap_["global"];
+  for (auto& pt : path)
+    if (countNodesInRange(g, pt.x(), pt.y(), param_.robot_size) == 0) return true;
+  return false;
+}
+
+bool TRG::planSafePath(Eigen::Vector2f& start2d, Eigen::Vector3f& goal_pose, std::vector<Eigen::Vector3f>& out_path,
+                       float& direct_dist, float& path_length, float& avg_risk) {  // trg.cpp:603-690
+  std::lock_guard<std::mutex> lock(mtx.graph);
+  auto t0 = Clock::now();
+  last_path_ids_.clear();
+  trgStruct& g = *trgMap_["global"];
+  if (g.nodes.empty()) return false;
+  this->setGoalUnlocked(goal_pose);
+  Node* start_node = nearestNode(g, start2d.x(), start2d.y());
+  direct_dist = norm2(goal_.node->pos_.x() - start_node->pos_.x(), goal_.node->pos_.y() - start_node->pos_.y());
+  ensureDeviceGraph();
+  const int32_t s = start_node->id_, t = goal_.node->id_;
+  uint8_t found = 0;
+  float cost = 0.f, plen = 0.f, risk = 0.f;
+  int64_t offs[2] = {0, 0};
+  std::vector<int32_t> ids(std::max<size_t>(1024, 64));
+  int rc = trgb_sssp_batch(dev_graph_, &s, &t, 1, param_.safety_factor, &found, &cost, &plen, &risk, offs, ids.data(),
+                           (int64_t)ids.size());
+  if (rc == TRGB_E_NOMEM && offs[1] > (int64_t)ids.size()) {
+    ids.resize((size_t)offs[1]);
+    rc = trgb_sssp_batch(dev_graph_, &s, &t, 1, param_.safety_factor, &found, &cost, &plen, &risk, offs, ids.data(),
+                         (int64_t)ids.size());
+  }
+  K(rc, "trgb_sssp_batch");
+  secs_["plan"] = since(t0);
+  if (!found) return false;
+  for (int64_t k = offs[0]; k < offs[1]; ++k) {
+    out_path.push_back(dev_graph_nodes_[ids[k]]->pos_);
+    last_path_ids_.push_back(ids[k]);
+  }
+  path_length = plen;
+  avg_risk    = risk;
+  return true;
+}
+
+void TRG::planSafePathBatch(const float* queries, int64_t n, PathBatch& out) {
+  std::lock_guard<std::mutex> lock(mtx.graph);
+  auto t0 = Clock::now();
+  trgStruct& g = *trgMap_["global"];
+  out = PathBatch();
+  out.found.assign(n, 0); out.goal_known.assign(n, 0);
+  out.cost.assign(n, 0.f); out.path_length.assign(n, 0.f); out.avg_risk.assign(n, 0.f); out.direct_dist.assign(n, 0.f);
+  out.offsets.assign(n + 1, 0);
+  if (n <= 0 || g.nodes.empty()) return;
+  ensureDeviceGraph();
+  std::vector<int32_t> s(n), t(n);
+  for (int64_t i = 0; i < n; ++i) {
+    const float* q = queries + 5 * i;
+    Eigen::Vector3f goal(q[2], q[3], q[4]);
+    setGoalUnlocked(goal);
+    Node* st = nearestNode(g, q[0], q[1]);
+    s[i] = st->id_;
+    t[i] = goal_.node->id_;
+    out.goal_known[i] = goal_.isKnown ? 1 : 0;
+    out.direct_dist[i] = norm2(goal_.node->pos_.x() - st->pos_.x(), goal_.node->pos_.y() - st->pos_.y());
+  }
+  secs_["plan_snap"] = since(t0);
+  size_t cap = std::max<size_t>((size_t)1 << 20, (size_t)n * 1024);
+  out.node_ids.resize(cap);
+  int rc = trgb_sssp_batch(dev_graph_, s.data(), t.data(), n, param_.safety_factor, out.found.data(), out.cost.data(),
+                           out.path_length.data(), out.avg_risk.data(), out.offsets.data(), out.node_ids.data(), (int64_t)cap);
+  if (rc == TRGB_E_NOMEM && out.offsets[n] > (int64_t)cap) {
+    cap = (size_t)out.offsets[n];
+    out.node_ids.resize(cap);
+    rc = trgb_sssp_batch(dev_graph_, s.data(), t.data(), n, param_.safety_factor, out.found.data(), out.cost.data(),
+                         out.path_length.data(), out.avg_risk.data(), out.offsets.data(), out.node_ids.data(), (int64_t)cap);
+  }
+  K(rc, "trgb_sssp_batch");
+  out.node_ids.resize((size_t)out.offsets[n]);
+  secs_["plan_batch"] = since(t0);
+}
+
+void TRG::refinePath(std::vector<Eigen::Vector3f>& in_path, std::vector<Eigen::Vector3f>& out_path) {  // trg.cpp:692-730
+  // point_between == 1 in the reference: every interior point is emitted twice, then a 3-tap mean
+  std::vector<Eigen::Vector3f> dense;
+  for (int i = 0; i + 1 < (int)in_path.size(); ++i) {
+    dense.push_back(in_path[i]);
+    dense.push_back(in_path[i + 1]);
+  }
+  std::vector<Eigen::Vector3f> smooth;
+  const int m = (int)dense.size();
+  for (int i = 0; i < m; ++i) {
+    if (i == m - 1) {
+      smooth.push_back(dense[i]);
+      break;
+    }
+    Eigen::Vector3f sum(0.f, 0.f, 0.f);
+    int cnt = 0;
+    for (int j = i - 1; j < i + 2; ++j) {
+      if (j < 0 || j >= m) continue;
+      sum += dense[j];
+      cnt++;
+    }
+    smooth.push_back(sum / (float)cnt);
+  }
+  out_path = smooth;
+}
+
+// ================================================================================================
+// accessors
+// ================================================================================================
+std::unordered_map<int, TRG::Node*> TRG::getGraph(std::string type) { return trgMap_.at(type)->nodes; }  // trg.cpp:805-808
+
+std::unordered_map<int, TRG::Node*> TRG::getGraphCopy(std::string type) {  // trg.cpp:810-824
+  std::lock_guard<std::mutex>         lock(mtx.graph);
+  std::unordered_map<int, TRG::Node*> nodes_copy;
+  trgStruct&                          graph = *trgMap_.at(type);
+  for (auto& node : graph.nodes) {
+    Eigen::Vector2f pos = node.second->pos_.head(2);
+    Node* node_copy = new Node(node.second->id_, pos, node.second->pos_.z(), node.second->state_);
+    for (auto& edge : node.second->edges_) node_copy->edges_.push_back(new Edge(edge->dst_id_, edge->weight_, edge->dist_));
+    nodes_copy[node.first] = node_copy;
+  }
+  return nodes_copy;
+}
+
+void TRG::lockGraph() { mtx.graph.lock(); }
+void TRG::unlockGraph() { mtx.graph.unlock(); }
+
+double TRG::lastSeconds(const std::string& what) const {
+  auto it = secs_.find(what);
+  return it == secs_.end() ? -1.0 : it->second;
+}
+int64_t TRG::stat(const std::string& what) const {
+  if (what == "rng_draws") return (int64_t)draw_next_;
+  if (what == "batches") return (int64_t)dev_->batches;
+  auto it = stat_.find(what);
+  return it == stat_.end() ? 0 : it->second;
+}
+trgb_map* TRG::deviceMap(const std::string& type) { return trgMap_.at(type)->map_index; }

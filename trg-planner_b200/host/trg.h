@@ -203,32 +203,50 @@ class TRG {
 
  private:
   friend class trg_b200::Expander;
-  // buffered view of (gen_, distr_): draw k of the stream, generated on demand, consumed in order
+  // Buffered view of (gen_, distr_): position k of the stream, generated on demand in blocks and
+  // consumed strictly in order. The sampling-window kernel reads the derived offsets
+  // (expand_dist*cosf(angle_k), expand_dist*sinf(angle_k)) from a device-resident copy.
   float nextUniform();
   void  ensureDraws(size_t upto);
-  std::vector<float> draw_u_;          // u_k for k >= draw_base_
-  std::vector<float> draw_cx_, draw_cy_;  // expand_dist*cosf(angle_k), expand_dist*sinf(angle_k)
-  size_t draw_base_ = 0;               // stream index of draw_u_[0]
-  size_t draw_next_ = 0;               // next unconsumed stream index
+  void  compactDraws();
+  void  syncDraws();
+  std::vector<float> draw_u_;   // u_k for k >= draw_base_
+  std::vector<float> draw_xy_;  // 2 per draw
+  size_t draw_base_ = 0;        // stream index of draw_u_[0]
+  size_t draw_next_ = 0;        // next unconsumed stream index
 
   void nodeIndexInsert(trgStruct& g, Node* n);
   void nodeIndexReset(trgStruct& g);
+  void ensureGrid(trgStruct& g);
   void ensureTree(trgStruct& g);
   Node* nearestNode(trgStruct& g, float x, float y);
   void rangeNodesOrdered(trgStruct& g, float x, float y, float r, std::vector<Node*>& out);
+  int  countNodesInRange(trgStruct& g, float x, float y, float r);
   void buildMapIndex(trgStruct& g, const float* xyz, int64_t n, int stride, bool device);
+  trgb_map* requireMap(trgStruct& g, const char* who);
   void invalidateDeviceGraph();
   void ensureDeviceGraph();
   Node* newNode(int id, Eigen::Vector2f& p, float z, NodeState s);
   Edge* newEdge(int dst, float w, float d);
+  void setGoalUnlocked(Eigen::Vector3f& goal);
+  void runExpansion(const std::vector<Node*>& roots, trgStruct& g);
 
   std::unique_ptr<trg_b200::DeviceSession> dev_;
   trgb_graph* dev_graph_ = nullptr;
+  std::vector<Node*> dev_graph_nodes_;  // row -> node of the uploaded CSR
   std::deque<Node> node_pool_;
   std::deque<Edge> edge_pool_;
   std::unordered_map<std::string, double>  secs_;
   std::unordered_map<std::string, int64_t> stat_;
   std::vector<int32_t> last_path_ids_;
+
+ public:
+  // [+] tuning knobs of the wavefront scheduler (defaults are fine; exposed for benchmarks)
+  struct Tuning {
+    int chunk_nodes = 2048;   // pops evaluated per batch
+    int window = 128;         // sampling-window draws per node (<= 256)
+    float map_cell_scale = 0.5f;  // map index cell = map_cell_scale * robot_size
+  } tuning_;
 };
 
 #endif  // TRG_PLANNER_B200_HOST_TRG_H_
