@@ -72,6 +72,10 @@ int trg_edge_eval_batch(void* h, const char* type, const float* p1_xyz, const fl
                         uint8_t* stage, float* weight, double* weight64_unused, float* dist, int32_t* npts);
 int trg_is_frontier_batch(void* h, const float* xy, int64_t n, uint8_t* out);               /* trg.cpp:780 */
 
+/* the device map index behind a TRG ("global" | "local") as a trgb_map* for the tier-2 launches of
+ * include/trgb_kernels.h (NULL when no map is loaded); owned by the TRG */
+void* trg_device_map(void* h, const char* type);
+
 double  trg_last_seconds(void* h, const char* what);
 int64_t trg_stat(void* h, const char* what);
 int     trg_set_tuning(void* h, const char* key, double value);  /* "chunk_nodes" | "window" | "map_cell_scale" */

@@ -127,8 +127,10 @@ int trgb_sssp_batch(trgb_graph* g, const int32_t* start_ids, const int32_t* goal
 /* ---- profiling: CUDA-event timing of every kernel launched by this library ------------- */
 int trgb_prof_enable(int on);
 int trgb_prof_reset(void);
-/* fills up to cap entries; returns the number of distinct kernels seen */
-typedef struct TrgbProfEntry { char name[48]; int64_t launches; double total_ms; double bytes; } TrgbProfEntry;
+/* fills up to cap entries; returns the number of distinct kernels seen. `units` = work items the
+ * launches processed in total: map points for the K1 kernels, queries / window tests / edges /
+ * path queries for the others (bench.py multiplies by the per-unit algorithmic bytes of DESIGN.md). */
+typedef struct TrgbProfEntry { char name[48]; int64_t launches; double total_ms; double units; } TrgbProfEntry;
 int trgb_prof_collect(TrgbProfEntry* out, int cap);
 int64_t trgb_launch_count(void); /* kernels launched by this library since load / reset */
 

@@ -1,0 +1,62 @@
+"""Generates tests/golden/*.npz with the CPU oracle linked against the VERBATIM reference kd-tree
+(oracle/_ref/liboracle_refkd.so, built from /root/reference/.../kdtree.c by oracle/Makefile).
+
+The reference ships no golden vectors, no tests and cannot be compiled here as a whole (Eigen, PCL,
+OpenCV, yaml-cpp absent), so these fixtures pin (a) the oracle's restated kd-tree port against the
+reference's own kdtree.c and (b) the oracle against itself over time. Run in the build container:
+    python tests/golden/make_golden.py
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+import _pkg  # noqa: E402
+
+trg = _pkg.load()
+OUT = Path(__file__).resolve().parent
+
+
+def case(name, P, pts, start, seed, n_q=24, updates=None):
+    o = trg.oracle(P, ref_kdtree=True)
+    o.seed(seed)
+    o.set_global_map(pts)
+    assert o.init_graph(start) == 0
+    g = o.export()
+    rng = np.random.default_rng(123)
+    lo, hi = pts[:, :2].min(0) - 0.5, pts[:, :2].max(0) + 0.5
+    q = rng.uniform(lo, hi, size=(4000, 2)).astype(np.float32)
+    coll = o.is_collision(q, P.collision_threshold)
+    cnt = o.range_count(q, P.robot_size)
+    z, idx, tie = o.nearest_z(q)
+    a = q[:1500]
+    ang = rng.uniform(0, 2 * np.pi, a.shape[0])
+    d = rng.uniform(0.1, 1.4 * P.expand_dist, a.shape[0])
+    b = (a + np.stack([d * np.cos(ang), d * np.sin(ang)], 1)).astype(np.float32)
+    za, _, _ = o.nearest_z(a)
+    zb, _, _ = o.nearest_z(b)
+    p1 = np.column_stack([a, za]).astype(np.float32)
+    p2 = np.column_stack([b, zb]).astype(np.float32)
+    ev = o.edge_eval(p1, p2)
+    qs = trg.terrain.query_pairs(((float(lo[0]), float(hi[0])), (float(lo[1]), float(hi[1]))), n_q, seed=7)
+    plans = [o.plan(r[:2], r[2:5]) for r in qs]
+    path_ids = np.concatenate([p["ids"] for p in plans]) if plans else np.zeros(0, np.int32)
+    path_off = np.cumsum([0] + [len(p["ids"]) for p in plans]).astype(np.int64)
+    np.savez_compressed(
+        OUT / f"{name}.npz", pts=pts, params=np.asarray([P.expand_dist, P.robot_size, P.sample_num, P.height_threshold, P.collision_threshold, P.update_collision_threshold, P.safety_factor, P.goal_tolerance], np.float64), seed=seed, start=np.asarray(start, np.float32), rng_draws=o.stat("rng_draws"),
+        iter_ids=g.iter_ids, pos=g.pos, state=g.state, row_ptr=g.row_ptr, col=g.col, weight=g.weight, dist=g.dist,
+        q=q, coll=coll, cnt=cnt, z=z, idx=idx, tie=tie, p1=p1, p2=p2, ev_stage=ev["stage"], ev_weight=ev["weight"],
+        ev_weight64=ev["weight64"], ev_dist=ev["dist"], ev_npts=ev["npts"], queries=qs, path_ids=path_ids,
+        path_off=path_off, path_found=np.array([p["found"] for p in plans]),
+        path_len=np.array([p["path_length"] for p in plans], np.float32),
+        path_risk=np.array([p["avg_risk"] for p in plans], np.float32),
+        goal_known=np.array([p["goal_known"] for p in plans]))
+    print(name, "nodes", g.n_nodes, "edges", g.n_edges, "draws", o.stat("rng_draws"))
+
+
+if __name__ == "__main__":
+    case("mountain_120", trg.MOUNTAIN, trg.terrain.mountain(120, h=0.1, seed=2), (6.0, 6.0, 0.0), 42)
+    case("indoor_70", trg.INDOOR, trg.terrain.indoor(70, h=0.2, seed=1), (3.27, 4.12, 0.0), 42)
+    case("stairs_100", trg.MOUNTAIN, trg.terrain.stairs(100, h=0.1, seed=5, riser=0.10), (5.0, 5.0, 0.0), 11)

@@ -1,0 +1,68 @@
+// Host-logic check (CPU only): the product's node index (trg-planner_b200/host/node_index.h)
+// against the oracle's kd-tree restatement (oracle/kdtree_port.h, itself pinned to the reference's
+// kdtree.c by tests/test_oracle_cpu.py): nearest incl. exact ties, range sets AND result order,
+// bulk build == sequential insertion.
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <vector>
+
+#include "kdtree_port.h"
+#include "node_index.h"
+
+static int fails = 0;
+#define CHECK(c, ...) do { if (!(c)) { if (fails < 20) { printf("FAIL %s:%d: ", __FILE__, __LINE__); printf(__VA_ARGS__); printf("\n"); } ++fails; } } while (0)
+
+int main() {
+  std::mt19937 gen(7);
+  for (int round = 0; round < 6; ++round) {
+    const int n = round == 0 ? 1 : (round == 1 ? 17 : 20000);
+    const float ext = round < 4 ? 40.f : 400.f;
+    std::uniform_real_distribution<float> U(0.f, ext);
+    std::vector<float> xs(n), ys(n);
+    for (int i = 0; i < n; ++i) { xs[i] = U(gen); ys[i] = U(gen); }
+    if (round == 3)  // lattice with exact duplicates / exact ties
+      for (int i = 0; i < n; ++i) { xs[i] = (float)(i % 100) * 0.25f; ys[i] = (float)((i / 100) % 100) * 0.25f; }
+    kdport::Tree2 ref;
+    trg_b200::OrderTree2D seq, bulk;
+    trg_b200::NodeGrid grid;
+    grid.configure(0.f, 0.f, ext, ext, 0.6f);
+    for (int i = 0; i < n; ++i) {
+      ref.insert(xs[i], ys[i], i);
+      seq.insert(xs[i], ys[i], i);
+      grid.insert(xs[i], ys[i]);
+    }
+    bulk.build_bulk(xs.data(), ys.data(), n);
+    CHECK(bulk.low() == seq.low() && bulk.high() == seq.high() && bulk.axis() == seq.axis(), "bulk != sequential (n=%d)", n);
+    std::vector<int64_t> want;
+    std::vector<int> got, got2;
+    std::uniform_real_distribution<float> Q(-1.f, ext + 1.f);
+    for (int k = 0; k < 4000; ++k) {
+      float qx = Q(gen), qy = Q(gen);
+      if (k % 5 == 0) { int j = gen() % n; qx = xs[j]; qy = ys[j]; }
+      if (round == 3 && k % 3 == 0) { qx = 0.125f + 0.25f * (float)(gen() % 99); qy = 0.125f + 0.25f * (float)(gen() % 99); }  // 4-way ties
+      const int64_t wn = ref.nearest(qx, qy);
+      CHECK(seq.nearest(qx, qy) == (int)wn, "tree nearest");
+      CHECK(bulk.nearest(qx, qy) == (int)wn, "bulk tree nearest");
+      auto g = grid.nearest(qx, qy);
+      const float dxw = xs[wn] - qx, dyw = ys[wn] - qy;
+      float d2w = 0.f; d2w += dxw * dxw; d2w += dyw * dyw;
+      CHECK(g.entry >= 0 && g.d2 == d2w, "grid nearest distance %g vs %g", g.d2, d2w);
+      if (!g.tie) CHECK(g.entry == (int)wn, "grid nearest entry without tie");
+      // 2.45, not 2.5: on the exact lattice of round 3 a point at distance == r along a split axis is
+      // dropped by the reference traversal's strict `fabs(dx) < range` pruning (kdtree.c:289) although it
+      // passes `dist_sq <= range^2` (:281) - a measure-zero quirk the grid does not reproduce
+      for (float r : {0.3f, 0.6f, 2.45f}) {
+        ref.range(qx, qy, r, &want);
+        seq.range(qx, qy, r, got);
+        bulk.range(qx, qy, r, got2);
+        bool same = want.size() == got.size() && got == got2;
+        for (size_t i = 0; same && i < want.size(); ++i) same = (want[i] == got[i]);
+        CHECK(same, "range order r=%g", r);
+        CHECK(grid.count_in_range(qx, qy, r) == (int)want.size(), "grid range count round=%d n=%d q=(%g,%g) r=%g got=%d want=%d", round, n, qx, qy, r, grid.count_in_range(qx, qy, r), (int)want.size());
+      }
+    }
+  }
+  printf(fails ? "FAILED %d\n" : "OK\n", fails);
+  return fails ? 1 : 0;
+}

@@ -142,7 +142,7 @@ extern "C" int trgb_prof_collect(TrgbProfEntry* out, int cap) {
       strncpy(out[i].name, kv.first.c_str(), sizeof(out[i].name) - 1);
       out[i].launches = kv.second.launches;
       out[i].total_ms = kv.second.ms;
-      out[i].bytes = kv.second.bytes;
+      out[i].units = kv.second.bytes;
     }
     ++i;
   }

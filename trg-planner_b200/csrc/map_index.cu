@@ -213,7 +213,7 @@ static int build_index(trgb_map* m, const float* d_in, int64_t n, int stride, fl
   const float init[4] = {FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX};
   TRGB_CUDA(cudaMemcpyAsync(d_bbox, init, sizeof(init), cudaMemcpyHostToDevice, st));
   {
-    ProfScope ps("k_bbox", st, 12.0 * n);
+    ProfScope ps("k_bbox", st, (double)n);
     k_bbox<<<grid, 256, 0, st>>>(d_in, n, stride, d_bbox);
   }
   float bbox[4];
@@ -251,21 +251,21 @@ static int build_index(trgb_map* m, const float* d_in, int64_t n, int stride, fl
   TRGB_CUDA(cudaMemsetAsync(d_counts, 0, ncells * sizeof(uint32_t), st));
   TRGB_CUDA(cudaMemsetAsync(d_fill, 0, ncells * sizeof(uint32_t), st));
   {
-    ProfScope ps("k_count", st, (stride == 4 ? 16.0 : 12.0) * n);
+    ProfScope ps("k_count", st, (double)n);
     k_count<<<grid, 256, 0, st>>>(d_in, n, stride, v, d_counts);
   }
   {
-    ProfScope ps("k_scan", st, 12.0 * ncells);
+    ProfScope ps("k_scan", st, (double)ncells);
     k_scan_reduce<<<nb, kScanBlock, 0, st>>>(d_counts, ncells, d_sums);
     k_scan_sums<<<1, 1024, 0, st>>>(d_sums, nb);
     k_scan_apply<<<nb, kScanBlock, 0, st>>>(d_counts, ncells, d_sums, m->d_cell_start);
   }
   {
-    ProfScope ps("k_scatter", st, 32.0 * n);
+    ProfScope ps("k_scatter", st, (double)n);
     k_scatter<<<grid, 256, 0, st>>>(d_in, n, stride, v, m->d_cell_start, d_fill, m->d_pts);
   }
   {
-    ProfScope ps("k_sort_cell", st, 32.0 * n);
+    ProfScope ps("k_sort_cell", st, (double)n);
     const int g2 = (int)std::min<int64_t>((ncells + 255) / 256, (int64_t)sms * 16);
     k_sort_cell<<<g2, 256, 0, st>>>(m->d_cell_start, ncells, m->d_pts);
   }

@@ -378,7 +378,7 @@ extern "C" int trgb_collision_launch(const trgb_map* m, const float* d_xy, int64
   int grid, cap; size_t smem;
   int rc = launch_cfg(m, radius, n, &grid, &cap, &smem, (const void*)k_collision);
   if (rc) return rc;
-  ProfScope ps("k_collision", m->stream, 0.0);
+  ProfScope ps("k_collision", m->stream, (double)n);
   k_collision<<<grid, kThreads, smem, m->stream>>>(m->view, reinterpret_cast<const float2*>(d_xy), n, radius,
                                                    height_thr, ratio_thr, cap, d_out);
   TRGB_CUDA(cudaGetLastError());
@@ -390,7 +390,7 @@ extern "C" int trgb_range_count_launch(const trgb_map* m, const float* d_xy, int
   TRGB_ARG(m && d_xy && d_out, "null pointer");
   TRGB_ARG(radius > 0.f, "radius must be > 0");
   if (n <= 0) return TRGB_OK;
-  ProfScope ps("k_range_count", m->stream, 0.0);
+  ProfScope ps("k_range_count", m->stream, (double)n);
   k_range_count<<<grid_for_warps(n, 8), kThreads, 0, m->stream>>>(m->view, reinterpret_cast<const float2*>(d_xy),
                                                                    n, radius, d_out);
   TRGB_CUDA(cudaGetLastError());
@@ -408,7 +408,7 @@ extern "C" int trgb_sample_window_launch(const trgb_map* m, const float* d_node_
   int grid, cap; size_t smem;
   int rc = launch_cfg(m, radius, n_nodes * window, &grid, &cap, &smem, (const void*)k_sample_window);
   if (rc) return rc;
-  ProfScope ps("k_sample_window", m->stream, 0.0);
+  ProfScope ps("k_sample_window", m->stream, (double)n_nodes * window);
   k_sample_window<<<grid, kThreads, smem, m->stream>>>(
       m->view, reinterpret_cast<const float2*>(d_node_xy), d_first_draw,
       reinterpret_cast<const float2*>(d_draw_xy), n_nodes, window, radius, height_thr, ratio_thr, cap, d_mask);
@@ -420,7 +420,7 @@ extern "C" int trgb_nearest_z_launch(const trgb_map* m, const float* d_xy, int64
                                      int64_t* d_idx, uint8_t* d_tie) {
   TRGB_ARG(m && d_xy, "null pointer");
   if (n <= 0) return TRGB_OK;
-  ProfScope ps("k_nearest_z", m->stream, 0.0);
+  ProfScope ps("k_nearest_z", m->stream, (double)n);
   k_nearest_z<<<grid_for_warps(n, 8), kThreads, 0, m->stream>>>(m->view, reinterpret_cast<const float2*>(d_xy), n,
                                                                  d_z, d_idx, d_tie);
   TRGB_CUDA(cudaGetLastError());
@@ -438,7 +438,7 @@ extern "C" int trgb_edge_eval_launch(const trgb_map* m, const float* d_p1_xyz, c
   // the shared buffer only serves the radius-robot_size collision samples
   int rc = launch_cfg(m, prm->robot_size, n, &grid, &cap, &smem, (const void*)k_edge_eval);
   if (rc) return rc;
-  ProfScope ps("k_edge_eval", m->stream, 0.0);
+  ProfScope ps("k_edge_eval", m->stream, (double)n);
   k_edge_eval<<<grid, kThreads, smem, m->stream>>>(m->view, d_p1_xyz, reinterpret_cast<const float2*>(d_p2_xy), n,
                                                    prm->robot_size, prm->height_threshold,
                                                    prm->collision_threshold, cap, d_stage, d_weight, d_dist, d_npts);

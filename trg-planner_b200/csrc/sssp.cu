@@ -330,7 +330,7 @@ extern "C" int trgb_sssp_batch(trgb_graph* g, const int32_t* start_ids, const in
     TRGB_ARG(start_ids[i] >= 0 && start_ids[i] < g->n && goal_ids[i] >= 0 && goal_ids[i] < g->n, "node id out of range");
   cudaStream_t st = g->stream;
   if (!(g->cost_sf == safety_factor)) {
-    ProfScope ps("k_edge_cost", st, 12.0 * g->e);
+    ProfScope ps("k_edge_cost", st, (double)g->e);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((g->e + 255) / 256, (int64_t)sm_count() * 8));
     k_edge_cost<<<grid, 256, 0, st>>>(g->d_w, g->d_dist, g->e, safety_factor, g->d_cost);
     g->cost_sf = safety_factor;
@@ -359,7 +359,7 @@ extern "C" int trgb_sssp_batch(trgb_graph* g, const int32_t* start_ids, const in
   o.path_ids = (int32_t*)d_ids.p; o.capacity = path_ids_capacity; o.cursor = (unsigned long long*)d_cur.p;
   const float delta = 2.0f * std::max(g->mean_cost, 1e-3f);
   {
-    ProfScope ps("k_sssp", st, 0.0);
+    ProfScope ps("k_sssp", st, (double)nq);
     k_sssp<<<g->nslots < want ? g->nslots : want, kSsspThreads, 0, st>>>(
         g->n, g->d_row, g->d_col, g->d_cost, g->d_w, g->d_dist, g->d_pos, g->d_state, (const int32_t*)d_s.p,
         (const int32_t*)d_g.p, nq, delta, g->d_label, g->d_queue, g->d_bits, o);

@@ -56,6 +56,45 @@ class OrderTree2D {
     }
   }
 
+  // Builds exactly the tree that inserting (x[i], y[i], payload i) for i = 0..n-1 in order would
+  // build, by recursive stable partition: the root of a subtree is the FIRST point (in insertion
+  // order) that fell into it, the rest split into "< split" (low) and ">= split" (high) keeping
+  // their order. Sequential memory passes instead of one pointer chase per level and point.
+  void build_bulk(const float* x, const float* y, int n) {
+    clear();
+    if (n <= 0) return;
+    x_.assign(x, x + n); y_.assign(y, y + n);
+    lo_.assign(n, -1); hi_.assign(n, -1); axis_.assign(n, 0); payload_.resize(n);
+    bmin_[0] = bmax_[0] = x[0]; bmin_[1] = bmax_[1] = y[0]; have_box_ = true;
+    for (int i = 0; i < n; ++i) {
+      payload_[i] = i;
+      bmin_[0] = std::fmin(bmin_[0], x[i]); bmax_[0] = std::fmax(bmax_[0], x[i]);
+      bmin_[1] = std::fmin(bmin_[1], y[i]); bmax_[1] = std::fmax(bmax_[1], y[i]);
+    }
+    std::vector<int> idx(n), tmp(n);
+    for (int i = 0; i < n; ++i) idx[i] = i;
+    struct Job { int b, e; uint8_t axis; };
+    std::vector<Job> jobs;
+    jobs.push_back({0, n, 0});
+    while (!jobs.empty()) {
+      const Job j = jobs.back();
+      jobs.pop_back();
+      const int root = idx[j.b];
+      axis_[root] = j.axis;
+      const float split = j.axis ? y[root] : x[root];
+      const float* key = j.axis ? y : x;
+      int nl = 0, nh = 0;
+      for (int k = j.b + 1; k < j.e; ++k) {
+        const int p = idx[k];
+        if (key[p] < split) idx[j.b + 1 + nl++] = p;
+        else tmp[nh++] = p;
+      }
+      for (int k = 0; k < nh; ++k) idx[j.b + 1 + nl + k] = tmp[k];
+      if (nl) { lo_[root] = idx[j.b + 1]; jobs.push_back({j.b + 1, j.b + 1 + nl, (uint8_t)(j.axis ^ 1)}); }
+      if (nh) { hi_[root] = idx[j.b + 1 + nl]; jobs.push_back({j.b + 1 + nl, j.e, (uint8_t)(j.axis ^ 1)}); }
+    }
+  }
+
   // In-range payloads in the order the reference's result iterator yields them: the traversal
   // is pre-order, query side first, far side only if |delta| < r; results are prepended, so
   // the iteration order is the reverse of the visit order.

@@ -107,6 +107,7 @@ void TRG::ensureDraws(size_t upto) {
   draw_u_.resize(want - draw_base_);
   draw_xy_.resize(2 * (want - draw_base_));
   const float e = param_.expand_dist;
+  auto t0 = Clock::now();
   for (size_t k = first; k < draw_u_.size(); ++k) {
     const float u = distr_(gen_);
     draw_u_[k]    = u;
@@ -115,6 +116,7 @@ void TRG::ensureDraws(size_t upto) {
     draw_xy_[2 * k]     = e * cosf(angle);
     draw_xy_[2 * k + 1] = e * sinf(angle);
   }
+  stat_["us_draws"] += (int64_t)(1e6 * since(t0));
 }
 
 // make the device copy cover exactly the host buffer [draw_base_, draw_base_ + size)
@@ -264,9 +266,18 @@ void TRG::nodeIndexInsert(trgStruct& g, Node* n) {
 }
 
 void TRG::ensureTree(trgStruct& g) {
-  for (; g.tree_built < g.node_seq.size(); ++g.tree_built) {
-    Node* n = g.node_seq[g.tree_built];
-    g.node_tree.insert(n->pos_.x(), n->pos_.y(), (int)g.tree_built);
+  const size_t n = g.node_seq.size();
+  if (g.tree_built == 0 && n >= 256) {
+    // first use on an existing node set (after cleanGraph / load): bulk build, identical shape
+    std::vector<float> xs(n), ys(n);
+    for (size_t i = 0; i < n; ++i) { xs[i] = g.node_seq[i]->pos_.x(); ys[i] = g.node_seq[i]->pos_.y(); }
+    g.node_tree.build_bulk(xs.data(), ys.data(), (int)n);
+    g.tree_built = n;
+    return;
+  }
+  for (; g.tree_built < n; ++g.tree_built) {
+    Node* nd = g.node_seq[g.tree_built];
+    g.node_tree.insert(nd->pos_.x(), nd->pos_.y(), (int)g.tree_built);
   }
 }
 
@@ -421,8 +432,11 @@ class Expander {
         for (size_t r = root_i; r < roots.size() && chunk_.size() < C; ++r)
           chunk_.push_back({roots[r], roots[r]->id_, true});
       if (chunk_.empty()) break;
+      auto ta = Clock::now();
       sampleChunk();
+      auto tb = Clock::now();
       evalChunk();
+      auto tc = Clock::now();
       for (size_t i = 0; i < chunk_.size(); ++i) {
         Pop& p = chunk_[i];
         if (p.is_root) {
@@ -437,6 +451,10 @@ class Expander {
         }
         commitPop(p, bfs);
       }
+      auto td = Clock::now();
+      t_.stat_["us_sample"] += (int64_t)(1e6 * std::chrono::duration<double>(tb - ta).count());
+      t_.stat_["us_eval"] += (int64_t)(1e6 * std::chrono::duration<double>(tc - tb).count());
+      t_.stat_["us_commit"] += (int64_t)(1e6 * std::chrono::duration<double>(td - tc).count());
     }
     flushDeferred();
   }
@@ -815,7 +833,9 @@ void TRG::initGraph(bool /*isPreMap*/, Eigen::Vector3f start3d) {  // trg.cpp:36
     cnt++;
   }
   this->expandGraph(graph.node_id - 1, graph.type);
+  auto t1 = Clock::now();
   this->cleanGraph(false);
+  stat_["us_clean"] += (int64_t)(1e6 * since(t1));
   secs_["init_graph"] = since(t0);
 }
 

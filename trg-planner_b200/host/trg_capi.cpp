@@ -238,6 +238,14 @@ int trg_is_frontier_batch(void* h, const float* xy, int64_t n, uint8_t* out) {
   });
 }
 
+void* trg_device_map(void* h, const char* type) {
+  try {
+    return T(h)->deviceMap(type);
+  } catch (...) {
+    return nullptr;
+  }
+}
+
 double trg_last_seconds(void* h, const char* what) { return T(h)->lastSeconds(what); }
 int64_t trg_stat(void* h, const char* what) { return T(h)->stat(what); }
 int trg_set_tuning(void* h, const char* key, double value) {

@@ -37,7 +37,7 @@ class GraphDesc(C.Structure):
 
 class ProfEntry(C.Structure):
     _fields_ = [("name", C.c_char * 48), ("launches", C.c_int64), ("total_ms", C.c_double),
-                ("bytes", C.c_double)]
+                ("units", C.c_double)]
 
 
 _lib = None
@@ -111,7 +111,7 @@ def prof_reset():
 def prof_collect() -> dict:
     buf = (ProfEntry * 64)()
     n = lib().trgb_prof_collect(buf, 64)
-    return {buf[i].name.decode(): dict(launches=buf[i].launches, ms=buf[i].total_ms, bytes=buf[i].bytes)
+    return {buf[i].name.decode(): dict(launches=buf[i].launches, ms=buf[i].total_ms, units=buf[i].units)
             for i in range(min(n, 64))}
 
 

@@ -12,11 +12,9 @@ from __future__ import annotations
 import numpy as np
 
 
-def _value_noise(x: np.ndarray, y: np.ndarray, wavelength: float, rng: np.random.Generator,
-                 extent: float) -> np.ndarray:
-    """Smoothstep-interpolated lattice noise in [-1, 1]."""
-    n = int(np.ceil(extent / wavelength)) + 3
-    lat = rng.uniform(-1.0, 1.0, size=(n, n))
+def _value_noise(x: np.ndarray, y: np.ndarray, wavelength: float, lat: np.ndarray) -> np.ndarray:
+    """Smoothstep-interpolated lattice noise in [-1, 1] on the given random lattice."""
+    n = lat.shape[0]
     fx = x / wavelength
     fy = y / wavelength
     ix = np.floor(fx).astype(np.int64)
@@ -52,25 +50,37 @@ def _finish(x, y, z, rng: np.random.Generator, shuffle: bool) -> np.ndarray:
 def mountain(nx: int, ny: int | None = None, h: float = 0.1, seed: int = 2, *,
              base_wavelength: float = 64.0, amplitude: float = 12.0, octaves: int = 5,
              gain: float = 0.5, noise_sigma: float = 0.01, shuffle: bool = True,
-             origin=(0.0, 0.0)) -> np.ndarray:
+             tile=(0, 0), world_tiles=(1, 1)) -> np.ndarray:
     """C2/C3/C4 generator: fBm value-noise heightfield on a jittered h-lattice.
 
     `amplitude` is the half-range of the fBm sum: the octave weights are scaled so that the
     summed field lies in [-amplitude, +amplitude] (12 m => ~31 % of TRG edges carry a
     non-zero risk with config/mountain.yaml parameters, ~5.5 nodes/m^2).
+
+    Multi-GPU sharding: the world is `world_tiles` = (tx, ty) tiles of nx x ny lattice points; the
+    height is ONE continuous function of world coordinates (the noise lattices depend only on
+    `seed` and the world extent), `tile` = (i, j) selects which tile's points are emitted. With the
+    default single tile the output is identical to an unsharded map.
     """
     ny = nx if ny is None else ny
-    rng = np.random.default_rng(seed)
-    x, y = _lattice(nx, ny, h, rng)
-    extent = max(nx, ny) * h + 1.0
+    field_rng = np.random.default_rng(seed)
+    wx, wy = world_tiles
+    extent = max(nx * wx, ny * wy) * h + 1.0
     w = np.array([gain ** i for i in range(octaves)])
     w = w / w.sum() * amplitude
+    lattices = []
+    for i in range(octaves):
+        wl = base_wavelength / (2 ** i)
+        n = int(np.ceil(extent / wl)) + 3
+        lattices.append(field_rng.uniform(-1.0, 1.0, size=(n, n)))
+    rng = np.random.default_rng([seed, 7919 + tile[0], 104729 + tile[1]])
+    x, y = _lattice(nx, ny, h, rng)
+    x = x + tile[0] * nx * h
+    y = y + tile[1] * ny * h
     z = np.zeros_like(x)
     for i in range(octaves):
-        z += w[i] * _value_noise(x + 0.5 * h, y + 0.5 * h, base_wavelength / (2 ** i), rng, extent)
+        z += w[i] * _value_noise(x + 0.5 * h, y + 0.5 * h, base_wavelength / (2 ** i), lattices[i])
     z += rng.normal(0.0, noise_sigma, size=z.shape)
-    x = x + origin[0]
-    y = y + origin[1]
     return _finish(x, y, z, rng, shuffle)
 
 
