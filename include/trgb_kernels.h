@@ -61,6 +61,9 @@ void trgb_map_destroy(trgb_map* m);
 int  trgb_map_info(const trgb_map* m, TrgbMapInfo* info);
 void* trgb_map_stream(const trgb_map* m); /* cudaStream_t */
 int  trgb_map_sync(const trgb_map* m);
+/* options: "force_warp_path" (0/1) routes every query launch through the warp-per-item kernels
+ * instead of the thread-per-item fast path (both must give identical results; used by tests) */
+int  trgb_map_set_option(trgb_map* m, const char* key, int value);
 
 /* ---- tier 1: host-buffer batches (synchronous) ---------------------------------------- */
 /* K2 — TRG::isCollision (trg.cpp:746-778) for n query points xy[2n]; out[i] in {0,1} */

@@ -181,3 +181,44 @@ def r_len(g, ids):
         e = g.row_ptr[a] + np.nonzero(g.col[g.row_ptr[a]:g.row_ptr[a + 1]] == b)[0][0]
         s = np.float32(s + g.dist[e])
     return float(s)
+
+
+def test_thread_path_equals_warp_path(pkg, K, small_mountain, small_indoor):
+    """The thread-per-item fast path and the warp-per-item kernels must agree bit for bit
+    (collision booleans, edge stage / dist / npts / weight)."""
+    for pts, P in ((small_mountain, pkg.MOUNTAIN), (small_indoor, pkg.INDOOR)):
+        o = pkg.oracle(P)
+        o.set_global_map(pts)
+        a, b = K.DeviceMap(pts, 0.5 * P.robot_size), K.DeviceMap(pts, 0.5 * P.robot_size)
+        b.set_option("force_warp_path", 1)
+        q = _queries(pts, 100_000, 21)
+        ca = a.collision(q, P.robot_size, P.height_threshold, P.collision_threshold)
+        cb = b.collision(q, P.robot_size, P.height_threshold, P.collision_threshold)
+        np.testing.assert_array_equal(ca, cb)
+        np.testing.assert_array_equal(ca, o.is_collision(q, P.collision_threshold))
+        p1, p2 = _edge_pairs(pts, o, 30_000, 22, P.expand_dist)
+        ea = a.edge_eval(p1, p2, P.robot_size, P.height_threshold, P.collision_threshold)
+        eb = b.edge_eval(p1, p2, P.robot_size, P.height_threshold, P.collision_threshold)
+        for k in ("stage", "dist", "npts"):
+            np.testing.assert_array_equal(ea[k], eb[k])
+        # double sums are accumulated in a different order (per thread vs across lanes): <= 1 ulp-ish
+        np.testing.assert_allclose(ea["weight"], eb["weight"], rtol=2e-6, atol=0)
+
+
+def test_thread_path_overflow_falls_back(pkg, K):
+    """A clustered map: most cylinders hold far more points than the per-thread column sized from
+    the mean density -> the in-kernel warp fallback must take over without changing results."""
+    rng = np.random.default_rng(5)
+    base = pkg.terrain.mountain(150, h=0.1, seed=3)
+    cl = rng.normal(0, 0.12, size=(60_000, 2)) + rng.uniform(2, 13, size=(30, 1, 2)).repeat(2000, 1).reshape(-1, 2)
+    zc = rng.normal(0, 0.1, size=cl.shape[0])
+    pts = np.concatenate([base, np.column_stack([cl, zc]).astype(np.float32)])
+    P = pkg.MOUNTAIN
+    o = pkg.oracle(P)
+    o.set_global_map(pts)
+    dm = K.DeviceMap(pts, 0.5 * P.robot_size)
+    q = np.concatenate([_queries(pts, 20_000, 23), (cl[:20_000] + 0.05).astype(np.float32)])
+    np.testing.assert_array_equal(dm.collision(q, P.robot_size, P.height_threshold, P.collision_threshold),
+                                  o.is_collision(q, P.collision_threshold))
+    cnt = o.range_count(q, P.robot_size)
+    assert cnt.max() > 500   # far above any per-thread column

@@ -256,12 +256,65 @@ __device__ __forceinline__ bool warp_is_collision(const MapView& m, float qx, fl
   return ratio > rthr;
 }
 
+// ------------------------------------------------------------------------------------------
+// Thread-per-query variant of TRG::isCollision (trg.cpp:746-778): one THREAD walks the cell
+// runs of its query, keeps the in-cylinder z values insertion-sorted in a private shared-memory
+// column zcol[k * stride] (bank-conflict free when stride is a multiple of 32 and the column
+// index is the lane), and reads the upper median at rank n/2. 32 queries advance per warp
+// instruction instead of one; neighbouring threads should hold neighbouring queries so that the
+// cell runs they read share L1 lines.
+// Returns 0 / 1, or 2 when the cylinder holds more than `cap` points (caller falls back to the
+// warp-cooperative routine, which needs no storage). *n_out = points in the cylinder.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int thread_is_collision(const MapView& m, float qx, float qy, float r, float hthr,
+                                                   float rthr, float* zcol, int stride, int cap) {
+  const float r2 = __fmul_rn(r, r);
+  const float rr = inflate(r, qx, qy);
+  const int cx0 = cell_coord(qx - rr, m.x0, m.inv_cell, m.W);
+  const int cx1 = cell_coord(qx + rr, m.x0, m.inv_cell, m.W);
+  const int cy0 = cell_coord(qy - rr, m.y0, m.inv_cell, m.H);
+  const int cy1 = cell_coord(qy + rr, m.y0, m.inv_cell, m.H);
+  int n = 0;
+  for (int row = cy0; row <= cy1; ++row) {
+    const size_t b = (size_t)row * (size_t)m.W;
+    const uint32_t s = __ldg(m.cell_start + b + cx0);
+    const uint32_t e = __ldg(m.cell_start + b + cx1 + 1);
+    for (uint32_t i = s; i < e; ++i) {
+      const float4 p = ld_pt(m.pts + i);
+      const float dx = __fsub_rn(p.x, qx), dy = __fsub_rn(p.y, qy);
+      const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+      if (d2 <= r2) {
+        if (n < cap) {
+          int j = n;
+          while (j > 0) {
+            const float t = zcol[(j - 1) * stride];
+            if (!(t > p.z)) break;
+            zcol[j * stride] = t;
+            --j;
+          }
+          zcol[j * stride] = p.z;
+        }
+        ++n;
+      }
+    }
+  }
+  if (n == 0) return 1;  // :749-752 empty cylinder => collision
+  if (n > cap) return 2;
+  const float zmed = zcol[(n >> 1) * stride];  // :764 upper median
+  int cnt = 0;
+  for (int k = 0; k < n; ++k) cnt += (fabsf(__fsub_rn(zcol[k * stride], zmed)) > hthr);
+  const float ratio = __fdiv_rn((float)cnt, (float)n);  // :773
+  return ratio > rthr ? 1 : 0;
+}
+
 #endif  // __CUDACC__
 
 // shared launch geometry: 8 warps per CTA, one query per warp at a time, grid sized to a
 // multiple of the SM count (persistent-style grid-stride loop)
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
+// thread-per-query kernels: 128 threads per CTA, one shared z column per thread
+constexpr int kTqThreads = 128;
 int sm_count();
 int grid_for_warps(int64_t n_warps, int ctas_per_sm);
 
@@ -276,6 +329,7 @@ struct trgb_map {
   int64_t device_bytes = 0;
   cudaStream_t stream = nullptr;
   int zcap = 128;  // per-warp shared z buffer (floats) for the collision kernels
+  int force_warp_path = 0;  // tests: route every launch through the warp-per-item kernels
   // pinned/device staging for the host-buffer tier
   void* h_stage = nullptr;
   size_t h_stage_bytes = 0;

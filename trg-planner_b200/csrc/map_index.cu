@@ -347,6 +347,13 @@ extern "C" int trgb_map_info(const trgb_map* m, TrgbMapInfo* info) {
 
 extern "C" void* trgb_map_stream(const trgb_map* m) { return m ? (void*)m->stream : nullptr; }
 
+extern "C" int trgb_map_set_option(trgb_map* m, const char* key, int value) {
+  TRGB_ARG(m && key, "null handle");
+  if (std::string(key) == "force_warp_path") m->force_warp_path = value;
+  else TRGB_ARG(false, "unknown option");
+  return TRGB_OK;
+}
+
 extern "C" int trgb_map_sync(const trgb_map* m) {
   TRGB_ARG(m, "null handle");
   TRGB_CUDA(cudaStreamSynchronize(m->stream));

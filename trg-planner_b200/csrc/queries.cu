@@ -228,6 +228,121 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
+// covariance sums -> trg.cpp:337-363 (cov, JacobiSVD, Frobenius-normalised U, weight)
+__device__ __forceinline__ float weight_from_sums(int npts, double sx, double sy, double sz, double sxx, double sxy,
+                                                  double sxz, double syy, double syz, double szz) {
+  // :337-338 cov = centered^T centered / (n-1)
+  const double nn = (double)npts, dn = (double)(npts - 1);
+  float cov[9];
+  cov[0] = (float)((sxx - sx * sx / nn) / dn);
+  cov[1] = cov[3] = (float)((sxy - sx * sy / nn) / dn);
+  cov[2] = cov[6] = (float)((sxz - sx * sz / nn) / dn);
+  cov[4] = (float)((syy - sy * sy / nn) / dn);
+  cov[5] = cov[7] = (float)((syz - sy * sz / nn) / dn);
+  cov[8] = (float)((szz - sz * sz / nn) / dn);
+  float U[9], sv[3];
+  jacobi_svd3(cov, U, sv);
+  // :340 matrixU().normalized(): Frobenius norm of the 3x3
+  float fro = 0.f;
+  for (int k = 0; k < 9; ++k) fro += U[k] * U[k];
+  float e20 = U[6], e21 = U[7];
+  if (fro > 0.f) {
+    const float nrm = __fsqrt_rn(fro);
+    e20 = __fdiv_rn(e20, nrm);
+    e21 = __fdiv_rn(e21, nrm);
+  }
+  const float hor = fabsf(e20), ver = fabsf(e21);  // :347-354
+  const float ratio = 0.8f;
+  float weight = __fadd_rn(__fmul_rn(ratio, hor), __fmul_rn(__fsub_rn(1.f, ratio), ver));  // :360
+  if ((double)weight < 0.1) weight = 0.f;  // :361-363
+  return weight;
+}
+
+struct EdgeGeom {
+  float dist, dirx, diry;
+};
+// :276 dist = (node1 - node2).norm() ; :277 dir = (node2 - node1).normalized()
+__device__ __forceinline__ EdgeGeom edge_geom(float p1x, float p1y, float p2x, float p2y) {
+  EdgeGeom g;
+  const float ax = __fsub_rn(p1x, p2x), ay = __fsub_rn(p1y, p2y);
+  g.dist = __fsqrt_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)));
+  const float ex = __fsub_rn(p2x, p1x), ey = __fsub_rn(p2y, p1y);
+  const float sq = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+  g.dirx = ex;
+  g.diry = ey;
+  if (sq > 0.f) {
+    const float s = __fsqrt_rn(sq);
+    g.dirx = __fdiv_rn(ex, s);
+    g.diry = __fdiv_rn(ey, s);
+  }
+  return g;
+}
+
+// geometric part of TRG::wireEdge for ONE edge executed by ONE WARP (any density / radius)
+__device__ __forceinline__ void warp_edge_eval(const MapView& m, float p1x, float p1y, float p1z, float p2x, float p2y,
+                                               float rs, float hthr, float cthr, float* zbuf, int cap, int* stage_o,
+                                               float* weight_o, float* dist_o, int* npts_o) {
+  const EdgeGeom g = edge_geom(p1x, p1y, p2x, p2y);
+  const float dist = g.dist, dirx = g.dirx, diry = g.diry;
+  int stage = TRGB_EDGE_OK;
+  float weight = 0.f;
+  int npts = 0;
+  // :282-288 collision samples every robot_size/2 along the segment (float accumulator)
+  const float ds = 0.5f * rs;
+  for (float t = 0.f; t < dist; t = __fadd_rn(t, ds)) {
+    const float sx = __fadd_rn(p1x, __fmul_rn(t, dirx)), sy = __fadd_rn(p1y, __fmul_rn(t, diry));
+    if (warp_is_collision(m, sx, sy, rs, hthr, cthr, zbuf, cap, nullptr)) {
+      stage = TRGB_EDGE_COLLISION;
+      break;
+    }
+  }
+  if (stage == TRGB_EDGE_OK) {
+    // :291-297 ellipse with foci at the two nodes (circle when the nodes are close)
+    const float c = 0.5f * dist;
+    const float b = rs;
+    float a = b;
+    if (c >= b) a = __fsqrt_rn(__fadd_rn(__fmul_rn(c, c), __fmul_rn(b, b)));
+    const bool circle = (a == b);
+    const float cx = __fadd_rn(p1x, __fmul_rn(c, dirx)), cy = __fadd_rn(p1y, __fmul_rn(c, diry));
+    const float a2 = __fmul_rn(a, a), b2 = __fmul_rn(b, b);
+    const float rhs = __fmul_rn(__fmul_rn(a2, b), b);  // a*a*b*b, left to right
+    const float ndiry = -diry;
+    int nrange = 0;
+    double sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
+    warp_for_each_candidate(m, cx, cy, inflate(a, cx, cy), [&](bool valid, const float4& p) {
+      const float qx = __fsub_rn(p.x, cx), qy = __fsub_rn(p.y, cy);
+      const float d2 = __fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy));
+      const bool in_range = valid && d2 <= a2;  // kd_nearest_range2(center, a)
+      nrange += in_range;
+      // :312-316 p2d = R * (pt - center), R = [dir.x -dir.y; dir.y dir.x]
+      const float px = __fadd_rn(__fmul_rn(dirx, qx), __fmul_rn(ndiry, qy));
+      const float py = __fadd_rn(__fmul_rn(diry, qx), __fmul_rn(dirx, qy));
+      bool keep = in_range;
+      if (!circle)  // :320
+        keep = keep && (__fadd_rn(__fmul_rn(__fmul_rn(px, px), b2), __fmul_rn(__fmul_rn(py, py), a2)) < rhs);
+      if (keep) {
+        // covariance sums in double about the pivot z = p1.z: order-independent to ~1e-16,
+        // i.e. at least as close to the reference's float result as any float ordering
+        const double X = px, Y = py, Z = (double)p.z - (double)p1z;
+        npts += 1;
+        sx += X; sy += Y; sz += Z;
+        sxx += X * X; sxy += X * Y; sxz += X * Z; syy += Y * Y; syz += Y * Z; szz += Z * Z;
+      }
+    });
+    nrange = __reduce_add_sync(FULL, nrange);
+    npts = __reduce_add_sync(FULL, npts);
+    if (nrange == 0) stage = TRGB_EDGE_EMPTY;       // :305
+    else if (npts < 3) stage = TRGB_EDGE_FEWPTS;    // :327
+    else {
+      sx = warp_sum_d(sx); sy = warp_sum_d(sy); sz = warp_sum_d(sz);
+      sxx = warp_sum_d(sxx); sxy = warp_sum_d(sxy); sxz = warp_sum_d(sxz);
+      syy = warp_sum_d(syy); syz = warp_sum_d(syz); szz = warp_sum_d(szz);
+      weight = weight_from_sums(npts, sx, sy, sz, sxx, sxy, sxz, syy, syz, szz);
+    }
+  }
+  *stage_o = stage; *weight_o = weight; *dist_o = dist; *npts_o = npts;
+}
+
 __global__ void __launch_bounds__(kThreads) k_edge_eval(MapView m, const float* __restrict__ p1_xyz,
                                                         const float2* __restrict__ p2_xy, int64_t n,
                                                         float rs, float hthr, float cthr, int cap,
@@ -242,96 +357,9 @@ __global__ void __launch_bounds__(kThreads) k_edge_eval(MapView m, const float* 
   for (int64_t i = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); i < n; i += wstride) {
     const float p1x = __ldg(p1_xyz + 3 * i), p1y = __ldg(p1_xyz + 3 * i + 1), p1z = __ldg(p1_xyz + 3 * i + 2);
     const float2 p2 = __ldg(p2_xy + i);
-    // :276 dist = (node1 - node2).norm() ; :277 dir = (node2 - node1).normalized()
-    const float ax = __fsub_rn(p1x, p2.x), ay = __fsub_rn(p1y, p2.y);
-    const float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)));
-    const float ex = __fsub_rn(p2.x, p1x), ey = __fsub_rn(p2.y, p1y);
-    const float sq = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
-    float dirx = ex, diry = ey;
-    if (sq > 0.f) {
-      const float s = __fsqrt_rn(sq);
-      dirx = __fdiv_rn(ex, s);
-      diry = __fdiv_rn(ey, s);
-    }
-    int stage = TRGB_EDGE_OK;
-    float weight = 0.f;
-    int npts = 0;
-    // :282-288 collision samples every robot_size/2 along the segment (float accumulator)
-    const float ds = 0.5f * rs;
-    for (float t = 0.f; t < dist; t = __fadd_rn(t, ds)) {
-      const float sx = __fadd_rn(p1x, __fmul_rn(t, dirx)), sy = __fadd_rn(p1y, __fmul_rn(t, diry));
-      if (warp_is_collision(m, sx, sy, rs, hthr, cthr, zbuf, cap, nullptr)) {
-        stage = TRGB_EDGE_COLLISION;
-        break;
-      }
-    }
-    if (stage == TRGB_EDGE_OK) {
-      // :291-297 ellipse with foci at the two nodes (circle when the nodes are close)
-      const float c = 0.5f * dist;
-      const float b = rs;
-      float a = b;
-      if (c >= b) a = __fsqrt_rn(__fadd_rn(__fmul_rn(c, c), __fmul_rn(b, b)));
-      const bool circle = (a == b);
-      const float cx = __fadd_rn(p1x, __fmul_rn(c, dirx)), cy = __fadd_rn(p1y, __fmul_rn(c, diry));
-      const float a2 = __fmul_rn(a, a), b2 = __fmul_rn(b, b);
-      const float rhs = __fmul_rn(__fmul_rn(a2, b), b);  // a*a*b*b, left to right
-      const float ndiry = -diry;
-      int nrange = 0;
-      double sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
-      warp_for_each_candidate(m, cx, cy, inflate(a, cx, cy), [&](bool valid, const float4& p) {
-        const float qx = __fsub_rn(p.x, cx), qy = __fsub_rn(p.y, cy);
-        const float d2 = __fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy));
-        const bool in_range = valid && d2 <= a2;  // kd_nearest_range2(center, a)
-        nrange += in_range;
-        // :312-316 p2d = R * (pt - center), R = [dir.x -dir.y; dir.y dir.x]
-        const float px = __fadd_rn(__fmul_rn(dirx, qx), __fmul_rn(ndiry, qy));
-        const float py = __fadd_rn(__fmul_rn(diry, qx), __fmul_rn(dirx, qy));
-        bool keep = in_range;
-        if (!circle)  // :320
-          keep = keep && (__fadd_rn(__fmul_rn(__fmul_rn(px, px), b2), __fmul_rn(__fmul_rn(py, py), a2)) < rhs);
-        if (keep) {
-          // covariance sums in double about the pivot z = p1.z: order-independent to ~1e-16,
-          // i.e. at least as close to the reference's float result as any float ordering
-          const double X = px, Y = py, Z = (double)p.z - (double)p1z;
-          npts += 1;
-          sx += X; sy += Y; sz += Z;
-          sxx += X * X; sxy += X * Y; sxz += X * Z; syy += Y * Y; syz += Y * Z; szz += Z * Z;
-        }
-      });
-      nrange = __reduce_add_sync(FULL, nrange);
-      npts = __reduce_add_sync(FULL, npts);
-      if (nrange == 0) stage = TRGB_EDGE_EMPTY;       // :305
-      else if (npts < 3) stage = TRGB_EDGE_FEWPTS;    // :327
-      else {
-        sx = warp_sum_d(sx); sy = warp_sum_d(sy); sz = warp_sum_d(sz);
-        sxx = warp_sum_d(sxx); sxy = warp_sum_d(sxy); sxz = warp_sum_d(sxz);
-        syy = warp_sum_d(syy); syz = warp_sum_d(syz); szz = warp_sum_d(szz);
-        // :337-338 cov = centered^T centered / (n-1)
-        const double nn = (double)npts, dn = (double)(npts - 1);
-        float cov[9];
-        cov[0] = (float)((sxx - sx * sx / nn) / dn);
-        cov[1] = cov[3] = (float)((sxy - sx * sy / nn) / dn);
-        cov[2] = cov[6] = (float)((sxz - sx * sz / nn) / dn);
-        cov[4] = (float)((syy - sy * sy / nn) / dn);
-        cov[5] = cov[7] = (float)((syz - sy * sz / nn) / dn);
-        cov[8] = (float)((szz - sz * sz / nn) / dn);
-        float U[9], sv[3];
-        jacobi_svd3(cov, U, sv);
-        // :340 matrixU().normalized(): Frobenius norm of the 3x3
-        float fro = 0.f;
-        for (int k = 0; k < 9; ++k) fro += U[k] * U[k];
-        float e20 = U[6], e21 = U[7];
-        if (fro > 0.f) {
-          const float nrm = __fsqrt_rn(fro);
-          e20 = __fdiv_rn(e20, nrm);
-          e21 = __fdiv_rn(e21, nrm);
-        }
-        const float hor = fabsf(e20), ver = fabsf(e21);  // :347-354
-        const float ratio = 0.8f;
-        weight = __fadd_rn(__fmul_rn(ratio, hor), __fmul_rn(__fsub_rn(1.f, ratio), ver));  // :360
-        if ((double)weight < 0.1) weight = 0.f;  // :361-363
-      }
-    }
+    int stage, npts;
+    float weight, dist;
+    warp_edge_eval(m, p1x, p1y, p1z, p2.x, p2.y, rs, hthr, cthr, zbuf, cap, &stage, &weight, &dist, &npts);
     if (lane == 0) {
       stage_out[i] = (uint8_t)stage;
       w_out[i] = weight;
@@ -341,12 +369,174 @@ __global__ void __launch_bounds__(kThreads) k_edge_eval(MapView m, const float* 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Thread-per-item kernels (the fast path for densities where a cylinder holds <= cap points).
+// Items whose cylinder overflows the per-thread column fall back, inside the same launch, to the
+// warp-cooperative routines above, so results never depend on which path ran.
+// ------------------------------------------------------------------------------------------
+// shared layout during the thread phase: column of thread t = zsm[k * kTqThreads + t];
+// during the fallback phase warp w owns the contiguous slice zsm[w * 32 * cap ...)
+#define TQ_FALLBACK_BEGIN(res)                                 \
+  if (__syncthreads_or((res) == 2)) {                          \
+    float* wbuf = zsm + (threadIdx.x >> 5) * 32 * cap;         \
+    unsigned ov = __ballot_sync(FULL, (res) == 2);             \
+    while (ov) {                                               \
+      const int src = __ffs(ov) - 1;                           \
+      ov &= ov - 1;
+#define TQ_FALLBACK_END \
+    }                   \
+    __syncthreads();    \
+  }
+
+__global__ void __launch_bounds__(kTqThreads) k_collision_tq(MapView m, const float2* __restrict__ q, int64_t n,
+                                                             float r, float hthr, float rthr, int cap,
+                                                             uint8_t* __restrict__ out) {
+  extern __shared__ float zsm[];
+  float* zcol = zsm + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  for (int64_t base = (int64_t)blockIdx.x * kTqThreads; base < n; base += (int64_t)gridDim.x * kTqThreads) {
+    const int64_t i = base + threadIdx.x;
+    float2 p = make_float2(0.f, 0.f);
+    int res = 0;
+    if (i < n) {
+      p = __ldg(q + i);
+      res = thread_is_collision(m, p.x, p.y, r, hthr, rthr, zcol, kTqThreads, cap);
+    }
+    TQ_FALLBACK_BEGIN(res)
+      const float qx = __shfl_sync(FULL, p.x, src), qy = __shfl_sync(FULL, p.y, src);
+      const bool c = warp_is_collision(m, qx, qy, r, hthr, rthr, wbuf, 32 * cap, nullptr);
+      if (lane == src) res = c ? 1 : 0;
+    TQ_FALLBACK_END
+    if (i < n) out[i] = (uint8_t)res;
+  }
+}
+
+// one thread per (node, draw); bit j of mask[node] = isCollision(node + draw[first+j])
+__global__ void __launch_bounds__(kTqThreads) k_sample_window_tq(
+    MapView m, const float2* __restrict__ node_xy, const int32_t* __restrict__ first_draw,
+    const float2* __restrict__ draw_xy, int64_t n_nodes, int window, float r, float hthr, float rthr,
+    int cap, unsigned long long* __restrict__ mask) {
+  extern __shared__ float zsm[];
+  float* zcol = zsm + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t items = n_nodes * window;
+  const int words = (window + 63) >> 6;
+  for (int64_t base = (int64_t)blockIdx.x * kTqThreads; base < items; base += (int64_t)gridDim.x * kTqThreads) {
+    const int64_t it = base + threadIdx.x;
+    float sx = 0.f, sy = 0.f;
+    int res = 0;
+    int64_t node = 0;
+    int j = 0;
+    if (it < items) {
+      node = it / window;
+      j = (int)(it - node * window);
+      const float2 np = __ldg(node_xy + node);
+      const float2 d = __ldg(draw_xy + (__ldg(first_draw + node) + j));
+      // sample = node->pos_.head(2) + Vector2f(e*cos, e*sin)   (trg.cpp:396-397); d = (e*cos, e*sin)
+      sx = __fadd_rn(np.x, d.x);
+      sy = __fadd_rn(np.y, d.y);
+      res = thread_is_collision(m, sx, sy, r, hthr, rthr, zcol, kTqThreads, cap);
+    }
+    TQ_FALLBACK_BEGIN(res)
+      const float qx = __shfl_sync(FULL, sx, src), qy = __shfl_sync(FULL, sy, src);
+      const bool c = warp_is_collision(m, qx, qy, r, hthr, rthr, wbuf, 32 * cap, nullptr);
+      if (lane == src) res = c ? 1 : 0;
+    TQ_FALLBACK_END
+    if (it < items && res) atomicOr(mask + node * words + (j >> 6), 1ull << (j & 63));
+  }
+}
+
+__global__ void __launch_bounds__(kTqThreads) k_edge_eval_tq(MapView m, const float* __restrict__ p1_xyz,
+                                                             const float2* __restrict__ p2_xy, int64_t n, float rs,
+                                                             float hthr, float cthr, int cap,
+                                                             uint8_t* __restrict__ stage_out,
+                                                             float* __restrict__ w_out, float* __restrict__ dist_out,
+                                                             int32_t* __restrict__ npts_out) {
+  extern __shared__ float zsm[];
+  float* zcol = zsm + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  for (int64_t base = (int64_t)blockIdx.x * kTqThreads; base < n; base += (int64_t)gridDim.x * kTqThreads) {
+    const int64_t i = base + threadIdx.x;
+    float p1x = 0.f, p1y = 0.f, p1z = 0.f, p2x = 0.f, p2y = 0.f;
+    int stage = TRGB_EDGE_OK, npts = 0, res = 0;
+    float weight = 0.f, dist = 0.f;
+    if (i < n) {
+      p1x = __ldg(p1_xyz + 3 * i); p1y = __ldg(p1_xyz + 3 * i + 1); p1z = __ldg(p1_xyz + 3 * i + 2);
+      const float2 p2 = __ldg(p2_xy + i);
+      p2x = p2.x; p2y = p2.y;
+      const EdgeGeom g = edge_geom(p1x, p1y, p2x, p2y);
+      dist = g.dist;
+      const float dirx = g.dirx, diry = g.diry;
+      const float ds = 0.5f * rs;
+      for (float t = 0.f; t < dist; t = __fadd_rn(t, ds)) {  // :282-288
+        const float sx = __fadd_rn(p1x, __fmul_rn(t, dirx)), sy = __fadd_rn(p1y, __fmul_rn(t, diry));
+        const int c = thread_is_collision(m, sx, sy, rs, hthr, cthr, zcol, kTqThreads, cap);
+        if (c == 2) { res = 2; break; }
+        if (c == 1) { stage = TRGB_EDGE_COLLISION; break; }
+      }
+      if (res != 2 && stage == TRGB_EDGE_OK) {
+        const float c = 0.5f * dist;
+        const float b = rs;
+        float a = b;
+        if (c >= b) a = __fsqrt_rn(__fadd_rn(__fmul_rn(c, c), __fmul_rn(b, b)));
+        const bool circle = (a == b);
+        const float cx = __fadd_rn(p1x, __fmul_rn(c, dirx)), cy = __fadd_rn(p1y, __fmul_rn(c, diry));
+        const float a2 = __fmul_rn(a, a), b2 = __fmul_rn(b, b);
+        const float rhs = __fmul_rn(__fmul_rn(a2, b), b);
+        const float ndiry = -diry;
+        const float rr = inflate(a, cx, cy);
+        const int cx0 = cell_coord(cx - rr, m.x0, m.inv_cell, m.W), cx1 = cell_coord(cx + rr, m.x0, m.inv_cell, m.W);
+        const int cy0 = cell_coord(cy - rr, m.y0, m.inv_cell, m.H), cy1 = cell_coord(cy + rr, m.y0, m.inv_cell, m.H);
+        int nrange = 0;
+        double sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
+        for (int row = cy0; row <= cy1; ++row) {
+          const size_t rb = (size_t)row * (size_t)m.W;
+          const uint32_t s = __ldg(m.cell_start + rb + cx0), e = __ldg(m.cell_start + rb + cx1 + 1);
+          for (uint32_t k = s; k < e; ++k) {
+            const float4 p = ld_pt(m.pts + k);
+            const float qx = __fsub_rn(p.x, cx), qy = __fsub_rn(p.y, cy);
+            const float d2 = __fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy));
+            if (!(d2 <= a2)) continue;
+            ++nrange;
+            const float px = __fadd_rn(__fmul_rn(dirx, qx), __fmul_rn(ndiry, qy));
+            const float py = __fadd_rn(__fmul_rn(diry, qx), __fmul_rn(dirx, qy));
+            if (!circle && !(__fadd_rn(__fmul_rn(__fmul_rn(px, px), b2), __fmul_rn(__fmul_rn(py, py), a2)) < rhs)) continue;
+            const double X = px, Y = py, Z = (double)p.z - (double)p1z;
+            ++npts;
+            sx += X; sy += Y; sz += Z;
+            sxx += X * X; sxy += X * Y; sxz += X * Z; syy += Y * Y; syz += Y * Z; szz += Z * Z;
+          }
+        }
+        if (nrange == 0) stage = TRGB_EDGE_EMPTY;
+        else if (npts < 3) stage = TRGB_EDGE_FEWPTS;
+        else weight = weight_from_sums(npts, sx, sy, sz, sxx, sxy, sxz, syy, syz, szz);
+      }
+    }
+    TQ_FALLBACK_BEGIN(res)
+      const float a1 = __shfl_sync(FULL, p1x, src), b1 = __shfl_sync(FULL, p1y, src), c1 = __shfl_sync(FULL, p1z, src);
+      const float a2_ = __shfl_sync(FULL, p2x, src), b2_ = __shfl_sync(FULL, p2y, src);
+      int st, np_;
+      float w_, d_;
+      warp_edge_eval(m, a1, b1, c1, a2_, b2_, rs, hthr, cthr, wbuf, 32 * cap, &st, &w_, &d_, &np_);
+      if (lane == src) { stage = st; weight = w_; dist = d_; npts = np_; res = 0; }
+    TQ_FALLBACK_END
+    if (i < n) {
+      stage_out[i] = (uint8_t)stage;
+      w_out[i] = weight;
+      dist_out[i] = dist;
+      if (npts_out) npts_out[i] = npts;
+    }
+  }
+}
+
 // per-warp shared z-buffer capacity for a radius-r cylinder on this map
-static int pick_cap(const trgb_map* m, float r) {
+static double map_density(const trgb_map* m) {
   const double area = (double)m->view.W * m->view.H * (double)m->view.cell * m->view.cell;
-  const double density = (double)m->n / std::max(area, 1e-9);
+  return (double)m->n / std::max(area, 1e-9);
+}
+static int pick_cap(const trgb_map* m, float r) {
   const double side = 2.0 * r + m->view.cell;
-  double cand = 4.0 * density * side * side + 64.0;
+  double cand = 4.0 * map_density(m) * side * side + 64.0;
   int cap = 64;
   while (cap < cand && cap < 4096) cap <<= 1;
   return cap;
@@ -365,6 +555,29 @@ static int launch_cfg(const trgb_map* m, float r, int64_t n_items, int* grid, in
   return TRGB_OK;
 }
 
+// Thread-per-item configuration: usable when the expected cylinder population (with 60 % head
+// room for clustering) fits a per-thread column of at most 96 floats. Returns false otherwise
+// (large radii / dense maps -> warp-per-item kernels).
+static bool tq_cfg(const trgb_map* m, float r, int64_t n_items, int* grid, int* cap, size_t* smem, const void* kernel) {
+  if (m->force_warp_path) return false;
+  const double k = map_density(m) * 3.14159265358979 * (double)r * r;
+  int c = (int)(1.6 * k) + 12;
+  c = (c + 7) & ~7;
+  if (c > 96) return false;
+  *cap = c;
+  *smem = (size_t)kTqThreads * c * sizeof(float);
+  if (*smem > 48 * 1024 &&
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  const int64_t need = (n_items + kTqThreads - 1) / kTqThreads;
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(12, (200 * 1024) / std::max<size_t>(*smem, 1)));
+  const int64_t cap_grid = (int64_t)sm_count() * per_sm;
+  *grid = (int)std::max<int64_t>(1, std::min(need, cap_grid));
+  return true;
+}
+
 }  // namespace trgb
 
 using namespace trgb;
@@ -376,9 +589,16 @@ extern "C" int trgb_collision_launch(const trgb_map* m, const float* d_xy, int64
   TRGB_ARG(radius > 0.f, "radius must be > 0");
   if (n <= 0) return TRGB_OK;
   int grid, cap; size_t smem;
+  if (tq_cfg(m, radius, n, &grid, &cap, &smem, (const void*)k_collision_tq)) {
+    ProfScope ps("k_collision", m->stream, (double)n);
+    k_collision_tq<<<grid, kTqThreads, smem, m->stream>>>(m->view, reinterpret_cast<const float2*>(d_xy), n, radius,
+                                                          height_thr, ratio_thr, cap, d_out);
+    TRGB_CUDA(cudaGetLastError());
+    return TRGB_OK;
+  }
   int rc = launch_cfg(m, radius, n, &grid, &cap, &smem, (const void*)k_collision);
   if (rc) return rc;
-  ProfScope ps("k_collision", m->stream, (double)n);
+  ProfScope ps("k_collision_warp", m->stream, (double)n);
   k_collision<<<grid, kThreads, smem, m->stream>>>(m->view, reinterpret_cast<const float2*>(d_xy), n, radius,
                                                    height_thr, ratio_thr, cap, d_out);
   TRGB_CUDA(cudaGetLastError());
@@ -406,9 +626,17 @@ extern "C" int trgb_sample_window_launch(const trgb_map* m, const float* d_node_
   TRGB_ARG(radius > 0.f, "radius must be > 0");
   if (n_nodes <= 0) return TRGB_OK;
   int grid, cap; size_t smem;
+  if (tq_cfg(m, radius, n_nodes * window, &grid, &cap, &smem, (const void*)k_sample_window_tq)) {
+    ProfScope ps("k_sample_window", m->stream, (double)n_nodes * window);
+    k_sample_window_tq<<<grid, kTqThreads, smem, m->stream>>>(
+        m->view, reinterpret_cast<const float2*>(d_node_xy), d_first_draw,
+        reinterpret_cast<const float2*>(d_draw_xy), n_nodes, window, radius, height_thr, ratio_thr, cap, d_mask);
+    TRGB_CUDA(cudaGetLastError());
+    return TRGB_OK;
+  }
   int rc = launch_cfg(m, radius, n_nodes * window, &grid, &cap, &smem, (const void*)k_sample_window);
   if (rc) return rc;
-  ProfScope ps("k_sample_window", m->stream, (double)n_nodes * window);
+  ProfScope ps("k_sample_window_warp", m->stream, (double)n_nodes * window);
   k_sample_window<<<grid, kThreads, smem, m->stream>>>(
       m->view, reinterpret_cast<const float2*>(d_node_xy), d_first_draw,
       reinterpret_cast<const float2*>(d_draw_xy), n_nodes, window, radius, height_thr, ratio_thr, cap, d_mask);
@@ -436,9 +664,17 @@ extern "C" int trgb_edge_eval_launch(const trgb_map* m, const float* d_p1_xyz, c
   int grid, cap; size_t smem;
   // the ellipse gather reaches sqrt((1.25*expand)^2 + r^2) but keeps nothing in shared memory;
   // the shared buffer only serves the radius-robot_size collision samples
+  if (tq_cfg(m, prm->robot_size, n, &grid, &cap, &smem, (const void*)k_edge_eval_tq)) {
+    ProfScope ps("k_edge_eval", m->stream, (double)n);
+    k_edge_eval_tq<<<grid, kTqThreads, smem, m->stream>>>(m->view, d_p1_xyz, reinterpret_cast<const float2*>(d_p2_xy), n,
+                                                          prm->robot_size, prm->height_threshold,
+                                                          prm->collision_threshold, cap, d_stage, d_weight, d_dist, d_npts);
+    TRGB_CUDA(cudaGetLastError());
+    return TRGB_OK;
+  }
   int rc = launch_cfg(m, prm->robot_size, n, &grid, &cap, &smem, (const void*)k_edge_eval);
   if (rc) return rc;
-  ProfScope ps("k_edge_eval", m->stream, (double)n);
+  ProfScope ps("k_edge_eval_warp", m->stream, (double)n);
   k_edge_eval<<<grid, kThreads, smem, m->stream>>>(m->view, d_p1_xyz, reinterpret_cast<const float2*>(d_p2_xy), n,
                                                    prm->robot_size, prm->height_threshold,
                                                    prm->collision_threshold, cap, d_stage, d_weight, d_dist, d_npts);

@@ -19,6 +19,17 @@
 #include "device_session.h"
 #include "trgb_kernels.h"
 
+#ifdef TRG_FINE_TIMERS
+#include <x86intrin.h>
+#define FT_DECL(name) uint64_t ft_##name = 0
+#define FT_BEGIN() uint64_t _ft0 = __rdtsc()
+#define FT_LAP(name) do { const uint64_t _t = __rdtsc(); ft_##name += _t - _ft0; _ft0 = _t; } while (0)
+#else
+#define FT_DECL(name)
+#define FT_BEGIN()
+#define FT_LAP(name)
+#endif
+
 namespace {
 using Clock = std::chrono::steady_clock;
 inline double since(Clock::time_point t0) { return std::chrono::duration<double>(Clock::now() - t0).count(); }
@@ -89,6 +100,7 @@ void TRG::reseed(uint32_t seed) {
 
 TRG::Node* TRG::newNode(int id, Eigen::Vector2f& p, float z, NodeState s) {
   node_pool_.emplace_back(id, p, z, s);
+  node_pool_.back().edges_.reserve(8);  // typical degree 7: one allocation instead of four
   return &node_pool_.back();
 }
 TRG::Edge* TRG::newEdge(int dst, float w, float d) {
@@ -255,7 +267,7 @@ void TRG::ensureGrid(trgStruct& g) {
   const trgStruct& m = global_trg_.map_index ? global_trg_ : g;
   float x0 = m.bbox[0], y0 = m.bbox[1], x1 = m.bbox[2], y1 = m.bbox[3];
   if (!(x1 > x0) || !(y1 > y0)) { x0 = y0 = -64.f; x1 = y1 = 64.f; }
-  const float cell = std::max(param_.expand_dist, param_.robot_size);
+  const float cell = 1.5f * param_.robot_size;
   g.node_grid.configure(x0 - 2.f, y0 - 2.f, x1 + 2.f, y1 + 2.f, cell);
 }
 
@@ -360,7 +372,29 @@ bool TRG::addNode(int node_id, Eigen::Vector2f& node_pos, NodeState state, std::
 }
 
 namespace {
-// trg.cpp:269-274 — slope gate, float overloads (SURVEY.md hard part 2)
+// trg.cpp:269-274 — slope gate, float overloads (SURVEY.md hard part 2):
+//   atan2(fabs(dz), norm) > atan2(height_threshold, robot_size)
+// atan2f is only evaluated when dz/norm is within 0.1 % of the threshold ratio; outside that band
+// the comparison of the two angles is decided by the ratio alone (atan is strictly monotone and
+// glibc's atan2f error is a few ulp, far below the band).
+struct SlopeGate {
+  float max_slope, lo, hi;
+  SlopeGate(float height_thr, float robot_size) {
+    max_slope = atan2f(height_thr, robot_size);
+    const float t = height_thr / robot_size;
+    lo = t * 0.999f;
+    hi = t * 1.001f;
+  }
+  bool rejects(const Eigen::Vector3f& a, const Eigen::Vector3f& b) const {
+    const float dz = fabsf(a.z() - b.z());
+    const float d  = norm2(a.x() - b.x(), a.y() - b.y());
+    if (d > 0.f && lo > 0.f) {
+      if (dz < lo * d) return false;
+      if (dz > hi * d) return true;
+    }
+    return atan2f(dz, d) > max_slope;
+  }
+};
 inline bool slope_rejects(const Eigen::Vector3f& a, const Eigen::Vector3f& b, float height_thr, float robot_size) {
   const float max_slope = atan2f(height_thr, robot_size);
   const float slope     = atan2f(fabsf(a.z() - b.z()), norm2(a.x() - b.x(), a.y() - b.y()));
@@ -411,7 +445,8 @@ namespace trg_b200 {
 
 class Expander {
  public:
-  Expander(TRG& t, TRG::trgStruct& g) : t_(t), g_(g), P_(t.param_) {
+  Expander(TRG& t, TRG::trgStruct& g)
+      : t_(t), g_(g), P_(t.param_), gate_(t.param_.height_threshold, t.param_.robot_size) {
     map_ = t.requireMap(g, "expandGraph");
     st_  = (cudaStream_t)trgb_map_stream(map_);
     // trg.cpp:429 — `float - float < double * float`
@@ -457,6 +492,15 @@ class Expander {
       t_.stat_["us_commit"] += (int64_t)(1e6 * std::chrono::duration<double>(td - tc).count());
     }
     flushDeferred();
+    t_.stat_["pops"] += n_pops_;
+    t_.stat_["nearest_node"] += n_nearest_;
+    t_.stat_["z_ties"] += n_zties_;
+    t_.stat_["stalls"] += n_stalls_;
+#ifdef TRG_FINE_TIMERS
+    t_.stat_["cyc_nearest"] += (int64_t)ft_nearest;
+    t_.stat_["cyc_wire"] += (int64_t)ft_wire;
+    t_.stat_["cyc_newnode"] += (int64_t)ft_newnode;
+#endif
   }
 
  private:
@@ -708,7 +752,7 @@ class Expander {
       for (TRG::Edge* e : b->edges_)
         if (e->dst_id_ == a->id_ && e->dist_ >= 0.f) return;
     }
-    if (slope_rejects(a->pos_, b->pos_, P_.height_threshold, P_.robot_size)) return;
+    if (gate_.rejects(a->pos_, b->pos_)) return;
     const float tag = -(float)(deferred_.size() + 1);
     TRG::Edge* ea = t_.newEdge(b->id_, -1.f, tag);
     TRG::Edge* eb = t_.newEdge(a->id_, -2.f, tag);
@@ -721,22 +765,25 @@ class Expander {
   void commitPop(const Pop& p, std::deque<TRG::Node*>& bfs) {
     TRG::Node* node = p.node;
     t_.draw_next_ = p.draw_start + (size_t)p.consumed;
-    t_.stat_["pops"]++;
+    ++n_pops_;
     const TRG::NodeState new_state = (p.ref_id == 0) ? TRG::NodeState::Valid : TRG::NodeState::Frontier;
     // index of this pop's first sample inside the speculative arrays
     const size_t s0 = p.acc_begin;
     for (uint32_t j = 0; j < p.acc_count; ++j) {
       const Sample& s = acc_[s0 + j];
-      t_.stat_["nearest_node"]++;
+      ++n_nearest_;
+      FT_BEGIN();
       TRG::Node* ex = t_.nearestNode(g_, s.x, s.y);
+      FT_LAP(nearest);
       if (ex->state_ == TRG::NodeState::Invalid) continue;
       if (norm2(ex->pos_.x() - s.x, ex->pos_.y() - s.y) < P_.robot_size) {
         wireDeferred(node, ex);
+        FT_LAP(wire);
         continue;
       }
       // 2. new node (addNode never fails for id != 0)
       const size_t si = s0 + j;
-      if (spec_.tie[si]) t_.stat_["z_ties"]++;
+      if (spec_.tie[si]) ++n_zties_;
       Eigen::Vector2f pos2(s.x, s.y);
       TRG::Node* nn = t_.newNode(g_.node_id, pos2, spec_.z[si], new_state);
       g_.nodes[g_.node_id] = nn;
@@ -744,7 +791,7 @@ class Expander {
       g_.node_id++;
       // 2.1 wireEdge(node, new): slope gate on the host, geometry from the speculative batch
       bool parent_ok = false;
-      if (!slope_rejects(node->pos_, nn->pos_, P_.height_threshold, P_.robot_size) && spec_.stage[si] == TRGB_EDGE_OK) {
+      if (spec_.stage[si] == TRGB_EDGE_OK && !gate_.rejects(node->pos_, nn->pos_)) {
         node->edges_.push_back(t_.newEdge(nn->id_, spec_.w[si], spec_.d[si]));
         nn->edges_.push_back(t_.newEdge(node->id_, spec_.w[si], spec_.d[si]));
         parent_ok = true;
@@ -758,7 +805,7 @@ class Expander {
         }
         if (!parent_ok && !nn->edges_.empty()) {
           // the node survives only if one of its pending edges does: resolve them now
-          t_.stat_["stalls"]++;
+          ++n_stalls_;
           flushDeferred();
         }
       }
@@ -768,8 +815,10 @@ class Expander {
         continue;
       }
       bfs.push_back(nn);
+      FT_LAP(newnode);
     }
   }
+  FT_DECL(nearest); FT_DECL(wire); FT_DECL(newnode);
 
   struct Spec {
     size_t n = 0;
@@ -783,8 +832,10 @@ class Expander {
   TRG& t_;
   TRG::trgStruct& g_;
   const decltype(TRG::param_)& P_;
+  SlopeGate gate_;
   trgb_map* map_ = nullptr;
   cudaStream_t st_ = nullptr;
+  int64_t n_pops_ = 0, n_nearest_ = 0, n_zties_ = 0, n_stalls_ = 0;
   bool step3_ = false;
   double mean_ = 8.0, var_ = 2.0;
   std::vector<Pop> chunk_;
@@ -841,9 +892,15 @@ void TRG::initGraph(bool /*isPreMap*/, Eigen::Vector3f start3d) {  // trg.cpp:36
 
 void TRG::cleanGraph(bool updateLocal) {  // trg.cpp:491-535
   trgStruct&                     g = *trgMap_["global"];
-  std::unordered_map<int, int>   old2new;
   std::unordered_map<int, Node*> new_nodes;
   int                            new_id = 0;
+  // old id -> (node, new id) tables instead of the reference's old2new map and per-edge map lookups:
+  // same mapping, direct indexing (ids are dense counters: trg.cpp:250, 502)
+  int max_id = -1;
+  for (auto& node : g.nodes) max_id = std::max(max_id, node.first);
+  std::vector<Node*> by_id((size_t)(max_id + 1), nullptr);
+  std::vector<int>   old2new((size_t)(max_id + 1), -1);
+  for (auto& node : g.nodes) by_id[node.first] = node.second;
   for (auto& node : g.nodes) {
     if (node.second->state_ == NodeState::Invalid || node.second->edges_.size() < 1) continue;
     new_nodes[new_id]   = node.second;
@@ -851,15 +908,17 @@ void TRG::cleanGraph(bool updateLocal) {  // trg.cpp:491-535
     new_id++;
   }
   // the reference collects the ids of Invalid edge targets in a vector and std::find()s every edge
-  // against it (:515); the same predicate is "target node is Invalid", evaluated directly here
+  // against it (:515); the same predicate is "target node is Invalid", evaluated directly here.
+  // Edges are rewritten in place (same order, same values as the reference's fresh copies).
   for (auto& node : new_nodes) {
-    std::vector<Edge*> new_edges;
-    new_edges.reserve(node.second->edges_.size());
-    for (auto& edge : node.second->edges_) {
-      if (g.nodes.at(edge->dst_id_)->state_ == NodeState::Invalid) continue;
-      new_edges.push_back(newEdge(old2new[edge->dst_id_], edge->weight_, edge->dist_));
+    auto&  edges = node.second->edges_;
+    size_t keep  = 0;
+    for (Edge* edge : edges) {
+      if (by_id[edge->dst_id_]->state_ == NodeState::Invalid) continue;
+      edge->dst_id_  = old2new[edge->dst_id_] >= 0 ? old2new[edge->dst_id_] : 0;  // (:518 old2new[] default-inserts 0)
+      edges[keep++] = edge;
     }
-    node.second->edges_ = std::move(new_edges);
+    edges.resize(keep);
   }
   for (auto& node : new_nodes) node.second->id_ = node.first;
   this->resetGraph(g.type);

@@ -58,6 +58,7 @@ def lib():
         L.trgb_map_stream.argtypes = [_vp]
         L.trgb_map_stream.restype = _vp
         L.trgb_map_sync.argtypes = [_vp]
+        L.trgb_map_set_option.argtypes = [_vp, C.c_char_p, C.c_int]
         L.trgb_collision_batch.argtypes = [_vp, _vp, C.c_int64, C.c_float, C.c_float, C.c_float, _vp]
         L.trgb_range_count_batch.argtypes = [_vp, _vp, C.c_int64, C.c_float, _vp]
         L.trgb_nearest_z_batch.argtypes = [_vp, _vp, C.c_int64, _vp, _vp, _vp]
@@ -150,6 +151,9 @@ class DeviceMap:
 
     def sync(self):
         _chk(lib().trgb_map_sync(self.h), "trgb_map_sync")
+
+    def set_option(self, key: str, value: int):
+        _chk(lib().trgb_map_set_option(self.h, key.encode(), int(value)), "trgb_map_set_option")
 
     def collision(self, xy, radius, height_thr, ratio_thr):
         xy = np.ascontiguousarray(xy, dtype=np.float32)
