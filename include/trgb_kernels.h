@@ -45,6 +45,10 @@ typedef struct TrgbEdgeParams {
   float robot_size;
   float height_threshold;
   float collision_threshold;
+  /* threads per edge in the segment-collision kernel = expected upper bound on the samples of an
+   * edge, ceil(dist / (robot_size/2)). 0 = library default (8). Purely a performance hint: the
+   * last thread of an edge walks any samples beyond it, so results never depend on the value. */
+  int32_t max_edge_samples;
 } TrgbEdgeParams;
 
 const char* trgb_last_error(void);
@@ -98,6 +102,19 @@ int trgb_nearest_z_launch(const trgb_map* m, const float* d_xy, int64_t n, float
 int trgb_edge_eval_launch(const trgb_map* m, const float* d_p1_xyz, const float* d_p2_xy, int64_t n,
                           const TrgbEdgeParams* prm, uint8_t* d_stage, float* d_weight, float* d_dist,
                           int32_t* d_npts);
+
+/* ---- K5: device grid over graph nodes (append-only) — batched kd_nearest2 on the node tree
+ *      (trg.cpp:408; kdtree.c:364-417). Indices are append order. All launches are asynchronous on
+ *      the given cudaStream_t. Exact float argmin; tie[i]=1 when two nodes share the minimal dist^2
+ *      (the caller resolves those with the reference's tree order). idx = -1 on an empty grid. */
+typedef struct trgb_nodes trgb_nodes;
+int     trgb_nodes_create(trgb_nodes** out, float x0, float y0, float x1, float y1, float cell);
+void    trgb_nodes_destroy(trgb_nodes* g);
+int     trgb_nodes_reset(trgb_nodes* g, void* stream);
+int64_t trgb_nodes_count(const trgb_nodes* g);
+int     trgb_nodes_append_launch(trgb_nodes* g, const float* d_xy, int64_t n, void* stream);
+int     trgb_nodes_nearest_launch(const trgb_nodes* g, const float* d_xy, int64_t n, int32_t* d_idx, float* d_d2,
+                                  uint8_t* d_tie, void* stream);
 
 /* ---- K7: graph upload + batched risk-aware shortest path (TRG::planSafePath, trg.cpp:618-688).
  *      CSR rows = node id 0..n-1, columns in `edges_` order. Start/goal snapping

@@ -38,7 +38,7 @@ for rep in range(a.reps):
     prof = K.prof_collect(); K.prof_enable(False)
     stats = {k: t.stat(k) for k in ("pops", "rng_draws", "window_launches", "eval_launches", "flush_launches", "stalls",
                                     "window_tests", "edge_evals", "nearest_map", "batches", "node_ties", "z_ties",
-                                    "us_sample", "us_eval", "us_commit", "us_draws", "us_clean", "cyc_nearest", "cyc_wire", "cyc_newnode")}
+                                    "us_sample", "us_eval", "us_commit", "us_draws", "us_clean", "cyc_nearest", "cyc_wire", "cyc_newnode", "us_w_draws", "us_w_prep", "us_w_gpu")}
     print(json.dumps(dict(rep=rep, map_s=round(w1 - w0, 4), init_s=round(w2 - w1, 4), plan_s=round(w3 - w2, 4),
                           snap_s=round(t.seconds("plan_snap"), 4), nodes=nn, edges=ne, found=int(r["found"].sum()),
                           pts_per_s=round(pts.shape[0] / (w2 - w0)), nodes_per_s=round(nn / (w2 - w0)),

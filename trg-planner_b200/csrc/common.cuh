@@ -258,16 +258,54 @@ __device__ __forceinline__ bool warp_is_collision(const MapView& m, float qx, fl
 
 // ------------------------------------------------------------------------------------------
 // Thread-per-query variant of TRG::isCollision (trg.cpp:746-778): one THREAD walks the cell
-// runs of its query, keeps the in-cylinder z values insertion-sorted in a private shared-memory
-// column zcol[k * stride] (bank-conflict free when stride is a multiple of 32 and the column
-// index is the lane), and reads the upper median at rank n/2. 32 queries advance per warp
-// instruction instead of one; neighbouring threads should hold neighbouring queries so that the
-// cell runs they read share L1 lines.
-// Returns 0 / 1, or 2 when the cylinder holds more than `cap` points (caller falls back to the
-// warp-cooperative routine, which needs no storage). *n_out = points in the cylinder.
+// runs of its query and appends the in-cylinder z values to a private shared-memory column
+// zcol[k * stride] (bank-conflict free: stride is a multiple of 32, column index = lane). The
+// column is then pulled into registers and ordered by a compile-time bitonic network — no
+// data-dependent shared-memory chain, no divergence — and the upper median is picked at rank
+// n/2. 32 queries advance per warp instruction; neighbouring threads should hold neighbouring
+// queries so that the cell runs they read share L1 lines.
+// Returns 0 / 1, or 2 when the cylinder holds more than kTqCap points (the caller falls back to
+// the warp-cooperative routine, which needs no storage).
 // ------------------------------------------------------------------------------------------
+constexpr int kTqCap = 64;  // per-thread column length (floats)
+
+template <int N>
+__device__ __forceinline__ void bitonic_sort_regs(float (&a)[N]) {
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const int l = i ^ j;
+        if (l > i) {
+          const float lo = fminf(a[i], a[l]), hi = fmaxf(a[i], a[l]);
+          if ((i & k) == 0) { a[i] = lo; a[l] = hi; }
+          else { a[i] = hi; a[l] = lo; }
+        }
+      }
+    }
+  }
+}
+
+template <int N>
+__device__ __forceinline__ int median_outlier_count(const float* zcol, int stride, int n, float hthr) {
+  float a[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) a[k] = (k < n) ? zcol[k * stride] : INFINITY;
+  bitonic_sort_regs<N>(a);
+  const int mid = n >> 1;  // :764 upper median
+  float zmed = 0.f;
+#pragma unroll
+  for (int k = 0; k < N; ++k) zmed = (k == mid) ? a[k] : zmed;
+  int cnt = 0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) cnt += (k < n && fabsf(__fsub_rn(a[k], zmed)) > hthr);
+  return cnt;
+}
+
 __device__ __forceinline__ int thread_is_collision(const MapView& m, float qx, float qy, float r, float hthr,
-                                                   float rthr, float* zcol, int stride, int cap) {
+                                                   float rthr, float* zcol, int stride) {
   const float r2 = __fmul_rn(r, r);
   const float rr = inflate(r, qx, qy);
   const int cx0 = cell_coord(qx - rr, m.x0, m.inv_cell, m.W);
@@ -279,30 +317,23 @@ __device__ __forceinline__ int thread_is_collision(const MapView& m, float qx, f
     const size_t b = (size_t)row * (size_t)m.W;
     const uint32_t s = __ldg(m.cell_start + b + cx0);
     const uint32_t e = __ldg(m.cell_start + b + cx1 + 1);
+#pragma unroll 4
     for (uint32_t i = s; i < e; ++i) {
       const float4 p = ld_pt(m.pts + i);
       const float dx = __fsub_rn(p.x, qx), dy = __fsub_rn(p.y, qy);
       const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
       if (d2 <= r2) {
-        if (n < cap) {
-          int j = n;
-          while (j > 0) {
-            const float t = zcol[(j - 1) * stride];
-            if (!(t > p.z)) break;
-            zcol[j * stride] = t;
-            --j;
-          }
-          zcol[j * stride] = p.z;
-        }
+        if (n < kTqCap) zcol[n * stride] = p.z;
         ++n;
       }
     }
   }
   if (n == 0) return 1;  // :749-752 empty cylinder => collision
-  if (n > cap) return 2;
-  const float zmed = zcol[(n >> 1) * stride];  // :764 upper median
-  int cnt = 0;
-  for (int k = 0; k < n; ++k) cnt += (fabsf(__fsub_rn(zcol[k * stride], zmed)) > hthr);
+  if (n > kTqCap) return 2;
+  // the whole warp takes the short network when every lane fits it (keeps the branch uniform)
+  int cnt;
+  if (__all_sync(__activemask(), n <= 32)) cnt = median_outlier_count<32>(zcol, stride, n, hthr);
+  else cnt = median_outlier_count<64>(zcol, stride, n, hthr);
   const float ratio = __fdiv_rn((float)cnt, (float)n);  // :773
   return ratio > rthr ? 1 : 0;
 }

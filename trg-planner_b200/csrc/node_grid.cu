@@ -1,0 +1,180 @@
+// K5 — device-resident uniform grid over GRAPH NODES (append-only), the batched counterpart of the
+// reference's kd_nearest2 on `node_tree` inside TRG::expandGraph (trg.cpp:408, kdtree.c:364-417).
+// The wavefront scheduler asks, for every accepted sample of a batch, for the exact nearest node
+// among the nodes that existed when the batch started; the host then only has to look at the few
+// nodes created inside the batch. Distances use the same float arithmetic as kdtree.c
+// (fl(fl(dx*dx)+fl(dy*dy)), strict `<`), so the minimum is the same number; exact ties are
+// flagged and resolved on the host by the insertion-order tree.
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+struct trgb_nodes {
+  float x0 = 0, y0 = 0, cell = 1, inv = 1;
+  int W = 0, H = 0;
+  int64_t count = 0, cap = 0;
+  int32_t* d_head = nullptr;  // W*H, -1 = empty
+  float2* d_xy = nullptr;     // cap
+  int32_t* d_next = nullptr;  // cap
+};
+
+namespace trgb {
+
+__device__ __forceinline__ int ncell(float v, float origin, float inv, int dim) {
+  const float f = floorf(__fmul_rn(__fsub_rn(v, origin), inv));
+  if (!(f > 0.0f)) return 0;
+  if (f >= (float)dim) return dim - 1;
+  return (int)f;
+}
+
+__global__ void __launch_bounds__(256) k_nodes_append(const float2* __restrict__ xy_new, int64_t n, int64_t base,
+                                                      float x0, float y0, float inv, int W, int H,
+                                                      float2* __restrict__ xy, int32_t* __restrict__ next,
+                                                      int32_t* __restrict__ head) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float2 p = xy_new[i];
+    const int id = (int)(base + i);
+    xy[id] = p;
+    const int c = ncell(p.y, y0, inv, H) * W + ncell(p.x, x0, inv, W);
+    next[id] = atomicExch(head + c, id);
+  }
+}
+
+struct NearAcc {
+  float d2;
+  int idx;
+  int tie;
+};
+__device__ __forceinline__ void scan_cell(const int32_t* __restrict__ head, const float2* __restrict__ xy,
+                                          const int32_t* __restrict__ next, int W, int H, int cx, int cy, float qx,
+                                          float qy, NearAcc& b) {
+  if (cx < 0 || cy < 0 || cx >= W || cy >= H) return;
+  for (int e = __ldg(head + (size_t)cy * W + cx); e >= 0; e = __ldg(next + e)) {
+    const float2 p = __ldg(xy + e);
+    const float dx = __fsub_rn(p.x, qx), dy = __fsub_rn(p.y, qy);
+    const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+    if (d2 < b.d2) { b.d2 = d2; b.idx = e; b.tie = 0; }
+    else if (d2 == b.d2 && e != b.idx) { b.tie = 1; }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_nodes_nearest(const float2* __restrict__ q, int64_t n, float x0, float y0,
+                                                       float cell, float inv, int W, int H,
+                                                       const int32_t* __restrict__ head, const float2* __restrict__ xy,
+                                                       const int32_t* __restrict__ next, int64_t count,
+                                                       int32_t* __restrict__ idx_out, float* __restrict__ d2_out,
+                                                       uint8_t* __restrict__ tie_out) {
+  const int maxr = max(W, H);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float2 p = __ldg(q + i);
+    NearAcc b{INFINITY, -1, 0};
+    if (count > 0) {
+      const int qcx = ncell(p.x, x0, inv, W), qcy = ncell(p.y, y0, inv, H);
+      const float fuzz = 4e-6f * (fabsf(p.x) + fabsf(p.y) + cell * (float)(W + H));
+      for (int R = 1; R <= maxr; ++R) {
+        if (R == 1) {
+          for (int yy = qcy - 1; yy <= qcy + 1; ++yy)
+            for (int xx = qcx - 1; xx <= qcx + 1; ++xx) scan_cell(head, xy, next, W, H, xx, yy, p.x, p.y, b);
+        } else {
+          for (int xx = qcx - R; xx <= qcx + R; ++xx) {
+            scan_cell(head, xy, next, W, H, xx, qcy - R, p.x, p.y, b);
+            scan_cell(head, xy, next, W, H, xx, qcy + R, p.x, p.y, b);
+          }
+          for (int yy = qcy - R + 1; yy <= qcy + R - 1; ++yy) {
+            scan_cell(head, xy, next, W, H, qcx - R, yy, p.x, p.y, b);
+            scan_cell(head, xy, next, W, H, qcx + R, yy, p.x, p.y, b);
+          }
+        }
+        // cells outside the scanned block are at least R whole cells away from the query's cell
+        const float g = (float)R * cell * 0.9999f - fuzz;
+        if (b.idx >= 0 && g > 0.f && b.d2 <= g * g) break;
+        if (qcx - R <= 0 && qcy - R <= 0 && qcx + R >= W - 1 && qcy + R >= H - 1) break;
+      }
+    }
+    idx_out[i] = b.idx;
+    d2_out[i] = b.d2;
+    tie_out[i] = (uint8_t)b.tie;
+  }
+}
+
+}  // namespace trgb
+
+using namespace trgb;
+
+extern "C" void trgb_nodes_destroy(trgb_nodes* g) {
+  if (!g) return;
+  cudaFree(g->d_head); cudaFree(g->d_xy); cudaFree(g->d_next);
+  delete g;
+}
+
+extern "C" int trgb_nodes_create(trgb_nodes** out, float x0, float y0, float x1, float y1, float cell) {
+  TRGB_ARG(out, "out is null");
+  TRGB_ARG(cell > 0.f && x1 > x0 && y1 > y0, "bad node grid extent");
+  trgb_nodes* g = new trgb_nodes();
+  g->cell = cell;
+  g->inv = 1.0f / cell;
+  g->x0 = x0 - 2.f * cell;
+  g->y0 = y0 - 2.f * cell;
+  const double w = std::floor(((double)x1 - g->x0) / cell) + 4, h = std::floor(((double)y1 - g->y0) / cell) + 4;
+  if (w * h > 2.0e9) { delete g; set_error("node grid too large"); return TRGB_E_ARG; }
+  g->W = (int)w;
+  g->H = (int)h;
+  cudaError_t e = cudaMalloc((void**)&g->d_head, (size_t)g->W * g->H * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMemset(g->d_head, 0xff, (size_t)g->W * g->H * sizeof(int32_t));
+  if (e != cudaSuccess) { trgb_nodes_destroy(g); return cuda_fail(e, "node grid alloc", __FILE__, __LINE__); }
+  *out = g;
+  return TRGB_OK;
+}
+
+extern "C" int trgb_nodes_reset(trgb_nodes* g, void* stream) {
+  TRGB_ARG(g, "null handle");
+  g->count = 0;
+  TRGB_CUDA(cudaMemsetAsync(g->d_head, 0xff, (size_t)g->W * g->H * sizeof(int32_t), (cudaStream_t)stream));
+  return TRGB_OK;
+}
+
+extern "C" int64_t trgb_nodes_count(const trgb_nodes* g) { return g ? g->count : 0; }
+
+extern "C" int trgb_nodes_append_launch(trgb_nodes* g, const float* d_xy, int64_t n, void* stream) {
+  TRGB_ARG(g && (n == 0 || d_xy), "null pointer");
+  if (n <= 0) return TRGB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g->count + n > g->cap) {
+    int64_t want = g->cap ? g->cap : (1 << 16);
+    while (want < g->count + n) want *= 2;
+    float2* nxy = nullptr;
+    int32_t* nnext = nullptr;
+    TRGB_CUDA(cudaMalloc((void**)&nxy, (size_t)want * sizeof(float2)));
+    TRGB_CUDA(cudaMalloc((void**)&nnext, (size_t)want * sizeof(int32_t)));
+    if (g->count) {
+      TRGB_CUDA(cudaMemcpyAsync(nxy, g->d_xy, (size_t)g->count * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+      TRGB_CUDA(cudaMemcpyAsync(nnext, g->d_next, (size_t)g->count * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    }
+    TRGB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(g->d_xy); cudaFree(g->d_next);
+    g->d_xy = nxy; g->d_next = nnext; g->cap = want;
+  }
+  {
+    ProfScope ps("k_nodes_append", st, (double)n);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8));
+    k_nodes_append<<<grid, 256, 0, st>>>(reinterpret_cast<const float2*>(d_xy), n, g->count, g->x0, g->y0, g->inv,
+                                         g->W, g->H, g->d_xy, g->d_next, g->d_head);
+  }
+  TRGB_CUDA(cudaGetLastError());
+  g->count += n;
+  return TRGB_OK;
+}
+
+extern "C" int trgb_nodes_nearest_launch(const trgb_nodes* g, const float* d_xy, int64_t n, int32_t* d_idx,
+                                         float* d_d2, uint8_t* d_tie, void* stream) {
+  TRGB_ARG(g && (n == 0 || (d_xy && d_idx && d_d2 && d_tie)), "null pointer");
+  if (n <= 0) return TRGB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope ps("k_nodes_nearest", st, (double)n);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8));
+  k_nodes_nearest<<<grid, 256, 0, st>>>(reinterpret_cast<const float2*>(d_xy), n, g->x0, g->y0, g->cell, g->inv, g->W,
+                                        g->H, g->d_head, g->d_xy, g->d_next, g->count, d_idx, d_d2, d_tie);
+  TRGB_CUDA(cudaGetLastError());
+  return TRGB_OK;
+}

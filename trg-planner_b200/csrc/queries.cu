@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(kTqThreads) k_collision_tq(MapView m, const fl
     int res = 0;
     if (i < n) {
       p = __ldg(q + i);
-      res = thread_is_collision(m, p.x, p.y, r, hthr, rthr, zcol, kTqThreads, cap);
+      res = thread_is_collision(m, p.x, p.y, r, hthr, rthr, zcol, kTqThreads);
     }
     TQ_FALLBACK_BEGIN(res)
       const float qx = __shfl_sync(FULL, p.x, src), qy = __shfl_sync(FULL, p.y, src);
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(kTqThreads) k_sample_window_tq(
       // sample = node->pos_.head(2) + Vector2f(e*cos, e*sin)   (trg.cpp:396-397); d = (e*cos, e*sin)
       sx = __fadd_rn(np.x, d.x);
       sy = __fadd_rn(np.y, d.y);
-      res = thread_is_collision(m, sx, sy, r, hthr, rthr, zcol, kTqThreads, cap);
+      res = thread_is_collision(m, sx, sy, r, hthr, rthr, zcol, kTqThreads);
     }
     TQ_FALLBACK_BEGIN(res)
       const float qx = __shfl_sync(FULL, sx, src), qy = __shfl_sync(FULL, sy, src);
@@ -446,82 +446,133 @@ __global__ void __launch_bounds__(kTqThreads) k_sample_window_tq(
   }
 }
 
-__global__ void __launch_bounds__(kTqThreads) k_edge_eval_tq(MapView m, const float* __restrict__ p1_xyz,
-                                                             const float2* __restrict__ p2_xy, int64_t n, float rs,
-                                                             float hthr, float cthr, int cap,
-                                                             uint8_t* __restrict__ stage_out,
-                                                             float* __restrict__ w_out, float* __restrict__ dist_out,
-                                                             int32_t* __restrict__ npts_out) {
+// ---- K4 fast path, two launches on one stream ------------------------------------------------
+// (a) k_edge_collide_tq: one thread per (edge, segment sample k). Sample k sits at the k-th value
+//     of the reference's accumulating float counter `for (float i = 0; i < dist; i += ds)`
+//     (trg.cpp:283). Any colliding sample marks the edge TRGB_EDGE_COLLISION in `stage`
+//     (zeroed by the launcher). kmax = samples needed by the longest edge of the batch.
+// (b) k_edge_pca: kPcaLanes lanes per edge split the cell rows of the ellipse gather, combine
+//     their covariance sums and run the Jacobi SVD; edges already marked colliding are skipped.
+__global__ void __launch_bounds__(kTqThreads) k_edge_collide_tq(MapView m, const float* __restrict__ p1_xyz,
+                                                                const float2* __restrict__ p2_xy, int64_t n, int kmax,
+                                                                float rs, float hthr, float cthr, int cap,
+                                                                uint8_t* __restrict__ stage) {
   extern __shared__ float zsm[];
   float* zcol = zsm + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  for (int64_t base = (int64_t)blockIdx.x * kTqThreads; base < n; base += (int64_t)gridDim.x * kTqThreads) {
-    const int64_t i = base + threadIdx.x;
-    float p1x = 0.f, p1y = 0.f, p1z = 0.f, p2x = 0.f, p2y = 0.f;
-    int stage = TRGB_EDGE_OK, npts = 0, res = 0;
-    float weight = 0.f, dist = 0.f;
-    if (i < n) {
-      p1x = __ldg(p1_xyz + 3 * i); p1y = __ldg(p1_xyz + 3 * i + 1); p1z = __ldg(p1_xyz + 3 * i + 2);
-      const float2 p2 = __ldg(p2_xy + i);
-      p2x = p2.x; p2y = p2.y;
-      const EdgeGeom g = edge_geom(p1x, p1y, p2x, p2y);
-      dist = g.dist;
-      const float dirx = g.dirx, diry = g.diry;
+  const int64_t items = n * kmax;
+  for (int64_t base = (int64_t)blockIdx.x * kTqThreads; base < items; base += (int64_t)gridDim.x * kTqThreads) {
+    const int64_t it = base + threadIdx.x;
+    float sx = 0.f, sy = 0.f;
+    int res = 0;
+    int64_t e = 0;
+    if (it < items) {
+      e = it / kmax;
+      const int k = (int)(it - e * kmax);
+      const float p1x = __ldg(p1_xyz + 3 * e), p1y = __ldg(p1_xyz + 3 * e + 1);
+      const float2 p2 = __ldg(p2_xy + e);
+      const EdgeGeom g = edge_geom(p1x, p1y, p2.x, p2.y);
       const float ds = 0.5f * rs;
-      for (float t = 0.f; t < dist; t = __fadd_rn(t, ds)) {  // :282-288
-        const float sx = __fadd_rn(p1x, __fmul_rn(t, dirx)), sy = __fadd_rn(p1y, __fmul_rn(t, diry));
-        const int c = thread_is_collision(m, sx, sy, rs, hthr, cthr, zcol, kTqThreads, cap);
-        if (c == 2) { res = 2; break; }
-        if (c == 1) { stage = TRGB_EDGE_COLLISION; break; }
-      }
-      if (res != 2 && stage == TRGB_EDGE_OK) {
-        const float c = 0.5f * dist;
-        const float b = rs;
-        float a = b;
-        if (c >= b) a = __fsqrt_rn(__fadd_rn(__fmul_rn(c, c), __fmul_rn(b, b)));
-        const bool circle = (a == b);
-        const float cx = __fadd_rn(p1x, __fmul_rn(c, dirx)), cy = __fadd_rn(p1y, __fmul_rn(c, diry));
-        const float a2 = __fmul_rn(a, a), b2 = __fmul_rn(b, b);
-        const float rhs = __fmul_rn(__fmul_rn(a2, b), b);
-        const float ndiry = -diry;
-        const float rr = inflate(a, cx, cy);
-        const int cx0 = cell_coord(cx - rr, m.x0, m.inv_cell, m.W), cx1 = cell_coord(cx + rr, m.x0, m.inv_cell, m.W);
-        const int cy0 = cell_coord(cy - rr, m.y0, m.inv_cell, m.H), cy1 = cell_coord(cy + rr, m.y0, m.inv_cell, m.H);
-        int nrange = 0;
-        double sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
-        for (int row = cy0; row <= cy1; ++row) {
-          const size_t rb = (size_t)row * (size_t)m.W;
-          const uint32_t s = __ldg(m.cell_start + rb + cx0), e = __ldg(m.cell_start + rb + cx1 + 1);
-          for (uint32_t k = s; k < e; ++k) {
-            const float4 p = ld_pt(m.pts + k);
-            const float qx = __fsub_rn(p.x, cx), qy = __fsub_rn(p.y, cy);
-            const float d2 = __fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy));
-            if (!(d2 <= a2)) continue;
-            ++nrange;
-            const float px = __fadd_rn(__fmul_rn(dirx, qx), __fmul_rn(ndiry, qy));
-            const float py = __fadd_rn(__fmul_rn(diry, qx), __fmul_rn(dirx, qy));
-            if (!circle && !(__fadd_rn(__fmul_rn(__fmul_rn(px, px), b2), __fmul_rn(__fmul_rn(py, py), a2)) < rhs)) continue;
-            const double X = px, Y = py, Z = (double)p.z - (double)p1z;
-            ++npts;
-            sx += X; sy += Y; sz += Z;
-            sxx += X * X; sxy += X * Y; sxz += X * Z; syy += Y * Y; syz += Y * Z; szz += Z * Z;
-          }
-        }
-        if (nrange == 0) stage = TRGB_EDGE_EMPTY;
-        else if (npts < 3) stage = TRGB_EDGE_FEWPTS;
-        else weight = weight_from_sums(npts, sx, sy, sz, sxx, sxy, sxz, syy, syz, szz);
+      float t = 0.f;
+      for (int j = 0; j < k; ++j) t = __fadd_rn(t, ds);
+      // the thread of the last slot also walks any samples beyond kmax (long edges), so no
+      // sample is ever skipped whatever kmax is
+      while (t < g.dist) {
+        sx = __fadd_rn(p1x, __fmul_rn(t, g.dirx));
+        sy = __fadd_rn(p1y, __fmul_rn(t, g.diry));
+        res = thread_is_collision(m, sx, sy, rs, hthr, cthr, zcol, kTqThreads);
+        if (res != 0 || k != kmax - 1) break;
+        t = __fadd_rn(t, ds);
       }
     }
     TQ_FALLBACK_BEGIN(res)
-      const float a1 = __shfl_sync(FULL, p1x, src), b1 = __shfl_sync(FULL, p1y, src), c1 = __shfl_sync(FULL, p1z, src);
-      const float a2_ = __shfl_sync(FULL, p2x, src), b2_ = __shfl_sync(FULL, p2y, src);
-      int st, np_;
-      float w_, d_;
-      warp_edge_eval(m, a1, b1, c1, a2_, b2_, rs, hthr, cthr, wbuf, 32 * cap, &st, &w_, &d_, &np_);
-      if (lane == src) { stage = st; weight = w_; dist = d_; npts = np_; res = 0; }
+      const float qx = __shfl_sync(FULL, sx, src), qy = __shfl_sync(FULL, sy, src);
+      const bool c = warp_is_collision(m, qx, qy, rs, hthr, cthr, wbuf, 32 * cap, nullptr);
+      if (lane == src) res = c ? 1 : 0;
     TQ_FALLBACK_END
-    if (i < n) {
-      stage_out[i] = (uint8_t)stage;
+    if (it < items && res == 1) stage[e] = (uint8_t)TRGB_EDGE_COLLISION;
+  }
+}
+
+constexpr int kPcaLanes = 4;
+__global__ void __launch_bounds__(256) k_edge_pca(MapView m, const float* __restrict__ p1_xyz,
+                                                  const float2* __restrict__ p2_xy, int64_t n, float rs,
+                                                  uint8_t* __restrict__ stage_io, float* __restrict__ w_out,
+                                                  float* __restrict__ dist_out, int32_t* __restrict__ npts_out) {
+  const int sub = threadIdx.x & (kPcaLanes - 1);
+  const int64_t gstride = (int64_t)gridDim.x * (256 / kPcaLanes);
+  for (int64_t base = (int64_t)blockIdx.x * (256 / kPcaLanes); base < n; base += gstride) {
+    const int64_t i = base + (threadIdx.x / kPcaLanes);
+    const bool live = i < n;
+    float p1x = 0.f, p1y = 0.f, p1z = 0.f, p2x = 1.f, p2y = 0.f;
+    int st = TRGB_EDGE_OK;
+    if (live) {
+      p1x = __ldg(p1_xyz + 3 * i); p1y = __ldg(p1_xyz + 3 * i + 1); p1z = __ldg(p1_xyz + 3 * i + 2);
+      const float2 p2 = __ldg(p2_xy + i);
+      p2x = p2.x; p2y = p2.y;
+      st = stage_io[i];
+    }
+    const EdgeGeom g = edge_geom(p1x, p1y, p2x, p2y);
+    const float dist = g.dist, dirx = g.dirx, diry = g.diry;
+    int nrange = 0, npts = 0;
+    double sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
+    if (live && st != TRGB_EDGE_COLLISION) {
+      // :291-297 ellipse with foci at the two nodes (circle when the nodes are close)
+      const float c = 0.5f * dist;
+      const float b = rs;
+      float a = b;
+      if (c >= b) a = __fsqrt_rn(__fadd_rn(__fmul_rn(c, c), __fmul_rn(b, b)));
+      const bool circle = (a == b);
+      const float cx = __fadd_rn(p1x, __fmul_rn(c, dirx)), cy = __fadd_rn(p1y, __fmul_rn(c, diry));
+      const float a2 = __fmul_rn(a, a), b2 = __fmul_rn(b, b);
+      const float rhs = __fmul_rn(__fmul_rn(a2, b), b);  // a*a*b*b, left to right
+      const float ndiry = -diry;
+      const float rr = inflate(a, cx, cy);
+      const int cx0 = cell_coord(cx - rr, m.x0, m.inv_cell, m.W), cx1 = cell_coord(cx + rr, m.x0, m.inv_cell, m.W);
+      const int cy0 = cell_coord(cy - rr, m.y0, m.inv_cell, m.H), cy1 = cell_coord(cy + rr, m.y0, m.inv_cell, m.H);
+      for (int row = cy0 + sub; row <= cy1; row += kPcaLanes) {
+        const size_t rb = (size_t)row * (size_t)m.W;
+        const uint32_t s = __ldg(m.cell_start + rb + cx0), e = __ldg(m.cell_start + rb + cx1 + 1);
+#pragma unroll 4
+        for (uint32_t k = s; k < e; ++k) {
+          const float4 p = ld_pt(m.pts + k);
+          const float qx = __fsub_rn(p.x, cx), qy = __fsub_rn(p.y, cy);
+          const float d2 = __fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy));
+          if (!(d2 <= a2)) continue;  // kd_nearest_range2(center, a)
+          ++nrange;
+          // :312-316 p2d = R * (pt - center), R = [dir.x -dir.y; dir.y dir.x]
+          const float px = __fadd_rn(__fmul_rn(dirx, qx), __fmul_rn(ndiry, qy));
+          const float py = __fadd_rn(__fmul_rn(diry, qx), __fmul_rn(dirx, qy));
+          if (!circle && !(__fadd_rn(__fmul_rn(__fmul_rn(px, px), b2), __fmul_rn(__fmul_rn(py, py), a2)) < rhs)) continue;
+          // covariance sums in double about the pivot z = p1.z (see warp_edge_eval)
+          const double X = px, Y = py, Z = (double)p.z - (double)p1z;
+          ++npts;
+          sx += X; sy += Y; sz += Z;
+          sxx += X * X; sxy += X * Y; sxz += X * Z; syy += Y * Y; syz += Y * Z; szz += Z * Z;
+        }
+      }
+    }
+    // combine the kPcaLanes partial sums (all lanes of the warp take part; dead groups add zeros)
+#pragma unroll
+    for (int d = 1; d < kPcaLanes; d <<= 1) {
+      nrange += __shfl_xor_sync(FULL, nrange, d);
+      npts += __shfl_xor_sync(FULL, npts, d);
+      sx += __shfl_xor_sync(FULL, sx, d); sy += __shfl_xor_sync(FULL, sy, d); sz += __shfl_xor_sync(FULL, sz, d);
+      sxx += __shfl_xor_sync(FULL, sxx, d); sxy += __shfl_xor_sync(FULL, sxy, d); sxz += __shfl_xor_sync(FULL, sxz, d);
+      syy += __shfl_xor_sync(FULL, syy, d); syz += __shfl_xor_sync(FULL, syz, d); szz += __shfl_xor_sync(FULL, szz, d);
+    }
+    if (live && sub == 0) {
+      float weight = 0.f;
+      if (st == TRGB_EDGE_COLLISION) {
+        npts = 0;
+      } else if (nrange == 0) {
+        st = TRGB_EDGE_EMPTY;   // :305
+      } else if (npts < 3) {
+        st = TRGB_EDGE_FEWPTS;  // :327
+      } else {
+        weight = weight_from_sums(npts, sx, sy, sz, sxx, sxy, sxz, syy, syz, szz);
+      }
+      stage_io[i] = (uint8_t)st;
       w_out[i] = weight;
       dist_out[i] = dist;
       if (npts_out) npts_out[i] = npts;
@@ -561,11 +612,9 @@ static int launch_cfg(const trgb_map* m, float r, int64_t n_items, int* grid, in
 static bool tq_cfg(const trgb_map* m, float r, int64_t n_items, int* grid, int* cap, size_t* smem, const void* kernel) {
   if (m->force_warp_path) return false;
   const double k = map_density(m) * 3.14159265358979 * (double)r * r;
-  int c = (int)(1.6 * k) + 12;
-  c = (c + 7) & ~7;
-  if (c > 96) return false;
-  *cap = c;
-  *smem = (size_t)kTqThreads * c * sizeof(float);
+  if (k > 0.625 * kTqCap) return false;  // expected population must leave 60 % head room in the column
+  *cap = kTqCap;
+  *smem = (size_t)kTqThreads * kTqCap * sizeof(float);
   if (*smem > 48 * 1024 &&
       cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem) != cudaSuccess) {
     cudaGetLastError();
@@ -664,11 +713,22 @@ extern "C" int trgb_edge_eval_launch(const trgb_map* m, const float* d_p1_xyz, c
   int grid, cap; size_t smem;
   // the ellipse gather reaches sqrt((1.25*expand)^2 + r^2) but keeps nothing in shared memory;
   // the shared buffer only serves the radius-robot_size collision samples
-  if (tq_cfg(m, prm->robot_size, n, &grid, &cap, &smem, (const void*)k_edge_eval_tq)) {
-    ProfScope ps("k_edge_eval", m->stream, (double)n);
-    k_edge_eval_tq<<<grid, kTqThreads, smem, m->stream>>>(m->view, d_p1_xyz, reinterpret_cast<const float2*>(d_p2_xy), n,
-                                                          prm->robot_size, prm->height_threshold,
-                                                          prm->collision_threshold, cap, d_stage, d_weight, d_dist, d_npts);
+  const int kmax = prm->max_edge_samples > 0 ? prm->max_edge_samples : 8;
+  if (tq_cfg(m, prm->robot_size, n * kmax, &grid, &cap, &smem, (const void*)k_edge_collide_tq)) {
+    TRGB_CUDA(cudaMemsetAsync(d_stage, 0, (size_t)n, m->stream));
+    {
+      ProfScope ps("k_edge_collide", m->stream, (double)n);
+      k_edge_collide_tq<<<grid, kTqThreads, smem, m->stream>>>(m->view, d_p1_xyz, reinterpret_cast<const float2*>(d_p2_xy),
+                                                               n, kmax, prm->robot_size, prm->height_threshold,
+                                                               prm->collision_threshold, cap, d_stage);
+    }
+    {
+      ProfScope ps("k_edge_pca", m->stream, (double)n);
+      const int64_t need = (n + (256 / kPcaLanes) - 1) / (256 / kPcaLanes);
+      const int g2 = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)sm_count() * 8));
+      k_edge_pca<<<g2, 256, 0, m->stream>>>(m->view, d_p1_xyz, reinterpret_cast<const float2*>(d_p2_xy), n,
+                                            prm->robot_size, d_stage, d_weight, d_dist, d_npts);
+    }
     TRGB_CUDA(cudaGetLastError());
     return TRGB_OK;
   }

@@ -6,6 +6,8 @@
 #pragma once
 #include <cuda_runtime_api.h>
 
+#include "trgb_kernels.h"
+
 #include <cstddef>
 #include <cstdint>
 #include <stdexcept>
@@ -78,7 +80,7 @@ class DrawBuffer {
   // append n (x,y) pairs that follow the current end
   void append(const float* xy, size_t n, cudaStream_t s) {
     if (count_ + n > cap_) {
-      size_t want = cap_ ? cap_ : (size_t)1 << 16;
+      size_t want = cap_ ? cap_ : (size_t)1 << 21;
       while (want < count_ + n) want *= 2;
       float* nd = nullptr;
       cuda_check(cudaMalloc(reinterpret_cast<void**>(&nd), want * 2 * sizeof(float)), "cudaMalloc(draws)");
@@ -102,7 +104,15 @@ class DrawBuffer {
 // All staging state of one TRG instance.
 class DeviceSession {
  public:
-  ~DeviceSession() { if (copy_) cudaStreamDestroy(copy_); }
+  ~DeviceSession() {
+    if (copy_) cudaStreamDestroy(copy_);
+    if (nodes) trgb_nodes_destroy(nodes);
+  }
+  // device grid over the nodes of the graph being expanded (K5) and how much of node_seq it holds
+  trgb_nodes* nodes = nullptr;
+  const void* nodes_owner = nullptr;
+  float nodes_box[5] = {0, 0, 0, 0, 0};
+  size_t nodes_uploaded = 0;
   Arena in, out;    // batch staging (windows, speculative evaluation)
   Arena in2, out2;  // mid-commit flushes: must not disturb the results `out` still holds
   DrawBuffer draws;

@@ -230,9 +230,19 @@ class NodeGrid {
     y0_ = y0 - 2.f * cell;
     w_ = static_cast<int>(std::floor((x1 - x0_) * inv_)) + 4;
     h_ = static_cast<int>(std::floor((y1 - y0_) * inv_)) + 4;
-    cells_.assign(static_cast<size_t>(w_) * h_, Cell{});
+    bw_ = (w_ + kTile - 1) / kTile;
+    const int bh = (h_ + kTile - 1) / kTile;
+    cells_.assign(static_cast<size_t>(bw_) * bh * kTile * kTile, Cell{});
     over_.clear();
     count_ = 0;
+  }
+  // prefetch the buckets a nearest() query at (qx, qy) will read first
+  void prefetch(float qx, float qy) const {
+    if (cells_.empty()) return;
+    const int qcx = cx(qx), qcy = cy(qy);
+    for (int yy = qcy - 1; yy <= qcy + 1; ++yy)
+      for (int xx = qcx - 1; xx <= qcx + 1; ++xx)
+        if (xx >= 0 && yy >= 0 && xx < w_ && yy < h_) __builtin_prefetch(&cells_[cidx(xx, yy)], 0, 1);
   }
   bool configured() const { return w_ > 0; }
   void clear() {
@@ -245,7 +255,7 @@ class NodeGrid {
   // entries are numbered in insertion order (0, 1, 2, ...)
   int insert(float x, float y) {
     const int id = static_cast<int>(count_++);
-    Cell& c = cells_[static_cast<size_t>(cy(y)) * w_ + cx(x)];
+    Cell& c = cells_[cidx(cx(x), cy(y))];
     if (c.n < kInline) {
       c.x[c.n] = x; c.y[c.n] = y; c.id[c.n] = id;
       ++c.n;
@@ -290,12 +300,28 @@ class NodeGrid {
     const int cx0 = cx(qx - rr), cx1 = cx(qx + rr), cy0 = cy(qy - rr), cy1 = cy(qy + rr);
     for (int yy = cy0; yy <= cy1; ++yy)
       for (int xx = cx0; xx <= cx1; ++xx)
-        visit(cells_[static_cast<size_t>(yy) * w_ + xx], [&](float x, float y, int e) {
+        visit(cells_[cidx(xx, yy)], [&](float x, float y, int e) {
           const float dx = x - qx, dy = y - qy;
           float d2 = 0.f;
           d2 += dx * dx;
           d2 += dy * dy;
           if (d2 <= r2) f(e);
+        });
+  }
+  // entries with fl(dx^2+dy^2) <= d2max, searching the cells within `reach` of the query
+  template <class F>
+  void for_each_within_d2(float qx, float qy, float d2max, float reach, F&& f) const {
+    if (count_ == 0) return;
+    const float rr = reach * 1.0001f + 1e-5f + 4e-6f * (std::fabs(qx) + std::fabs(qy));
+    const int cx0 = cx(qx - rr), cx1 = cx(qx + rr), cy0 = cy(qy - rr), cy1 = cy(qy + rr);
+    for (int yy = cy0; yy <= cy1; ++yy)
+      for (int xx = cx0; xx <= cx1; ++xx)
+        visit(cells_[cidx(xx, yy)], [&](float x, float y, int e) {
+          const float dx = x - qx, dy = y - qy;
+          float d2 = 0.f;
+          d2 += dx * dx;
+          d2 += dy * dy;
+          if (d2 <= d2max) f(e);
         });
   }
   int count_in_range(float qx, float qy, float r) const {
@@ -306,6 +332,13 @@ class NodeGrid {
 
  private:
   static constexpr int kInline = 4;
+  // buckets are stored in 8x8 tiles (64 buckets = 4 KB = one page): a 3x3 neighbourhood lives in
+  // at most four pages instead of three rows tens of KB apart
+  static constexpr int kTile = 8;
+  size_t cidx(int xx, int yy) const {
+    return (static_cast<size_t>(yy / kTile) * bw_ + static_cast<size_t>(xx / kTile)) * (kTile * kTile) +
+           static_cast<size_t>((yy % kTile) * kTile + (xx % kTile));
+  }
   struct alignas(64) Cell {
     uint32_t n = 0;
     int32_t over = -1;  // head of the overflow chain (index into over_)
@@ -334,7 +367,7 @@ class NodeGrid {
   }
   void scan_cell(int xx, int yy, float qx, float qy, Nearest& best) const {
     if (xx < 0 || yy < 0 || xx >= w_ || yy >= h_) return;
-    visit(cells_[static_cast<size_t>(yy) * w_ + xx], [&](float x, float y, int e) {
+    visit(cells_[cidx(xx, yy)], [&](float x, float y, int e) {
       const float dx = x - qx, dy = y - qy;
       float d2 = 0.f;
       d2 += dx * dx;
@@ -360,7 +393,7 @@ class NodeGrid {
   }
 
   float cell_ = 1.f, inv_ = 1.f, x0_ = 0.f, y0_ = 0.f;
-  int w_ = 0, h_ = 0;
+  int w_ = 0, h_ = 0, bw_ = 0;
   size_t count_ = 0;
   std::vector<Cell> cells_;
   std::vector<Over> over_;

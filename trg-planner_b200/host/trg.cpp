@@ -66,6 +66,7 @@ TRG::TRG(bool isVerbose, float expand_dist, float robot_size, int sample_num, fl
 }
 
 TRG::~TRG() {
+  joinDrawPrefetch();
   for (auto& kv : trgMap_) {
     if (kv.second->map_index) trgb_map_destroy(kv.second->map_index);
     kv.second->map_index = nullptr;
@@ -90,6 +91,7 @@ void TRG::resetMap(std::string type) {  // trg.cpp:739-744
 }
 
 void TRG::reseed(uint32_t seed) {
+  joinDrawPrefetch();  // a block generated ahead belongs to the old stream
   gen_.seed(seed);
   distr_.reset();
   draw_u_.clear();
@@ -111,22 +113,42 @@ TRG::Edge* TRG::newEdge(int dst, float w, float d) {
 // ================================================================================================
 // sampling stream
 // ================================================================================================
-void TRG::ensureDraws(size_t upto) {
-  const size_t have = draw_base_ + draw_u_.size();
-  if (upto <= have) return;
-  size_t want = std::max(upto, have + (size_t)(1 << 15));  // generate in blocks
-  const size_t first = draw_u_.size();
-  draw_u_.resize(want - draw_base_);
-  draw_xy_.resize(2 * (want - draw_base_));
+// One block of the sampling stream: u_k = distr_(gen_), then the offsets of trg.cpp:395-397
+//   float angle = distr_(gen_) * 2 * M_PI;  Vector2f(expand_dist * cos(angle), expand_dist * sin(angle))
+// (float overloads, glibc). Runs on a helper thread one block ahead of consumption: the stream is
+// consumed strictly in order, so generating it early changes nothing.
+void TRG::generateDrawBlock(size_t n, std::vector<float>& u, std::vector<float>& xy) {
+  u.resize(n);
+  xy.resize(2 * n);
   const float e = param_.expand_dist;
+  for (size_t k = 0; k < n; ++k) {
+    const float v = distr_(gen_);
+    u[k] = v;
+    const float angle = v * 2 * M_PI;
+    xy[2 * k]     = e * cosf(angle);
+    xy[2 * k + 1] = e * sinf(angle);
+  }
+}
+
+void TRG::joinDrawPrefetch() {
+  if (draw_prefetch_.valid()) draw_prefetch_.get();
+}
+
+void TRG::ensureDraws(size_t upto) {
   auto t0 = Clock::now();
-  for (size_t k = first; k < draw_u_.size(); ++k) {
-    const float u = distr_(gen_);
-    draw_u_[k]    = u;
-    // trg.cpp:395-397: float angle = distr_(gen_) * 2 * M_PI; Vector2f(e * cos(angle), e * sin(angle))
-    const float angle   = u * 2 * M_PI;
-    draw_xy_[2 * k]     = e * cosf(angle);
-    draw_xy_[2 * k + 1] = e * sinf(angle);
+  while (upto > draw_base_ + draw_u_.size()) {
+    const size_t have = draw_base_ + draw_u_.size();
+    const size_t block = have < ((size_t)1 << 15) ? ((size_t)1 << 12) : ((size_t)1 << 18);
+    if (draw_prefetch_.valid()) {
+      draw_prefetch_.get();  // block generated ahead by the helper
+    } else {
+      generateDrawBlock(block, pre_u_, pre_xy_);
+    }
+    draw_u_.insert(draw_u_.end(), pre_u_.begin(), pre_u_.end());
+    draw_xy_.insert(draw_xy_.end(), pre_xy_.begin(), pre_xy_.end());
+    // start the next block right away once the stream is clearly in heavy use
+    if (draw_u_.size() >= ((size_t)1 << 15))
+      draw_prefetch_ = std::async(std::launch::async, [this] { generateDrawBlock((size_t)1 << 18, pre_u_, pre_xy_); });
   }
   stat_["us_draws"] += (int64_t)(1e6 * since(t0));
 }
@@ -258,7 +280,10 @@ void TRG::nodeIndexReset(trgStruct& g) {
   g.node_seq.clear();
   g.node_grid.clear();
   g.node_tree.clear();
+  g.grid_built = 0;
   g.tree_built = 0;
+  g.iter_rank.clear();
+  if (dev_ && dev_->nodes_owner == &g) dev_->nodes_owner = nullptr;  // device copy is stale
 }
 
 void TRG::ensureGrid(trgStruct& g) {
@@ -272,9 +297,16 @@ void TRG::ensureGrid(trgStruct& g) {
 }
 
 void TRG::nodeIndexInsert(trgStruct& g, Node* n) {
+  g.node_seq.push_back(n);  // the host grid / order tree catch up lazily (ensureGridBuilt / ensureTree)
+  if (!g.iter_rank.empty()) g.iter_rank.clear();
+}
+
+void TRG::ensureGridBuilt(trgStruct& g) {
   ensureGrid(g);
-  g.node_grid.insert(n->pos_.x(), n->pos_.y());
-  g.node_seq.push_back(n);
+  for (; g.grid_built < g.node_seq.size(); ++g.grid_built) {
+    Node* n = g.node_seq[g.grid_built];
+    g.node_grid.insert(n->pos_.x(), n->pos_.y());
+  }
 }
 
 void TRG::ensureTree(trgStruct& g) {
@@ -296,6 +328,7 @@ void TRG::ensureTree(trgStruct& g) {
 // kd_nearest2 on node_tree (kdtree.c:364-417): exact float argmin; exact ties by tree visit order
 TRG::Node* TRG::nearestNode(trgStruct& g, float x, float y) {
   if (g.node_seq.empty()) return nullptr;
+  ensureGridBuilt(g);
   auto nn = g.node_grid.nearest(x, y);
   if (nn.entry >= 0 && !nn.tie) return g.node_seq[nn.entry];
   ensureTree(g);
@@ -315,6 +348,7 @@ void TRG::rangeNodesOrdered(trgStruct& g, float x, float y, float r, std::vector
 
 int TRG::countNodesInRange(trgStruct& g, float x, float y, float r) {
   if (g.node_seq.empty()) return 0;
+  ensureGridBuilt(g);
   return g.node_grid.count_in_range(x, y, r);
 }
 
@@ -413,7 +447,7 @@ void TRG::wireEdge(Node* node1, Node* node2, std::string type) {  // trg.cpp:254
   trgStruct& graph = *trgMap_.at(type);
   const float p1[3] = {node1->pos_.x(), node1->pos_.y(), node1->pos_.z()};
   const float p2[3] = {node2->pos_.x(), node2->pos_.y(), node2->pos_.z()};
-  TrgbEdgeParams prm{param_.robot_size, param_.height_threshold, param_.collision_threshold};
+  TrgbEdgeParams prm{param_.robot_size, param_.height_threshold, param_.collision_threshold, 0};
   uint8_t stage = 0;
   float w = 0.f, d = 0.f;
   K(trgb_edge_eval_batch(requireMap(graph, "wireEdge"), p1, p2, 1, &prm, &stage, &w, &d, nullptr), "trgb_edge_eval_batch");
@@ -443,6 +477,77 @@ void TRG::wireEdge(Node* node1, Node* node2, std::string type) {  // trg.cpp:254
 // ================================================================================================
 namespace trg_b200 {
 
+// Nodes created while the current batch is being committed: they are not yet in the device node
+// grid that produced the batch's nearest-node candidates, so the commit merges those candidates
+// with an exact nearest search over this small, cache-resident hash grid.
+class ChunkTable {
+ public:
+  void configure(float x0, float y0, float cell) { x0_ = x0; y0_ = y0; cell_ = cell; inv_ = 1.0f / cell; }
+  bool empty() const { return ent_.empty(); }
+  void clear() {
+    for (uint32_t h : touched_) head_[h] = -1;
+    touched_.clear();
+    ent_.clear();
+  }
+  void insert(float x, float y, int seq) {
+    const int cx = cc(x, x0_), cy = cc(y, y0_);
+    const uint32_t h = hash(cx, cy);
+    if (head_[h] < 0) touched_.push_back(h);
+    ent_.push_back({x, y, seq, head_[h], cx, cy});
+    head_[h] = static_cast<int32_t>(ent_.size()) - 1;
+  }
+  // improve (d2, seq, tie) with any stored node that is strictly nearer; equal distance -> tie
+  void refine(float qx, float qy, float& d2, int& seq, bool& tie) const {
+    if (ent_.empty()) return;
+    if (!(d2 < std::numeric_limits<float>::infinity())) {
+      for (const E& e : ent_) consider(e, qx, qy, d2, seq, tie);
+      return;
+    }
+    const int qcx = cc(qx, x0_), qcy = cc(qy, y0_);
+    const float fuzz = 1e-5f + 4e-6f * (std::fabs(qx) + std::fabs(qy));
+    for (int R = 1;; ++R) {
+      if (R == 1) {
+        for (int yy = qcy - 1; yy <= qcy + 1; ++yy)
+          for (int xx = qcx - 1; xx <= qcx + 1; ++xx) scan(xx, yy, qx, qy, d2, seq, tie);
+      } else {
+        for (int xx = qcx - R; xx <= qcx + R; ++xx) { scan(xx, qcy - R, qx, qy, d2, seq, tie); scan(xx, qcy + R, qx, qy, d2, seq, tie); }
+        for (int yy = qcy - R + 1; yy <= qcy + R - 1; ++yy) { scan(qcx - R, yy, qx, qy, d2, seq, tie); scan(qcx + R, yy, qx, qy, d2, seq, tie); }
+      }
+      // everything outside the scanned block is at least R whole cells away
+      const float g = static_cast<float>(R) * cell_ * 0.9999f - fuzz;
+      if (g > 0.f && d2 <= g * g) break;
+      if (R > 64) {  // pathological (nearest far away): finish exhaustively
+        for (const E& e : ent_) consider(e, qx, qy, d2, seq, tie);
+        break;
+      }
+    }
+  }
+
+ private:
+  struct E { float x, y; int seq; int32_t next; int cx, cy; };
+  static constexpr uint32_t kMask = (1u << 14) - 1;
+  static uint32_t hash(int cx, int cy) {
+    return (static_cast<uint32_t>(cx) * 73856093u ^ static_cast<uint32_t>(cy) * 19349663u) & kMask;
+  }
+  int cc(float v, float o) const { return static_cast<int>(std::floor((v - o) * inv_)); }
+  static void consider(const E& e, float qx, float qy, float& d2, int& seq, bool& tie) {
+    const float dx = e.x - qx, dy = e.y - qy;
+    float v = 0.f;
+    v += dx * dx;
+    v += dy * dy;
+    if (v < d2) { d2 = v; seq = e.seq; tie = false; }
+    else if (v == d2 && e.seq != seq) tie = true;
+  }
+  void scan(int cx, int cy, float qx, float qy, float& d2, int& seq, bool& tie) const {
+    for (int32_t i = head_[hash(cx, cy)]; i >= 0; i = ent_[i].next)
+      if (ent_[i].cx == cx && ent_[i].cy == cy) consider(ent_[i], qx, qy, d2, seq, tie);
+  }
+  float x0_ = 0.f, y0_ = 0.f, cell_ = 1.f, inv_ = 1.f;
+  std::vector<int32_t> head_ = std::vector<int32_t>(kMask + 1, -1);
+  std::vector<uint32_t> touched_;
+  std::vector<E> ent_;
+};
+
 class Expander {
  public:
   Expander(TRG& t, TRG::trgStruct& g)
@@ -452,6 +557,23 @@ class Expander {
     // trg.cpp:429 — `float - float < double * float`
     step3_ = (P_.expand_dist - P_.robot_size < 0.25 * P_.expand_dist);
     mean_  = 1.15 * P_.sample_num;
+    // device grid over the graph's nodes (K5), kept across expansions of the same graph
+    DeviceSession& d = *t.dev_;
+    const float cell = 1.5f * P_.robot_size;
+    const float box[5] = {t.global_trg_.bbox[0], t.global_trg_.bbox[1], t.global_trg_.bbox[2], t.global_trg_.bbox[3], cell};
+    if (!d.nodes || std::memcmp(box, d.nodes_box, sizeof(box)) != 0) {
+      if (d.nodes) trgb_nodes_destroy(d.nodes);
+      d.nodes = nullptr;
+      K(trgb_nodes_create(&d.nodes, box[0] - 2.f, box[1] - 2.f, box[2] + 2.f, box[3] + 2.f, cell), "trgb_nodes_create");
+      std::memcpy(d.nodes_box, box, sizeof(box));
+      d.nodes_owner = nullptr;
+    }
+    if (d.nodes_owner != &g || d.nodes_uploaded > g.node_seq.size()) {
+      K(trgb_nodes_reset(d.nodes, st_), "trgb_nodes_reset");
+      d.nodes_owner = &g;
+      d.nodes_uploaded = 0;
+    }
+    table_.configure(box[0], box[1], cell);
   }
 
   void run(const std::vector<TRG::Node*>& roots) {
@@ -549,8 +671,10 @@ class Expander {
         guess_[i] = gpos;
         hi = std::max(hi, gpos + (size_t)W);
       }
+      auto tp0 = Clock::now();
       t_.ensureDraws(hi);
       t_.syncDraws();
+      auto tp1 = Clock::now();
       DrawBuffer& db = t_.dev_->draws;
       Arena& in  = t_.dev_->in;
       Arena& out = t_.dev_->out;
@@ -566,6 +690,7 @@ class Expander {
         xy[2 * (i - done) + 1] = chunk_[i].node->pos_.y();
         fd[i - done]           = (int32_t)(guess_[i] - db.base());
       }
+      auto tp2 = Clock::now();
       in.h2d(st_);
       out.zero_d(o_mk, n_live * words * sizeof(unsigned long long), st_);
       K(trgb_sample_window_launch(map_, in.d<float>(o_xy), in.d<int32_t>(o_fd), db.dev(), (int64_t)n_live, W,
@@ -574,6 +699,10 @@ class Expander {
         "trgb_sample_window_launch");
       out.d2h(st_);
       cuda_check(cudaStreamSynchronize(st_), "sync(windows)");
+      auto tp3 = Clock::now();
+      t_.stat_["us_w_draws"] += (int64_t)(1e6 * std::chrono::duration<double>(tp1 - tp0).count());
+      t_.stat_["us_w_prep"] += (int64_t)(1e6 * std::chrono::duration<double>(tp2 - tp1).count());
+      t_.stat_["us_w_gpu"] += (int64_t)(1e6 * std::chrono::duration<double>(tp3 - tp2).count());
       t_.dev_->batches++;
       t_.stat_["window_launches"]++;
       t_.stat_["window_tests"] += (int64_t)n_live * W;
@@ -633,15 +762,30 @@ class Expander {
     Arena& in  = t_.dev_->in;
     Arena& out = t_.dev_->out;
     const size_t ne = ns + nd;
-    in.reset(Arena::padded(ne * 3 * sizeof(float)) + Arena::padded(ne * 2 * sizeof(float)));
-    out.reset(Arena::padded(ns * sizeof(float)) + Arena::padded(ns) + Arena::padded(ne) + 2 * Arena::padded(ne * sizeof(float)));
+    DeviceSession& dv = *t_.dev_;
+    const size_t n_new = g_.node_seq.size() - dv.nodes_uploaded;  // nodes the device grid has not seen yet
+    in.reset(Arena::padded(ne * 3 * sizeof(float)) + Arena::padded(ne * 2 * sizeof(float)) + Arena::padded(n_new * 2 * sizeof(float)));
+    out.reset(Arena::padded(ns * sizeof(float)) + Arena::padded(ns) + Arena::padded(ne) + 2 * Arena::padded(ne * sizeof(float)) +
+              2 * Arena::padded(ns * sizeof(float)) + Arena::padded(ns));
     const size_t o_p1 = in.take(ne * 3 * sizeof(float));
     const size_t o_p2 = in.take(ne * 2 * sizeof(float));
+    const size_t o_nn = in.take(n_new * 2 * sizeof(float));
     const size_t o_z  = out.take(ns * sizeof(float));
     const size_t o_t  = out.take(ns);
     const size_t o_s  = out.take(ne);
     const size_t o_w  = out.take(ne * sizeof(float));
     const size_t o_d  = out.take(ne * sizeof(float));
+    const size_t o_ni = out.take(ns * sizeof(int32_t));
+    const size_t o_nd = out.take(ns * sizeof(float));
+    const size_t o_nt = out.take(ns);
+    {
+      float* nn = in.h<float>(o_nn);
+      for (size_t i = 0; i < n_new; ++i) {
+        const TRG::Node* nd = g_.node_seq[dv.nodes_uploaded + i];
+        nn[2 * i] = nd->pos_.x();
+        nn[2 * i + 1] = nd->pos_.y();
+      }
+    }
     float* p1 = in.h<float>(o_p1);
     float* p2 = in.h<float>(o_p2);
     size_t k = 0;
@@ -657,10 +801,17 @@ class Expander {
       ++k;
     }
     in.h2d(st_);
-    if (ns)
+    K(trgb_nodes_append_launch(dv.nodes, in.d<float>(o_nn), (int64_t)n_new, st_), "trgb_nodes_append_launch");
+    dv.nodes_uploaded += n_new;
+    table_.clear();  // every node created so far is now on the device
+    if (ns) {
+      K(trgb_nodes_nearest_launch(dv.nodes, in.d<float>(o_p2), (int64_t)ns, out.d<int32_t>(o_ni), out.d<float>(o_nd),
+                                  out.d<uint8_t>(o_nt), st_),
+        "trgb_nodes_nearest_launch");
       K(trgb_nearest_z_launch(map_, in.d<float>(o_p2), (int64_t)ns, out.d<float>(o_z), nullptr, out.d<uint8_t>(o_t)),
         "trgb_nearest_z_launch");
-    TrgbEdgeParams prm{P_.robot_size, P_.height_threshold, P_.collision_threshold};
+    }
+    TrgbEdgeParams prm{P_.robot_size, P_.height_threshold, P_.collision_threshold, 0};
     K(trgb_edge_eval_launch(map_, in.d<float>(o_p1), in.d<float>(o_p2), (int64_t)ne, &prm, out.d<uint8_t>(o_s),
                             out.d<float>(o_w), out.d<float>(o_d), nullptr),
       "trgb_edge_eval_launch");
@@ -675,6 +826,9 @@ class Expander {
     spec_.stage = out.h<uint8_t>(o_s);
     spec_.w = out.h<float>(o_w);
     spec_.d = out.h<float>(o_d);
+    spec_.nn_idx = out.h<int32_t>(o_ni);
+    spec_.nn_d2 = out.h<float>(o_nd);
+    spec_.nn_tie = out.h<uint8_t>(o_nt);
     resolveDeferred(spec_.stage + ns, spec_.w + ns, spec_.d + ns);
   }
 
@@ -722,7 +876,7 @@ class Expander {
       p2[2 * k] = d.b->pos_.x(); p2[2 * k + 1] = d.b->pos_.y();
     }
     in.h2d(st_);
-    TrgbEdgeParams prm{P_.robot_size, P_.height_threshold, P_.collision_threshold};
+    TrgbEdgeParams prm{P_.robot_size, P_.height_threshold, P_.collision_threshold, 0};
     K(trgb_edge_eval_launch(map_, in.d<float>(o_p1), in.d<float>(o_p2), (int64_t)nd, &prm, out.d<uint8_t>(o_s),
                             out.d<float>(o_w), out.d<float>(o_d), nullptr),
       "trgb_edge_eval_launch");
@@ -773,7 +927,18 @@ class Expander {
       const Sample& s = acc_[s0 + j];
       ++n_nearest_;
       FT_BEGIN();
-      TRG::Node* ex = t_.nearestNode(g_, s.x, s.y);
+      // kd_nearest2(node_tree, sample) (trg.cpp:408): device candidate (nodes that existed when the
+      // batch was evaluated) merged with the nodes created since; exact ties -> reference tree order
+      TRG::Node* ex;
+      {
+        const size_t sj = s0 + j;
+        float d2 = spec_.nn_d2[sj];
+        int seq = spec_.nn_idx[sj];
+        bool tie = spec_.nn_tie[sj] != 0;
+        if (seq < 0) d2 = std::numeric_limits<float>::infinity();
+        table_.refine(s.x, s.y, d2, seq, tie);
+        ex = (tie || seq < 0) ? t_.nearestNode(g_, s.x, s.y) : g_.node_seq[seq];
+      }
       FT_LAP(nearest);
       if (ex->state_ == TRG::NodeState::Invalid) continue;
       if (norm2(ex->pos_.x() - s.x, ex->pos_.y() - s.y) < P_.robot_size) {
@@ -788,6 +953,7 @@ class Expander {
       TRG::Node* nn = t_.newNode(g_.node_id, pos2, spec_.z[si], new_state);
       g_.nodes[g_.node_id] = nn;
       t_.nodeIndexInsert(g_, nn);
+      table_.insert(s.x, s.y, static_cast<int>(g_.node_seq.size()) - 1);
       g_.node_id++;
       // 2.1 wireEdge(node, new): slope gate on the host, geometry from the speculative batch
       bool parent_ok = false;
@@ -827,7 +993,11 @@ class Expander {
     const uint8_t* stage = nullptr;
     const float* w = nullptr;
     const float* d = nullptr;
+    const int32_t* nn_idx = nullptr;  // nearest node (node_seq index) among the nodes on the device grid
+    const float* nn_d2 = nullptr;
+    const uint8_t* nn_tie = nullptr;
   } spec_;
+  ChunkTable table_;
 
   TRG& t_;
   TRG::trgStruct& g_;
@@ -922,8 +1092,10 @@ void TRG::cleanGraph(bool updateLocal) {  // trg.cpp:491-535
   }
   for (auto& node : new_nodes) node.second->id_ = node.first;
   this->resetGraph(g.type);
-  g.nodes   = new_nodes;
+  // (the reference copy-assigns; a move leaves the same buckets, order and rehash state)
+  g.nodes   = std::move(new_nodes);
   g.node_id = new_id;
+  g.node_seq.reserve(g.nodes.size());
   for (auto& node : g.nodes) nodeIndexInsert(g, node.second);
   invalidateDeviceGraph();
   if (updateLocal) this->setLocalGraph(false);
@@ -1028,12 +1200,41 @@ void TRG::setGoalUnlocked(Eigen::Vector3f& goal) {  // trg.cpp:537-565
   static thread_local std::vector<Node*> res;
   rangeNodesOrdered(g, goal.x(), goal.y(), param_.robot_size, res);
   if (res.empty()) {
-    float min_dist = std::numeric_limits<float>::max();
-    for (auto& node : g.nodes) {
-      float dist = norm2(node.second->pos_.x() - goal.x(), node.second->pos_.y() - goal.y());
-      if (dist < min_dist) {
-        min_dist   = dist;
-        goal_.node = node.second;
+    // Reference (:543-553): linear scan over the node map, strict `<` on dist = sqrt(dx^2+dy^2),
+    // i.e. the first node IN MAP ITERATION ORDER among those whose rounded dist is minimal. The
+    // grid finds the minimal dist^2; every node whose sqrtf equals the minimal dist is a
+    // candidate (several dist^2 values can round to one dist), ranked by iteration order.
+    goal_.node = nullptr;
+    ensureGridBuilt(g);
+    auto nn = g.node_grid.nearest(goal.x(), goal.y());
+    if (nn.entry >= 0) {
+      const float min_dist = sqrtf(nn.d2);
+      float d2max = nn.d2;
+      for (int k = 0; k < 8; ++k) {
+        const float up = std::nextafter(d2max, std::numeric_limits<float>::infinity());
+        if (sqrtf(up) != min_dist) break;
+        d2max = up;
+      }
+      int n_cand = 0;
+      Node* only = nullptr;
+      const float reach = min_dist * 1.001f + 1e-4f;
+      g.node_grid.for_each_within_d2(goal.x(), goal.y(), d2max, reach, [&](int e) { ++n_cand; only = g.node_seq[e]; });
+      if (n_cand == 1) {
+        goal_.node = only;
+      } else {
+        // rare: rank the candidates by map iteration order (built once per graph state)
+        if (g.iter_rank.size() != g.nodes.size()) {
+          g.iter_rank.clear();
+          g.iter_rank.reserve(g.nodes.size());
+          size_t k = 0;
+          for (auto& node : g.nodes) g.iter_rank[node.second] = k++;
+        }
+        size_t best = std::numeric_limits<size_t>::max();
+        g.node_grid.for_each_within_d2(goal.x(), goal.y(), d2max, reach, [&](int e) {
+          Node* c = g.node_seq[e];
+          const size_t rk = g.iter_rank.at(c);
+          if (rk < best) { best = rk; goal_.node = c; }
+        });
       }
     }
     goal_.isKnown = false;

@@ -18,6 +18,7 @@
 
 #include <cstdint>
 #include <deque>
+#include <future>
 #include <memory>
 #include <mutex>
 #include <random>
@@ -160,7 +161,9 @@ class TRG {
     std::vector<Node*>      node_seq;
     trg_b200::NodeGrid      node_grid;
     trg_b200::OrderTree2D   node_tree;
+    size_t                  grid_built = 0;  // prefix of node_seq already in node_grid (filled lazily)
     size_t                  tree_built = 0;  // prefix of node_seq already in node_tree
+    std::unordered_map<const Node*, size_t> iter_rank;  // lazily: position in `nodes` iteration order
     // replaces `kdtree* map_tree` (trg.h:110): device cell index
     trgb_map*               map_index = nullptr;
     int64_t                 map_points = 0;
@@ -209,6 +212,10 @@ class TRG {
   float nextUniform();
   void  ensureDraws(size_t upto);
   void  compactDraws();
+  void  generateDrawBlock(size_t n, std::vector<float>& u, std::vector<float>& xy);
+  void  joinDrawPrefetch();
+  std::future<void> draw_prefetch_;   // helper generating the next block into pre_u_/pre_xy_
+  std::vector<float> pre_u_, pre_xy_;
   void  syncDraws();
   std::vector<float> draw_u_;   // u_k for k >= draw_base_
   std::vector<float> draw_xy_;  // 2 per draw
@@ -218,6 +225,7 @@ class TRG {
   void nodeIndexInsert(trgStruct& g, Node* n);
   void nodeIndexReset(trgStruct& g);
   void ensureGrid(trgStruct& g);
+  void ensureGridBuilt(trgStruct& g);
   void ensureTree(trgStruct& g);
   Node* nearestNode(trgStruct& g, float x, float y);
   void rangeNodesOrdered(trgStruct& g, float x, float y, float r, std::vector<Node*>& out);

@@ -220,7 +220,7 @@ int trg_edge_eval_batch(void* h, const char* type, const float* p1, const float*
   return guard([&] {
     trgb_map* m = T(h)->deviceMap(type);
     if (!m) throw std::runtime_error("trg_b200: no map loaded");
-    TrgbEdgeParams prm{X(h)->robotSize(), X(h)->heightThr(), X(h)->collThr()};
+    TrgbEdgeParams prm{X(h)->robotSize(), X(h)->heightThr(), X(h)->collThr(), 0};
     if (trgb_edge_eval_batch(m, p1, p2, n, &prm, stage, weight, dist, npts) != TRGB_OK)
       throw std::runtime_error(trgb_last_error());
     if (weight64) for (int64_t i = 0; i < n; ++i) weight64[i] = std::numeric_limits<double>::quiet_NaN();

@@ -27,7 +27,7 @@ class MapInfo(C.Structure):
 
 class EdgeParams(C.Structure):
     _fields_ = [("robot_size", C.c_float), ("height_threshold", C.c_float),
-                ("collision_threshold", C.c_float)]
+                ("collision_threshold", C.c_float), ("max_edge_samples", C.c_int32)]
 
 
 class GraphDesc(C.Structure):
