@@ -61,13 +61,23 @@ def test_init_graph_parity(pkg, K, which, prm, start, small_mountain, small_indo
 
 
 @pytest.mark.parametrize("tuning", [dict(chunk_nodes=1, window=8), dict(chunk_nodes=7, window=16),
-                                    dict(chunk_nodes=100000, window=256), dict(map_cell_scale=1.0)])
+                                    dict(chunk_nodes=100000, window=256), dict(map_cell_scale=1.0),
+                                    dict(overlap=0), dict(chunk_nodes=64, overlap=1)])
 def test_init_graph_scheduler_invariance(pkg, K, tuning, small_indoor):
     """The wavefront scheduler's batching knobs must not change a single decision."""
     pts = small_indoor[: len(small_indoor)]
     t, o = build_pair(pkg, pkg.INDOOR, pts, (3.27, 4.12, 0.0), seed=7, tuning=tuning)
     assert t.stat("rng_draws") == o.stat("rng_draws")
     assert_graph_equal(t.export(), o.export(), str(tuning))
+
+
+def test_overlapped_build_mountain(pkg, K, small_mountain):
+    """Mountain parameters take the two-thread path (helper feeds batch k+1 while batch k commits):
+    small batches force many hand-overs; the graph must not change."""
+    for tuning in (dict(chunk_nodes=300, overlap=1), dict(chunk_nodes=300, overlap=0), dict(chunk_nodes=32, window=32)):
+        t, o = build_pair(pkg, pkg.MOUNTAIN, small_mountain, (15.0, 15.0, 0.0), seed=9, tuning=tuning)
+        assert t.stat("rng_draws") == o.stat("rng_draws")
+        assert_graph_equal(t.export(), o.export(), str(tuning))
 
 
 def test_seeds_differ_and_reproduce(pkg, K, small_mountain):

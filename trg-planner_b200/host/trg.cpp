@@ -150,7 +150,7 @@ void TRG::ensureDraws(size_t upto) {
     if (draw_u_.size() >= ((size_t)1 << 15))
       draw_prefetch_ = std::async(std::launch::async, [this] { generateDrawBlock((size_t)1 << 18, pre_u_, pre_xy_); });
   }
-  stat_["us_draws"] += (int64_t)(1e6 * since(t0));
+  us_draws_ += 1e6 * since(t0);  // (plain member: runs on the helper thread)
 }
 
 // make the device copy cover exactly the host buffer [draw_base_, draw_base_ + size)
@@ -332,7 +332,7 @@ TRG::Node* TRG::nearestNode(trgStruct& g, float x, float y) {
   auto nn = g.node_grid.nearest(x, y);
   if (nn.entry >= 0 && !nn.tie) return g.node_seq[nn.entry];
   ensureTree(g);
-  stat_["node_ties"]++;
+  ++n_node_ties_;
   return g.node_seq[g.node_tree.nearest(x, y)];
 }
 
@@ -489,6 +489,15 @@ class ChunkTable {
     touched_.clear();
     ent_.clear();
   }
+  // forget nodes with seq < min_seq (they are on the device grid by now); entries are in seq order
+  void prune(int min_seq) {
+    size_t first = 0;
+    while (first < ent_.size() && ent_[first].seq < min_seq) ++first;
+    if (first == 0) return;
+    std::vector<E> keep(ent_.begin() + first, ent_.end());
+    clear();
+    for (const E& e : keep) insert(e.x, e.y, e.seq);
+  }
   void insert(float x, float y, int seq) {
     const int cx = cc(x, x0_), cy = cc(y, y0_);
     const uint32_t h = hash(cx, cy);
@@ -573,51 +582,63 @@ class Expander {
       d.nodes_owner = &g;
       d.nodes_uploaded = 0;
     }
+    handed_nodes_ = d.nodes_uploaded;
     table_.configure(box[0], box[1], cell);
   }
 
+  // expandGraph(root) for every root, in order (trg.cpp:372-454 / :483-487).
+  //
+  // Two host threads when possible: while this thread commits batch k, a helper runs the device
+  // phases (sampling windows, chain scan, speculative evaluation) of batch k+1, whose pops are
+  // already sitting in the BFS queue. That is legal because the sampling chain never looks at the
+  // graph; what batch k creates in the meantime reaches the device one batch later and is covered
+  // on the host by ChunkTable. Used for a single BFS without step-3 stalls; otherwise serial.
   void run(const std::vector<TRG::Node*>& roots) {
     t_.compactDraws();
-    size_t root_i = 0;
-    std::deque<TRG::Node*> bfs;
-    int cur_ref = -1;
     const size_t C = (size_t)std::max(1, t_.tuning_.chunk_nodes);
+    const bool overlap = t_.tuning_.overlap && roots.size() == 1 && !step3_;
+    size_t root_i = 0;
+    int cur_ref = -1;
+    int cur = 0;
+    // first batch: nothing to overlap with
+    if (!prepare(B_[cur], roots, root_i, cur_ref, C, t_.draw_next_)) return;
+    feed(B_[cur]);
     while (true) {
-      chunk_.clear();
-      for (size_t k = 0; k < bfs.size() && chunk_.size() < C; ++k) chunk_.push_back({bfs[k], cur_ref, false});
-      if (chunk_.size() == bfs.size())
-        for (size_t r = root_i; r < roots.size() && chunk_.size() < C; ++r)
-          chunk_.push_back({roots[r], roots[r]->id_, true});
-      if (chunk_.empty()) break;
-      auto ta = Clock::now();
-      sampleChunk();
-      auto tb = Clock::now();
-      evalChunk();
-      auto tc = Clock::now();
-      for (size_t i = 0; i < chunk_.size(); ++i) {
-        Pop& p = chunk_[i];
-        if (p.is_root) {
-          if (!bfs.empty()) break;  // the previous root's BFS is still running: speculation is stale
-        }
-        if (p.draw_start != t_.draw_next_) break;
-        if (p.is_root) {
-          cur_ref = p.ref_id;
-          ++root_i;
-        } else {
-          bfs.pop_front();
-        }
-        commitPop(p, bfs);
+      Batch& b = B_[cur];
+      Batch& nb = B_[cur ^ 1];
+      std::future<void> fut;
+      bool launched = false;
+      if (overlap && bfs_.size() - sent_ >= std::min<size_t>(256, C)) {
+        launched = prepare(nb, roots, root_i, cur_ref, C, b.chain_end);
+        if (launched) fut = std::async(std::launch::async, [this, &nb] { feed(nb); });
       }
-      auto td = Clock::now();
-      t_.stat_["us_sample"] += (int64_t)(1e6 * std::chrono::duration<double>(tb - ta).count());
-      t_.stat_["us_eval"] += (int64_t)(1e6 * std::chrono::duration<double>(tc - tb).count());
-      t_.stat_["us_commit"] += (int64_t)(1e6 * std::chrono::duration<double>(td - tc).count());
+      auto tc = Clock::now();
+      try {
+        commit(b, roots, root_i, cur_ref);
+      } catch (...) {
+        if (launched) fut.wait();
+        throw;
+      }
+      us_commit_ += 1e6 * since(tc);
+      if (launched) {
+        auto tw = Clock::now();
+        fut.get();
+        us_wait_ += 1e6 * since(tw);
+      } else {
+        if (!prepare(nb, roots, root_i, cur_ref, C, t_.draw_next_)) break;
+        feed(nb);
+      }
+      absorb(b);
+      cur ^= 1;
     }
+    absorb(B_[cur]);
     flushDeferred();
     t_.stat_["pops"] += n_pops_;
     t_.stat_["nearest_node"] += n_nearest_;
     t_.stat_["z_ties"] += n_zties_;
     t_.stat_["stalls"] += n_stalls_;
+    t_.stat_["us_commit"] += (int64_t)us_commit_;
+    t_.stat_["us_wait"] += (int64_t)us_wait_;
 #ifdef TRG_FINE_TIMERS
     t_.stat_["cyc_nearest"] += (int64_t)ft_nearest;
     t_.stat_["cyc_wire"] += (int64_t)ft_wire;
@@ -628,6 +649,7 @@ class Expander {
  private:
   struct Pop {
     TRG::Node* node;
+    float x, y, z;  // cached: the helper thread never dereferences graph objects
     int ref_id;
     bool is_root;
     size_t draw_start = 0;
@@ -635,15 +657,88 @@ class Expander {
     uint32_t acc_begin = 0, acc_count = 0;
   };
   struct Sample { float x, y; };
-  struct Deferred { TRG::Node *a, *b; TRG::Edge *ea, *eb; int primary; bool ok; };
+  struct Deferred {
+    TRG::Node *a, *b;
+    TRG::Edge *ea, *eb;
+    float ax, ay, az, bx, by;
+  };
+  // one unit of device work; filled by prepare() (committing thread), feed() (either thread)
+  struct Batch {
+    std::vector<Pop> pops;
+    std::vector<float> new_xy;       // nodes created since the previous hand-over -> device node grid
+    std::vector<Deferred> deferred;  // edge evaluations deferred by earlier commits
+    size_t chain_start = 0, chain_end = 0;
+    size_t grid_count = 0;           // node_seq prefix the nearest-node candidates cover
+    std::vector<Sample> acc;
+    std::vector<float> z, w, d, nn_d2, d_w, d_d;
+    std::vector<uint8_t> tie, stage, nn_tie, d_stage;
+    std::vector<int32_t> nn_idx;
+    // helper-side counters, merged by absorb()
+    int64_t window_launches = 0, window_tests = 0, eval_launches = 0, edge_evals = 0, nearest_map = 0, batches = 0;
+    double us_sample = 0, us_eval = 0;
+  };
+
+  // ---- batch formation (committing thread) --------------------------------------------------
+  // The pop sequence is: the BFS queue of the current root, then — speculatively, and only when
+  // the whole queue is inside this batch — the following roots (updateGraph).
+  bool prepare(Batch& b, const std::vector<TRG::Node*>& roots, size_t root_i, int cur_ref, size_t C, size_t chain_start) {
+    b.pops.clear();
+    for (size_t k = sent_; k < bfs_.size() && b.pops.size() < C; ++k) {
+      TRG::Node* n = bfs_[k];
+      b.pops.push_back({n, n->pos_.x(), n->pos_.y(), n->pos_.z(), cur_ref, false});
+    }
+    const size_t from_queue = b.pops.size();
+    if (sent_ + from_queue == bfs_.size() && sent_ == head_) {
+      // queue fully covered and nothing of it in flight: following roots may be speculated
+      for (size_t r = root_i; r < roots.size() && b.pops.size() < C; ++r) {
+        TRG::Node* n = roots[r];
+        b.pops.push_back({n, n->pos_.x(), n->pos_.y(), n->pos_.z(), n->id_, true});
+      }
+    }
+    if (b.pops.empty()) return false;
+    sent_ += from_queue;
+    b.chain_start = chain_start;
+    b.new_xy.clear();
+    for (size_t i = handed_nodes_; i < g_.node_seq.size(); ++i) {
+      b.new_xy.push_back(g_.node_seq[i]->pos_.x());
+      b.new_xy.push_back(g_.node_seq[i]->pos_.y());
+    }
+    handed_nodes_ = g_.node_seq.size();
+    b.grid_count  = handed_nodes_;
+    b.deferred.swap(pending_);
+    pending_.clear();
+    return true;
+  }
+
+  void feed(Batch& b) {
+    auto ta = Clock::now();
+    sampleBatch(b);
+    auto tb = Clock::now();
+    evalBatch(b);
+    b.us_sample += 1e6 * std::chrono::duration<double>(tb - ta).count();
+    b.us_eval += 1e6 * since(tb);
+  }
+
+  void absorb(Batch& b) {
+    t_.stat_["window_launches"] += b.window_launches;
+    t_.stat_["window_tests"] += b.window_tests;
+    t_.stat_["eval_launches"] += b.eval_launches;
+    t_.stat_["edge_evals"] += b.edge_evals;
+    t_.stat_["nearest_map"] += b.nearest_map;
+    t_.stat_["us_sample"] += (int64_t)b.us_sample;
+    t_.stat_["us_eval"] += (int64_t)b.us_eval;
+    t_.dev_->batches += (uint64_t)b.batches;
+    b.window_launches = b.window_tests = b.eval_launches = b.edge_evals = b.nearest_map = b.batches = 0;
+    b.us_sample = b.us_eval = 0;
+  }
 
   // ---- phase A: sampling windows (trg.cpp:384-403) ------------------------------------------
-  void sampleChunk() {
+  void sampleBatch(Batch& b) {
     const int S = P_.sample_num;
-    const size_t m = chunk_.size();
-    acc_.clear();
+    const size_t m = b.pops.size();
+    b.acc.clear();
     size_t done = 0;
-    size_t pos = t_.draw_next_;  // stream position reached by the chain
+    size_t pos = b.chain_start;  // stream position reached by the chain
     int part_acc = 0, part_trials = 0;
     bool part_open = false;
     int W = std::min(256, std::max(8, t_.tuning_.window));
@@ -671,10 +766,8 @@ class Expander {
         guess_[i] = gpos;
         hi = std::max(hi, gpos + (size_t)W);
       }
-      auto tp0 = Clock::now();
       t_.ensureDraws(hi);
       t_.syncDraws();
-      auto tp1 = Clock::now();
       DrawBuffer& db = t_.dev_->draws;
       Arena& in  = t_.dev_->in;
       Arena& out = t_.dev_->out;
@@ -686,11 +779,10 @@ class Expander {
       float* xy   = in.h<float>(o_xy);
       int32_t* fd = in.h<int32_t>(o_fd);
       for (size_t i = done; i < m; ++i) {
-        xy[2 * (i - done)]     = chunk_[i].node->pos_.x();
-        xy[2 * (i - done) + 1] = chunk_[i].node->pos_.y();
+        xy[2 * (i - done)]     = b.pops[i].x;
+        xy[2 * (i - done) + 1] = b.pops[i].y;
         fd[i - done]           = (int32_t)(guess_[i] - db.base());
       }
-      auto tp2 = Clock::now();
       in.h2d(st_);
       out.zero_d(o_mk, n_live * words * sizeof(unsigned long long), st_);
       K(trgb_sample_window_launch(map_, in.d<float>(o_xy), in.d<int32_t>(o_fd), db.dev(), (int64_t)n_live, W,
@@ -699,22 +791,18 @@ class Expander {
         "trgb_sample_window_launch");
       out.d2h(st_);
       cuda_check(cudaStreamSynchronize(st_), "sync(windows)");
-      auto tp3 = Clock::now();
-      t_.stat_["us_w_draws"] += (int64_t)(1e6 * std::chrono::duration<double>(tp1 - tp0).count());
-      t_.stat_["us_w_prep"] += (int64_t)(1e6 * std::chrono::duration<double>(tp2 - tp1).count());
-      t_.stat_["us_w_gpu"] += (int64_t)(1e6 * std::chrono::duration<double>(tp3 - tp2).count());
-      t_.dev_->batches++;
-      t_.stat_["window_launches"]++;
-      t_.stat_["window_tests"] += (int64_t)n_live * W;
+      b.batches++;
+      b.window_launches++;
+      b.window_tests += (int64_t)n_live * W;
       const unsigned long long* mk = out.h<unsigned long long>(o_mk);
       // host chain scan
       const size_t done_before = done;
       const size_t pos_before  = pos;
       for (size_t i = done; i < m; ++i) {
-        Pop& p = chunk_[i];
+        Pop& p = b.pops[i];
         if (!part_open) {
           p.draw_start = pos;
-          p.acc_begin  = (uint32_t)acc_.size();
+          p.acc_begin  = (uint32_t)b.acc.size();
           part_acc = 0;
           part_trials = 0;
           part_open = true;
@@ -722,7 +810,6 @@ class Expander {
         if (pos < guess_[i]) break;  // the window starts past the chain position: re-plan from here
         const unsigned long long* w = mk + (i - done_before) * words;
         bool miss = false;
-        const float nx = p.node->pos_.x(), ny = p.node->pos_.y();
         while (part_acc < S) {
           if (part_trials > 1000) break;  // trg.cpp:390-392 (checked before every draw)
           const size_t rel = pos - guess_[i];
@@ -731,12 +818,12 @@ class Expander {
           const size_t d  = pos - t_.draw_base_;
           ++pos;
           if (coll) { ++part_trials; continue; }
-          acc_.push_back({nx + t_.draw_xy_[2 * d], ny + t_.draw_xy_[2 * d + 1]});  // trg.cpp:396-397
+          b.acc.push_back({p.x + t_.draw_xy_[2 * d], p.y + t_.draw_xy_[2 * d + 1]});  // trg.cpp:396-397
           ++part_acc;
         }
         if (miss) break;
         p.consumed  = (int)(pos - p.draw_start);
-        p.acc_count = (uint32_t)acc_.size() - p.acc_begin;
+        p.acc_count = (uint32_t)b.acc.size() - p.acc_begin;
         part_open   = false;
         ++done;
         const double c = (double)p.consumed;
@@ -751,19 +838,22 @@ class Expander {
       }
       if (done == done_before) W = std::min(256, W * 2);  // a single pop needs a longer window
     }
+    b.chain_end = pos;
   }
 
-  // ---- phase B: speculative z + parent edge per accepted sample, plus deferred edges -------
-  void evalChunk() {
-    const size_t ns = acc_.size();
-    const size_t nd = deferred_.size();
-    spec_.n = ns;
-    if (ns + nd == 0) return;
-    Arena& in  = t_.dev_->in;
-    Arena& out = t_.dev_->out;
-    const size_t ne = ns + nd;
+  // ---- phase B: nearest node, z and parent edge per accepted sample, plus deferred edges ----
+  void evalBatch(Batch& b) {
+    const size_t ns = b.acc.size();
+    const size_t nd = b.deferred.size();
+    const size_t n_new = b.new_xy.size() / 2;
     DeviceSession& dv = *t_.dev_;
-    const size_t n_new = g_.node_seq.size() - dv.nodes_uploaded;  // nodes the device grid has not seen yet
+    const size_t ne = ns + nd;
+    b.z.resize(ns); b.tie.resize(ns); b.stage.resize(ns); b.w.resize(ns); b.d.resize(ns);
+    b.nn_idx.resize(ns); b.nn_d2.resize(ns); b.nn_tie.resize(ns);
+    b.d_stage.resize(nd); b.d_w.resize(nd); b.d_d.resize(nd);
+    if (ne + n_new == 0) return;
+    Arena& in  = dv.in;
+    Arena& out = dv.out;
     in.reset(Arena::padded(ne * 3 * sizeof(float)) + Arena::padded(ne * 2 * sizeof(float)) + Arena::padded(n_new * 2 * sizeof(float)));
     out.reset(Arena::padded(ns * sizeof(float)) + Arena::padded(ns) + Arena::padded(ne) + 2 * Arena::padded(ne * sizeof(float)) +
               2 * Arena::padded(ns * sizeof(float)) + Arena::padded(ns));
@@ -778,32 +868,24 @@ class Expander {
     const size_t o_ni = out.take(ns * sizeof(int32_t));
     const size_t o_nd = out.take(ns * sizeof(float));
     const size_t o_nt = out.take(ns);
-    {
-      float* nn = in.h<float>(o_nn);
-      for (size_t i = 0; i < n_new; ++i) {
-        const TRG::Node* nd = g_.node_seq[dv.nodes_uploaded + i];
-        nn[2 * i] = nd->pos_.x();
-        nn[2 * i + 1] = nd->pos_.y();
-      }
-    }
+    if (n_new) std::memcpy(in.h<float>(o_nn), b.new_xy.data(), n_new * 2 * sizeof(float));
     float* p1 = in.h<float>(o_p1);
     float* p2 = in.h<float>(o_p2);
     size_t k = 0;
-    for (const Pop& p : chunk_) {
+    for (const Pop& p : b.pops) {
       for (uint32_t j = 0; j < p.acc_count; ++j, ++k) {
-        p1[3 * k] = p.node->pos_.x(); p1[3 * k + 1] = p.node->pos_.y(); p1[3 * k + 2] = p.node->pos_.z();
-        p2[2 * k] = acc_[p.acc_begin + j].x; p2[2 * k + 1] = acc_[p.acc_begin + j].y;
+        p1[3 * k] = p.x; p1[3 * k + 1] = p.y; p1[3 * k + 2] = p.z;
+        p2[2 * k] = b.acc[p.acc_begin + j].x; p2[2 * k + 1] = b.acc[p.acc_begin + j].y;
       }
     }
-    for (const Deferred& d : deferred_) {
-      p1[3 * k] = d.a->pos_.x(); p1[3 * k + 1] = d.a->pos_.y(); p1[3 * k + 2] = d.a->pos_.z();
-      p2[2 * k] = d.b->pos_.x(); p2[2 * k + 1] = d.b->pos_.y();
+    for (const Deferred& d : b.deferred) {
+      p1[3 * k] = d.ax; p1[3 * k + 1] = d.ay; p1[3 * k + 2] = d.az;
+      p2[2 * k] = d.bx; p2[2 * k + 1] = d.by;
       ++k;
     }
     in.h2d(st_);
     K(trgb_nodes_append_launch(dv.nodes, in.d<float>(o_nn), (int64_t)n_new, st_), "trgb_nodes_append_launch");
     dv.nodes_uploaded += n_new;
-    table_.clear();  // every node created so far is now on the device
     if (ns) {
       K(trgb_nodes_nearest_launch(dv.nodes, in.d<float>(o_p2), (int64_t)ns, out.d<int32_t>(o_ni), out.d<float>(o_nd),
                                   out.d<uint8_t>(o_nt), st_),
@@ -811,39 +893,50 @@ class Expander {
       K(trgb_nearest_z_launch(map_, in.d<float>(o_p2), (int64_t)ns, out.d<float>(o_z), nullptr, out.d<uint8_t>(o_t)),
         "trgb_nearest_z_launch");
     }
-    TrgbEdgeParams prm{P_.robot_size, P_.height_threshold, P_.collision_threshold, 0};
-    K(trgb_edge_eval_launch(map_, in.d<float>(o_p1), in.d<float>(o_p2), (int64_t)ne, &prm, out.d<uint8_t>(o_s),
-                            out.d<float>(o_w), out.d<float>(o_d), nullptr),
-      "trgb_edge_eval_launch");
+    if (ne) {
+      TrgbEdgeParams prm{P_.robot_size, P_.height_threshold, P_.collision_threshold, 0};
+      K(trgb_edge_eval_launch(map_, in.d<float>(o_p1), in.d<float>(o_p2), (int64_t)ne, &prm, out.d<uint8_t>(o_s),
+                              out.d<float>(o_w), out.d<float>(o_d), nullptr),
+        "trgb_edge_eval_launch");
+    }
     out.d2h(st_);
     cuda_check(cudaStreamSynchronize(st_), "sync(eval)");
-    t_.dev_->batches++;
-    t_.stat_["eval_launches"]++;
-    t_.stat_["nearest_map"] += (int64_t)ns;
-    t_.stat_["edge_evals"] += (int64_t)ne;
-    spec_.z = out.h<float>(o_z);
-    spec_.tie = out.h<uint8_t>(o_t);
-    spec_.stage = out.h<uint8_t>(o_s);
-    spec_.w = out.h<float>(o_w);
-    spec_.d = out.h<float>(o_d);
-    spec_.nn_idx = out.h<int32_t>(o_ni);
-    spec_.nn_d2 = out.h<float>(o_nd);
-    spec_.nn_tie = out.h<uint8_t>(o_nt);
-    resolveDeferred(spec_.stage + ns, spec_.w + ns, spec_.d + ns);
+    b.batches++;
+    b.eval_launches++;
+    b.nearest_map += (int64_t)ns;
+    b.edge_evals += (int64_t)ne;
+    // results leave the staging arena: the next batch may be fed while this one is committed
+    if (ns) {
+      std::memcpy(b.z.data(), out.h<float>(o_z), ns * sizeof(float));
+      std::memcpy(b.tie.data(), out.h<uint8_t>(o_t), ns);
+      std::memcpy(b.stage.data(), out.h<uint8_t>(o_s), ns);
+      std::memcpy(b.w.data(), out.h<float>(o_w), ns * sizeof(float));
+      std::memcpy(b.d.data(), out.h<float>(o_d), ns * sizeof(float));
+      std::memcpy(b.nn_idx.data(), out.h<int32_t>(o_ni), ns * sizeof(int32_t));
+      std::memcpy(b.nn_d2.data(), out.h<float>(o_nd), ns * sizeof(float));
+      std::memcpy(b.nn_tie.data(), out.h<uint8_t>(o_nt), ns);
+    }
+    if (nd) {
+      std::memcpy(b.d_stage.data(), out.h<uint8_t>(o_s) + ns, nd);
+      std::memcpy(b.d_w.data(), out.h<float>(o_w) + ns, nd * sizeof(float));
+      std::memcpy(b.d_d.data(), out.h<float>(o_d) + ns, nd * sizeof(float));
+    }
   }
 
-  // Resolve every deferred evaluation in call order. An entry with `primary >= 0` is the
-  // opposite-orientation retry of an earlier pending entry: it only counts if that one failed.
-  void resolveDeferred(const uint8_t* stage, const float* w, const float* d) {
+  // Resolve deferred evaluations in call order. If a resolved edge a->b exists by now, the entry
+  // was the opposite-orientation retry of an evaluation that succeeded: a duplicate, dropped.
+  void resolveDeferred(std::vector<Deferred>& list, const uint8_t* stage, const float* w, const float* d) {
     auto drop = [](TRG::Node* n, TRG::Edge* x) {
       auto it = std::find(n->edges_.begin(), n->edges_.end(), x);
       if (it != n->edges_.end()) n->edges_.erase(it);
     };
-    for (size_t i = 0; i < deferred_.size(); ++i) {
-      Deferred& e = deferred_[i];
+    for (size_t i = 0; i < list.size(); ++i) {
+      Deferred& e = list[i];
       bool ok = stage[i] == TRGB_EDGE_OK;
-      if (e.primary >= 0 && deferred_[e.primary].ok) ok = false;  // duplicate of an edge that exists
-      e.ok = ok;
+      if (ok) {
+        for (TRG::Edge* x : e.a->edges_)
+          if (x->dst_id_ == e.b->id_ && x->dist_ >= 0.f) { ok = false; break; }
+      }
       if (ok) {
         e.ea->weight_ = e.eb->weight_ = w[i];
         e.ea->dist_ = e.eb->dist_ = d[i];
@@ -852,12 +945,13 @@ class Expander {
         drop(e.b, e.eb);
       }
     }
-    deferred_.clear();
+    list.clear();
   }
 
-  // synchronous resolution of everything deferred so far (end of expansion / validity stall)
+  // synchronous resolution of everything deferred and not yet handed over (end of expansion /
+  // validity stall); earlier hand-overs are always resolved before this is reached
   void flushDeferred() {
-    const size_t nd = deferred_.size();
+    const size_t nd = pending_.size();
     if (!nd) return;
     Arena& in  = t_.dev_->in2;
     Arena& out = t_.dev_->out2;
@@ -871,9 +965,9 @@ class Expander {
     float* p1 = in.h<float>(o_p1);
     float* p2 = in.h<float>(o_p2);
     for (size_t k = 0; k < nd; ++k) {
-      const Deferred& d = deferred_[k];
-      p1[3 * k] = d.a->pos_.x(); p1[3 * k + 1] = d.a->pos_.y(); p1[3 * k + 2] = d.a->pos_.z();
-      p2[2 * k] = d.b->pos_.x(); p2[2 * k + 1] = d.b->pos_.y();
+      const Deferred& d = pending_[k];
+      p1[3 * k] = d.ax; p1[3 * k + 1] = d.ay; p1[3 * k + 2] = d.az;
+      p2[2 * k] = d.bx; p2[2 * k + 1] = d.by;
     }
     in.h2d(st_);
     TrgbEdgeParams prm{P_.robot_size, P_.height_threshold, P_.collision_threshold, 0};
@@ -885,56 +979,73 @@ class Expander {
     t_.dev_->batches++;
     t_.stat_["flush_launches"]++;
     t_.stat_["edge_evals"] += (int64_t)nd;
-    resolveDeferred(out.h<uint8_t>(o_s), out.h<float>(o_w), out.h<float>(o_d));
+    resolveDeferred(pending_, out.h<uint8_t>(o_s), out.h<float>(o_w), out.h<float>(o_d));
   }
 
   // wireEdge(a, b) against an existing node (trg.cpp:254-370): duplicate check + slope gate now,
-  // geometry in the next batch. Placeholder edges (dist_ < 0 encodes the deferred index,
-  // weight_ -1 on the origin side / -2 on the far side) keep the reference's edge order.
-  // Evaluation is a pure function of the ORIENTED pair, so while (b, a) is pending a call
-  // (a, b) must be kept as a conditional retry: the reference would run it if (b, a) failed.
+  // geometry in a later batch. Placeholder edges (dist_ = -1; weight_ = -1 on the origin side, -2 on
+  // the far side) keep the reference's edge order. Evaluation is a pure function of the ORIENTED
+  // pair, so while (b, a) is pending a call (a, b) is kept as a conditional retry: the reference
+  // would run it if (b, a) failed (see resolveDeferred).
   void wireDeferred(TRG::Node* a, TRG::Node* b) {
     if (a->id_ == b->id_) return;
-    int primary = -1;
+    bool opposite_pending = false;
     for (TRG::Edge* e : a->edges_) {
       if (e->dst_id_ != b->id_) continue;
-      if (e->dist_ >= 0.f) return;          // resolved edge exists
-      if (e->weight_ == -1.f) return;       // same orientation already pending: same outcome
-      primary = (int)(-e->dist_) - 1;       // opposite orientation pending
+      if (e->dist_ >= 0.f) return;     // resolved edge exists
+      if (e->weight_ == -1.f) return;  // same orientation already pending: same outcome
+      opposite_pending = true;
     }
-    if (primary < 0) {
+    if (!opposite_pending) {
       for (TRG::Edge* e : b->edges_)
         if (e->dst_id_ == a->id_ && e->dist_ >= 0.f) return;
     }
     if (gate_.rejects(a->pos_, b->pos_)) return;
-    const float tag = -(float)(deferred_.size() + 1);
-    TRG::Edge* ea = t_.newEdge(b->id_, -1.f, tag);
-    TRG::Edge* eb = t_.newEdge(a->id_, -2.f, tag);
+    TRG::Edge* ea = t_.newEdge(b->id_, -1.f, -1.f);
+    TRG::Edge* eb = t_.newEdge(a->id_, -2.f, -1.f);
     a->edges_.push_back(ea);
     b->edges_.push_back(eb);
-    deferred_.push_back({a, b, ea, eb, primary, false});
+    pending_.push_back({a, b, ea, eb, a->pos_.x(), a->pos_.y(), a->pos_.z(), b->pos_.x(), b->pos_.y()});
   }
 
-  // ---- phase C: commit one pop in the reference's order (trg.cpp:406-452) ------------------
-  void commitPop(const Pop& p, std::deque<TRG::Node*>& bfs) {
+  // ---- phase C: commit a batch in the reference's order (trg.cpp:406-452) -------------------
+  void commit(Batch& b, const std::vector<TRG::Node*>& roots, size_t& root_i, int& cur_ref) {
+    resolveDeferred(b.deferred, b.d_stage.data(), b.d_w.data(), b.d_d.data());
+    table_.prune(static_cast<int>(b.grid_count));
+    for (size_t i = 0; i < b.pops.size(); ++i) {
+      Pop& p = b.pops[i];
+      if (p.is_root) {
+        if (head_ != bfs_.size()) break;  // the previous root's BFS is still running: speculation is stale
+        if (p.draw_start != t_.draw_next_) break;
+        cur_ref = p.ref_id;
+        ++root_i;
+      } else {
+        if (p.draw_start != t_.draw_next_) throw std::logic_error("trg_b200: sampling chain out of step");
+        ++head_;
+      }
+      commitPop(b, p);
+    }
+    (void)roots;
+  }
+
+  void commitPop(Batch& b, const Pop& p) {
     TRG::Node* node = p.node;
     t_.draw_next_ = p.draw_start + (size_t)p.consumed;
     ++n_pops_;
     const TRG::NodeState new_state = (p.ref_id == 0) ? TRG::NodeState::Valid : TRG::NodeState::Frontier;
-    // index of this pop's first sample inside the speculative arrays
     const size_t s0 = p.acc_begin;
     for (uint32_t j = 0; j < p.acc_count; ++j) {
-      const Sample& s = acc_[s0 + j];
+      const size_t si = s0 + j;
+      const Sample& s = b.acc[si];
       ++n_nearest_;
       FT_BEGIN();
       // kd_nearest2(node_tree, sample) (trg.cpp:408): device candidate (nodes that existed when the
-      // batch was evaluated) merged with the nodes created since; exact ties -> reference tree order
+      // batch was handed over) merged with the nodes created since; exact ties -> reference tree order
       TRG::Node* ex;
       {
-        const size_t sj = s0 + j;
-        float d2 = spec_.nn_d2[sj];
-        int seq = spec_.nn_idx[sj];
-        bool tie = spec_.nn_tie[sj] != 0;
+        float d2 = b.nn_d2[si];
+        int seq = b.nn_idx[si];
+        bool tie = b.nn_tie[si] != 0;
         if (seq < 0) d2 = std::numeric_limits<float>::infinity();
         table_.refine(s.x, s.y, d2, seq, tie);
         ex = (tie || seq < 0) ? t_.nearestNode(g_, s.x, s.y) : g_.node_seq[seq];
@@ -947,19 +1058,18 @@ class Expander {
         continue;
       }
       // 2. new node (addNode never fails for id != 0)
-      const size_t si = s0 + j;
-      if (spec_.tie[si]) ++n_zties_;
+      if (b.tie[si]) ++n_zties_;
       Eigen::Vector2f pos2(s.x, s.y);
-      TRG::Node* nn = t_.newNode(g_.node_id, pos2, spec_.z[si], new_state);
+      TRG::Node* nn = t_.newNode(g_.node_id, pos2, b.z[si], new_state);
       g_.nodes[g_.node_id] = nn;
       t_.nodeIndexInsert(g_, nn);
       table_.insert(s.x, s.y, static_cast<int>(g_.node_seq.size()) - 1);
       g_.node_id++;
       // 2.1 wireEdge(node, new): slope gate on the host, geometry from the speculative batch
       bool parent_ok = false;
-      if (spec_.stage[si] == TRGB_EDGE_OK && !gate_.rejects(node->pos_, nn->pos_)) {
-        node->edges_.push_back(t_.newEdge(nn->id_, spec_.w[si], spec_.d[si]));
-        nn->edges_.push_back(t_.newEdge(node->id_, spec_.w[si], spec_.d[si]));
+      if (b.stage[si] == TRGB_EDGE_OK && !gate_.rejects(node->pos_, nn->pos_)) {
+        node->edges_.push_back(t_.newEdge(nn->id_, b.w[si], b.d[si]));
+        nn->edges_.push_back(t_.newEdge(node->id_, b.w[si], b.d[si]));
         parent_ok = true;
       }
       // 3. wire to the neighbours within expand_dist, in kd result order
@@ -980,25 +1090,13 @@ class Expander {
         nn->state_ = TRG::NodeState::Invalid;
         continue;
       }
-      bfs.push_back(nn);
+      bfs_.push_back(nn);
       FT_LAP(newnode);
     }
   }
   FT_DECL(nearest); FT_DECL(wire); FT_DECL(newnode);
 
-  struct Spec {
-    size_t n = 0;
-    const float* z = nullptr;
-    const uint8_t* tie = nullptr;
-    const uint8_t* stage = nullptr;
-    const float* w = nullptr;
-    const float* d = nullptr;
-    const int32_t* nn_idx = nullptr;  // nearest node (node_seq index) among the nodes on the device grid
-    const float* nn_d2 = nullptr;
-    const uint8_t* nn_tie = nullptr;
-  } spec_;
   ChunkTable table_;
-
   TRG& t_;
   TRG::trgStruct& g_;
   const decltype(TRG::param_)& P_;
@@ -1006,12 +1104,16 @@ class Expander {
   trgb_map* map_ = nullptr;
   cudaStream_t st_ = nullptr;
   int64_t n_pops_ = 0, n_nearest_ = 0, n_zties_ = 0, n_stalls_ = 0;
+  double us_commit_ = 0, us_wait_ = 0;
   bool step3_ = false;
-  double mean_ = 8.0, var_ = 2.0;
-  std::vector<Pop> chunk_;
-  std::vector<Sample> acc_;
+  double mean_ = 8.0, var_ = 2.0;  // helper-side: running draws/pop statistics
+  Batch B_[2];
+  std::vector<TRG::Node*> bfs_;    // every node ever queued, in queue order
+  size_t head_ = 0;                // next queue entry to commit
+  size_t sent_ = 0;                // next queue entry not yet placed in a batch
+  size_t handed_nodes_ = 0;        // node_seq prefix already handed to the device node grid
   std::vector<size_t> guess_;
-  std::vector<Deferred> deferred_;
+  std::vector<Deferred> pending_;  // deferred since the last hand-over
   std::vector<TRG::Node*> cand_;
 };
 
@@ -1387,6 +1489,8 @@ double TRG::lastSeconds(const std::string& what) const {
 }
 int64_t TRG::stat(const std::string& what) const {
   if (what == "rng_draws") return (int64_t)draw_next_;
+  if (what == "us_draws") return (int64_t)us_draws_;
+  if (what == "node_ties") return n_node_ties_;
   if (what == "batches") return (int64_t)dev_->batches;
   auto it = stat_.find(what);
   return it == stat_.end() ? 0 : it->second;

@@ -247,6 +247,8 @@ class TRG {
   std::unordered_map<std::string, double>  secs_;
   std::unordered_map<std::string, int64_t> stat_;
   std::vector<int32_t> last_path_ids_;
+  double  us_draws_ = 0;
+  int64_t n_node_ties_ = 0;
 
  public:
   // [+] tuning knobs of the wavefront scheduler (defaults are fine; exposed for benchmarks)
@@ -254,6 +256,7 @@ class TRG {
     int chunk_nodes = 2048;   // pops evaluated per batch
     int window = 128;         // sampling-window draws per node (<= 256)
     float map_cell_scale = 0.5f;  // map index cell = map_cell_scale * robot_size
+    bool overlap = true;      // run the device phases of batch k+1 on a helper thread while batch k commits
   } tuning_;
 };
 

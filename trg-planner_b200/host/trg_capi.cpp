@@ -254,6 +254,7 @@ int trg_set_tuning(void* h, const char* key, double value) {
     if (k == "chunk_nodes") T(h)->tuning_.chunk_nodes = (int)value;
     else if (k == "window") T(h)->tuning_.window = (int)value;
     else if (k == "map_cell_scale") T(h)->tuning_.map_cell_scale = (float)value;
+    else if (k == "overlap") T(h)->tuning_.overlap = value != 0;
     else throw std::runtime_error("unknown tuning key " + k);
     return 0;
   });
