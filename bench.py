@@ -51,13 +51,13 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+    def __init__(self, gpu_index: int, period_ms: int = 200):
+        self.rows, self.proc, self.gpu, self.period = [], None, gpu_index, period_ms
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -119,12 +119,20 @@ def unit_bytes(kernel: str, P, rho: float, cell: float) -> float:
         return 16.0 * k_r + 8 + 4
     if kernel == "k_nearest_z":
         return 16.0 * (9.0 * cell * cell * rho) + 12
-    if kernel == "k_edge_eval":
-        e = P.expand_dist
-        m = int(np.ceil(e / (0.5 * r)))
-        c = 0.5 * e
-        a = np.sqrt(c * c + r * r) if c >= r else r
+    # K4 = segment collision samples (k_edge_collide) + ellipse PCA (k_edge_pca); the two halves of
+    # SURVEY.md's 16*(m*k(r) + k_e) + 32 + 9 figure, each reading the two endpoints (20 B)
+    e = P.expand_dist
+    m = int(np.ceil(e / (0.5 * r)))
+    c = 0.5 * e
+    a = np.sqrt(c * c + r * r) if c >= r else r
+    if kernel == "k_edge_collide":
+        return 16.0 * m * k_r + 20 + 1
+    if kernel == "k_edge_pca":
+        return 16.0 * np.pi * a * a * rho + 20 + 9
+    if kernel in ("k_edge_eval", "k_edge_eval_warp"):
         return 16.0 * (m * k_r + np.pi * a * a * rho) + 32 + 9
+    if kernel in ("k_nodes_nearest",):
+        return 0.0
     if kernel in ("k_bbox", "k_count"):
         return 12.0
     if kernel in ("k_scatter", "k_sort_cell"):
@@ -178,8 +186,12 @@ def run_product(a):
         got = sharding.allgather_boundary(dist, torch, g.pos[sel], g.ids[sel], torch.device("cuda", local))
         return int(sum(p.shape[0] for p, _ in got) * 16)
 
+    STAT_KEYS = ("us_sample", "us_eval", "us_commit", "us_wait", "us_clean", "us_draws", "pops", "window_launches",
+                 "eval_launches", "window_tests", "edge_evals")
+
     def one_step(resident: bool):
         t.seed(SEED_RNG)
+        s0 = {k: t.stat(k) for k in STAT_KEYS}
         w0 = time.perf_counter()
         if resident:
             t.set_global_map_dev(d_pts.data_ptr(), n, 3)
@@ -193,7 +205,10 @@ def run_product(a):
         r = t.plan_batch(queries)
         w3 = time.perf_counter()
         nn, ne = t.counts()
-        return dict(build_s=w1 - w0, exch_s=w2 - w1, query_s=w3 - w2, step_s=w3 - w0, nodes=nn, edges=ne,
+        host = {k: t.stat(k) - s0[k] for k in STAT_KEYS}
+        host.update(map_ms=round(1e3 * t.seconds("set_global_map"), 2), init_ms=round(1e3 * t.seconds("init_graph"), 2),
+                    snap_ms=round(1e3 * t.seconds("plan_snap"), 2), plan_ms=round(1e3 * t.seconds("plan_batch"), 2))
+        return dict(host=host, build_s=w1 - w0, exch_s=w2 - w1, query_s=w3 - w2, step_s=w3 - w0, nodes=nn, edges=ne,
                     found=int(r["found"].sum()), d2h=int(r["ids"].nbytes + 4 * 4 * a.queries + 2 * a.queries +
                                                          8 * (a.queries + 1)), xbytes=xb)
 
@@ -204,7 +219,7 @@ def run_product(a):
         if prof:
             K.prof_reset(); K.prof_enable(True)
         l0 = K.launch_count()
-        sampler = ClockSampler(local).start() if rank == 0 else None
+        sampler = ClockSampler(local, a.clock_ms).start() if (rank == 0 and a.clock_ms > 0) else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rows = [one_step(resident) for _ in range(steps)]
@@ -296,6 +311,7 @@ def run_product(a):
                 "build_ms": 1e3 * e_build, "query_ms": 1e3 * e_query, "paths_per_sec": tot_q / e_query,
                 "nodes_per_sec": tot_nodes / e_build},
         "gpu_launches": int(val["launches"]),
+        "host_breakdown_per_step": {"value_leg": [r["host"] for r in val["rows"]], "e2e_leg": [r["host"] for r in e2e["rows"]]},
         "clocks": val["clocks"],
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -319,6 +335,8 @@ def saturated_kernels(trg, K, torch, t, P, bb, rho, cell, peak):
     rng = np.random.default_rng(10)
     nq = 4_000_000
     q = np.stack([rng.uniform(bb[0][0], bb[0][1], nq), rng.uniform(bb[1][0], bb[1][1], nq)], 1).astype(np.float32)
+    key = np.floor((q[:, 1] - bb[1][0]) / 0.6).astype(np.int64) * 1_000_000 + np.floor((q[:, 0] - bb[0][0]) / 0.6).astype(np.int64)
+    q = q[np.argsort(key, kind="stable")]
     ne = 1_000_000
     ang = rng.uniform(0, 2 * np.pi, ne)
     p1 = np.column_stack([q[:ne], np.zeros(ne, np.float32)]).astype(np.float32)
@@ -334,7 +352,7 @@ def saturated_kernels(trg, K, torch, t, P, bb, rho, cell, peak):
     tl.trg_device_map.restype = C.c_void_p
     tl.trg_device_map.argtypes = [C.c_void_p, C.c_char_p]
     m = C.c_void_p(tl.trg_device_map(t.h, b"global"))
-    prm = K.EdgeParams(P.robot_size, P.height_threshold, P.collision_threshold)
+    prm = K.EdgeParams(P.robot_size, P.height_threshold, P.collision_threshold, 0)
     res = {}
     for rep in range(4):
         if rep == 1:
@@ -345,11 +363,19 @@ def saturated_kernels(trg, K, torch, t, P, bb, rho, cell, peak):
                                 C.c_void_p(st8.data_ptr()), C.c_void_p(w.data_ptr()), C.c_void_p(dd.data_ptr()), None)
         L.trgb_map_sync(m)
     pr = K.prof_collect(); K.prof_enable(False)
-    for k in ("k_collision", "k_edge_eval"):
+    for k in ("k_collision", "k_edge_collide", "k_edge_pca"):
+        if k not in pr:
+            continue
         v = pr[k]
         gbs = unit_bytes(k, P, rho, cell) * v["units"] / v["ms"] / 1e6
         res[k] = {"units_per_launch": int(v["units"] / v["launches"]), "avg_launch_ms": round(v["ms"] / v["launches"], 4),
                   "units_per_s": v["units"] / v["ms"] * 1e3, "achieved_gbs": round(gbs, 1), "frac_of_peak": round(gbs / peak, 4)}
+    if "k_edge_collide" in pr and "k_edge_pca" in pr:   # K4 as a whole
+        ms = pr["k_edge_collide"]["ms"] + pr["k_edge_pca"]["ms"]
+        units = pr["k_edge_pca"]["units"]
+        gbs = unit_bytes("k_edge_eval", P, rho, cell) * units / ms / 1e6
+        res["edge_eval_total"] = {"units_per_s": units / ms * 1e3, "achieved_gbs": round(gbs, 1), "frac_of_peak": round(gbs / peak, 4)}
+    res["note"] = "queries uniform over the map, sorted by 0.6 m tile (spatially coherent threads)"
     return res
 
 
@@ -417,6 +443,7 @@ def main():
     ap.add_argument("--cpu-side", type=int, default=CPU_SAMPLE_SIDE)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sat", action="store_true")
+    ap.add_argument("--clock-ms", type=int, default=200, help="nvidia-smi sampling period during the timed region (0 = off)")
     a = ap.parse_args()
     if a.warmup < 3 and a.impl == "b200":
         a.warmup = max(a.warmup, 1)

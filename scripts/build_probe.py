@@ -16,6 +16,8 @@ ap.add_argument("--chunk", type=int, default=0)
 ap.add_argument("--window", type=int, default=0)
 ap.add_argument("--cell", type=float, default=0)
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--reuse", action="store_true")
+ap.add_argument("--noq", action="store_true")
 a = ap.parse_args()
 P = trg.MOUNTAIN if a.kind == "mountain" else trg.INDOOR
 t0 = time.time()
@@ -23,8 +25,11 @@ pts = trg.terrain.mountain(a.n, h=a.h, seed=2) if a.kind == "mountain" else trg.
 print(f"gen {pts.shape[0]} pts {time.time()-t0:.1f}s", flush=True)
 ext = a.n * a.h
 start = (ext / 2, ext / 2, 0.0) if a.kind == "mountain" else (3.27, 4.12, 0.0)
+t = None
 for rep in range(a.reps):
-    t = trg.product(P)
+    if t is None or not a.reuse:
+        t = trg.product(P)
+    prev = {k: t.stat(k) for k in ("us_sample", "us_eval", "us_commit", "us_draws", "us_clean", "us_wait")}
     if a.chunk: t.set_tuning("chunk_nodes", a.chunk)
     if a.window: t.set_tuning("window", a.window)
     if a.cell: t.set_tuning("map_cell_scale", a.cell)
@@ -34,7 +39,7 @@ for rep in range(a.reps):
     t.init_graph(start); w2 = time.time()
     nn, ne = t.counts()
     q = trg.terrain.query_pairs(trg.terrain.bbox(pts), a.queries, seed=7)
-    r = t.plan_batch(q); w3 = time.time()
+    r = t.plan_batch(q) if not a.noq else dict(found=np.zeros(1)); w3 = time.time()
     prof = K.prof_collect(); K.prof_enable(False)
     stats = {k: t.stat(k) for k in ("pops", "rng_draws", "window_launches", "eval_launches", "flush_launches", "stalls",
                                     "window_tests", "edge_evals", "nearest_map", "batches", "node_ties", "z_ties",
@@ -45,4 +50,6 @@ for rep in range(a.reps):
                           paths_per_s=round(a.queries / (w3 - w2)), stats=stats)), flush=True)
     for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
         print(f"   {k:18s} launches={v['launches']:6d} ms={v['ms']:10.3f} avg_us={1e3*v['ms']/max(1,v['launches']):9.2f}")
-    t.close()
+    print("   delta", {k: t.stat(k) - v for k, v in prev.items()})
+    if not a.reuse:
+        t.close()

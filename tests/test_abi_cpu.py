@@ -36,7 +36,7 @@ def test_oracle_facade_mirrors_product_facade(built):
 
 def test_host_node_index_against_kdtree_port(built, tmp_path):
     exe = tmp_path / "node_index_check"
-    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", f"-I{ROOT/'oracle'}",
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-pthread", f"-I{ROOT/'oracle'}",
                     f"-I{ROOT/'trg-planner_b200'/'host'}", str(ROOT / "tests" / "host" / "node_index_check.cpp"),
                     "-o", str(exe)], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)

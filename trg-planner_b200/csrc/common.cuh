@@ -346,6 +346,7 @@ constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
 // thread-per-query kernels: 128 threads per CTA, one shared z column per thread
 constexpr int kTqThreads = 128;
+void tune_mempool_once();  // raise the default mempool's release threshold (map_index.cu)
 int sm_count();
 int grid_for_warps(int64_t n_warps, int ctas_per_sm);
 

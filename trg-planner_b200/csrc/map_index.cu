@@ -203,13 +203,30 @@ __global__ void __launch_bounds__(256) k_sort_cell(const uint32_t* __restrict__ 
   }
 }
 
+// Device memory comes from the stream-ordered pool with an unbounded release threshold: a TRG that
+// is rebuilt again and again (bench steps, per-scan local maps) reuses the same blocks instead of
+// paying cudaMalloc / cudaFree (which occasionally stall for a second on a freshly freed 100+ MB).
+void tune_mempool_once() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  int dev = 0;
+  cudaMemPool_t pool;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  cudaGetLastError();
+}
+
 static int build_index(trgb_map* m, const float* d_in, int64_t n, int stride, float cell) {
   cudaStream_t st = m->stream;
+  tune_mempool_once();
   const int sms = sm_count();
   const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sms * 16);
 
   float* d_bbox = nullptr;
-  TRGB_CUDA(cudaMalloc(&d_bbox, 4 * sizeof(float)));
+  TRGB_CUDA(cudaMallocAsync((void**)&d_bbox, 4 * sizeof(float), st));
   const float init[4] = {FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX};
   TRGB_CUDA(cudaMemcpyAsync(d_bbox, init, sizeof(init), cudaMemcpyHostToDevice, st));
   {
@@ -219,7 +236,7 @@ static int build_index(trgb_map* m, const float* d_in, int64_t n, int stride, fl
   float bbox[4];
   TRGB_CUDA(cudaMemcpyAsync(bbox, d_bbox, sizeof(bbox), cudaMemcpyDeviceToHost, st));
   TRGB_CUDA(cudaStreamSynchronize(st));
-  cudaFree(d_bbox);
+  cudaFreeAsync(d_bbox, st);
   if (!(bbox[0] <= bbox[2]) || !(bbox[1] <= bbox[3]) || !std::isfinite(bbox[0]) ||
       !std::isfinite(bbox[3])) {
     set_error("map_create: non-finite or empty bounding box");
@@ -242,11 +259,11 @@ static int build_index(trgb_map* m, const float* d_in, int64_t n, int stride, fl
 
   uint32_t *d_counts = nullptr, *d_fill = nullptr, *d_sums = nullptr;
   const int nb = (int)((ncells + kScanTile - 1) / kScanTile);
-  TRGB_CUDA(cudaMalloc(&d_counts, ncells * sizeof(uint32_t)));
-  TRGB_CUDA(cudaMalloc(&d_fill, ncells * sizeof(uint32_t)));
-  TRGB_CUDA(cudaMalloc(&d_sums, (size_t)std::max(nb, 1) * sizeof(uint32_t)));
-  TRGB_CUDA(cudaMalloc(&m->d_cell_start, (ncells + 1) * sizeof(uint32_t)));
-  TRGB_CUDA(cudaMalloc(&m->d_pts, (size_t)n * sizeof(float4)));
+  TRGB_CUDA(cudaMallocAsync((void**)&d_counts, ncells * sizeof(uint32_t), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&d_fill, ncells * sizeof(uint32_t), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&d_sums, (size_t)std::max(nb, 1) * sizeof(uint32_t), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&m->d_cell_start, (ncells + 1) * sizeof(uint32_t), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&m->d_pts, (size_t)n * sizeof(float4), st));
   m->device_bytes = (ncells + 1) * (int64_t)sizeof(uint32_t) + n * (int64_t)sizeof(float4);
   TRGB_CUDA(cudaMemsetAsync(d_counts, 0, ncells * sizeof(uint32_t), st));
   TRGB_CUDA(cudaMemsetAsync(d_fill, 0, ncells * sizeof(uint32_t), st));
@@ -270,10 +287,10 @@ static int build_index(trgb_map* m, const float* d_in, int64_t n, int stride, fl
     k_sort_cell<<<g2, 256, 0, st>>>(m->d_cell_start, ncells, m->d_pts);
   }
   TRGB_CUDA(cudaGetLastError());
+  cudaFreeAsync(d_counts, st);
+  cudaFreeAsync(d_fill, st);
+  cudaFreeAsync(d_sums, st);
   TRGB_CUDA(cudaStreamSynchronize(st));
-  cudaFree(d_counts);
-  cudaFree(d_fill);
-  cudaFree(d_sums);
   v.pts = m->d_pts;
   v.cell_start = m->d_cell_start;
   return TRGB_OK;
@@ -310,23 +327,26 @@ extern "C" int trgb_map_create(trgb_map** out, const float* host_pts, int64_t n,
                                float cell_size) {
   TRGB_ARG(host_pts != nullptr && n > 0, "empty point cloud");
   TRGB_ARG(stride_floats == 3 || stride_floats == 4, "stride_floats must be 3 or 4");
+  tune_mempool_once();
   float* d_in = nullptr;
   const size_t bytes = (size_t)n * stride_floats * sizeof(float);
-  TRGB_CUDA(cudaMalloc(&d_in, bytes));
-  cudaError_t e = cudaMemcpy(d_in, host_pts, bytes, cudaMemcpyHostToDevice);
+  TRGB_CUDA(cudaMallocAsync((void**)&d_in, bytes, 0));
+  cudaError_t e = cudaMemcpyAsync(d_in, host_pts, bytes, cudaMemcpyHostToDevice, 0);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(0);
   if (e != cudaSuccess) {
-    cudaFree(d_in);
+    cudaFreeAsync(d_in, 0);
     return cuda_fail(e, "cudaMemcpy H2D (map points)", __FILE__, __LINE__);
   }
   int rc = trgb_map_create_dev(out, d_in, n, stride_floats, cell_size);
-  cudaFree(d_in);
+  cudaFreeAsync(d_in, 0);
   return rc;
 }
 
 extern "C" void trgb_map_destroy(trgb_map* m) {
   if (!m) return;
-  if (m->d_pts) cudaFree(m->d_pts);
-  if (m->d_cell_start) cudaFree(m->d_cell_start);
+  if (m->d_pts) cudaFreeAsync(m->d_pts, m->stream);
+  if (m->d_cell_start) cudaFreeAsync(m->d_cell_start, m->stream);
+  if (m->stream) cudaStreamSynchronize(m->stream);
   if (m->d_stage) cudaFree(m->d_stage);
   if (m->h_stage) cudaFreeHost(m->h_stage);
   if (m->stream) cudaStreamDestroy(m->stream);

@@ -266,11 +266,21 @@ __global__ void __launch_bounds__(kSsspThreads) k_sssp(
 
 using namespace trgb;
 
+// All device memory of a graph handle comes from the stream-ordered pool (release threshold
+// raised to "never" by trgb::tune_mempool_once): a TRG that is rebuilt every few hundred
+// milliseconds re-uses the multi-GB search scratch instead of paying cudaMalloc / cudaFree.
+static void gfree(void* p, cudaStream_t st) {
+  if (p) cudaFreeAsync(p, st);
+}
 extern "C" void trgb_graph_destroy(trgb_graph* g) {
   if (!g) return;
-  cudaFree(g->d_row); cudaFree(g->d_col); cudaFree(g->d_w); cudaFree(g->d_dist); cudaFree(g->d_cost);
-  cudaFree(g->d_pos); cudaFree(g->d_state); cudaFree(g->d_label); cudaFree(g->d_queue); cudaFree(g->d_bits);
-  if (g->stream) cudaStreamDestroy(g->stream);
+  cudaStream_t st = g->stream;
+  gfree(g->d_row, st); gfree(g->d_col, st); gfree(g->d_w, st); gfree(g->d_dist, st); gfree(g->d_cost, st);
+  gfree(g->d_pos, st); gfree(g->d_state, st); gfree(g->d_label, st); gfree(g->d_queue, st); gfree(g->d_bits, st);
+  if (g->stream) {
+    cudaStreamSynchronize(g->stream);
+    cudaStreamDestroy(g->stream);
+  }
   delete g;
 }
 
@@ -278,7 +288,12 @@ extern "C" int trgb_graph_upload(trgb_graph** out, const TrgbGraphDesc* d) {
   TRGB_ARG(out && d, "null pointer");
   TRGB_ARG(d->n_nodes > 0 && d->row_ptr && d->pos_xyz && d->state, "empty graph");
   TRGB_ARG(d->n_edges == 0 || (d->col && d->weight && d->dist), "null edge arrays");
+  trgb::tune_mempool_once();
   trgb_graph* g = new trgb_graph();
+  {
+    cudaError_t es = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
+    if (es != cudaSuccess) { delete g; return cuda_fail(es, "cudaStreamCreate", __FILE__, __LINE__); }
+  }
   g->n = d->n_nodes;
   g->e = d->n_edges;
   const size_t n = g->n, e = g->e;
@@ -289,8 +304,8 @@ extern "C" int trgb_graph_upload(trgb_graph** out, const TrgbGraphDesc* d) {
   g->mean_cost = e ? (float)(mean / e) : 1.f;
 #define UP(dst, src, bytes)                                                                     \
   do {                                                                                          \
-    cudaError_t _e = cudaMalloc((void**)&(dst), (bytes) ? (bytes) : 1);                          \
-    if (_e == cudaSuccess && (bytes)) _e = cudaMemcpy((dst), (src), (bytes), cudaMemcpyHostToDevice); \
+    cudaError_t _e = cudaMallocAsync((void**)&(dst), (bytes) ? (bytes) : 1, g->stream);          \
+    if (_e == cudaSuccess && (bytes)) _e = cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, g->stream); \
     if (_e != cudaSuccess) { trgb_graph_destroy(g); return cuda_fail(_e, "graph upload", __FILE__, __LINE__); } \
   } while (0)
   UP(g->d_row, d->row_ptr, (n + 1) * sizeof(int64_t));
@@ -300,8 +315,8 @@ extern "C" int trgb_graph_upload(trgb_graph** out, const TrgbGraphDesc* d) {
   UP(g->d_pos, pos.data(), n * sizeof(float2));
   UP(g->d_state, d->state, n * sizeof(int32_t));
 #undef UP
-  cudaError_t er = cudaMalloc((void**)&g->d_cost, (e ? e : 1) * sizeof(float));
-  if (er == cudaSuccess) er = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
+  cudaError_t er = cudaMallocAsync((void**)&g->d_cost, (e ? e : 1) * sizeof(float), g->stream);
+  if (er == cudaSuccess) er = cudaStreamSynchronize(g->stream);  // the host arrays may go away after return
   if (er != cudaSuccess) { trgb_graph_destroy(g); return cuda_fail(er, "graph alloc", __FILE__, __LINE__); }
   *out = g;
   return TRGB_OK;
@@ -309,12 +324,12 @@ extern "C" int trgb_graph_upload(trgb_graph** out, const TrgbGraphDesc* d) {
 
 static int ensure_slots(trgb_graph* g, int want) {
   if (g->nslots >= want) return TRGB_OK;
-  cudaFree(g->d_label); cudaFree(g->d_queue); cudaFree(g->d_bits);
+  gfree(g->d_label, g->stream); gfree(g->d_queue, g->stream); gfree(g->d_bits, g->stream);
   g->d_label = nullptr; g->d_queue = nullptr; g->d_bits = nullptr; g->nslots = 0;
   const size_t n = g->n, words = (n + 31) / 32;
-  TRGB_CUDA(cudaMalloc((void**)&g->d_label, (size_t)want * n * sizeof(unsigned long long)));
-  TRGB_CUDA(cudaMalloc((void**)&g->d_queue, (size_t)want * 4 * n * sizeof(int32_t)));
-  TRGB_CUDA(cudaMalloc((void**)&g->d_bits, (size_t)want * 2 * words * sizeof(uint32_t)));
+  TRGB_CUDA(cudaMallocAsync((void**)&g->d_label, (size_t)want * n * sizeof(unsigned long long), g->stream));
+  TRGB_CUDA(cudaMallocAsync((void**)&g->d_queue, (size_t)want * 4 * n * sizeof(int32_t), g->stream));
+  TRGB_CUDA(cudaMallocAsync((void**)&g->d_bits, (size_t)want * 2 * words * sizeof(uint32_t), g->stream));
   g->nslots = want;
   return TRGB_OK;
 }
@@ -342,9 +357,9 @@ extern "C" int trgb_sssp_batch(trgb_graph* g, const int32_t* start_ids, const in
   int rc = ensure_slots(g, want);
   if (rc) return rc;
 
-  struct Dev { void* p = nullptr; ~Dev() { if (p) cudaFree(p); } };
+  struct Dev { void* p = nullptr; cudaStream_t s = nullptr; ~Dev() { if (p) cudaFreeAsync(p, s); } };
   Dev d_s, d_g, d_found, d_cost, d_len, d_risk, d_off, d_plen, d_ids, d_cur;
-#define DALLOC(b, bytes) TRGB_CUDA(cudaMalloc(&(b).p, (bytes) ? (bytes) : 1))
+#define DALLOC(b, bytes) do { (b).s = st; TRGB_CUDA(cudaMallocAsync(&(b).p, (bytes) ? (bytes) : 1, st)); } while (0)
   DALLOC(d_s, nq * sizeof(int32_t)); DALLOC(d_g, nq * sizeof(int32_t));
   DALLOC(d_found, nq); DALLOC(d_cost, nq * sizeof(float)); DALLOC(d_len, nq * sizeof(float));
   DALLOC(d_risk, nq * sizeof(float)); DALLOC(d_off, nq * sizeof(int64_t)); DALLOC(d_plen, nq * sizeof(int32_t));

@@ -12,6 +12,7 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <future>
 #include <limits>
 #include <vector>
 
@@ -73,9 +74,17 @@ class OrderTree2D {
     }
     std::vector<int> idx(n), tmp(n);
     for (int i = 0; i < n; ++i) idx[i] = i;
-    struct Job { int b, e; uint8_t axis; };
+    build_range(x, y, idx.data(), tmp.data(), 0, n, 0, 0);
+  }
+
+ private:
+  // subtree over idx[b, e) (insertion order preserved); large halves run on helper threads —
+  // the two halves touch disjoint slices of idx / tmp and disjoint tree nodes
+  void build_range(const float* x, const float* y, int* idx, int* tmp, int b, int e, uint8_t axis, int depth) {
+    struct Job { int b, e; uint8_t axis; int depth; };
     std::vector<Job> jobs;
-    jobs.push_back({0, n, 0});
+    std::vector<std::future<void>> helpers;
+    jobs.push_back({b, e, axis, depth});
     while (!jobs.empty()) {
       const Job j = jobs.back();
       jobs.pop_back();
@@ -87,14 +96,25 @@ class OrderTree2D {
       for (int k = j.b + 1; k < j.e; ++k) {
         const int p = idx[k];
         if (key[p] < split) idx[j.b + 1 + nl++] = p;
-        else tmp[nh++] = p;
+        else tmp[j.b + nh++] = p;
       }
-      for (int k = 0; k < nh; ++k) idx[j.b + 1 + nl + k] = tmp[k];
-      if (nl) { lo_[root] = idx[j.b + 1]; jobs.push_back({j.b + 1, j.b + 1 + nl, (uint8_t)(j.axis ^ 1)}); }
-      if (nh) { hi_[root] = idx[j.b + 1 + nl]; jobs.push_back({j.b + 1 + nl, j.e, (uint8_t)(j.axis ^ 1)}); }
+      for (int k = 0; k < nh; ++k) idx[j.b + 1 + nl + k] = tmp[j.b + k];
+      const uint8_t nax = static_cast<uint8_t>(j.axis ^ 1);
+      if (nl) lo_[root] = idx[j.b + 1];
+      if (nh) hi_[root] = idx[j.b + 1 + nl];
+      const int lb = j.b + 1, le = j.b + 1 + nl, hb = le, he = j.e, nd = j.depth + 1;
+      if (nh) {
+        if (j.depth < 5 && nh > 8192 && nl > 8192)
+          helpers.push_back(std::async(std::launch::async, [=] { build_range(x, y, idx, tmp, hb, he, nax, nd); }));
+        else
+          jobs.push_back({hb, he, nax, nd});
+      }
+      if (nl) jobs.push_back({lb, le, nax, nd});
     }
+    for (auto& h : helpers) h.get();
   }
 
+ public:
   // In-range payloads in the order the reference's result iterator yields them: the traversal
   // is pre-order, query side first, far side only if |delta| < r; results are prepended, so
   // the iteration order is the reverse of the visit order.
