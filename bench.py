@@ -154,7 +154,13 @@ def run_product(a):
     torch.cuda.set_device(local)
     K.set_device(local)
     dist = None
+    saved_stdout = None
     if world > 1:
+        # NCCL prints its version banner on stdout when the communicator is created; the driver wants
+        # exactly one JSON line there, so stdout points at stderr until the result is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -181,7 +187,7 @@ def run_product(a):
         if dist is None:
             return 0
         from trg_planner_b200 import sharding
-        g = t.export()
+        g = t.export(edges=False)
         sel = sharding.boundary_nodes(g.pos, bb[0][0], bb[0][1], P.expand_dist + P.robot_size, rank, world)
         got = sharding.allgather_boundary(dist, torch, g.pos[sel], g.ids[sel], torch.device("cuda", local))
         return int(sum(p.shape[0] for p, _ in got) * 16)
@@ -323,7 +329,10 @@ def run_product(a):
     }
     if world > 1:
         line["exchange"] = {"allgather_bytes_per_step": val["rows"][-1]["xbytes"], "ms": 1e3 * val["exch_s"]}
-    print(json.dumps(line))
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 

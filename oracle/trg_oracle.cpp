@@ -611,6 +611,27 @@ class TRGOracle {
     return found;
   }
 
+  // trg.cpp:567-574
+  bool checkReadched(V2 pos2d) {
+    float dist = erst::v2_norm(goal_.pose2d.x - pos2d.x, goal_.pose2d.y - pos2d.y);
+    if (dist < param_.goal_tolerance) return true;
+    return false;
+  }
+
+  // trg.cpp:576-601
+  bool checkReplan(V2 pos2d, const std::vector<V3>& path) {
+    if (goal_.node == nullptr) return false;
+    float dist2subgoal = erst::v2_norm(goal_.node->pos_.x - pos2d.x, goal_.node->pos_.y - pos2d.y);
+    if (!goal_.isKnown && dist2subgoal < param_.goal_tolerance) return true;
+    if (!goal_.isKnown && goal_.node->state_ != Frontier) return true;
+    std::vector<int64_t> r;
+    for (auto& pt : path) {
+      global_.node_tree.range(pt.x, pt.y, param_.robot_size, &r);
+      if (r.empty()) return true;
+    }
+    return false;
+  }
+
   // trg.cpp:692-730 (point_between = 1)
   void refinePath(const std::vector<V3>& in_path, std::vector<V3>& out_path) {
     std::deque<V3> dense_path;
@@ -746,6 +767,13 @@ int orc_refine_path(void* h, const float* in_xyz, int n_in, float* out_xyz, int*
     out_xyz[3 * i] = out[i].x; out_xyz[3 * i + 1] = out[i].y; out_xyz[3 * i + 2] = out[i].z;
   }
   return 0;
+}
+
+int orc_check_reached(void* h, float x, float y) { return H(h)->checkReadched({x, y}) ? 1 : 0; }
+int orc_check_replan(void* h, float x, float y, const float* path_xyz, int n_path) {
+  std::vector<V3> path(n_path);
+  for (int i = 0; i < n_path; ++i) path[i] = {path_xyz[3 * i], path_xyz[3 * i + 1], path_xyz[3 * i + 2]};
+  return H(h)->checkReplan({x, y}, path) ? 1 : 0;
 }
 
 int orc_is_collision_batch(void* h, const char* type, const float* xy, int64_t n, float threshold,

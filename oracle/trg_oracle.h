@@ -68,6 +68,8 @@ int orc_plan(void* h, float sx, float sy, float gx, float gy, float gz,
              int* goal_known, int64_t* n_expanded);
 // TRG::refinePath trg.cpp:692
 int orc_refine_path(void* h, const float* in_xyz, int n_in, float* out_xyz, int* n_out);
+int orc_check_reached(void* h, float x, float y);                                         // trg.cpp:567
+int orc_check_replan(void* h, float x, float y, const float* path_xyz, int n_path);       // trg.cpp:576
 
 // ---- pure functions of (query, static map, params): kernel-level parity ----
 int orc_is_collision_batch(void* h, const char* type, const float* xy, int64_t n,

@@ -74,7 +74,8 @@ def test_init_graph_scheduler_invariance(pkg, K, tuning, small_indoor):
 def test_overlapped_build_mountain(pkg, K, small_mountain):
     """Mountain parameters take the two-thread path (helper feeds batch k+1 while batch k commits):
     small batches force many hand-overs; the graph must not change."""
-    for tuning in (dict(chunk_nodes=300, overlap=1), dict(chunk_nodes=300, overlap=0), dict(chunk_nodes=32, window=32)):
+    for tuning in (dict(chunk_nodes=300, overlap=1), dict(chunk_nodes=300, overlap=0), dict(chunk_nodes=32, window=32),
+                   dict(split_commit=1), dict(split_commit=1, overlap=0), dict(chunk_nodes=50, split_commit=1, overlap=1)):
         t, o = build_pair(pkg, pkg.MOUNTAIN, small_mountain, (15.0, 15.0, 0.0), seed=9, tuning=tuning)
         assert t.stat("rng_draws") == o.stat("rng_draws")
         assert_graph_equal(t.export(), o.export(), str(tuning))
@@ -126,6 +127,17 @@ def test_plan_parity_single_and_batch(pkg, K, small_mountain):
             assert abs(res["avg_risk"][i] - ro["avg_risk"]) <= TOL * max(1e-3, ro["avg_risk"]) + 1e-7
     print(f"identical node sequences {same}/{len(q)}")
     assert same >= 0.9 * len(q)
+    # checkReadched / checkReplan (trg.cpp:567-601) after each single plan: goal state, subgoal
+    # distance, and the "path still covered by nodes" scan
+    rng = np.random.default_rng(3)
+    for i in range(0, 60, 3):
+        r1, ro = t.plan(q[i, :2], q[i, 2:5]), o.plan(q[i, :2], q[i, 2:5])
+        for probe in (q[i, :2], q[i, 2:4], q[i, 2:4] + rng.uniform(-0.7, 0.7, 2).astype(np.float32)):
+            assert t.check_reached(probe) == o.check_reached(probe)
+            path = ro["path"] if ro["found"] else np.zeros((0, 3), np.float32)
+            assert t.check_replan(probe, path) == o.check_replan(probe, path)
+            off = path + np.float32([40.0, 0.0, 0.0]) if len(path) else path   # a path far off the graph
+            assert t.check_replan(probe, off) == o.check_replan(probe, off)
     # single-query API (TRG::planSafePath) == batch
     for i in (0, 5, 17):
         r1 = t.plan(q[i, :2], q[i, 2:5])

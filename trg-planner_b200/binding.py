@@ -88,6 +88,8 @@ class TrgFacade:
         f("last_seconds").argtypes = [_vp, C.c_char_p]
         f("stat").restype = C.c_int64
         f("stat").argtypes = [_vp, C.c_char_p]
+        f("check_reached").argtypes = [_vp, C.c_float, C.c_float]
+        f("check_replan").argtypes = [_vp, C.c_float, C.c_float, _vp, C.c_int]
         if self.p == "trg":
             f("last_error").restype = C.c_char_p
             f("last_error").argtypes = []
@@ -96,8 +98,6 @@ class TrgFacade:
             f("load_graph").argtypes = [_vp, C.c_char_p]
             f("set_tuning").argtypes = [_vp, C.c_char_p, C.c_double]
             f("set_global_map_dev").argtypes = [_vp, _vp, C.c_int64, C.c_int]
-            f("check_reached").argtypes = [_vp, C.c_float, C.c_float]
-            f("check_replan").argtypes = [_vp, C.c_float, C.c_float, _vp, C.c_int]
 
     def last_error(self) -> str:
         if self.p != "trg":
@@ -144,16 +144,16 @@ class TrgFacade:
         self._f("graph_counts")(self.h, type_.encode(), C.byref(n), C.byref(e))
         return n.value, e.value
 
-    def export(self, type_="global") -> GraphSnapshot:
+    def export(self, type_="global", edges: bool = True) -> GraphSnapshot:
         n, e = self.counts(type_)
         iter_ids = np.empty(n, np.int32)
         ids = np.empty(n, np.int32)
         pos = np.empty((n, 3), np.float32)
         state = np.empty(n, np.int32)
         row_ptr = np.empty(n + 1, np.int64)
-        col = np.empty(e, np.int32)
-        w = np.empty(e, np.float32)
-        d = np.empty(e, np.float32)
+        col = np.empty(e, np.int32) if edges else None
+        w = np.empty(e, np.float32) if edges else None
+        d = np.empty(e, np.float32) if edges else None
         self._chk(self._f("graph_export")(self.h, type_.encode(), *[_ptr(a) for a in
                                           (iter_ids, ids, pos, state, row_ptr, col, w, d)]), "graph_export")
         return GraphSnapshot(iter_ids, ids, pos, state, row_ptr, col, w, d)
@@ -205,6 +205,13 @@ class TrgFacade:
     def set_global_map_dev(self, dev_ptr: int, n: int, stride: int = 3):
         """Map cloud already resident in HBM (bench `value` leg)."""
         self._chk(self._f("set_global_map_dev")(self.h, C.c_void_p(dev_ptr), n, stride), "set_global_map_dev")
+
+    def check_reached(self, xy) -> bool:
+        return bool(self._chk(self._f("check_reached")(self.h, float(xy[0]), float(xy[1])), "check_reached"))
+
+    def check_replan(self, xy, path: np.ndarray) -> bool:
+        p = np.ascontiguousarray(path, dtype=np.float32)
+        return bool(self._chk(self._f("check_replan")(self.h, float(xy[0]), float(xy[1]), _ptr(p), p.shape[0]), "check_replan"))
 
     def refine_path(self, path: np.ndarray):
         p = np.ascontiguousarray(path, dtype=np.float32)

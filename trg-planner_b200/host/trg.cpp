@@ -14,7 +14,11 @@
 #include <chrono>
 #include <cstring>
 #include <limits>
+#include <atomic>
+#include <exception>
+#include <functional>
 #include <stdexcept>
+#include <thread>
 
 #include "device_session.h"
 #include "trgb_kernels.h"
@@ -557,12 +561,81 @@ class ChunkTable {
   std::vector<E> ent_;
 };
 
+// Single-producer / single-consumer queue of edge-list operations. While the committing thread
+// decides (nearest node, new node or not, queue push), a second thread applies what those decisions
+// imply for the adjacency lists — duplicate checks, slope gate, placeholder edges — in the same
+// order. Legal whenever no decision reads an edge list, i.e. without the step-3 neighbour wiring
+// (there a new node is Invalid exactly when its parent edge failed, which the decider knows).
+struct EdgeOp {
+  TRG::Node* a;
+  TRG::Node* b;
+  float w, d;
+  int kind;  // 0 = wireEdge(a, b) deferred, 1 = parent edge a <-> b with (w, d)
+};
+
+template <class Apply>
+class EdgeWorker {
+ public:
+  explicit EdgeWorker(Apply apply) : apply_(std::move(apply)), ring_(kCap) {
+    thread_ = std::thread([this] { loop(); });
+  }
+  ~EdgeWorker() {
+    stop_.store(true, std::memory_order_release);
+    if (thread_.joinable()) thread_.join();
+  }
+  void push(const EdgeOp& op) {
+    const size_t t = tail_.load(std::memory_order_relaxed);
+    while (t - head_.load(std::memory_order_acquire) >= kCap) pause();
+    ring_[t & (kCap - 1)] = op;
+    tail_.store(t + 1, std::memory_order_release);
+  }
+  // wait until every pushed operation has been applied; rethrows a failure of the worker
+  void drain() {
+    const size_t t = tail_.load(std::memory_order_relaxed);
+    while (head_.load(std::memory_order_acquire) < t && !failed_.load(std::memory_order_acquire)) pause();
+    if (failed_.load(std::memory_order_acquire)) std::rethrow_exception(error_);
+  }
+
+ private:
+  static constexpr size_t kCap = (size_t)1 << 16;
+  static void pause() {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+  void loop() {
+    try {
+      size_t h = 0;
+      while (true) {
+        const size_t t = tail_.load(std::memory_order_acquire);
+        if (h == t) {
+          if (stop_.load(std::memory_order_acquire)) return;
+          pause();
+          continue;
+        }
+        for (; h < t; ++h) apply_(ring_[h & (kCap - 1)]);
+        head_.store(h, std::memory_order_release);
+      }
+    } catch (...) {
+      error_ = std::current_exception();
+      failed_.store(true, std::memory_order_release);
+    }
+  }
+  Apply apply_;
+  std::vector<EdgeOp> ring_;
+  std::atomic<size_t> head_{0}, tail_{0};
+  std::atomic<bool> stop_{false}, failed_{false};
+  std::exception_ptr error_;
+  std::thread thread_;
+};
+
 class Expander {
  public:
   Expander(TRG& t, TRG::trgStruct& g)
       : t_(t), g_(g), P_(t.param_), gate_(t.param_.height_threshold, t.param_.robot_size) {
     map_ = t.requireMap(g, "expandGraph");
     st_  = (cudaStream_t)trgb_map_stream(map_);
+    cuda_check(cudaGetDevice(&device_), "cudaGetDevice");
     // trg.cpp:429 — `float - float < double * float`
     step3_ = (P_.expand_dist - P_.robot_size < 0.25 * P_.expand_dist);
     mean_  = 1.15 * P_.sample_num;
@@ -597,6 +670,14 @@ class Expander {
     t_.compactDraws();
     const size_t C = (size_t)std::max(1, t_.tuning_.chunk_nodes);
     const bool overlap = t_.tuning_.overlap && roots.size() == 1 && !step3_;
+    auto apply = [this](const EdgeOp& op) { applyEdgeOp(op); };
+    std::unique_ptr<EdgeWorker<decltype(apply)>> worker;
+    if (t_.tuning_.split_commit && !step3_) {
+      worker.reset(new EdgeWorker<decltype(apply)>(apply));
+      push_op_ = [&worker](const EdgeOp& op) { worker->push(op); };
+    } else {
+      push_op_ = [this](const EdgeOp& op) { applyEdgeOp(op); };
+    }
     size_t root_i = 0;
     int cur_ref = -1;
     int cur = 0;
@@ -610,11 +691,16 @@ class Expander {
       bool launched = false;
       if (overlap && bfs_.size() - sent_ >= std::min<size_t>(256, C)) {
         launched = prepare(nb, roots, root_i, cur_ref, C, b.chain_end);
-        if (launched) fut = std::async(std::launch::async, [this, &nb] { feed(nb); });
+        if (launched)
+          fut = std::async(std::launch::async, [this, &nb] {
+            cuda_check(cudaSetDevice(device_), "cudaSetDevice(helper)");  // the current device is per thread
+            feed(nb);
+          });
       }
       auto tc = Clock::now();
       try {
         commit(b, roots, root_i, cur_ref);
+        if (worker) worker->drain();  // edge lists and pending_ are settled before the next hand-over
       } catch (...) {
         if (launched) fut.wait();
         throw;
@@ -632,6 +718,7 @@ class Expander {
       cur ^= 1;
     }
     absorb(B_[cur]);
+    worker.reset();  // joins the edge thread
     flushDeferred();
     t_.stat_["pops"] += n_pops_;
     t_.stat_["nearest_node"] += n_nearest_;
@@ -1008,6 +1095,15 @@ class Expander {
     pending_.push_back({a, b, ea, eb, a->pos_.x(), a->pos_.y(), a->pos_.z(), b->pos_.x(), b->pos_.y()});
   }
 
+  void applyEdgeOp(const EdgeOp& op) {
+    if (op.kind == 0) {
+      wireDeferred(op.a, op.b);
+    } else {
+      op.a->edges_.push_back(t_.newEdge(op.b->id_, op.w, op.d));
+      op.b->edges_.push_back(t_.newEdge(op.a->id_, op.w, op.d));
+    }
+  }
+
   // ---- phase C: commit a batch in the reference's order (trg.cpp:406-452) -------------------
   void commit(Batch& b, const std::vector<TRG::Node*>& roots, size_t& root_i, int& cur_ref) {
     resolveDeferred(b.deferred, b.d_stage.data(), b.d_w.data(), b.d_d.data());
@@ -1053,7 +1149,7 @@ class Expander {
       FT_LAP(nearest);
       if (ex->state_ == TRG::NodeState::Invalid) continue;
       if (norm2(ex->pos_.x() - s.x, ex->pos_.y() - s.y) < P_.robot_size) {
-        wireDeferred(node, ex);
+        push_op_({node, ex, 0.f, 0.f, 0});  // wireEdge(node, existing_node)
         FT_LAP(wire);
         continue;
       }
@@ -1068,8 +1164,7 @@ class Expander {
       // 2.1 wireEdge(node, new): slope gate on the host, geometry from the speculative batch
       bool parent_ok = false;
       if (b.stage[si] == TRGB_EDGE_OK && !gate_.rejects(node->pos_, nn->pos_)) {
-        node->edges_.push_back(t_.newEdge(nn->id_, b.w[si], b.d[si]));
-        nn->edges_.push_back(t_.newEdge(node->id_, b.w[si], b.d[si]));
+        push_op_({node, nn, b.w[si], b.d[si], 1});
         parent_ok = true;
       }
       // 3. wire to the neighbours within expand_dist, in kd result order
@@ -1085,8 +1180,9 @@ class Expander {
           flushDeferred();
         }
       }
-      // 4.
-      if (nn->edges_.size() < 1) {
+      // 4. `new_node->edges_.size() < 1` (trg.cpp:447): without step 3 the only possible edge is the
+      // parent edge; with it the lists are current (operations are applied inline in that mode)
+      if (step3_ ? nn->edges_.size() < 1 : !parent_ok) {
         nn->state_ = TRG::NodeState::Invalid;
         continue;
       }
@@ -1103,11 +1199,13 @@ class Expander {
   SlopeGate gate_;
   trgb_map* map_ = nullptr;
   cudaStream_t st_ = nullptr;
+  int device_ = 0;
   int64_t n_pops_ = 0, n_nearest_ = 0, n_zties_ = 0, n_stalls_ = 0;
   double us_commit_ = 0, us_wait_ = 0;
   bool step3_ = false;
   double mean_ = 8.0, var_ = 2.0;  // helper-side: running draws/pop statistics
   Batch B_[2];
+  std::function<void(const EdgeOp&)> push_op_;
   std::vector<TRG::Node*> bfs_;    // every node ever queued, in queue order
   size_t head_ = 0;                // next queue entry to commit
   size_t sent_ = 0;                // next queue entry not yet placed in a batch
@@ -1166,39 +1264,58 @@ void TRG::cleanGraph(bool updateLocal) {  // trg.cpp:491-535
   trgStruct&                     g = *trgMap_["global"];
   std::unordered_map<int, Node*> new_nodes;
   int                            new_id = 0;
-  // old id -> (node, new id) tables instead of the reference's old2new map and per-edge map lookups:
-  // same mapping, direct indexing (ids are dense counters: trg.cpp:250, 502)
+  // old id -> node / new id tables instead of the reference's old2new map and per-edge map lookups:
+  // same mapping, direct indexing. Every node of the map is in node_seq with id_ == its key
+  // (trg.cpp:248-250, 502, 526; loadPrebuiltGraph :96), so the tables fill sequentially.
   int max_id = -1;
-  for (auto& node : g.nodes) max_id = std::max(max_id, node.first);
+  for (Node* n : g.node_seq) max_id = std::max(max_id, n->id_);
   std::vector<Node*> by_id((size_t)(max_id + 1), nullptr);
   std::vector<int>   old2new((size_t)(max_id + 1), -1);
-  for (auto& node : g.nodes) by_id[node.first] = node.second;
+  for (Node* n : g.node_seq) by_id[n->id_] = n;
+  // survivors get their new ids in the map's iteration order (:497-504)
+  std::vector<Node*> kept;
+  kept.reserve(g.nodes.size());
   for (auto& node : g.nodes) {
     if (node.second->state_ == NodeState::Invalid || node.second->edges_.size() < 1) continue;
     new_nodes[new_id]   = node.second;
     old2new[node.first] = new_id;
+    kept.push_back(node.second);
     new_id++;
   }
-  // the reference collects the ids of Invalid edge targets in a vector and std::find()s every edge
+  // The reference collects the ids of Invalid edge targets in a vector and std::find()s every edge
   // against it (:515); the same predicate is "target node is Invalid", evaluated directly here.
-  // Edges are rewritten in place (same order, same values as the reference's fresh copies).
-  for (auto& node : new_nodes) {
-    auto&  edges = node.second->edges_;
-    size_t keep  = 0;
-    for (Edge* edge : edges) {
-      if (by_id[edge->dst_id_]->state_ == NodeState::Invalid) continue;
-      edge->dst_id_  = old2new[edge->dst_id_] >= 0 ? old2new[edge->dst_id_] : 0;  // (:518 old2new[] default-inserts 0)
-      edges[keep++] = edge;
+  // Edges are rewritten in place (same order, same values as the reference's fresh copies); nodes
+  // are independent of each other, so the rewrite runs on a few threads.
+  auto rewrite = [&](size_t b, size_t e) {
+    for (size_t k = b; k < e; ++k) {
+      Node*  nd    = kept[k];
+      auto&  edges = nd->edges_;
+      size_t keep  = 0;
+      for (Edge* edge : edges) {
+        if (by_id[edge->dst_id_]->state_ == NodeState::Invalid) continue;
+        edge->dst_id_ = old2new[edge->dst_id_] >= 0 ? old2new[edge->dst_id_] : 0;  // (:518 old2new[] default-inserts 0)
+        edges[keep++] = edge;
+      }
+      edges.resize(keep);
     }
-    edges.resize(keep);
+  };
+  const size_t nk = kept.size();
+  const size_t nthreads = nk > 50000 ? std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+  if (nthreads <= 1) {
+    rewrite(0, nk);
+  } else {
+    std::vector<std::future<void>> jobs;
+    for (size_t t = 0; t < nthreads; ++t)
+      jobs.push_back(std::async(std::launch::async, rewrite, nk * t / nthreads, nk * (t + 1) / nthreads));
+    for (auto& j : jobs) j.get();
   }
-  for (auto& node : new_nodes) node.second->id_ = node.first;
+  for (size_t k = 0; k < nk; ++k) kept[k]->id_ = (int)k;
   this->resetGraph(g.type);
   // (the reference copy-assigns; a move leaves the same buckets, order and rehash state)
   g.nodes   = std::move(new_nodes);
   g.node_id = new_id;
   g.node_seq.reserve(g.nodes.size());
-  for (auto& node : g.nodes) nodeIndexInsert(g, node.second);
+  for (auto& node : g.nodes) nodeIndexInsert(g, node.second);  // node_tree order = new map's iteration order (:528-530)
   invalidateDeviceGraph();
   if (updateLocal) this->setLocalGraph(false);
 }

@@ -257,6 +257,7 @@ class TRG {
     int window = 128;         // sampling-window draws per node (<= 256)
     float map_cell_scale = 0.5f;  // map index cell = map_cell_scale * robot_size
     bool overlap = true;      // run the device phases of batch k+1 on a helper thread while batch k commits
+    bool split_commit = false;  // apply edge-list operations on a second thread while the first decides (measured slower on a 10 M-point map: cross-core traffic on the adjacency lists; kept for experiments)
   } tuning_;
 };
 
