@@ -270,7 +270,7 @@ def run_product(a):
 
     # ---- roofline of the dominant kernel inside the timed region -------------------------------
     rho = n / ((bb[0][1] - bb[0][0]) * (bb[1][1] - bb[1][0]))
-    cell = 0.5 * P.robot_size
+    cell = 0.67 * P.robot_size
     peak, peak_src = measured_peak_gbs()
     prof = {k: v for k, v in val["prof"].items() if v["launches"] > 0}
     dom = max((k for k in prof if unit_bytes(k, P, rho, cell) > 0), key=lambda k: prof[k]["ms"])

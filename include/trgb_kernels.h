@@ -28,7 +28,8 @@ enum { TRGB_OK = 0, TRGB_E_ARG = -1, TRGB_E_CUDA = -2, TRGB_E_NOMEM = -3, TRGB_E
 
 /* stage at which TRG::wireEdge's geometric part stops (trg.cpp:269-329). The slope gate
  * (:269-274, glibc atan2f) is applied on the host side of the boundary. */
-enum { TRGB_EDGE_OK = 0, TRGB_EDGE_SLOPE = 1, TRGB_EDGE_COLLISION = 2, TRGB_EDGE_EMPTY = 3, TRGB_EDGE_FEWPTS = 4 };
+enum { TRGB_EDGE_OK = 0, TRGB_EDGE_SLOPE = 1, TRGB_EDGE_COLLISION = 2, TRGB_EDGE_EMPTY = 3, TRGB_EDGE_FEWPTS = 4,
+       TRGB_EDGE_SKIPPED = 5 /* not evaluated: see trgb_edge_eval_launch_skip */ };
 
 typedef struct trgb_map trgb_map;     /* device-resident cell index over one point cloud  */
 typedef struct trgb_graph trgb_graph; /* device-resident CSR graph + node kd-tree arrays  */
@@ -66,7 +67,9 @@ int  trgb_map_info(const trgb_map* m, TrgbMapInfo* info);
 void* trgb_map_stream(const trgb_map* m); /* cudaStream_t */
 int  trgb_map_sync(const trgb_map* m);
 /* options: "force_warp_path" (0/1) routes every query launch through the warp-per-item kernels
- * instead of the thread-per-item fast path (both must give identical results; used by tests) */
+ * instead of the thread-per-item fast path; "use_staging" (0/1) selects the shared-memory staged
+ * sampling-window kernel (off by default: measured 14 % slower than the L1-cached per-thread loads,
+ * profiles/README.md). All variants give identical results (tests). */
 int  trgb_map_set_option(trgb_map* m, const char* key, int value);
 
 /* ---- tier 1: host-buffer batches (synchronous) ---------------------------------------- */
@@ -95,6 +98,11 @@ int trgb_range_count_launch(const trgb_map* m, const float* d_xy, int64_t n, flo
 int trgb_sample_window_launch(const trgb_map* m, const float* d_node_xy, const int32_t* d_first_draw,
                               const float* d_draw_xy, int64_t n_nodes, int window, float radius,
                               float height_thr, float ratio_thr, unsigned long long* d_mask);
+/* same, with the promise that every |draw_xy| offset is at most max_offset (> 0): lets the kernel stage
+ * each node's neighbourhood cells in shared memory once and run all its window tests from there */
+int trgb_sample_window_launch2(const trgb_map* m, const float* d_node_xy, const int32_t* d_first_draw,
+                               const float* d_draw_xy, int64_t n_nodes, int window, float max_offset, float radius,
+                               float height_thr, float ratio_thr, unsigned long long* d_mask);
 int trgb_nearest_z_launch(const trgb_map* m, const float* d_xy, int64_t n, float* d_z, int64_t* d_idx,
                           uint8_t* d_tie);
 /* p1: (x,y,z) start node; p2: (x,y) end point (its z only enters the host-side slope gate).
@@ -102,6 +110,17 @@ int trgb_nearest_z_launch(const trgb_map* m, const float* d_xy, int64_t n, float
 int trgb_edge_eval_launch(const trgb_map* m, const float* d_p1_xyz, const float* d_p2_xy, int64_t n,
                           const TrgbEdgeParams* prm, uint8_t* d_stage, float* d_weight, float* d_dist,
                           int32_t* d_npts);
+
+/* Speculation filter for the wavefront scheduler: items i < n_skip whose sqrt(d_skip_d2[i]) < skip_below
+ * are not evaluated (stage = TRGB_EDGE_SKIPPED, z = 0). d_skip_d2 is the squared distance from the
+ * sample to its nearest graph node (trgb_nodes_nearest_launch on the same stream): such a sample can
+ * only be wired to an existing node (trg.cpp:414-417), never become a new one, so neither its height
+ * nor its parent edge will be needed. */
+int trgb_edge_eval_launch_skip(const trgb_map* m, const float* d_p1_xyz, const float* d_p2_xy, int64_t n,
+                               const TrgbEdgeParams* prm, uint8_t* d_stage, float* d_weight, float* d_dist,
+                               int32_t* d_npts, const float* d_skip_d2, int64_t n_skip, float skip_below);
+int trgb_nearest_z_launch_skip(const trgb_map* m, const float* d_xy, int64_t n, float* d_z, int64_t* d_idx,
+                               uint8_t* d_tie, const float* d_skip_d2, float skip_below);
 
 /* ---- K5: device grid over graph nodes (append-only) — batched kd_nearest2 on the node tree
  *      (trg.cpp:408; kdtree.c:364-417). Indices are append order. All launches are asynchronous on

@@ -16,13 +16,14 @@ ap.add_argument("--ne", type=int, default=1_000_000)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--radius", type=float, default=0.3)
 ap.add_argument("--warp", action="store_true")
+ap.add_argument("--cell", type=float, default=0.5, help="map cell as a multiple of robot_size")
 ap.add_argument("--sorted", action="store_true", help="sort queries by cell (spatially coherent threads)")
 a = ap.parse_args()
 import torch
 P = trg.MOUNTAIN
 pts = trg.terrain.mountain(a.side, h=0.1, seed=2)
 ext = a.side * 0.1
-dm = K.DeviceMap(pts, 0.5 * P.robot_size)
+dm = K.DeviceMap(pts, a.cell * P.robot_size)
 if a.warp:
     dm.set_option("force_warp_path", 1)
 rng = np.random.default_rng(10)

@@ -81,6 +81,49 @@ def test_overlapped_build_mountain(pkg, K, small_mountain):
         assert_graph_equal(t.export(), o.export(), str(tuning))
 
 
+def test_staged_window_kernel_equals_plain(pkg, K, small_mountain):
+    """The shared-memory staged sampling-window kernel against the per-thread global-load one
+    (same bits), incl. windows that leave the map and a dense cluster that does not fit the stage."""
+    import ctypes as C
+    rng = np.random.default_rng(4)
+    cl = (rng.normal(0, 0.1, size=(3000, 2)) + np.float32([12.0, 12.0])).astype(np.float32)
+    pts = np.concatenate([small_mountain, np.column_stack([cl, rng.normal(0, 0.05, 3000)]).astype(np.float32)])
+    P = pkg.MOUNTAIN
+    L = K.lib()
+    L.trgb_sample_window_launch2.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_int, C.c_float, C.c_float, C.c_float,
+                                                                C.c_float, C.c_void_p]
+    import torch
+    n_nodes, W = 3000, 128
+    nodes = rng.uniform(-0.5, 30.5, size=(n_nodes, 2)).astype(np.float32)
+    nodes[:200] = cl[:200]
+    ang = rng.uniform(0, 2 * np.pi, 5000)
+    draws = (P.expand_dist * np.stack([np.cos(ang), np.sin(ang)], 1)).astype(np.float32)
+    first = rng.integers(0, 5000 - W, n_nodes).astype(np.int32)
+    d_nodes, d_draws, d_first = (torch.from_numpy(a).cuda() for a in (nodes, draws, first))
+    out = []
+    for use_staging in (1, 0):
+        dm = K.DeviceMap(pts, 0.5 * P.robot_size)
+        dm.set_option("use_staging", use_staging)
+        mask = torch.zeros(n_nodes * 2, dtype=torch.int64, device="cuda")
+        rc = L.trgb_sample_window_launch2(dm.h, d_nodes.data_ptr(), d_first.data_ptr(), d_draws.data_ptr(), n_nodes, W,
+                                          P.expand_dist * 1.0001, P.robot_size, P.height_threshold,
+                                          P.collision_threshold, mask.data_ptr())
+        assert rc == 0, K.lib().trgb_last_error()
+        dm.sync()
+        out.append(mask.cpu().numpy())
+    np.testing.assert_array_equal(out[0], out[1])
+    # and both equal the oracle's isCollision on the same sample positions
+    o = pkg.oracle(P)
+    o.set_global_map(pts)
+    j = np.arange(W)
+    for node in (0, 5, 250, 1234, 2999):
+        s = nodes[node] + draws[first[node] + j]
+        want = o.is_collision(s.astype(np.float32), P.collision_threshold)
+        bits = out[0].view(np.uint64)[2 * node:2 * node + 2]
+        got = np.array([(int(bits[int(k) >> 6]) >> (int(k) & 63)) & 1 for k in j], np.uint8)
+        np.testing.assert_array_equal(got, want)
+
+
 def test_seeds_differ_and_reproduce(pkg, K, small_mountain):
     P = pkg.MOUNTAIN
     t1, _ = build_pair(pkg, P, small_mountain, (15.0, 15.0, 0.0), seed=1)

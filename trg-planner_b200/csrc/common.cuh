@@ -362,6 +362,7 @@ struct trgb_map {
   cudaStream_t stream = nullptr;
   int zcap = 128;  // per-warp shared z buffer (floats) for the collision kernels
   int force_warp_path = 0;  // tests: route every launch through the warp-per-item kernels
+  int use_staging = 0;      // shared-memory staged sampling-window kernel (measured slower than the L1 path: off)
   // pinned/device staging for the host-buffer tier
   void* h_stage = nullptr;
   size_t h_stage_bytes = 0;

@@ -370,6 +370,7 @@ extern "C" void* trgb_map_stream(const trgb_map* m) { return m ? (void*)m->strea
 extern "C" int trgb_map_set_option(trgb_map* m, const char* key, int value) {
   TRGB_ARG(m && key, "null handle");
   if (std::string(key) == "force_warp_path") m->force_warp_path = value;
+  else if (std::string(key) == "use_staging") m->use_staging = value;
   else TRGB_ARG(false, "unknown option");
   return TRGB_OK;
 }

@@ -79,11 +79,20 @@ __global__ void __launch_bounds__(kThreads) k_sample_window(
 __global__ void __launch_bounds__(kThreads) k_nearest_z(MapView m, const float2* __restrict__ q,
                                                         int64_t n, float* __restrict__ z_out,
                                                         int64_t* __restrict__ idx_out,
-                                                        uint8_t* __restrict__ tie_out) {
+                                                        uint8_t* __restrict__ tie_out,
+                                                        const float* __restrict__ skip_d2, float skip_below) {
   const int lane = threadIdx.x & 31;
   const int64_t wstride = (int64_t)gridDim.x * kWarpsPerCta;
   const float extent = (float)m.W * m.cell + (float)m.H * m.cell;
   for (int64_t i = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); i < n; i += wstride) {
+    if (skip_d2 && __fsqrt_rn(__ldg(skip_d2 + i)) < skip_below) {  // speculation filter (warp-uniform)
+      if (lane == 0) {
+        if (z_out) z_out[i] = 0.f;
+        if (idx_out) idx_out[i] = -1;
+        if (tie_out) tie_out[i] = 0;
+      }
+      continue;
+    }
     const float2 p = __ldg(q + i);
     const int qcx = cell_coord(p.x, m.x0, m.inv_cell, m.W);
     const int qcy = cell_coord(p.y, m.y0, m.inv_cell, m.H);
@@ -446,6 +455,124 @@ __global__ void __launch_bounds__(kTqThreads) k_sample_window_tq(
   }
 }
 
+// Sampling windows with the node's neighbourhood staged in shared memory: one CTA per node. All
+// `window` samples of a node lie within max_offset of it, so the cells they can touch form one
+// small block of the grid (<= kStRows x kStCols cells, <= kStPts points, a few KB): its cell table
+// and its points are copied once, coalesced, into shared memory and every thread then walks its
+// query's cell runs there instead of issuing per-thread global loads. Nodes whose neighbourhood
+// does not fit (very dense spots) and threads whose query leaves the staged block use the global path.
+constexpr int kStRows = 16, kStCols = 16, kStPts = 1024;
+
+__device__ __forceinline__ int thread_is_collision_staged(const float4* __restrict__ spts, const uint32_t* __restrict__ scs,
+                                                          const uint32_t* __restrict__ srow, int cols1, int bx0, int by0,
+                                                          const MapView& m, float qx, float qy, float r, float hthr,
+                                                          float rthr, float* zcol, int stride, int cx0, int cx1, int cy0,
+                                                          int cy1) {
+  const float r2 = __fmul_rn(r, r);
+  int n = 0;
+  for (int row = cy0; row <= cy1; ++row) {
+    const int rr_ = row - by0;
+    const uint32_t base = scs[rr_ * cols1];
+    const uint32_t s = scs[rr_ * cols1 + (cx0 - bx0)] - base + srow[rr_];
+    const uint32_t e = scs[rr_ * cols1 + (cx1 - bx0) + 1] - base + srow[rr_];
+#pragma unroll 4
+    for (uint32_t i = s; i < e; ++i) {
+      const float4 p = spts[i];
+      const float dx = __fsub_rn(p.x, qx), dy = __fsub_rn(p.y, qy);
+      const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+      if (d2 <= r2) {
+        if (n < kTqCap) zcol[n * stride] = p.z;
+        ++n;
+      }
+    }
+  }
+  if (n == 0) return 1;
+  if (n > kTqCap) return 2;
+  int cnt;
+  if (__all_sync(__activemask(), n <= 32)) cnt = median_outlier_count<32>(zcol, stride, n, hthr);
+  else cnt = median_outlier_count<64>(zcol, stride, n, hthr);
+  const float ratio = __fdiv_rn((float)cnt, (float)n);
+  return ratio > rthr ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(kTqThreads) k_sample_window_sm(
+    MapView m, const float2* __restrict__ node_xy, const int32_t* __restrict__ first_draw,
+    const float2* __restrict__ draw_xy, int64_t n_nodes, int window, float max_offset, float r, float hthr, float rthr,
+    int cap, unsigned long long* __restrict__ mask) {
+  extern __shared__ float zsm[];                       // kTqThreads * kTqCap floats (z columns / fallback buffers)
+  __shared__ float4 spts[kStPts];
+  __shared__ uint32_t scs[kStRows * (kStCols + 1)];
+  __shared__ uint32_t srow[kStRows + 1];
+  __shared__ int s_ok;
+  float* zcol = zsm + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int words = (window + 63) >> 6;
+  for (int64_t node = blockIdx.x; node < n_nodes; node += gridDim.x) {
+    const float2 np = __ldg(node_xy + node);
+    // block of cells any sample of this node can touch
+    const float reach = max_offset + inflate(r, fabsf(np.x) + max_offset, fabsf(np.y) + max_offset);
+    const int bx0 = cell_coord(np.x - reach, m.x0, m.inv_cell, m.W), bx1 = cell_coord(np.x + reach, m.x0, m.inv_cell, m.W);
+    const int by0 = cell_coord(np.y - reach, m.y0, m.inv_cell, m.H), by1 = cell_coord(np.y + reach, m.y0, m.inv_cell, m.H);
+    const int rows = by1 - by0 + 1, cols1 = bx1 - bx0 + 2;
+    const bool fits = rows <= kStRows && cols1 <= kStCols + 1;
+    if (fits) {
+      for (int t = threadIdx.x; t < rows * cols1; t += kTqThreads) {
+        const int rr_ = t / cols1, cc = t - rr_ * cols1;
+        scs[rr_ * cols1 + cc] = __ldg(m.cell_start + (size_t)(by0 + rr_) * m.W + bx0 + cc);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t acc = 0;
+      if (fits) {
+        for (int rr_ = 0; rr_ < rows; ++rr_) {
+          srow[rr_] = acc;
+          acc += scs[rr_ * cols1 + cols1 - 1] - scs[rr_ * cols1];
+        }
+        srow[rows] = acc;
+      }
+      s_ok = fits && acc <= (uint32_t)kStPts;
+    }
+    __syncthreads();
+    const bool staged = s_ok != 0;
+    if (staged) {
+      const uint32_t total = srow[rows];
+      for (uint32_t i = threadIdx.x; i < total; i += kTqThreads) {
+        int rr_ = 0;
+        while (i >= srow[rr_ + 1]) ++rr_;
+        spts[i] = ld_pt(m.pts + scs[rr_ * cols1] + (i - srow[rr_]));
+      }
+    }
+    __syncthreads();
+    const int32_t fd = __ldg(first_draw + node);
+    for (int jb = 0; jb < window; jb += kTqThreads) {   // block-uniform trip count
+      const int j = jb + threadIdx.x;
+      float sx = 0.f, sy = 0.f;
+      int res = 0;
+      if (j < window) {
+        const float2 d = __ldg(draw_xy + (fd + j));
+        sx = __fadd_rn(np.x, d.x);   // trg.cpp:396-397
+        sy = __fadd_rn(np.y, d.y);
+        const float rr = inflate(r, sx, sy);
+        const int cx0 = cell_coord(sx - rr, m.x0, m.inv_cell, m.W), cx1 = cell_coord(sx + rr, m.x0, m.inv_cell, m.W);
+        const int cy0 = cell_coord(sy - rr, m.y0, m.inv_cell, m.H), cy1 = cell_coord(sy + rr, m.y0, m.inv_cell, m.H);
+        if (staged && cx0 >= bx0 && cx1 <= bx1 && cy0 >= by0 && cy1 <= by1)
+          res = thread_is_collision_staged(spts, scs, srow, cols1, bx0, by0, m, sx, sy, r, hthr, rthr, zcol, kTqThreads, cx0,
+                                           cx1, cy0, cy1);
+        else
+          res = thread_is_collision(m, sx, sy, r, hthr, rthr, zcol, kTqThreads);
+      }
+      TQ_FALLBACK_BEGIN(res)
+        const float qx = __shfl_sync(FULL, sx, src), qy = __shfl_sync(FULL, sy, src);
+        const bool c = warp_is_collision(m, qx, qy, r, hthr, rthr, wbuf, 32 * cap, nullptr);
+        if (lane == src) res = c ? 1 : 0;
+      TQ_FALLBACK_END
+      if (j < window && res) atomicOr(mask + node * words + (j >> 6), 1ull << (j & 63));
+    }
+    __syncthreads();   // spts / scs are rewritten for the next node
+  }
+}
+
 // ---- K4 fast path, two launches on one stream ------------------------------------------------
 // (a) k_edge_collide_tq: one thread per (edge, segment sample k). Sample k sits at the k-th value
 //     of the reference's accumulating float counter `for (float i = 0; i < dist; i += ds)`
@@ -456,7 +583,9 @@ __global__ void __launch_bounds__(kTqThreads) k_sample_window_tq(
 __global__ void __launch_bounds__(kTqThreads) k_edge_collide_tq(MapView m, const float* __restrict__ p1_xyz,
                                                                 const float2* __restrict__ p2_xy, int64_t n, int kmax,
                                                                 float rs, float hthr, float cthr, int cap,
-                                                                uint8_t* __restrict__ stage) {
+                                                                uint8_t* __restrict__ stage,
+                                                                const float* __restrict__ skip_d2, int64_t n_skip,
+                                                                float skip_below) {
   extern __shared__ float zsm[];
   float* zcol = zsm + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -466,8 +595,12 @@ __global__ void __launch_bounds__(kTqThreads) k_edge_collide_tq(MapView m, const
     float sx = 0.f, sy = 0.f;
     int res = 0;
     int64_t e = 0;
-    if (it < items) {
+    bool live = it < items;
+    if (live) {
       e = it / kmax;
+      if (e < n_skip && __fsqrt_rn(__ldg(skip_d2 + e)) < skip_below) live = false;  // speculation filter
+    }
+    if (live) {
       const int k = (int)(it - e * kmax);
       const float p1x = __ldg(p1_xyz + 3 * e), p1y = __ldg(p1_xyz + 3 * e + 1);
       const float2 p2 = __ldg(p2_xy + e);
@@ -498,7 +631,12 @@ constexpr int kPcaLanes = 4;
 __global__ void __launch_bounds__(256) k_edge_pca(MapView m, const float* __restrict__ p1_xyz,
                                                   const float2* __restrict__ p2_xy, int64_t n, float rs,
                                                   uint8_t* __restrict__ stage_io, float* __restrict__ w_out,
-                                                  float* __restrict__ dist_out, int32_t* __restrict__ npts_out) {
+                                                  float* __restrict__ dist_out, int32_t* __restrict__ npts_out,
+                                                  const float* __restrict__ skip_d2, int64_t n_skip,
+                                                  float skip_below) {
+  __shared__ double s_sum[9][256 / kPcaLanes];
+  __shared__ int s_cnt[3][256 / kPcaLanes];
+  __shared__ float s_dist[256 / kPcaLanes];
   const int sub = threadIdx.x & (kPcaLanes - 1);
   const int64_t gstride = (int64_t)gridDim.x * (256 / kPcaLanes);
   for (int64_t base = (int64_t)blockIdx.x * (256 / kPcaLanes); base < n; base += gstride) {
@@ -511,12 +649,13 @@ __global__ void __launch_bounds__(256) k_edge_pca(MapView m, const float* __rest
       const float2 p2 = __ldg(p2_xy + i);
       p2x = p2.x; p2y = p2.y;
       st = stage_io[i];
+      if (i < n_skip && __fsqrt_rn(__ldg(skip_d2 + i)) < skip_below) st = TRGB_EDGE_SKIPPED;
     }
     const EdgeGeom g = edge_geom(p1x, p1y, p2x, p2y);
     const float dist = g.dist, dirx = g.dirx, diry = g.diry;
     int nrange = 0, npts = 0;
     double sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
-    if (live && st != TRGB_EDGE_COLLISION) {
+    if (live && st != TRGB_EDGE_COLLISION && st != TRGB_EDGE_SKIPPED) {
       // :291-297 ellipse with foci at the two nodes (circle when the nodes are close)
       const float c = 0.5f * dist;
       const float b = rs;
@@ -561,22 +700,41 @@ __global__ void __launch_bounds__(256) k_edge_pca(MapView m, const float* __rest
       sxx += __shfl_xor_sync(FULL, sxx, d); sxy += __shfl_xor_sync(FULL, sxy, d); sxz += __shfl_xor_sync(FULL, sxz, d);
       syy += __shfl_xor_sync(FULL, syy, d); syz += __shfl_xor_sync(FULL, syz, d); szz += __shfl_xor_sync(FULL, szz, d);
     }
-    if (live && sub == 0) {
-      float weight = 0.f;
-      if (st == TRGB_EDGE_COLLISION) {
-        npts = 0;
-      } else if (nrange == 0) {
-        st = TRGB_EDGE_EMPTY;   // :305
-      } else if (npts < 3) {
-        st = TRGB_EDGE_FEWPTS;  // :327
-      } else {
-        weight = weight_from_sums(npts, sx, sy, sz, sxx, sxy, sxz, syy, syz, szz);
-      }
-      stage_io[i] = (uint8_t)st;
-      w_out[i] = weight;
-      dist_out[i] = dist;
-      if (npts_out) npts_out[i] = npts;
+    // phase 2: the block's 64 edges are finished by its first 64 threads, one edge per thread, so the
+    // Jacobi SVD runs in two full warps instead of one lane in four of all eight
+    const int le = threadIdx.x / kPcaLanes;
+    if (sub == 0) {
+      s_sum[0][le] = sx; s_sum[1][le] = sy; s_sum[2][le] = sz; s_sum[3][le] = sxx; s_sum[4][le] = sxy;
+      s_sum[5][le] = sxz; s_sum[6][le] = syy; s_sum[7][le] = syz; s_sum[8][le] = szz;
+      s_cnt[0][le] = npts; s_cnt[1][le] = nrange; s_cnt[2][le] = live ? st : -1;
+      s_dist[le] = dist;
     }
+    __syncthreads();
+    if (threadIdx.x < 256 / kPcaLanes) {
+      const int t = threadIdx.x;
+      const int64_t ei = base + t;
+      int st2 = s_cnt[2][t];
+      if (ei < n && st2 >= 0) {
+        int np2 = s_cnt[0][t];
+        const int nr2 = s_cnt[1][t];
+        float weight = 0.f;
+        if (st2 == TRGB_EDGE_COLLISION || st2 == TRGB_EDGE_SKIPPED) {
+          np2 = 0;
+        } else if (nr2 == 0) {
+          st2 = TRGB_EDGE_EMPTY;   // :305
+        } else if (np2 < 3) {
+          st2 = TRGB_EDGE_FEWPTS;  // :327
+        } else {
+          weight = weight_from_sums(np2, s_sum[0][t], s_sum[1][t], s_sum[2][t], s_sum[3][t], s_sum[4][t], s_sum[5][t],
+                                    s_sum[6][t], s_sum[7][t], s_sum[8][t]);
+        }
+        stage_io[ei] = (uint8_t)st2;
+        w_out[ei] = weight;
+        dist_out[ei] = s_dist[t];
+        if (npts_out) npts_out[ei] = np2;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -670,11 +828,33 @@ extern "C" int trgb_sample_window_launch(const trgb_map* m, const float* d_node_
                                          const int32_t* d_first_draw, const float* d_draw_xy,
                                          int64_t n_nodes, int window, float radius, float height_thr,
                                          float ratio_thr, unsigned long long* d_mask) {
+  return trgb_sample_window_launch2(m, d_node_xy, d_first_draw, d_draw_xy, n_nodes, window, 0.f, radius, height_thr,
+                                    ratio_thr, d_mask);
+}
+
+extern "C" int trgb_sample_window_launch2(const trgb_map* m, const float* d_node_xy,
+                                          const int32_t* d_first_draw, const float* d_draw_xy,
+                                          int64_t n_nodes, int window, float max_offset, float radius, float height_thr,
+                                          float ratio_thr, unsigned long long* d_mask) {
   TRGB_ARG(m && d_node_xy && d_first_draw && d_draw_xy && d_mask, "null pointer");
   TRGB_ARG(window >= 1 && window <= 256, "window must be in [1,256]");
   TRGB_ARG(radius > 0.f, "radius must be > 0");
   if (n_nodes <= 0) return TRGB_OK;
   int grid, cap; size_t smem;
+  if (max_offset > 0.f && m->use_staging &&
+      tq_cfg(m, radius, n_nodes * kTqThreads, &grid, &cap, &smem, (const void*)k_sample_window_sm)) {
+    // staged variant: one CTA per node (grid-stride), neighbourhood in shared memory
+    // (static 17.5 KB + dynamic 32 KB exceeds the 48 KB default: opt in explicitly)
+    TRGB_CUDA(cudaFuncSetAttribute((const void*)k_sample_window_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int per_sm = 4;
+    const int g2 = (int)std::max<int64_t>(1, std::min<int64_t>(n_nodes, (int64_t)sm_count() * per_sm));
+    ProfScope ps("k_sample_window", m->stream, (double)n_nodes * window);
+    k_sample_window_sm<<<g2, kTqThreads, smem, m->stream>>>(
+        m->view, reinterpret_cast<const float2*>(d_node_xy), d_first_draw,
+        reinterpret_cast<const float2*>(d_draw_xy), n_nodes, window, max_offset, radius, height_thr, ratio_thr, cap, d_mask);
+    TRGB_CUDA(cudaGetLastError());
+    return TRGB_OK;
+  }
   if (tq_cfg(m, radius, n_nodes * window, &grid, &cap, &smem, (const void*)k_sample_window_tq)) {
     ProfScope ps("k_sample_window", m->stream, (double)n_nodes * window);
     k_sample_window_tq<<<grid, kTqThreads, smem, m->stream>>>(
@@ -693,20 +873,33 @@ extern "C" int trgb_sample_window_launch(const trgb_map* m, const float* d_node_
   return TRGB_OK;
 }
 
-extern "C" int trgb_nearest_z_launch(const trgb_map* m, const float* d_xy, int64_t n, float* d_z,
-                                     int64_t* d_idx, uint8_t* d_tie) {
+extern "C" int trgb_nearest_z_launch_skip(const trgb_map* m, const float* d_xy, int64_t n, float* d_z,
+                                          int64_t* d_idx, uint8_t* d_tie, const float* d_skip_d2, float skip_below) {
   TRGB_ARG(m && d_xy, "null pointer");
   if (n <= 0) return TRGB_OK;
   ProfScope ps("k_nearest_z", m->stream, (double)n);
   k_nearest_z<<<grid_for_warps(n, 8), kThreads, 0, m->stream>>>(m->view, reinterpret_cast<const float2*>(d_xy), n,
-                                                                 d_z, d_idx, d_tie);
+                                                                 d_z, d_idx, d_tie, d_skip_d2, skip_below);
   TRGB_CUDA(cudaGetLastError());
   return TRGB_OK;
+}
+
+extern "C" int trgb_nearest_z_launch(const trgb_map* m, const float* d_xy, int64_t n, float* d_z,
+                                     int64_t* d_idx, uint8_t* d_tie) {
+  return trgb_nearest_z_launch_skip(m, d_xy, n, d_z, d_idx, d_tie, nullptr, 0.f);
 }
 
 extern "C" int trgb_edge_eval_launch(const trgb_map* m, const float* d_p1_xyz, const float* d_p2_xy,
                                      int64_t n, const TrgbEdgeParams* prm, uint8_t* d_stage,
                                      float* d_weight, float* d_dist, int32_t* d_npts) {
+  return trgb_edge_eval_launch_skip(m, d_p1_xyz, d_p2_xy, n, prm, d_stage, d_weight, d_dist, d_npts, nullptr, 0, 0.f);
+}
+
+extern "C" int trgb_edge_eval_launch_skip(const trgb_map* m, const float* d_p1_xyz, const float* d_p2_xy,
+                                          int64_t n, const TrgbEdgeParams* prm, uint8_t* d_stage,
+                                          float* d_weight, float* d_dist, int32_t* d_npts,
+                                          const float* d_skip_d2, int64_t n_skip, float skip_below) {
+  if (!d_skip_d2) n_skip = 0;
   TRGB_ARG(m && d_p1_xyz && d_p2_xy && prm && d_stage && d_weight && d_dist, "null pointer");
   TRGB_ARG(prm->robot_size > 0.f, "robot_size must be > 0");
   if (n <= 0) return TRGB_OK;
@@ -720,14 +913,16 @@ extern "C" int trgb_edge_eval_launch(const trgb_map* m, const float* d_p1_xyz, c
       ProfScope ps("k_edge_collide", m->stream, (double)n);
       k_edge_collide_tq<<<grid, kTqThreads, smem, m->stream>>>(m->view, d_p1_xyz, reinterpret_cast<const float2*>(d_p2_xy),
                                                                n, kmax, prm->robot_size, prm->height_threshold,
-                                                               prm->collision_threshold, cap, d_stage);
+                                                               prm->collision_threshold, cap, d_stage, d_skip_d2, n_skip,
+                                                               skip_below);
     }
     {
       ProfScope ps("k_edge_pca", m->stream, (double)n);
       const int64_t need = (n + (256 / kPcaLanes) - 1) / (256 / kPcaLanes);
       const int g2 = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)sm_count() * 8));
       k_edge_pca<<<g2, 256, 0, m->stream>>>(m->view, d_p1_xyz, reinterpret_cast<const float2*>(d_p2_xy), n,
-                                            prm->robot_size, d_stage, d_weight, d_dist, d_npts);
+                                            prm->robot_size, d_stage, d_weight, d_dist, d_npts, d_skip_d2, n_skip,
+                                            skip_below);
     }
     TRGB_CUDA(cudaGetLastError());
     return TRGB_OK;

@@ -872,9 +872,10 @@ class Expander {
       }
       in.h2d(st_);
       out.zero_d(o_mk, n_live * words * sizeof(unsigned long long), st_);
-      K(trgb_sample_window_launch(map_, in.d<float>(o_xy), in.d<int32_t>(o_fd), db.dev(), (int64_t)n_live, W,
-                                  P_.robot_size, P_.height_threshold, P_.collision_threshold,
-                                  out.d<unsigned long long>(o_mk)),
+      // every draw offset is (e*cosf, e*sinf): each component is at most e in magnitude (+ rounding)
+      K(trgb_sample_window_launch2(map_, in.d<float>(o_xy), in.d<int32_t>(o_fd), db.dev(), (int64_t)n_live, W,
+                                   P_.expand_dist * 1.0001f, P_.robot_size, P_.height_threshold, P_.collision_threshold,
+                                   out.d<unsigned long long>(o_mk)),
         "trgb_sample_window_launch");
       out.d2h(st_);
       cuda_check(cudaStreamSynchronize(st_), "sync(windows)");
@@ -977,13 +978,19 @@ class Expander {
       K(trgb_nodes_nearest_launch(dv.nodes, in.d<float>(o_p2), (int64_t)ns, out.d<int32_t>(o_ni), out.d<float>(o_nd),
                                   out.d<uint8_t>(o_nt), st_),
         "trgb_nodes_nearest_launch");
-      K(trgb_nearest_z_launch(map_, in.d<float>(o_p2), (int64_t)ns, out.d<float>(o_z), nullptr, out.d<uint8_t>(o_t)),
+      // speculation filter: a sample whose nearest node (already on the device) is closer than
+      // robot_size can only be wired to an existing node (trg.cpp:414-417) — no height, no parent edge
+      K(trgb_nearest_z_launch_skip(map_, in.d<float>(o_p2), (int64_t)ns, out.d<float>(o_z), nullptr, out.d<uint8_t>(o_t),
+                                   out.d<float>(o_nd), P_.robot_size),
         "trgb_nearest_z_launch");
     }
     if (ne) {
-      TrgbEdgeParams prm{P_.robot_size, P_.height_threshold, P_.collision_threshold, 0};
-      K(trgb_edge_eval_launch(map_, in.d<float>(o_p1), in.d<float>(o_p2), (int64_t)ne, &prm, out.d<uint8_t>(o_s),
-                              out.d<float>(o_w), out.d<float>(o_d), nullptr),
+      // threads per edge in the segment-collision kernel: deferred edges reach expand_dist + robot_size
+      const int kmax = (int)std::ceil((P_.expand_dist + P_.robot_size) / (0.5f * P_.robot_size));
+      TrgbEdgeParams prm{P_.robot_size, P_.height_threshold, P_.collision_threshold, std::max(2, std::min(kmax, 16))};
+      K(trgb_edge_eval_launch_skip(map_, in.d<float>(o_p1), in.d<float>(o_p2), (int64_t)ne, &prm, out.d<uint8_t>(o_s),
+                                   out.d<float>(o_w), out.d<float>(o_d), nullptr, ns ? out.d<float>(o_nd) : nullptr,
+                                   (int64_t)ns, P_.robot_size),
         "trgb_edge_eval_launch");
     }
     out.d2h(st_);
@@ -1154,6 +1161,7 @@ class Expander {
         continue;
       }
       // 2. new node (addNode never fails for id != 0)
+      if (b.stage[si] == TRGB_EDGE_SKIPPED) throw std::logic_error("trg_b200: speculation filter skipped a sample that became a node");
       if (b.tie[si]) ++n_zties_;
       Eigen::Vector2f pos2(s.x, s.y);
       TRG::Node* nn = t_.newNode(g_.node_id, pos2, b.z[si], new_state);
