@@ -1,0 +1,89 @@
+"""BASELINE configs #3 and #4 on ONE GPU.
+  #3: 50 M-point mountain map, full TRG build + 10 k start/goal queries (single GPU; the tile-sharded
+      multi-GPU form is bench.py under torchrun).
+  #4: incremental update: 200 k-point scans along a trajectory against a 20 M-point prebuilt map,
+      per-scan latency of setLocalMap + updateGraph (trg.cpp:195-231, 456-489).
+"""
+import argparse, json, sys, time
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import numpy as np
+import _pkg
+trg = _pkg.load()
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--which", default="3,4")
+ap.add_argument("--side3", type=int, default=7072)
+ap.add_argument("--side4", type=int, default=4473)
+ap.add_argument("--queries", type=int, default=10000)
+ap.add_argument("--scans", type=int, default=30)
+ap.add_argument("--overlap", type=int, default=1)
+ap.add_argument("--chunk", type=int, default=0)
+ap.add_argument("--lookahead", type=int, default=0)
+ap.add_argument("--reps3", type=int, default=1)
+a = ap.parse_args()
+P = trg.MOUNTAIN
+out = {}
+if "3" in a.which.split(","):
+    t0 = time.time()
+    pts = trg.terrain.mountain(a.side3, h=0.1, seed=3)
+    print(f"C3: generated {pts.shape[0]} points in {time.time()-t0:.0f}s", flush=True)
+    ext = a.side3 * 0.1
+    from trg_planner_b200 import kernels as K
+    t = trg.product(P); t.seed(42); t.set_tuning("overlap", a.overlap)
+    if a.chunk: t.set_tuning("chunk_nodes", a.chunk)
+    if a.lookahead: t.set_tuning("lookahead", a.lookahead)
+    w0 = time.time(); t.set_global_map(pts); w1 = time.time()
+    K.prof_reset(); K.prof_enable(True)
+    t.init_graph((ext / 2, ext / 2, 0.0)); w2 = time.time()
+    pr = K.prof_collect(); K.prof_enable(False)
+    for k, v in sorted(pr.items(), key=lambda kv: -kv[1]["ms"])[:8]:
+        print(f"   {k:18s} launches={v['launches']:6d} ms={v['ms']:10.3f} avg_us={1e3*v['ms']/max(1,v['launches']):9.2f}", flush=True)
+    nn, ne = t.counts()
+    q = trg.terrain.query_pairs(trg.terrain.bbox(pts), a.queries, seed=8)
+    r = t.plan_batch(q, max_total_nodes=a.queries * 4096); w3 = time.time()
+    out["C3"] = dict(points=int(pts.shape[0]), nodes=nn, edges=ne, map_s=round(w1 - w0, 3), init_s=round(w2 - w1, 3),
+                     points_per_s=round(pts.shape[0] / (w2 - w0)), nodes_per_s=round(nn / (w2 - w0)),
+                     queries=a.queries, found=int(r["found"].sum()), query_s=round(w3 - w2, 3),
+                     paths_per_s=round(a.queries / (w3 - w2)), snap_s=round(t.seconds("plan_snap"), 3),
+                     mean_path_nodes=round(float(np.diff(r["offsets"]).mean()), 1),
+                     host={k: t.stat(k) for k in ("us_commit", "us_clean", "us_wait", "us_sample", "us_eval", "pops", "batches", "node_ties", "cyc_nearest", "cyc_wire", "cyc_newnode", "cyc_nn_a", "cyc_nn_b", "cyc_nn_c", "window_launches", "eval_launches")})
+    print(json.dumps(out["C3"]), flush=True)
+    t.close(); del pts
+if "4" in a.which.split(","):
+    pts = trg.terrain.mountain(a.side4, h=0.1, seed=4)
+    ext = a.side4 * 0.1
+    t = trg.product(P); t.seed(42)
+    t.set_global_map(pts)
+    # build only around the trajectory start: the prebuilt graph covers the whole map in the reference's use;
+    # here the full build is done once (untimed) and the scans then update it
+    w0 = time.time(); t.init_graph((ext / 2, ext / 2, 0.0)); w1 = time.time()
+    nn, ne = t.counts()
+    print(f"C4: prebuilt map {pts.shape[0]} points, graph {nn} nodes built in {w1-w0:.2f}s", flush=True)
+    rng = np.random.default_rng(9)
+    lat, sizes, nodes_after = [], [], []
+    half = 11.2
+    # spatial buckets for fast window extraction
+    order = np.argsort(pts[:, 0], kind="stable"); xs = pts[order, 0]
+    for k in range(a.scans):
+        cx, cy = ext / 2 - 50.0 + 2.0 * k, ext / 2
+        lo, hi = np.searchsorted(xs, cx - half), np.searchsorted(xs, cx + half)
+        cand = pts[order[lo:hi]]
+        scan = cand[np.abs(cand[:, 1] - cy) < half].copy()
+        scan[:, 2] += rng.normal(0, 0.01, scan.shape[0]).astype(np.float32)
+        sizes.append(int(scan.shape[0]))
+        s0 = time.perf_counter()
+        t.set_local_map(cx, cy, scan)
+        s1 = time.perf_counter()
+        t.update_graph()
+        s2 = time.perf_counter()
+        lat.append((s1 - s0, s2 - s1))
+        nodes_after.append(t.counts()[0])
+    L = np.array(lat) * 1e3
+    out["C4"] = dict(map_points=int(pts.shape[0]), graph_nodes=nn, scans=a.scans, scan_points_mean=int(np.mean(sizes)),
+                     set_local_map_ms=dict(mean=round(float(L[1:, 0].mean()), 2), p50=round(float(np.median(L[1:, 0])), 2), max=round(float(L[1:, 0].max()), 2)),
+                     update_graph_ms=dict(mean=round(float(L[1:, 1].mean()), 2), p50=round(float(np.median(L[1:, 1])), 2), max=round(float(L[1:, 1].max()), 2)),
+                     per_scan_ms_mean=round(float(L[1:].sum(1).mean()), 2), first_scan_ms=round(float(L[0].sum()), 2),
+                     nodes_after_last=nodes_after[-1])
+    print(json.dumps(out["C4"]), flush=True)
+json.dump(out, open("gpurun_out/config34.json", "w"), indent=1)

@@ -104,13 +104,18 @@ using namespace trgb;
 
 extern "C" void trgb_nodes_destroy(trgb_nodes* g) {
   if (!g) return;
-  cudaFree(g->d_head); cudaFree(g->d_xy); cudaFree(g->d_next);
+  cudaDeviceSynchronize();  // destruction is rare; work on any stream may still read the arrays
+  cudaFree(g->d_head);
+  if (g->d_xy) cudaFreeAsync(g->d_xy, 0);
+  if (g->d_next) cudaFreeAsync(g->d_next, 0);
+  cudaStreamSynchronize(0);
   delete g;
 }
 
 extern "C" int trgb_nodes_create(trgb_nodes** out, float x0, float y0, float x1, float y1, float cell) {
   TRGB_ARG(out, "out is null");
   TRGB_ARG(cell > 0.f && x1 > x0 && y1 > y0, "bad node grid extent");
+  trgb::tune_mempool_once();
   trgb_nodes* g = new trgb_nodes();
   g->cell = cell;
   g->inv = 1.0f / cell;
@@ -141,18 +146,19 @@ extern "C" int trgb_nodes_append_launch(trgb_nodes* g, const float* d_xy, int64_
   if (n <= 0) return TRGB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (g->count + n > g->cap) {
-    int64_t want = g->cap ? g->cap : (1 << 16);
+    int64_t want = g->cap ? g->cap : (1 << 20);
     while (want < g->count + n) want *= 2;
+    // stream-ordered pool (see tune_mempool_once): growth never stalls on cudaMalloc / cudaFree
     float2* nxy = nullptr;
     int32_t* nnext = nullptr;
-    TRGB_CUDA(cudaMalloc((void**)&nxy, (size_t)want * sizeof(float2)));
-    TRGB_CUDA(cudaMalloc((void**)&nnext, (size_t)want * sizeof(int32_t)));
+    TRGB_CUDA(cudaMallocAsync((void**)&nxy, (size_t)want * sizeof(float2), st));
+    TRGB_CUDA(cudaMallocAsync((void**)&nnext, (size_t)want * sizeof(int32_t), st));
     if (g->count) {
       TRGB_CUDA(cudaMemcpyAsync(nxy, g->d_xy, (size_t)g->count * sizeof(float2), cudaMemcpyDeviceToDevice, st));
       TRGB_CUDA(cudaMemcpyAsync(nnext, g->d_next, (size_t)g->count * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     }
-    TRGB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(g->d_xy); cudaFree(g->d_next);
+    if (g->d_xy) cudaFreeAsync(g->d_xy, st);
+    if (g->d_next) cudaFreeAsync(g->d_next, st);
     g->d_xy = nxy; g->d_next = nnext; g->cap = want;
   }
   {

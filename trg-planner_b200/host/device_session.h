@@ -71,7 +71,7 @@ class Arena {
 // sampling-window kernel.
 class DrawBuffer {
  public:
-  ~DrawBuffer() { if (d_) cudaFree(d_); }
+  ~DrawBuffer() { if (d_) { cudaDeviceSynchronize(); cudaFreeAsync(d_, 0); cudaStreamSynchronize(0); } }
   void clear() { count_ = 0; base_ = 0; }
   size_t base() const { return base_; }
   size_t end() const { return base_ + count_; }
@@ -82,11 +82,12 @@ class DrawBuffer {
     if (count_ + n > cap_) {
       size_t want = cap_ ? cap_ : (size_t)1 << 21;
       while (want < count_ + n) want *= 2;
+      // stream-ordered pool: growing a 100+ MB buffer must not stall on cudaMalloc / cudaFree
       float* nd = nullptr;
-      cuda_check(cudaMalloc(reinterpret_cast<void**>(&nd), want * 2 * sizeof(float)), "cudaMalloc(draws)");
+      cuda_check(cudaMallocAsync(reinterpret_cast<void**>(&nd), want * 2 * sizeof(float), s), "cudaMallocAsync(draws)");
       if (count_) cuda_check(cudaMemcpyAsync(nd, d_, count_ * 2 * sizeof(float), cudaMemcpyDeviceToDevice, s), "D2D(draws)");
+      if (d_) cudaFreeAsync(d_, s);
       cuda_check(cudaStreamSynchronize(s), "sync(draws)");
-      if (d_) cudaFree(d_);
       d_ = nd;
       cap_ = want;
     }

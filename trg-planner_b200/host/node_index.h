@@ -236,6 +236,57 @@ class OrderTree2D {
   mutable std::vector<Frame> frames_;
 };
 
+// Which of several points at the IDENTICAL float distance from (qx, qy) kd_nearest returns, without
+// materialising the insertion-order tree. kd_nearest_i (kdtree.c:303-362) visits, at every tree
+// node, the subtree on the query's side, then the node, then the other subtree, and replaces its
+// result only on a strictly smaller distance — so the first tied point visited wins, and the root
+// (the initial result) always wins. The root path of a point is recovered by one pass over the
+// earlier insertions: the first inserted point that falls into a subtree's region is its root.
+// x, y: coordinates in insertion order (at least up to the largest candidate); cand: ascending
+// insertion indices of the tied points. Returns the winning index.
+inline int first_visited_of(const float* x, const float* y, const std::vector<int>& cand, float qx, float qy) {
+  if (cand.size() == 1 || cand[0] == 0) return cand[0];
+  struct Step { int node; bool low; };  // ancestor and the side taken below it
+  auto root_path = [&](int target) {
+    std::vector<Step> path;
+    float lo[2] = {-std::numeric_limits<float>::infinity(), -std::numeric_limits<float>::infinity()};
+    float hi[2] = {std::numeric_limits<float>::infinity(), std::numeric_limits<float>::infinity()};
+    const float t[2] = {x[target], y[target]};
+    int axis = 0;
+    for (int i = 0; i < target; ++i) {
+      const float p[2] = {x[i], y[i]};
+      // region of the current subtree: low side is `< split`, high side is `>= split` (kdtree.c:190-193)
+      if (!(p[0] >= lo[0] && p[0] < hi[0] && p[1] >= lo[1] && p[1] < hi[1])) continue;
+      const bool low = t[axis] < p[axis];
+      path.push_back({i, low});
+      if (low) hi[axis] = p[axis]; else lo[axis] = p[axis];
+      axis ^= 1;
+    }
+    return path;
+  };
+  std::vector<std::vector<Step>> paths;
+  for (int c : cand) paths.push_back(root_path(c));
+  const float q[2] = {qx, qy};
+  auto near_low = [&](int node, int depth) { const int ax = depth & 1; return (q[ax] - (ax ? y[node] : x[node])) <= 0.f; };
+  // true when candidate a is visited before candidate b
+  auto before = [&](size_t a, size_t b) {
+    const auto& pa = paths[a];
+    const auto& pb = paths[b];
+    size_t j = 0;
+    while (j < pa.size() && j < pb.size() && pa[j].node == pb[j].node && pa[j].low == pb[j].low) ++j;
+    if (j == pa.size())  // a is an ancestor of b: b comes first iff it sits in a's near subtree
+      return !(pb[j].low == near_low(cand[a], static_cast<int>(j)));
+    if (j == pb.size())  // b is an ancestor of a
+      return pa[j].low == near_low(cand[b], static_cast<int>(j));
+    // they part below the common ancestor pa[j].node (same node in both paths, different sides)
+    return pa[j].low == near_low(pa[j].node, static_cast<int>(j));
+  };
+  size_t best = 0;
+  for (size_t k = 1; k < cand.size(); ++k)
+    if (before(k, best)) best = k;
+  return cand[best];
+}
+
 // Uniform grid over node positions. One 64-byte, cache-line-aligned bucket per cell holding up to
 // 5 entries inline (x, y, entry id): a nearest query touches 9 independent cache lines instead of
 // chasing linked lists. TRG nodes are pairwise >= robot_size apart (a node is only created when its

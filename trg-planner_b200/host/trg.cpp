@@ -315,8 +315,11 @@ void TRG::ensureGridBuilt(trgStruct& g) {
 
 void TRG::ensureTree(trgStruct& g) {
   const size_t n = g.node_seq.size();
-  if (g.tree_built == 0 && n >= 256) {
-    // first use on an existing node set (after cleanGraph / load): bulk build, identical shape
+  const size_t pending = n - g.tree_built;
+  // Catching up by single insertions costs one cache-missing descent per node; past a few tens of
+  // thousands of pending nodes (exact-distance ties during a big build are ~1e-7 per query, so the
+  // tree is usually far behind when it is needed) a parallel bulk rebuild of the identical tree wins.
+  if (n >= 256 && (g.tree_built == 0 || pending > 20000)) {
     std::vector<float> xs(n), ys(n);
     for (size_t i = 0; i < n; ++i) { xs[i] = g.node_seq[i]->pos_.x(); ys[i] = g.node_seq[i]->pos_.y(); }
     g.node_tree.build_bulk(xs.data(), ys.data(), (int)n);
@@ -335,9 +338,28 @@ TRG::Node* TRG::nearestNode(trgStruct& g, float x, float y) {
   ensureGridBuilt(g);
   auto nn = g.node_grid.nearest(x, y);
   if (nn.entry >= 0 && !nn.tie) return g.node_seq[nn.entry];
-  ensureTree(g);
   ++n_node_ties_;
-  return g.node_seq[g.node_tree.nearest(x, y)];
+  if (g.tree_built == g.node_seq.size()) return g.node_seq[g.node_tree.nearest(x, y)];  // tree is current: ask it
+  return resolveNearestTie(g, x, y, nn.d2);
+}
+
+// Which of several nodes at the IDENTICAL float distance kd_nearest returns, without materialising
+// the insertion-order tree (during a big build it is far behind and a tie shows up ~1e-7 per query).
+// kd_nearest_i (kdtree.c:303-362) visits, at every tree node, the subtree on the query's side, then
+// the node, then the other subtree, and replaces its result only on a strictly smaller distance —
+// so the first tied node visited wins, and the root (the initial result, :393-395) always wins.
+// The root path of a node is recovered by one pass over the earlier insertions: the first inserted
+// point that falls into a subtree's region is that subtree's root.
+TRG::Node* TRG::resolveNearestTie(trgStruct& g, float qx, float qy, float d2min) {
+  std::vector<int> cand;
+  g.node_grid.for_each_within_d2(qx, qy, d2min, sqrtf(d2min) * 1.001f + 1e-4f, [&](int e) { cand.push_back(e); });
+  std::sort(cand.begin(), cand.end());
+  if (cand.empty()) return g.node_seq[g.node_grid.nearest(qx, qy).entry];
+  if (cand.size() == 1 || cand[0] == 0) return g.node_seq[cand[0]];
+  const int last = cand.back();
+  std::vector<float> xs((size_t)last + 1), ys((size_t)last + 1);
+  for (int i = 0; i <= last; ++i) { xs[i] = g.node_seq[i]->pos_.x(); ys[i] = g.node_seq[i]->pos_.y(); }
+  return g.node_seq[trg_b200::first_visited_of(xs.data(), ys.data(), cand, qx, qy)];
 }
 
 // kd_nearest_range2 on node_tree in the reference's result-iteration order
@@ -489,7 +511,7 @@ class ChunkTable {
   void configure(float x0, float y0, float cell) { x0_ = x0; y0_ = y0; cell_ = cell; inv_ = 1.0f / cell; }
   bool empty() const { return ent_.empty(); }
   void clear() {
-    for (uint32_t h : touched_) head_[h] = -1;
+    for (uint32_t h : touched_) { head_[h] = -1; occ_[h >> 6] = 0; }
     touched_.clear();
     ent_.clear();
   }
@@ -506,6 +528,7 @@ class ChunkTable {
     const int cx = cc(x, x0_), cy = cc(y, y0_);
     const uint32_t h = hash(cx, cy);
     if (head_[h] < 0) touched_.push_back(h);
+    occ_[h >> 6] |= 1ull << (h & 63);
     ent_.push_back({x, y, seq, head_[h], cx, cy});
     head_[h] = static_cast<int32_t>(ent_.size()) - 1;
   }
@@ -552,11 +575,14 @@ class ChunkTable {
     else if (v == d2 && e.seq != seq) tie = true;
   }
   void scan(int cx, int cy, float qx, float qy, float& d2, int& seq, bool& tie) const {
-    for (int32_t i = head_[hash(cx, cy)]; i >= 0; i = ent_[i].next)
+    const uint32_t h = hash(cx, cy);
+    if (!((occ_[h >> 6] >> (h & 63)) & 1ull)) return;  // 2 KB bitmap: almost every probe ends here
+    for (int32_t i = head_[h]; i >= 0; i = ent_[i].next)
       if (ent_[i].cx == cx && ent_[i].cy == cy) consider(ent_[i], qx, qy, d2, seq, tie);
   }
   float x0_ = 0.f, y0_ = 0.f, cell_ = 1.f, inv_ = 1.f;
   std::vector<int32_t> head_ = std::vector<int32_t>(kMask + 1, -1);
+  std::vector<uint64_t> occ_ = std::vector<uint64_t>((kMask + 1) / 64, 0);
   std::vector<uint32_t> touched_;
   std::vector<E> ent_;
 };
@@ -656,7 +682,9 @@ class Expander {
       d.nodes_uploaded = 0;
     }
     handed_nodes_ = d.nodes_uploaded;
-    table_.configure(box[0], box[1], cell);
+    // samples sit expand_dist from their node, so their nearest node is never farther than that: with
+    // cells this wide the first 3x3 pass of ChunkTable::refine always settles the search
+    table_.configure(box[0], box[1], std::max(cell, 1.5f * P_.expand_dist));
   }
 
   // expandGraph(root) for every root, in order (trg.cpp:372-454 / :483-487).
@@ -689,7 +717,7 @@ class Expander {
       Batch& nb = B_[cur ^ 1];
       std::future<void> fut;
       bool launched = false;
-      if (overlap && bfs_.size() - sent_ >= std::min<size_t>(256, C)) {
+      if (overlap && bfs_.size() - sent_ >= std::min<size_t>((size_t)std::max(1, t_.tuning_.lookahead), C)) {
         launched = prepare(nb, roots, root_i, cur_ref, C, b.chain_end);
         if (launched)
           fut = std::async(std::launch::async, [this, &nb] {
@@ -730,6 +758,9 @@ class Expander {
     t_.stat_["cyc_nearest"] += (int64_t)ft_nearest;
     t_.stat_["cyc_wire"] += (int64_t)ft_wire;
     t_.stat_["cyc_newnode"] += (int64_t)ft_newnode;
+    t_.stat_["cyc_nn_a"] += (int64_t)ft_nn_a;
+    t_.stat_["cyc_nn_b"] += (int64_t)ft_nn_b;
+    t_.stat_["cyc_nn_c"] += (int64_t)ft_nn_c;
 #endif
   }
 
@@ -1150,10 +1181,12 @@ class Expander {
         int seq = b.nn_idx[si];
         bool tie = b.nn_tie[si] != 0;
         if (seq < 0) d2 = std::numeric_limits<float>::infinity();
+        FT_LAP(nn_a);
         table_.refine(s.x, s.y, d2, seq, tie);
+        FT_LAP(nn_b);
         ex = (tie || seq < 0) ? t_.nearestNode(g_, s.x, s.y) : g_.node_seq[seq];
+        FT_LAP(nn_c);
       }
-      FT_LAP(nearest);
       if (ex->state_ == TRG::NodeState::Invalid) continue;
       if (norm2(ex->pos_.x() - s.x, ex->pos_.y() - s.y) < P_.robot_size) {
         push_op_({node, ex, 0.f, 0.f, 0});  // wireEdge(node, existing_node)
@@ -1198,7 +1231,7 @@ class Expander {
       FT_LAP(newnode);
     }
   }
-  FT_DECL(nearest); FT_DECL(wire); FT_DECL(newnode);
+  FT_DECL(nearest); FT_DECL(wire); FT_DECL(newnode); FT_DECL(nn_a); FT_DECL(nn_b); FT_DECL(nn_c);
 
   ChunkTable table_;
   TRG& t_;

@@ -228,6 +228,7 @@ class TRG {
   void ensureGridBuilt(trgStruct& g);
   void ensureTree(trgStruct& g);
   Node* nearestNode(trgStruct& g, float x, float y);
+  Node* resolveNearestTie(trgStruct& g, float qx, float qy, float d2min);
   void rangeNodesOrdered(trgStruct& g, float x, float y, float r, std::vector<Node*>& out);
   int  countNodesInRange(trgStruct& g, float x, float y, float r);
   void buildMapIndex(trgStruct& g, const float* xyz, int64_t n, int stride, bool device);
@@ -253,8 +254,9 @@ class TRG {
  public:
   // [+] tuning knobs of the wavefront scheduler (defaults are fine; exposed for benchmarks)
   struct Tuning {
-    int chunk_nodes = 2048;   // pops evaluated per batch
+    int chunk_nodes = 4096;   // pops evaluated per batch
     int window = 128;         // sampling-window draws per node (<= 256)
+    int lookahead = 1024;     // queued pops needed before the next batch is fed ahead of the current commit
     float map_cell_scale = 0.67f;  // map index cell = map_cell_scale * robot_size (0.34..1.0 measured: 0.67-1.0 best)
     bool overlap = true;      // run the device phases of batch k+1 on a helper thread while batch k commits
     bool split_commit = false;  // apply edge-list operations on a second thread while the first decides (measured slower on a 10 M-point map: cross-core traffic on the adjacency lists; kept for experiments)
