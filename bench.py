@@ -219,13 +219,19 @@ def run_product(a):
                                                          8 * (a.queries + 1)), xbytes=xb)
 
     def timed(resident: bool, warmup: int, steps: int, prof: bool):
+        # nvidia-smi is started BEFORE the warm-up: its start-up (NVML init) holds driver locks for
+        # a second or so and stalled whichever CUDA call of the first timed step ran into it
+        sampler = ClockSampler(local, a.clock_ms).start() if (rank == 0 and a.clock_ms > 0) else None
+        if prof:
+            K.prof_enable(True)    # the profiler's event pool is created during the warm-up as well
         for _ in range(warmup):
             one_step(resident)
         sync_all()
+        if sampler:
+            sampler.rows.clear()   # keep only samples taken during the timed region
         if prof:
-            K.prof_reset(); K.prof_enable(True)
+            K.prof_reset()
         l0 = K.launch_count()
-        sampler = ClockSampler(local, a.clock_ms).start() if (rank == 0 and a.clock_ms > 0) else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rows = [one_step(resident) for _ in range(steps)]

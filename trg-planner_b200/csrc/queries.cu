@@ -939,10 +939,10 @@ extern "C" int trgb_edge_eval_launch_skip(const trgb_map* m, const float* d_p1_x
 
 // ---- tier 1: host buffers ------------------------------------------------------------------
 namespace {
-struct DevBuf {
+struct DevBuf {  // staging of the host-buffer tier: stream-ordered pool, no cudaMalloc / cudaFree stalls
   void* p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
-  int alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1) == cudaSuccess ? 0 : -1; }
+  ~DevBuf() { if (p) cudaFreeAsync(p, 0); }
+  int alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, 0) == cudaSuccess && cudaStreamSynchronize(0) == cudaSuccess ? 0 : -1; }
   template <class T> T* as() { return static_cast<T*>(p); }
 };
 #define TRGB_ALLOC(buf, bytes) \

@@ -12,6 +12,7 @@
 // HBM layout per slot: label u64[n] | 4 queues int32[n] | 2 bitmaps u32[ceil(n/32)].
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -372,7 +373,8 @@ extern "C" int trgb_sssp_batch(trgb_graph* g, const int32_t* start_ids, const in
   o.found = (uint8_t*)d_found.p; o.cost = (float*)d_cost.p; o.path_length = (float*)d_len.p;
   o.avg_risk = (float*)d_risk.p; o.path_off = (int64_t*)d_off.p; o.path_len = (int32_t*)d_plen.p;
   o.path_ids = (int32_t*)d_ids.p; o.capacity = path_ids_capacity; o.cursor = (unsigned long long*)d_cur.p;
-  const float delta = 2.0f * std::max(g->mean_cost, 1e-3f);
+  // threshold step: 0.5..32 x the mean edge length measured; 1..2 is the flat optimum (profiles/README.md)
+  const float delta = 1.5f * std::max(g->mean_cost, 1e-3f);
   {
     ProfScope ps("k_sssp", st, (double)nq);
     k_sssp<<<g->nslots < want ? g->nslots : want, kSsspThreads, 0, st>>>(

@@ -104,14 +104,38 @@ void TRG::reseed(uint32_t seed) {
   dev_->draws.set_base(0);
 }
 
+// Nodes and edges live in pools (the reference leaks every `new Node` / `new Edge`). A full rebuild
+// (initGraph / loadPrebuiltGraph) rewinds the pools and recycles the objects, adjacency vectors
+// included, so repeated builds neither grow memory nor re-allocate 0.5 M small vectors.
 TRG::Node* TRG::newNode(int id, Eigen::Vector2f& p, float z, NodeState s) {
+  if (node_used_ < node_pool_.size()) {
+    Node& n = node_pool_[node_used_++];
+    n.id_ = id;
+    n.pos_ = Eigen::Vector3f(p.x(), p.y(), z);
+    n.state_ = s;
+    n.edges_.clear();
+    return &n;
+  }
   node_pool_.emplace_back(id, p, z, s);
   node_pool_.back().edges_.reserve(8);  // typical degree 7: one allocation instead of four
+  ++node_used_;
   return &node_pool_.back();
 }
 TRG::Edge* TRG::newEdge(int dst, float w, float d) {
+  if (edge_used_ < edge_pool_.size()) {
+    Edge& e = edge_pool_[edge_used_++];
+    e.dst_id_ = dst; e.weight_ = w; e.dist_ = d;
+    return &e;
+  }
   edge_pool_.emplace_back(dst, w, d);
+  ++edge_used_;
   return &edge_pool_.back();
+}
+void TRG::rewindPools() {
+  node_used_ = 0;
+  edge_used_ = 0;
+  goal_.node = nullptr;  // pointed into the recycled pool
+  last_path_ids_.clear();
 }
 
 // ================================================================================================
@@ -1280,6 +1304,8 @@ void TRG::initGraph(bool /*isPreMap*/, Eigen::Vector3f start3d) {  // trg.cpp:36
   auto t0 = Clock::now();
   trgStruct& graph = *trgMap_["global"];
   this->resetGraph(graph.type);
+  this->resetGraph("local");  // local nodes are pointers into the global graph
+  rewindPools();
   requireMap(graph, "initGraph");
 
   graph.root_pos           = start3d.head(2);
@@ -1427,27 +1453,39 @@ void TRG::invalidateDeviceGraph() {
 void TRG::ensureDeviceGraph() {
   if (dev_graph_) return;
   trgStruct& g = *trgMap_["global"];
+  // rows by node id; every node of the map is in node_seq with id_ == its key (see cleanGraph)
   int max_id = -1;
-  for (auto& kv : g.nodes) max_id = std::max(max_id, kv.first);
+  for (Node* nd : g.node_seq) max_id = std::max(max_id, nd->id_);
   const int n = max_id + 1;
   if (n <= 0) throw std::runtime_error("trg_b200: planSafePath on an empty graph");
   dev_graph_nodes_.assign(n, nullptr);
-  for (auto& kv : g.nodes) dev_graph_nodes_[kv.first] = kv.second;
+  for (Node* nd : g.node_seq) dev_graph_nodes_[nd->id_] = nd;
   std::vector<int64_t> row(n + 1, 0);
   for (int i = 0; i < n; ++i) row[i + 1] = row[i] + (dev_graph_nodes_[i] ? (int64_t)dev_graph_nodes_[i]->edges_.size() : 0);
   const int64_t e = row[n];
   std::vector<int32_t> col(e), state(n, -1);
   std::vector<float> w(e), d(e), pos(3 * (size_t)n, 0.f);
-  for (int i = 0; i < n; ++i) {
-    Node* nd = dev_graph_nodes_[i];
-    if (!nd) continue;
-    state[i] = (int32_t)nd->state_;
-    pos[3 * i] = nd->pos_.x(); pos[3 * i + 1] = nd->pos_.y(); pos[3 * i + 2] = nd->pos_.z();
-    int64_t k = row[i];
-    for (Edge* ed : nd->edges_) {
-      col[k] = ed->dst_id_; w[k] = ed->weight_; d[k] = ed->dist_;
-      ++k;
+  auto fill = [&](int b, int en) {
+    for (int i = b; i < en; ++i) {
+      Node* nd = dev_graph_nodes_[i];
+      if (!nd) continue;
+      state[i] = (int32_t)nd->state_;
+      pos[3 * i] = nd->pos_.x(); pos[3 * i + 1] = nd->pos_.y(); pos[3 * i + 2] = nd->pos_.z();
+      int64_t k = row[i];
+      for (Edge* ed : nd->edges_) {
+        col[k] = ed->dst_id_; w[k] = ed->weight_; d[k] = ed->dist_;
+        ++k;
+      }
     }
+  };
+  const int nthreads = n > 50000 ? (int)std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+  if (nthreads <= 1) {
+    fill(0, n);
+  } else {
+    std::vector<std::future<void>> jobs;
+    for (int t = 0; t < nthreads; ++t)
+      jobs.push_back(std::async(std::launch::async, fill, (int)((int64_t)n * t / nthreads), (int)((int64_t)n * (t + 1) / nthreads)));
+    for (auto& j : jobs) j.get();
   }
   TrgbGraphDesc desc{n, e, row.data(), col.data(), w.data(), d.data(), pos.data(), state.data()};
   K(trgb_graph_upload(&dev_graph_, &desc), "trgb_graph_upload");

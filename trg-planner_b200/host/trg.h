@@ -237,6 +237,8 @@ class TRG {
   void ensureDeviceGraph();
   Node* newNode(int id, Eigen::Vector2f& p, float z, NodeState s);
   Edge* newEdge(int dst, float w, float d);
+  void  rewindPools();
+  size_t node_used_ = 0, edge_used_ = 0;  // pool cursors
   void setGoalUnlocked(Eigen::Vector3f& goal);
   void runExpansion(const std::vector<Node*>& roots, trgStruct& g);
 

@@ -189,6 +189,8 @@ void TRG::loadPrebuiltGraph(const std::string& filepath) {  // trg.cpp:66-128
 
   trgStruct& g = *trgMap_["global"];
   this->resetGraph("global");
+  this->resetGraph("local");
+  rewindPools();
   std::unordered_map<int, Node*> id_to_node;
   for (const JValue& nj : root.at("nodes").arr()) {
     const int id = (int)nj.at("id").num();
