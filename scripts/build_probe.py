@@ -29,7 +29,7 @@ t = None
 for rep in range(a.reps):
     if t is None or not a.reuse:
         t = trg.product(P)
-    prev = {k: t.stat(k) for k in ("us_sample", "us_eval", "us_commit", "us_draws", "us_clean", "us_wait")}
+    prev = {k: t.stat(k) for k in ("us_sample", "us_eval", "us_commit", "us_draws", "us_clean", "us_wait", "us_reset", "us_root", "us_expand_end", "us_prepare", "us_serial_feed", "batches")}
     if a.chunk: t.set_tuning("chunk_nodes", a.chunk)
     if a.window: t.set_tuning("window", a.window)
     if a.cell: t.set_tuning("map_cell_scale", a.cell)

@@ -825,6 +825,11 @@ class Expander {
   // the whole queue is inside this batch — the following roots (updateGraph).
   bool prepare(Batch& b, const std::vector<TRG::Node*>& roots, size_t root_i, int cur_ref, size_t C, size_t chain_start) {
     b.pops.clear();
+    // leave about half of what is queued for the next batch, so that it can be fed while this one
+    // commits (a BFS generation is only a few thousand pops); small remainders go out whole
+    const size_t avail = bfs_.size() - sent_;
+    const size_t look  = (size_t)std::max(1, t_.tuning_.lookahead);
+    if (avail > look) C = std::min(C, std::max(look, avail / 2));
     for (size_t k = sent_; k < bfs_.size() && b.pops.size() < C; ++k) {
       TRG::Node* n = bfs_[k];
       b.pops.push_back({n, n->pos_.x(), n->pos_.y(), n->pos_.z(), cur_ref, false});
