@@ -70,6 +70,16 @@ int main() {
         bool same = want.size() == got.size() && got == got2;
         for (size_t i = 0; same && i < want.size(); ++i) same = (want[i] == got[i]);
         CHECK(same, "range order r=%g", r);
+        if (r < 1.0f) {  // grid candidates + root-path ordering must reproduce the traversal's result order
+          std::vector<int> c2;
+          grid.for_each_in_range(qx, qy, r, [&](int e) { c2.push_back(e); });
+          seq.order_like_range(c2, qx, qy);
+          CHECK(c2 == got, "order_like_range r=%g (%zu candidates)", r, c2.size());
+          std::vector<int> c3 = got;
+          std::reverse(c3.begin(), c3.end());
+          bulk.order_like_range(c3, qx, qy);
+          CHECK(c3 == got, "order_like_range on the bulk-built tree");
+        }
         CHECK(grid.count_in_range(qx, qy, r) == (int)want.size(), "grid range count round=%d n=%d q=(%g,%g) r=%g got=%d want=%d", round, n, qx, qy, r, grid.count_in_range(qx, qy, r), (int)want.size());
       }
     }

@@ -10,6 +10,7 @@
 //                kd_nearest_range2 results are iterated (head of list = last node visited;
 //                kdtree.c:270-301, 759-777). It is built lazily from the insertion sequence.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <future>
@@ -21,7 +22,7 @@ namespace trg_b200 {
 class OrderTree2D {
  public:
   void clear() {
-    x_.clear(); y_.clear(); lo_.clear(); hi_.clear(); axis_.clear(); payload_.clear();
+    x_.clear(); y_.clear(); lo_.clear(); hi_.clear(); axis_.clear(); payload_.clear(); parent_.clear();
     have_box_ = false;
   }
   size_t size() const { return x_.size(); }
@@ -34,6 +35,7 @@ class OrderTree2D {
   void insert(float x, float y, int payload) {
     const int self = static_cast<int>(x_.size());
     uint8_t axis = 0;
+    parent_of_new_ = -1;
     if (self > 0) {
       int at = 0;
       while (true) {
@@ -42,6 +44,7 @@ class OrderTree2D {
         if (slot < 0) {
           slot = self;
           axis = axis_[at] ^ 1;
+          parent_of_new_ = at;
           break;
         }
         at = slot;
@@ -49,6 +52,7 @@ class OrderTree2D {
     }
     x_.push_back(x); y_.push_back(y); lo_.push_back(-1); hi_.push_back(-1);
     axis_.push_back(axis); payload_.push_back(payload);
+    parent_.push_back(parent_of_new_);
     if (!have_box_) {
       bmin_[0] = bmax_[0] = x; bmin_[1] = bmax_[1] = y; have_box_ = true;
     } else {
@@ -75,6 +79,45 @@ class OrderTree2D {
     std::vector<int> idx(n), tmp(n);
     for (int i = 0; i < n; ++i) idx[i] = i;
     build_range(x, y, idx.data(), tmp.data(), 0, n, 0, 0);
+    parent_.assign(n, -1);
+    for (int i = 0; i < n; ++i) {
+      if (lo_[i] >= 0) parent_[lo_[i]] = i;
+      if (hi_[i] >= 0) parent_[hi_[i]] = i;
+    }
+  }
+
+  // Order the given tree nodes (indices = insertion order) the way kd_nearest_range2's result
+  // iterator yields them for a query at (qx, qy) whose range contains them all: the traversal
+  // (kdtree.c:270-301) is pre-order, query-side child first, and results are PREPENDED, so the
+  // iteration runs from the last visited to the first. Only the root paths of the candidates are
+  // walked (depth ~ 2.5 log2 n each) instead of traversing the tree around the query.
+  void order_like_range(std::vector<int>& cand, float qx, float qy) const {
+    if (cand.size() < 2) return;
+    auto path_of = [&](int v, std::vector<int>& out) {
+      out.clear();
+      for (int a = v; a >= 0; a = parent_[a]) out.push_back(a);  // v ... root
+    };
+    std::vector<std::vector<int>> paths(cand.size());
+    for (size_t i = 0; i < cand.size(); ++i) path_of(cand[i], paths[i]);
+    // visited_before(a, b): a is reached before b by the traversal
+    auto visited_before = [&](size_t ia, size_t ib) {
+      const auto& pa = paths[ia];
+      const auto& pb = paths[ib];
+      size_t ka = pa.size(), kb = pb.size();   // walk down from the root while the paths agree
+      while (ka > 0 && kb > 0 && pa[ka - 1] == pb[kb - 1]) { --ka; --kb; }
+      if (ka == 0) return true;    // a is an ancestor of b (or equal): pre-order visits it first
+      if (kb == 0) return false;   // b is an ancestor of a
+      const int l = pa[ka];        // lowest common ancestor (last agreeing node)
+      const float dx = axis_[l] ? (qy - y_[l]) : (qx - x_[l]);
+      const int near = dx <= 0.0f ? lo_[l] : hi_[l];
+      return pa[ka - 1] == near;   // a sits in the subtree the traversal enters first
+    };
+    std::vector<size_t> ord(cand.size());
+    for (size_t i = 0; i < ord.size(); ++i) ord[i] = i;
+    std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return a != b && visited_before(b, a); });  // reverse visit order
+    std::vector<int> out(cand.size());
+    for (size_t i = 0; i < ord.size(); ++i) out[i] = cand[ord[i]];
+    cand.swap(out);
   }
 
  private:
@@ -230,6 +273,8 @@ class OrderTree2D {
   std::vector<int> lo_, hi_;
   std::vector<uint8_t> axis_;
   std::vector<int> payload_;
+  std::vector<int> parent_;
+  int parent_of_new_ = -1;
   float bmin_[2] = {0, 0}, bmax_[2] = {0, 0};
   bool have_box_ = false;
   mutable std::vector<Step> walk_;

@@ -386,13 +386,18 @@ TRG::Node* TRG::resolveNearestTie(trgStruct& g, float qx, float qy, float d2min)
   return g.node_seq[trg_b200::first_visited_of(xs.data(), ys.data(), cand, qx, qy)];
 }
 
-// kd_nearest_range2 on node_tree in the reference's result-iteration order
+// kd_nearest_range2 on node_tree in the reference's result-iteration order: the in-range SET comes
+// from the hash grid, the ORDER from the root paths of those few nodes in the insertion-order tree
+// (OrderTree2D::order_like_range) instead of a traversal of the unbalanced tree around the query.
 void TRG::rangeNodesOrdered(trgStruct& g, float x, float y, float r, std::vector<Node*>& out) {
   out.clear();
   if (g.node_seq.empty()) return;
   ensureTree(g);
+  ensureGridBuilt(g);
   static thread_local std::vector<int> idx;
-  g.node_tree.range(x, y, r, idx);
+  idx.clear();
+  g.node_grid.for_each_in_range(x, y, r, [&](int e) { idx.push_back(e); });
+  g.node_tree.order_like_range(idx, x, y);
   for (int i : idx) out.push_back(g.node_seq[i]);
 }
 
