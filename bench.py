@@ -181,16 +181,27 @@ def run_product(a):
             dist.barrier()
             torch.cuda.synchronize()
 
+    last_stitch = {}
+
     def exchange_boundary():
-        """NCCL all-gather of the nodes within expand_dist + robot_size of a shared tile border
-        (what a neighbour needs to stitch cross-tile edges). Returns bytes gathered."""
+        """N > 1: stitch the per-tile TRGs. NCCL all-gathers of boundary nodes, boundary strips of
+        the map and the stitched edges; cross-tile candidate edges are validated by the K4 kernels
+        on a map of the two strips (trg-planner_b200/sharding.py). Returns bytes gathered."""
         if dist is None:
             return 0
         from trg_planner_b200 import sharding
         g = t.export(edges=False)
-        sel = sharding.boundary_nodes(g.pos, bb[0][0], bb[0][1], P.expand_dist + P.robot_size, rank, world)
-        got = sharding.allgather_boundary(dist, torch, g.pos[sel], g.ids[sel], torch.device("cuda", local))
-        return int(sum(p.shape[0] for p, _ in got) * 16)
+
+        def edge_eval(strip_pts, p1, p2):
+            dm = K.DeviceMap(strip_pts, 0.67 * P.robot_size)
+            r = dm.edge_eval(p1, p2, P.robot_size, P.height_threshold, P.collision_threshold)
+            dm.close()
+            return r["stage"], r["weight"], r["dist"]
+
+        _, st = sharding.stitch_tiles(dist, torch, torch.device("cuda", local), rank, world, pts, g.pos, g.ids,
+                                      bb[0][0], bb[0][1], P.expand_dist, P.robot_size, edge_eval)
+        last_stitch.update(st)
+        return st["bytes"]
 
     STAT_KEYS = ("us_sample", "us_eval", "us_commit", "us_wait", "us_clean", "us_draws", "pops", "window_launches",
                  "eval_launches", "window_tests", "edge_evals")
@@ -334,7 +345,7 @@ def run_product(a):
         "cpu_baseline": cpu,
     }
     if world > 1:
-        line["exchange"] = {"allgather_bytes_per_step": val["rows"][-1]["xbytes"], "ms": 1e3 * val["exch_s"]}
+        line["exchange"] = {"allgather_bytes_per_step": val["rows"][-1]["xbytes"], "ms": 1e3 * val["exch_s"], **last_stitch}
     if saved_stdout is not None:
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)

@@ -91,3 +91,74 @@ def test_boundary_allgather_gloo_world2():
     for i, j in pairs:
         a, b = res[0][4][0][0][i], res[0][4][1][0][j]
         assert np.hypot(a[0] - b[0], a[1] - b[1]) <= 0.9 + 1e-6
+
+
+def _stitch_worker(rank, world, port, q):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    import _pkg
+    trg = _pkg.load()
+    from trg_planner_b200 import sharding
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    P = trg.MOUNTAIN
+    side = 140
+    pts = trg.terrain.mountain(side, h=0.1, seed=2, tile=(rank, 0), world_tiles=(world, 1))
+    x_lo, x_hi = rank * side * 0.1, (rank + 1) * side * 0.1
+    o = trg.oracle(P)
+    o.seed(42 + rank)
+    o.set_global_map(pts)
+    assert o.init_graph((0.5 * (x_lo + x_hi), 7.0, 0.0)) == 0
+    g = o.export()
+
+    def edge_eval(strip_pts, p1, p2):      # CPU tests: the oracle stands in for the K4 kernels
+        e = trg.oracle(P)
+        e.set_global_map(strip_pts)
+        r = e.edge_eval(p1, p2)
+        return r["stage"], r["weight"], r["dist"]
+
+    edges, st = sharding.stitch_tiles(dist, torch, torch.device("cpu"), rank, world, pts, g.pos, g.ids, x_lo, x_hi,
+                                      P.expand_dist, P.robot_size, edge_eval)
+    q.put((rank, edges, st, g.pos, g.ids, pts))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_stitch_tiles_gloo_world2(pkg):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 300)
+    procs = [ctx.Process(target=_stitch_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(2):
+        r = q.get(timeout=300)
+        res[r[0]] = r
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    e0, e1 = res[0][1], res[1][1]
+    np.testing.assert_array_equal(e0, e1)              # every rank ends with the same stitched edge list
+    assert res[0][2]["stitched_edges_total"] == len(e0) > 20
+    assert res[0][2]["strip_points"] > 1000 and res[0][2]["candidate_pairs"] >= len(e0)
+    # every stitched edge joins a node of tile 0 to a node of tile 1 closer than expand_dist, and
+    # re-evaluating it on the merged strips gives the same risk
+    P = pkg.MOUNTAIN
+    pos0 = {int(i): p for i, p in zip(res[0][4], res[0][3])}
+    pos1 = {int(i): p for i, p in zip(res[1][4], res[1][3])}
+    merged = np.concatenate([res[0][5][res[0][5][:, 0] > 14.0 - 2.0], res[1][5][res[1][5][:, 0] < 14.0 + 2.0]])
+    o = pkg.oracle(P)
+    o.set_global_map(merged)
+    p1 = np.array([pos0[int(e[1])] for e in e0], np.float32)
+    p2 = np.array([pos1[int(e[3])] for e in e0], np.float32)
+    assert (e0[:, 0] == 0).all() and (e0[:, 2] == 1).all()
+    d = np.hypot(p1[:, 0] - p2[:, 0], p1[:, 1] - p2[:, 1])
+    # (a node may sit up to robot_size beyond the last points of its own tile)
+    assert (d < P.expand_dist + 1e-6).all() and (p1[:, 0] < 14.0 + P.robot_size + 0.05).all() and (p2[:, 0] > 14.0 - P.robot_size - 0.05).all()
+    ev = o.edge_eval(p1, p2)
+    assert (ev["stage"] == 0).all()
+    np.testing.assert_allclose(ev["weight"], e0[:, 4], rtol=1e-6)
+    np.testing.assert_allclose(ev["dist"], e0[:, 5], rtol=1e-6)

@@ -65,3 +65,81 @@ def cross_tile_candidates(mine_pos: np.ndarray, other_pos: np.ndarray, max_dist:
         for j in nb:
             pairs.append((i, j))
     return np.asarray(pairs, np.int64).reshape(-1, 2)
+
+
+def allgather_rows(dist, torch, rows: np.ndarray, device) -> list[np.ndarray]:
+    """All-gather one float32 matrix per rank (same column count, ragged row counts): two
+    collectives (counts, then the payload padded to the longest). Returns the matrix of every rank."""
+    world = dist.get_world_size()
+    rows = np.ascontiguousarray(rows, np.float32)
+    ncol = rows.shape[1]
+    cnt = torch.tensor([rows.shape[0]], dtype=torch.int64, device=device)
+    cnts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(cnts, cnt)
+    counts = [int(c.item()) for c in cnts]
+    mx = max(1, max(counts))
+    pad = torch.zeros((mx, ncol), dtype=torch.float32, device=device)
+    if rows.shape[0]:
+        pad[: rows.shape[0]] = torch.from_numpy(rows).to(device)
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad)
+    return [out[r][: counts[r]].cpu().numpy().copy() for r in range(world)]
+
+
+def stitch_tiles(dist, torch, device, rank: int, world: int, tile_pts: np.ndarray, node_pos: np.ndarray,
+                 node_ids: np.ndarray, x_lo: float, x_hi: float, expand_dist: float, robot_size: float,
+                 edge_eval, strip: float = 2.0):
+    """Wire the TRGs of neighbouring tiles together (tiles laid out along x).
+
+    Exchange step (NCCL / gloo all-gather, three collectives' worth of payload):
+      1. boundary nodes: nodes within expand_dist + robot_size of a shared border (pos, id);
+      2. boundary strips: the map points within `strip` of a shared border, so that the rank that
+         evaluates a cross-tile edge sees the terrain on BOTH sides of the border;
+      3. the stitched edges, so both owners of a border know them.
+    Rank r owns the border between tiles r and r+1: it builds a map of the two strips, pairs its
+    right-band nodes with the neighbour's left-band nodes closer than expand_dist (the radius of
+    TRG::expandGraph's neighbour wiring, trg.cpp:429-444) and validates every pair with the same edge
+    evaluation as inside a tile (`edge_eval(strip_pts, p1_xyz, p2_xyz) -> stage, weight, dist`;
+    the batched K4 kernel on the GPU, the oracle in the CPU tests).
+    Returns (edges, stats): edges = float64 array of rows (rank_a, id_a, rank_b, id_b, weight, dist)
+    for EVERY border (identical on all ranks).
+    """
+    band = expand_dist + robot_size
+    x = node_pos[:, 0]
+    left = np.nonzero(x < x_lo + band)[0] if rank > 0 else np.zeros(0, np.int64)
+    right = np.nonzero(x > x_hi - band)[0] if rank < world - 1 else np.zeros(0, np.int64)
+    sel = np.concatenate([left, right])
+    side = np.concatenate([np.zeros(left.size), np.ones(right.size)]).astype(np.float32)
+    ids_f = np.ascontiguousarray(node_ids[sel], np.int32).view(np.float32)   # ids travel bit-cast
+    nodes_rows = np.column_stack([node_pos[sel], ids_f, side]).astype(np.float32) if sel.size else np.zeros((0, 5), np.float32)
+    px = tile_pts[:, 0]
+    pl = tile_pts[px < x_lo + strip] if rank > 0 else np.zeros((0, 3), np.float32)
+    pr = tile_pts[px > x_hi - strip] if rank < world - 1 else np.zeros((0, 3), np.float32)
+    strip_rows = np.concatenate([np.column_stack([pl, np.zeros(len(pl), np.float32)]),
+                                 np.column_stack([pr, np.ones(len(pr), np.float32)])]).astype(np.float32)
+    all_nodes = allgather_rows(dist, torch, nodes_rows, device)
+    all_strips = allgather_rows(dist, torch, strip_rows, device)
+    mine = np.zeros((0, 6), np.float64)
+    n_pairs = 0
+    if rank < world - 1:
+        a = all_nodes[rank][all_nodes[rank][:, 4] == 1.0]          # my right band
+        b = all_nodes[rank + 1][all_nodes[rank + 1][:, 4] == 0.0]  # neighbour's left band
+        pairs = cross_tile_candidates(a[:, :3], b[:, :3], expand_dist)
+        n_pairs = len(pairs)
+        if n_pairs:
+            sp = np.concatenate([all_strips[rank][all_strips[rank][:, 3] == 1.0][:, :3],
+                                 all_strips[rank + 1][all_strips[rank + 1][:, 3] == 0.0][:, :3]]).astype(np.float32)
+            stage, w, d = edge_eval(np.ascontiguousarray(sp), np.ascontiguousarray(a[pairs[:, 0], :3]),
+                                    np.ascontiguousarray(b[pairs[:, 1], :3]))
+            ok = np.nonzero(np.asarray(stage) == 0)[0]
+            ida = np.ascontiguousarray(a[:, 3]).view(np.int32)[pairs[ok, 0]]
+            idb = np.ascontiguousarray(b[:, 3]).view(np.int32)[pairs[ok, 1]]
+            mine = np.column_stack([np.full(ok.size, rank), ida, np.full(ok.size, rank + 1), idb,
+                                    np.asarray(w)[ok], np.asarray(d)[ok]]).astype(np.float64)
+    # share the stitched edges (float32 payload: ids < 2^24 exact; larger ids would need the bit-cast trick)
+    got = allgather_rows(dist, torch, mine.astype(np.float32), device)
+    edges = np.concatenate(got) if got else mine
+    stats = dict(boundary_nodes=int(sum(len(m) for m in all_nodes)), strip_points=int(sum(len(m) for m in all_strips)),
+                 candidate_pairs=int(n_pairs), stitched_edges_total=int(len(edges)),
+                 bytes=int(sum(m.nbytes for m in all_nodes) + sum(m.nbytes for m in all_strips) + sum(m.nbytes for m in got)))
+    return edges, stats
