@@ -13,4 +13,4 @@ for rep in range(3):
     K.prof_reset(); K.prof_enable(True)
     w=time.time(); r=t.plan_batch(q, max_total_nodes=nq*4096); dt=time.time()-w
     pr=K.prof_collect(); K.prof_enable(False)
-    print(json.dumps(dict(delta=os.environ.get("TRGB_SSSP_DELTA","2"), rep=rep, plan_s=round(dt,4), snap_s=round(t.seconds("plan_snap"),4), sssp_ms=round(pr["k_sssp"]["ms"],2), found=int(r["found"].sum()), cost_sum=float(r["cost"].sum()))), flush=True)
+    print(json.dumps(dict(delta=os.environ.get("TRGB_SSSP_DELTA","2"), rep=rep, plan_s=round(dt,4), snap_s=round(t.seconds("plan_snap"),4), csr_s=round(t.seconds("plan_csr"),4), tree_s=round(t.seconds("plan_tree"),4), grid_s=round(t.seconds("plan_grid"),4), sssp_ms=round(pr["k_sssp"]["ms"],2), found=int(r["found"].sum()), cost_sum=float(r["cost"].sum()))), flush=True)

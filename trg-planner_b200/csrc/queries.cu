@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(kThreads) k_collision(MapView m, const float2*
                                                         int64_t n, float r, float hthr, float rthr,
                                                         int cap, uint8_t* __restrict__ out) {
   extern __shared__ float zsm[];
-  float* zbuf = zsm + (threadIdx.x >> 5) * cap;
+  float* zbuf = zsm + (threadIdx.x >> 5) * (cap + 256);  // + 256 bins for the histogram select
   const int lane = threadIdx.x & 31;
   const int64_t wstride = (int64_t)gridDim.x * kWarpsPerCta;
   for (int64_t i = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); i < n; i += wstride) {
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kThreads) k_sample_window(
     const float2* __restrict__ draw_xy, int64_t n_nodes, int window, float r, float hthr, float rthr,
     int cap, unsigned long long* __restrict__ mask) {
   extern __shared__ float zsm[];
-  float* zbuf = zsm + (threadIdx.x >> 5) * cap;
+  float* zbuf = zsm + (threadIdx.x >> 5) * (cap + 256);  // + 256 bins for the histogram select
   const int lane = threadIdx.x & 31;
   const int64_t items = n_nodes * window;
   const int64_t wstride = (int64_t)gridDim.x * kWarpsPerCta;
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(kThreads) k_edge_eval(MapView m, const float* 
                                                         float* __restrict__ dist_out,
                                                         int32_t* __restrict__ npts_out) {
   extern __shared__ float zsm[];
-  float* zbuf = zsm + (threadIdx.x >> 5) * cap;
+  float* zbuf = zsm + (threadIdx.x >> 5) * (cap + 256);  // + 256 bins for the histogram select
   const int lane = threadIdx.x & 31;
   const int64_t wstride = (int64_t)gridDim.x * kWarpsPerCta;
   for (int64_t i = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); i < n; i += wstride) {
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(kTqThreads) k_collision_tq(MapView m, const fl
     }
     TQ_FALLBACK_BEGIN(res)
       const float qx = __shfl_sync(FULL, p.x, src), qy = __shfl_sync(FULL, p.y, src);
-      const bool c = warp_is_collision(m, qx, qy, r, hthr, rthr, wbuf, 32 * cap, nullptr);
+      const bool c = warp_is_collision(m, qx, qy, r, hthr, rthr, wbuf, 32 * cap - 256, nullptr);
       if (lane == src) res = c ? 1 : 0;
     TQ_FALLBACK_END
     if (i < n) out[i] = (uint8_t)res;
@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(kTqThreads) k_sample_window_tq(
     }
     TQ_FALLBACK_BEGIN(res)
       const float qx = __shfl_sync(FULL, sx, src), qy = __shfl_sync(FULL, sy, src);
-      const bool c = warp_is_collision(m, qx, qy, r, hthr, rthr, wbuf, 32 * cap, nullptr);
+      const bool c = warp_is_collision(m, qx, qy, r, hthr, rthr, wbuf, 32 * cap - 256, nullptr);
       if (lane == src) res = c ? 1 : 0;
     TQ_FALLBACK_END
     if (it < items && res) atomicOr(mask + node * words + (j >> 6), 1ull << (j & 63));
@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(kTqThreads) k_sample_window_sm(
       }
       TQ_FALLBACK_BEGIN(res)
         const float qx = __shfl_sync(FULL, sx, src), qy = __shfl_sync(FULL, sy, src);
-        const bool c = warp_is_collision(m, qx, qy, r, hthr, rthr, wbuf, 32 * cap, nullptr);
+        const bool c = warp_is_collision(m, qx, qy, r, hthr, rthr, wbuf, 32 * cap - 256, nullptr);
         if (lane == src) res = c ? 1 : 0;
       TQ_FALLBACK_END
       if (j < window && res) atomicOr(mask + node * words + (j >> 6), 1ull << (j & 63));
@@ -620,7 +620,7 @@ __global__ void __launch_bounds__(kTqThreads) k_edge_collide_tq(MapView m, const
     }
     TQ_FALLBACK_BEGIN(res)
       const float qx = __shfl_sync(FULL, sx, src), qy = __shfl_sync(FULL, sy, src);
-      const bool c = warp_is_collision(m, qx, qy, rs, hthr, cthr, wbuf, 32 * cap, nullptr);
+      const bool c = warp_is_collision(m, qx, qy, rs, hthr, cthr, wbuf, 32 * cap - 256, nullptr);
       if (lane == src) res = c ? 1 : 0;
     TQ_FALLBACK_END
     if (it < items && res == 1) stage[e] = (uint8_t)TRGB_EDGE_COLLISION;
@@ -670,8 +670,11 @@ __global__ void __launch_bounds__(256) k_edge_pca(MapView m, const float* __rest
       const int cx0 = cell_coord(cx - rr, m.x0, m.inv_cell, m.W), cx1 = cell_coord(cx + rr, m.x0, m.inv_cell, m.W);
       const int cy0 = cell_coord(cy - rr, m.y0, m.inv_cell, m.H), cy1 = cell_coord(cy + rr, m.y0, m.inv_cell, m.H);
       for (int row = cy0 + sub; row <= cy1; row += kPcaLanes) {
+        int ca, cb;
+        row_chord(m, cx, cy, rr, row, cx0, cx1, &ca, &cb);  // chord of the radius-a disc in this row
+        if (ca > cb) continue;
         const size_t rb = (size_t)row * (size_t)m.W;
-        const uint32_t s = __ldg(m.cell_start + rb + cx0), e = __ldg(m.cell_start + rb + cx1 + 1);
+        const uint32_t s = __ldg(m.cell_start + rb + ca), e = __ldg(m.cell_start + rb + cb + 1);
 #pragma unroll 4
         for (uint32_t k = s; k < e; ++k) {
           const float4 p = ld_pt(m.pts + k);
@@ -754,7 +757,7 @@ static int pick_cap(const trgb_map* m, float r) {
 static int launch_cfg(const trgb_map* m, float r, int64_t n_items, int* grid, int* cap, size_t* smem,
                       const void* kernel) {
   *cap = pick_cap(m, r);
-  *smem = (size_t)kWarpsPerCta * (*cap) * sizeof(float);
+  *smem = (size_t)kWarpsPerCta * (*cap + 256) * sizeof(float);  // hits + 256 histogram bins per warp
   if (*smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(smem)", __FILE__, __LINE__);

@@ -1614,7 +1614,22 @@ void TRG::planSafePathBatch(const float* queries, int64_t n, PathBatch& out) {
   out.cost.assign(n, 0.f); out.path_length.assign(n, 0.f); out.avg_risk.assign(n, 0.f); out.direct_dist.assign(n, 0.f);
   out.offsets.assign(n + 1, 0);
   if (n <= 0 || g.nodes.empty()) return;
-  ensureDeviceGraph();
+  {
+    // per-graph preparation, three independent pieces side by side: CSR build + upload (this
+    // thread), order tree for goal snapping, hash grid for start snapping
+    auto f_tree = std::async(std::launch::async, [&] { ensureTree(g); });
+    auto f_grid = std::async(std::launch::async, [&] { ensureGridBuilt(g); });
+    try {
+      ensureDeviceGraph();
+    } catch (...) {
+      f_tree.wait();
+      f_grid.wait();
+      throw;
+    }
+    f_tree.get();
+    f_grid.get();
+  }
+  secs_["plan_prep"] = since(t0);
   std::vector<int32_t> s(n), t(n);
   for (int64_t i = 0; i < n; ++i) {
     const float* q = queries + 5 * i;
