@@ -448,8 +448,10 @@ def run_reference(a):
     line = {"impl": "reference", "metric": "trg_build_points_per_sec", "value": v, "unit": "points/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C2 synthetic mountain heightfield, config/mountain.yaml params, full TRG build + path queries; "
-                                   f"each step = bounded sample {a.cpu_side}x{a.cpu_side} tile",
+            "config": {"workload": f"C2 synthetic mountain heightfield {a.side}x{a.side} (h=0.1 m), config/mountain.yaml params, "
+                                   f"full TRG build + path queries",
+                       "sample": f"each step = the reference's CPU path (oracle: restated trg.cpp + kdtree.c) on a bounded sample: "
+                                 f"one {a.cpu_side}x{a.cpu_side} tile ({a.cpu_side * a.cpu_side} points) of the same generator + 50 queries, 1 thread",
                        "mt19937_seed": SEED_RNG},
             "nodes_per_sec": float(np.mean([r["nodes_per_sec"] for r in rows])),
             "paths_per_sec": float(np.mean([r["paths_per_sec"] for r in rows])),

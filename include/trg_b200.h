@@ -63,6 +63,19 @@ int trg_refine_path(void* h, const float* in_xyz, int n_in, float* out_xyz, int*
 int trg_check_reached(void* h, float x, float y);                                          /* TRG::checkReadched trg.cpp:567 */
 int trg_check_replan(void* h, float x, float y, const float* path_xyz, int n_path);        /* TRG::checkReplan   trg.cpp:576 */
 
+/* ---- the step before the path: configuration and map ingestion ------------------------------
+ * TRGPlanner::setParams (src/planner/trg_planner.cpp:103-129): reads the config yaml files; `out` receives the
+ * nine TRG constructor arguments, the map settings come back through the other pointers (any may
+ * be NULL; strings are copied into caller buffers of `path_cap` bytes). */
+int trg_load_params_yaml(const char* config_path, TrgParams* out, int* is_prebuilt_map, char* prebuilt_map_path,
+                         int path_cap, int* is_voxelize, float* voxel_size, int* is_update);
+/* pcl::io::loadPCDFile (trg_planner.cpp:85): number of points in *n; xyz may be NULL to query the size */
+int trg_load_pcd(const char* path, float* xyz, int64_t cap_points, int64_t* n);
+int trg_save_pcd(const char* path, const float* xyz, int64_t n, int binary);
+/* TRGPlanner::loadPrebuiltMap (trg_planner.cpp:76-101): PCD -> optional voxel filter (device) ->
+ * TRG::setGlobalMap. n_raw / n_map receive the point counts before / after the filter. */
+int trg_load_prebuilt_map(void* h, const char* pcd_path, int is_voxelize, float voxel_size, int64_t* n_raw, int64_t* n_map);
+
 /* pure batched evaluations */
 int trg_is_collision_batch(void* h, const char* type, const float* xy, int64_t n, float threshold, uint8_t* out); /* trg.cpp:746 */
 int trg_range_count_batch(void* h, const char* type, const float* xy, int64_t n, float radius, int32_t* out);

@@ -135,6 +135,15 @@ int     trgb_nodes_append_launch(trgb_nodes* g, const float* d_xy, int64_t n, vo
 int     trgb_nodes_nearest_launch(const trgb_nodes* g, const float* d_xy, int64_t n, int32_t* d_idx, float* d_d2,
                                   uint8_t* d_tie, void* stream);
 
+/* ---- K8: voxel-grid centroid filter — the optional down-sampling of the map ingestion,
+ *      TRGPlanner::loadPrebuiltMap -> pcl::VoxelGrid (src/planner/trg_planner.cpp:90-94). One output
+ *      point per occupied leaf = centroid, in ascending leaf index (PCL's order). Returns TRGB_E_STATE
+ *      and passes the cloud through when the leaf grid would overflow 32-bit indices (PCL does the
+ *      same with a warning). out_xyz of the host variant must hold 3*n floats. */
+int  trgb_voxel_filter(const float* xyz, int64_t n, int stride_floats, float leaf, float* out_xyz, int64_t* n_out);
+int  trgb_voxel_filter_dev(const float* d_pts, int64_t n, int stride_floats, float leaf, float** d_out, int64_t* n_out);
+void trgb_device_free(void* p);
+
 /* ---- K7: graph upload + batched risk-aware shortest path (TRG::planSafePath, trg.cpp:618-688).
  *      CSR rows = node id 0..n-1, columns in `edges_` order. Start/goal snapping
  *      (TRG::setGoal trg.cpp:537-565, kd_nearest2 :615) is order-dependent host logic and stays

@@ -124,6 +124,39 @@ def test_staged_window_kernel_equals_plain(pkg, K, small_mountain):
         np.testing.assert_array_equal(got, want)
 
 
+@pytest.mark.parametrize("kind", ["mountain", "indoor", "stairs"])
+def test_many_seeds_and_starts(pkg, K, kind):
+    """Randomised sweep: 8 (map seed, RNG seed, start) combinations per terrain family, every one
+    bit-exact against the oracle — including builds whose root lands in collision and is retried
+    with random offsets (trg.cpp:47-56) and starts near the map border."""
+    rng = np.random.default_rng({"mountain": 1, "indoor": 2, "stairs": 3}[kind])
+    for trial in range(8):
+        ms = int(rng.integers(1, 1000))
+        if kind == "mountain":
+            P, pts = pkg.MOUNTAIN, pkg.terrain.mountain(110, h=0.1, seed=ms, amplitude=float(rng.choice([6.0, 12.0, 25.0])))
+        elif kind == "indoor":
+            P, pts = pkg.INDOOR, pkg.terrain.indoor(60, h=0.2, seed=ms, room=float(rng.choice([4.0, 6.0])))
+        else:
+            P, pts = pkg.MOUNTAIN, pkg.terrain.stairs(100, h=0.1, seed=ms, riser=float(rng.choice([0.08, 0.12])))
+        ext = float(pts[:, 0].max())
+        start = (float(rng.uniform(0.3, ext - 0.9)), float(rng.uniform(0.3, ext - 0.3)), 0.0)
+        seed = int(rng.integers(0, 2 ** 31))
+        t, o = pkg.product(P), pkg.oracle(P)
+        t.seed(seed); o.seed(seed)
+        t.set_global_map(pts); o.set_global_map(pts)
+        try:
+            rc_o = o.init_graph(start)
+        except RuntimeError:
+            rc_o = -1
+        if rc_o != 0:   # the reference exit(1)s when no root can be placed: the product must fail too
+            with pytest.raises(RuntimeError):
+                t.init_graph(start)
+            continue
+        assert t.init_graph(start) == 0
+        assert t.stat("rng_draws") == o.stat("rng_draws"), (kind, trial)
+        assert_graph_equal(t.export(), o.export(), f"{kind} trial {trial}")
+
+
 def test_seeds_differ_and_reproduce(pkg, K, small_mountain):
     P = pkg.MOUNTAIN
     t1, _ = build_pair(pkg, P, small_mountain, (15.0, 15.0, 0.0), seed=1)

@@ -6,5 +6,6 @@ generators used by tests/ and bench.py. The directory name has a hyphen (fixed b
 project layout), so it is imported under the module name `trg_planner_b200` via `_pkg.py`.
 """
 from . import params, terrain  # noqa: F401
-from .binding import TrgFacade, oracle, product  # noqa: F401
+from . import binding  # noqa: F401
+from .binding import TrgFacade, load_params_yaml, load_pcd, oracle, product, save_pcd  # noqa: F401
 from .params import INDOOR, MOUNTAIN, TrgParams  # noqa: F401

@@ -213,6 +213,14 @@ class TrgFacade:
         p = np.ascontiguousarray(path, dtype=np.float32)
         return bool(self._chk(self._f("check_replan")(self.h, float(xy[0]), float(xy[1]), _ptr(p), p.shape[0]), "check_replan"))
 
+    def load_prebuilt_map(self, pcd_path, is_voxelize=False, voxel_size=0.1):
+        """TRGPlanner::loadPrebuiltMap (trg_planner.cpp:76-101). Product only. Returns (n_raw, n_map)."""
+        self._f("load_prebuilt_map").argtypes = [_vp, C.c_char_p, C.c_int, C.c_float, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        a, b = C.c_int64(), C.c_int64()
+        self._chk(self._f("load_prebuilt_map")(self.h, str(pcd_path).encode(), int(is_voxelize), float(voxel_size),
+                                               C.byref(a), C.byref(b)), "load_prebuilt_map")
+        return a.value, b.value
+
     def refine_path(self, path: np.ndarray):
         p = np.ascontiguousarray(path, dtype=np.float32)
         out = np.empty((2 * max(p.shape[0], 1), 3), np.float32)
@@ -268,6 +276,52 @@ class TrgFacade:
 
     def stat(self, what: str) -> int:
         return int(self._f("stat")(self.h, what.encode()))
+
+
+def _product_lib():
+    if not PRODUCT_LIB.exists():
+        raise FileNotFoundError(f"{PRODUCT_LIB} is missing — run __graft_entry__.build()")
+    L = C.CDLL(str(PRODUCT_LIB), mode=C.RTLD_GLOBAL)
+    L.trg_last_error.restype = C.c_char_p
+    L.trg_load_params_yaml.argtypes = [C.c_char_p, C.POINTER(CParams), C.POINTER(C.c_int), C.c_char_p, C.c_int,
+                                       C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    L.trg_load_pcd.argtypes = [C.c_char_p, _vp, C.c_int64, C.POINTER(C.c_int64)]
+    L.trg_save_pcd.argtypes = [C.c_char_p, _vp, C.c_int64, C.c_int]
+    L.trg_load_prebuilt_map.argtypes = [_vp, C.c_char_p, C.c_int, C.c_float, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    return L
+
+
+def load_params_yaml(path) -> dict:
+    """TRGPlanner::setParams (trg_planner.cpp:103-129) through the C facade."""
+    L = _product_lib()
+    cp = CParams()
+    pre, vox, upd = C.c_int(), C.c_int(), C.c_int()
+    vs = C.c_float()
+    buf = C.create_string_buffer(1024)
+    if L.trg_load_params_yaml(str(path).encode(), C.byref(cp), C.byref(pre), buf, 1024, C.byref(vox), C.byref(vs), C.byref(upd)) < 0:
+        raise RuntimeError((L.trg_last_error() or b"").decode())
+    trg = TrgParams(bool(cp.is_verbose), cp.expand_dist, cp.robot_size, cp.sample_num, cp.height_threshold,
+                    cp.collision_threshold, cp.update_collision_threshold, cp.safety_factor, cp.goal_tolerance)
+    return dict(trg=trg, is_prebuilt_map=bool(pre.value), prebuilt_map_path=buf.value.decode(),
+                is_voxelize=bool(vox.value), voxel_size=vs.value, is_update=bool(upd.value))
+
+
+def load_pcd(path) -> np.ndarray:
+    L = _product_lib()
+    n = C.c_int64()
+    if L.trg_load_pcd(str(path).encode(), None, 0, C.byref(n)) < 0:
+        raise RuntimeError((L.trg_last_error() or b"").decode())
+    out = np.empty((n.value, 3), np.float32)
+    if L.trg_load_pcd(str(path).encode(), _ptr(out), n.value, C.byref(n)) < 0:
+        raise RuntimeError((L.trg_last_error() or b"").decode())
+    return out
+
+
+def save_pcd(path, xyz: np.ndarray, binary: bool = True):
+    L = _product_lib()
+    a = np.ascontiguousarray(xyz, np.float32)
+    if L.trg_save_pcd(str(path).encode(), _ptr(a), a.shape[0], int(binary)) < 0:
+        raise RuntimeError((L.trg_last_error() or b"").decode())
 
 
 def oracle(params: TrgParams, ref_kdtree: bool = False) -> TrgFacade:

@@ -152,14 +152,6 @@ __global__ void __launch_bounds__(kThreads) k_nearest_z(MapView m, const float2*
 // rotations accumulated into U, negative diagonals flipped, columns sorted descending.
 struct Rot { float c, s; };
 __device__ __forceinline__ Rot rot_mul(Rot a, Rot b) { return {a.c * b.c - a.s * b.s, a.c * b.s + a.s * b.c}; }
-__device__ __forceinline__ void rot_plane(float* x, int incx, float* y, int incy, int n, Rot j) {
-  if (j.c == 1.f && j.s == 0.f) return;
-  for (int i = 0; i < n; ++i) {
-    const float xi = x[i * incx], yi = y[i * incy];
-    x[i * incx] = j.c * xi + j.s * yi;
-    y[i * incy] = -j.s * xi + j.c * yi;
-  }
-}
 __device__ __forceinline__ Rot make_jacobi(float x, float y, float z) {
   const float deno = 2.f * fabsf(y);
   if (deno < 1.17549435e-38f) return {1.f, 0.f};
@@ -173,61 +165,108 @@ __device__ __forceinline__ Rot make_jacobi(float x, float y, float z) {
   r.c = nn;
   return r;
 }
-__device__ void jacobi_svd3(const float* A, float* U, float* sv) {
+// One (p, q) step of the sweep with compile-time indices: W and U stay in registers (no local
+// memory, no dynamic indexing). Same arithmetic, in the same order, as the loop form it replaces.
+template <int P, int Q>
+__device__ __forceinline__ void jacobi_pair(float (&W)[9], float (&U)[9], float& maxDiag, bool& finished) {
   const float precision = 2.f * 1.1920929e-07f;
   const float tiny = 1.17549435e-38f;
+  const float thr = fmaxf(tiny, precision * maxDiag);
+  if (!(fabsf(W[P * 3 + Q]) > thr || fabsf(W[Q * 3 + P]) > thr)) return;
+  finished = false;
+  float m0 = W[P * 3 + P], m1 = W[P * 3 + Q], m2 = W[Q * 3 + P], m3 = W[Q * 3 + Q];
+  Rot rot1;
+  const float t = m0 + m3, d = m2 - m1;
+  if (fabsf(d) < tiny) { rot1.s = 0.f; rot1.c = 1.f; }
+  else {
+    const float u = __fdiv_rn(t, d);
+    const float tmp = __fsqrt_rn(1.f + u * u);
+    rot1.s = __fdiv_rn(1.f, tmp);
+    rot1.c = __fdiv_rn(u, tmp);
+  }
+  if (!(rot1.c == 1.f && rot1.s == 0.f)) {  // rot_plane(mm+0, mm+2, n=2, rot1): rows (m0 m1) and (m2 m3)
+    const float a0 = rot1.c * m0 + rot1.s * m2, b0 = -rot1.s * m0 + rot1.c * m2;
+    const float a1 = rot1.c * m1 + rot1.s * m3, b1 = -rot1.s * m1 + rot1.c * m3;
+    m0 = a0; m2 = b0; m1 = a1; m3 = b1;
+  }
+  const Rot jr = make_jacobi(m0, m1, m3);
+  const Rot jl = rot_mul(rot1, Rot{jr.c, -jr.s});
+  if (!(jl.c == 1.f && jl.s == 0.f)) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {  // rows P, Q of W  (applyOnTheLeft)
+      const float x = W[P * 3 + i], y = W[Q * 3 + i];
+      W[P * 3 + i] = jl.c * x + jl.s * y;
+      W[Q * 3 + i] = -jl.s * x + jl.c * y;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {  // columns P, Q of U  (U.applyOnTheRight(p, q, j_left^T))
+      const float x = U[i * 3 + P], y = U[i * 3 + Q];
+      U[i * 3 + P] = jl.c * x + jl.s * y;
+      U[i * 3 + Q] = -jl.s * x + jl.c * y;
+    }
+  }
+  const Rot jrt{jr.c, -jr.s};
+  if (!(jrt.c == 1.f && jrt.s == 0.f)) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {  // columns P, Q of W  (applyOnTheRight(p, q, j_right))
+      const float x = W[i * 3 + P], y = W[i * 3 + Q];
+      W[i * 3 + P] = jrt.c * x + jrt.s * y;
+      W[i * 3 + Q] = -jrt.s * x + jrt.c * y;
+    }
+  }
+  maxDiag = fmaxf(maxDiag, fmaxf(fabsf(W[P * 3 + P]), fabsf(W[Q * 3 + Q])));
+}
+
+template <int I, int J>
+__device__ __forceinline__ void swap_cols(float (&U)[9], float (&sv)[3]) {
+  const float ts = sv[I]; sv[I] = sv[J]; sv[J] = ts;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) { const float tu = U[r * 3 + I]; U[r * 3 + I] = U[r * 3 + J]; U[r * 3 + J] = tu; }
+}
+
+__device__ __forceinline__ void jacobi_svd3(const float (&A)[9], float (&U)[9], float (&sv)[3]) {
   float scale = 0.f;
+#pragma unroll
   for (int i = 0; i < 9; ++i) scale = fmaxf(scale, fabsf(A[i]));
+#pragma unroll
   for (int i = 0; i < 9; ++i) U[i] = (i % 4 == 0) ? 1.f : 0.f;
   if (!isfinite(scale)) { sv[0] = sv[1] = sv[2] = NAN; return; }
   if (scale == 0.f) scale = 1.f;
   float W[9];
+#pragma unroll
   for (int i = 0; i < 9; ++i) W[i] = __fdiv_rn(A[i], scale);
   float maxDiag = fmaxf(fabsf(W[0]), fmaxf(fabsf(W[4]), fabsf(W[8])));
   bool finished = false;
+#pragma unroll 1
   for (int guard = 0; !finished && guard < 1000; ++guard) {
     finished = true;
-    for (int p = 1; p < 3; ++p)
-      for (int q = 0; q < p; ++q) {
-        const float thr = fmaxf(tiny, precision * maxDiag);
-        if (fabsf(W[p * 3 + q]) > thr || fabsf(W[q * 3 + p]) > thr) {
-          finished = false;
-          float mm[4] = {W[p * 3 + p], W[p * 3 + q], W[q * 3 + p], W[q * 3 + q]};
-          Rot rot1;
-          const float t = mm[0] + mm[3], d = mm[2] - mm[1];
-          if (fabsf(d) < tiny) { rot1.s = 0.f; rot1.c = 1.f; }
-          else {
-            const float u = __fdiv_rn(t, d);
-            const float tmp = __fsqrt_rn(1.f + u * u);
-            rot1.s = __fdiv_rn(1.f, tmp);
-            rot1.c = __fdiv_rn(u, tmp);
-          }
-          rot_plane(mm + 0, 1, mm + 2, 1, 2, rot1);
-          const Rot jr = make_jacobi(mm[0], mm[1], mm[3]);
-          const Rot jl = rot_mul(rot1, Rot{jr.c, -jr.s});
-          rot_plane(W + p * 3, 1, W + q * 3, 1, 3, jl);  // applyOnTheLeft(p,q,j_left)
-          rot_plane(U + p, 3, U + q, 3, 3, jl);          // U.applyOnTheRight(p,q,j_left^T)
-          rot_plane(W + p, 3, W + q, 3, 3, Rot{jr.c, -jr.s});  // applyOnTheRight(p,q,j_right)
-          maxDiag = fmaxf(maxDiag, fmaxf(fabsf(W[p * 3 + p]), fabsf(W[q * 3 + q])));
-        }
-      }
+    jacobi_pair<1, 0>(W, U, maxDiag, finished);  // sweep order p = 1..2, q < p
+    jacobi_pair<2, 0>(W, U, maxDiag, finished);
+    jacobi_pair<2, 1>(W, U, maxDiag, finished);
   }
+#pragma unroll
   for (int i = 0; i < 3; ++i) {
     const float a = W[i * 3 + i];
     sv[i] = fabsf(a);
-    if (a < 0.f) for (int r = 0; r < 3; ++r) U[r * 3 + i] = -U[r * 3 + i];
-  }
-  for (int i = 0; i < 3; ++i) sv[i] *= scale;
-  for (int i = 0; i < 3; ++i) {
-    int pos = 0;
-    float best = sv[i];
-    for (int k = i + 1; k < 3; ++k) if (sv[k] > best) { best = sv[k]; pos = k - i; }
-    if (best == 0.f) break;
-    if (pos) {
-      pos += i;
-      float ts = sv[i]; sv[i] = sv[pos]; sv[pos] = ts;
-      for (int r = 0; r < 3; ++r) { float tu = U[r * 3 + i]; U[r * 3 + i] = U[r * 3 + pos]; U[r * 3 + pos] = tu; }
+    if (a < 0.f) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) U[r * 3 + i] = -U[r * 3 + i];
     }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) sv[i] *= scale;
+  // selection sort, descending, swapping U columns (first maximum wins ties; stop at a zero maximum)
+  {
+    int pos = 0;
+    float best = sv[0];
+    if (sv[1] > best) { best = sv[1]; pos = 1; }
+    if (sv[2] > best) { best = sv[2]; pos = 2; }
+    if (best == 0.f) return;
+    if (pos == 1) swap_cols<0, 1>(U, sv);
+    else if (pos == 2) swap_cols<0, 2>(U, sv);
+  }
+  {
+    if (sv[2] > sv[1]) swap_cols<1, 2>(U, sv);   // (a zero maximum leaves equal zeros: no swap either way)
   }
 }
 

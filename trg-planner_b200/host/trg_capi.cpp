@@ -7,6 +7,7 @@
 #include <limits>
 #include <string>
 
+#include "map_io.h"
 #include "trg.h"
 #include "trg_b200.h"
 #include "trgb_kernels.h"
@@ -190,6 +191,65 @@ int trg_check_replan(void* h, float x, float y, const float* path_xyz, int n_pat
     std::vector<Eigen::Vector3f> path(n_path);
     for (int i = 0; i < n_path; ++i) path[i] = Eigen::Vector3f(path_xyz[3 * i], path_xyz[3 * i + 1], path_xyz[3 * i + 2]);
     return T(h)->checkReplan(p, path) ? 1 : 0;
+  });
+}
+
+int trg_load_params_yaml(const char* config_path, TrgParams* out, int* is_prebuilt_map, char* prebuilt_map_path,
+                         int path_cap, int* is_voxelize, float* voxel_size, int* is_update) {
+  return guard([&] {
+    const trg_b200::PlannerParams p = trg_b200::load_params_yaml(config_path);
+    if (out) {
+      // the nine arguments TRGPlanner::init passes to TRG::TRG (trg_planner.cpp:23-31)
+      *out = TrgParams{p.isVerbose ? 1 : 0, p.expandDist, p.robotSize, p.sampleNum, p.heightThreshold,
+                       p.collisionThreshold, p.updateCollisionThreshold, p.safetyFactor, p.goal_tolerance};
+    }
+    if (is_prebuilt_map) *is_prebuilt_map = p.isPreMap ? 1 : 0;
+    if (prebuilt_map_path && path_cap > 0) {
+      std::strncpy(prebuilt_map_path, p.preMapPath.c_str(), (size_t)path_cap - 1);
+      prebuilt_map_path[path_cap - 1] = 0;
+    }
+    if (is_voxelize) *is_voxelize = p.isVoxelize ? 1 : 0;
+    if (voxel_size) *voxel_size = p.VoxelSize;
+    if (is_update) *is_update = p.isUpdate ? 1 : 0;
+    return 0;
+  });
+}
+
+int trg_load_pcd(const char* path, float* xyz, int64_t cap_points, int64_t* n) {
+  return guard([&] {
+    const std::vector<float> v = trg_b200::load_pcd_xyz(path);
+    const int64_t np = (int64_t)v.size() / 3;
+    if (n) *n = np;
+    if (xyz) {
+      if (np > cap_points) throw std::runtime_error("trg_b200: PCD buffer too small");
+      std::memcpy(xyz, v.data(), v.size() * sizeof(float));
+    }
+    return 0;
+  });
+}
+
+int trg_save_pcd(const char* path, const float* xyz, int64_t n, int binary) {
+  return guard([&] { trg_b200::save_pcd_xyz(path, xyz, n, binary != 0); return 0; });
+}
+
+int trg_load_prebuilt_map(void* h, const char* pcd_path, int is_voxelize, float voxel_size, int64_t* n_raw, int64_t* n_map) {
+  return guard([&] {
+    std::vector<float> raw = trg_b200::load_pcd_xyz(pcd_path);
+    int64_t n = (int64_t)raw.size() / 3;
+    if (n_raw) *n_raw = n;
+    if (n == 0) throw std::runtime_error("trg_b200: empty prebuilt map");
+    if (is_voxelize) {
+      std::vector<float> out(raw.size());
+      int64_t nv = 0;
+      const int rc = trgb_voxel_filter(raw.data(), n, 3, voxel_size, out.data(), &nv);
+      if (rc != TRGB_OK && rc != TRGB_E_STATE) throw std::runtime_error(trgb_last_error());
+      out.resize((size_t)nv * 3);
+      raw.swap(out);
+      n = nv;
+    }
+    if (n_map) *n_map = n;
+    T(h)->setGlobalMapRaw(raw.data(), n, 3, false);
+    return 0;
   });
 }
 

@@ -73,6 +73,7 @@ def lib():
         L.trgb_graph_destroy.argtypes = [_vp]
         L.trgb_graph_destroy.restype = None
         L.trgb_sssp_batch.argtypes = [_vp, _vp, _vp, C.c_int64, C.c_float] + [_vp] * 6 + [C.c_int64]
+        L.trgb_voxel_filter.argtypes = [_vp, C.c_int64, C.c_int, C.c_float, _vp, C.POINTER(C.c_int64)]
         L.trgb_prof_enable.argtypes = [C.c_int]
         L.trgb_prof_collect.argtypes = [C.POINTER(ProfEntry), C.c_int]
         L.trgb_launch_count.restype = C.c_int64
@@ -114,6 +115,17 @@ def prof_collect() -> dict:
     n = lib().trgb_prof_collect(buf, 64)
     return {buf[i].name.decode(): dict(launches=buf[i].launches, ms=buf[i].total_ms, units=buf[i].units)
             for i in range(min(n, 64))}
+
+
+def voxel_filter(xyz: np.ndarray, leaf: float) -> np.ndarray:
+    """K8: pcl::VoxelGrid centroid filter on the device (trg_planner.cpp:90-94)."""
+    a = np.ascontiguousarray(xyz, np.float32)
+    out = np.empty((a.shape[0], 3), np.float32)
+    n = C.c_int64()
+    rc = lib().trgb_voxel_filter(_p(a), a.shape[0], a.shape[1], float(leaf), _p(out), C.byref(n))
+    if rc not in (0, -4):   # -4 = TRGB_E_STATE: leaf too small, cloud passed through (PCL does the same)
+        _chk(rc, "trgb_voxel_filter")
+    return out[: n.value].copy()
 
 
 class DeviceMap:
