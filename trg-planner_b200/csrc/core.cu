@@ -94,8 +94,10 @@ ProfScope::~ProfScope() {
   if (!start_) return;
   std::lock_guard<std::mutex> lk(g_pmx);
   cudaEventRecord(stop_, s_);
+  // No draining here: synchronising on events in the middle of a run would stall whichever host
+  // thread happens to launch next. Pending pairs are resolved by trgb_prof_collect / _reset; the
+  // event pool therefore grows to two events per launch of the profiled region and is recycled.
   g_pending.push_back({name_, start_, stop_, bytes_});
-  if (g_pending.size() >= 2048) drain_locked();
 }
 
 }  // namespace trgb
