@@ -222,3 +222,51 @@ def test_thread_path_overflow_falls_back(pkg, K):
                                   o.is_collision(q, P.collision_threshold))
     cnt = o.range_count(q, P.robot_size)
     assert cnt.max() > 500   # far above any per-thread column
+
+
+def test_edge_cases_empty_tiny_and_far(pkg, K):
+    """Empty batches, a one-point map, duplicate points (exact distance ties), queries far outside
+    the map, and a map far from the origin (float resolution ~1e-4 m at 1 km)."""
+    P = pkg.MOUNTAIN
+    pts = pkg.terrain.mountain(60, h=0.1, seed=4)
+    dm = K.DeviceMap(pts, 0.2)
+    e2 = np.zeros((0, 2), np.float32)
+    e3 = np.zeros((0, 3), np.float32)
+    assert dm.collision(e2, 0.3, 0.16, 0.1).shape == (0,)
+    assert dm.range_count(e2, 0.3).shape == (0,)
+    assert dm.nearest_z(e2)[0].shape == (0,)
+    assert dm.edge_eval(e3, e3, 0.3, 0.16, 0.1)["stage"].shape == (0,)
+    # far outside: empty cylinder => collision (trg.cpp:749-752); nearest still defined
+    far = np.array([[1e4, 1e4], [-500.0, 3.0], [3.0, 1e6]], np.float32)
+    o = pkg.oracle(P); o.set_global_map(pts)
+    np.testing.assert_array_equal(dm.collision(far, 0.3, 0.16, 0.1), [1, 1, 1])
+    np.testing.assert_array_equal(dm.range_count(far, 0.3), [0, 0, 0])
+    z, idx, tie = dm.nearest_z(far)
+    oz, oidx, otie = o.nearest_z(far)
+    np.testing.assert_array_equal(idx[tie == 0], oidx[tie == 0])
+    # one-point map
+    one = np.array([[1.0, 2.0, 3.0]], np.float32)
+    d1 = K.DeviceMap(one, 0.2)
+    q = np.array([[1.0, 2.0], [1.2, 2.0], [1.31, 2.0], [50.0, 50.0]], np.float32)
+    np.testing.assert_array_equal(d1.range_count(q, 0.3), [1, 1, 0, 0])
+    np.testing.assert_array_equal(d1.collision(q, 0.3, 0.16, 0.1), [0, 0, 1, 1])   # 1 point: ratio 0
+    np.testing.assert_array_equal(d1.nearest_z(q)[0], [3.0, 3.0, 3.0, 3.0])
+    # duplicates: every point twice -> nearest-z ties flagged, collision / counts still exact
+    dup = np.concatenate([pts, pts + np.float32([0, 0, 0.5])])
+    dd = K.DeviceMap(dup, 0.2)
+    od = pkg.oracle(P); od.set_global_map(dup)
+    qq = _queries(pts, 20_000, 31)
+    np.testing.assert_array_equal(dd.range_count(qq, 0.3), od.range_count(qq, 0.3))
+    np.testing.assert_array_equal(dd.collision(qq, 0.3, 0.16, 0.1), od.is_collision(qq, 0.1))
+    assert dd.nearest_z(qq)[2].all()     # every nearest is an exact tie between the two copies
+    # map 1 km from the origin
+    shifted = pts + np.float32([1000.0, -2000.0, 50.0])
+    ds = K.DeviceMap(shifted, 0.2)
+    os_ = pkg.oracle(P); os_.set_global_map(shifted)
+    qs = _queries(shifted, 50_000, 32)
+    np.testing.assert_array_equal(ds.collision(qs, 0.3, 0.16, 0.1), os_.is_collision(qs, 0.1))
+    np.testing.assert_array_equal(ds.range_count(qs, 0.3), os_.range_count(qs, 0.3))
+    with pytest.raises(RuntimeError):
+        K.DeviceMap(np.zeros((0, 3), np.float32), 0.2)
+    with pytest.raises(RuntimeError):
+        K.DeviceMap(np.array([[np.nan, 0, 0]], np.float32), 0.2)
