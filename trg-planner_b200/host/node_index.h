@@ -13,11 +13,26 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <future>
+#include <thread>
 #include <limits>
 #include <vector>
 
 namespace trg_b200 {
+
+// Helper threads a burst of host work may use: the cores of the box shared between the ranks
+// of a multi-GPU run (torchrun exports LOCAL_WORLD_SIZE), capped at 8.
+inline int thread_budget() {
+  static const int budget = [] {
+    int hw = static_cast<int>(std::thread::hardware_concurrency());
+    if (hw <= 0) hw = 4;
+    int ranks = 1;
+    if (const char* e = std::getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, std::atoi(e));
+    return std::max(1, std::min(8, (hw - 2 * ranks) / ranks));  // two pipeline threads per rank are always busy
+  }();
+  return budget;
+}
 
 class OrderTree2D {
  public:
@@ -147,7 +162,7 @@ class OrderTree2D {
       if (nh) hi_[root] = idx[j.b + 1 + nl];
       const int lb = j.b + 1, le = j.b + 1 + nl, hb = le, he = j.e, nd = j.depth + 1;
       if (nh) {
-        if (j.depth < 5 && nh > 8192 && nl > 8192)
+        if ((1 << j.depth) < thread_budget() && nh > 8192 && nl > 8192)
           helpers.push_back(std::async(std::launch::async, [=] { build_range(x, y, idx, tmp, hb, he, nax, nd); }));
         else
           jobs.push_back({hb, he, nax, nd});

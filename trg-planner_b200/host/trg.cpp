@@ -1377,7 +1377,7 @@ void TRG::cleanGraph(bool updateLocal) {  // trg.cpp:491-535
     }
   };
   const size_t nk = kept.size();
-  const size_t nthreads = nk > 50000 ? std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+  const size_t nthreads = nk > 50000 ? (size_t)trg_b200::thread_budget() : 1;
   if (nthreads <= 1) {
     rewrite(0, nk);
   } else {
@@ -1488,7 +1488,7 @@ void TRG::ensureDeviceGraph() {
       }
     }
   };
-  const int nthreads = n > 50000 ? (int)std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+  const int nthreads = n > 50000 ? trg_b200::thread_budget() : 1;
   if (nthreads <= 1) {
     fill(0, n);
   } else {
