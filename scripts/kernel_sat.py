@@ -18,7 +18,10 @@ ap.add_argument("--radius", type=float, default=0.3)
 ap.add_argument("--warp", action="store_true")
 ap.add_argument("--cell", type=float, default=0.5, help="map cell as a multiple of robot_size")
 ap.add_argument("--sorted", action="store_true", help="sort queries by cell (spatially coherent threads)")
+ap.add_argument("--lib", default=None, help="time a build variant of the kernel library (scripts/build_variants.sh)")
 a = ap.parse_args()
+if a.lib:
+    K.KERNEL_LIB = Path(a.lib).resolve()
 import torch
 P = trg.MOUNTAIN
 pts = trg.terrain.mountain(a.side, h=0.1, seed=2)
@@ -37,8 +40,8 @@ p2 = (q[:a.ne] + P.expand_dist * np.stack([np.cos(ang), np.sin(ang)], 1)).astype
 dq, dp1, dp2 = torch.from_numpy(q).cuda(), torch.from_numpy(p1).cuda(), torch.from_numpy(p2).cuda()
 out8 = torch.empty(a.nq, dtype=torch.uint8, device="cuda")
 st8 = torch.empty(a.ne, dtype=torch.uint8, device="cuda")
-w = torch.empty(a.ne, dtype=torch.float32, device="cuda")
-dd = torch.empty(a.ne, dtype=torch.float32, device="cuda")
+w = torch.zeros(a.ne, dtype=torch.float32, device="cuda")
+dd = torch.zeros(a.ne, dtype=torch.float32, device="cuda")
 torch.cuda.synchronize()
 for rep in range(a.reps + 1):
     if rep == 1:
@@ -54,4 +57,6 @@ for k, v in pr.items():
     per = 16 * np.pi * a.radius ** 2 * rho + 9 if "collision" in k else 16 * (4 * np.pi * 0.09 * rho + np.pi * 0.18 * rho) + 41
     print(json.dumps(dict(kernel=k, launches=v["launches"], avg_ms=round(v["ms"] / v["launches"], 4), units_per_s=round(ups),
                           alg_gbs=round(ups * per / 1e9, 1), frac_hbm=round(ups * per / 1e9 / 6551.7, 4))))
-print("collision rate", float(out8.float().mean()), "edge ok", float((st8 == 0).float().mean()))
+import hashlib
+sig = hashlib.sha1(out8.cpu().numpy().tobytes() + st8.cpu().numpy().tobytes() + w.cpu().numpy().tobytes()).hexdigest()[:16]
+print("collision rate", float(out8.float().mean()), "edge ok", float((st8 == 0).float().mean()), "sha1", sig, "lib", a.lib)

@@ -224,6 +224,33 @@ def test_thread_path_overflow_falls_back(pkg, K):
     assert cnt.max() > 500   # far above any per-thread column
 
 
+def test_thread_path_dense_map_long_columns(pkg, K):
+    """h = 0.085 m: ~39 points per cylinder, so most warps take the 64-value selection network,
+    columns run close to their capacity (the per-group overflow check) and some overflow into the
+    warp fallback; cell sizes on both sides of the register-held row count of the gather."""
+    P = pkg.MOUNTAIN
+    pts = pkg.terrain.mountain(170, h=0.085, seed=6)
+    rng = np.random.default_rng(33)
+    patch = rng.uniform(5.0, 8.0, size=(750, 2))       # +60 % density on 9 m^2: columns of 55 - 70 values
+    pts = np.concatenate([pts, np.column_stack([patch, rng.normal(3.0, 0.05, 750)]).astype(np.float32)])
+    o = pkg.oracle(P)
+    o.set_global_map(pts)
+    q = np.concatenate([_queries(pts, 50_000, 31), rng.uniform(4.5, 8.5, size=(10_000, 2)).astype(np.float32)])
+    want = o.is_collision(q, P.collision_threshold)
+    cnt = o.range_count(q, P.robot_size)
+    assert 33 < np.median(cnt) < 48 and (cnt > 64).sum() > 100 and ((cnt > 56) & (cnt <= 64)).sum() > 100
+    for cell in (0.4, 0.67, 1.0):
+        dm = K.DeviceMap(pts, cell * P.robot_size)
+        np.testing.assert_array_equal(dm.collision(q, P.robot_size, P.height_threshold, P.collision_threshold), want)
+    p1, p2 = _edge_pairs(pts, o, 20_000, 32, P.expand_dist)
+    a, b = K.DeviceMap(pts, 0.67 * P.robot_size), K.DeviceMap(pts, 0.67 * P.robot_size)
+    b.set_option("force_warp_path", 1)
+    ea = a.edge_eval(p1, p2, P.robot_size, P.height_threshold, P.collision_threshold)
+    eb = b.edge_eval(p1, p2, P.robot_size, P.height_threshold, P.collision_threshold)
+    for k in ("stage", "dist", "npts"):
+        np.testing.assert_array_equal(ea[k], eb[k])
+
+
 def test_edge_cases_empty_tiny_and_far(pkg, K):
     """Empty batches, a one-point map, duplicate points (exact distance ties), queries far outside
     the map, and a map far from the origin (float resolution ~1e-4 m at 1 km)."""

@@ -162,3 +162,38 @@ def test_stitch_tiles_gloo_world2(pkg):
     assert (ev["stage"] == 0).all()
     np.testing.assert_allclose(ev["weight"], e0[:, 4], rtol=1e-6)
     np.testing.assert_allclose(ev["dist"], e0[:, 5], rtol=1e-6)
+
+
+def test_stitch_tiles_gloo_world3_middle_tile_has_two_borders(pkg):
+    """N >= 3: the middle rank shares a border with both neighbours (what N = 4 / 8 runs look like)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world = 3
+    port = 29900 + (os.getpid() % 90)
+    procs = [ctx.Process(target=_stitch_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(world):
+        r = q.get(timeout=400)
+        res[r[0]] = r
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    e = res[0][1]
+    for r in range(1, world):
+        np.testing.assert_array_equal(e, res[r][1])
+    assert res[1][2]["stitched_edges_total"] == len(e)
+    # edges only between x-adjacent tiles, and both borders are stitched
+    assert (e[:, 2] == e[:, 0] + 1).all()
+    for left in (0, 1):
+        sel = e[e[:, 0] == left]
+        assert len(sel) > 10
+        border = 14.0 * (left + 1)
+        pl = {int(i): p for i, p in zip(res[left][4], res[left][3])}
+        pr = {int(i): p for i, p in zip(res[left + 1][4], res[left + 1][3])}
+        a = np.array([pl[int(v[1])] for v in sel], np.float32)
+        b = np.array([pr[int(v[3])] for v in sel], np.float32)
+        assert (np.hypot(a[:, 0] - b[:, 0], a[:, 1] - b[:, 1]) < pkg.MOUNTAIN.expand_dist + 1e-6).all()
+        assert (np.abs(a[:, 0] - border) < 1.0).all() and (np.abs(b[:, 0] - border) < 1.0).all()

@@ -85,6 +85,12 @@ __device__ __forceinline__ unsigned lanemask_lt() {
 }
 
 __device__ __forceinline__ float4 ld_pt(const float4* p) { return __ldg(p); }
+// two consecutive points with one 256-bit load (sm_100: LDG.E.ENL2.256); p must be 32-byte aligned
+__device__ __forceinline__ void ld_pt2(const float4* p, float4& a, float4& b) {
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+      : "l"(p));
+}
 
 // order-preserving float -> uint key (ascending)
 __device__ __forceinline__ uint32_t fkey(float f) {
@@ -326,7 +332,31 @@ __device__ __forceinline__ bool warp_is_collision(const MapView& m, float qx, fl
 // Returns 0 / 1, or 2 when the cylinder holds more than kTqCap points (the caller falls back to
 // the warp-cooperative routine, which needs no storage).
 // ------------------------------------------------------------------------------------------
-constexpr int kTqCap = 64;  // per-thread column length (floats)
+// Build-time knobs of the thread-per-query kernels (scripts/build_variants.sh sweeps them on the GPU;
+// the defaults are the measured optimum, see profiles/README.md).
+#ifndef TQ_CAP
+#define TQ_CAP 64
+#endif
+#ifndef TQ_FLAT
+#define TQ_FLAT 1
+#endif
+#ifndef TQ_LD256
+#define TQ_LD256 1  // 256-bit point loads (two points each) in the grouped gather
+#endif
+#ifndef TQ_UNROLL
+#define TQ_UNROLL 2  // groups of four loads in flight per thread
+#endif
+#ifndef TQ_MINBLK
+#define TQ_MINBLK 6  // resident CTAs per SM asked of ptxas (80 registers; 0 = its own heuristic)
+#endif
+#if TQ_MINBLK > 0
+#define TQ_BOUNDS __launch_bounds__(128, TQ_MINBLK)
+#else
+#define TQ_BOUNDS __launch_bounds__(128)
+#endif
+#define TQ_PRAGMA_(x) _Pragma(#x)
+#define TQ_PRAGMA_UNROLL(n) TQ_PRAGMA_(unroll n)
+constexpr int kTqCap = TQ_CAP;  // per-thread column length (floats)
 
 template <int N>
 __device__ __forceinline__ void bitonic_sort_regs(float (&a)[N]) {
@@ -349,19 +379,30 @@ __device__ __forceinline__ void bitonic_sort_regs(float (&a)[N]) {
 
 template <int N>
 __device__ __forceinline__ int median_outlier_count(const float* zcol, int stride, int n, float hthr) {
+  // The n values are padded to N with -inf / +inf alternating from index n on: ceil((N-n)/2) pads
+  // sort below the data and floor((N-n)/2) above it, which puts the upper median (rank n/2 of the
+  // data, :764) at index N/2 of the sorted array whatever n is. Only that one output is read, so
+  // the compiler prunes the last merge of the network to the 31 (N = 32) half compare-exchanges
+  // that feed it - a selection network - and the outliers are counted over the column itself.
+  const float pad_even = (n & 1) ? INFINITY : -INFINITY;  // pad at an even index k >= n
+  const float pad_odd = -pad_even;
   float a[N];
 #pragma unroll
-  for (int k = 0; k < N; ++k) a[k] = (k < n) ? zcol[k * stride] : INFINITY;
+  for (int k = 0; k < N; ++k) a[k] = (k < n) ? zcol[k * stride] : ((k & 1) ? pad_odd : pad_even);
   bitonic_sort_regs<N>(a);
-  const int mid = n >> 1;  // :764 upper median
-  float zmed = 0.f;
-#pragma unroll
-  for (int k = 0; k < N; ++k) zmed = (k == mid) ? a[k] : zmed;
+  const float zmed = a[N / 2];
   int cnt = 0;
 #pragma unroll
-  for (int k = 0; k < N; ++k) cnt += (k < n && fabsf(__fsub_rn(a[k], zmed)) > hthr);
+  for (int k = 0; k < N; ++k) cnt += (k < n && fabsf(__fsub_rn(zcol[k * stride], zmed)) > hthr);
   return cnt;
 }
+
+// kTqRows: grid rows the flattened gather below holds in registers. A radius-r disc spans
+// floor(2 rr / cell) + 1 or + 2 rows; the map is built with cell ~ 0.67 r, i.e. 4 - 5 rows.
+#ifndef TQ_ROWS
+#define TQ_ROWS 5
+#endif
+constexpr int kTqRows = TQ_ROWS;
 
 __device__ __forceinline__ int thread_is_collision(const MapView& m, float qx, float qy, float r, float hthr,
                                                    float rthr, float* zcol, int stride) {
@@ -372,22 +413,103 @@ __device__ __forceinline__ int thread_is_collision(const MapView& m, float qx, f
   const int cy0 = cell_coord(qy - rr, m.y0, m.inv_cell, m.H);
   const int cy1 = cell_coord(qy + rr, m.y0, m.inv_cell, m.H);
   int n = 0;
-  for (int row = cy0; row <= cy1; ++row) {
-    // only the chord of the (inflated) disc that this row of cells can contain: ~20 % fewer candidates
-    int ca, cb;
-    row_chord(m, qx, qy, rr, row, cx0, cx1, &ca, &cb);
-    if (ca > cb) continue;
-    const size_t b = (size_t)row * (size_t)m.W;
-    const uint32_t s = __ldg(m.cell_start + b + ca);
-    const uint32_t e = __ldg(m.cell_start + b + cb + 1);
+  if (TQ_FLAT && cy1 - cy0 < kTqRows) {
+    // Flattened gather: the rows' runs (only the chord of the inflated disc each row of cells can
+    // contain: ~20 % fewer candidates) are located first - all cell_start loads in flight at once -
+    // and then walked as ONE loop over groups of four consecutive points starting at an even index
+    // (a group may cover one point before its run and up to three behind it - masked; the point
+    // array is padded), fetched with two 256-bit loads: the kernel is bound by L1 tag look-ups, one
+    // per distinct line a warp-wide load touches, and wide loads halve their number. Lanes of
+    // a warp differ in how their candidates split over rows but hardly in the total, so the loop
+    // runs with most lanes active, where a loop per row idles every lane whose run is shorter than
+    // the longest one in the warp. Group g belongs to the row k whose cumulative group count first
+    // exceeds g and starts at pts[gb[k] + 4 g]; one address per group and a
+    // branch-free body (predicated stores at a running column offset).
+    uint32_t gb[kTqRows], gs[kTqRows], ge[kTqRows], gc[kTqRows];
+    uint32_t totg = 0;
+    const float slack = 1e-3f * m.cell + 4e-6f * (fabsf(qy) + fabsf(m.y0));
+#pragma unroll
+    for (int k = 0; k < kTqRows; ++k) {
+      const int row = cy0 + k;
+      // row_chord() without its branches: same conservative band and chord (the approximate
+      // square root is off by ~1e-7 relative, the chord is widened by 1e-4), clamped to the
+      // query's cell block, and an empty span for rows past cy1 or outside the disc
+      const float ylo = m.y0 + (float)row * m.cell - slack;
+      const float yhi = m.y0 + (float)(row + 1) * m.cell + slack;
+      const float dy = fmaxf(0.f, fmaxf(ylo - qy, qy - yhi));
+      const float h2 = rr * rr - dy * dy;
+      float half;
+      asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(half) : "f"(fmaxf(h2, 0.f)));
+      half = half * 1.0001f + 1e-6f;
+      const int ca = max(cx0, min(m.W - 1, __float2int_rd(__fmul_rn(__fsub_rn(qx - half, m.x0), m.inv_cell))));
+      const int cb = min(cx1, max(0, __float2int_rd(__fmul_rn(__fsub_rn(qx + half, m.x0), m.inv_cell))));
+      const bool any = row <= cy1 && h2 > 0.f && ca <= cb;
+      const uint32_t* cs = m.cell_start + (size_t)min(row, cy1) * (size_t)m.W;
+      const uint32_t s = any ? __ldg(cs + ca) : 0u;
+      const uint32_t e = any ? __ldg(cs + cb + 1) : 0u;
+      const uint32_t sa = TQ_LD256 ? s & ~1u : s;  // groups start at even indices: 32-byte aligned
+      gb[k] = sa - 4u * totg;
+      gs[k] = s;
+      ge[k] = e;
+      totg += e > s ? (e - sa + 3u) >> 2 : 0u;
+      gc[k] = totg;
+    }
+    int wo = 0;                                // column offset of the next store (floats)
+    const int wlim = (kTqCap - 4) * stride;    // checked once per group: at most 4 stores past it
+    bool ovf = false;
+    TQ_PRAGMA_UNROLL(TQ_UNROLL)
+    for (uint32_t g = 0; g < totg; ++g) {
+      uint32_t b = gb[0], lo = gs[0], e = ge[0];
+#pragma unroll
+      for (int k = 1; k < kTqRows; ++k) {
+        const bool in = g >= gc[k - 1];
+        b = in ? gb[k] : b;
+        lo = in ? gs[k] : lo;
+        e = in ? ge[k] : e;
+      }
+      const uint32_t i0 = b + 4u * g;  // >= lo - 1; only slot 0 can lie before the run, slots 1..3 behind it
+      float4 p0, p1, p2, p3;
+      if (TQ_LD256) {
+        ld_pt2(m.pts + i0, p0, p1);
+        ld_pt2(m.pts + i0 + 2, p2, p3);
+      } else {
+        p0 = ld_pt(m.pts + i0), p1 = ld_pt(m.pts + i0 + 1), p2 = ld_pt(m.pts + i0 + 2), p3 = ld_pt(m.pts + i0 + 3);
+      }
+#define TQ_CAND(P, U)                                                              \
+      {                                                                            \
+        const float dx = __fsub_rn(P.x, qx), dy = __fsub_rn(P.y, qy);              \
+        const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));          \
+        if (d2 <= r2 && (U == 0 ? i0 >= lo : i0 + U < e)) {                        \
+          zcol[wo] = P.z;                                                          \
+          wo += stride;                                                            \
+        }                                                                          \
+      }
+      TQ_CAND(p0, 0) TQ_CAND(p1, 1) TQ_CAND(p2, 2) TQ_CAND(p3, 3)
+#undef TQ_CAND
+      // (no early exit: a second way out of this loop keeps the warp from reconverging before the
+      //  sorting network below, which then runs once per distinct trip count)
+      ovf |= wo > wlim;
+      wo = min(wo, wlim);
+    }
+    if (ovf) return 2;  // the column overflowed: the caller's fallback needs no storage
+    n = wo / stride;
+  } else {
+    for (int row = cy0; row <= cy1; ++row) {
+      int ca, cb;
+      row_chord(m, qx, qy, rr, row, cx0, cx1, &ca, &cb);
+      if (ca > cb) continue;
+      const size_t b = (size_t)row * (size_t)m.W;
+      const uint32_t s = __ldg(m.cell_start + b + ca);
+      const uint32_t e = __ldg(m.cell_start + b + cb + 1);
 #pragma unroll 4
-    for (uint32_t i = s; i < e; ++i) {
-      const float4 p = ld_pt(m.pts + i);
-      const float dx = __fsub_rn(p.x, qx), dy = __fsub_rn(p.y, qy);
-      const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-      if (d2 <= r2) {
-        if (n < kTqCap) zcol[n * stride] = p.z;
-        ++n;
+      for (uint32_t i = s; i < e; ++i) {
+        const float4 p = ld_pt(m.pts + i);
+        const float dx = __fsub_rn(p.x, qx), dy = __fsub_rn(p.y, qy);
+        const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        if (d2 <= r2) {
+          if (n < kTqCap) zcol[n * stride] = p.z;
+          ++n;
+        }
       }
     }
   }
@@ -409,6 +531,7 @@ constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
 // thread-per-query kernels: 128 threads per CTA, one shared z column per thread
 constexpr int kTqThreads = 128;
+constexpr int kPtsPad = 4;  // float4 slots allocated (zeroed) behind the sorted points of a map
 void tune_mempool_once();  // raise the default mempool's release threshold (map_index.cu)
 int sm_count();
 int grid_for_warps(int64_t n_warps, int ctas_per_sm);

@@ -263,8 +263,11 @@ static int build_index(trgb_map* m, const float* d_in, int64_t n, int stride, fl
   TRGB_CUDA(cudaMallocAsync((void**)&d_fill, ncells * sizeof(uint32_t), st));
   TRGB_CUDA(cudaMallocAsync((void**)&d_sums, (size_t)std::max(nb, 1) * sizeof(uint32_t), st));
   TRGB_CUDA(cudaMallocAsync((void**)&m->d_cell_start, (ncells + 1) * sizeof(uint32_t), st));
-  TRGB_CUDA(cudaMallocAsync((void**)&m->d_pts, (size_t)n * sizeof(float4), st));
-  m->device_bytes = (ncells + 1) * (int64_t)sizeof(uint32_t) + n * (int64_t)sizeof(float4);
+  // kPtsPad zeroed points behind the last one: the grouped gather of the thread-per-query kernels
+  // reads whole groups of four and masks what lies beyond a run (common.cuh)
+  TRGB_CUDA(cudaMallocAsync((void**)&m->d_pts, ((size_t)n + kPtsPad) * sizeof(float4), st));
+  TRGB_CUDA(cudaMemsetAsync(m->d_pts + n, 0, kPtsPad * sizeof(float4), st));
+  m->device_bytes = (ncells + 1) * (int64_t)sizeof(uint32_t) + (n + kPtsPad) * (int64_t)sizeof(float4);
   TRGB_CUDA(cudaMemsetAsync(d_counts, 0, ncells * sizeof(uint32_t), st));
   TRGB_CUDA(cudaMemsetAsync(d_fill, 0, ncells * sizeof(uint32_t), st));
   {

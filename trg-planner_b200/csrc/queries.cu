@@ -436,7 +436,14 @@ __global__ void __launch_bounds__(kThreads) k_edge_eval(MapView m, const float* 
     __syncthreads();    \
   }
 
-__global__ void __launch_bounds__(kTqThreads) k_collision_tq(MapView m, const float2* __restrict__ q, int64_t n,
+// item index -> (owner, slot): the emulated 64-bit division costs ~100 instructions per thread;
+// every batch the builder launches fits 32 bits (uniform branch)
+__device__ __forceinline__ int64_t idiv_items(int64_t it, int per, int64_t items) {
+  if (items < (1ll << 31)) return (int64_t)((uint32_t)it / (uint32_t)per);
+  return it / per;
+}
+
+__global__ void TQ_BOUNDS k_collision_tq(MapView m, const float2* __restrict__ q, int64_t n,
                                                              float r, float hthr, float rthr, int cap,
                                                              uint8_t* __restrict__ out) {
   extern __shared__ float zsm[];
@@ -460,7 +467,7 @@ __global__ void __launch_bounds__(kTqThreads) k_collision_tq(MapView m, const fl
 }
 
 // one thread per (node, draw); bit j of mask[node] = isCollision(node + draw[first+j])
-__global__ void __launch_bounds__(kTqThreads) k_sample_window_tq(
+__global__ void TQ_BOUNDS k_sample_window_tq(
     MapView m, const float2* __restrict__ node_xy, const int32_t* __restrict__ first_draw,
     const float2* __restrict__ draw_xy, int64_t n_nodes, int window, float r, float hthr, float rthr,
     int cap, unsigned long long* __restrict__ mask) {
@@ -476,7 +483,7 @@ __global__ void __launch_bounds__(kTqThreads) k_sample_window_tq(
     int64_t node = 0;
     int j = 0;
     if (it < items) {
-      node = it / window;
+      node = idiv_items(it, window, items);
       j = (int)(it - node * window);
       const float2 np = __ldg(node_xy + node);
       const float2 d = __ldg(draw_xy + (__ldg(first_draw + node) + j));
@@ -619,7 +626,7 @@ __global__ void __launch_bounds__(kTqThreads) k_sample_window_sm(
 //     (zeroed by the launcher). kmax = samples needed by the longest edge of the batch.
 // (b) k_edge_pca<L>: L = 4 or 8 lanes per edge split the cell rows of the ellipse gather, combine
 //     their covariance sums and run the Jacobi SVD; edges already marked colliding are skipped.
-__global__ void __launch_bounds__(kTqThreads) k_edge_collide_tq(MapView m, const float* __restrict__ p1_xyz,
+__global__ void TQ_BOUNDS k_edge_collide_tq(MapView m, const float* __restrict__ p1_xyz,
                                                                 const float2* __restrict__ p2_xy, int64_t n, int kmax,
                                                                 float rs, float hthr, float cthr, int cap,
                                                                 uint8_t* __restrict__ stage,
@@ -636,7 +643,7 @@ __global__ void __launch_bounds__(kTqThreads) k_edge_collide_tq(MapView m, const
     int64_t e = 0;
     bool live = it < items;
     if (live) {
-      e = it / kmax;
+      e = idiv_items(it, kmax, items);
       if (e < n_skip && __fsqrt_rn(__ldg(skip_d2 + e)) < skip_below) live = false;  // speculation filter
     }
     if (live) {
