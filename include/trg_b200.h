@@ -91,7 +91,7 @@ void* trg_device_map(void* h, const char* type);
 
 double  trg_last_seconds(void* h, const char* what);
 int64_t trg_stat(void* h, const char* what);
-int     trg_set_tuning(void* h, const char* key, double value);  /* "chunk_nodes" | "window" | "map_cell_scale" */
+int     trg_set_tuning(void* h, const char* key, double value);  /* "chunk_nodes" | "window" | "lookahead" | "map_cell_scale" | "table_cell_scale" | "overlap" | "split_commit" */
 
 #ifdef __cplusplus
 }

@@ -15,10 +15,15 @@ ap.add_argument("--queries", type=int, default=1000)
 ap.add_argument("--chunk", type=int, default=0)
 ap.add_argument("--window", type=int, default=0)
 ap.add_argument("--cell", type=float, default=0)
+ap.add_argument("--tcell", type=float, default=0)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--reuse", action="store_true")
 ap.add_argument("--noq", action="store_true")
+ap.add_argument("--lib", default=None, help="host library variant (e.g. built with -DTRG_FINE_TIMERS)")
 a = ap.parse_args()
+if a.lib:
+    from trg_planner_b200 import binding as _b
+    _b.PRODUCT_LIB = Path(a.lib).resolve()
 P = trg.MOUNTAIN if a.kind == "mountain" else trg.INDOOR
 t0 = time.time()
 pts = trg.terrain.mountain(a.n, h=a.h, seed=2) if a.kind == "mountain" else trg.terrain.indoor(a.n, h=a.h, seed=1)
@@ -33,6 +38,7 @@ for rep in range(a.reps):
     if a.chunk: t.set_tuning("chunk_nodes", a.chunk)
     if a.window: t.set_tuning("window", a.window)
     if a.cell: t.set_tuning("map_cell_scale", a.cell)
+    if a.tcell: t.set_tuning("table_cell_scale", a.tcell)
     t.seed(42)
     K.prof_reset(); K.prof_enable(True)
     w0 = time.time(); t.set_global_map(pts); w1 = time.time()
@@ -43,7 +49,7 @@ for rep in range(a.reps):
     prof = K.prof_collect(); K.prof_enable(False)
     stats = {k: t.stat(k) for k in ("pops", "rng_draws", "window_launches", "eval_launches", "flush_launches", "stalls",
                                     "window_tests", "edge_evals", "nearest_map", "batches", "node_ties", "z_ties",
-                                    "us_sample", "us_eval", "us_commit", "us_draws", "us_clean", "cyc_nearest", "cyc_wire", "cyc_newnode", "us_w_draws", "us_w_prep", "us_w_gpu")}
+                                    "us_sample", "us_eval", "us_commit", "us_draws", "us_clean", "cyc_nearest", "cyc_wire", "cyc_newnode", "cyc_nn_a", "cyc_nn_b", "cyc_nn_c", "cyc_pre", "cyc_alloc", "cyc_umap", "cyc_index", "cyc_table", "us_w_draws", "us_w_prep", "us_w_gpu")}
     print(json.dumps(dict(rep=rep, map_s=round(w1 - w0, 4), init_s=round(w2 - w1, 4), plan_s=round(w3 - w2, 4),
                           snap_s=round(t.seconds("plan_snap"), 4), nodes=nn, edges=ne, found=int(r["found"].sum()),
                           pts_per_s=round(pts.shape[0] / (w2 - w0)), nodes_per_s=round(nn / (w2 - w0)),

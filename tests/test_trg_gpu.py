@@ -62,7 +62,7 @@ def test_init_graph_parity(pkg, K, which, prm, start, small_mountain, small_indo
 
 @pytest.mark.parametrize("tuning", [dict(chunk_nodes=1, window=8), dict(chunk_nodes=7, window=16),
                                     dict(chunk_nodes=100000, window=256), dict(map_cell_scale=1.0),
-                                    dict(overlap=0), dict(chunk_nodes=64, overlap=1)])
+                                    dict(overlap=0), dict(chunk_nodes=64, overlap=1), dict(parallel_min_nodes=0)])
 def test_init_graph_scheduler_invariance(pkg, K, tuning, small_indoor):
     """The wavefront scheduler's batching knobs must not change a single decision."""
     pts = small_indoor[: len(small_indoor)]
@@ -75,6 +75,7 @@ def test_overlapped_build_mountain(pkg, K, small_mountain):
     """Mountain parameters take the two-thread path (helper feeds batch k+1 while batch k commits):
     small batches force many hand-overs; the graph must not change."""
     for tuning in (dict(chunk_nodes=300, overlap=1), dict(chunk_nodes=300, overlap=0), dict(chunk_nodes=32, window=32),
+                   dict(parallel_min_nodes=0), dict(table_cell_scale=0.7), dict(table_cell_scale=4.0, chunk_nodes=200),
                    dict(split_commit=1), dict(split_commit=1, overlap=0), dict(chunk_nodes=50, split_commit=1, overlap=1)):
         t, o = build_pair(pkg, pkg.MOUNTAIN, small_mountain, (15.0, 15.0, 0.0), seed=9, tuning=tuning)
         assert t.stat("rng_draws") == o.stat("rng_draws")

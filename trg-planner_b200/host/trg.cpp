@@ -17,6 +17,7 @@
 #include <atomic>
 #include <exception>
 #include <functional>
+#include <future>
 #include <stdexcept>
 #include <thread>
 
@@ -568,8 +569,21 @@ class ChunkTable {
       for (const E& e : ent_) consider(e, qx, qy, d2, seq, tie);
       return;
     }
-    const int qcx = cc(qx, x0_), qcy = cc(qy, y0_);
     const float fuzz = 1e-5f + 4e-6f * (std::fabs(qx) + std::fabs(qy));
+    {
+      // the device candidate bounds the search: only cells the disc of radius sqrt(d2) touches
+      // (inflated so that a node at exactly the same distance is seen and flagged as a tie) -
+      // usually one or two cells instead of nine
+      const float reach = std::sqrt(d2) * 1.00001f + fuzz;
+      const int cx0 = cc(qx - reach, x0_), cx1 = cc(qx + reach, x0_);
+      const int cy0 = cc(qy - reach, y0_), cy1 = cc(qy + reach, y0_);
+      if ((cx1 - cx0 + 1) * (cy1 - cy0 + 1) <= 9) {
+        for (int yy = cy0; yy <= cy1; ++yy)
+          for (int xx = cx0; xx <= cx1; ++xx) scan(xx, yy, qx, qy, d2, seq, tie);
+        return;
+      }
+    }
+    const int qcx = cc(qx, x0_), qcy = cc(qy, y0_);
     for (int R = 1;; ++R) {
       if (R == 1) {
         for (int yy = qcy - 1; yy <= qcy + 1; ++yy)
@@ -591,8 +605,11 @@ class ChunkTable {
  private:
   struct E { float x, y; int seq; int32_t next; int cx, cy; };
   static constexpr uint32_t kMask = (1u << 14) - 1;
+  // toroidal 128 x 128 tile of cells: neighbouring cells are neighbouring buckets (the 2 x 2 block a
+  // query usually probes sits in two cache lines) and there is nothing to multiply; cells 128 apart
+  // share a bucket and are told apart by (cx, cy)
   static uint32_t hash(int cx, int cy) {
-    return (static_cast<uint32_t>(cx) * 73856093u ^ static_cast<uint32_t>(cy) * 19349663u) & kMask;
+    return ((static_cast<uint32_t>(cy) & 127u) << 7) | (static_cast<uint32_t>(cx) & 127u);
   }
   int cc(float v, float o) const { return static_cast<int>(std::floor((v - o) * inv_)); }
   static void consider(const E& e, float qx, float qy, float& d2, int& seq, bool& tie) {
@@ -711,9 +728,9 @@ class Expander {
       d.nodes_uploaded = 0;
     }
     handed_nodes_ = d.nodes_uploaded;
-    // samples sit expand_dist from their node, so their nearest node is never farther than that: with
-    // cells this wide the first 3x3 pass of ChunkTable::refine always settles the search
-    table_.configure(box[0], box[1], std::max(cell, 1.5f * P_.expand_dist));
+    // most samples have a device candidate within robot_size, so ChunkTable::refine probes the 1 - 4
+    // cells of this width that the candidate's disc touches (about one stored node each)
+    table_.configure(box[0], box[1], t_.tuning_.table_cell_scale * P_.robot_size);
   }
 
   // expandGraph(root) for every root, in order (trg.cpp:372-454 / :483-487).
@@ -790,6 +807,11 @@ class Expander {
     t_.stat_["cyc_nn_a"] += (int64_t)ft_nn_a;
     t_.stat_["cyc_nn_b"] += (int64_t)ft_nn_b;
     t_.stat_["cyc_nn_c"] += (int64_t)ft_nn_c;
+    t_.stat_["cyc_pre"] += (int64_t)ft_pre;
+    t_.stat_["cyc_alloc"] += (int64_t)ft_alloc;
+    t_.stat_["cyc_umap"] += (int64_t)ft_umap;
+    t_.stat_["cyc_index"] += (int64_t)ft_index;
+    t_.stat_["cyc_table"] += (int64_t)ft_table;
 #endif
   }
 
@@ -1222,6 +1244,7 @@ class Expander {
         FT_LAP(nn_c);
       }
       if (ex->state_ == TRG::NodeState::Invalid) continue;
+      FT_LAP(pre);
       if (norm2(ex->pos_.x() - s.x, ex->pos_.y() - s.y) < P_.robot_size) {
         push_op_({node, ex, 0.f, 0.f, 0});  // wireEdge(node, existing_node)
         FT_LAP(wire);
@@ -1231,10 +1254,15 @@ class Expander {
       if (b.stage[si] == TRGB_EDGE_SKIPPED) throw std::logic_error("trg_b200: speculation filter skipped a sample that became a node");
       if (b.tie[si]) ++n_zties_;
       Eigen::Vector2f pos2(s.x, s.y);
+      FT_LAP(pre);
       TRG::Node* nn = t_.newNode(g_.node_id, pos2, b.z[si], new_state);
+      FT_LAP(alloc);
       g_.nodes[g_.node_id] = nn;
+      FT_LAP(umap);
       t_.nodeIndexInsert(g_, nn);
+      FT_LAP(index);
       table_.insert(s.x, s.y, static_cast<int>(g_.node_seq.size()) - 1);
+      FT_LAP(table);
       g_.node_id++;
       // 2.1 wireEdge(node, new): slope gate on the host, geometry from the speculative batch
       bool parent_ok = false;
@@ -1266,6 +1294,7 @@ class Expander {
     }
   }
   FT_DECL(nearest); FT_DECL(wire); FT_DECL(newnode); FT_DECL(nn_a); FT_DECL(nn_b); FT_DECL(nn_c);
+  FT_DECL(pre); FT_DECL(alloc); FT_DECL(umap); FT_DECL(index); FT_DECL(table);
 
   ChunkTable table_;
   TRG& t_;
@@ -1349,16 +1378,37 @@ void TRG::cleanGraph(bool updateLocal) {  // trg.cpp:491-535
   std::vector<Node*> by_id((size_t)(max_id + 1), nullptr);
   std::vector<int>   old2new((size_t)(max_id + 1), -1);
   for (Node* n : g.node_seq) by_id[n->id_] = n;
-  // survivors get their new ids in the map's iteration order (:497-504)
-  std::vector<Node*> kept;
-  kept.reserve(g.nodes.size());
+  // survivors get their new ids in the map's iteration order (:497-504). The new map is keyed
+  // 0, 1, 2, ... in that order, so its insertions do not depend on which nodes survive: on large
+  // graphs a second thread builds it (same sequence of operator[] calls => same buckets, order and
+  // rehash history) while this one is still walking the old map and, later, rewriting edges.
+  std::vector<Node*> kept(g.nodes.size(), nullptr);
+  const bool piped = g.nodes.size() > (size_t)tuning_.parallel_min_nodes && trg_b200::thread_budget() > 1;
+  std::atomic<size_t> published{0};
+  std::atomic<bool>   walked{false};
+  std::future<void>   builder;
+  if (piped) {
+    builder = std::async(std::launch::async, [&] {
+      size_t k = 0;
+      for (;;) {
+        const size_t avail = published.load(std::memory_order_acquire);
+        for (; k < avail; ++k) new_nodes[(int)k] = kept[k];
+        if (walked.load(std::memory_order_acquire) && k == published.load(std::memory_order_acquire)) break;
+        if (k == avail) std::this_thread::yield();
+      }
+    });
+  }
   for (auto& node : g.nodes) {
     if (node.second->state_ == NodeState::Invalid || node.second->edges_.size() < 1) continue;
-    new_nodes[new_id]   = node.second;
+    if (!piped) new_nodes[new_id] = node.second;
     old2new[node.first] = new_id;
-    kept.push_back(node.second);
+    kept[new_id] = node.second;
     new_id++;
+    if (piped && (new_id & 1023) == 0) published.store((size_t)new_id, std::memory_order_release);
   }
+  published.store((size_t)new_id, std::memory_order_release);
+  walked.store(true, std::memory_order_release);
+  kept.resize((size_t)new_id);
   // The reference collects the ids of Invalid edge targets in a vector and std::find()s every edge
   // against it (:515); the same predicate is "target node is Invalid", evaluated directly here.
   // Edges are rewritten in place (same order, same values as the reference's fresh copies); nodes
@@ -1377,7 +1427,7 @@ void TRG::cleanGraph(bool updateLocal) {  // trg.cpp:491-535
     }
   };
   const size_t nk = kept.size();
-  const size_t nthreads = nk > 50000 ? (size_t)trg_b200::thread_budget() : 1;
+  const size_t nthreads = nk > (size_t)tuning_.parallel_min_nodes ? (size_t)trg_b200::thread_budget() : 1;
   if (nthreads <= 1) {
     rewrite(0, nk);
   } else {
@@ -1387,12 +1437,20 @@ void TRG::cleanGraph(bool updateLocal) {  // trg.cpp:491-535
     for (auto& j : jobs) j.get();
   }
   for (size_t k = 0; k < nk; ++k) kept[k]->id_ = (int)k;
+  if (piped) builder.get();
+  // the old map's half a million hash nodes are freed on the side (clear() would keep only its
+  // bucket array, which the assignment below replaces anyway)
+  std::unordered_map<int, Node*> old_nodes;
+  old_nodes.swap(g.nodes);
+  std::future<void> disposal;
+  if (piped) disposal = std::async(std::launch::async, [&old_nodes] { old_nodes.clear(); });
   this->resetGraph(g.type);
   // (the reference copy-assigns; a move leaves the same buckets, order and rehash state)
   g.nodes   = std::move(new_nodes);
   g.node_id = new_id;
   g.node_seq.reserve(g.nodes.size());
   for (auto& node : g.nodes) nodeIndexInsert(g, node.second);  // node_tree order = new map's iteration order (:528-530)
+  if (piped) disposal.get();
   invalidateDeviceGraph();
   if (updateLocal) this->setLocalGraph(false);
 }
@@ -1488,7 +1546,7 @@ void TRG::ensureDeviceGraph() {
       }
     }
   };
-  const int nthreads = n > 50000 ? trg_b200::thread_budget() : 1;
+  const int nthreads = n > tuning_.parallel_min_nodes ? trg_b200::thread_budget() : 1;
   if (nthreads <= 1) {
     fill(0, n);
   } else {

@@ -260,6 +260,8 @@ class TRG {
     int window = 128;         // sampling-window draws per node (<= 256)
     int lookahead = 768;      // queued pops needed before the next batch is fed ahead of the current commit
     float map_cell_scale = 0.67f;  // map index cell = map_cell_scale * robot_size (0.34..1.0 measured: 0.67-1.0 best)
+    float table_cell_scale = 2.0f; // cell of the host table of just-created nodes = table_cell_scale * robot_size
+    int parallel_min_nodes = 50000;  // graphs larger than this use helper threads in cleanGraph / CSR export
     bool overlap = true;      // run the device phases of batch k+1 on a helper thread while batch k commits
     bool split_commit = false;  // apply edge-list operations on a second thread while the first decides (measured slower on a 10 M-point map: cross-core traffic on the adjacency lists; kept for experiments)
   } tuning_;

@@ -315,6 +315,8 @@ int trg_set_tuning(void* h, const char* key, double value) {
     else if (k == "window") T(h)->tuning_.window = (int)value;
     else if (k == "lookahead") T(h)->tuning_.lookahead = (int)value;
     else if (k == "map_cell_scale") T(h)->tuning_.map_cell_scale = (float)value;
+    else if (k == "table_cell_scale") T(h)->tuning_.table_cell_scale = (float)value;
+    else if (k == "parallel_min_nodes") T(h)->tuning_.parallel_min_nodes = (int)value;
     else if (k == "overlap") T(h)->tuning_.overlap = value != 0;
     else if (k == "split_commit") T(h)->tuning_.split_commit = value != 0;
     else throw std::runtime_error("unknown tuning key " + k);
