@@ -123,6 +123,17 @@ extern "C" int trgb_set_device(int device) {
 extern "C" int trgb_prof_enable(int on) {
   std::lock_guard<std::mutex> lk(g_pmx);
   g_prof_on = on != 0;
+  // Pre-create the events of a few profiled 10 M-point builds (2 per launch, ~14 k launches each):
+  // creating them on demand put bursts of cudaEventCreate - and the driver's bookkeeping for tens
+  // of thousands of new timing events - inside the region being timed.
+  if (g_prof_on) {
+    constexpr size_t kPrefill = 1u << 17;
+    while (g_pool.size() + 2 * g_pending.size() < kPrefill) {
+      cudaEvent_t e = nullptr;
+      if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); break; }
+      g_pool.push_back(e);
+    }
+  }
   return TRGB_OK;
 }
 
