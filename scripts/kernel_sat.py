@@ -54,7 +54,16 @@ pr = K.prof_collect()
 rho = pts.shape[0] / (ext * ext)
 for k, v in pr.items():
     ups = v["units"] / v["ms"] * 1e3
-    per = 16 * np.pi * a.radius ** 2 * rho + 9 if "collision" in k else 16 * (4 * np.pi * 0.09 * rho + np.pi * 0.18 * rho) + 41
+    # algorithmic bytes per unit: K2 16 k(r) + 9; K4 split into its two kernels:
+    # collide 16 m k(r) + 21 with m = 4 segment samples, PCA 16 k(a) + 29 with a^2 = (e/2)^2 + r^2 = 0.18
+    if "edge_collide" in k:
+        per = 16 * 4 * np.pi * 0.09 * rho + 21
+    elif "edge_pca" in k:
+        per = 16 * np.pi * 0.18 * rho + 29
+    elif "edge_eval" in k:
+        per = 16 * (4 * np.pi * 0.09 * rho + np.pi * 0.18 * rho) + 41
+    else:
+        per = 16 * np.pi * a.radius ** 2 * rho + 9
     print(json.dumps(dict(kernel=k, launches=v["launches"], avg_ms=round(v["ms"] / v["launches"], 4), units_per_s=round(ups),
                           alg_gbs=round(ups * per / 1e9, 1), frac_hbm=round(ups * per / 1e9 / 6551.7, 4))))
 import hashlib

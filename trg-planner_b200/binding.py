@@ -150,7 +150,7 @@ class TrgFacade:
         ids = np.empty(n, np.int32)
         pos = np.empty((n, 3), np.float32)
         state = np.empty(n, np.int32)
-        row_ptr = np.empty(n + 1, np.int64)
+        row_ptr = np.empty(n + 1, np.int64) if edges else None
         col = np.empty(e, np.int32) if edges else None
         w = np.empty(e, np.float32) if edges else None
         d = np.empty(e, np.float32) if edges else None

@@ -118,6 +118,8 @@ class TRG {
 
   std::unordered_map<int, Node*> getGraph(std::string type = "global");
   std::unordered_map<int, Node*> getGraphCopy(std::string type = "global");
+  // [+] the same map by reference (no half-million-entry copy); the caller holds lockGraph()
+  const std::unordered_map<int, Node*>& getGraphRef(const std::string& type = "global") const { return trgMap_.at(type)->nodes; }
   void                           lockGraph();
   void                           unlockGraph();
 

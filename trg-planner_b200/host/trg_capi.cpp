@@ -75,12 +75,12 @@ int trg_update_graph(void* h) {
 int trg_graph_counts(void* h, const char* type, int64_t* n_nodes, int64_t* n_edges) {
   return guard([&] {
     T(h)->lockGraph();
-    auto g = T(h)->getGraph(type);
+    const auto& g = T(h)->getGraphRef(type);
     int64_t e = 0;
     for (auto& kv : g) e += (int64_t)kv.second->edges_.size();
-    T(h)->unlockGraph();
     *n_nodes = (int64_t)g.size();
     *n_edges = e;
+    T(h)->unlockGraph();
     return 0;
   });
 }
@@ -89,22 +89,25 @@ int trg_graph_export(void* h, const char* type, int32_t* iter_ids, int32_t* ids_
                      int32_t* state, int64_t* row_ptr, int32_t* col, float* weight, float* dist) {
   return guard([&] {
     T(h)->lockGraph();
-    auto g = T(h)->getGraph(type);
-    std::vector<int> ids;
+    const auto& g = T(h)->getGraphRef(type);
+    std::vector<std::pair<int, TRG::Node*>> ids;
+    ids.reserve(g.size());
     int64_t k = 0;
     for (auto& kv : g) {
       if (iter_ids) iter_ids[k] = kv.first;
-      ids.push_back(kv.first);
+      ids.emplace_back(kv.first, kv.second);
       ++k;
     }
-    std::sort(ids.begin(), ids.end());
+    std::sort(ids.begin(), ids.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    const bool want_edges = row_ptr || col || weight || dist;
     int64_t e = 0;
     for (size_t i = 0; i < ids.size(); ++i) {
-      TRG::Node* n = g.at(ids[i]);
-      if (ids_sorted) ids_sorted[i] = ids[i];
+      TRG::Node* n = ids[i].second;
+      if (ids_sorted) ids_sorted[i] = ids[i].first;
       if (pos_xyz) { pos_xyz[3 * i] = n->pos_.x(); pos_xyz[3 * i + 1] = n->pos_.y(); pos_xyz[3 * i + 2] = n->pos_.z(); }
       if (state) state[i] = (int32_t)n->state_;
       if (row_ptr) row_ptr[i] = e;
+      if (!want_edges) continue;
       for (auto* ed : n->edges_) {
         if (col) col[e] = ed->dst_id_;
         if (weight) weight[e] = ed->weight_;

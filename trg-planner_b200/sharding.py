@@ -71,16 +71,19 @@ def allgather_rows(dist, torch, rows: np.ndarray, device) -> list[np.ndarray]:
     """All-gather one float32 matrix per rank (same column count, ragged row counts): two
     collectives (counts, then the payload padded to the longest). Returns the matrix of every rank."""
     world = dist.get_world_size()
-    rows = np.ascontiguousarray(rows, np.float32)
-    ncol = rows.shape[1]
-    cnt = torch.tensor([rows.shape[0]], dtype=torch.int64, device=device)
+    if hasattr(rows, "is_cuda"):
+        rows_t = rows.to(device=device, dtype=torch.float32).contiguous()
+    else:
+        rows_t = torch.from_numpy(np.ascontiguousarray(rows, np.float32)).to(device)
+    ncol = rows_t.shape[1]
+    cnt = torch.tensor([rows_t.shape[0]], dtype=torch.int64, device=device)
     cnts = [torch.zeros_like(cnt) for _ in range(world)]
     dist.all_gather(cnts, cnt)
-    counts = [int(c.item()) for c in cnts]
+    counts = [int(c) for c in torch.cat(cnts).cpu()]
     mx = max(1, max(counts))
     pad = torch.zeros((mx, ncol), dtype=torch.float32, device=device)
-    if rows.shape[0]:
-        pad[: rows.shape[0]] = torch.from_numpy(rows).to(device)
+    if rows_t.shape[0]:
+        pad[: rows_t.shape[0]] = rows_t
     out = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(out, pad)
     return [out[r][: counts[r]].cpu().numpy().copy() for r in range(world)]
@@ -104,6 +107,16 @@ def stitch_tiles(dist, torch, device, rank: int, world: int, tile_pts: np.ndarra
     Returns (edges, stats): edges = float64 array of rows (rank_a, id_a, rank_b, id_b, weight, dist)
     for EVERY border (identical on all ranks).
     """
+    import time
+    tm = {}
+    t0 = time.perf_counter()
+
+    def lap(name):
+        nonlocal t0
+        t1 = time.perf_counter()
+        tm[name] = tm.get(name, 0.0) + 1e3 * (t1 - t0)
+        t0 = t1
+
     band = expand_dist + robot_size
     x = node_pos[:, 0]
     left = np.nonzero(x < x_lo + band)[0] if rank > 0 else np.zeros(0, np.int64)
@@ -112,13 +125,28 @@ def stitch_tiles(dist, torch, device, rank: int, world: int, tile_pts: np.ndarra
     side = np.concatenate([np.zeros(left.size), np.ones(right.size)]).astype(np.float32)
     ids_f = np.ascontiguousarray(node_ids[sel], np.int32).view(np.float32)   # ids travel bit-cast
     nodes_rows = np.column_stack([node_pos[sel], ids_f, side]).astype(np.float32) if sel.size else np.zeros((0, 5), np.float32)
-    px = tile_pts[:, 0]
-    pl = tile_pts[px < x_lo + strip] if rank > 0 else np.zeros((0, 3), np.float32)
-    pr = tile_pts[px > x_hi - strip] if rank < world - 1 else np.zeros((0, 3), np.float32)
-    strip_rows = np.concatenate([np.column_stack([pl, np.zeros(len(pl), np.float32)]),
-                                 np.column_stack([pr, np.ones(len(pr), np.float32)])]).astype(np.float32)
+    if hasattr(tile_pts, "is_cuda"):
+        # the tile's cloud as a torch tensor (resident in HBM on the GPU box): select the strips there
+        px = tile_pts[:, 0]
+        parts = []
+        if rank > 0:
+            pl = tile_pts[px < x_lo + strip][:, :3]
+            parts.append(torch.cat([pl, torch.zeros((pl.shape[0], 1), dtype=pl.dtype, device=pl.device)], 1))
+        if rank < world - 1:
+            pr = tile_pts[px > x_hi - strip][:, :3]
+            parts.append(torch.cat([pr, torch.ones((pr.shape[0], 1), dtype=pr.dtype, device=pr.device)], 1))
+        strip_rows = torch.cat(parts).to(torch.float32) if parts else torch.zeros((0, 4), dtype=torch.float32, device=device)
+    else:
+        px = tile_pts[:, 0]
+        pl = tile_pts[px < x_lo + strip] if rank > 0 else np.zeros((0, 3), np.float32)
+        pr = tile_pts[px > x_hi - strip] if rank < world - 1 else np.zeros((0, 3), np.float32)
+        strip_rows = np.concatenate([np.column_stack([pl, np.zeros(len(pl), np.float32)]),
+                                     np.column_stack([pr, np.ones(len(pr), np.float32)])]).astype(np.float32)
+    lap("select_ms")
     all_nodes = allgather_rows(dist, torch, nodes_rows, device)
+    lap("gather_nodes_ms")   # first collective of the step: includes waiting for the slowest rank's build
     all_strips = allgather_rows(dist, torch, strip_rows, device)
+    lap("gather_strips_ms")
     mine = np.zeros((0, 6), np.float64)
     n_pairs = 0
     if rank < world - 1:
@@ -126,11 +154,13 @@ def stitch_tiles(dist, torch, device, rank: int, world: int, tile_pts: np.ndarra
         b = all_nodes[rank + 1][all_nodes[rank + 1][:, 4] == 0.0]  # neighbour's left band
         pairs = cross_tile_candidates(a[:, :3], b[:, :3], expand_dist)
         n_pairs = len(pairs)
+        lap("pairs_ms")
         if n_pairs:
             sp = np.concatenate([all_strips[rank][all_strips[rank][:, 3] == 1.0][:, :3],
                                  all_strips[rank + 1][all_strips[rank + 1][:, 3] == 0.0][:, :3]]).astype(np.float32)
             stage, w, d = edge_eval(np.ascontiguousarray(sp), np.ascontiguousarray(a[pairs[:, 0], :3]),
                                     np.ascontiguousarray(b[pairs[:, 1], :3]))
+            lap("edge_eval_ms")
             ok = np.nonzero(np.asarray(stage) == 0)[0]
             ida = np.ascontiguousarray(a[:, 3]).view(np.int32)[pairs[ok, 0]]
             idb = np.ascontiguousarray(b[:, 3]).view(np.int32)[pairs[ok, 1]]
@@ -138,8 +168,10 @@ def stitch_tiles(dist, torch, device, rank: int, world: int, tile_pts: np.ndarra
                                     np.asarray(w)[ok], np.asarray(d)[ok]]).astype(np.float64)
     # share the stitched edges (float32 payload: ids < 2^24 exact; larger ids would need the bit-cast trick)
     got = allgather_rows(dist, torch, mine.astype(np.float32), device)
+    lap("gather_edges_ms")
     edges = np.concatenate(got) if got else mine
     stats = dict(boundary_nodes=int(sum(len(m) for m in all_nodes)), strip_points=int(sum(len(m) for m in all_strips)),
                  candidate_pairs=int(n_pairs), stitched_edges_total=int(len(edges)),
-                 bytes=int(sum(m.nbytes for m in all_nodes) + sum(m.nbytes for m in all_strips) + sum(m.nbytes for m in got)))
+                 bytes=int(sum(m.nbytes for m in all_nodes) + sum(m.nbytes for m in all_strips) + sum(m.nbytes for m in got)),
+                 **{k: round(v, 2) for k, v in tm.items()})
     return edges, stats
