@@ -21,6 +21,7 @@ ap.add_argument("--overlap", type=int, default=1)
 ap.add_argument("--chunk", type=int, default=0)
 ap.add_argument("--lookahead", type=int, default=0)
 ap.add_argument("--reps3", type=int, default=1)
+ap.add_argument("--half", type=float, default=22.36, help="half width of a scan window (m): 22.36 -> 200 k points at h = 0.1 m")
 a = ap.parse_args()
 P = trg.MOUNTAIN
 out = {}
@@ -62,7 +63,7 @@ if "4" in a.which.split(","):
     print(f"C4: prebuilt map {pts.shape[0]} points, graph {nn} nodes built in {w1-w0:.2f}s", flush=True)
     rng = np.random.default_rng(9)
     lat, sizes, nodes_after = [], [], []
-    half = 11.2
+    half = a.half
     # spatial buckets for fast window extraction
     order = np.argsort(pts[:, 0], kind="stable"); xs = pts[order, 0]
     for k in range(a.scans):

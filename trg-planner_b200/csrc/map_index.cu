@@ -14,6 +14,10 @@
 #include <cmath>
 #include <vector>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace trgb {
@@ -219,9 +223,24 @@ void tune_mempool_once() {
   cudaGetLastError();
 }
 
+// TRGB_MAP_TRACE=1: report (stderr) any phase of a map build / teardown that takes more than 20 ms
+struct MapTrace {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  MapTrace() : on(std::getenv("TRGB_MAP_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+  void lap(const char* what) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    const double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    if (ms > 20.0) fprintf(stderr, "[trgb map trace] %s: %.1f ms\n", what, ms);
+    t0 = t1;
+  }
+};
+
 static int build_index(trgb_map* m, const float* d_in, int64_t n, int stride, float cell) {
   cudaStream_t st = m->stream;
   tune_mempool_once();
+  MapTrace tr;
   const int sms = sm_count();
   const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sms * 16);
 
@@ -235,7 +254,9 @@ static int build_index(trgb_map* m, const float* d_in, int64_t n, int stride, fl
   }
   float bbox[4];
   TRGB_CUDA(cudaMemcpyAsync(bbox, d_bbox, sizeof(bbox), cudaMemcpyDeviceToHost, st));
+  tr.lap("bbox launch");
   TRGB_CUDA(cudaStreamSynchronize(st));
+  tr.lap("bbox sync");
   cudaFreeAsync(d_bbox, st);
   if (!(bbox[0] <= bbox[2]) || !(bbox[1] <= bbox[3]) || !std::isfinite(bbox[0]) ||
       !std::isfinite(bbox[3])) {
@@ -268,6 +289,7 @@ static int build_index(trgb_map* m, const float* d_in, int64_t n, int stride, fl
   TRGB_CUDA(cudaMallocAsync((void**)&m->d_pts, ((size_t)n + kPtsPad) * sizeof(float4), st));
   TRGB_CUDA(cudaMemsetAsync(m->d_pts + n, 0, kPtsPad * sizeof(float4), st));
   m->device_bytes = (ncells + 1) * (int64_t)sizeof(uint32_t) + (n + kPtsPad) * (int64_t)sizeof(float4);
+  tr.lap("allocations");
   TRGB_CUDA(cudaMemsetAsync(d_counts, 0, ncells * sizeof(uint32_t), st));
   TRGB_CUDA(cudaMemsetAsync(d_fill, 0, ncells * sizeof(uint32_t), st));
   {
@@ -293,7 +315,9 @@ static int build_index(trgb_map* m, const float* d_in, int64_t n, int stride, fl
   cudaFreeAsync(d_counts, st);
   cudaFreeAsync(d_fill, st);
   cudaFreeAsync(d_sums, st);
+  tr.lap("index launches");
   TRGB_CUDA(cudaStreamSynchronize(st));
+  tr.lap("index sync");
   v.pts = m->d_pts;
   v.cell_start = m->d_cell_start;
   return TRGB_OK;
@@ -311,7 +335,9 @@ extern "C" int trgb_map_create_dev(trgb_map** out, const float* dev_pts, int64_t
   TRGB_ARG(stride_floats == 3 || stride_floats == 4, "stride_floats must be 3 or 4");
   TRGB_ARG(cell_size > 0.f && std::isfinite(cell_size), "cell_size must be > 0");
   trgb_map* m = new trgb_map();
+  MapTrace tr;
   cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+  tr.lap("stream create");
   if (e != cudaSuccess) {
     delete m;
     return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__);
@@ -349,10 +375,14 @@ extern "C" void trgb_map_destroy(trgb_map* m) {
   if (!m) return;
   if (m->d_pts) cudaFreeAsync(m->d_pts, m->stream);
   if (m->d_cell_start) cudaFreeAsync(m->d_cell_start, m->stream);
+  MapTrace tr;
   if (m->stream) cudaStreamSynchronize(m->stream);
+  tr.lap("destroy: stream sync");
   if (m->d_stage) cudaFree(m->d_stage);
   if (m->h_stage) cudaFreeHost(m->h_stage);
+  tr.lap("destroy: staging free");
   if (m->stream) cudaStreamDestroy(m->stream);
+  tr.lap("destroy: stream destroy");
   delete m;
 }
 

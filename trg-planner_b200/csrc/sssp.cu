@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -34,6 +35,8 @@ struct trgb_graph {
   unsigned long long* d_label = nullptr;
   int32_t* d_queue = nullptr;
   uint32_t* d_bits = nullptr;
+  size_t label_bytes = 0, queue_bytes = 0, bits_bytes = 0;  // allocated sizes
+  int device = 0;
   cudaStream_t stream = nullptr;
 };
 
@@ -273,11 +276,48 @@ using namespace trgb;
 static void gfree(void* p, cudaStream_t st) {
   if (p) cudaFreeAsync(p, st);
 }
+
+// The search scratch (labels, queues, bitmaps: ~13 KB per node and slot, several GB for a
+// half-million-node graph) outlives its graph handle: a TRG that is rebuilt every few hundred
+// milliseconds destroys and re-creates the handle each time, and returning a multi-GB block to the
+// pool only to carve it up for the next map's 160 MB left the pool fragmented - the following
+// cudaMallocAsync calls then went to the driver for fresh memory (80 - 1100 ms stalls, measured).
+// One set of buffers per process is parked here between handles.
+namespace {
+struct ScratchCache {
+  void *label = nullptr, *queue = nullptr, *bits = nullptr;
+  size_t label_bytes = 0, queue_bytes = 0, bits_bytes = 0;
+  int device = -1;
+};
+ScratchCache g_scratch;
+std::mutex g_scratch_mx;
+}  // namespace
+
+static void release_scratch(trgb_graph* g) {  // the handle's stream has been synchronised by the caller
+  if (!g->d_label && !g->d_queue && !g->d_bits) return;
+  std::lock_guard<std::mutex> lk(g_scratch_mx);
+  const bool bigger = g->label_bytes >= g_scratch.label_bytes && g->queue_bytes >= g_scratch.queue_bytes &&
+                      g->bits_bytes >= g_scratch.bits_bytes;
+  if (g->d_label && g->d_queue && g->d_bits && (g_scratch.label == nullptr || bigger)) {
+    if (g_scratch.label) {  // replace the parked (smaller) set
+      cudaFreeAsync(g_scratch.label, g->stream); cudaFreeAsync(g_scratch.queue, g->stream); cudaFreeAsync(g_scratch.bits, g->stream);
+    }
+    g_scratch = ScratchCache{g->d_label, g->d_queue, g->d_bits, g->label_bytes, g->queue_bytes, g->bits_bytes, g->device};
+  } else {
+    gfree(g->d_label, g->stream); gfree(g->d_queue, g->stream); gfree(g->d_bits, g->stream);
+  }
+  g->d_label = nullptr; g->d_queue = nullptr; g->d_bits = nullptr;
+  g->label_bytes = g->queue_bytes = g->bits_bytes = 0;
+  g->nslots = 0;
+}
+
 extern "C" void trgb_graph_destroy(trgb_graph* g) {
   if (!g) return;
   cudaStream_t st = g->stream;
   gfree(g->d_row, st); gfree(g->d_col, st); gfree(g->d_w, st); gfree(g->d_dist, st); gfree(g->d_cost, st);
-  gfree(g->d_pos, st); gfree(g->d_state, st); gfree(g->d_label, st); gfree(g->d_queue, st); gfree(g->d_bits, st);
+  gfree(g->d_pos, st); gfree(g->d_state, st);
+  if (st) cudaStreamSynchronize(st);
+  release_scratch(g);
   if (g->stream) {
     cudaStreamSynchronize(g->stream);
     cudaStreamDestroy(g->stream);
@@ -297,6 +337,7 @@ extern "C" int trgb_graph_upload(trgb_graph** out, const TrgbGraphDesc* d) {
   }
   g->n = d->n_nodes;
   g->e = d->n_edges;
+  cudaGetDevice(&g->device);
   const size_t n = g->n, e = g->e;
   std::vector<float2> pos(n);
   double mean = 0;
@@ -325,12 +366,35 @@ extern "C" int trgb_graph_upload(trgb_graph** out, const TrgbGraphDesc* d) {
 
 static int ensure_slots(trgb_graph* g, int want) {
   if (g->nslots >= want) return TRGB_OK;
-  gfree(g->d_label, g->stream); gfree(g->d_queue, g->stream); gfree(g->d_bits, g->stream);
-  g->d_label = nullptr; g->d_queue = nullptr; g->d_bits = nullptr; g->nslots = 0;
   const size_t n = g->n, words = (n + 31) / 32;
-  TRGB_CUDA(cudaMallocAsync((void**)&g->d_label, (size_t)want * n * sizeof(unsigned long long), g->stream));
-  TRGB_CUDA(cudaMallocAsync((void**)&g->d_queue, (size_t)want * 4 * n * sizeof(int32_t), g->stream));
-  TRGB_CUDA(cudaMallocAsync((void**)&g->d_bits, (size_t)want * 2 * words * sizeof(uint32_t), g->stream));
+  const size_t need_l = (size_t)want * n * sizeof(unsigned long long);
+  const size_t need_q = (size_t)want * 4 * n * sizeof(int32_t);
+  const size_t need_b = (size_t)want * 2 * words * sizeof(uint32_t);
+  if (g->d_label && g->label_bytes >= need_l && g->queue_bytes >= need_q && g->bits_bytes >= need_b) {
+    g->nslots = want;
+    return TRGB_OK;
+  }
+  cudaStreamSynchronize(g->stream);
+  release_scratch(g);
+  {
+    std::lock_guard<std::mutex> lk(g_scratch_mx);
+    if (g_scratch.label && g_scratch.device == g->device && g_scratch.label_bytes >= need_l &&
+        g_scratch.queue_bytes >= need_q && g_scratch.bits_bytes >= need_b) {
+      g->d_label = (unsigned long long*)g_scratch.label; g->d_queue = (int32_t*)g_scratch.queue; g->d_bits = (uint32_t*)g_scratch.bits;
+      g->label_bytes = g_scratch.label_bytes; g->queue_bytes = g_scratch.queue_bytes; g->bits_bytes = g_scratch.bits_bytes;
+      g_scratch = ScratchCache{};
+      g->nslots = want;
+      return TRGB_OK;
+    }
+  }
+  // a little head room so that the next, slightly larger graph of a rebuild loop fits the parked set
+  const size_t al = need_l + need_l / 16, aq = need_q + need_q / 16, ab = need_b + need_b / 16 + 256;
+  TRGB_CUDA(cudaMallocAsync((void**)&g->d_label, al, g->stream));
+  g->label_bytes = al;
+  TRGB_CUDA(cudaMallocAsync((void**)&g->d_queue, aq, g->stream));
+  g->queue_bytes = aq;
+  TRGB_CUDA(cudaMallocAsync((void**)&g->d_bits, ab, g->stream));
+  g->bits_bytes = ab;
   g->nslots = want;
   return TRGB_OK;
 }
