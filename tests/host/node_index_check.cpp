@@ -16,8 +16,52 @@ static int fails = 0;
 static long n_ties = 0;
 #define CHECK(c, ...) do { if (!(c)) { if (fails < 20) { printf("FAIL %s:%d: ", __FILE__, __LINE__); printf(__VA_ARGS__); printf("\n"); } ++fails; } } while (0)
 
+// ChunkTable::refine (nodes created since the last hand-over) against a brute-force merge: same
+// float arithmetic as the table (dx*dx then += dy*dy), candidates at any distance (pruned probe,
+// ring fallback, exhaustive fallback), exact ties on a lattice, prune() and clear().
+static void check_chunk_table(std::mt19937& gen) {
+  for (int round = 0; round < 6; ++round) {
+    const bool lattice = round >= 4;
+    const float ext = round % 2 ? 300.f : 30.f;
+    const float cell = round % 3 == 0 ? 0.3f : (round % 3 == 1 ? 0.6f : 0.9f);
+    const int n = 6000;
+    std::uniform_real_distribution<float> U(0.f, ext);
+    std::vector<float> xs(n), ys(n);
+    for (int i = 0; i < n; ++i) { xs[i] = U(gen); ys[i] = U(gen); }
+    if (lattice) for (int i = 0; i < n; ++i) { xs[i] = 3.f + (float)(i % 80) * 0.25f; ys[i] = 5.f + (float)((i / 80) % 75) * 0.25f; }
+    const int handed = n / 2;  // seq < handed: "on the device"; the rest is in the table
+    trg_b200::ChunkTable tab;
+    tab.configure(-1.f, -2.f, cell);
+    for (int i = handed; i < n; ++i) tab.insert(xs[i], ys[i], i);
+    auto d2f = [&](int i, float qx, float qy) { const float dx = xs[i] - qx, dy = ys[i] - qy; float v = 0.f; v += dx * dx; v += dy * dy; return v; };
+    for (int pass = 0; pass < 2; ++pass) {
+      int lo = handed;
+      if (pass == 1) { lo = handed + n / 4; tab.prune(lo); }  // forget the older half of the table
+      for (int q = 0; q < 4000; ++q) {
+        float qx = U(gen), qy = U(gen);
+        if (lattice && q % 2) { qx = 3.f + 0.125f + 0.25f * (float)(q % 79); qy = 5.f + 0.125f + 0.25f * (float)((q / 79) % 74); }  // cell centres: 4-way ties
+        // device candidate: brute force over seq < handed (every third query: none at all)
+        float d2 = std::numeric_limits<float>::infinity(); int seq = -1; bool tie = false;
+        if (q % 3) for (int i = 0; i < handed; ++i) { const float v = d2f(i, qx, qy); if (v < d2) { d2 = v; seq = i; tie = false; } else if (v == d2) tie = true; }
+        float wd = d2; int ws = seq; bool wt = tie;
+        for (int i = lo; i < n; ++i) { const float v = d2f(i, qx, qy); if (v < wd) { wd = v; ws = i; wt = false; } else if (v == wd && i != ws) wt = true; }
+        tab.refine(qx, qy, d2, seq, tie);
+        CHECK(d2 == wd, "chunk table d2 %g want %g (round %d pass %d q %d)", d2, wd, round, pass, q);
+        CHECK(tie == wt, "chunk table tie %d want %d (round %d pass %d q %d)", (int)tie, (int)wt, round, pass, q);
+        if (!wt) CHECK(seq == ws, "chunk table seq %d want %d (round %d pass %d q %d)", seq, ws, round, pass, q);
+        if (wt) ++n_ties;
+      }
+    }
+    tab.clear();
+    float d2 = 4.f; int seq = 7; bool tie = false;
+    tab.refine(1.f, 1.f, d2, seq, tie);
+    CHECK(d2 == 4.f && seq == 7 && !tie && tab.empty(), "cleared table must not change the candidate");
+  }
+}
+
 int main() {
   std::mt19937 gen(7);
+  check_chunk_table(gen);
   for (int round = 0; round < 6; ++round) {
     const int n = round == 0 ? 1 : (round == 1 ? 17 : 20000);
     const float ext = round < 4 ? 40.f : 400.f;

@@ -530,4 +530,104 @@ class NodeGrid {
   std::vector<Over> over_;
 };
 
+// Nodes created while the current batch is being committed: they are not yet in the device node
+// grid that produced the batch's nearest-node candidates, so the commit merges those candidates
+// with an exact nearest search over this small, cache-resident hash grid.
+class ChunkTable {
+ public:
+  void configure(float x0, float y0, float cell) { x0_ = x0; y0_ = y0; cell_ = cell; inv_ = 1.0f / cell; }
+  bool empty() const { return ent_.empty(); }
+  void clear() {
+    for (uint32_t h : touched_) { head_[h] = -1; occ_[h >> 6] = 0; }
+    touched_.clear();
+    ent_.clear();
+  }
+  // forget nodes with seq < min_seq (they are on the device grid by now); entries are in seq order
+  void prune(int min_seq) {
+    size_t first = 0;
+    while (first < ent_.size() && ent_[first].seq < min_seq) ++first;
+    if (first == 0) return;
+    std::vector<E> keep(ent_.begin() + first, ent_.end());
+    clear();
+    for (const E& e : keep) insert(e.x, e.y, e.seq);
+  }
+  void insert(float x, float y, int seq) {
+    const int cx = cc(x, x0_), cy = cc(y, y0_);
+    const uint32_t h = hash(cx, cy);
+    if (head_[h] < 0) touched_.push_back(h);
+    occ_[h >> 6] |= 1ull << (h & 63);
+    ent_.push_back({x, y, seq, head_[h], cx, cy});
+    head_[h] = static_cast<int32_t>(ent_.size()) - 1;
+  }
+  // improve (d2, seq, tie) with any stored node that is strictly nearer; equal distance -> tie
+  void refine(float qx, float qy, float& d2, int& seq, bool& tie) const {
+    if (ent_.empty()) return;
+    if (!(d2 < std::numeric_limits<float>::infinity())) {
+      for (const E& e : ent_) consider(e, qx, qy, d2, seq, tie);
+      return;
+    }
+    const float fuzz = 1e-5f + 4e-6f * (std::fabs(qx) + std::fabs(qy));
+    {
+      // the device candidate bounds the search: only cells the disc of radius sqrt(d2) touches
+      // (inflated so that a node at exactly the same distance is seen and flagged as a tie) -
+      // usually one or two cells instead of nine
+      const float reach = std::sqrt(d2) * 1.00001f + fuzz;
+      const int cx0 = cc(qx - reach, x0_), cx1 = cc(qx + reach, x0_);
+      const int cy0 = cc(qy - reach, y0_), cy1 = cc(qy + reach, y0_);
+      if ((cx1 - cx0 + 1) * (cy1 - cy0 + 1) <= 9) {
+        for (int yy = cy0; yy <= cy1; ++yy)
+          for (int xx = cx0; xx <= cx1; ++xx) scan(xx, yy, qx, qy, d2, seq, tie);
+        return;
+      }
+    }
+    const int qcx = cc(qx, x0_), qcy = cc(qy, y0_);
+    for (int R = 1;; ++R) {
+      if (R == 1) {
+        for (int yy = qcy - 1; yy <= qcy + 1; ++yy)
+          for (int xx = qcx - 1; xx <= qcx + 1; ++xx) scan(xx, yy, qx, qy, d2, seq, tie);
+      } else {
+        for (int xx = qcx - R; xx <= qcx + R; ++xx) { scan(xx, qcy - R, qx, qy, d2, seq, tie); scan(xx, qcy + R, qx, qy, d2, seq, tie); }
+        for (int yy = qcy - R + 1; yy <= qcy + R - 1; ++yy) { scan(qcx - R, yy, qx, qy, d2, seq, tie); scan(qcx + R, yy, qx, qy, d2, seq, tie); }
+      }
+      // everything outside the scanned block is at least R whole cells away
+      const float g = static_cast<float>(R) * cell_ * 0.9999f - fuzz;
+      if (g > 0.f && d2 <= g * g) break;
+      if (R > 64) {  // pathological (nearest far away): finish exhaustively
+        for (const E& e : ent_) consider(e, qx, qy, d2, seq, tie);
+        break;
+      }
+    }
+  }
+
+ private:
+  struct E { float x, y; int seq; int32_t next; int cx, cy; };
+  static constexpr uint32_t kMask = (1u << 14) - 1;
+  // toroidal 128 x 128 tile of cells: neighbouring cells are neighbouring buckets (the 2 x 2 block a
+  // query usually probes sits in two cache lines) and there is nothing to multiply; cells 128 apart
+  // share a bucket and are told apart by (cx, cy)
+  static uint32_t hash(int cx, int cy) {
+    return ((static_cast<uint32_t>(cy) & 127u) << 7) | (static_cast<uint32_t>(cx) & 127u);
+  }
+  int cc(float v, float o) const { return static_cast<int>(std::floor((v - o) * inv_)); }
+  static void consider(const E& e, float qx, float qy, float& d2, int& seq, bool& tie) {
+    const float dx = e.x - qx, dy = e.y - qy;
+    float v = 0.f;
+    v += dx * dx;
+    v += dy * dy;
+    if (v < d2) { d2 = v; seq = e.seq; tie = false; }
+    else if (v == d2 && e.seq != seq) tie = true;
+  }
+  void scan(int cx, int cy, float qx, float qy, float& d2, int& seq, bool& tie) const {
+    const uint32_t h = hash(cx, cy);
+    if (!((occ_[h >> 6] >> (h & 63)) & 1ull)) return;  // 2 KB bitmap: almost every probe ends here
+    for (int32_t i = head_[h]; i >= 0; i = ent_[i].next)
+      if (ent_[i].cx == cx && ent_[i].cy == cy) consider(ent_[i], qx, qy, d2, seq, tie);
+  }
+  float x0_ = 0.f, y0_ = 0.f, cell_ = 1.f, inv_ = 1.f;
+  std::vector<int32_t> head_ = std::vector<int32_t>(kMask + 1, -1);
+  std::vector<uint64_t> occ_ = std::vector<uint64_t>((kMask + 1) / 64, 0);
+  std::vector<uint32_t> touched_;
+  std::vector<E> ent_;
+};
+
 }  // namespace trg_b200
