@@ -17,3 +17,15 @@ def load():
     sys.modules[name] = mod
     spec.loader.exec_module(mod)
     return mod
+
+
+def load_oracle():
+    """The CPU oracle's loader (oracle/facade.py) - test infrastructure: tests, smoke(), bench cpu_baseline."""
+    name = "trg_oracle_facade"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, ROOT / "oracle" / "facade.py")
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod

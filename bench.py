@@ -436,7 +436,8 @@ def cpu_sample(trg, side, queries_n):
     P = trg.MOUNTAIN
     pts = trg.terrain.mountain(side, h=0.1, seed=SEED_MAP, tile=(0, 0), world_tiles=(1, 1))
     refkd = (ROOT / "oracle" / "_ref" / "liboracle_refkd.so").exists()
-    o = trg.oracle(P, ref_kdtree=refkd)
+    import _pkg
+    o = _pkg.load_oracle().oracle(P, ref_kdtree=refkd)   # the checker, timed as the CPU baseline
     o.seed(SEED_RNG)
     bb = trg.terrain.bbox(pts)
     w0 = time.perf_counter()

@@ -23,7 +23,7 @@ res["b200"] = dict(map_s=round(w1 - w0, 4), init_s=round(w2 - w1, 4), nodes=a.n_
                    stalls=t2.stat("stalls"), flush_launches=t2.stat("flush_launches"), batches=t2.stat("batches"),
                    path_nodes=len(rp["ids"]), path_found=rp["found"])
 refkd = (Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "liboracle_refkd.so").exists()
-o = trg.oracle(P, ref_kdtree=refkd); o.seed(42)
+o = _pkg.load_oracle().oracle(P, ref_kdtree=refkd); o.seed(42)
 w0 = time.time(); o.set_global_map(pts); w1 = time.time(); o.init_graph(start); w2 = time.time()
 b = o.export()
 w3 = time.time(); ro = o.plan(start[:2], goal); w4 = time.time()

@@ -10,7 +10,20 @@ sys.path.insert(0, str(ROOT))
 
 import _pkg  # noqa: E402
 
-trg = _pkg.load()
+
+
+class _Kit:
+    """What the tests call `pkg`: the product package plus, under `.oracle`, the loader of the CPU
+    oracle (oracle/facade.py). The product package itself knows nothing about the oracle."""
+
+    def __init__(self, package, oracle):
+        self._package, self.oracle = package, oracle
+
+    def __getattr__(self, name):
+        return getattr(self._package, name)
+
+
+trg = _Kit(_pkg.load(), _pkg.load_oracle().oracle)
 
 
 def pytest_configure(config):

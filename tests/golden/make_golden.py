@@ -20,7 +20,7 @@ OUT = Path(__file__).resolve().parent
 
 
 def case(name, P, pts, start, seed, n_q=24, updates=None):
-    o = trg.oracle(P, ref_kdtree=True)
+    o = _pkg.load_oracle().oracle(P, ref_kdtree=True)
     o.seed(seed)
     o.set_global_map(pts)
     assert o.init_graph(start) == 0

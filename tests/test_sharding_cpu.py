@@ -106,14 +106,15 @@ def _stitch_worker(rank, world, port, q):
     side = 140
     pts = trg.terrain.mountain(side, h=0.1, seed=2, tile=(rank, 0), world_tiles=(world, 1))
     x_lo, x_hi = rank * side * 0.1, (rank + 1) * side * 0.1
-    o = trg.oracle(P)
+    oracle = _pkg.load_oracle().oracle
+    o = oracle(P)
     o.seed(42 + rank)
     o.set_global_map(pts)
     assert o.init_graph((0.5 * (x_lo + x_hi), 7.0, 0.0)) == 0
     g = o.export()
 
     def edge_eval(strip_pts, p1, p2):      # CPU tests: the oracle stands in for the K4 kernels
-        e = trg.oracle(P)
+        e = oracle(P)
         e.set_global_map(strip_pts)
         r = e.edge_eval(p1, p2)
         return r["stage"], r["weight"], r["dist"]

@@ -7,5 +7,5 @@ project layout), so it is imported under the module name `trg_planner_b200` via 
 """
 from . import params, terrain  # noqa: F401
 from . import binding  # noqa: F401
-from .binding import TrgFacade, load_params_yaml, load_pcd, oracle, product, save_pcd  # noqa: F401
+from .binding import TrgFacade, load_params_yaml, load_pcd, product, save_pcd  # noqa: F401
 from .params import INDOOR, MOUNTAIN, TrgParams  # noqa: F401

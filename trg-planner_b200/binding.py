@@ -18,8 +18,6 @@ from .params import CParams, TrgParams
 ROOT = Path(__file__).resolve().parent.parent
 PRODUCT_LIB = ROOT / "trg-planner_b200" / "lib" / "libtrg_b200.so"
 KERNEL_LIB = ROOT / "trg-planner_b200" / "lib" / "libtrgb_kernels.so"
-ORACLE_LIB = ROOT / "oracle" / "liboracle.so"
-ORACLE_REFKD_LIB = ROOT / "oracle" / "_ref" / "liboracle_refkd.so"
 
 _f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 _vp = C.c_void_p
@@ -323,10 +321,6 @@ def save_pcd(path, xyz: np.ndarray, binary: bool = True):
     if L.trg_save_pcd(str(path).encode(), _ptr(a), a.shape[0], int(binary)) < 0:
         raise RuntimeError((L.trg_last_error() or b"").decode())
 
-
-def oracle(params: TrgParams, ref_kdtree: bool = False) -> TrgFacade:
-    """CPU oracle — tests / smoke / cpu_baseline only."""
-    return TrgFacade(ORACLE_REFKD_LIB if ref_kdtree else ORACLE_LIB, "orc", params)
 
 
 def product(params: TrgParams) -> TrgFacade:
