@@ -137,9 +137,17 @@ def stitch_tiles(dist, torch, device, rank: int, world: int, tile_pts: np.ndarra
             parts.append(torch.cat([pr, torch.ones((pr.shape[0], 1), dtype=pr.dtype, device=pr.device)], 1))
         strip_rows = torch.cat(parts).to(torch.float32) if parts else torch.zeros((0, 4), dtype=torch.float32, device=device)
     else:
+        # one pass over the 10 M-point cloud (combined mask, one index gather), then split the ~1 %
+        # that survives; row order inside each strip stays the cloud's order
         px = tile_pts[:, 0]
-        pl = tile_pts[px < x_lo + strip] if rank > 0 else np.zeros((0, 3), np.float32)
-        pr = tile_pts[px > x_hi - strip] if rank < world - 1 else np.zeros((0, 3), np.float32)
+        lo_cut = x_lo + strip if rank > 0 else -np.inf
+        hi_cut = x_hi - strip if rank < world - 1 else np.inf
+        if lo_cut > hi_cut:   # tile narrower than two strips: a point may belong to both
+            pl, pr = tile_pts[px < lo_cut][:, :3], tile_pts[px > hi_cut][:, :3]
+        else:
+            sub = tile_pts[np.flatnonzero((px < lo_cut) | (px > hi_cut))][:, :3]
+            is_left = sub[:, 0] < lo_cut
+            pl, pr = sub[is_left], sub[~is_left]
         strip_rows = np.concatenate([np.column_stack([pl, np.zeros(len(pl), np.float32)]),
                                      np.column_stack([pr, np.ones(len(pr), np.float32)])]).astype(np.float32)
     lap("select_ms")
