@@ -56,7 +56,48 @@ def case(name, P, pts, start, seed, n_q=24, updates=None):
     print(name, "nodes", g.n_nodes, "edges", g.n_edges, "draws", o.stat("rng_draws"))
 
 
+def update_scans(pts, n_steps=3):
+    """The scan sequence of the incremental-update cases (same recipe as tests/test_trg_gpu.py)."""
+    rng = np.random.default_rng(9)
+    out = []
+    for step in range(n_steps):
+        cx, cy = 4.0 + 3.0 * step, 6.0
+        m = (np.abs(pts[:, 0] - cx) < 3.5) & (np.abs(pts[:, 1] - cy) < 3.5)
+        scan = pts[m].copy()
+        scan[:, 2] += rng.normal(0, 0.01, size=scan.shape[0]).astype(np.float32)
+        if step == 1:   # an obstacle appears in the scan: a 1 m block 0.8 m high
+            blk = (np.abs(scan[:, 0] - cx - 1.5) < 0.5) & (np.abs(scan[:, 1] - cy) < 0.5)
+            scan[blk, 2] += np.where(rng.uniform(size=int(blk.sum())) < 0.5, 0.8, 0.0).astype(np.float32)
+        out.append((cx, cy, scan))
+    return out
+
+
+def update_case(name, P, pts, start, seed):
+    """setLocalMap + updateGraph (trg.cpp:195-231, 456-489): the graph after every scan."""
+    o = _pkg.load_oracle().oracle(P, ref_kdtree=True)
+    o.seed(seed)
+    o.set_global_map(pts)
+    assert o.init_graph(start) == 0
+    rec = dict(pts=pts, params=np.asarray([P.expand_dist, P.robot_size, P.sample_num, P.height_threshold, P.collision_threshold, P.update_collision_threshold, P.safety_factor, P.goal_tolerance], np.float64),
+               seed=seed, start=np.asarray(start, np.float32))
+    for i, (cx, cy, scan) in enumerate(update_scans(pts)):
+        o.set_local_map(cx, cy, scan)
+        rec[f"local_before_{i}"] = o.export("local").iter_ids
+        o.update_graph()
+        g = o.export()
+        for k in ("iter_ids", "pos", "state", "row_ptr", "col", "weight", "dist"):
+            rec[f"{k}_{i}"] = getattr(g, k)
+        rec[f"local_after_{i}"] = o.export("local").iter_ids
+        rec[f"draws_{i}"] = o.stat("rng_draws")
+    fr = np.random.default_rng(5).uniform(1, 11, size=(300, 2)).astype(np.float32)
+    rec["frontier_q"] = fr
+    rec["frontier"] = o.is_frontier(fr)
+    np.savez_compressed(OUT / f"{name}.npz", **rec)
+    print(name, "nodes after last scan", len(rec["iter_ids_2"]), "draws", rec["draws_2"])
+
+
 if __name__ == "__main__":
+    update_case("update_120", trg.MOUNTAIN, trg.terrain.mountain(120, h=0.1, seed=4), (4.0, 6.0, 0.0), 3)
     case("mountain_120", trg.MOUNTAIN, trg.terrain.mountain(120, h=0.1, seed=2), (6.0, 6.0, 0.0), 42)
     case("indoor_70", trg.INDOOR, trg.terrain.indoor(70, h=0.2, seed=1), (3.27, 4.12, 0.0), 42)
     case("stairs_100", trg.MOUNTAIN, trg.terrain.stairs(100, h=0.1, seed=5, riser=0.10), (5.0, 5.0, 0.0), 11)

@@ -57,6 +57,33 @@ def test_oracle_matches_golden(pkg, built, case):
                 assert np.float32(r["avg_risk"]) == g["path_risk"][i]
 
 
+def test_oracle_update_path_matches_golden(pkg, built):
+    """setLocalMap / setLocalGraph / updateGraph / isFrontier (trg.cpp:195-231, 456-489, 780-803):
+    graph, local node set and draw count after every scan, port and reference kd-tree builds."""
+    sys_path_added = str(GOLD) not in __import__("sys").path
+    if sys_path_added:
+        __import__("sys").path.insert(0, str(GOLD))
+    from make_golden import update_scans
+    g = np.load(GOLD / "update_120.npz")
+    P = params_of(pkg, g)
+    for name, refkd in oracles(pkg):
+        o = pkg.oracle(P, ref_kdtree=refkd)
+        o.seed(int(g["seed"]))
+        o.set_global_map(g["pts"])
+        assert o.init_graph(tuple(g["start"])) == 0
+        for i, (cx, cy, scan) in enumerate(update_scans(g["pts"])):
+            o.set_local_map(cx, cy, scan)
+            np.testing.assert_array_equal(o.export("local").iter_ids, g[f"local_before_{i}"], err_msg=f"{name}: local set {i}")
+            o.update_graph()
+            assert o.stat("rng_draws") == int(g[f"draws_{i}"]), (name, i)
+            e = o.export()
+            for k in ("iter_ids", "pos", "state", "row_ptr", "col", "weight", "dist"):
+                np.testing.assert_array_equal(getattr(e, k), g[f"{k}_{i}"], err_msg=f"{name}: scan {i}: {k}")
+            np.testing.assert_array_equal(o.export("local").iter_ids, g[f"local_after_{i}"])
+        np.testing.assert_array_equal(o.is_frontier(g["frontier_q"]), g["frontier"])
+        assert len(g["iter_ids_2"]) != len(g["iter_ids_0"]) or not np.array_equal(g["state_2"], g["state_0"])  # the scans did change the graph
+
+
 def test_kdtree_port_equals_reference_kdtree(pkg, built):
     """Restated kd-tree (oracle/kdtree_port.h) vs the reference's kdtree.c compiled where it lies:
     same result ORDER for range queries is what setGoal / wireEdge order depend on."""
