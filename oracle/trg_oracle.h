@@ -3,10 +3,14 @@
 // legs may load this library, and only as the checker / the timed CPU baseline.
 // The product (trg-planner_b200/) never links, loads or calls anything in oracle/.
 //
-// C facade of the CPU restatement of the reference TRG hot path
-// (cpp/trg_planner/core/trg_planner/src/graph/trg.cpp + src/kdtree/kdtree.c).
-// PARITY UNPINNED at the Eigen boundary (see eigen_restate.h): the reference ships no
-// tests / golden vectors, and trg.cpp cannot be compiled here (Eigen/PCL absent).
+// C facade of the CPU oracle of the reference TRG hot path
+// (cpp/trg_planner/core/trg_planner/src/graph/trg.cpp + src/kdtree/kdtree.c). Two implementations
+// export it: trg_oracle.cpp (a restatement) and ref_harness.cpp (the reference's own UNMODIFIED
+// trg.cpp + kdtree.c compiled against oracle/shim/ into oracle/_ref/libtrg_ref.so). The restatement
+// is pinned to the reference build bit for bit (tests/test_oracle_cpu.py) and tests/golden/ are
+// outputs of the reference build. What stays PARITY UNPINNED is Eigen alone (absent from the image
+// and from /root/reference): JacobiSVD and the float summation order of the 3x3 covariance are
+// restated in eigen_restate.h / shim/Eigen/Core for BOTH builds.
 //
 // The same entry points, with prefix `trg_` instead of `orc_`, are exported by the
 // product's host library so tests drive both through one binding.

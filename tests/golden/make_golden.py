@@ -1,9 +1,13 @@
-"""Generates tests/golden/*.npz with the CPU oracle linked against the VERBATIM reference kd-tree
-(oracle/_ref/liboracle_refkd.so, built from /root/reference/.../kdtree.c by oracle/Makefile).
+"""Generates tests/golden/*.npz by RUNNING THE REFERENCE ITSELF: oracle/_ref/libtrg_ref.so is the
+reference's unmodified src/graph/trg.cpp + src/kdtree/kdtree.c, compiled where they lie by
+oracle/Makefile against the stand-in headers of oracle/shim/ (Eigen / PCL / OpenCV / yaml-cpp are
+absent from the image; only Eigen's JacobiSVD and float reductions are restated there).
 
-The reference ships no golden vectors, no tests and cannot be compiled here as a whole (Eigen, PCL,
-OpenCV, yaml-cpp absent), so these fixtures pin (a) the oracle's restated kd-tree port against the
-reference's own kdtree.c and (b) the oracle against itself over time. Run in the build container:
+The reference ships no golden vectors and no tests, so these fixtures are outputs of the reference
+run here on seeded synthetic maps (graph, CSR, draw count, kernel-level answers, paths). The three
+fields the reference cannot report (wireEdge's return stage, the number of PCA points, the float64
+twin of the weight) come from the restated oracle, which `PinnedOracle.edge_eval` first requires
+to agree bit for bit with the reference on every created edge. Run in the build container:
     python tests/golden/make_golden.py
 """
 import sys
@@ -20,7 +24,7 @@ OUT = Path(__file__).resolve().parent
 
 
 def case(name, P, pts, start, seed, n_q=24, updates=None):
-    o = _pkg.load_oracle().oracle(P, ref_kdtree=True)
+    o = _pkg.load_oracle().oracle(P, kind="ref")
     o.seed(seed)
     o.set_global_map(pts)
     assert o.init_graph(start) == 0
@@ -74,7 +78,7 @@ def update_scans(pts, n_steps=3):
 
 def update_case(name, P, pts, start, seed):
     """setLocalMap + updateGraph (trg.cpp:195-231, 456-489): the graph after every scan."""
-    o = _pkg.load_oracle().oracle(P, ref_kdtree=True)
+    o = _pkg.load_oracle().oracle(P, kind="ref")
     o.seed(seed)
     o.set_global_map(pts)
     assert o.init_graph(start) == 0

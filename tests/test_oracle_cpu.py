@@ -1,6 +1,8 @@
-"""-m "not gpu": the CPU oracle against the committed golden fixtures (generated with the VERBATIM
-reference kdtree.c linked in, tests/golden/make_golden.py), the restated kd-tree port against the
-reference kd-tree, and the restated Eigen JacobiSVD against numpy."""
+"""-m "not gpu": every oracle build against the committed golden fixtures — which are outputs of the
+REFERENCE ITSELF (oracle/_ref/libtrg_ref.so = the unmodified trg.cpp + kdtree.c compiled against
+oracle/shim/, tests/golden/make_golden.py) —, the restatement against the reference build on fresh
+inputs, the restated kd-tree port against the reference kd-tree, and the restated Eigen JacobiSVD
+against numpy."""
 from pathlib import Path
 
 import numpy as np
@@ -8,6 +10,7 @@ import pytest
 
 GOLD = Path(__file__).resolve().parent / "golden"
 REFKD_LIB = Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "liboracle_refkd.so"
+REF_LIB = Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "libtrg_ref.so"
 CASES = ["mountain_120", "indoor_70", "stairs_100"]
 
 
@@ -17,9 +20,11 @@ def params_of(pkg, g):
 
 
 def oracles(pkg):
-    out = [("port", False)]
+    out = ["port"]
     if REFKD_LIB.exists():
-        out.append(("refkd", True))
+        out.append("refkd")
+    if REF_LIB.exists():
+        out.append("ref")
     return out
 
 
@@ -27,8 +32,8 @@ def oracles(pkg):
 def test_oracle_matches_golden(pkg, built, case):
     g = np.load(GOLD / f"{case}.npz")
     P = params_of(pkg, g)
-    for name, refkd in oracles(pkg):
-        o = pkg.oracle(P, ref_kdtree=refkd)
+    for name in oracles(pkg):
+        o = pkg.oracle(P, kind=name)
         o.seed(int(g["seed"]))
         o.set_global_map(g["pts"])
         assert o.init_graph(tuple(g["start"])) == 0
@@ -66,8 +71,8 @@ def test_oracle_update_path_matches_golden(pkg, built):
     from make_golden import update_scans
     g = np.load(GOLD / "update_120.npz")
     P = params_of(pkg, g)
-    for name, refkd in oracles(pkg):
-        o = pkg.oracle(P, ref_kdtree=refkd)
+    for name in oracles(pkg):
+        o = pkg.oracle(P, kind=name)
         o.seed(int(g["seed"]))
         o.set_global_map(g["pts"])
         assert o.init_graph(tuple(g["start"])) == 0
@@ -91,7 +96,7 @@ def test_kdtree_port_equals_reference_kdtree(pkg, built):
         pytest.skip("oracle/_ref not built (reference tree absent on this box)")
     P = pkg.INDOOR
     pts = pkg.terrain.indoor(90, h=0.2, seed=3)
-    a, b = pkg.oracle(P, False), pkg.oracle(P, True)
+    a, b = pkg.oracle(P, kind="port"), pkg.oracle(P, kind="refkd")
     for o in (a, b):
         o.seed(5); o.set_global_map(pts); assert o.init_graph((3.27, 4.12, 0.0)) == 0
     ea, eb = a.export(), b.export()
@@ -100,7 +105,7 @@ def test_kdtree_port_equals_reference_kdtree(pkg, built):
     # raster-ordered input (degenerate tree), duplicates in x and y
     raster = pkg.terrain.mountain(60, h=0.1, seed=9, shuffle=False)
     raster[::7, 0] = raster[0, 0]
-    a2, b2 = pkg.oracle(P, False), pkg.oracle(P, True)
+    a2, b2 = pkg.oracle(P, kind="port"), pkg.oracle(P, kind="refkd")
     rng = np.random.default_rng(1)
     q = rng.uniform(-0.5, 6.5, size=(3000, 2)).astype(np.float32)
     q[:200] = raster[:200, :2]   # queries exactly on points
@@ -131,7 +136,7 @@ def test_edge_weight_restatement_vs_numpy(pkg, built):
     on well-conditioned patches."""
     P = pkg.MOUNTAIN
     pts = pkg.terrain.mountain(120, h=0.1, seed=2)
-    o = pkg.oracle(P)
+    o = pkg.oracle(P, kind="port")
     o.set_global_map(pts)
     g = np.load(GOLD / "mountain_120.npz")
     ev = o.edge_eval(g["p1"], g["p2"])
@@ -165,11 +170,135 @@ def test_edge_weight_restatement_vs_numpy(pkg, built):
 
 def test_refine_path_and_frontier(pkg, built):
     P = pkg.MOUNTAIN
-    o = pkg.oracle(P)
     path = np.array([[0, 0, 0], [1, 0, 0.5], [2, 1, 1.0], [3, 3, 0.0]], np.float32)
-    out = o.refine_path(path)
-    assert out.shape == (6, 3)
-    np.testing.assert_allclose(out[0], (path[0] + path[1]) / 2)          # 2 taps at the head
-    np.testing.assert_allclose(out[1], (path[0] + 2 * path[1]) / 3, rtol=1e-6)
-    np.testing.assert_array_equal(out[-1], path[-1])                        # last point kept
-    assert o.refine_path(path[:1]).shape[0] == 0                            # single point -> empty
+    for name in oracles(pkg):
+        o = pkg.oracle(P, kind=name)
+        out = o.refine_path(path)
+        assert out.shape == (6, 3)
+        np.testing.assert_allclose(out[0], (path[0] + path[1]) / 2)          # 2 taps at the head
+        np.testing.assert_allclose(out[1], (path[0] + 2 * path[1]) / 3, rtol=1e-6)
+        np.testing.assert_array_equal(out[-1], path[-1])                        # last point kept
+        assert o.refine_path(path[:1]).shape[0] == 0                            # single point -> empty
+
+
+# ---- the restatement against the reference's own trg.cpp on inputs no golden holds --------------------
+
+needs_ref = pytest.mark.skipif(not REF_LIB.exists(), reason="oracle/_ref/libtrg_ref.so not built (reference tree absent)")
+
+
+def _same_graph(a, b, what):
+    for k in ("iter_ids", "pos", "state", "row_ptr", "col", "weight", "dist"):
+        np.testing.assert_array_equal(getattr(a, k), getattr(b, k), err_msg=f"{what}: {k}")
+
+
+@needs_ref
+@pytest.mark.parametrize("kind,seed", [("mountain", 1), ("mountain", 77), ("indoor", 5), ("stairs", 9), ("indoor", 31)])
+def test_restatement_equals_reference_build(pkg, built, kind, seed):
+    """trg_oracle.cpp (restated) == libtrg_ref.so (the reference's unmodified trg.cpp) bit for bit: graph,
+    CSR, weights, draw count, goal snapping, A* paths, refinePath, checkReplan — fresh maps and seeds."""
+    P = pkg.INDOOR if kind == "indoor" else pkg.MOUNTAIN
+    pts = {"mountain": lambda: pkg.terrain.mountain(150, h=0.1, seed=seed),
+           "indoor": lambda: pkg.terrain.indoor(80, h=0.2, seed=seed),
+           "stairs": lambda: pkg.terrain.stairs(110, h=0.1, seed=seed, riser=0.10)}[kind]()
+    lo, hi = pts[:, :2].min(0), pts[:, :2].max(0)
+    start = (float(lo[0] + 0.4 * (hi[0] - lo[0])), float(lo[1] + 0.45 * (hi[1] - lo[1])), 0.0)
+    r, o = pkg.oracle(P, kind="ref"), pkg.oracle(P, kind="port")
+    for t in (r, o):
+        t.seed(seed); t.set_global_map(pts)
+    rc_r, rc_o = r.init_graph(start), o.init_graph(start)
+    assert rc_r == rc_o
+    if rc_r != 0:
+        return
+    assert r.stat("rng_draws") == o.stat("rng_draws")
+    _same_graph(r.export(), o.export(), "build")
+    assert r.export().n_nodes > 50
+    qs = pkg.terrain.query_pairs(((float(lo[0]) - 1, float(hi[0]) + 1), (float(lo[1]) - 1, float(hi[1]) + 1)), 40, seed=seed)
+    for row in qs:
+        a, b = r.plan(row[:2], row[2:5]), o.plan(row[:2], row[2:5])
+        assert a["found"] == b["found"] and a["goal_known"] == b["goal_known"]
+        np.testing.assert_array_equal(a["ids"], b["ids"])
+        np.testing.assert_array_equal(a["path"], b["path"])
+        for k in ("direct_dist", "path_length", "avg_risk"):
+            assert np.float32(a[k]) == np.float32(b[k]), k
+        if a["found"] and len(a["ids"]) > 1:
+            np.testing.assert_array_equal(r.refine_path(a["path"]), o.refine_path(b["path"]))
+            probe = a["path"][len(a["path"]) // 2, :2]
+            assert r.check_replan(probe, a["path"]) == o.check_replan(probe, b["path"])
+            assert r.check_reached(probe) == o.check_reached(probe)
+
+
+@needs_ref
+def test_restatement_equals_reference_build_updates(pkg, built):
+    """setLocalMap / updateGraph / isFrontier over five scans, reference build vs restatement."""
+    P = pkg.MOUNTAIN
+    pts = pkg.terrain.mountain(140, h=0.1, seed=21)
+    r, o = pkg.oracle(P, kind="ref"), pkg.oracle(P, kind="port")
+    for t in (r, o):
+        t.seed(8); t.set_global_map(pts); assert t.init_graph((5.0, 7.0, 0.0)) == 0
+    rng = np.random.default_rng(3)
+    for step in range(5):
+        cx, cy = 3.0 + 2.0 * step, 7.0 + 0.5 * step
+        m = (np.abs(pts[:, 0] - cx) < 3.0) & (np.abs(pts[:, 1] - cy) < 3.0)
+        scan = pts[m].copy()
+        scan[:, 2] += rng.normal(0, 0.01, size=scan.shape[0]).astype(np.float32)
+        if step in (1, 3):
+            blk = (np.abs(scan[:, 0] - cx - 1.0) < 0.6) & (np.abs(scan[:, 1] - cy) < 0.6)
+            scan[blk, 2] += np.where(rng.uniform(size=int(blk.sum())) < 0.5, 0.9, 0.0).astype(np.float32)
+        for t in (r, o):
+            t.set_local_map(cx, cy, scan)
+        np.testing.assert_array_equal(r.export("local").iter_ids, o.export("local").iter_ids)
+        fq = rng.uniform(1, 13, size=(200, 2)).astype(np.float32)
+        np.testing.assert_array_equal(r.is_frontier(fq), o.is_frontier(fq))
+        np.testing.assert_array_equal(r.is_collision(fq, P.update_collision_threshold, "local"),
+                                      o.is_collision(fq, P.update_collision_threshold, "local"))
+        for t in (r, o):
+            t.update_graph()
+        assert r.stat("rng_draws") == o.stat("rng_draws")
+        _same_graph(r.export(), o.export(), f"scan {step}")
+        np.testing.assert_array_equal(r.export("local").iter_ids, o.export("local").iter_ids)
+
+
+@needs_ref
+def test_reference_root_failure_is_reported_not_fatal(pkg, built):
+    """`exit(1)` of TRG::initGraph (trg.cpp:49-52) when no root can be placed: the harness turns it
+    into rc -1 (like the restatement and the product) and the handle stays usable."""
+    P = pkg.MOUNTAIN
+    pts = pkg.terrain.mountain(60, h=0.1, seed=2)
+    r, o = pkg.oracle(P, kind="ref"), pkg.oracle(P, kind="port")
+    for t in (r, o):
+        t.seed(1); t.set_global_map(pts)
+    far = (500.0, 500.0, 0.0)   # no map point within robot_size of any retry: every root collides
+    with pytest.raises(RuntimeError):
+        r.init_graph(far)
+    with pytest.raises(RuntimeError):
+        o.init_graph(far)
+    assert r.stat("rng_draws") == o.stat("rng_draws") == 2 * 101
+    assert r.init_graph((3.0, 3.0, 0.0)) == 0 and o.init_graph((3.0, 3.0, 0.0)) == 0
+    _same_graph(r.export(), o.export(), "after a failed root")
+
+
+@needs_ref
+def test_reference_kernel_level_answers(pkg, built):
+    """isCollision / kd_nearest_range2 / kd_nearest2 / wireEdge of the reference build vs the restatement
+    on queries that include points exactly on map points, far outside the map, and duplicates."""
+    P = pkg.MOUNTAIN
+    pts = pkg.terrain.stairs(120, h=0.1, seed=4, riser=0.08)
+    r, o = pkg.oracle(P, kind="ref"), pkg.oracle(P, kind="port")
+    for t in (r, o):
+        t.set_global_map(pts)
+    rng = np.random.default_rng(2)
+    q = rng.uniform(-1, 13, size=(6000, 2)).astype(np.float32)
+    q[:300] = pts[:300, :2]
+    for thr in (0.05, P.collision_threshold, 0.5):
+        np.testing.assert_array_equal(r.is_collision(q, thr), o.is_collision(q, thr))
+    for rad in (0.05, 0.3, 0.9):
+        np.testing.assert_array_equal(r.range_count(q, rad), o.range_count(q, rad))
+    (za, ia, ta), (zb, ib, tb) = r.nearest_z(q), o.nearest_z(q)
+    np.testing.assert_array_equal(za, zb); np.testing.assert_array_equal(ia, ib); np.testing.assert_array_equal(ta, tb)
+    a = q[:3000]
+    ang = rng.uniform(0, 2 * np.pi, a.shape[0]); d = rng.uniform(0.05, 1.0, a.shape[0])
+    b = (a + np.stack([d * np.cos(ang), d * np.sin(ang)], 1)).astype(np.float32)
+    p1 = np.column_stack([a, r.nearest_z(a)[0]]).astype(np.float32)
+    p2 = np.column_stack([b, r.nearest_z(b)[0]]).astype(np.float32)
+    ev = r.edge_eval(p1, p2)       # PinnedOracle: raises if the restatement disagrees with the reference
+    assert (ev["stage"] == 0).sum() > 300 and len(set(ev["stage"].tolist())) >= 3
