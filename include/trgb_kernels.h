@@ -135,6 +135,56 @@ int     trgb_nodes_append_launch(trgb_nodes* g, const float* d_xy, int64_t n, vo
 int     trgb_nodes_nearest_launch(const trgb_nodes* g, const float* d_xy, int64_t n, int32_t* d_idx, float* d_d2,
                                   uint8_t* d_tie, void* stream);
 
+/* ---- K9: device-resident graph expansion — TRG::expandGraph (trg.cpp:372-454) as a BFS that runs on the
+ *      GPU including its decisions (trg-planner_b200/csrc/expand.cu). Usable when step 3 of expandGraph
+ *      (neighbour wiring, trg.cpp:429) is off, i.e. expand_dist - robot_size >= 0.25 * expand_dist, and
+ *      the map is sparse enough for the thread-per-query kernels (TRGB_E_STATE otherwise: the caller
+ *      keeps its host-driven path). The host feeds the sampling stream (mt19937 + glibc cosf / sinf live
+ *      on the host side of the boundary) and polls a status block; an exact distance tie between nodes or
+ *      a slope gate within 3 ulp of its threshold interrupts the engine at that pop, which the caller
+ *      then handles itself (reference tie / libm rules) and hands back with trgb_expander_apply_pop. */
+typedef struct trgb_expander trgb_expander;
+typedef struct TrgbExpandParams {
+  float   expand_dist, robot_size, height_threshold, collision_threshold;
+  int32_t sample_num;
+  float   max_slope;     /* atan2f(height_threshold, robot_size) as the HOST libm computes it (trg.cpp:269) */
+  int32_t max_pops;      /* queue pops per step, 32..8192 */
+  int32_t window_words;  /* sampling window per pop = 64 * window_words draws, 2..4 */
+  int32_t new_state;     /* NodeState of created nodes: 0 Valid (ref_id == 0, trg.cpp:420) or 1 Frontier */
+} TrgbExpandParams;
+typedef struct TrgbExpandStatus {
+  int32_t head, tail, n_nodes, interrupt, interrupt_pop;
+  int64_t n_req, pos, draws_end;
+  int64_t window_tests, steps, steps_active, rounds, pops, z_ties, redo_pops, samples, created;
+  float   mean, var;
+} TrgbExpandStatus;
+int  trgb_expander_create(trgb_expander** out, const trgb_map* map, const TrgbExpandParams* prm, float x0, float y0,
+                          float x1, float y1, int64_t node_capacity);
+void trgb_expander_destroy(trgb_expander* e);
+/* point an existing engine at a rebuilt map of the same extent (keeps its buffers); TRGB_E_STATE if it does not fit */
+int  trgb_expander_rebind(trgb_expander* e, const trgb_map* map, float x0, float y0, float x1, float y1,
+                          int64_t node_capacity);
+/* reset: the root (node 0, Valid) is the only node and the only queue entry; draws start at stream position draw_pos */
+int  trgb_expander_begin(trgb_expander* e, float root_x, float root_y, float root_z, int64_t draw_pos);
+/* n more (expand_dist*cosf(angle), expand_dist*sinf(angle)) pairs following the ones pushed so far */
+int  trgb_expander_push_draws(trgb_expander* e, const float* xy, int64_t n);
+/* queue n_steps steps (asynchronous); pops_hint sizes the launches (a step takes at most that many pops) */
+int  trgb_expander_enqueue(trgb_expander* e, int n_steps, int pops_hint);
+/* asynchronous copy of the status block into slot 0/1 + wait for it */
+int  trgb_expander_snapshot(trgb_expander* e, int slot);
+int  trgb_expander_wait(trgb_expander* e, int slot, TrgbExpandStatus* out);
+int  trgb_expander_nodes(trgb_expander* e, int64_t from, int64_t to, float* xyz, int8_t* state);
+int  trgb_expander_head_pop(trgb_expander* e, int32_t* node_id);
+/* result of a pop the caller handled: nodes (x, y, z, state) in creation order, requests in call order
+ * (req_b with bit 31 set = parent edge carrying its weight / dist; otherwise wireEdge(a, b) to evaluate) */
+int  trgb_expander_apply_pop(trgb_expander* e, int n_new, const float* nodes_xyzs, int n_req, const int32_t* req_a,
+                             const int32_t* req_b, const float* req_w, const float* req_d, int64_t new_pos);
+/* evaluate the recorded wireEdge requests (one saturated K4 launch), keep the first success of every pair,
+ * group by node in request order = the reference's edges_ order. Ids = creation order (root 0). */
+int  trgb_expander_finalize(trgb_expander* e, int64_t* n_nodes, int64_t* n_directed_edges);
+int  trgb_expander_download(trgb_expander* e, float* xyz, int8_t* state, int64_t* row_ptr, int32_t* col, float* weight,
+                            float* dist);
+
 /* ---- K8: voxel-grid centroid filter — the optional down-sampling of the map ingestion,
  *      TRGPlanner::loadPrebuiltMap -> pcl::VoxelGrid (src/planner/trg_planner.cpp:90-94). One output
  *      point per occupied leaf = centroid, in ascending leaf index (PCL's order). Returns TRGB_E_STATE

@@ -139,7 +139,7 @@ class TrgFacade:
 
     def counts(self, type_="global"):
         n, e = C.c_int64(), C.c_int64()
-        self._f("graph_counts")(self.h, type_.encode(), C.byref(n), C.byref(e))
+        self._chk(self._f("graph_counts")(self.h, type_.encode(), C.byref(n), C.byref(e)), "graph_counts")
         return n.value, e.value
 
     def export(self, type_="global", edges: bool = True) -> GraphSnapshot:

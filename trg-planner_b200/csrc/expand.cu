@@ -1,0 +1,1377 @@
+// K9 — device-resident graph expansion: TRG::expandGraph (trg.cpp:372-454) as a BFS that lives on the
+// GPU, decisions included. The host only feeds the sampling stream and polls a status block.
+//
+// The reference pops one node at a time: draw angles until `sample_num` collision-free samples
+// (:384-403), then for each sample look up the nearest EXISTING node and either wire to it or insert
+// a new node (:406-452). Every decision depends on the nodes inserted by earlier samples, so the
+// loop looks sequential. It is not: a sample's outcome depends only on nodes closer to it than its
+// parent (expand_dist away), and within one BFS frontier the chains of "my outcome depends on an
+// earlier, still undecided sample next to me" are short (5 - 8 links). One STEP of this engine
+// handles up to a few thousand queued pops at once:
+//
+//   k_exp_plan     pops of this step, their guessed stream positions (running mean / variance)
+//   k_exp_window   collision bit of every (pop, draw) in a window around the guess   [K2 device code]
+//   k_exp_tables   per pop: draws consumed as a function of the start offset; composed per 32 pops
+//   k_exp_top      the exact chain o_{i+1} = o_i + consumed_i(o_i) over the composed blocks
+//   k_exp_emit     accepted samples of every pop whose chain position is now known
+//   k_exp_nearest  nearest node among those that existed before the step               [K5 grid]
+//   K3 + K4        height and parent edge of every sample that may become a node (existing kernels)
+//   k_exp_commit   deterministic-reservation rounds: a sample is decided once no earlier undecided
+//                  sample that could still become a node lies within its current nearest distance;
+//                  decided samples are applied in (pop, sample) order: node ids by prefix sum, queue
+//                  pushes, wire requests — exactly the reference's sequential outcome
+//
+// Edges to existing nodes do not feed back into the expansion when step 3 of expandGraph is off
+// (trg.cpp:429, the mountain configuration): they are recorded as requests and evaluated in one
+// saturated K4 launch at the end (trgb_expander_finalize), then grouped into adjacency lists in
+// request order by two radix sorts.
+//
+// Exactness hazards are never guessed: an exact distance tie between two nodes, or a slope-gate
+// decision within 3 ulp of the threshold (the reference uses glibc's atan2f), interrupts the engine
+// at that pop; the host library handles that single pop with the reference's tie / libm rules and
+// resumes (trgb_expander_apply_pop).
+#include <cooperative_groups.h>
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace trgb {
+
+constexpr int kExpMaxPops = 8192;     // pops per step (upper bound of TrgbExpandParams::max_pops)
+constexpr int kExpMaxS = 32;          // sample_num upper bound of the device engine
+constexpr int kExpSlowWords = 17;     // slow mode: one pop, 1088-bit window (>= 1001 + sample_num draws)
+constexpr int kExpHash = 8192;        // buckets of the commit kernel's hash grid (shared memory)
+
+enum { EXP_INT_NONE = 0, EXP_INT_TIE = 1, EXP_INT_SLOPE = 2, EXP_INT_CAPACITY = 3, EXP_INT_DRAWS = 4 };
+
+// sample decision states
+enum : int { ST_UNDECIDED = 0, ST_SKIP = 1, ST_WIRE = 2, ST_CREATE = 3, ST_VOID = 4 };
+
+struct ExpCtl {
+  // persistent
+  int head, tail;          // BFS queue [head, tail)
+  int n_nodes;
+  int interrupt, interrupt_pop;  // interrupt_pop: queue index of the pop the host must handle
+  int stuck;               // consecutive steps whose chain could not finish the first pop
+  long long n_req;
+  long long pos;           // absolute stream position of the next draw
+  long long draws_base, draws_end;
+  float mean, var;         // running draws / pop statistics
+  // step scratch
+  int m, W, words, D, slow;
+  int n_done;              // pops of this step whose chain position is known
+  int n_commit;
+  int ipop;                // first pop of the step the host must handle (tie / slope), INT_MAX = none
+  int und[2][16];          // undecided samples per commit CTA, double-buffered by round parity
+  long long pos0, pos_done;
+  // statistics
+  long long window_tests, steps, steps_active, rounds, pops, z_ties, redo_pops, samples, created, pc_samples;
+};
+
+struct ExpView {
+  ExpCtl* ctl;
+  // graph nodes
+  float2* node_xy; float* node_z; signed char* node_state; int* queue;
+  int node_cap;
+  // K5 grid over nodes
+  int* ghead; int* gnext; float gx0, gy0, gcell, ginv; int GW, GH;
+  // requests
+  int* req_a; int* req_b; float* req_w; float* req_d; long long req_cap;
+  // stream
+  const float2* draws;
+  // step scratch
+  int* g_off; unsigned long long* mask; unsigned char* ctab; int* blk_end; unsigned char* blk_stop; int* blk_start;
+  int* pop_off; unsigned short* pop_cons; unsigned char* pop_acc;
+  float2* s_xy; float* s_p1; int* s_nn; float* s_d2; unsigned char* s_tie;
+  float* s_z; unsigned char* s_ztie; unsigned char* s_stage; float* s_w; float* s_d;
+  int* st; float* cur_d2; int* cur_nn; int* hnext; unsigned char* s_pc;
+  // params
+  float e, r, hthr, cthr, max_slope; int S, C, norm_words, new_state;
+};
+
+__device__ __forceinline__ int exp_ncell(float v, float origin, float inv, int dim) {
+  const float f = floorf(__fmul_rn(__fsub_rn(v, origin), inv));
+  if (!(f > 0.0f)) return 0;
+  if (f >= (float)dim) return dim - 1;
+  return (int)f;
+}
+
+// ------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_exp_plan(ExpView v, int c_step) {
+  ExpCtl* c = v.ctl;
+  __shared__ int s_m, s_words, s_D, s_fit;
+  __shared__ float s_mean, s_var;
+  __shared__ long long s_room;
+  if (threadIdx.x == 0) {
+    c->steps++;
+    int m = 0;
+    c->slow = 0;
+    c->n_done = 0;
+    c->n_commit = 0;
+    c->ipop = 0x7fffffff;
+    int words = v.norm_words;
+    if (!c->interrupt && c->head < c->tail) {
+      const int avail = c->tail - c->head;
+      if (c->stuck >= 1) {  // the first pop needs more draws than a normal window covers
+        m = 1;
+        words = kExpSlowWords;
+        c->slow = 1;
+      } else {
+        const int D = 64 * words - 32;
+        // longest chain whose drift (random walk, variance `var` per pop) stays inside the admissible
+        // start offsets with ~2 sigma: 2 + 2 sqrt(L var) <= D / 2
+        const float half = 0.5f * (float)D - 2.f;
+        int L = (int)((half * half * 0.25f) / fmaxf(c->var, 0.05f));
+        L = max(L, 64);
+        m = min(min(avail, c_step), min(L, v.C));
+      }
+      c->W = 64 * words; c->words = words; c->D = c->slow ? 1 : 64 * words - 32;
+      c->pos0 = c->pos;
+    }
+    s_m = m; s_words = words; s_D = c->D; s_fit = m;
+    s_mean = c->mean; s_var = c->var;
+    s_room = c->draws_end - c->pos;  // draws available from pos0 on
+  }
+  __syncthreads();
+  // guesses (relative to pos0): exact for pop 0, extrapolated with the running mean minus a lead that
+  // grows like the random walk for the others; never below the S draws every pop consumes. The step
+  // keeps the pops whose whole window lies inside the draws pushed so far.
+  const int m0 = s_m, W = 64 * s_words, D = s_D;
+  const int smin = min(v.S, 1001);
+  for (int i = threadIdx.x; i < m0; i += blockDim.x) {
+    int g = 0;
+    if (i > 0) {
+      const float lead = fminf(2.f + 2.f * sqrtf((float)i * s_var), 0.5f * (float)D);
+      g = max(i * smin, (int)floorf((float)i * s_mean - lead));
+    }
+    v.g_off[i] = g;
+    if ((long long)g + W > s_room) atomicMin(&s_fit, i);  // guesses are non-decreasing in i
+  }
+  __syncthreads();
+  const int m = s_fit;  // 0: the host must push draws first (it sees pos / draws_end in the status block)
+  if (threadIdx.x == 0) {
+    c->m = m;
+    if (m > 0) c->steps_active++;
+  }
+  const int n = m * s_words;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) v.mask[k] = 0ull;
+}
+
+// ------------------------------------------------------------------------------------------
+// sampling windows: one thread per (pop, draw); bit j of mask[pop] = isCollision(node + draw[g + j])
+// (trg.cpp:395-398). Same per-thread routine as k_sample_window_tq.
+// ------------------------------------------------------------------------------------------
+#define EXP_FALLBACK_BEGIN(res)                                \
+  if (__syncthreads_or((res) == 2)) {                          \
+    float* wbuf = zsm + (threadIdx.x >> 5) * 32 * cap;         \
+    unsigned ov = __ballot_sync(FULL, (res) == 2);             \
+    while (ov) {                                               \
+      const int src = __ffs(ov) - 1;                           \
+      ov &= ov - 1;
+#define EXP_FALLBACK_END \
+    }                    \
+    __syncthreads();     \
+  }
+
+__global__ void TQ_BOUNDS k_exp_window(MapView m, ExpView v, int cap) {
+  extern __shared__ float zsm[];
+  float* zcol = zsm + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const ExpCtl* c = v.ctl;
+  const int np = c->m;
+  if (np == 0) return;
+  const int W = c->W, words = c->words;
+  const int items = np * W;
+  const long long dbase = c->pos0 - c->draws_base;
+  const int head = c->head;
+  for (int base = blockIdx.x * kTqThreads; base < items; base += gridDim.x * kTqThreads) {
+    const int it = base + threadIdx.x;
+    float sx = 0.f, sy = 0.f;
+    int res = 0, pop = 0, j = 0;
+    if (it < items) {
+      pop = it / W;
+      j = it - pop * W;
+      const float2 np2 = v.node_xy[v.queue[head + pop]];
+      const float2 d = __ldg(v.draws + (dbase + v.g_off[pop] + j));
+      sx = __fadd_rn(np2.x, d.x);  // trg.cpp:396-397
+      sy = __fadd_rn(np2.y, d.y);
+      res = thread_is_collision(m, sx, sy, v.r, v.hthr, v.cthr, zcol, kTqThreads);
+    }
+    EXP_FALLBACK_BEGIN(res)
+      const float qx = __shfl_sync(FULL, sx, src), qy = __shfl_sync(FULL, sy, src);
+      const bool cc = warp_is_collision(m, qx, qy, v.r, v.hthr, v.cthr, wbuf, 32 * cap - 256, nullptr);
+      if (lane == src) res = cc ? 1 : 0;
+    EXP_FALLBACK_END
+    if (it < items && res) atomicOr(v.mask + (size_t)pop * words + (j >> 6), 1ull << (j & 63));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd((unsigned long long*)&v.ctl->window_tests, (unsigned long long)items);
+}
+
+// draws consumed by a pop that starts at bit `r` of its window: S collision-free draws (trg.cpp:387-403;
+// the trial cap of :388 cannot trigger inside a normal window of <= 256 draws). 255 = the window ends first.
+__device__ __forceinline__ int next_zero(const unsigned long long (&mk)[4], int words, int from) {  // first free draw at or after `from`
+  int w = from >> 6;
+  if (w >= words) return -1;
+  unsigned long long cur = ~mk[w] & (~0ull << (from & 63));
+  while (true) {
+    if (cur) return w * 64 + __ffsll((long long)cur) - 1;
+    if (++w >= words) return -1;
+    cur = ~mk[w];
+  }
+}
+
+constexpr int kRow = 228;  // bytes per table row in shared memory (57 words: lanes hit distinct banks)
+
+// consumed(start offset) of one pop for every start offset < D, by one lane: the S-th free draw at or
+// after r moves to the next free draw whenever r passes a free draw (two pointers, O(W) in all)
+__device__ __forceinline__ void pop_table(const unsigned long long* gmask, int words, int D, int S, unsigned char* row) {
+  unsigned long long mk[4] = {~0ull, ~0ull, ~0ull, ~0ull};
+  for (int w = 0; w < words; ++w) mk[w] = gmask[w];
+  int q = -1;  // position of the S-th free draw at or after r
+  {
+    int p = -1;
+    for (int k = 0; k < S; ++k) {
+      p = next_zero(mk, words, p + 1);
+      if (p < 0) break;
+    }
+    q = p;
+  }
+  for (int r = 0; r < D; ++r) {
+    const int cc = q < 0 ? 255 : min(255, q + 1 - r);
+    row[r] = (unsigned char)cc;
+    const bool freebit = !((mk[r >> 6] >> (r & 63)) & 1ull);
+    if (freebit && q >= 0) q = next_zero(mk, words, q + 1);
+  }
+}
+
+// one warp per block of 32 pops: lane p builds the table of pop p, then lane r composes the block's
+// map (start offset at its first pop -> end position, pops completed)
+__global__ void __launch_bounds__(128) k_exp_tables(ExpView v) {
+  const ExpCtl* c = v.ctl;
+  const int m = c->m;
+  if (m == 0 || c->slow) return;
+  const int words = c->words, D = c->D, S = v.S;
+  const int lane = threadIdx.x & 31;
+  const int nblk = (m + 31) >> 5;
+  __shared__ unsigned char tab[4][32 * kRow];
+  unsigned char* t = tab[threadIdx.x >> 5];
+  for (int b = blockIdx.x * 4 + (threadIdx.x >> 5); b < nblk; b += gridDim.x * 4) {
+    const int first = b << 5;
+    const int cnt = min(32, m - first);
+    if (lane < cnt) pop_table(v.mask + (size_t)(first + lane) * words, words, D, S, t + lane * kRow);
+    __syncwarp();
+    const int g0 = v.g_off[first];
+    const int gl = lane < cnt ? v.g_off[first + lane] : 0;
+    for (int r = lane; r < D; r += 32) {  // D is a multiple of 32: the warp stays converged for the shuffles
+      int a = g0 + r;  // relative to pos0
+      int stop = cnt;
+      for (int p = 0; p < cnt; ++p) {
+        const int gp = __shfl_sync(FULL, gl, p);
+        if (stop == cnt) {
+          const int rr = a - gp;
+          if (rr < 0 || rr >= D) stop = p;
+          else {
+            const int cc = t[p * kRow + rr];
+            if (cc == 255) stop = p; else a += cc;
+          }
+        }
+      }
+      v.blk_end[(size_t)b * 256 + r] = a;
+      v.blk_stop[(size_t)b * 256 + r] = (unsigned char)stop;
+    }
+    __syncwarp();
+  }
+}
+
+// the chain over the composed blocks: tables staged in shared memory, then one thread walks them;
+// or the single pop of slow mode
+__global__ void __launch_bounds__(1024) k_exp_top(ExpView v) {
+  ExpCtl* c = v.ctl;
+  const int m = c->m;
+  if (m == 0) return;
+  const int S = v.S;
+  if (c->slow) {
+    if (threadIdx.x != 0) return;
+    // sequential walk with the trial cap (trg.cpp:387-403): `if (trial_sample > 1000) break` is
+    // checked before every draw
+    const unsigned long long* mk = v.mask;
+    int acc = 0, trials = 0, j = 0;
+    const int W = c->W;
+    bool ok = true;
+    while (acc < S) {
+      if (trials > 1000) break;
+      if (j >= W) { ok = false; break; }
+      const bool coll = (mk[j >> 6] >> (j & 63)) & 1ull;
+      ++j;
+      if (coll) ++trials; else ++acc;
+    }
+    if (!ok) {  // cannot happen: W >= 1001 + S
+      c->n_done = 0;
+      return;
+    }
+    v.pop_off[0] = 0;
+    v.pop_cons[0] = (unsigned short)j;
+    v.blk_start[0] = 0;
+    c->n_done = 1;
+    c->pos_done = c->pos0 + j;
+    return;
+  }
+  extern __shared__ int top_sm[];
+  const int D = c->D;
+  const int nblk = (m + 31) >> 5;
+  int* s_end = top_sm;                                            // nblk * D
+  unsigned char* s_stop = reinterpret_cast<unsigned char*>(s_end + nblk * D);  // nblk * D
+  for (int k = threadIdx.x; k < nblk * D; k += blockDim.x) {
+    const int b = k / D, r = k - b * D;
+    s_end[k] = v.blk_end[(size_t)b * 256 + r];
+    s_stop[k] = v.blk_stop[(size_t)b * 256 + r];
+  }
+  __shared__ int s_g[kExpMaxPops / 32];
+  for (int b = threadIdx.x; b < nblk; b += blockDim.x) s_g[b] = v.g_off[b << 5];
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  int a = 0, done = 0;
+  for (int b = 0; b < nblk; ++b) {
+    const int first = b << 5;
+    const int rr = a - s_g[b];
+    if (rr < 0 || rr >= D) break;
+    v.blk_start[b] = a;
+    const int cnt = min(32, m - first);
+    const int stop = s_stop[b * D + rr];
+    a = s_end[b * D + rr];
+    done = first + stop;
+    if (stop < cnt) break;
+  }
+  c->n_done = done;
+  c->pos_done = c->pos0 + a;
+}
+
+// accepted samples of every pop with a known chain position; one warp per block of 32 pops
+__global__ void __launch_bounds__(128) k_exp_emit(ExpView v) {
+  const ExpCtl* c = v.ctl;
+  const int n_done = c->n_done;
+  if (n_done == 0) return;
+  const int words = c->words, S = v.S, D = c->D;
+  const int lane = threadIdx.x & 31;
+  const int nblk = (n_done + 31) >> 5;
+  const int head = c->head;
+  const long long dbase = c->pos0 - c->draws_base;
+  __shared__ unsigned char tab[4][32 * kRow];
+  unsigned char* t = tab[threadIdx.x >> 5];
+  for (int b = blockIdx.x * 4 + (threadIdx.x >> 5); b < nblk; b += gridDim.x * 4) {
+    const int first = b << 5;
+    const int cnt = min(32, n_done - first);
+    int my_start = 0, my_cons = 0;
+    if (c->slow) {
+      my_start = 0;
+      my_cons = v.pop_cons[0];
+    } else {
+      // rebuild the block's tables (cheaper than reading them back) and walk it; lane p keeps pop p
+      if (lane < cnt) pop_table(v.mask + (size_t)(first + lane) * words, words, D, S, t + lane * kRow);
+      __syncwarp();
+      const int gl = lane < cnt ? v.g_off[first + lane] : 0;
+      int a = v.blk_start[b];
+      for (int p = 0; p < cnt; ++p) {
+        const int rr = a - __shfl_sync(FULL, gl, p);
+        const int cc = t[p * kRow + rr];
+        if (lane == p) { my_start = a; my_cons = cc; }
+        a += cc;
+      }
+      __syncwarp();
+    }
+    if (lane < cnt) {
+      const int i = first + lane;
+      const int g = v.g_off[i];
+      const unsigned long long* mk = v.mask + (size_t)i * words;
+      const int node = v.queue[head + i];
+      const float2 np2 = v.node_xy[node];
+      const float nz = v.node_z[node];
+      v.pop_off[i] = my_start;
+      v.pop_cons[i] = (unsigned short)my_cons;
+      int acc = 0;
+      for (int j = my_start - g; j < my_start - g + my_cons; ++j) {
+        const bool coll = (mk[j >> 6] >> (j & 63)) & 1ull;
+        if (coll) continue;
+        const float2 d = __ldg(v.draws + (dbase + g + j));
+        const size_t slot = (size_t)i * S + acc;
+        v.s_xy[slot] = make_float2(__fadd_rn(np2.x, d.x), __fadd_rn(np2.y, d.y));
+        v.s_p1[3 * slot] = np2.x; v.s_p1[3 * slot + 1] = np2.y; v.s_p1[3 * slot + 2] = nz;
+        ++acc;
+      }
+      v.pop_acc[i] = (unsigned char)acc;  // < S only when the trial cap ended the pop
+    }
+  }
+}
+
+// nearest node (among those that existed before the step) of every sample slot; slots without a
+// sample get d2 = 0, which makes the K3 / K4 launches skip them
+__global__ void __launch_bounds__(256) k_exp_nearest(ExpView v, int c_step) {
+  const ExpCtl* c = v.ctl;
+  const int S = v.S;
+  const int n_done = c->n_done;
+  const int total = c_step * S;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < total; s += gridDim.x * blockDim.x) {
+    const int i = s / S, j = s - i * S;
+    if (i >= n_done || j >= v.pop_acc[i]) {
+      v.s_d2[s] = 0.f;
+      v.s_nn[s] = -1;
+      v.s_tie[s] = 0;
+      continue;
+    }
+    const float2 p = v.s_xy[s];
+    float bd = INFINITY;
+    int bi = -1, tie = 0;
+    const int qcx = exp_ncell(p.x, v.gx0, v.ginv, v.GW), qcy = exp_ncell(p.y, v.gy0, v.ginv, v.GH);
+    const float fuzz = 4e-6f * (fabsf(p.x) + fabsf(p.y) + v.gcell * (float)(v.GW + v.GH));
+    const int maxr = max(v.GW, v.GH);
+    auto scan = [&](int e) {
+      for (; e >= 0; e = v.gnext[e]) {
+        const float2 q = v.node_xy[e];
+        const float dx = __fsub_rn(q.x, p.x), dy = __fsub_rn(q.y, p.y);
+        const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        if (d2 < bd) { bd = d2; bi = e; tie = 0; }
+        else if (d2 == bd && e != bi) tie = 1;
+      }
+    };
+    {  // the 3 x 3 block: all nine list heads are fetched before any list is walked
+      int hd[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const int xx = qcx + (k % 3) - 1, yy = qcy + (k / 3) - 1;
+        hd[k] = (xx < 0 || yy < 0 || xx >= v.GW || yy >= v.GH) ? -1 : v.ghead[(size_t)yy * v.GW + xx];
+      }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) scan(hd[k]);
+    }
+    for (int R = 1; R <= maxr; ++R) {
+      if (R > 1) {
+        for (int yy = qcy - R; yy <= qcy + R; ++yy) {
+          if (yy < 0 || yy >= v.GH) continue;
+          const bool edge_row = (yy == qcy - R || yy == qcy + R);
+          for (int xx = qcx - R; xx <= qcx + R; ++xx) {
+            if (xx < 0 || xx >= v.GW) continue;
+            if (!edge_row && xx != qcx - R && xx != qcx + R) continue;  // ring only
+            scan(v.ghead[(size_t)yy * v.GW + xx]);
+          }
+        }
+      }
+      const float g = (float)R * v.gcell * 0.9999f - fuzz;
+      if (bi >= 0 && g > 0.f && bd <= g * g) break;
+      if (qcx - R <= 0 && qcy - R <= 0 && qcx + R >= v.GW - 1 && qcy + R >= v.GH - 1) break;
+    }
+    v.s_d2[s] = bd;
+    v.s_nn[s] = bi;
+    v.s_tie[s] = (unsigned char)tie;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// commit: one CTA
+// ------------------------------------------------------------------------------------------
+// slope gate of wireEdge (trg.cpp:269-274) with the reference's float operands; the comparison of
+// the float results of glibc's atan2f is reproduced only when it cannot depend on the last ulps:
+// 0 pass, 1 reject, 2 within 3 float ulps of the threshold (host decides)
+__device__ __forceinline__ int slope_gate(float x1, float y1, float z1, float x2, float y2, float z2, float max_slope) {
+  const float dz = fabsf(__fsub_rn(z1, z2));
+  const float ax = __fsub_rn(x1, x2), ay = __fsub_rn(y1, y2);
+  const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)));
+  const double s = atan2((double)dz, (double)d);
+  const double ms = (double)max_slope;
+  const double band = 3.0 * 5.9604644775390625e-08 * fmax(1.0, ms * 2.0);  // 3 ulp of a float in [0.5, 2)
+  if (s > ms + band) return 1;
+  if (s < ms - band) return 0;
+  return 2;
+}
+
+__device__ __forceinline__ unsigned exp_hash(int cx, int cy) {
+  return ((unsigned)cx * 73856093u ^ (unsigned)cy * 19349663u) & (kExpHash - 1);
+}
+
+constexpr int kCommitCtas = 8;  // thread-block cluster running the reservation rounds
+
+// Reservation rounds on a cluster of kCommitCtas CTAs (samples are dealt round-robin to their threads;
+// cluster barriers between the read and the write half of a round), then CTA 0 applies the decisions
+// in (pop, sample) order.
+__global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v) {
+  cg::cluster_group cl = cg::this_cluster();
+  const int NC = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+  ExpCtl* c = v.ctl;
+  const int n_done = c->n_done;
+  const int tid = threadIdx.x, T = blockDim.x;
+  if (n_done == 0) {
+    if (rank == 0 && tid == 0 && c->m > 0) {
+      c->stuck++;  // not even the first pop fitted its window: slow mode next
+      c->redo_pops += c->m;
+    }
+    return;
+  }
+  __shared__ int hhead[kExpHash];
+  __shared__ int s_any, s_und;
+  __shared__ unsigned long long s_part[1024];
+  __shared__ unsigned long long s_sum, s_sq, s_tot;
+  const int S = v.S;
+  const int ns = n_done * S;
+  const float r = v.r;
+  const float hcell = v.e * 1.001f + 1e-5f;
+  const float hinv = 1.0f / hcell;
+  const int head = c->head;
+  const int n_nodes0 = c->n_nodes;
+  int* hnext = v.hnext + (size_t)rank * ((size_t)v.C * S);  // this CTA's chains
+  for (int k = tid; k < kExpHash; k += T) hhead[k] = -1;
+  // ---- initial state (dealt over the whole cluster) ----------------------------------------------
+  for (int s = rank * T + tid; s < ns; s += NC * T) {
+    const int i = s / S, j = s - i * S;
+    int st = ST_UNDECIDED;
+    unsigned char pc = 0;
+    if (j >= v.pop_acc[i]) st = ST_VOID;
+    else {
+      if (v.s_tie[s]) atomicMin(&c->ipop, i);  // tie among existing nodes: the host resolves this pop
+      if (__fsqrt_rn(v.s_d2[s]) >= r) {        // trg.cpp:414 with the pre-step nearest node: may become a node
+        // validity of the would-be node = its parent edge (trg.cpp:425, 447): K4 stage + slope gate
+        int valid = 0;
+        if (v.s_stage[s] == TRGB_EDGE_OK) {
+          const float2 p = v.s_xy[s];
+          const int g = slope_gate(v.s_p1[3 * s], v.s_p1[3 * s + 1], v.s_p1[3 * s + 2], p.x, p.y, v.s_z[s], v.max_slope);
+          valid = (g == 0) ? 1 : (g == 1 ? 0 : 2);
+        } else if (v.s_stage[s] == TRGB_EDGE_SKIPPED) {
+          valid = 3;  // cannot happen for a potential creator
+        }
+        pc = (unsigned char)(1 | (valid << 1));  // bit 0 potential creator, bits 1-2: 0 invalid 1 valid 2/3 host decides
+      }
+    }
+    v.st[s] = st;
+    v.s_pc[s] = pc;
+    v.cur_d2[s] = v.s_d2[s];
+    v.cur_nn[s] = v.s_nn[s];
+  }
+  cl.sync();
+  // ---- every CTA hashes all potential creators into its own shared table ---------------------------
+  for (int s = tid; s < ns; s += T) {
+    if (!(v.s_pc[s] & 1)) continue;
+    const float2 p = v.s_xy[s];
+    const unsigned h = exp_hash((int)floorf((p.x - v.gx0) * hinv), (int)floorf((p.y - v.gy0) * hinv));
+    hnext[s] = atomicExch(&hhead[h], s);
+  }
+  __syncthreads();
+  // ---- reservation rounds ----------------------------------------------------------------------------
+  int rounds = 0;
+  while (true) {
+    // read half: nearest decided node so far; wait if an earlier undecided sample that may still become a
+    // node lies at least as close
+    for (int s = rank * T + tid; s < ns; s += NC * T) {
+      if (v.st[s] != ST_UNDECIDED) continue;
+      const float2 p = v.s_xy[s];
+      float bd = v.s_d2[s];
+      int bn = v.s_nn[s];
+      int tie = 0;
+      float mu = INFINITY;  // closest earlier undecided potential creator
+      const int cx = (int)floorf((p.x - v.gx0) * hinv), cy = (int)floorf((p.y - v.gy0) * hinv);
+      for (int yy = cy - 1; yy <= cy + 1; ++yy)
+        for (int xx = cx - 1; xx <= cx + 1; ++xx)
+          for (int j = hhead[exp_hash(xx, yy)]; j >= 0; j = hnext[j]) {
+            if (j >= s) continue;
+            const int sj = v.st[j];
+            if (sj != ST_CREATE && sj != ST_UNDECIDED) continue;
+            const float2 q = v.s_xy[j];
+            const float dx = __fsub_rn(q.x, p.x), dy = __fsub_rn(q.y, p.y);
+            const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+            if (sj == ST_CREATE) {
+              if (d2 < bd) { bd = d2; bn = -2 - j; tie = 0; }
+              else if (d2 == bd && bn != -2 - j) tie = 1;
+            } else if (__fsqrt_rn(v.cur_d2[j]) >= r) {  // (a stale, larger value only delays this sample)
+              mu = fminf(mu, d2);
+            }
+          }
+      const bool wait = mu <= bd;
+      v.cur_d2[s] = bd;
+      v.cur_nn[s] = bn;
+      // the decision itself is written in the second half; the verdict travels in s_tie (its pre-step value was consumed above)
+      v.s_tie[s] = (unsigned char)((wait ? 2 : 0) | (tie ? 1 : 0));
+    }
+    cl.sync();
+    // write half
+    int undecided = 0;
+    for (int s = rank * T + tid; s < ns; s += NC * T) {
+      if (v.st[s] != ST_UNDECIDED) continue;
+      const unsigned char f = v.s_tie[s];
+      if (f & 2) { ++undecided; continue; }
+      const int i = s / S;
+      const int bn = v.cur_nn[s];
+      const float bd = v.cur_d2[s];
+      if (f & 1) atomicMin(&c->ipop, i);
+      int nstate;  // state of the nearest node (NodeState: -1 invalid)
+      if (bn >= 0) nstate = v.node_state[bn];
+      else if (bn <= -2) nstate = (((v.s_pc[-2 - bn] >> 1) & 3) == 0) ? -1 : 0;
+      else nstate = -1;  // no node at all (cannot happen: the root exists)
+      int st;
+      if (nstate == -1) st = ST_SKIP;                               // trg.cpp:411
+      else if (__fsqrt_rn(bd) < r) st = ST_WIRE;                    // trg.cpp:414
+      else {
+        st = ST_CREATE;                                             // trg.cpp:421
+        if (((v.s_pc[s] >> 1) & 3) >= 2) atomicMin(&c->ipop, i);    // slope gate too close to call
+      }
+      v.st[s] = st;
+    }
+    const int und_cta = __syncthreads_count(undecided > 0);
+    if (tid == 0) c->und[rounds & 1][rank] = und_cta;
+    ++rounds;
+    cl.sync();
+    if (tid == 0) {
+      int tot = 0;
+      for (int k = 0; k < NC; ++k) tot += c->und[(rounds - 1) & 1][k];
+      s_und = tot;
+    }
+    __syncthreads();
+    if (s_und == 0) break;
+  }
+  if (rank != 0) return;
+  // ---- CTA 0 applies the decisions of the pops before the first one the host must handle -----------
+  const int n_commit = min(c->ipop, n_done);
+  const int nsc = n_commit * S;
+  // per-thread contiguous runs; packed counters: created (bits 0-20), queued (21-41), requests (42-62)
+  const int per = (nsc + T - 1) / T;
+  const int b0 = min(nsc, tid * per), b1 = min(nsc, b0 + per);
+  unsigned long long mine = 0;
+  for (int s = b0; s < b1; ++s) {
+    const int st = v.st[s];
+    if (st == ST_CREATE) {
+      const int valid = ((v.s_pc[s] >> 1) & 3) == 1;
+      mine += 1ull + (valid ? (1ull << 21) + (1ull << 42) : 0ull);
+    } else if (st == ST_WIRE) {
+      mine += 1ull << 42;
+    }
+  }
+  s_part[tid] = mine;
+  if (tid == 0) { s_sum = 0; s_sq = 0; }
+  __syncthreads();
+  {  // draws / pop statistics of the committed pops
+    unsigned long long a = 0, b = 0;
+    for (int i = tid; i < n_commit; i += T) { const unsigned long long cc = v.pop_cons[i]; a += cc; b += cc * cc; }
+    if (a) { atomicAdd(&s_sum, a); atomicAdd(&s_sq, b); }
+  }
+  // exclusive scan of the 1024 partials by warp 0 (32 values per lane)
+  if (tid < 32) {
+    unsigned long long sum = 0;
+    for (int k = 0; k < 32; ++k) { const unsigned long long x = s_part[tid * 32 + k]; s_part[tid * 32 + k] = sum; sum += x; }
+    unsigned long long inc = sum;
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long t = __shfl_up_sync(FULL, inc, d);
+      if (tid >= d) inc += t;
+    }
+    const unsigned long long exc = inc - sum;
+    for (int k = 0; k < 32; ++k) s_part[tid * 32 + k] += exc;
+    if (tid == 31) {
+      s_tot = inc;
+      const int n_new = (int)(inc & 0x1fffff), n_q = (int)((inc >> 21) & 0x1fffff);
+      const long long n_rq = (long long)((inc >> 42) & 0x1fffff);
+      // capacity: never write past the arrays (the packing bound of the caller makes this unreachable)
+      s_any = (n_nodes0 + n_new > v.node_cap || c->n_req + n_rq > v.req_cap || c->tail + n_q > v.node_cap) ? 1 : 0;
+    }
+  }
+  __syncthreads();
+  if (s_any) {
+    if (tid == 0) {
+      c->interrupt = EXP_INT_CAPACITY;
+      c->interrupt_pop = head;
+      c->n_commit = 0;
+    }
+    return;
+  }
+  const long long req0 = c->n_req;
+  const int tail0 = c->tail;
+  {
+    unsigned long long run = s_part[tid];
+    for (int s = b0; s < b1; ++s) {
+      const int st = v.st[s];
+      const int i = s / S;
+      const int parent = v.queue[head + i];
+      const int nid = n_nodes0 + (int)(run & 0x1fffff);
+      const int qi = tail0 + (int)((run >> 21) & 0x1fffff);
+      const long long ri = req0 + (long long)((run >> 42) & 0x1fffff);
+      if (st == ST_CREATE) {
+        const int valid = ((v.s_pc[s] >> 1) & 3) == 1;
+        const float2 p = v.s_xy[s];
+        v.node_xy[nid] = p;
+        v.node_z[nid] = v.s_z[s];
+        v.node_state[nid] = (signed char)(valid ? v.new_state : -1);
+        v.cur_nn[s] = nid;  // id of the node this sample became (read by later samples' requests)
+        const int cell = exp_ncell(p.y, v.gy0, v.ginv, v.GH) * v.GW + exp_ncell(p.x, v.gx0, v.ginv, v.GW);
+        v.gnext[nid] = atomicExch(v.ghead + cell, nid);
+        if (v.s_ztie[s]) atomicAdd((unsigned long long*)&c->z_ties, 1ull);
+        if (valid) {
+          v.queue[qi] = nid;
+          v.req_a[ri] = parent;
+          v.req_b[ri] = nid | 0x80000000;  // parent edge: evaluated already
+          v.req_w[ri] = v.s_w[s];
+          v.req_d[ri] = v.s_d[s];
+        }
+        run += 1ull + (valid ? (1ull << 21) + (1ull << 42) : 0ull);
+      } else if (st == ST_WIRE) {
+        v.req_a[ri] = parent;
+        v.req_b[ri] = v.cur_nn[s];  // >= 0 existing node, <= -2 sample index (patched below)
+        run += 1ull << 42;
+      }
+    }
+  }
+  __syncthreads();
+  // requests that point at a node created in this step: sample index -> node id
+  {
+    unsigned long long run = s_part[tid];
+    for (int s = b0; s < b1; ++s) {
+      const int st = v.st[s];
+      const long long ri = req0 + (long long)((run >> 42) & 0x1fffff);
+      if (st == ST_CREATE) {
+        const int valid = ((v.s_pc[s] >> 1) & 3) == 1;
+        run += 1ull + (valid ? (1ull << 21) + (1ull << 42) : 0ull);
+      } else if (st == ST_WIRE) {
+        const int b = v.req_b[ri];
+        if (b <= -2) v.req_b[ri] = v.cur_nn[-2 - b];
+        run += 1ull << 42;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned long long tot = s_tot;
+    const int n_new = (int)(tot & 0x1fffff), n_q = (int)((tot >> 21) & 0x1fffff);
+    const long long n_rq = (long long)((tot >> 42) & 0x1fffff);
+    __threadfence();
+    c->n_nodes = n_nodes0 + n_new;
+    c->tail = tail0 + n_q;
+    c->n_req = req0 + n_rq;
+    c->head = head + n_commit;
+    c->n_commit = n_commit;
+    // stream position after the last committed pop
+    long long pos = c->pos0;
+    if (n_commit > 0) pos = c->pos0 + v.pop_off[n_commit - 1] + v.pop_cons[n_commit - 1];
+    c->pos = pos;
+    c->pops += n_commit;
+    c->created += n_new;
+    c->samples += nsc;
+    c->rounds += rounds;
+    c->redo_pops += c->m - n_commit;
+    c->stuck = 0;
+    if (n_commit < n_done) {
+      c->interrupt = EXP_INT_TIE;  // tie or slope: the host handles pop `head` with the reference's rules
+      c->interrupt_pop = c->head;
+    }
+    // running draws / pop statistics (step estimate blended in)
+    if (n_commit >= 8) {
+      const double mu = (double)s_sum / n_commit;
+      const double var = fmax(0.0, (double)s_sq / n_commit - mu * mu);
+      const float w = n_commit >= 256 ? 0.5f : 0.2f;
+      c->mean += w * ((float)mu - c->mean);
+      c->var += w * ((float)var - c->var);
+      if (c->var < 0.05f) c->var = 0.05f;
+    }
+  }
+}
+
+// a pop handled by the host (interrupt): append its nodes, queue entries and requests
+__global__ void k_exp_apply(ExpView v, int n_new, const float* __restrict__ nodes /* x,y,z,state per node */,
+                            int n_req, const int* __restrict__ ra, const int* __restrict__ rb,
+                            const float* __restrict__ rw, const float* __restrict__ rd, long long new_pos) {
+  ExpCtl* c = v.ctl;
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int nid = c->n_nodes;
+  int tail = c->tail;
+  for (int k = 0; k < n_new; ++k, ++nid) {
+    const float x = nodes[4 * k], y = nodes[4 * k + 1];
+    v.node_xy[nid] = make_float2(x, y);
+    v.node_z[nid] = nodes[4 * k + 2];
+    const int stt = (int)nodes[4 * k + 3];
+    v.node_state[nid] = (signed char)stt;
+    const int cell = exp_ncell(y, v.gy0, v.ginv, v.GH) * v.GW + exp_ncell(x, v.gx0, v.ginv, v.GW);
+    v.gnext[nid] = v.ghead[cell];
+    v.ghead[cell] = nid;
+    if (stt != -1) v.queue[tail++] = nid;
+  }
+  long long ri = c->n_req;
+  for (int k = 0; k < n_req; ++k, ++ri) {
+    v.req_a[ri] = ra[k]; v.req_b[ri] = rb[k]; v.req_w[ri] = rw[k]; v.req_d[ri] = rd[k];
+  }
+  c->n_nodes = nid;
+  c->tail = tail;
+  c->n_req = ri;
+  c->head += 1;
+  c->pos = new_pos;
+  c->pops += 1;
+  c->interrupt = EXP_INT_NONE;
+  c->stuck = 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// finalize: evaluate the wire requests, keep the first success of every unordered pair, group by node
+// ------------------------------------------------------------------------------------------
+__global__ void k_fin_prepare(ExpView v, long long n_req, float* __restrict__ p1, float2* __restrict__ p2,
+                              float* __restrict__ skip) {
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n_req; k += (long long)gridDim.x * blockDim.x) {
+    const int a = v.req_a[k], b = v.req_b[k];
+    if (b < 0) {  // parent edge, evaluated during the expansion
+      skip[k] = 0.f;
+      p1[3 * k] = p1[3 * k + 1] = p1[3 * k + 2] = 0.f;
+      p2[k] = make_float2(1.f, 0.f);
+      continue;
+    }
+    const float2 pa = v.node_xy[a], pb = v.node_xy[b];
+    p1[3 * k] = pa.x; p1[3 * k + 1] = pa.y; p1[3 * k + 2] = v.node_z[a];
+    p2[k] = pb;
+    skip[k] = INFINITY;
+  }
+}
+
+// ok[k] = 1 when request k would create its edge if it were the first of its pair (trg.cpp:255, 269-329);
+// 2 = slope gate too close to call (host decides)
+__global__ void k_fin_gate(ExpView v, long long n_req, const unsigned char* __restrict__ stage, const float* __restrict__ w,
+                           const float* __restrict__ d, unsigned char* __restrict__ ok, int* __restrict__ unc_list,
+                           int* __restrict__ unc_count, int unc_cap) {
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n_req; k += (long long)gridDim.x * blockDim.x) {
+    const int a = v.req_a[k], b = v.req_b[k];
+    if (b < 0) { ok[k] = 1; continue; }
+    if (a == b) { ok[k] = 0; continue; }  // trg.cpp:255
+    int res = 0;
+    if (stage[k] == TRGB_EDGE_OK) {
+      const float2 pa = v.node_xy[a], pb = v.node_xy[b];
+      const int g = slope_gate(pa.x, pa.y, v.node_z[a], pb.x, pb.y, v.node_z[b], v.max_slope);
+      if (g == 0) res = 1;
+      else if (g == 2) {
+        res = 2;
+        const int slot = atomicAdd(unc_count, 1);
+        if (slot < unc_cap) unc_list[slot] = (int)k;
+      }
+    }
+    if (res == 1) { v.req_w[k] = w[k]; v.req_d[k] = d[k]; }
+    ok[k] = (unsigned char)res;
+  }
+}
+
+__global__ void k_fin_keys(ExpView v, long long n_req, const unsigned char* __restrict__ ok,
+                           unsigned long long* __restrict__ key, unsigned int* __restrict__ val, int* __restrict__ count) {
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n_req; k += (long long)gridDim.x * blockDim.x) {
+    if (ok[k] != 1) continue;
+    const int a = v.req_a[k], b = v.req_b[k] & 0x7fffffff;
+    const unsigned lo = (unsigned)min(a, b), hi = (unsigned)max(a, b);
+    const int slot = atomicAdd(count, 1);
+    key[slot] = ((unsigned long long)lo << 32) | hi;
+    val[slot] = (unsigned)k;
+  }
+}
+
+// after the (pair, request index) sort: the first entry of every pair is the edge; emit both directions
+__global__ void k_fin_edges(ExpView v, int n, const unsigned long long* __restrict__ key, const unsigned int* __restrict__ val,
+                            unsigned long long* __restrict__ dkey, unsigned int* __restrict__ dval, int* __restrict__ count) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (i > 0 && key[i - 1] == key[i]) continue;  // a later request for the same pair: edge exists (trg.cpp:258-267)
+    const unsigned k = val[i];
+    const int a = v.req_a[k], b = v.req_b[k] & 0x7fffffff;
+    const int slot = atomicAdd(count, 2);
+    dkey[slot] = ((unsigned long long)(unsigned)a << 32) | k;      // node1->edges_.push_back(edge to node2)
+    dval[slot] = (unsigned)b;
+    dkey[slot + 1] = ((unsigned long long)(unsigned)b << 32) | k;  // node2->edges_.push_back(edge to node1)
+    dval[slot + 1] = (unsigned)a;
+  }
+}
+
+__global__ void k_fin_csr(ExpView v, int n_dir, int n_nodes, const unsigned long long* __restrict__ dkey,
+                          const unsigned int* __restrict__ dval, long long* __restrict__ row_ptr, int* __restrict__ col,
+                          float* __restrict__ w, float* __restrict__ d) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= n_dir; i += gridDim.x * blockDim.x) {
+    const int src = i < n_dir ? (int)(dkey[i] >> 32) : n_nodes;
+    const int prev = i > 0 ? (int)(dkey[i - 1] >> 32) : -1;
+    for (int s = prev + 1; s <= src; ++s) row_ptr[s] = i;  // rows without edges get an empty range
+    if (i < n_dir) {
+      const unsigned k = (unsigned)(dkey[i] & 0xffffffffu);
+      col[i] = (int)dval[i];
+      w[i] = v.req_w[k];
+      d[i] = v.req_d[k];
+    }
+  }
+}
+
+}  // namespace trgb
+
+using namespace trgb;
+
+struct trgb_expander {
+  const trgb_map* map = nullptr;
+  TrgbExpandParams prm{};
+  ExpView v{};
+  cudaStream_t st = nullptr;
+  int cap = 0;               // z-column capacity of the window kernel
+  size_t win_smem = 0;
+  int win_grid = 0;
+  // owned device memory
+  std::vector<void*> owned;
+  float2* d_draws = nullptr;
+  long long draws_cap = 0, draws_base = 0, draws_end = 0;
+  ExpCtl* h_status[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  // finalize outputs
+  long long* d_row = nullptr; int* d_col = nullptr; float* d_w = nullptr; float* d_d = nullptr;
+  int n_dir = 0;
+  int n_nodes_final = 0;
+};
+
+namespace {
+template <class T>
+int dalloc(trgb_expander* e, T** p, size_t n) {
+  void* q = nullptr;
+  cudaError_t err = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+  if (err != cudaSuccess) return cuda_fail(err, "cudaMalloc(expander)", __FILE__, __LINE__);
+  e->owned.push_back(q);
+  *p = static_cast<T*>(q);
+  return TRGB_OK;
+}
+#define EXP_ALLOC(ptr, n) do { int _rc = dalloc(e, &(ptr), (n)); if (_rc) return _rc; } while (0)
+}  // namespace
+
+extern "C" void trgb_expander_destroy(trgb_expander* e) {
+  if (!e) return;
+  cudaDeviceSynchronize();
+  for (void* p : e->owned) cudaFree(p);
+  if (e->d_draws) cudaFree(e->d_draws);
+  for (int k = 0; k < 2; ++k) {
+    if (e->h_status[k]) cudaFreeHost(e->h_status[k]);
+    if (e->ev[k]) cudaEventDestroy(e->ev[k]);
+  }
+  if (e->d_row) cudaFreeAsync(e->d_row, 0);
+  if (e->d_col) cudaFreeAsync(e->d_col, 0);
+  if (e->d_w) cudaFreeAsync(e->d_w, 0);
+  if (e->d_d) cudaFreeAsync(e->d_d, 0);
+  cudaStreamSynchronize(0);
+  delete e;
+}
+
+extern "C" int trgb_expander_create(trgb_expander** out, const trgb_map* map, const TrgbExpandParams* prm, float x0,
+                                    float y0, float x1, float y1, int64_t node_capacity) {
+  TRGB_ARG(out && map && prm, "null pointer");
+  TRGB_ARG(prm->sample_num >= 1 && prm->sample_num <= kExpMaxS, "sample_num out of range for the device expander");
+  TRGB_ARG(prm->max_pops >= 32 && prm->max_pops <= kExpMaxPops, "max_pops out of range");
+  TRGB_ARG(prm->window_words >= 2 && prm->window_words <= 4, "window_words must be 2..4");
+  TRGB_ARG(node_capacity >= 1024 && node_capacity < (1ll << 21) * 512, "node_capacity out of range");
+  TRGB_ARG(x1 > x0 && y1 > y0, "bad extent");
+  // the window kernel is the thread-per-query routine: the map must be sparse enough for its column
+  const double area = (double)map->view.W * map->view.H * (double)map->view.cell * map->view.cell;
+  const double k = (double)map->n / std::max(area, 1e-9) * 3.14159265358979 * (double)prm->robot_size * prm->robot_size;
+  if (map->force_warp_path || k > 0.625 * kTqCap) {
+    set_error("device expander: map too dense for the thread-per-query window kernel");
+    return TRGB_E_STATE;
+  }
+  tune_mempool_once();
+  trgb_expander* e = new trgb_expander();
+  e->map = map;
+  e->prm = *prm;
+  e->st = map->stream;
+  ExpView& v = e->v;
+  v.e = prm->expand_dist; v.r = prm->robot_size; v.hthr = prm->height_threshold; v.cthr = prm->collision_threshold;
+  v.max_slope = prm->max_slope; v.S = prm->sample_num; v.C = prm->max_pops; v.norm_words = prm->window_words;
+  v.new_state = prm->new_state;
+  v.node_cap = (int)node_capacity;
+  v.req_cap = node_capacity * 10;
+  v.gcell = 1.5f * prm->robot_size;
+  v.ginv = 1.0f / v.gcell;
+  v.gx0 = x0 - 2.f - 2.f * v.gcell;
+  v.gy0 = y0 - 2.f - 2.f * v.gcell;
+  const double gw = std::floor(((double)x1 + 2.0 - v.gx0) / v.gcell) + 4, gh = std::floor(((double)y1 + 2.0 - v.gy0) / v.gcell) + 4;
+  if (gw * gh > 2.0e9) { delete e; set_error("node grid too large"); return TRGB_E_ARG; }
+  v.GW = (int)gw; v.GH = (int)gh;
+  const size_t C = (size_t)prm->max_pops, S = (size_t)prm->sample_num, CS = C * S;
+  EXP_ALLOC(v.ctl, 1);
+  EXP_ALLOC(v.node_xy, node_capacity); EXP_ALLOC(v.node_z, node_capacity); EXP_ALLOC(v.node_state, node_capacity);
+  EXP_ALLOC(v.queue, node_capacity); EXP_ALLOC(v.gnext, node_capacity);
+  EXP_ALLOC(v.ghead, (size_t)v.GW * v.GH);
+  EXP_ALLOC(v.req_a, v.req_cap); EXP_ALLOC(v.req_b, v.req_cap); EXP_ALLOC(v.req_w, v.req_cap); EXP_ALLOC(v.req_d, v.req_cap);
+  EXP_ALLOC(v.g_off, C);
+  EXP_ALLOC(v.mask, std::max<size_t>(C * 4, kExpSlowWords));
+  EXP_ALLOC(v.ctab, C * 256);
+  const size_t nblk = (C + 31) / 32;
+  EXP_ALLOC(v.blk_end, nblk * 256); EXP_ALLOC(v.blk_stop, nblk * 256); EXP_ALLOC(v.blk_start, nblk);
+  EXP_ALLOC(v.pop_off, C); EXP_ALLOC(v.pop_cons, C); EXP_ALLOC(v.pop_acc, C);
+  EXP_ALLOC(v.s_xy, CS); EXP_ALLOC(v.s_p1, 3 * CS); EXP_ALLOC(v.s_nn, CS); EXP_ALLOC(v.s_d2, CS); EXP_ALLOC(v.s_tie, CS);
+  EXP_ALLOC(v.s_z, CS); EXP_ALLOC(v.s_ztie, CS); EXP_ALLOC(v.s_stage, CS); EXP_ALLOC(v.s_w, CS); EXP_ALLOC(v.s_d, CS);
+  EXP_ALLOC(v.st, CS); EXP_ALLOC(v.cur_d2, CS); EXP_ALLOC(v.cur_nn, CS); EXP_ALLOC(v.hnext, CS * kCommitCtas); EXP_ALLOC(v.s_pc, CS);
+  for (int k2 = 0; k2 < 2; ++k2) {
+    TRGB_CUDA(cudaMallocHost((void**)&e->h_status[k2], sizeof(ExpCtl)));
+    TRGB_CUDA(cudaEventCreateWithFlags(&e->ev[k2], cudaEventDisableTiming));
+  }
+  {
+    const size_t top_smem = ((size_t)prm->max_pops + 31) / 32 * (64 * (size_t)prm->window_words - 32) * 5;
+    if (top_smem > 200 * 1024) { trgb_expander_destroy(e); set_error("expander: max_pops x window too large for the chain kernel"); return TRGB_E_ARG; }
+    TRGB_CUDA(cudaFuncSetAttribute((const void*)k_exp_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(top_smem, 1024)));
+  }
+  e->cap = kTqCap;
+  e->win_smem = (size_t)kTqThreads * kTqCap * sizeof(float);
+  TRGB_CUDA(cudaFuncSetAttribute((const void*)k_exp_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->win_smem));
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(12, (200 * 1024) / e->win_smem));
+  e->win_grid = sm_count() * per_sm;
+  *out = e;
+  return TRGB_OK;
+}
+
+// a rebuilt map of the same extent: keep every buffer, swap the map (and its stream)
+extern "C" int trgb_expander_rebind(trgb_expander* e, const trgb_map* map, float x0, float y0, float x1, float y1,
+                                    int64_t node_capacity) {
+  TRGB_ARG(e && map, "null pointer");
+  const ExpView& v = e->v;
+  const float gx0 = x0 - 2.f - 2.f * v.gcell, gy0 = y0 - 2.f - 2.f * v.gcell;
+  const double gw = std::floor(((double)x1 + 2.0 - gx0) / v.gcell) + 4, gh = std::floor(((double)y1 + 2.0 - gy0) / v.gcell) + 4;
+  const double area = (double)map->view.W * map->view.H * (double)map->view.cell * map->view.cell;
+  const double k = (double)map->n / std::max(area, 1e-9) * 3.14159265358979 * (double)v.r * v.r;
+  if (gx0 != v.gx0 || gy0 != v.gy0 || (int)gw != v.GW || (int)gh != v.GH || node_capacity > v.node_cap || map->force_warp_path ||
+      k > 0.625 * kTqCap) {
+    set_error("expander: map extent changed");
+    return TRGB_E_STATE;
+  }
+  cudaStreamSynchronize(e->st);
+  e->map = map;
+  e->st = map->stream;
+  return TRGB_OK;
+}
+
+extern "C" int trgb_expander_begin(trgb_expander* e, float root_x, float root_y, float root_z, int64_t draw_pos) {
+  TRGB_ARG(e, "null handle");
+  ExpView& v = e->v;
+  cudaStream_t st = e->st;
+  TRGB_CUDA(cudaMemsetAsync(v.ghead, 0xff, (size_t)v.GW * v.GH * sizeof(int), st));
+  ExpCtl c{};
+  c.head = 0; c.tail = 1; c.n_nodes = 1; c.pos = draw_pos; c.draws_base = draw_pos; c.draws_end = draw_pos;
+  c.mean = 1.15f * (float)v.S; c.var = 2.0f;
+  e->draws_base = e->draws_end = draw_pos;
+  TRGB_CUDA(cudaMemcpyAsync(v.ctl, &c, sizeof(c), cudaMemcpyHostToDevice, st));
+  const float2 rxy = make_float2(root_x, root_y);
+  const signed char rs = 0;
+  const int zero = 0;
+  TRGB_CUDA(cudaMemcpyAsync(v.node_xy, &rxy, sizeof(rxy), cudaMemcpyHostToDevice, st));
+  TRGB_CUDA(cudaMemcpyAsync(v.node_z, &root_z, sizeof(float), cudaMemcpyHostToDevice, st));
+  TRGB_CUDA(cudaMemcpyAsync(v.node_state, &rs, 1, cudaMemcpyHostToDevice, st));
+  TRGB_CUDA(cudaMemcpyAsync(v.queue, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+  // root into the node grid (host computes the cell with the same float arithmetic)
+  auto cellof = [](float val, float origin, float inv, int dim) {
+    const float f = floorf((val - origin) * inv);
+    if (!(f > 0.0f)) return 0;
+    if (f >= (float)dim) return dim - 1;
+    return (int)f;
+  };
+  const int cell = cellof(root_y, v.gy0, v.ginv, v.GH) * v.GW + cellof(root_x, v.gx0, v.ginv, v.GW);
+  const int minus1 = -1;
+  TRGB_CUDA(cudaMemcpyAsync(v.ghead + cell, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+  TRGB_CUDA(cudaMemcpyAsync(v.gnext, &minus1, sizeof(int), cudaMemcpyHostToDevice, st));
+  TRGB_CUDA(cudaStreamSynchronize(st));
+  return TRGB_OK;
+}
+
+// append n draws (x, y offsets) that follow the current end of the device copy of the stream
+extern "C" int trgb_expander_push_draws(trgb_expander* e, const float* xy, int64_t n) {
+  TRGB_ARG(e && (n == 0 || xy), "null pointer");
+  if (n <= 0) return TRGB_OK;
+  cudaStream_t st = e->st;
+  const long long have = e->draws_end - e->draws_base;
+  if (have + n > e->draws_cap) {
+    long long want = e->draws_cap ? e->draws_cap : (1ll << 22);
+    while (want < have + n) want *= 2;
+    float2* nd = nullptr;
+    TRGB_CUDA(cudaMalloc((void**)&nd, (size_t)want * sizeof(float2)));
+    TRGB_CUDA(cudaStreamSynchronize(st));  // queued steps still read the old buffer
+    if (have) TRGB_CUDA(cudaMemcpy(nd, e->d_draws, (size_t)have * sizeof(float2), cudaMemcpyDeviceToDevice));
+    if (e->d_draws) cudaFree(e->d_draws);
+    e->d_draws = nd;
+    e->draws_cap = want;
+    e->v.draws = nd;
+  }
+  TRGB_CUDA(cudaMemcpyAsync(e->d_draws + have, xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, st));
+  e->draws_end += n;
+  // published to the device control block in stream order (steps queued later see it)
+  TRGB_CUDA(cudaMemcpyAsync(&e->v.ctl->draws_end, &e->draws_end, sizeof(long long), cudaMemcpyHostToDevice, st));
+  return TRGB_OK;
+}
+
+extern "C" int trgb_expander_enqueue(trgb_expander* e, int n_steps, int pops_hint) {
+  TRGB_ARG(e && n_steps >= 0, "bad argument");
+  ExpView& v = e->v;
+  cudaStream_t st = e->st;
+  const trgb_map* m = e->map;
+  int c_step = std::max(32, std::min(pops_hint, v.C));
+  c_step = (c_step + 31) & ~31;
+  const int S = v.S;
+  const int64_t ns = (int64_t)c_step * S;
+  const int kmax = std::max(2, std::min(16, (int)std::ceil((v.e * 1.001f) / (0.5f * v.r))));
+  TrgbEdgeParams ep{v.r, v.hthr, v.cthr, kmax};
+  for (int k = 0; k < n_steps; ++k) {
+    {
+      ProfScope ps("k_exp_plan", st, 1.0);
+      k_exp_plan<<<1, 256, 0, st>>>(v, c_step);
+    }
+    {
+      ProfScope ps("k_exp_window", st, (double)c_step * 64.0 * v.norm_words);
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)c_step * 64 * v.norm_words + kTqThreads - 1) / kTqThreads, e->win_grid));
+      k_exp_window<<<grid, kTqThreads, e->win_smem, st>>>(m->view, v, e->cap);
+    }
+    {
+      ProfScope ps("k_exp_chain", st, (double)c_step);
+      const int nblk = (c_step + 31) / 32;
+      k_exp_tables<<<(nblk + 3) / 4, 128, 0, st>>>(v);
+      k_exp_top<<<1, 1024, (size_t)nblk * (64 * v.norm_words - 32) * 5, st>>>(v);
+      k_exp_emit<<<(nblk + 3) / 4, 128, 0, st>>>(v);
+    }
+    {
+      ProfScope ps("k_exp_nearest", st, (double)ns);
+      k_exp_nearest<<<(int)((ns + 255) / 256), 256, 0, st>>>(v, c_step);
+    }
+    int rc = trgb_nearest_z_launch_skip(m, reinterpret_cast<const float*>(v.s_xy), ns, v.s_z, nullptr, v.s_ztie, v.s_d2, v.r);
+    if (rc) return rc;
+    rc = trgb_edge_eval_launch_skip(m, v.s_p1, reinterpret_cast<const float*>(v.s_xy), ns, &ep, v.s_stage, v.s_w, v.s_d, nullptr,
+                                    v.s_d2, ns, v.r);
+    if (rc) return rc;
+    {
+      ProfScope ps("k_exp_commit", st, (double)ns);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(kCommitCtas);
+      cfg.blockDim = dim3(1024);
+      cfg.dynamicSmemBytes = 0;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = kCommitCtas;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      TRGB_CUDA(cudaLaunchKernelEx(&cfg, k_exp_commit, v));
+    }
+  }
+  TRGB_CUDA(cudaGetLastError());
+  return TRGB_OK;
+}
+
+static void fill_status(const ExpCtl& c, TrgbExpandStatus* s) {
+  s->head = c.head; s->tail = c.tail; s->n_nodes = c.n_nodes; s->interrupt = c.interrupt; s->interrupt_pop = c.interrupt_pop;
+  s->n_req = c.n_req; s->pos = c.pos; s->draws_end = c.draws_end; s->window_tests = c.window_tests; s->steps = c.steps;
+  s->steps_active = c.steps_active; s->rounds = c.rounds; s->pops = c.pops; s->z_ties = c.z_ties; s->redo_pops = c.redo_pops;
+  s->samples = c.samples; s->created = c.created; s->mean = c.mean; s->var = c.var;
+}
+
+extern "C" int trgb_expander_snapshot(trgb_expander* e, int slot) {
+  TRGB_ARG(e && (slot == 0 || slot == 1), "bad argument");
+  TRGB_CUDA(cudaMemcpyAsync(e->h_status[slot], e->v.ctl, sizeof(ExpCtl), cudaMemcpyDeviceToHost, e->st));
+  TRGB_CUDA(cudaEventRecord(e->ev[slot], e->st));
+  return TRGB_OK;
+}
+
+extern "C" int trgb_expander_wait(trgb_expander* e, int slot, TrgbExpandStatus* out) {
+  TRGB_ARG(e && out && (slot == 0 || slot == 1), "bad argument");
+  TRGB_CUDA(cudaEventSynchronize(e->ev[slot]));
+  fill_status(*e->h_status[slot], out);
+  return TRGB_OK;
+}
+
+// nodes [from, to): xyz (3 floats each) and state
+extern "C" int trgb_expander_nodes(trgb_expander* e, int64_t from, int64_t to, float* xyz, int8_t* state) {
+  TRGB_ARG(e && from >= 0 && to >= from, "bad range");
+  const int64_t n = to - from;
+  if (n == 0) return TRGB_OK;
+  std::vector<float2> xy((size_t)n);
+  std::vector<float> z((size_t)n);
+  TRGB_CUDA(cudaMemcpyAsync(xy.data(), e->v.node_xy + from, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, e->st));
+  TRGB_CUDA(cudaMemcpyAsync(z.data(), e->v.node_z + from, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, e->st));
+  if (state) TRGB_CUDA(cudaMemcpyAsync(state, e->v.node_state + from, (size_t)n, cudaMemcpyDeviceToHost, e->st));
+  TRGB_CUDA(cudaStreamSynchronize(e->st));
+  if (xyz)
+    for (int64_t i = 0; i < n; ++i) { xyz[3 * i] = xy[i].x; xyz[3 * i + 1] = xy[i].y; xyz[3 * i + 2] = z[i]; }
+  return TRGB_OK;
+}
+
+// the pop at the queue head, for the host to handle after an interrupt
+extern "C" int trgb_expander_head_pop(trgb_expander* e, int32_t* node_id) {
+  TRGB_ARG(e && node_id, "null pointer");
+  ExpCtl c;
+  TRGB_CUDA(cudaMemcpyAsync(&c, e->v.ctl, sizeof(c), cudaMemcpyDeviceToHost, e->st));
+  TRGB_CUDA(cudaStreamSynchronize(e->st));
+  TRGB_CUDA(cudaMemcpyAsync(node_id, e->v.queue + c.head, sizeof(int), cudaMemcpyDeviceToHost, e->st));
+  TRGB_CUDA(cudaStreamSynchronize(e->st));
+  return TRGB_OK;
+}
+
+extern "C" int trgb_expander_apply_pop(trgb_expander* e, int n_new, const float* nodes_xyzs, int n_req, const int32_t* req_a,
+                                       const int32_t* req_b, const float* req_w, const float* req_d, int64_t new_pos) {
+  TRGB_ARG(e && n_new >= 0 && n_req >= 0, "bad argument");
+  cudaStream_t st = e->st;
+  float* dn = nullptr; int* da = nullptr; int* db = nullptr; float* dw = nullptr; float* dd = nullptr;
+  TRGB_CUDA(cudaMallocAsync((void**)&dn, std::max(1, n_new) * 4 * sizeof(float), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&da, std::max(1, n_req) * sizeof(int), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&db, std::max(1, n_req) * sizeof(int), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&dw, std::max(1, n_req) * sizeof(float), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&dd, std::max(1, n_req) * sizeof(float), st));
+  if (n_new) TRGB_CUDA(cudaMemcpyAsync(dn, nodes_xyzs, (size_t)n_new * 4 * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (n_req) {
+    TRGB_CUDA(cudaMemcpyAsync(da, req_a, (size_t)n_req * sizeof(int), cudaMemcpyHostToDevice, st));
+    TRGB_CUDA(cudaMemcpyAsync(db, req_b, (size_t)n_req * sizeof(int), cudaMemcpyHostToDevice, st));
+    TRGB_CUDA(cudaMemcpyAsync(dw, req_w, (size_t)n_req * sizeof(float), cudaMemcpyHostToDevice, st));
+    TRGB_CUDA(cudaMemcpyAsync(dd, req_d, (size_t)n_req * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  k_exp_apply<<<1, 32, 0, st>>>(e->v, n_new, dn, n_req, da, db, dw, dd, (long long)new_pos);
+  TRGB_CUDA(cudaGetLastError());
+  cudaFreeAsync(dn, st); cudaFreeAsync(da, st); cudaFreeAsync(db, st); cudaFreeAsync(dw, st); cudaFreeAsync(dd, st);
+  TRGB_CUDA(cudaStreamSynchronize(st));
+  return TRGB_OK;
+}
+
+extern "C" int trgb_expander_finalize(trgb_expander* e, int64_t* n_nodes, int64_t* n_dir_edges) {
+  TRGB_ARG(e && n_nodes && n_dir_edges, "null pointer");
+  cudaStream_t st = e->st;
+  ExpView& v = e->v;
+  ExpCtl c;
+  TRGB_CUDA(cudaMemcpyAsync(&c, v.ctl, sizeof(c), cudaMemcpyDeviceToHost, st));
+  TRGB_CUDA(cudaStreamSynchronize(st));
+  const long long nr = c.n_req;
+  const int nn = c.n_nodes;
+  e->n_nodes_final = nn;
+  // (stream-ordered pool: cudaMalloc / cudaFree stall for tens of ms once the pool holds GBs)
+  if (e->d_row) { cudaFreeAsync(e->d_row, st); e->d_row = nullptr; }
+  if (e->d_col) { cudaFreeAsync(e->d_col, st); e->d_col = nullptr; }
+  if (e->d_w) { cudaFreeAsync(e->d_w, st); e->d_w = nullptr; }
+  if (e->d_d) { cudaFreeAsync(e->d_d, st); e->d_d = nullptr; }
+  TRGB_CUDA(cudaMallocAsync((void**)&e->d_row, ((size_t)nn + 1) * sizeof(long long), st));
+  if (nr == 0) {
+    TRGB_CUDA(cudaMemsetAsync(e->d_row, 0, ((size_t)nn + 1) * sizeof(long long), st));
+    TRGB_CUDA(cudaStreamSynchronize(st));
+    e->n_dir = 0;
+    *n_nodes = nn; *n_dir_edges = 0;
+    return TRGB_OK;
+  }
+  const int grid = sm_count() * 8;
+  float* p1 = nullptr; float2* p2 = nullptr; float* skip = nullptr; unsigned char* stage = nullptr; float* w = nullptr; float* d = nullptr;
+  unsigned char* ok = nullptr; int* cnt = nullptr; int* unc = nullptr;
+  const int unc_cap = 1 << 16;
+  TRGB_CUDA(cudaMallocAsync((void**)&p1, (size_t)nr * 3 * sizeof(float), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&p2, (size_t)nr * sizeof(float2), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&skip, (size_t)nr * sizeof(float), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&stage, (size_t)nr, st));
+  TRGB_CUDA(cudaMallocAsync((void**)&w, (size_t)nr * sizeof(float), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&d, (size_t)nr * sizeof(float), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&ok, (size_t)nr, st));
+  TRGB_CUDA(cudaMallocAsync((void**)&cnt, 4 * sizeof(int), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&unc, (size_t)unc_cap * sizeof(int), st));
+  TRGB_CUDA(cudaMemsetAsync(cnt, 0, 4 * sizeof(int), st));
+  k_fin_prepare<<<grid, 256, 0, st>>>(v, nr, p1, p2, skip);
+  // wire requests reach expand_dist + robot_size (a node created robot_size from the sample's parent circle)
+  const int kmax = std::max(2, std::min(16, (int)std::ceil((v.e + v.r) / (0.5f * v.r))));
+  TrgbEdgeParams ep{v.r, v.hthr, v.cthr, kmax};
+  int rc = trgb_edge_eval_launch_skip(e->map, p1, reinterpret_cast<const float*>(p2), nr, &ep, stage, w, d, nullptr, skip, nr, 1.0f);
+  if (rc) return rc;
+  {
+    ProfScope ps("k_fin_gate", st, (double)nr);
+    k_fin_gate<<<grid, 256, 0, st>>>(v, nr, stage, w, d, ok, unc, cnt + 1, unc_cap);
+  }
+  int h_unc = 0;
+  TRGB_CUDA(cudaMemcpyAsync(&h_unc, cnt + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  TRGB_CUDA(cudaStreamSynchronize(st));
+  if (h_unc > unc_cap) { set_error("finalize: too many uncertain slope gates"); return TRGB_E_STATE; }
+  if (h_unc > 0) {
+    // glibc's atan2f decides, as in the reference (trg.cpp:269-274)
+    std::vector<int> list((size_t)h_unc);
+    TRGB_CUDA(cudaMemcpy(list.data(), unc, (size_t)h_unc * sizeof(int), cudaMemcpyDeviceToHost));
+    const float max_slope = v.max_slope;
+    for (int k : list) {
+      int ab[2];
+      TRGB_CUDA(cudaMemcpy(&ab[0], v.req_a + k, sizeof(int), cudaMemcpyDeviceToHost));
+      TRGB_CUDA(cudaMemcpy(&ab[1], v.req_b + k, sizeof(int), cudaMemcpyDeviceToHost));
+      float2 pa, pb; float za, zb;
+      TRGB_CUDA(cudaMemcpy(&pa, v.node_xy + ab[0], sizeof(float2), cudaMemcpyDeviceToHost));
+      TRGB_CUDA(cudaMemcpy(&pb, v.node_xy + ab[1], sizeof(float2), cudaMemcpyDeviceToHost));
+      TRGB_CUDA(cudaMemcpy(&za, v.node_z + ab[0], sizeof(float), cudaMemcpyDeviceToHost));
+      TRGB_CUDA(cudaMemcpy(&zb, v.node_z + ab[1], sizeof(float), cudaMemcpyDeviceToHost));
+      const float dx = pa.x - pb.x, dy = pa.y - pb.y;
+      const float slope = atan2f(fabsf(za - zb), sqrtf(dx * dx + dy * dy));
+      const unsigned char res = slope > max_slope ? 0 : 1;
+      TRGB_CUDA(cudaMemcpy(ok + k, &res, 1, cudaMemcpyHostToDevice));
+      if (res) {
+        TRGB_CUDA(cudaMemcpy(v.req_w + k, w + k, sizeof(float), cudaMemcpyDeviceToDevice));
+        TRGB_CUDA(cudaMemcpy(v.req_d + k, d + k, sizeof(float), cudaMemcpyDeviceToDevice));
+      }
+    }
+  }
+  // (pair, request index) of every request that would succeed, in request order per pair
+  unsigned long long *key = nullptr, *key2 = nullptr; unsigned int *val = nullptr, *val2 = nullptr;
+  TRGB_CUDA(cudaMallocAsync((void**)&key, (size_t)nr * sizeof(unsigned long long), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&key2, (size_t)nr * sizeof(unsigned long long), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&val, (size_t)nr * sizeof(unsigned int), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&val2, (size_t)nr * sizeof(unsigned int), st));
+  // compaction by atomics loses the request order inside a pair: sort by (pair, index) instead, in
+  // two stable passes (index first — it is the value —, then pair)
+  k_fin_keys<<<grid, 256, 0, st>>>(v, nr, ok, key, val, cnt);
+  int n_ok = 0;
+  TRGB_CUDA(cudaMemcpyAsync(&n_ok, cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
+  TRGB_CUDA(cudaStreamSynchronize(st));
+  size_t tmp_bytes = 0, tb2 = 0;
+  void* tmp = nullptr;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, val, val2, key, key2, n_ok, 0, 32, st);
+  cub::DeviceRadixSort::SortPairs(nullptr, tb2, key2, key, val2, val, std::max(n_ok, 2 * n_ok), 0, 64, st);
+  tmp_bytes = std::max(tmp_bytes, tb2);
+  TRGB_CUDA(cudaMallocAsync(&tmp, std::max<size_t>(tmp_bytes, 16), st));
+  {
+    ProfScope ps("k_fin_sort", st, (double)n_ok);
+    // pass 1: by request index (keys = val); pass 2: stable by pair
+    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, val, val2, key, key2, n_ok, 0, 32, st);
+    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key2, key, val2, val, n_ok, 0, 64, st);
+  }
+  // first of each pair -> two directed entries keyed (source node, request index)
+  unsigned long long *dkey = nullptr, *dkey2 = nullptr; unsigned int *dval = nullptr, *dval2 = nullptr;
+  const size_t nd_cap = (size_t)2 * std::max(n_ok, 1);
+  TRGB_CUDA(cudaMallocAsync((void**)&dkey, nd_cap * sizeof(unsigned long long), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&dkey2, nd_cap * sizeof(unsigned long long), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&dval, nd_cap * sizeof(unsigned int), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&dval2, nd_cap * sizeof(unsigned int), st));
+  k_fin_edges<<<grid, 256, 0, st>>>(v, n_ok, key, val, dkey, dval, cnt + 2);
+  int n_dir = 0;
+  TRGB_CUDA(cudaMemcpyAsync(&n_dir, cnt + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+  TRGB_CUDA(cudaStreamSynchronize(st));
+  if (n_dir > 0) {
+    size_t tb3 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb3, dkey, dkey2, dval, dval2, n_dir, 0, 64, st);
+    if (tb3 > tmp_bytes) {
+      cudaFreeAsync(tmp, st);
+      tmp_bytes = tb3;
+      TRGB_CUDA(cudaMallocAsync(&tmp, tmp_bytes, st));
+    }
+    ProfScope ps("k_fin_sort", st, (double)n_dir);
+    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dkey, dkey2, dval, dval2, n_dir, 0, 64, st);
+  }
+  TRGB_CUDA(cudaMallocAsync((void**)&e->d_col, std::max<size_t>(n_dir, 1) * sizeof(int), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&e->d_w, std::max<size_t>(n_dir, 1) * sizeof(float), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&e->d_d, std::max<size_t>(n_dir, 1) * sizeof(float), st));
+  k_fin_csr<<<grid, 256, 0, st>>>(v, n_dir, nn, dkey2, dval2, e->d_row, e->d_col, e->d_w, e->d_d);
+  TRGB_CUDA(cudaGetLastError());
+  for (void* p : {(void*)p1, (void*)p2, (void*)skip, (void*)stage, (void*)w, (void*)d, (void*)ok, (void*)cnt, (void*)unc, (void*)key,
+                  (void*)key2, (void*)val, (void*)val2, (void*)dkey, (void*)dkey2, (void*)dval, (void*)dval2, tmp})
+    cudaFreeAsync(p, st);
+  TRGB_CUDA(cudaStreamSynchronize(st));
+  e->n_dir = n_dir;
+  *n_nodes = nn;
+  *n_dir_edges = n_dir;
+  return TRGB_OK;
+}
+
+extern "C" int trgb_expander_download(trgb_expander* e, float* xyz, int8_t* state, int64_t* row_ptr, int32_t* col, float* weight,
+                                      float* dist) {
+  TRGB_ARG(e && e->d_row, "finalize first");
+  const int nn = e->n_nodes_final;
+  int rc = trgb_expander_nodes(e, 0, nn, xyz, state);
+  if (rc) return rc;
+  cudaStream_t st = e->st;
+  if (row_ptr) TRGB_CUDA(cudaMemcpyAsync(row_ptr, e->d_row, ((size_t)nn + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  if (e->n_dir > 0) {
+    if (col) TRGB_CUDA(cudaMemcpyAsync(col, e->d_col, (size_t)e->n_dir * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (weight) TRGB_CUDA(cudaMemcpyAsync(weight, e->d_w, (size_t)e->n_dir * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (dist) TRGB_CUDA(cudaMemcpyAsync(dist, e->d_d, (size_t)e->n_dir * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  TRGB_CUDA(cudaStreamSynchronize(st));
+  return TRGB_OK;
+}

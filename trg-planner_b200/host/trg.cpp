@@ -72,6 +72,7 @@ TRG::TRG(bool isVerbose, float expand_dist, float robot_size, int sample_num, fl
 
 TRG::~TRG() {
   joinDrawPrefetch();
+  destroyExpander();
   for (auto& kv : trgMap_) {
     if (kv.second->map_index) trgb_map_destroy(kv.second->map_index);
     kv.second->map_index = nullptr;
@@ -89,6 +90,7 @@ void TRG::resetGraph(std::string type) {  // trg.cpp:732-737
 
 void TRG::resetMap(std::string type) {  // trg.cpp:739-744
   trgStruct& graph = *trgMap_.at(type);
+  if (graph.map_index && graph.map_index == expander_map_) expander_map_ = nullptr;
   if (graph.map_index) trgb_map_destroy(graph.map_index);
   graph.map_index  = nullptr;
   graph.map_points = 0;
@@ -150,13 +152,23 @@ void TRG::generateDrawBlock(size_t n, std::vector<float>& u, std::vector<float>&
   u.resize(n);
   xy.resize(2 * n);
   const float e = param_.expand_dist;
-  for (size_t k = 0; k < n; ++k) {
-    const float v = distr_(gen_);
-    u[k] = v;
-    const float angle = v * 2 * M_PI;
-    xy[2 * k]     = e * cosf(angle);
-    xy[2 * k + 1] = e * sinf(angle);
+  for (size_t k = 0; k < n; ++k) u[k] = distr_(gen_);  // the generator is sequential ...
+  auto trig = [&u, &xy, e](size_t b, size_t en) {      // ... glibc cosf / sinf are not: slices on helper threads
+    for (size_t k = b; k < en; ++k) {
+      const float angle = u[k] * 2 * M_PI;
+      xy[2 * k]     = e * cosf(angle);
+      xy[2 * k + 1] = e * sinf(angle);
+    }
+  };
+  const int threads = n >= ((size_t)1 << 16) ? std::min(6, trg_b200::thread_budget()) : 1;
+  if (threads <= 1) {
+    trig(0, n);
+    return;
   }
+  std::vector<std::future<void>> jobs;
+  for (int t = 1; t < threads; ++t) jobs.push_back(std::async(std::launch::async, trig, n * t / threads, n * (t + 1) / threads));
+  trig(0, n / threads);
+  for (auto& j : jobs) j.get();
 }
 
 void TRG::joinDrawPrefetch() {
@@ -209,6 +221,7 @@ void TRG::compactDraws() {
 // maps
 // ================================================================================================
 void TRG::buildMapIndex(trgStruct& g, const float* xyz, int64_t n, int stride, bool device) {
+  if (g.map_index && g.map_index == expander_map_) expander_map_ = nullptr;  // the engine is re-bound at the next build
   if (g.map_index) trgb_map_destroy(g.map_index);
   g.map_index  = nullptr;
   g.map_points = 0;
@@ -1261,10 +1274,12 @@ void TRG::initGraph(bool /*isPreMap*/, Eigen::Vector3f start3d) {  // trg.cpp:36
     root_pos = root_pos + Eigen::Vector2f(rx, ry);
     cnt++;
   }
-  this->expandGraph(graph.node_id - 1, graph.type);
-  auto t1 = Clock::now();
-  this->cleanGraph(false);
-  stat_["us_clean"] += (int64_t)(1e6 * since(t1));
+  if (!buildGraphOnDevice(graph)) {  // device-resident BFS + cleanGraph in one go when applicable
+    this->expandGraph(graph.node_id - 1, graph.type);
+    auto t1 = Clock::now();
+    this->cleanGraph(false);
+    stat_["us_clean"] += (int64_t)(1e6 * since(t1));
+  }
   secs_["init_graph"] = since(t0);
 }
 

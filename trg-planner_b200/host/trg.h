@@ -33,6 +33,7 @@
 
 struct trgb_map;
 struct trgb_graph;
+struct trgb_expander;
 
 namespace trg_b200 {
 class DeviceSession;
@@ -243,6 +244,13 @@ class TRG {
   size_t node_used_ = 0, edge_used_ = 0;  // pool cursors
   void setGoalUnlocked(Eigen::Vector3f& goal);
   void runExpansion(const std::vector<Node*>& roots, trgStruct& g);
+  // initGraph fast path (trg_device_build.cpp): expandGraph(0) as a device-resident BFS (K9) followed
+  // by cleanGraph(false), materialised straight into the cleaned containers. false = not applicable
+  // (step-3 wiring on, map too dense, capacity): the caller runs the host-driven path instead.
+  bool buildGraphOnDevice(trgStruct& g);
+  void destroyExpander();
+  trgb_expander*  expander_     = nullptr;
+  const trgb_map* expander_map_ = nullptr;
 
   std::unique_ptr<trg_b200::DeviceSession> dev_;
   trgb_graph* dev_graph_ = nullptr;
@@ -266,6 +274,10 @@ class TRG {
     int parallel_min_nodes = 50000;  // graphs larger than this use helper threads in cleanGraph / CSR export
     bool overlap = true;      // run the device phases of batch k+1 on a helper thread while batch k commits
     bool split_commit = false;  // apply edge-list operations on a second thread while the first decides (measured slower on a 10 M-point map: cross-core traffic on the adjacency lists; kept for experiments)
+    bool device_expand = true;  // initGraph: run the whole BFS, decisions included, on the device (K9) when applicable
+    int  expand_steps = 8;      // device BFS: steps queued per status poll (two polls in flight)
+    int  expand_window_words = 2;  // device BFS: sampling window per pop = 64 * words draws
+    int  expand_max_pops = 8192;   // device BFS: pops per step at most
   } tuning_;
 };
 

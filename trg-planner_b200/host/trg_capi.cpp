@@ -25,6 +25,18 @@ struct TRGX : TRG {
 };
 inline TRGX* X(void* h) { return static_cast<TRGX*>(h); }
 
+// lockGraph() / unlockGraph() as a scope: an exception between the two must not leave TRG::mtx.graph locked
+struct GraphLock {
+  explicit GraphLock(TRG* t) : t_(t) { t_->lockGraph(); }
+  ~GraphLock() { t_->unlockGraph(); }
+  TRG* t_;
+};
+inline void check_type(const char* type) {
+  if (!type) throw std::runtime_error("trg_b200: graph type is null");
+  const std::string s(type);
+  if (s != "global" && s != "local" && s != "prebuilt") throw std::runtime_error("trg_b200: unknown graph type '" + s + "'");
+}
+
 template <class F>
 int guard(F&& f) {
   try {
@@ -74,13 +86,14 @@ int trg_update_graph(void* h) {
 
 int trg_graph_counts(void* h, const char* type, int64_t* n_nodes, int64_t* n_edges) {
   return guard([&] {
-    T(h)->lockGraph();
+    check_type(type);
+    if (!n_nodes || !n_edges) throw std::runtime_error("trg_b200: null output pointer");
+    GraphLock lock(T(h));
     const auto& g = T(h)->getGraphRef(type);
     int64_t e = 0;
     for (auto& kv : g) e += (int64_t)kv.second->edges_.size();
     *n_nodes = (int64_t)g.size();
     *n_edges = e;
-    T(h)->unlockGraph();
     return 0;
   });
 }
@@ -88,7 +101,8 @@ int trg_graph_counts(void* h, const char* type, int64_t* n_nodes, int64_t* n_edg
 int trg_graph_export(void* h, const char* type, int32_t* iter_ids, int32_t* ids_sorted, float* pos_xyz,
                      int32_t* state, int64_t* row_ptr, int32_t* col, float* weight, float* dist) {
   return guard([&] {
-    T(h)->lockGraph();
+    check_type(type);
+    GraphLock lock(T(h));
     const auto& g = T(h)->getGraphRef(type);
     std::vector<std::pair<int, TRG::Node*>> ids;
     ids.reserve(g.size());
@@ -116,7 +130,6 @@ int trg_graph_export(void* h, const char* type, int32_t* iter_ids, int32_t* ids_
       }
     }
     if (row_ptr) row_ptr[ids.size()] = e;
-    T(h)->unlockGraph();
     return 0;
   });
 }
@@ -322,6 +335,10 @@ int trg_set_tuning(void* h, const char* key, double value) {
     else if (k == "parallel_min_nodes") T(h)->tuning_.parallel_min_nodes = (int)value;
     else if (k == "overlap") T(h)->tuning_.overlap = value != 0;
     else if (k == "split_commit") T(h)->tuning_.split_commit = value != 0;
+    else if (k == "device_expand") T(h)->tuning_.device_expand = value != 0;
+    else if (k == "expand_steps") T(h)->tuning_.expand_steps = std::max(1, (int)value);
+    else if (k == "expand_window_words") T(h)->tuning_.expand_window_words = std::min(4, std::max(2, (int)value));
+    else if (k == "expand_max_pops") T(h)->tuning_.expand_max_pops = std::min(8192, std::max(32, (int)value));
     else throw std::runtime_error("unknown tuning key " + k);
     return 0;
   });

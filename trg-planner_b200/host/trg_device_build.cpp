@@ -1,0 +1,378 @@
+// TRG::initGraph fast path: expandGraph(0) runs as a device-resident BFS (K9, csrc/expand.cu) —
+// sampling windows, chain scan, nearest node, height, parent edge AND the commit decisions on the
+// GPU — followed by cleanGraph(false), materialised straight into the cleaned host containers the
+// reference API exposes (std::unordered_map<int, Node*>, Node::edges_).
+//
+// What stays on the host, and why:
+//  * the sampling stream: std::mt19937 + uniform_real_distribution<float> + glibc cosf / sinf
+//    (trg.cpp:395-397) — generated ahead in blocks and pushed to the device;
+//  * a pop the device cannot decide bit-exactly (two nodes at the identical float distance from a
+//    sample: the reference's kd-tree visit order decides; a slope within 3 ulp of the gate: glibc's
+//    atan2f decides): handleInterruptedPop() runs the reference's rules for that one pop;
+//  * the two std::unordered_map iteration orders cleanGraph's renumbering goes through
+//    (trg.cpp:497-504, 528-530): ids must be bit-exact, so the first map's order is replayed from
+//    libstdc++'s own rehash policy and the second map is the real container.
+#include <math.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstring>
+#include <future>
+#include <limits>
+#include <stdexcept>
+#include <thread>
+
+#include "device_session.h"
+#include "trg.h"
+#include "trgb_kernels.h"
+
+namespace {
+using Clock = std::chrono::steady_clock;
+inline double since(Clock::time_point t0) { return std::chrono::duration<double>(Clock::now() - t0).count(); }
+[[noreturn]] void fail(const std::string& what) { throw std::runtime_error("trg_b200: " + what + ": " + trgb_last_error()); }
+inline void K(int rc, const char* what) {
+  if (rc != TRGB_OK) fail(what);
+}
+
+// Iteration order of a std::unordered_map<int, T> (libstdc++, identity hash, max load factor 1) into
+// which the keys 0 .. n-1 are inserted in ascending order, starting from `bucket_count` buckets
+// (1 = never used; otherwise what clear() left behind). A key whose bucket is empty becomes the new
+// head of the element list (hashtable.h _M_insert_bucket_begin), and keys below the bucket count all
+// have their own bucket; a rehash re-links the elements in list order, each again at the head
+// (_M_rehash_aux), i.e. reverses the list. Rehash points come from libstdc++'s own policy object.
+// Keys >= bucket count cannot occur before a rehash (the policy grows first), so no chain is shared.
+std::vector<int> sequential_map_order(size_t n, size_t bucket_count) {
+  std::__detail::_Prime_rehash_policy pol(1.0f);
+  size_t bkt = bucket_count;
+  pol._M_next_resize = bkt <= 1 ? 0 : (size_t)__builtin_floor((double)bkt * 1.0);
+  // deque with a direction flag: push at the logical front, reverse = flip
+  std::vector<int> buf(2 * n + 2);
+  size_t lo = n + 1, hi = n + 1;  // elements in [lo, hi)
+  bool flipped = false;           // logical front is at hi when flipped
+  for (size_t k = 0; k < n; ++k) {
+    const auto r = pol._M_need_rehash(bkt, k, 1);
+    if (r.first) {
+      bkt = r.second;
+      flipped = !flipped;
+    }
+    if (!flipped) buf[--lo] = (int)k; else buf[hi++] = (int)k;
+  }
+  std::vector<int> out(n);
+  if (!flipped) std::copy(buf.begin() + lo, buf.begin() + hi, out.begin());
+  else std::reverse_copy(buf.begin() + lo, buf.begin() + hi, out.begin());
+  return out;
+}
+
+template <class F>
+void parallel_for(size_t n, int threads, F&& f) {
+  if (threads <= 1 || n < 4096) {
+    f(0, n);
+    return;
+  }
+  std::vector<std::future<void>> jobs;
+  for (int t = 0; t < threads; ++t)
+    jobs.push_back(std::async(std::launch::async, [&f, n, t, threads] { f(n * t / threads, n * (t + 1) / threads); }));
+  for (auto& j : jobs) j.get();
+}
+}  // namespace
+
+void TRG::destroyExpander() {
+  if (expander_) trgb_expander_destroy(expander_);
+  expander_     = nullptr;
+  expander_map_ = nullptr;
+}
+
+bool TRG::buildGraphOnDevice(trgStruct& g) {
+  if (!tuning_.device_expand) return false;
+  if (param_.expand_dist - param_.robot_size < 0.25 * param_.expand_dist) return false;  // step-3 wiring (trg.cpp:429)
+  if (param_.sample_num < 1 || param_.sample_num > 32) return false;
+  if (g.node_seq.size() != 1) return false;
+  trgb_map* map = requireMap(g, "initGraph");
+  auto t_begin = Clock::now();
+
+  // ---- engine ------------------------------------------------------------------------------
+  const double area = ((double)g.bbox[2] - g.bbox[0] + 4.0) * ((double)g.bbox[3] - g.bbox[1] + 4.0);
+  // nodes are pairwise >= robot_size apart (trg.cpp:414-421): hexagonal packing bounds their number
+  const double dens = 2.0 / (std::sqrt(3.0) * (double)param_.robot_size * param_.robot_size);
+  const int64_t cap = (int64_t)std::min(area * dens * 1.05 + 65536.0, 6.0e8);
+  if (expander_ && expander_map_ != map) {
+    // a rebuilt map of the same extent keeps the engine's buffers
+    if (trgb_expander_rebind(expander_, map, g.bbox[0], g.bbox[1], g.bbox[2], g.bbox[3], cap) == TRGB_OK) expander_map_ = map;
+    else destroyExpander();
+  }
+  if (!expander_) {
+    TrgbExpandParams ep{};
+    ep.expand_dist = param_.expand_dist;
+    ep.robot_size = param_.robot_size;
+    ep.height_threshold = param_.height_threshold;
+    ep.collision_threshold = param_.collision_threshold;
+    ep.sample_num = param_.sample_num;
+    ep.max_slope = atan2f(param_.height_threshold, param_.robot_size);  // trg.cpp:269, float overload
+    ep.max_pops = tuning_.expand_max_pops;
+    ep.window_words = tuning_.expand_window_words;
+    ep.new_state = 0;  // ref_id == 0: new nodes are Valid (trg.cpp:420)
+    const int rc = trgb_expander_create(&expander_, map, &ep, g.bbox[0], g.bbox[1], g.bbox[2], g.bbox[3], cap);
+    if (rc == TRGB_E_STATE || rc == TRGB_E_ARG || rc == TRGB_E_NOMEM) {
+      expander_ = nullptr;
+      stat_["device_expand_unavailable"]++;
+      return false;
+    }
+    K(rc, "trgb_expander_create");
+    expander_map_ = map;
+  }
+  trgb_expander* e = expander_;
+  Node* root = g.node_seq[0];
+  compactDraws();
+  const size_t pos_start = draw_next_;
+  K(trgb_expander_begin(e, root->pos_.x(), root->pos_.y(), root->pos_.z(), (int64_t)pos_start), "trgb_expander_begin");
+
+  // ---- draws: keep the device copy of the stream `ahead` draws in front of the chain ------------
+  size_t pushed_end = pos_start;
+  auto push_upto = [&](size_t upto) {
+    if (upto <= pushed_end) return;
+    ensureDraws(upto);
+    const size_t have_end = draw_base_ + draw_u_.size();
+    // push whole generated blocks: fewer, larger copies
+    K(trgb_expander_push_draws(e, draw_xy_.data() + 2 * (pushed_end - draw_base_), (int64_t)(have_end - pushed_end)),
+      "trgb_expander_push_draws");
+    pushed_end = have_end;
+  };
+  const int S = param_.sample_num;
+  const int group = std::max(1, tuning_.expand_steps);
+  // two groups of steps are in flight; a step consumes ~ (S + collisions) draws per pop it takes
+  size_t ahead = (size_t)1 << 17;
+  push_upto(pos_start + ahead);
+
+  // host mirror of the node list, filled lazily (interrupts only)
+  std::vector<float> mx, my, mz;
+  std::vector<int8_t> mstate;
+  int64_t n_interrupts = 0;
+  bool out_of_capacity = false;
+
+  auto handle_interrupt = [&](const TrgbExpandStatus& st) {
+    ++n_interrupts;
+    if (st.interrupt == 3) { out_of_capacity = true; return; }
+    const int64_t n = st.n_nodes;
+    const int64_t have = (int64_t)mx.size();
+    if (n > have) {
+      std::vector<float> xyz((size_t)(n - have) * 3);
+      mstate.resize((size_t)n);
+      K(trgb_expander_nodes(e, have, n, xyz.data(), mstate.data() + have), "trgb_expander_nodes");
+      mx.resize((size_t)n); my.resize((size_t)n); mz.resize((size_t)n);
+      for (int64_t i = have; i < n; ++i) {
+        mx[i] = xyz[3 * (i - have)]; my[i] = xyz[3 * (i - have) + 1]; mz[i] = xyz[3 * (i - have) + 2];
+      }
+    }
+    int32_t pop_id = -1;
+    K(trgb_expander_head_pop(e, &pop_id), "trgb_expander_head_pop");
+    const float px = mx[pop_id], py = my[pop_id], pz = mz[pop_id];
+    // sampling (trg.cpp:384-403) with the reference's loop, collision bits fetched 64 draws at a time
+    size_t pos = (size_t)st.pos;
+    std::vector<std::pair<float, float>> samples;
+    int trial_sample = 0;
+    std::vector<float> qxy;
+    std::vector<uint8_t> coll;
+    size_t chunk_pos = 0;
+    size_t chunk_n = 0;
+    while ((int)samples.size() < S) {
+      if (trial_sample > 1000) break;
+      if (pos >= chunk_pos + chunk_n) {
+        chunk_pos = pos;
+        chunk_n = 64;
+        ensureDraws(chunk_pos + chunk_n);
+        qxy.resize(2 * chunk_n);
+        coll.resize(chunk_n);
+        for (size_t k = 0; k < chunk_n; ++k) {
+          const size_t d = chunk_pos + k - draw_base_;
+          qxy[2 * k]     = px + draw_xy_[2 * d];
+          qxy[2 * k + 1] = py + draw_xy_[2 * d + 1];
+        }
+        K(trgb_collision_batch(map, qxy.data(), (int64_t)chunk_n, param_.robot_size, param_.height_threshold,
+                               param_.collision_threshold, coll.data()), "trgb_collision_batch");
+      }
+      const size_t k = pos - chunk_pos;
+      ++pos;
+      if (coll[k]) { ++trial_sample; continue; }
+      samples.emplace_back(qxy[2 * k], qxy[2 * k + 1]);
+    }
+    // per sample: kd_nearest2 over every node so far, exact ties by the reference tree's visit order
+    std::vector<float> new_nodes;  // x, y, z, state
+    std::vector<int32_t> ra, rb;
+    std::vector<float> rw, rd;
+    for (auto& s : samples) {
+      const float sx = s.first, sy = s.second;
+      float best = std::numeric_limits<float>::infinity();
+      std::vector<int> cand;
+      const size_t N = mx.size();
+      for (size_t i = 0; i < N; ++i) {
+        const float dx = mx[i] - sx, dy = my[i] - sy;
+        const float d2 = dx * dx + dy * dy;
+        if (d2 < best) { best = d2; cand.clear(); cand.push_back((int)i); }
+        else if (d2 == best) cand.push_back((int)i);
+      }
+      int ex = cand[0];
+      if (cand.size() > 1) {
+        ++n_node_ties_;
+        ex = trg_b200::first_visited_of(mx.data(), my.data(), cand, sx, sy);
+      }
+      if (mstate[ex] == -1) continue;                                  // trg.cpp:411
+      if (sqrtf(best) < param_.robot_size) {                           // trg.cpp:414
+        ra.push_back(pop_id); rb.push_back(ex); rw.push_back(0.f); rd.push_back(0.f);
+        continue;
+      }
+      float z = 0.f;
+      uint8_t tie = 0;
+      const float xy[2] = {sx, sy};
+      K(trgb_nearest_z_batch(map, xy, 1, &z, nullptr, &tie), "trgb_nearest_z_batch");
+      if (tie) stat_["z_ties"]++;
+      const float p1[3] = {px, py, pz}, p2[3] = {sx, sy, z};
+      TrgbEdgeParams prm{param_.robot_size, param_.height_threshold, param_.collision_threshold, 0};
+      uint8_t stage = 0;
+      float w = 0.f, d = 0.f;
+      K(trgb_edge_eval_batch(map, p1, p2, 1, &prm, &stage, &w, &d, nullptr), "trgb_edge_eval_batch");  // incl. glibc slope gate
+      const bool valid = stage == TRGB_EDGE_OK;
+      const int nid = (int)mx.size();
+      mx.push_back(sx); my.push_back(sy); mz.push_back(z); mstate.push_back(valid ? 0 : -1);
+      new_nodes.push_back(sx); new_nodes.push_back(sy); new_nodes.push_back(z); new_nodes.push_back(valid ? 0.f : -1.f);
+      if (valid) { ra.push_back(pop_id); rb.push_back((int32_t)((uint32_t)nid | 0x80000000u)); rw.push_back(w); rd.push_back(d); }
+    }
+    K(trgb_expander_apply_pop(e, (int)(new_nodes.size() / 4), new_nodes.data(), (int)ra.size(), ra.data(), rb.data(), rw.data(),
+                              rd.data(), (int64_t)pos), "trgb_expander_apply_pop");
+  };
+
+  // ---- the BFS: two groups of steps in flight, one status poll per group ----------------------
+  int hint = 64;
+  TrgbExpandStatus st{};
+  int slot = 0;
+  K(trgb_expander_enqueue(e, group, hint), "trgb_expander_enqueue");
+  K(trgb_expander_snapshot(e, slot), "trgb_expander_snapshot");
+  int64_t polls = 0;
+  while (true) {
+    // next group goes out before this one is awaited
+    K(trgb_expander_enqueue(e, group, hint), "trgb_expander_enqueue");
+    K(trgb_expander_snapshot(e, slot ^ 1), "trgb_expander_snapshot");
+    K(trgb_expander_wait(e, slot, &st), "trgb_expander_wait");
+    ++polls;
+    slot ^= 1;
+    if (st.interrupt) {
+      K(trgb_expander_wait(e, slot, &st), "trgb_expander_wait");  // the group in flight is idle: drain it
+      handle_interrupt(st);
+      if (out_of_capacity) {  // cannot happen with the packing bound; the host-driven path takes over from the root
+        stat_["device_expand_capacity"]++;
+        return false;
+      }
+      K(trgb_expander_enqueue(e, group, hint), "trgb_expander_enqueue");
+      K(trgb_expander_snapshot(e, slot), "trgb_expander_snapshot");
+      continue;
+    }
+    if (st.head >= st.tail) {
+      K(trgb_expander_wait(e, slot, &st), "trgb_expander_wait");  // drain the idle group
+      if (st.interrupt || st.head < st.tail) throw std::logic_error("trg_b200: device expander restarted after draining");
+      break;
+    }
+    const int q = st.tail - st.head;
+    hint = std::min(tuning_.expand_max_pops, std::max(64, q + q / 4 + 64));
+    ahead = std::min<size_t>((size_t)1 << 22, std::max<size_t>((size_t)1 << 17, (size_t)4 * group * (size_t)hint * (size_t)(S + 2)));
+    push_upto((size_t)st.pos + ahead);
+    if (polls > 4000000) throw std::logic_error("trg_b200: device expander makes no progress");
+  }
+  draw_next_ = (size_t)st.pos;
+  const double t_bfs = since(t_begin);
+
+  // ---- edges on the device, then everything back ------------------------------------------------
+  auto t_fin = Clock::now();
+  int64_t n_all = 0, n_dir = 0;
+  K(trgb_expander_finalize(e, &n_all, &n_dir), "trgb_expander_finalize");
+  std::vector<float> xyz((size_t)n_all * 3), ew((size_t)n_dir), ed((size_t)n_dir);
+  std::vector<int8_t> state((size_t)n_all);
+  std::vector<int64_t> row((size_t)n_all + 1);
+  std::vector<int32_t> col((size_t)n_dir);
+  K(trgb_expander_download(e, xyz.data(), state.data(), row.data(), col.data(), ew.data(), ed.data()), "trgb_expander_download");
+  const double t_edges = since(t_fin);
+
+  // ---- cleanGraph(false) (trg.cpp:491-535), straight into the cleaned containers ------------------
+  auto t_mat = Clock::now();
+  const size_t n = (size_t)n_all;
+  // survivors in the iteration order of the map the reference filled with ids 0 .. n-1 (:497-504)
+  const std::vector<int> order1 = sequential_map_order(n, g.nodes.bucket_count());
+  std::vector<int> old2new(n, -1);
+  std::vector<int> kept;
+  kept.reserve(n);
+  for (int id : order1) {
+    if (state[id] == -1 || row[id + 1] == row[id]) continue;  // Invalid or no edges (:498)
+    old2new[id] = (int)kept.size();
+    kept.push_back(id);
+  }
+  const size_t m = kept.size();
+  // node / edge objects from the pools (recycled across builds), filled in parallel
+  rewindPools();
+  while (node_pool_.size() < m) {
+    Eigen::Vector2f z2(0.f, 0.f);
+    node_pool_.emplace_back(0, z2, 0.f, NodeState::Valid);
+    node_pool_.back().edges_.reserve(8);
+  }
+  size_t e_total = 0;
+  std::vector<size_t> e_off(m + 1, 0);
+  for (size_t k = 0; k < m; ++k) {
+    e_off[k] = e_total;
+    e_total += (size_t)(row[kept[k] + 1] - row[kept[k]]);
+  }
+  e_off[m] = e_total;
+  while (edge_pool_.size() < e_total) edge_pool_.emplace_back(0, 0.f, 0.f);
+  node_used_ = m;
+  edge_used_ = e_total;
+  const int threads = m > (size_t)tuning_.parallel_min_nodes ? trg_b200::thread_budget() : 1;
+  parallel_for(m, threads, [&](size_t b, size_t en) {
+    for (size_t k = b; k < en; ++k) {
+      const int old = kept[k];
+      Node& nd = node_pool_[k];
+      nd.id_ = (int)k;
+      nd.pos_ = Eigen::Vector3f(xyz[3 * (size_t)old], xyz[3 * (size_t)old + 1], xyz[3 * (size_t)old + 2]);
+      nd.state_ = static_cast<NodeState>((int)state[old]);
+      nd.edges_.clear();
+      size_t eo = e_off[k];
+      for (int64_t j = row[old]; j < row[old + 1]; ++j) {
+        // no edge leads to an Invalid node here (a node is Invalid from birth and never wired, :411), so
+        // the del_edges filter of :505-517 keeps everything; ids are remapped (:518)
+        Edge& ed2 = edge_pool_[eo++];
+        ed2.dst_id_ = old2new[col[(size_t)j]];
+        ed2.weight_ = ew[(size_t)j];
+        ed2.dist_ = ed[(size_t)j];
+        nd.edges_.push_back(&ed2);
+      }
+    }
+  });
+  // the renumbered map is a fresh container filled with 0 .. m-1 in order (:502, :526)
+  std::unordered_map<int, Node*> new_nodes;
+  for (size_t k = 0; k < m; ++k) new_nodes[(int)k] = &node_pool_[k];
+  std::unordered_map<int, Node*> old_nodes;
+  old_nodes.swap(g.nodes);
+  this->resetGraph(g.type);
+  this->resetGraph("local");
+  g.nodes   = std::move(new_nodes);
+  g.node_id = (int)m;
+  g.node_seq.reserve(m);
+  for (auto& node : g.nodes) nodeIndexInsert(g, node.second);  // node_tree order = new map's iteration order (:528-530)
+  invalidateDeviceGraph();
+  const double t_materialize = since(t_mat);
+
+  stat_["pops"] += st.pops;
+  stat_["window_tests"] += st.window_tests;
+  stat_["window_launches"] += st.steps_active;
+  stat_["eval_launches"] += st.steps_active;
+  stat_["z_ties"] += st.z_ties;
+  stat_["device_steps"] += st.steps;
+  stat_["device_steps_active"] += st.steps_active;
+  stat_["device_rounds"] += st.rounds;
+  stat_["device_redo_pops"] += st.redo_pops;
+  stat_["device_interrupts"] += n_interrupts;
+  stat_["device_polls"] += polls;
+  stat_["device_builds"]++;
+  stat_["nearest_node"] += st.samples;
+  stat_["edge_evals"] += st.n_req;
+  stat_["us_device_bfs"] += (int64_t)(1e6 * t_bfs);
+  stat_["us_device_edges"] += (int64_t)(1e6 * t_edges);
+  stat_["us_materialize"] += (int64_t)(1e6 * t_materialize);
+  return true;
+}
