@@ -211,7 +211,8 @@ def run_product(a):
         return st["bytes"]
 
     STAT_KEYS = ("us_sample", "us_eval", "us_commit", "us_wait", "us_clean", "us_draws", "pops", "window_launches",
-                 "eval_launches", "window_tests", "edge_evals")
+                 "eval_launches", "window_tests", "edge_evals", "us_device_bfs", "us_device_edges", "us_materialize",
+                 "device_steps", "device_rounds", "device_redo_pops", "device_interrupts", "device_builds")
 
     def one_step(resident: bool):
         resident_leg[0] = resident

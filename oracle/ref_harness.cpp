@@ -99,6 +99,10 @@ extern "C" void exit(int code) {
   _exit(code);
 }
 
+// The library is compiled with -fvisibility=hidden: the reference's class is called `TRG` like the
+// product's drop-in class, and both libraries live in one test process — only the orc_* facade may
+// be visible, or the dynamic linker would resolve one library's TRG::TRG(...) to the other's.
+#pragma GCC visibility push(default)
 extern "C" {
 
 void* orc_create(const OrcParams* p) { return new RefTRG(*p); }
@@ -365,3 +369,4 @@ int orc_load_graph(void* h, const char* path) {
 int orc_is_reference_build(void) { return 1; }
 
 }  // extern "C"
+#pragma GCC visibility pop

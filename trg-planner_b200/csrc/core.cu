@@ -1,5 +1,10 @@
 // Error state, device selection, launch geometry and the CUDA-event profiler shared by all
 // kernels of libtrgb_kernels.so.
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <vector>
@@ -7,6 +12,24 @@
 #include "common.cuh"
 
 namespace trgb {
+
+// TRGB_BACKTRACE=1: native backtrace on SIGSEGV / SIGFPE / SIGABRT (debugging aid; Python's faulthandler
+// only shows the Python frames)
+static void crash_handler(int sig) {
+  void* bt[64];
+  const int n = backtrace(bt, 64);
+  const char msg[] = "[trgb] fatal signal, native backtrace:\n";
+  if (write(2, msg, sizeof(msg) - 1) < 0) {}
+  backtrace_symbols_fd(bt, n, 2);
+  _exit(128 + sig);
+}
+static const bool g_crash_handler_installed = [] {
+  if (!std::getenv("TRGB_BACKTRACE")) return false;
+  signal(SIGSEGV, crash_handler);
+  signal(SIGFPE, crash_handler);
+  signal(SIGABRT, crash_handler);
+  return true;
+}();
 
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
@@ -55,6 +78,9 @@ static std::vector<Pending> g_pending;
 static std::vector<cudaEvent_t> g_pool;
 static std::map<std::string, Acc> g_acc;
 static std::atomic<int64_t> g_launches{0};
+
+bool prof_enabled() { return g_prof_on; }
+void count_launches(int64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 static cudaEvent_t get_event() {
   if (!g_pool.empty()) {

@@ -9,13 +9,16 @@
 // earlier, still undecided sample next to me" are short (5 - 8 links). One STEP of this engine
 // handles up to a few thousand queued pops at once:
 //
-//   k_exp_plan     pops of this step, their guessed stream positions (running mean / variance)
+//   (plan)         pops of this step, their guessed stream positions (running mean / variance): done by
+//                  the commit kernel of the step before (k_exp_plan for the first step of a queued group)
 //   k_exp_window   collision bit of every (pop, draw) in a window around the guess   [K2 device code]
 //   k_exp_tables   per pop: draws consumed as a function of the start offset; composed per 32 pops
 //   k_exp_top      the exact chain o_{i+1} = o_i + consumed_i(o_i) over the composed blocks
-//   k_exp_emit     accepted samples of every pop whose chain position is now known
-//   k_exp_nearest  nearest node among those that existed before the step               [K5 grid]
+//   k_exp_emit     accepted samples of every pop whose chain position is now known + their nearest node
+//                  among those that existed before the step                             [K5 grid]
+//   k_exp_deps     per sample: the few earlier samples of the step whose fate can change its own
 //   K3 + K4        height and parent edge of every sample that may become a node (existing kernels)
+// (one captured CUDA graph per launch size replays these; k_exp_deps runs beside K3 / K4)
 //   k_exp_commit   deterministic-reservation rounds: a sample is decided once no earlier undecided
 //                  sample that could still become a node lies within its current nearest distance;
 //                  decided samples are applied in (pop, sample) order: node ids by prefix sum, queue
@@ -31,10 +34,10 @@
 // at that pop; the host library handles that single pop with the reference's tie / libm rules and
 // resumes (trgb_expander_apply_pop).
 #include <cooperative_groups.h>
-#include <cub/cub.cuh>
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -68,6 +71,7 @@ struct ExpCtl {
   int n_done;              // pops of this step whose chain position is known
   int n_commit;
   int ipop;                // first pop of the step the host must handle (tie / slope), INT_MAX = none
+  int blocks_done;         // CTAs of k_exp_tables that have finished (the last one walks the chain)
   int und[2][16];          // undecided samples per commit CTA, double-buffered by round parity
   long long pos0, pos_done;
   // statistics
@@ -91,6 +95,7 @@ struct ExpView {
   float2* s_xy; float* s_p1; int* s_nn; float* s_d2; unsigned char* s_tie;
   float* s_z; unsigned char* s_ztie; unsigned char* s_stage; float* s_w; float* s_d;
   int* st; float* cur_d2; int* cur_nn; int* hnext; unsigned char* s_pc;
+  int* dhead; int* dnext; int* dep_j; float* dep_d2; int* dep_n;  // per-step hash of potential creators + dependency lists
   // params
   float e, r, hthr, cthr, max_slope; int S, C, norm_words, new_state;
 };
@@ -105,40 +110,46 @@ __device__ __forceinline__ int exp_ncell(float v, float origin, float inv, int d
 // ------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_exp_plan(ExpView v, int c_step) {
+// Plan of the next step, executed by one whole thread block (any size): pops taken, window geometry,
+// guessed stream positions, zeroed masks.
+__device__ void exp_plan_block(const ExpView& v, int c_step) {
   ExpCtl* c = v.ctl;
   __shared__ int s_m, s_words, s_D, s_fit;
   __shared__ float s_mean, s_var;
   __shared__ long long s_room;
+  __syncthreads();
   if (threadIdx.x == 0) {
-    c->steps++;
+    ExpCtl k = *c;  // (one read, one write-back)
     int m = 0;
-    c->slow = 0;
-    c->n_done = 0;
-    c->n_commit = 0;
-    c->ipop = 0x7fffffff;
+    k.slow = 0;
+    k.n_done = 0;
+    k.n_commit = 0;
+    k.ipop = 0x7fffffff;
+    k.blocks_done = 0;
     int words = v.norm_words;
-    if (!c->interrupt && c->head < c->tail) {
-      const int avail = c->tail - c->head;
-      if (c->stuck >= 1) {  // the first pop needs more draws than a normal window covers
+    if (!k.interrupt && k.head < k.tail) {
+      const int avail = k.tail - k.head;
+      if (k.stuck >= 1) {  // the first pop needs more draws than a normal window covers
         m = 1;
         words = kExpSlowWords;
-        c->slow = 1;
+        k.slow = 1;
       } else {
         const int D = 64 * words - 32;
         // longest chain whose drift (random walk, variance `var` per pop) stays inside the admissible
         // start offsets with ~2 sigma: 2 + 2 sqrt(L var) <= D / 2
         const float half = 0.5f * (float)D - 2.f;
-        int L = (int)((half * half * 0.25f) / fmaxf(c->var, 0.05f));
+        int L = (int)((half * half * 0.25f) / fmaxf(k.var, 0.05f));
         L = max(L, 64);
         m = min(min(avail, c_step), min(L, v.C));
       }
-      c->W = 64 * words; c->words = words; c->D = c->slow ? 1 : 64 * words - 32;
-      c->pos0 = c->pos;
+      k.W = 64 * words; k.words = words; k.D = k.slow ? 1 : 64 * words - 32;
+      k.pos0 = k.pos;
     }
-    s_m = m; s_words = words; s_D = c->D; s_fit = m;
-    s_mean = c->mean; s_var = c->var;
-    s_room = c->draws_end - c->pos;  // draws available from pos0 on
+    s_m = m; s_words = words; s_D = k.D; s_fit = m;
+    s_mean = k.mean; s_var = k.var;
+    s_room = k.draws_end - k.pos;  // draws available from pos0 on
+    k.m = m;
+    *c = k;
   }
   __syncthreads();
   // guesses (relative to pos0): exact for pop 0, extrapolated with the running mean minus a lead that
@@ -163,6 +174,12 @@ __global__ void __launch_bounds__(256) k_exp_plan(ExpView v, int c_step) {
   }
   const int n = m * s_words;
   for (int k = threadIdx.x; k < n; k += blockDim.x) v.mask[k] = 0ull;
+}
+
+// stand-alone plan: first step of a queued group, sized for that group's launches (the other steps are
+// planned by the commit kernel before them; planning twice is harmless)
+__global__ void __launch_bounds__(256) k_exp_plan(ExpView v, int c_step) {
+  exp_plan_block(v, c_step);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -215,88 +232,99 @@ __global__ void TQ_BOUNDS k_exp_window(MapView m, ExpView v, int cap) {
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd((unsigned long long*)&v.ctl->window_tests, (unsigned long long)items);
 }
 
+// ---- bit helpers on a pop's window (collision bits; a free draw is a ZERO bit) -------------------------
 // draws consumed by a pop that starts at bit `r` of its window: S collision-free draws (trg.cpp:387-403;
 // the trial cap of :388 cannot trigger inside a normal window of <= 256 draws). 255 = the window ends first.
-__device__ __forceinline__ int next_zero(const unsigned long long (&mk)[4], int words, int from) {  // first free draw at or after `from`
-  int w = from >> 6;
-  if (w >= words) return -1;
-  unsigned long long cur = ~mk[w] & (~0ull << (from & 63));
+__device__ __forceinline__ int consumed_from(const unsigned long long (&mk)[4], int words, int r, int S) {
+  int w = r >> 6;
+  unsigned long long cur = ~mk[w] & (~0ull << (r & 63));
+  int need = S;
   while (true) {
-    if (cur) return w * 64 + __ffsll((long long)cur) - 1;
-    if (++w >= words) return -1;
+    const int pc = __popcll(cur);
+    if (pc >= need) {
+      for (int k = 1; k < need; ++k) cur &= cur - 1;
+      return min(255, w * 64 + __ffsll((long long)cur) - r);  // index of the S-th free draw + 1 - r
+    }
+    need -= pc;
+    if (++w >= words) return 255;
     cur = ~mk[w];
   }
 }
-
-constexpr int kRow = 228;  // bytes per table row in shared memory (57 words: lanes hit distinct banks)
-
-// consumed(start offset) of one pop for every start offset < D, by one lane: the S-th free draw at or
-// after r moves to the next free draw whenever r passes a free draw (two pointers, O(W) in all)
-__device__ __forceinline__ void pop_table(const unsigned long long* gmask, int words, int D, int S, unsigned char* row) {
-  unsigned long long mk[4] = {~0ull, ~0ull, ~0ull, ~0ull};
-  for (int w = 0; w < words; ++w) mk[w] = gmask[w];
-  int q = -1;  // position of the S-th free draw at or after r
-  {
-    int p = -1;
-    for (int k = 0; k < S; ++k) {
-      p = next_zero(mk, words, p + 1);
-      if (p < 0) break;
-    }
-    q = p;
-  }
-  for (int r = 0; r < D; ++r) {
-    const int cc = q < 0 ? 255 : min(255, q + 1 - r);
-    row[r] = (unsigned char)cc;
-    const bool freebit = !((mk[r >> 6] >> (r & 63)) & 1ull);
-    if (freebit && q >= 0) q = next_zero(mk, words, q + 1);
-  }
+// number of free draws below bit b
+__device__ __forceinline__ int free_below(const unsigned long long (&mk)[4], int b) {
+  const int w = b >> 6;
+  int n = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k < w) n += __popcll(~mk[k]);
+  if (w < 4) n += __popcll(~mk[w] & ((1ull << (b & 63)) - 1ull));
+  return n;
 }
 
-// one warp per block of 32 pops: lane p builds the table of pop p, then lane r composes the block's
-// map (start offset at its first pop -> end position, pops completed)
-__global__ void __launch_bounds__(128) k_exp_tables(ExpView v) {
+constexpr int kRow = 228;  // bytes per table row in shared memory
+constexpr int kWarpSm = 32 * kRow + 256;  // per warp: 32 table rows + the free-draw positions of one pop
+constexpr int kDepMax = 16;    // earlier potential creators kept per sample (more: full-scan fallback)
+constexpr int kDepHash = 32768;  // buckets of the per-step hash over potential creators (global memory)
+
+__device__ __forceinline__ unsigned dep_hash(int cx, int cy) {
+  return ((unsigned)cx * 73856093u ^ (unsigned)cy * 19349663u) & (kDepHash - 1);
+}
+
+// ---- chain kernels --------------------------------------------------------------------------------------
+// tables: one CTA (8 warps) per block of 32 pops, four pops per warp. All 32 lanes of a warp work on one
+// pop at a time: positions of its free draws, then consumed(start offset) for every admissible offset
+// (the S-th free draw at or after r is free draw number free_below(r) + S - 1). Afterwards thread r
+// composes the block's map (start offset at its first pop -> end position, pops completed). The CTA
+// that finishes last walks the chain over all blocks (exp_top_phase).
+__device__ __forceinline__ void exp_tables_block(const ExpView& v, unsigned char* smem, int b) {
   const ExpCtl* c = v.ctl;
   const int m = c->m;
-  if (m == 0 || c->slow) return;
-  const int words = c->words, D = c->D, S = v.S;
-  const int lane = threadIdx.x & 31;
-  const int nblk = (m + 31) >> 5;
-  __shared__ unsigned char tab[4][32 * kRow];
-  unsigned char* t = tab[threadIdx.x >> 5];
-  for (int b = blockIdx.x * 4 + (threadIdx.x >> 5); b < nblk; b += gridDim.x * 4) {
-    const int first = b << 5;
-    const int cnt = min(32, m - first);
-    if (lane < cnt) pop_table(v.mask + (size_t)(first + lane) * words, words, D, S, t + lane * kRow);
+  const int words = c->words, D = c->D, S = v.S, W = c->W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* t = smem;                            // 32 rows of kRow bytes
+  unsigned char* zp = smem + 32 * kRow + warp * 256;  // free-draw positions of the pop a warp works on
+  const int first = b << 5;
+  const int cnt = min(32, m - first);
+  for (int p = warp; p < cnt; p += 8) {
+    unsigned long long mk[4] = {~0ull, ~0ull, ~0ull, ~0ull};
+    for (int w = 0; w < words; ++w) mk[w] = v.mask[(size_t)(first + p) * words + w];
+    for (int bpos = lane; bpos < W; bpos += 32)
+      if (!((mk[bpos >> 6] >> (bpos & 63)) & 1ull)) zp[free_below(mk, bpos)] = (unsigned char)bpos;
+    int nz = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) nz += __popcll(~mk[w]);
     __syncwarp();
-    const int g0 = v.g_off[first];
-    const int gl = lane < cnt ? v.g_off[first + lane] : 0;
-    for (int r = lane; r < D; r += 32) {  // D is a multiple of 32: the warp stays converged for the shuffles
-      int a = g0 + r;  // relative to pos0
-      int stop = cnt;
-      for (int p = 0; p < cnt; ++p) {
-        const int gp = __shfl_sync(FULL, gl, p);
-        if (stop == cnt) {
-          const int rr = a - gp;
-          if (rr < 0 || rr >= D) stop = p;
-          else {
-            const int cc = t[p * kRow + rr];
-            if (cc == 255) stop = p; else a += cc;
-          }
-        }
-      }
-      v.blk_end[(size_t)b * 256 + r] = a;
-      v.blk_stop[(size_t)b * 256 + r] = (unsigned char)stop;
+    for (int r = lane; r < D; r += 32) {
+      const int idx = free_below(mk, r) + S - 1;
+      const int cc = idx < nz ? min(255, (int)zp[idx] + 1 - r) : 255;
+      v.ctab[(size_t)(first + p) * 256 + r] = (unsigned char)cc;
+      t[p * kRow + r] = (unsigned char)cc;
     }
     __syncwarp();
   }
+  __shared__ int s_gl[32];
+  if (threadIdx.x < 32) s_gl[threadIdx.x] = threadIdx.x < cnt ? v.g_off[first + threadIdx.x] : 0;
+  __syncthreads();
+  for (int r = threadIdx.x; r < D; r += blockDim.x) {
+    int a = s_gl[0] + r;  // relative to pos0
+    int stop = cnt;
+    for (int p = 0; p < cnt; ++p) {
+      const int rr = a - s_gl[p];
+      if (rr < 0 || rr >= D) { stop = p; break; }
+      const int cc = t[p * kRow + rr];
+      if (cc == 255) { stop = p; break; }
+      a += cc;
+    }
+    v.blk_end[(size_t)b * 256 + r] = a;
+    v.blk_stop[(size_t)b * 256 + r] = (unsigned char)stop;
+  }
 }
 
-// the chain over the composed blocks: tables staged in shared memory, then one thread walks them;
-// or the single pop of slow mode
-__global__ void __launch_bounds__(1024) k_exp_top(ExpView v) {
+// top (one CTA): the chain over the composed blocks, staged in shared memory and walked by one
+// thread; or the single pop of slow mode
+__device__ __forceinline__ void exp_top_phase(const ExpView& v, unsigned char* smem) {
   ExpCtl* c = v.ctl;
   const int m = c->m;
-  if (m == 0) return;
   const int S = v.S;
   if (c->slow) {
     if (threadIdx.x != 0) return;
@@ -324,15 +352,14 @@ __global__ void __launch_bounds__(1024) k_exp_top(ExpView v) {
     c->pos_done = c->pos0 + j;
     return;
   }
-  extern __shared__ int top_sm[];
   const int D = c->D;
   const int nblk = (m + 31) >> 5;
-  int* s_end = top_sm;                                            // nblk * D
+  int* s_end = reinterpret_cast<int*>(smem);                                   // nblk * D
   unsigned char* s_stop = reinterpret_cast<unsigned char*>(s_end + nblk * D);  // nblk * D
   for (int k = threadIdx.x; k < nblk * D; k += blockDim.x) {
     const int b = k / D, r = k - b * D;
-    s_end[k] = v.blk_end[(size_t)b * 256 + r];
-    s_stop[k] = v.blk_stop[(size_t)b * 256 + r];
+    s_end[k] = __ldcg(v.blk_end + (size_t)b * 256 + r);   // written by other CTAs of this launch: L2 is the coherence point
+    s_stop[k] = __ldcg(v.blk_stop + (size_t)b * 256 + r);
   }
   __shared__ int s_g[kExpMaxPops / 32];
   for (int b = threadIdx.x; b < nblk; b += blockDim.x) s_g[b] = v.g_off[b << 5];
@@ -354,49 +381,113 @@ __global__ void __launch_bounds__(1024) k_exp_top(ExpView v) {
   c->pos_done = c->pos0 + a;
 }
 
-// accepted samples of every pop with a known chain position; one warp per block of 32 pops
-__global__ void __launch_bounds__(128) k_exp_emit(ExpView v) {
+// nearest node (among those that existed before the step) of one sample; a sample that may become a node
+// (nearest node at least robot_size away, trg.cpp:414) is entered into the step's hash
+__device__ __forceinline__ void exp_nearest_one(const ExpView& v, int s, float hinv) {
+  const float2 p = v.s_xy[s];
+  float bd = INFINITY;
+  int bi = -1, tie = 0;
+  const int qcx = exp_ncell(p.x, v.gx0, v.ginv, v.GW), qcy = exp_ncell(p.y, v.gy0, v.ginv, v.GH);
+  const float fuzz = 4e-6f * (fabsf(p.x) + fabsf(p.y) + v.gcell * (float)(v.GW + v.GH));
+  const int maxr = max(v.GW, v.GH);
+  auto scan = [&](int e) {
+    for (; e >= 0; e = v.gnext[e]) {
+      const float2 q = v.node_xy[e];
+      const float dx = __fsub_rn(q.x, p.x), dy = __fsub_rn(q.y, p.y);
+      const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+      if (d2 < bd) { bd = d2; bi = e; tie = 0; }
+      else if (d2 == bd && e != bi) tie = 1;
+    }
+  };
+  {  // the 3 x 3 block: all nine list heads are fetched before any list is walked
+    int hd[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const int xx = qcx + (k % 3) - 1, yy = qcy + (k / 3) - 1;
+      hd[k] = (xx < 0 || yy < 0 || xx >= v.GW || yy >= v.GH) ? -1 : v.ghead[(size_t)yy * v.GW + xx];
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) scan(hd[k]);
+  }
+  for (int R = 1; R <= maxr; ++R) {
+    if (R > 1) {
+      for (int yy = qcy - R; yy <= qcy + R; ++yy) {
+        if (yy < 0 || yy >= v.GH) continue;
+        const bool edge_row = (yy == qcy - R || yy == qcy + R);
+        for (int xx = qcx - R; xx <= qcx + R; ++xx) {
+          if (xx < 0 || xx >= v.GW) continue;
+          if (!edge_row && xx != qcx - R && xx != qcx + R) continue;  // ring only
+          scan(v.ghead[(size_t)yy * v.GW + xx]);
+        }
+      }
+    }
+    // cells outside the scanned block are at least R whole cells away from the query's cell
+    const float g = (float)R * v.gcell * 0.9999f - fuzz;
+    if (bi >= 0 && g > 0.f && bd <= g * g) break;
+    if (qcx - R <= 0 && qcy - R <= 0 && qcx + R >= v.GW - 1 && qcy + R >= v.GH - 1) break;
+  }
+  v.s_d2[s] = bd;
+  v.s_nn[s] = bi;
+  v.s_tie[s] = (unsigned char)tie;
+  const bool pc = __fsqrt_rn(bd) >= v.r;
+  v.s_pc[s] = pc ? 1 : 0;
+  if (pc) {
+    const unsigned h = dep_hash((int)floorf((p.x - v.gx0) * hinv), (int)floorf((p.y - v.gy0) * hinv));
+    v.dnext[s] = atomicExch(v.dhead + h, s);
+  }
+}
+
+// One CTA per block of 32 pops. Warp 0 walks the block again from its known start (lane p owns the window
+// of pop p and answers for it) and writes the accepted samples; then every thread of the CTA takes
+// samples of the block and looks up their nearest existing node. Slots without a sample get d2 = 0,
+// which makes the K3 / K4 launches skip them.
+__global__ void __launch_bounds__(256) k_exp_emit(ExpView v) {
   const ExpCtl* c = v.ctl;
   const int n_done = c->n_done;
-  if (n_done == 0) return;
-  const int words = c->words, S = v.S, D = c->D;
-  const int lane = threadIdx.x & 31;
-  const int nblk = (n_done + 31) >> 5;
-  const int head = c->head;
-  const long long dbase = c->pos0 - c->draws_base;
-  __shared__ unsigned char tab[4][32 * kRow];
-  unsigned char* t = tab[threadIdx.x >> 5];
-  for (int b = blockIdx.x * 4 + (threadIdx.x >> 5); b < nblk; b += gridDim.x * 4) {
-    const int first = b << 5;
-    const int cnt = min(32, n_done - first);
-    int my_start = 0, my_cons = 0;
-    if (c->slow) {
-      my_start = 0;
-      my_cons = v.pop_cons[0];
-    } else {
-      // rebuild the block's tables (cheaper than reading them back) and walk it; lane p keeps pop p
-      if (lane < cnt) pop_table(v.mask + (size_t)(first + lane) * words, words, D, S, t + lane * kRow);
-      __syncwarp();
-      const int gl = lane < cnt ? v.g_off[first + lane] : 0;
+  const int words = c->words, S = v.S;
+  const int b = blockIdx.x;
+  const int first = b << 5;
+  const int cnt = max(0, min(32, n_done - first));
+  __shared__ unsigned char s_acc[32];
+  __shared__ unsigned char s_tab[32 * 224];
+  __shared__ int s_start[32], s_cons[32], s_gl2[32];
+  const int D = c->D;
+  if (cnt > 0 && !c->slow) {
+    for (int k = threadIdx.x; k < cnt * D; k += blockDim.x) {
+      const int p = k / D, r = k - p * D;
+      s_tab[p * 224 + r] = v.ctab[(size_t)(first + p) * 256 + r];
+    }
+    if (threadIdx.x < cnt) s_gl2[threadIdx.x] = v.g_off[first + threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
       int a = v.blk_start[b];
       for (int p = 0; p < cnt; ++p) {
-        const int rr = a - __shfl_sync(FULL, gl, p);
-        const int cc = t[p * kRow + rr];
-        if (lane == p) { my_start = a; my_cons = cc; }
+        const int cc = s_tab[p * 224 + (a - s_gl2[p])];
+        s_start[p] = a;
+        s_cons[p] = cc;
         a += cc;
       }
-      __syncwarp();
     }
+    __syncthreads();
+  }
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int my_start = 0, my_cons = 0;
+    if (lane < cnt) {
+      if (c->slow) { my_start = 0; my_cons = v.pop_cons[0]; }
+      else { my_start = s_start[lane]; my_cons = s_cons[lane]; }
+    }
+    int acc = 0;
     if (lane < cnt) {
       const int i = first + lane;
       const int g = v.g_off[i];
       const unsigned long long* mk = v.mask + (size_t)i * words;
-      const int node = v.queue[head + i];
+      const int node = v.queue[c->head + i];
       const float2 np2 = v.node_xy[node];
       const float nz = v.node_z[node];
+      const long long dbase = c->pos0 - c->draws_base;
       v.pop_off[i] = my_start;
       v.pop_cons[i] = (unsigned short)my_cons;
-      int acc = 0;
       for (int j = my_start - g; j < my_start - g + my_cons; ++j) {
         const bool coll = (mk[j >> 6] >> (j & 63)) & 1ull;
         if (coll) continue;
@@ -408,69 +499,85 @@ __global__ void __launch_bounds__(128) k_exp_emit(ExpView v) {
       }
       v.pop_acc[i] = (unsigned char)acc;  // < S only when the trial cap ended the pop
     }
+    s_acc[lane] = (unsigned char)acc;
   }
-}
-
-// nearest node (among those that existed before the step) of every sample slot; slots without a
-// sample get d2 = 0, which makes the K3 / K4 launches skip them
-__global__ void __launch_bounds__(256) k_exp_nearest(ExpView v, int c_step) {
-  const ExpCtl* c = v.ctl;
-  const int S = v.S;
-  const int n_done = c->n_done;
-  const int total = c_step * S;
-  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < total; s += gridDim.x * blockDim.x) {
-    const int i = s / S, j = s - i * S;
-    if (i >= n_done || j >= v.pop_acc[i]) {
+  __syncthreads();  // (block-scope: the sample writes above are visible to the whole CTA)
+  const float hinv = 1.0f / (v.e * 1.001f + 1e-5f);
+  for (int k = threadIdx.x; k < 32 * S; k += blockDim.x) {
+    const int p = k / S, j = k - p * S;
+    const int s = (first + p) * S + j;
+    if (p >= cnt || j >= s_acc[p]) {
       v.s_d2[s] = 0.f;
       v.s_nn[s] = -1;
       v.s_tie[s] = 0;
+      v.s_pc[s] = 0;
       continue;
     }
-    const float2 p = v.s_xy[s];
-    float bd = INFINITY;
-    int bi = -1, tie = 0;
-    const int qcx = exp_ncell(p.x, v.gx0, v.ginv, v.GW), qcy = exp_ncell(p.y, v.gy0, v.ginv, v.GH);
-    const float fuzz = 4e-6f * (fabsf(p.x) + fabsf(p.y) + v.gcell * (float)(v.GW + v.GH));
-    const int maxr = max(v.GW, v.GH);
-    auto scan = [&](int e) {
-      for (; e >= 0; e = v.gnext[e]) {
-        const float2 q = v.node_xy[e];
-        const float dx = __fsub_rn(q.x, p.x), dy = __fsub_rn(q.y, p.y);
-        const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-        if (d2 < bd) { bd = d2; bi = e; tie = 0; }
-        else if (d2 == bd && e != bi) tie = 1;
-      }
-    };
-    {  // the 3 x 3 block: all nine list heads are fetched before any list is walked
-      int hd[9];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        const int xx = qcx + (k % 3) - 1, yy = qcy + (k / 3) - 1;
-        hd[k] = (xx < 0 || yy < 0 || xx >= v.GW || yy >= v.GH) ? -1 : v.ghead[(size_t)yy * v.GW + xx];
-      }
-#pragma unroll
-      for (int k = 0; k < 9; ++k) scan(hd[k]);
-    }
-    for (int R = 1; R <= maxr; ++R) {
-      if (R > 1) {
-        for (int yy = qcy - R; yy <= qcy + R; ++yy) {
-          if (yy < 0 || yy >= v.GH) continue;
-          const bool edge_row = (yy == qcy - R || yy == qcy + R);
-          for (int xx = qcx - R; xx <= qcx + R; ++xx) {
-            if (xx < 0 || xx >= v.GW) continue;
-            if (!edge_row && xx != qcx - R && xx != qcx + R) continue;  // ring only
-            scan(v.ghead[(size_t)yy * v.GW + xx]);
-          }
-        }
-      }
-      const float g = (float)R * v.gcell * 0.9999f - fuzz;
-      if (bi >= 0 && g > 0.f && bd <= g * g) break;
-      if (qcx - R <= 0 && qcy - R <= 0 && qcx + R >= v.GW - 1 && qcy + R >= v.GH - 1) break;
-    }
-    v.s_d2[s] = bd;
-    v.s_nn[s] = bi;
-    v.s_tie[s] = (unsigned char)tie;
+    exp_nearest_one(v, s, hinv);
   }
+}
+
+// Per sample, the earlier samples of the step that may become a node no farther away than the
+// sample's nearest existing node — the only ones whose fate can change the sample's own (a node is
+// relevant only if strictly nearer, or exactly as near: a tie the host resolves). Usually 0 - 3.
+__global__ void __launch_bounds__(256) k_exp_deps(ExpView v) {
+  const ExpCtl* c = v.ctl;
+  const int S = v.S;
+  const int ns = c->n_done * S;
+  if (ns == 0) return;
+  const float hinv = 1.0f / (v.e * 1.001f + 1e-5f);
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < ns; s += gridDim.x * blockDim.x) {
+    const int i = s / S, j = s - i * S;
+    if (j >= v.pop_acc[i]) continue;
+    const float2 p = v.s_xy[s];
+    const float bd = v.s_d2[s];
+    const int cx = (int)floorf((p.x - v.gx0) * hinv), cy = (int)floorf((p.y - v.gy0) * hinv);
+    int hd[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) hd[k] = v.dhead[dep_hash(cx + (k % 3) - 1, cy + (k / 3) - 1)];
+    int n = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+      for (int q = hd[k]; q >= 0; q = v.dnext[q]) {
+        if (q >= s) continue;
+        const float2 pq = v.s_xy[q];
+        const float dx = __fsub_rn(pq.x, p.x), dy = __fsub_rn(pq.y, p.y);
+        const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        if (!(d2 <= bd)) continue;
+        // (two buckets of the 3 x 3 block can collide in the hash: the same entry must not be listed twice)
+        bool dup = false;
+        for (int u = 0; u < min(n, kDepMax); ++u) dup |= v.dep_j[(size_t)s * kDepMax + u] == q;
+        if (dup) continue;
+        if (n < kDepMax) { v.dep_j[(size_t)s * kDepMax + n] = q; v.dep_d2[(size_t)s * kDepMax + n] = d2; }
+        ++n;
+      }
+    v.dep_n[s] = n;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_exp_tables(ExpView v) {
+  extern __shared__ unsigned char chsm[];
+  ExpCtl* c = v.ctl;
+  // (spare work: empty the hash the emit kernel fills)
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < kDepHash; k += gridDim.x * blockDim.x) v.dhead[k] = -1;
+  const int m = c->m;
+  if (m == 0) return;
+  if (c->slow) {
+    if (blockIdx.x == 0) exp_top_phase(v, chsm);
+    return;
+  }
+  const int nblk = (m + 31) >> 5;
+  if ((int)blockIdx.x >= nblk) return;
+  exp_tables_block(v, chsm, blockIdx.x);
+  // the CTA that finishes last walks the chain
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&c->blocks_done, 1) == nblk - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  exp_top_phase(v, chsm);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -491,50 +598,43 @@ __device__ __forceinline__ int slope_gate(float x1, float y1, float z1, float x2
   return 2;
 }
 
-__device__ __forceinline__ unsigned exp_hash(int cx, int cy) {
-  return ((unsigned)cx * 73856093u ^ (unsigned)cy * 19349663u) & (kExpHash - 1);
-}
-
-constexpr int kCommitCtas = 8;  // thread-block cluster running the reservation rounds
-
-// Reservation rounds on a cluster of kCommitCtas CTAs (samples are dealt round-robin to their threads;
-// cluster barriers between the read and the write half of a round), then CTA 0 applies the decisions
-// in (pop, sample) order.
-__global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v) {
-  cg::cluster_group cl = cg::this_cluster();
-  const int NC = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+// Reservation rounds + application of the decisions in (pop, sample) order + plan of the next step.
+// A round costs an undecided sample a walk over its short dependency list (phase 5 of the chain kernel);
+// everything is in global memory that only this CTA touches.
+__global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v, int c_step_next) {
   ExpCtl* c = v.ctl;
-  const int n_done = c->n_done;
   const int tid = threadIdx.x, T = blockDim.x;
+  const int n_done = c->n_done;
+  if (tid == 0) c->steps++;
   if (n_done == 0) {
-    if (rank == 0 && tid == 0 && c->m > 0) {
+    if (tid == 0 && c->m > 0) {
       c->stuck++;  // not even the first pop fitted its window: slow mode next
       c->redo_pops += c->m;
     }
+    exp_plan_block(v, c_step_next);
     return;
   }
-  __shared__ int hhead[kExpHash];
-  __shared__ int s_any, s_und;
+  extern __shared__ unsigned char sst[];  // decision state of every sample of the step
+  __shared__ int s_any, s_ipop;
   __shared__ unsigned long long s_part[1024];
   __shared__ unsigned long long s_sum, s_sq, s_tot;
   const int S = v.S;
-  const int ns = n_done * S;
   const float r = v.r;
-  const float hcell = v.e * 1.001f + 1e-5f;
-  const float hinv = 1.0f / hcell;
+  const float hinv = 1.0f / (v.e * 1.001f + 1e-5f);
   const int head = c->head;
   const int n_nodes0 = c->n_nodes;
-  int* hnext = v.hnext + (size_t)rank * ((size_t)v.C * S);  // this CTA's chains
-  for (int k = tid; k < kExpHash; k += T) hhead[k] = -1;
-  // ---- initial state (dealt over the whole cluster) ----------------------------------------------
-  for (int s = rank * T + tid; s < ns; s += NC * T) {
+  const int ns = n_done * S;
+  if (tid == 0) s_ipop = 0x7fffffff;
+  __syncthreads();
+  // ---- initial state ------------------------------------------------------------------------------
+  for (int s = tid; s < ns; s += T) {
     const int i = s / S, j = s - i * S;
     int st = ST_UNDECIDED;
     unsigned char pc = 0;
     if (j >= v.pop_acc[i]) st = ST_VOID;
     else {
-      if (v.s_tie[s]) atomicMin(&c->ipop, i);  // tie among existing nodes: the host resolves this pop
-      if (__fsqrt_rn(v.s_d2[s]) >= r) {        // trg.cpp:414 with the pre-step nearest node: may become a node
+      if (v.s_tie[s]) atomicMin(&s_ipop, i);   // tie among existing nodes: the host resolves this pop
+      if (v.s_pc[s]) {                         // trg.cpp:414 with the pre-step nearest node: may become a node
         // validity of the would-be node = its parent edge (trg.cpp:425, 447): K4 stage + slope gate
         int valid = 0;
         if (v.s_stage[s] == TRGB_EDGE_OK) {
@@ -547,18 +647,9 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v) {
         pc = (unsigned char)(1 | (valid << 1));  // bit 0 potential creator, bits 1-2: 0 invalid 1 valid 2/3 host decides
       }
     }
-    v.st[s] = st;
+    sst[s] = (unsigned char)st;
     v.s_pc[s] = pc;
     v.cur_d2[s] = v.s_d2[s];
-    v.cur_nn[s] = v.s_nn[s];
-  }
-  cl.sync();
-  // ---- every CTA hashes all potential creators into its own shared table ---------------------------
-  for (int s = tid; s < ns; s += T) {
-    if (!(v.s_pc[s] & 1)) continue;
-    const float2 p = v.s_xy[s];
-    const unsigned h = exp_hash((int)floorf((p.x - v.gx0) * hinv), (int)floorf((p.y - v.gy0) * hinv));
-    hnext[s] = atomicExch(&hhead[h], s);
   }
   __syncthreads();
   // ---- reservation rounds ----------------------------------------------------------------------------
@@ -566,47 +657,71 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v) {
   while (true) {
     // read half: nearest decided node so far; wait if an earlier undecided sample that may still become a
     // node lies at least as close
-    for (int s = rank * T + tid; s < ns; s += NC * T) {
-      if (v.st[s] != ST_UNDECIDED) continue;
-      const float2 p = v.s_xy[s];
-      float bd = v.s_d2[s];
-      int bn = v.s_nn[s];
+    for (int s = tid; s < ns; s += T) {
+      if (sst[s] != ST_UNDECIDED) continue;
+      float bd = __ldg(v.s_d2 + s);
+      int bn = __ldg(v.s_nn + s);
       int tie = 0;
       float mu = INFINITY;  // closest earlier undecided potential creator
-      const int cx = (int)floorf((p.x - v.gx0) * hinv), cy = (int)floorf((p.y - v.gy0) * hinv);
-      for (int yy = cy - 1; yy <= cy + 1; ++yy)
-        for (int xx = cx - 1; xx <= cx + 1; ++xx)
-          for (int j = hhead[exp_hash(xx, yy)]; j >= 0; j = hnext[j]) {
-            if (j >= s) continue;
-            const int sj = v.st[j];
-            if (sj != ST_CREATE && sj != ST_UNDECIDED) continue;
-            const float2 q = v.s_xy[j];
-            const float dx = __fsub_rn(q.x, p.x), dy = __fsub_rn(q.y, p.y);
-            const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-            if (sj == ST_CREATE) {
-              if (d2 < bd) { bd = d2; bn = -2 - j; tie = 0; }
-              else if (d2 == bd && bn != -2 - j) tie = 1;
-            } else if (__fsqrt_rn(v.cur_d2[j]) >= r) {  // (a stale, larger value only delays this sample)
-              mu = fminf(mu, d2);
+      const int nd = __ldg(v.dep_n + s);
+      if (nd <= kDepMax) {
+        for (int u = 0; u < nd; ++u) {
+          const int q = __ldg(v.dep_j + (size_t)s * kDepMax + u);
+          const int sq = sst[q];
+          if (sq != ST_CREATE && sq != ST_UNDECIDED) continue;
+          const float d2 = __ldg(v.dep_d2 + (size_t)s * kDepMax + u);
+          if (sq == ST_CREATE) {
+            if (d2 < bd) { bd = d2; bn = -2 - q; tie = 0; }
+            else if (d2 == bd && bn != -2 - q) tie = 1;
+          } else if (__fsqrt_rn(((volatile float*)v.cur_d2)[q]) >= r) {  // (a stale, larger value only delays this sample)
+            mu = fminf(mu, d2);
+          }
+        }
+      } else {
+        // list overflow (a crowd of samples in one spot): walk the hash itself
+        const float2 p = v.s_xy[s];
+        const int cx = (int)floorf((p.x - v.gx0) * hinv), cy = (int)floorf((p.y - v.gy0) * hinv);
+        for (int yy = cy - 1; yy <= cy + 1; ++yy)
+          for (int xx = cx - 1; xx <= cx + 1; ++xx) {
+            const unsigned h = dep_hash(xx, yy);
+            bool seen = false;  // hash collision inside the 3 x 3 block: walk each bucket once
+            for (int y2 = cy - 1; y2 <= yy; ++y2)
+              for (int x2 = cx - 1; x2 <= cx + 1; ++x2)
+                if ((y2 < yy || x2 < xx) && dep_hash(x2, y2) == h) seen = true;
+            if (seen) continue;
+            for (int q = v.dhead[h]; q >= 0; q = v.dnext[q]) {
+              if (q >= s) continue;
+              const int sq = sst[q];
+              if (sq != ST_CREATE && sq != ST_UNDECIDED) continue;
+              const float2 pq = v.s_xy[q];
+              const float dx = __fsub_rn(pq.x, p.x), dy = __fsub_rn(pq.y, p.y);
+              const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+              if (sq == ST_CREATE) {
+                if (d2 < bd) { bd = d2; bn = -2 - q; tie = 0; }
+                else if (d2 == bd && bn != -2 - q) tie = 1;
+              } else if (__fsqrt_rn(((volatile float*)v.cur_d2)[q]) >= r) {
+                mu = fminf(mu, d2);
+              }
             }
           }
+      }
       const bool wait = mu <= bd;
       v.cur_d2[s] = bd;
-      v.cur_nn[s] = bn;
+      v.cur_nn[s] = bn;  // nearest decided node: >= 0 existing, <= -2 sample of this step
       // the decision itself is written in the second half; the verdict travels in s_tie (its pre-step value was consumed above)
       v.s_tie[s] = (unsigned char)((wait ? 2 : 0) | (tie ? 1 : 0));
     }
-    cl.sync();
+    __syncthreads();
     // write half
     int undecided = 0;
-    for (int s = rank * T + tid; s < ns; s += NC * T) {
-      if (v.st[s] != ST_UNDECIDED) continue;
+    for (int s = tid; s < ns; s += T) {
+      if (sst[s] != ST_UNDECIDED) continue;
       const unsigned char f = v.s_tie[s];
       if (f & 2) { ++undecided; continue; }
       const int i = s / S;
       const int bn = v.cur_nn[s];
       const float bd = v.cur_d2[s];
-      if (f & 1) atomicMin(&c->ipop, i);
+      if (f & 1) atomicMin(&s_ipop, i);
       int nstate;  // state of the nearest node (NodeState: -1 invalid)
       if (bn >= 0) nstate = v.node_state[bn];
       else if (bn <= -2) nstate = (((v.s_pc[-2 - bn] >> 1) & 3) == 0) ? -1 : 0;
@@ -616,32 +731,22 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v) {
       else if (__fsqrt_rn(bd) < r) st = ST_WIRE;                    // trg.cpp:414
       else {
         st = ST_CREATE;                                             // trg.cpp:421
-        if (((v.s_pc[s] >> 1) & 3) >= 2) atomicMin(&c->ipop, i);    // slope gate too close to call
+        if (((v.s_pc[s] >> 1) & 3) >= 2) atomicMin(&s_ipop, i);     // slope gate too close to call
       }
-      v.st[s] = st;
+      sst[s] = (unsigned char)st;
     }
-    const int und_cta = __syncthreads_count(undecided > 0);
-    if (tid == 0) c->und[rounds & 1][rank] = und_cta;
     ++rounds;
-    cl.sync();
-    if (tid == 0) {
-      int tot = 0;
-      for (int k = 0; k < NC; ++k) tot += c->und[(rounds - 1) & 1][k];
-      s_und = tot;
-    }
-    __syncthreads();
-    if (s_und == 0) break;
+    if (!__syncthreads_or(undecided > 0)) break;
   }
-  if (rank != 0) return;
-  // ---- CTA 0 applies the decisions of the pops before the first one the host must handle -----------
-  const int n_commit = min(c->ipop, n_done);
+  // ---- apply the decisions of the pops before the first one the host must handle --------------------
+  const int n_commit = min(s_ipop, n_done);
   const int nsc = n_commit * S;
-  // per-thread contiguous runs; packed counters: created (bits 0-20), queued (21-41), requests (42-62)
-  const int per = (nsc + T - 1) / T;
-  const int b0 = min(nsc, tid * per), b1 = min(nsc, b0 + per);
+  const int per = (nsc + T - 1) / T;  // every thread applies a contiguous run
+  const int a0 = min(nsc, tid * per), a1 = min(nsc, a0 + per);
+  // packed counters: created (bits 0-20), queued (21-41), requests (42-62)
   unsigned long long mine = 0;
-  for (int s = b0; s < b1; ++s) {
-    const int st = v.st[s];
+  for (int s = a0; s < a1; ++s) {
+    const int st = sst[s];
     if (st == ST_CREATE) {
       const int valid = ((v.s_pc[s] >> 1) & 3) == 1;
       mine += 1ull + (valid ? (1ull << 21) + (1ull << 42) : 0ull);
@@ -653,11 +758,12 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v) {
   if (tid == 0) { s_sum = 0; s_sq = 0; }
   __syncthreads();
   {  // draws / pop statistics of the committed pops
-    unsigned long long a = 0, b = 0;
-    for (int i = tid; i < n_commit; i += T) { const unsigned long long cc = v.pop_cons[i]; a += cc; b += cc * cc; }
-    if (a) { atomicAdd(&s_sum, a); atomicAdd(&s_sq, b); }
+    unsigned a = 0, b = 0;  // (a pop consumes < 65536 draws; a thread owns few pops)
+    for (int i = tid; i < n_commit; i += T) { const unsigned cc = v.pop_cons[i]; a += cc; b += cc * cc; }
+    a = __reduce_add_sync(FULL, a);
+    b = __reduce_add_sync(FULL, b);
+    if ((tid & 31) == 0 && a) { atomicAdd(&s_sum, (unsigned long long)a); atomicAdd(&s_sq, (unsigned long long)b); }
   }
-  // exclusive scan of the 1024 partials by warp 0 (32 values per lane)
   if (tid < 32) {
     unsigned long long sum = 0;
     for (int k = 0; k < 32; ++k) { const unsigned long long x = s_part[tid * 32 + k]; s_part[tid * 32 + k] = sum; sum += x; }
@@ -683,14 +789,15 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v) {
       c->interrupt_pop = head;
       c->n_commit = 0;
     }
+    exp_plan_block(v, c_step_next);  // (plans an idle step: the interrupt flag is set)
     return;
   }
   const long long req0 = c->n_req;
   const int tail0 = c->tail;
   {
     unsigned long long run = s_part[tid];
-    for (int s = b0; s < b1; ++s) {
-      const int st = v.st[s];
+    for (int s = a0; s < a1; ++s) {
+      const int st = sst[s];
       const int i = s / S;
       const int parent = v.queue[head + i];
       const int nid = n_nodes0 + (int)(run & 0x1fffff);
@@ -702,7 +809,7 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v) {
         v.node_xy[nid] = p;
         v.node_z[nid] = v.s_z[s];
         v.node_state[nid] = (signed char)(valid ? v.new_state : -1);
-        v.cur_nn[s] = nid;  // id of the node this sample became (read by later samples' requests)
+        v.hnext[s] = nid;  // id of the node this sample became (read by later samples' requests)
         const int cell = exp_ncell(p.y, v.gy0, v.ginv, v.GH) * v.GW + exp_ncell(p.x, v.gx0, v.ginv, v.GW);
         v.gnext[nid] = atomicExch(v.ghead + cell, nid);
         if (v.s_ztie[s]) atomicAdd((unsigned long long*)&c->z_ties, 1ull);
@@ -725,15 +832,15 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v) {
   // requests that point at a node created in this step: sample index -> node id
   {
     unsigned long long run = s_part[tid];
-    for (int s = b0; s < b1; ++s) {
-      const int st = v.st[s];
+    for (int s = a0; s < a1; ++s) {
+      const int st = sst[s];
       const long long ri = req0 + (long long)((run >> 42) & 0x1fffff);
       if (st == ST_CREATE) {
         const int valid = ((v.s_pc[s] >> 1) & 3) == 1;
         run += 1ull + (valid ? (1ull << 21) + (1ull << 42) : 0ull);
       } else if (st == ST_WIRE) {
         const int b = v.req_b[ri];
-        if (b <= -2) v.req_b[ri] = v.cur_nn[-2 - b];
+        if (b <= -2) v.req_b[ri] = v.hnext[-2 - b];
         run += 1ull << 42;
       }
     }
@@ -744,35 +851,40 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v) {
     const int n_new = (int)(tot & 0x1fffff), n_q = (int)((tot >> 21) & 0x1fffff);
     const long long n_rq = (long long)((tot >> 42) & 0x1fffff);
     __threadfence();
-    c->n_nodes = n_nodes0 + n_new;
-    c->tail = tail0 + n_q;
-    c->n_req = req0 + n_rq;
-    c->head = head + n_commit;
-    c->n_commit = n_commit;
+    ExpCtl k = *c;  // one read, one write-back: every field access below would otherwise be an L2 round trip
+    k.n_nodes = n_nodes0 + n_new;
+    k.tail = tail0 + n_q;
+    k.n_req = req0 + n_rq;
+    k.head = head + n_commit;
+    k.n_commit = n_commit;
     // stream position after the last committed pop
-    long long pos = c->pos0;
-    if (n_commit > 0) pos = c->pos0 + v.pop_off[n_commit - 1] + v.pop_cons[n_commit - 1];
-    c->pos = pos;
-    c->pops += n_commit;
-    c->created += n_new;
-    c->samples += nsc;
-    c->rounds += rounds;
-    c->redo_pops += c->m - n_commit;
-    c->stuck = 0;
+    long long pos = k.pos0;
+    if (n_commit > 0) pos = k.pos0 + v.pop_off[n_commit - 1] + v.pop_cons[n_commit - 1];
+    k.pos = pos;
+    k.pops += n_commit;
+    k.created += n_new;
+    k.samples += nsc;
+    k.rounds += rounds;
+    k.redo_pops += k.m - n_commit;
+    k.stuck = 0;
     if (n_commit < n_done) {
-      c->interrupt = EXP_INT_TIE;  // tie or slope: the host handles pop `head` with the reference's rules
-      c->interrupt_pop = c->head;
+      k.interrupt = EXP_INT_TIE;  // tie or slope: the host handles pop `head` with the reference's rules
+      k.interrupt_pop = k.head;
     }
     // running draws / pop statistics (step estimate blended in)
     if (n_commit >= 8) {
       const double mu = (double)s_sum / n_commit;
       const double var = fmax(0.0, (double)s_sq / n_commit - mu * mu);
       const float w = n_commit >= 256 ? 0.5f : 0.2f;
-      c->mean += w * ((float)mu - c->mean);
-      c->var += w * ((float)var - c->var);
-      if (c->var < 0.05f) c->var = 0.05f;
+      k.mean += w * ((float)mu - k.mean);
+      k.var += w * ((float)var - k.var);
+      if (k.var < 0.05f) k.var = 0.05f;
     }
+    k.z_ties = c->z_ties;  // (bumped by atomics above)
+    *c = k;
   }
+  // ---- plan the next step --------------------------------------------------------------------------
+  exp_plan_block(v, c_step_next);
 }
 
 // a pop handled by the host (interrupt): append its nodes, queue entries and requests
@@ -908,6 +1020,15 @@ struct trgb_expander {
   int cap = 0;               // z-column capacity of the window kernel
   size_t win_smem = 0;
   int win_grid = 0;
+  size_t top_smem = 0;       // dynamic shared memory of k_exp_top
+  cudaStream_t st2 = nullptr;  // side stream of the dependency kernel
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  struct StepGraph { int c_step; cudaGraphExec_t exec; };
+  std::vector<StepGraph> graphs;
+  const float2* graph_draws = nullptr;
+  const trgb_map* graph_map = nullptr;
+  int graph_kernels = 0;
+  bool use_graphs = true;
   // owned device memory
   std::vector<void*> owned;
   float2* d_draws = nullptr;
@@ -919,6 +1040,8 @@ struct trgb_expander {
   int n_dir = 0;
   int n_nodes_final = 0;
 };
+
+static void drop_graphs(trgb_expander* e);
 
 namespace {
 template <class T>
@@ -936,6 +1059,10 @@ int dalloc(trgb_expander* e, T** p, size_t n) {
 extern "C" void trgb_expander_destroy(trgb_expander* e) {
   if (!e) return;
   cudaDeviceSynchronize();
+  drop_graphs(e);
+  if (e->st2) cudaStreamDestroy(e->st2);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
   for (void* p : e->owned) cudaFree(p);
   if (e->d_draws) cudaFree(e->d_draws);
   for (int k = 0; k < 2; ++k) {
@@ -956,6 +1083,7 @@ extern "C" int trgb_expander_create(trgb_expander** out, const trgb_map* map, co
   TRGB_ARG(prm->sample_num >= 1 && prm->sample_num <= kExpMaxS, "sample_num out of range for the device expander");
   TRGB_ARG(prm->max_pops >= 32 && prm->max_pops <= kExpMaxPops, "max_pops out of range");
   TRGB_ARG(prm->window_words >= 2 && prm->window_words <= 4, "window_words must be 2..4");
+  TRGB_ARG((int64_t)prm->max_pops * prm->sample_num <= 200 * 1024, "max_pops x sample_num too large for the commit kernel");
   TRGB_ARG(node_capacity >= 1024 && node_capacity < (1ll << 21) * 512, "node_capacity out of range");
   TRGB_ARG(x1 > x0 && y1 > y0, "bad extent");
   // the window kernel is the thread-per-query routine: the map must be sparse enough for its column
@@ -997,7 +1125,8 @@ extern "C" int trgb_expander_create(trgb_expander** out, const trgb_map* map, co
   EXP_ALLOC(v.pop_off, C); EXP_ALLOC(v.pop_cons, C); EXP_ALLOC(v.pop_acc, C);
   EXP_ALLOC(v.s_xy, CS); EXP_ALLOC(v.s_p1, 3 * CS); EXP_ALLOC(v.s_nn, CS); EXP_ALLOC(v.s_d2, CS); EXP_ALLOC(v.s_tie, CS);
   EXP_ALLOC(v.s_z, CS); EXP_ALLOC(v.s_ztie, CS); EXP_ALLOC(v.s_stage, CS); EXP_ALLOC(v.s_w, CS); EXP_ALLOC(v.s_d, CS);
-  EXP_ALLOC(v.st, CS); EXP_ALLOC(v.cur_d2, CS); EXP_ALLOC(v.cur_nn, CS); EXP_ALLOC(v.hnext, CS * kCommitCtas); EXP_ALLOC(v.s_pc, CS);
+  EXP_ALLOC(v.st, CS); EXP_ALLOC(v.cur_d2, CS); EXP_ALLOC(v.cur_nn, CS); EXP_ALLOC(v.hnext, CS);
+  EXP_ALLOC(v.dhead, kDepHash); EXP_ALLOC(v.dnext, CS); EXP_ALLOC(v.dep_j, CS * kDepMax); EXP_ALLOC(v.dep_d2, CS * kDepMax); EXP_ALLOC(v.dep_n, CS); EXP_ALLOC(v.s_pc, CS);
   for (int k2 = 0; k2 < 2; ++k2) {
     TRGB_CUDA(cudaMallocHost((void**)&e->h_status[k2], sizeof(ExpCtl)));
     TRGB_CUDA(cudaEventCreateWithFlags(&e->ev[k2], cudaEventDisableTiming));
@@ -1005,8 +1134,16 @@ extern "C" int trgb_expander_create(trgb_expander** out, const trgb_map* map, co
   {
     const size_t top_smem = ((size_t)prm->max_pops + 31) / 32 * (64 * (size_t)prm->window_words - 32) * 5;
     if (top_smem > 200 * 1024) { trgb_expander_destroy(e); set_error("expander: max_pops x window too large for the chain kernel"); return TRGB_E_ARG; }
-    TRGB_CUDA(cudaFuncSetAttribute((const void*)k_exp_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(top_smem, 1024)));
+    e->top_smem = std::max<size_t>(top_smem, 1024);
+    TRGB_CUDA(cudaFuncSetAttribute((const void*)k_exp_tables, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)std::max<size_t>(e->top_smem, (size_t)32 * kRow + 8 * 256)));
+    TRGB_CUDA(cudaFuncSetAttribute((const void*)k_exp_commit, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)std::max<size_t>((size_t)prm->max_pops * prm->sample_num, 1024)));
   }
+  TRGB_CUDA(cudaStreamCreateWithFlags(&e->st2, cudaStreamNonBlocking));
+  TRGB_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+  TRGB_CUDA(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+  if (const char* g = std::getenv("TRGB_EXPAND_GRAPHS")) e->use_graphs = std::atoi(g) != 0;
   e->cap = kTqCap;
   e->win_smem = (size_t)kTqThreads * kTqCap * sizeof(float);
   TRGB_CUDA(cudaFuncSetAttribute((const void*)k_exp_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->win_smem));
@@ -1030,7 +1167,8 @@ extern "C" int trgb_expander_rebind(trgb_expander* e, const trgb_map* map, float
     set_error("expander: map extent changed");
     return TRGB_E_STATE;
   }
-  cudaStreamSynchronize(e->st);
+  // (e->st belonged to the old map and may be gone: builds are synchronous, nothing of ours is in flight)
+  drop_graphs(e);  // the captured launches hold the old map's view and stream
   e->map = map;
   e->st = map->stream;
   return TRGB_OK;
@@ -1093,61 +1231,102 @@ extern "C" int trgb_expander_push_draws(trgb_expander* e, const float* xy, int64
   return TRGB_OK;
 }
 
+// the kernels of one step, in stream order on e->st (the dependency lists are built on a side stream,
+// beside the K3 / K4 launches they do not depend on)
+static int launch_step(trgb_expander* e, int c_step) {
+  ExpView& v = e->v;
+  cudaStream_t st = e->st;
+  const trgb_map* m = e->map;
+  const int S = v.S;
+  const int64_t ns = (int64_t)c_step * S;
+  const int nblk = c_step / 32;
+  const int kmax = std::max(2, std::min(16, (int)std::ceil((v.e * 1.001f) / (0.5f * v.r))));
+  TrgbEdgeParams ep{v.r, v.hthr, v.cthr, kmax};
+  {
+    ProfScope ps("k_exp_window", st, (double)c_step * 64.0 * v.norm_words);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)c_step * 64 * v.norm_words + kTqThreads - 1) / kTqThreads, e->win_grid));
+    k_exp_window<<<grid, kTqThreads, e->win_smem, st>>>(m->view, v, e->cap);
+  }
+  {
+    ProfScope ps("k_exp_tables", st, (double)c_step);
+    const size_t smem = std::max<size_t>((size_t)32 * kRow + 8 * 256, (size_t)nblk * (64 * v.norm_words - 32) * 5);
+    k_exp_tables<<<nblk, 256, smem, st>>>(v);
+  }
+  {
+    ProfScope ps("k_exp_emit", st, (double)ns);
+    k_exp_emit<<<nblk, 256, 0, st>>>(v);
+  }
+  TRGB_CUDA(cudaEventRecord(e->ev_fork, st));
+  TRGB_CUDA(cudaStreamWaitEvent(e->st2, e->ev_fork, 0));
+  {
+    ProfScope ps("k_exp_deps", e->st2, (double)ns);
+    k_exp_deps<<<(int)((ns + 255) / 256), 256, 0, e->st2>>>(v);
+  }
+  TRGB_CUDA(cudaEventRecord(e->ev_join, e->st2));
+  int rc = trgb_nearest_z_launch_skip(m, reinterpret_cast<const float*>(v.s_xy), ns, v.s_z, nullptr, v.s_ztie, v.s_d2, v.r);
+  if (rc) return rc;
+  rc = trgb_edge_eval_launch_skip(m, v.s_p1, reinterpret_cast<const float*>(v.s_xy), ns, &ep, v.s_stage, v.s_w, v.s_d, nullptr,
+                                  v.s_d2, ns, v.r);
+  if (rc) return rc;
+  TRGB_CUDA(cudaStreamWaitEvent(st, e->ev_join, 0));
+  {
+    ProfScope ps("k_exp_commit", st, (double)ns);
+    k_exp_commit<<<1, 1024, (size_t)c_step * S, st>>>(v, c_step);
+  }
+  TRGB_CUDA(cudaGetLastError());
+  return TRGB_OK;
+}
+
+static void drop_graphs(trgb_expander* e) {
+  for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
+  e->graphs.clear();
+}
+
 extern "C" int trgb_expander_enqueue(trgb_expander* e, int n_steps, int pops_hint) {
   TRGB_ARG(e && n_steps >= 0, "bad argument");
   ExpView& v = e->v;
   cudaStream_t st = e->st;
-  const trgb_map* m = e->map;
-  int c_step = std::max(32, std::min(pops_hint, v.C));
-  c_step = (c_step + 31) & ~31;
-  const int S = v.S;
-  const int64_t ns = (int64_t)c_step * S;
-  const int kmax = std::max(2, std::min(16, (int)std::ceil((v.e * 1.001f) / (0.5f * v.r))));
-  TrgbEdgeParams ep{v.r, v.hthr, v.cthr, kmax};
-  for (int k = 0; k < n_steps; ++k) {
-    {
-      ProfScope ps("k_exp_plan", st, 1.0);
-      k_exp_plan<<<1, 256, 0, st>>>(v, c_step);
-    }
-    {
-      ProfScope ps("k_exp_window", st, (double)c_step * 64.0 * v.norm_words);
-      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)c_step * 64 * v.norm_words + kTqThreads - 1) / kTqThreads, e->win_grid));
-      k_exp_window<<<grid, kTqThreads, e->win_smem, st>>>(m->view, v, e->cap);
-    }
-    {
-      ProfScope ps("k_exp_chain", st, (double)c_step);
-      const int nblk = (c_step + 31) / 32;
-      k_exp_tables<<<(nblk + 3) / 4, 128, 0, st>>>(v);
-      k_exp_top<<<1, 1024, (size_t)nblk * (64 * v.norm_words - 32) * 5, st>>>(v);
-      k_exp_emit<<<(nblk + 3) / 4, 128, 0, st>>>(v);
-    }
-    {
-      ProfScope ps("k_exp_nearest", st, (double)ns);
-      k_exp_nearest<<<(int)((ns + 255) / 256), 256, 0, st>>>(v, c_step);
-    }
-    int rc = trgb_nearest_z_launch_skip(m, reinterpret_cast<const float*>(v.s_xy), ns, v.s_z, nullptr, v.s_ztie, v.s_d2, v.r);
-    if (rc) return rc;
-    rc = trgb_edge_eval_launch_skip(m, v.s_p1, reinterpret_cast<const float*>(v.s_xy), ns, &ep, v.s_stage, v.s_w, v.s_d, nullptr,
-                                    v.s_d2, ns, v.r);
-    if (rc) return rc;
-    {
-      ProfScope ps("k_exp_commit", st, (double)ns);
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(kCommitCtas);
-      cfg.blockDim = dim3(1024);
-      cfg.dynamicSmemBytes = 0;
-      cfg.stream = st;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = kCommitCtas;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      TRGB_CUDA(cudaLaunchKernelEx(&cfg, k_exp_commit, v));
-    }
+  // launch sizes come in powers of two, so that a handful of captured graphs cover a build
+  int c_step = 64;
+  while (c_step < pops_hint && c_step < v.C) c_step <<= 1;
+  c_step = std::min(c_step, v.C) & ~31;
+  if (n_steps > 0) {
+    ProfScope ps("k_exp_plan", st, 1.0);
+    k_exp_plan<<<1, 256, 0, st>>>(v, c_step);
   }
-  TRGB_CUDA(cudaGetLastError());
+  if (prof_enabled() || !e->use_graphs) {
+    for (int k = 0; k < n_steps; ++k) {
+      const int rc = launch_step(e, c_step);
+      if (rc) return rc;
+    }
+    return TRGB_OK;
+  }
+  // one captured CUDA graph per launch size; replayed once per step
+  if (e->graph_draws != v.draws || e->graph_map != e->map) {
+    drop_graphs(e);
+    e->graph_draws = v.draws;
+    e->graph_map = e->map;
+  }
+  cudaGraphExec_t exec = nullptr;
+  for (auto& g : e->graphs)
+    if (g.c_step == c_step) exec = g.exec;
+  if (!exec) {
+    cudaGraph_t graph = nullptr;
+    const int64_t l0 = trgb_launch_count();
+    TRGB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = launch_step(e, c_step);
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture", __FILE__, __LINE__);
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaGraphInstantiate", __FILE__, __LINE__);
+    e->graph_kernels = (int)(trgb_launch_count() - l0);
+    count_launches(-e->graph_kernels);  // capturing launched nothing
+    e->graphs.push_back({c_step, exec});
+  }
+  for (int k = 0; k < n_steps; ++k) TRGB_CUDA(cudaGraphLaunch(exec, st));
+  count_launches((int64_t)n_steps * e->graph_kernels);
   return TRGB_OK;
 }
 
@@ -1310,17 +1489,13 @@ extern "C" int trgb_expander_finalize(trgb_expander* e, int64_t* n_nodes, int64_
   int n_ok = 0;
   TRGB_CUDA(cudaMemcpyAsync(&n_ok, cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
   TRGB_CUDA(cudaStreamSynchronize(st));
-  size_t tmp_bytes = 0, tb2 = 0;
-  void* tmp = nullptr;
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, val, val2, key, key2, n_ok, 0, 32, st);
-  cub::DeviceRadixSort::SortPairs(nullptr, tb2, key2, key, val2, val, std::max(n_ok, 2 * n_ok), 0, 64, st);
-  tmp_bytes = std::max(tmp_bytes, tb2);
-  TRGB_CUDA(cudaMallocAsync(&tmp, std::max<size_t>(tmp_bytes, 16), st));
   {
     ProfScope ps("k_fin_sort", st, (double)n_ok);
     // pass 1: by request index (keys = val); pass 2: stable by pair
-    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, val, val2, key, key2, n_ok, 0, 32, st);
-    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key2, key, val2, val, n_ok, 0, 64, st);
+    int rc2 = sort_pairs_u32_u64(val, val2, key, key2, n_ok, 32, st);
+    if (rc2) return rc2;
+    rc2 = sort_pairs_u64_u32(key2, key, val2, val, n_ok, 64, st);
+    if (rc2) return rc2;
   }
   // first of each pair -> two directed entries keyed (source node, request index)
   unsigned long long *dkey = nullptr, *dkey2 = nullptr; unsigned int *dval = nullptr, *dval2 = nullptr;
@@ -1334,15 +1509,9 @@ extern "C" int trgb_expander_finalize(trgb_expander* e, int64_t* n_nodes, int64_
   TRGB_CUDA(cudaMemcpyAsync(&n_dir, cnt + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
   TRGB_CUDA(cudaStreamSynchronize(st));
   if (n_dir > 0) {
-    size_t tb3 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tb3, dkey, dkey2, dval, dval2, n_dir, 0, 64, st);
-    if (tb3 > tmp_bytes) {
-      cudaFreeAsync(tmp, st);
-      tmp_bytes = tb3;
-      TRGB_CUDA(cudaMallocAsync(&tmp, tmp_bytes, st));
-    }
     ProfScope ps("k_fin_sort", st, (double)n_dir);
-    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dkey, dkey2, dval, dval2, n_dir, 0, 64, st);
+    const int rc3 = sort_pairs_u64_u32(dkey, dkey2, dval, dval2, n_dir, 64, st);
+    if (rc3) return rc3;
   }
   TRGB_CUDA(cudaMallocAsync((void**)&e->d_col, std::max<size_t>(n_dir, 1) * sizeof(int), st));
   TRGB_CUDA(cudaMallocAsync((void**)&e->d_w, std::max<size_t>(n_dir, 1) * sizeof(float), st));
@@ -1350,7 +1519,7 @@ extern "C" int trgb_expander_finalize(trgb_expander* e, int64_t* n_nodes, int64_
   k_fin_csr<<<grid, 256, 0, st>>>(v, n_dir, nn, dkey2, dval2, e->d_row, e->d_col, e->d_w, e->d_d);
   TRGB_CUDA(cudaGetLastError());
   for (void* p : {(void*)p1, (void*)p2, (void*)skip, (void*)stage, (void*)w, (void*)d, (void*)ok, (void*)cnt, (void*)unc, (void*)key,
-                  (void*)key2, (void*)val, (void*)val2, (void*)dkey, (void*)dkey2, (void*)dval, (void*)dval2, tmp})
+                  (void*)key2, (void*)val, (void*)val2, (void*)dkey, (void*)dkey2, (void*)dval, (void*)dval2})
     cudaFreeAsync(p, st);
   TRGB_CUDA(cudaStreamSynchronize(st));
   e->n_dir = n_dir;

@@ -12,7 +12,6 @@
 #include <cfloat>
 #include <climits>
 #include <cmath>
-#include <cub/cub.cuh>
 
 #include "common.cuh"
 
@@ -139,8 +138,6 @@ extern "C" int trgb_voxel_filter_dev(const float* d_pts, int64_t n, int stride_f
     return TRGB_E_STATE;
   }
   uint32_t *key = nullptr, *val = nullptr, *key2 = nullptr, *val2 = nullptr, *head = nullptr, *slot = nullptr;
-  void* tmp = nullptr;
-  size_t tmp_bytes = 0, tmp2 = 0;
   TRGB_CUDA(cudaMallocAsync((void**)&key, n * sizeof(uint32_t), st));
   TRGB_CUDA(cudaMallocAsync((void**)&val, n * sizeof(uint32_t), st));
   TRGB_CUDA(cudaMallocAsync((void**)&key2, n * sizeof(uint32_t), st));
@@ -152,13 +149,9 @@ extern "C" int trgb_voxel_filter_dev(const float* d_pts, int64_t n, int stride_f
     k_vox_index<<<grid, 256, 0, st>>>(d_pts, n, stride_floats, inv, mb[0], mb[1], mb[2], (int)div[0], (int)(div[0] * div[1]),
                                       key, val);
   }
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key, key2, val, val2, (int)n, 0, 32, st);
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp2, head, slot, (int)n, st);
-  tmp_bytes = std::max(tmp_bytes, tmp2);
-  TRGB_CUDA(cudaMallocAsync(&tmp, tmp_bytes, st));
-  cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key, key2, val, val2, (int)n, 0, 32, st);
+  { int rc = sort_pairs_u32_u32(key, key2, val, val2, (int)n, 32, st); if (rc) return rc; }
   k_vox_heads<<<grid, 256, 0, st>>>(key2, n, head);
-  cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, head, slot, (int)n, st);
+  { int rc = exclusive_sum_u32(head, slot, (int)n, st); if (rc) return rc; }
   uint32_t last_slot = 0, last_head = 0;
   TRGB_CUDA(cudaMemcpyAsync(&last_slot, slot + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   TRGB_CUDA(cudaMemcpyAsync(&last_head, head + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -172,7 +165,7 @@ extern "C" int trgb_voxel_filter_dev(const float* d_pts, int64_t n, int stride_f
   }
   TRGB_CUDA(cudaGetLastError());
   cudaFreeAsync(key, st); cudaFreeAsync(val, st); cudaFreeAsync(key2, st); cudaFreeAsync(val2, st);
-  cudaFreeAsync(head, st); cudaFreeAsync(slot, st); cudaFreeAsync(tmp, st);
+  cudaFreeAsync(head, st); cudaFreeAsync(slot, st);
   TRGB_CUDA(cudaStreamSynchronize(st));
   *d_out = out;
   *n_out = nv;

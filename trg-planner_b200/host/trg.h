@@ -276,8 +276,8 @@ class TRG {
     bool split_commit = false;  // apply edge-list operations on a second thread while the first decides (measured slower on a 10 M-point map: cross-core traffic on the adjacency lists; kept for experiments)
     bool device_expand = true;  // initGraph: run the whole BFS, decisions included, on the device (K9) when applicable
     int  expand_steps = 8;      // device BFS: steps queued per status poll (two polls in flight)
-    int  expand_window_words = 2;  // device BFS: sampling window per pop = 64 * words draws
-    int  expand_max_pops = 8192;   // device BFS: pops per step at most
+    int  expand_window_words = 4;  // device BFS: sampling window per pop = 64 * words draws (longer exact chains per step)
+    int  expand_max_pops = 4096;   // device BFS: pops per step at most
   } tuning_;
 };
 
