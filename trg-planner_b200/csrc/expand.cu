@@ -73,6 +73,7 @@ struct ExpCtl {
   int ipop;                // first pop of the step the host must handle (tie / slope), INT_MAX = none
   int blocks_done;         // CTAs of k_exp_tables that have finished (the last one walks the chain)
   int und[2][16];          // undecided samples per commit CTA, double-buffered by round parity
+  unsigned long long cta_tot[16];  // packed (created, queued, requests) totals per commit CTA
   long long pos0, pos_done;
   // statistics
   long long window_tests, steps, steps_active, rounds, pops, z_ties, redo_pops, samples, created, pc_samples;
@@ -598,42 +599,51 @@ __device__ __forceinline__ int slope_gate(float x1, float y1, float z1, float x2
   return 2;
 }
 
-// Reservation rounds + application of the decisions in (pop, sample) order + plan of the next step.
-// A round costs an undecided sample a walk over its short dependency list (phase 5 of the chain kernel);
-// everything is in global memory that only this CTA touches.
+constexpr int kCommitCtas = 8;  // thread-block cluster of the commit kernel
+
+// Reservation rounds + application of the decisions in (pop, sample) order + plan of the next step, on a
+// cluster of kCommitCtas CTAs: samples are dealt round-robin to the cluster's threads; a round costs an
+// undecided sample a walk over its short dependency list (k_exp_deps) and the cluster two barriers.
 __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v, int c_step_next) {
+  cg::cluster_group cl = cg::this_cluster();
+  const int NC = (int)cl.num_blocks(), rank = (int)cl.block_rank();
   ExpCtl* c = v.ctl;
   const int tid = threadIdx.x, T = blockDim.x;
+  const int gtid = rank * T + tid, GT = NC * T;
   const int n_done = c->n_done;
-  if (tid == 0) c->steps++;
+  const int m_step = c->m;
   if (n_done == 0) {
-    if (tid == 0 && c->m > 0) {
-      c->stuck++;  // not even the first pop fitted its window: slow mode next
-      c->redo_pops += c->m;
+    if (rank == 0) {
+      if (tid == 0) {
+        c->steps++;
+        if (m_step > 0) {
+          c->stuck++;  // not even the first pop fitted its window: slow mode next
+          c->redo_pops += m_step;
+        }
+      }
+      exp_plan_block(v, c_step_next);
     }
-    exp_plan_block(v, c_step_next);
     return;
   }
-  extern __shared__ unsigned char sst[];  // decision state of every sample of the step
-  __shared__ int s_any, s_ipop;
+  __shared__ int s_any, s_und;
   __shared__ unsigned long long s_part[1024];
-  __shared__ unsigned long long s_sum, s_sq, s_tot;
+  __shared__ unsigned long long s_base;
   const int S = v.S;
   const float r = v.r;
   const float hinv = 1.0f / (v.e * 1.001f + 1e-5f);
   const int head = c->head;
   const int n_nodes0 = c->n_nodes;
+  const long long req0 = c->n_req;
+  const int tail0 = c->tail;
   const int ns = n_done * S;
-  if (tid == 0) s_ipop = 0x7fffffff;
-  __syncthreads();
   // ---- initial state ------------------------------------------------------------------------------
-  for (int s = tid; s < ns; s += T) {
+  for (int s = gtid; s < ns; s += GT) {
     const int i = s / S, j = s - i * S;
     int st = ST_UNDECIDED;
     unsigned char pc = 0;
     if (j >= v.pop_acc[i]) st = ST_VOID;
     else {
-      if (v.s_tie[s]) atomicMin(&s_ipop, i);   // tie among existing nodes: the host resolves this pop
+      if (v.s_tie[s]) atomicMin(&c->ipop, i);  // tie among existing nodes: the host resolves this pop
       if (v.s_pc[s]) {                         // trg.cpp:414 with the pre-step nearest node: may become a node
         // validity of the would-be node = its parent edge (trg.cpp:425, 447): K4 stage + slope gate
         int valid = 0;
@@ -647,18 +657,18 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v, int c_step_ne
         pc = (unsigned char)(1 | (valid << 1));  // bit 0 potential creator, bits 1-2: 0 invalid 1 valid 2/3 host decides
       }
     }
-    sst[s] = (unsigned char)st;
+    v.st[s] = st;
     v.s_pc[s] = pc;
     v.cur_d2[s] = v.s_d2[s];
   }
-  __syncthreads();
+  cl.sync();
   // ---- reservation rounds ----------------------------------------------------------------------------
   int rounds = 0;
   while (true) {
     // read half: nearest decided node so far; wait if an earlier undecided sample that may still become a
     // node lies at least as close
-    for (int s = tid; s < ns; s += T) {
-      if (sst[s] != ST_UNDECIDED) continue;
+    for (int s = gtid; s < ns; s += GT) {
+      if (v.st[s] != ST_UNDECIDED) continue;
       float bd = __ldg(v.s_d2 + s);
       int bn = __ldg(v.s_nn + s);
       int tie = 0;
@@ -667,7 +677,7 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v, int c_step_ne
       if (nd <= kDepMax) {
         for (int u = 0; u < nd; ++u) {
           const int q = __ldg(v.dep_j + (size_t)s * kDepMax + u);
-          const int sq = sst[q];
+          const int sq = v.st[q];
           if (sq != ST_CREATE && sq != ST_UNDECIDED) continue;
           const float d2 = __ldg(v.dep_d2 + (size_t)s * kDepMax + u);
           if (sq == ST_CREATE) {
@@ -691,7 +701,7 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v, int c_step_ne
             if (seen) continue;
             for (int q = v.dhead[h]; q >= 0; q = v.dnext[q]) {
               if (q >= s) continue;
-              const int sq = sst[q];
+              const int sq = v.st[q];
               if (sq != ST_CREATE && sq != ST_UNDECIDED) continue;
               const float2 pq = v.s_xy[q];
               const float dx = __fsub_rn(pq.x, p.x), dy = __fsub_rn(pq.y, p.y);
@@ -711,17 +721,17 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v, int c_step_ne
       // the decision itself is written in the second half; the verdict travels in s_tie (its pre-step value was consumed above)
       v.s_tie[s] = (unsigned char)((wait ? 2 : 0) | (tie ? 1 : 0));
     }
-    __syncthreads();
+    cl.sync();
     // write half
     int undecided = 0;
-    for (int s = tid; s < ns; s += T) {
-      if (sst[s] != ST_UNDECIDED) continue;
+    for (int s = gtid; s < ns; s += GT) {
+      if (v.st[s] != ST_UNDECIDED) continue;
       const unsigned char f = v.s_tie[s];
       if (f & 2) { ++undecided; continue; }
       const int i = s / S;
       const int bn = v.cur_nn[s];
       const float bd = v.cur_d2[s];
-      if (f & 1) atomicMin(&s_ipop, i);
+      if (f & 1) atomicMin(&c->ipop, i);
       int nstate;  // state of the nearest node (NodeState: -1 invalid)
       if (bn >= 0) nstate = v.node_state[bn];
       else if (bn <= -2) nstate = (((v.s_pc[-2 - bn] >> 1) & 3) == 0) ? -1 : 0;
@@ -731,22 +741,31 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v, int c_step_ne
       else if (__fsqrt_rn(bd) < r) st = ST_WIRE;                    // trg.cpp:414
       else {
         st = ST_CREATE;                                             // trg.cpp:421
-        if (((v.s_pc[s] >> 1) & 3) >= 2) atomicMin(&s_ipop, i);     // slope gate too close to call
+        if (((v.s_pc[s] >> 1) & 3) >= 2) atomicMin(&c->ipop, i);    // slope gate too close to call
       }
-      sst[s] = (unsigned char)st;
+      v.st[s] = st;
     }
+    const int und_cta = __syncthreads_count(undecided > 0);
+    if (tid == 0) c->und[rounds & 1][rank] = und_cta;
     ++rounds;
-    if (!__syncthreads_or(undecided > 0)) break;
+    cl.sync();
+    if (tid == 0) {
+      int tot = 0;
+      for (int k = 0; k < NC; ++k) tot += ((volatile int*)c->und[(rounds - 1) & 1])[k];
+      s_und = tot;
+    }
+    __syncthreads();
+    if (s_und == 0) break;
   }
   // ---- apply the decisions of the pops before the first one the host must handle --------------------
-  const int n_commit = min(s_ipop, n_done);
+  const int n_commit = min(((volatile int*)&c->ipop)[0], n_done);
   const int nsc = n_commit * S;
-  const int per = (nsc + T - 1) / T;  // every thread applies a contiguous run
-  const int a0 = min(nsc, tid * per), a1 = min(nsc, a0 + per);
+  const int per = (nsc + GT - 1) / GT;  // every thread of the cluster applies a contiguous run
+  const int a0 = min(nsc, gtid * per), a1 = min(nsc, a0 + per);
   // packed counters: created (bits 0-20), queued (21-41), requests (42-62)
   unsigned long long mine = 0;
   for (int s = a0; s < a1; ++s) {
-    const int st = sst[s];
+    const int st = v.st[s];
     if (st == ST_CREATE) {
       const int valid = ((v.s_pc[s] >> 1) & 3) == 1;
       mine += 1ull + (valid ? (1ull << 21) + (1ull << 42) : 0ull);
@@ -755,16 +774,8 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v, int c_step_ne
     }
   }
   s_part[tid] = mine;
-  if (tid == 0) { s_sum = 0; s_sq = 0; }
   __syncthreads();
-  {  // draws / pop statistics of the committed pops
-    unsigned a = 0, b = 0;  // (a pop consumes < 65536 draws; a thread owns few pops)
-    for (int i = tid; i < n_commit; i += T) { const unsigned cc = v.pop_cons[i]; a += cc; b += cc * cc; }
-    a = __reduce_add_sync(FULL, a);
-    b = __reduce_add_sync(FULL, b);
-    if ((tid & 31) == 0 && a) { atomicAdd(&s_sum, (unsigned long long)a); atomicAdd(&s_sq, (unsigned long long)b); }
-  }
-  if (tid < 32) {
+  if (tid < 32) {  // exclusive scan of this CTA's 1024 partials (32 values per lane)
     unsigned long long sum = 0;
     for (int k = 0; k < 32; ++k) { const unsigned long long x = s_part[tid * 32 + k]; s_part[tid * 32 + k] = sum; sum += x; }
     unsigned long long inc = sum;
@@ -774,30 +785,40 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v, int c_step_ne
     }
     const unsigned long long exc = inc - sum;
     for (int k = 0; k < 32; ++k) s_part[tid * 32 + k] += exc;
-    if (tid == 31) {
-      s_tot = inc;
-      const int n_new = (int)(inc & 0x1fffff), n_q = (int)((inc >> 21) & 0x1fffff);
-      const long long n_rq = (long long)((inc >> 42) & 0x1fffff);
-      // capacity: never write past the arrays (the packing bound of the caller makes this unreachable)
-      s_any = (n_nodes0 + n_new > v.node_cap || c->n_req + n_rq > v.req_cap || c->tail + n_q > v.node_cap) ? 1 : 0;
+    if (tid == 31) c->cta_tot[rank] = inc;
+  }
+  cl.sync();
+  if (tid == 0) {
+    unsigned long long base = 0, tot = 0;
+    for (int k = 0; k < NC; ++k) {
+      const unsigned long long x = ((volatile unsigned long long*)c->cta_tot)[k];
+      if (k < rank) base += x;
+      tot += x;
     }
+    s_base = base;
+    const int n_new = (int)(tot & 0x1fffff), n_q = (int)((tot >> 21) & 0x1fffff);
+    const long long n_rq = (long long)((tot >> 42) & 0x1fffff);
+    // capacity: never write past the arrays (the packing bound of the caller makes this unreachable)
+    s_any = (n_nodes0 + n_new > v.node_cap || req0 + n_rq > v.req_cap || tail0 + n_q > v.node_cap) ? 1 : 0;
   }
   __syncthreads();
-  if (s_any) {
-    if (tid == 0) {
-      c->interrupt = EXP_INT_CAPACITY;
-      c->interrupt_pop = head;
-      c->n_commit = 0;
+  if (s_any) {  // (the same verdict in every CTA)
+    if (rank == 0) {
+      if (tid == 0) {
+        c->steps++;
+        c->interrupt = EXP_INT_CAPACITY;
+        c->interrupt_pop = head;
+        c->n_commit = 0;
+      }
+      exp_plan_block(v, c_step_next);  // (plans an idle step: the interrupt flag is set)
     }
-    exp_plan_block(v, c_step_next);  // (plans an idle step: the interrupt flag is set)
     return;
   }
-  const long long req0 = c->n_req;
-  const int tail0 = c->tail;
+  const unsigned long long run0 = s_base + s_part[tid];
   {
-    unsigned long long run = s_part[tid];
+    unsigned long long run = run0;
     for (int s = a0; s < a1; ++s) {
-      const int st = sst[s];
+      const int st = v.st[s];
       const int i = s / S;
       const int parent = v.queue[head + i];
       const int nid = n_nodes0 + (int)(run & 0x1fffff);
@@ -828,12 +849,12 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v, int c_step_ne
       }
     }
   }
-  __syncthreads();
+  cl.sync();
   // requests that point at a node created in this step: sample index -> node id
   {
-    unsigned long long run = s_part[tid];
+    unsigned long long run = run0;
     for (int s = a0; s < a1; ++s) {
-      const int st = sst[s];
+      const int st = v.st[s];
       const long long ri = req0 + (long long)((run >> 42) & 0x1fffff);
       if (st == ST_CREATE) {
         const int valid = ((v.s_pc[s] >> 1) & 3) == 1;
@@ -845,13 +866,28 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v, int c_step_ne
       }
     }
   }
+  cl.sync();
+  if (rank != 0) return;
+  // ---- CTA 0: control block, statistics, plan of the next step -----------------------------------------
+  __shared__ unsigned long long s_sum, s_sq;
+  if (tid == 0) { s_sum = 0; s_sq = 0; }
+  __syncthreads();
+  {  // draws / pop statistics of the committed pops
+    unsigned a = 0, b = 0;  // (a pop consumes < 65536 draws; a thread owns few pops)
+    for (int i = tid; i < n_commit; i += T) { const unsigned cc = v.pop_cons[i]; a += cc; b += cc * cc; }
+    a = __reduce_add_sync(FULL, a);
+    b = __reduce_add_sync(FULL, b);
+    if ((tid & 31) == 0 && a) { atomicAdd(&s_sum, (unsigned long long)a); atomicAdd(&s_sq, (unsigned long long)b); }
+  }
   __syncthreads();
   if (tid == 0) {
-    const unsigned long long tot = s_tot;
+    unsigned long long tot = 0;
+    for (int k = 0; k < NC; ++k) tot += ((volatile unsigned long long*)c->cta_tot)[k];
     const int n_new = (int)(tot & 0x1fffff), n_q = (int)((tot >> 21) & 0x1fffff);
     const long long n_rq = (long long)((tot >> 42) & 0x1fffff);
     __threadfence();
     ExpCtl k = *c;  // one read, one write-back: every field access below would otherwise be an L2 round trip
+    k.steps++;
     k.n_nodes = n_nodes0 + n_new;
     k.tail = tail0 + n_q;
     k.n_req = req0 + n_rq;
@@ -880,7 +916,6 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v, int c_step_ne
       k.var += w * ((float)var - k.var);
       if (k.var < 0.05f) k.var = 0.05f;
     }
-    k.z_ties = c->z_ties;  // (bumped by atomics above)
     *c = k;
   }
   // ---- plan the next step --------------------------------------------------------------------------
@@ -1083,7 +1118,6 @@ extern "C" int trgb_expander_create(trgb_expander** out, const trgb_map* map, co
   TRGB_ARG(prm->sample_num >= 1 && prm->sample_num <= kExpMaxS, "sample_num out of range for the device expander");
   TRGB_ARG(prm->max_pops >= 32 && prm->max_pops <= kExpMaxPops, "max_pops out of range");
   TRGB_ARG(prm->window_words >= 2 && prm->window_words <= 4, "window_words must be 2..4");
-  TRGB_ARG((int64_t)prm->max_pops * prm->sample_num <= 200 * 1024, "max_pops x sample_num too large for the commit kernel");
   TRGB_ARG(node_capacity >= 1024 && node_capacity < (1ll << 21) * 512, "node_capacity out of range");
   TRGB_ARG(x1 > x0 && y1 > y0, "bad extent");
   // the window kernel is the thread-per-query routine: the map must be sparse enough for its column
@@ -1137,8 +1171,7 @@ extern "C" int trgb_expander_create(trgb_expander** out, const trgb_map* map, co
     e->top_smem = std::max<size_t>(top_smem, 1024);
     TRGB_CUDA(cudaFuncSetAttribute((const void*)k_exp_tables, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)std::max<size_t>(e->top_smem, (size_t)32 * kRow + 8 * 256)));
-    TRGB_CUDA(cudaFuncSetAttribute((const void*)k_exp_commit, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)std::max<size_t>((size_t)prm->max_pops * prm->sample_num, 1024)));
+
   }
   TRGB_CUDA(cudaStreamCreateWithFlags(&e->st2, cudaStreamNonBlocking));
   TRGB_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
@@ -1271,7 +1304,19 @@ static int launch_step(trgb_expander* e, int c_step) {
   TRGB_CUDA(cudaStreamWaitEvent(st, e->ev_join, 0));
   {
     ProfScope ps("k_exp_commit", st, (double)ns);
-    k_exp_commit<<<1, 1024, (size_t)c_step * S, st>>>(v, c_step);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kCommitCtas);
+    cfg.blockDim = dim3(1024);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCommitCtas;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TRGB_CUDA(cudaLaunchKernelEx(&cfg, k_exp_commit, v, c_step));
   }
   TRGB_CUDA(cudaGetLastError());
   return TRGB_OK;

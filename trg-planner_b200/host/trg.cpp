@@ -71,6 +71,7 @@ TRG::TRG(bool isVerbose, float expand_dist, float robot_size, int sample_num, fl
 }
 
 TRG::~TRG() {
+  if (graph_disposal_.valid()) graph_disposal_.get();
   joinDrawPrefetch();
   destroyExpander();
   for (auto& kv : trgMap_) {
@@ -1257,6 +1258,17 @@ void TRG::initGraph(bool /*isPreMap*/, Eigen::Vector3f start3d) {  // trg.cpp:36
   std::lock_guard<std::mutex> lock(mtx.graph);
   auto t0 = Clock::now();
   trgStruct& graph = *trgMap_["global"];
+  // A large previous graph is disposed of on a helper thread (freeing half a million hash nodes takes
+  // ~20 ms). clear() would keep the bucket array, which decides the iteration order of the refilled
+  // map (hence the renumbering of cleanGraph): an empty map rehashed to the same bucket count is in
+  // the identical state (same count, same policy threshold).
+  if (graph_disposal_.valid()) graph_disposal_.get();
+  if (graph.nodes.size() > (size_t)tuning_.parallel_min_nodes) {
+    auto* old = new std::unordered_map<int, Node*>();
+    old->swap(graph.nodes);
+    graph.nodes.rehash(old->bucket_count());
+    graph_disposal_ = std::async(std::launch::async, [old] { delete old; });
+  }
   this->resetGraph(graph.type);
   this->resetGraph("local");  // local nodes are pointers into the global graph
   rewindPools();

@@ -249,6 +249,7 @@ class TRG {
   // (step-3 wiring on, map too dense, capacity): the caller runs the host-driven path instead.
   bool buildGraphOnDevice(trgStruct& g);
   void destroyExpander();
+  std::future<void> graph_disposal_;  // helper freeing the previous build's node map
   trgb_expander*  expander_     = nullptr;
   const trgb_map* expander_map_ = nullptr;
 

@@ -12,6 +12,7 @@
 //  * the two std::unordered_map iteration orders cleanGraph's renumbering goes through
 //    (trg.cpp:497-504, 528-530): ids must be bit-exact, so the first map's order is replayed from
 //    libstdc++'s own rehash policy and the second map is the real container.
+#include <assert.h>
 #include <math.h>
 
 #include <algorithm>
@@ -241,6 +242,28 @@ bool TRG::buildGraphOnDevice(trgStruct& g) {
                               rd.data(), (int64_t)pos), "trgb_expander_apply_pop");
   };
 
+  // ---- the renumbered node map (trg.cpp:502, 526) is a fresh std::unordered_map filled with the keys
+  // 0 .. m-1 in order, m = number of surviving nodes. Every Valid node ever queued survives (it has its
+  // parent edge), so the queue tail is a lower bound of m that only grows: a helper thread performs the
+  // insertions (placeholder values) while the BFS runs — same sequence of operator[] calls, hence the
+  // same buckets, order and rehash history as the reference's loop.
+  std::unordered_map<int, Node*> new_nodes;
+  std::atomic<int> map_target{0};
+  std::atomic<bool> map_stop{false};
+  std::thread map_builder([&new_nodes, &map_target, &map_stop] {
+    int k = 0;
+    for (;;) {
+      const int t = map_target.load(std::memory_order_acquire);
+      for (; k < t; ++k) new_nodes[k] = nullptr;
+      if (map_stop.load(std::memory_order_acquire) && k >= map_target.load(std::memory_order_acquire)) break;
+      if (k >= t) std::this_thread::sleep_for(std::chrono::microseconds(50));
+    }
+  });
+  struct JoinGuard {
+    std::thread& t; std::atomic<bool>& stop;
+    ~JoinGuard() { stop.store(true, std::memory_order_release); if (t.joinable()) t.join(); }
+  } map_guard{map_builder, map_stop};
+
   // ---- the BFS: two groups of steps in flight, one status poll per group ----------------------
   int hint = 64;
   TrgbExpandStatus st{};
@@ -272,6 +295,7 @@ bool TRG::buildGraphOnDevice(trgStruct& g) {
       break;
     }
     const int q = st.tail - st.head;
+    if (st.tail > 1) map_target.store(st.tail, std::memory_order_release);
     hint = std::min(tuning_.expand_max_pops, std::max(64, q + q / 4 + 64));
     ahead = std::min<size_t>((size_t)1 << 22, std::max<size_t>((size_t)1 << 17, (size_t)4 * group * (size_t)hint * (size_t)(S + 2)));
     push_upto((size_t)st.pos + ahead);
@@ -343,17 +367,32 @@ bool TRG::buildGraphOnDevice(trgStruct& g) {
       }
     }
   });
-  // the renumbered map is a fresh container filled with 0 .. m-1 in order (:502, :526)
-  std::unordered_map<int, Node*> new_nodes;
-  for (size_t k = 0; k < m; ++k) new_nodes[(int)k] = &node_pool_[k];
+  // the renumbered map: the helper inserted most keys already; finish, then point every key at its node
+  map_target.store((int)m, std::memory_order_release);
+  map_stop.store(true, std::memory_order_release);
+  map_builder.join();
+  if (new_nodes.size() != m) throw std::logic_error("trg_b200: renumbered map out of step with the survivors");
+  // its iteration order (needed for node_tree, :528-530) is again that of a sequentially filled fresh map
+  const std::vector<int> order2 = sequential_map_order(m, 1);
+  parallel_for(m, threads, [&](size_t b, size_t en) {
+    for (size_t k = b; k < en; ++k) new_nodes.find((int)k)->second = &node_pool_[k];
+  });
   std::unordered_map<int, Node*> old_nodes;
   old_nodes.swap(g.nodes);
   this->resetGraph(g.type);
   this->resetGraph("local");
   g.nodes   = std::move(new_nodes);
   g.node_id = (int)m;
-  g.node_seq.reserve(m);
-  for (auto& node : g.nodes) nodeIndexInsert(g, node.second);  // node_tree order = new map's iteration order (:528-530)
+  g.node_seq.resize(m);
+  parallel_for(m, threads, [&](size_t b, size_t en) {
+    for (size_t i = b; i < en; ++i) g.node_seq[i] = &node_pool_[(size_t)order2[i]];
+  });
+#ifndef NDEBUG
+  {
+    size_t i = 0;
+    for (auto& node : g.nodes) assert(node.second == g.node_seq[i++]);
+  }
+#endif
   invalidateDeviceGraph();
   const double t_materialize = since(t_mat);
 
