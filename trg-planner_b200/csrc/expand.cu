@@ -272,7 +272,7 @@ __device__ __forceinline__ unsigned dep_hash(int cx, int cy) {
 }
 
 // ---- chain kernels --------------------------------------------------------------------------------------
-// tables: one CTA (8 warps) per block of 32 pops, four pops per warp. All 32 lanes of a warp work on one
+// tables: one CTA (32 warps) per block of 32 pops, one pop per warp. All 32 lanes of a warp work on one
 // pop at a time: positions of its free draws, then consumed(start offset) for every admissible offset
 // (the S-th free draw at or after r is free draw number free_below(r) + S - 1). Afterwards thread r
 // composes the block's map (start offset at its first pop -> end position, pops completed). The CTA
@@ -286,7 +286,7 @@ __device__ __forceinline__ void exp_tables_block(const ExpView& v, unsigned char
   unsigned char* zp = smem + 32 * kRow + warp * 256;  // free-draw positions of the pop a warp works on
   const int first = b << 5;
   const int cnt = min(32, m - first);
-  for (int p = warp; p < cnt; p += 8) {
+  for (int p = warp; p < cnt; p += (int)(blockDim.x >> 5)) {
     unsigned long long mk[4] = {~0ull, ~0ull, ~0ull, ~0ull};
     for (int w = 0; w < words; ++w) mk[w] = v.mask[(size_t)(first + p) * words + w];
     for (int bpos = lane; bpos < W; bpos += 32)
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(256) k_exp_deps(ExpView v) {
   }
 }
 
-__global__ void __launch_bounds__(256) k_exp_tables(ExpView v) {
+__global__ void __launch_bounds__(1024) k_exp_tables(ExpView v) {
   extern __shared__ unsigned char chsm[];
   ExpCtl* c = v.ctl;
   // (spare work: empty the hash the emit kernel fills)
@@ -625,7 +625,7 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v, int c_step_ne
     }
     return;
   }
-  __shared__ int s_any, s_und;
+  __shared__ int s_any;
   __shared__ unsigned long long s_part[1024];
   __shared__ unsigned long long s_base;
   const int S = v.S;
@@ -662,13 +662,20 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v, int c_step_ne
     v.cur_d2[s] = v.s_d2[s];
   }
   cl.sync();
-  // ---- reservation rounds ----------------------------------------------------------------------------
+  // ---- reservations, asynchronously ---------------------------------------------------------------------
+  // No rounds, no barriers: every thread keeps sweeping its undecided samples. A sample is decided as soon
+  // as no earlier sample that may still become a node lies within its current nearest distance; what it
+  // reads of other samples (their state, their current nearest distance) only ever moves one way
+  // (undecided -> decided once, distance downwards), so a stale read can only delay it. The earliest
+  // undecided sample never waits, all CTAs of the cluster are resident: the sweep terminates.
   int rounds = 0;
-  while (true) {
-    // read half: nearest decided node so far; wait if an earlier undecided sample that may still become a
-    // node lies at least as close
+  volatile int* vst = v.st;
+  volatile float* vd2 = v.cur_d2;
+  for (int pending = 1; pending;) {
+    pending = 0;
+    ++rounds;
     for (int s = gtid; s < ns; s += GT) {
-      if (v.st[s] != ST_UNDECIDED) continue;
+      if (vst[s] != ST_UNDECIDED) continue;
       float bd = __ldg(v.s_d2 + s);
       int bn = __ldg(v.s_nn + s);
       int tie = 0;
@@ -677,13 +684,13 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v, int c_step_ne
       if (nd <= kDepMax) {
         for (int u = 0; u < nd; ++u) {
           const int q = __ldg(v.dep_j + (size_t)s * kDepMax + u);
-          const int sq = v.st[q];
+          const int sq = vst[q];
           if (sq != ST_CREATE && sq != ST_UNDECIDED) continue;
           const float d2 = __ldg(v.dep_d2 + (size_t)s * kDepMax + u);
           if (sq == ST_CREATE) {
             if (d2 < bd) { bd = d2; bn = -2 - q; tie = 0; }
             else if (d2 == bd && bn != -2 - q) tie = 1;
-          } else if (__fsqrt_rn(((volatile float*)v.cur_d2)[q]) >= r) {  // (a stale, larger value only delays this sample)
+          } else if (__fsqrt_rn(vd2[q]) >= r) {
             mu = fminf(mu, d2);
           }
         }
@@ -701,7 +708,7 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v, int c_step_ne
             if (seen) continue;
             for (int q = v.dhead[h]; q >= 0; q = v.dnext[q]) {
               if (q >= s) continue;
-              const int sq = v.st[q];
+              const int sq = vst[q];
               if (sq != ST_CREATE && sq != ST_UNDECIDED) continue;
               const float2 pq = v.s_xy[q];
               const float dx = __fsub_rn(pq.x, p.x), dy = __fsub_rn(pq.y, p.y);
@@ -709,29 +716,17 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v, int c_step_ne
               if (sq == ST_CREATE) {
                 if (d2 < bd) { bd = d2; bn = -2 - q; tie = 0; }
                 else if (d2 == bd && bn != -2 - q) tie = 1;
-              } else if (__fsqrt_rn(((volatile float*)v.cur_d2)[q]) >= r) {
+              } else if (__fsqrt_rn(vd2[q]) >= r) {
                 mu = fminf(mu, d2);
               }
             }
           }
       }
-      const bool wait = mu <= bd;
-      v.cur_d2[s] = bd;
-      v.cur_nn[s] = bn;  // nearest decided node: >= 0 existing, <= -2 sample of this step
-      // the decision itself is written in the second half; the verdict travels in s_tie (its pre-step value was consumed above)
-      v.s_tie[s] = (unsigned char)((wait ? 2 : 0) | (tie ? 1 : 0));
-    }
-    cl.sync();
-    // write half
-    int undecided = 0;
-    for (int s = gtid; s < ns; s += GT) {
-      if (v.st[s] != ST_UNDECIDED) continue;
-      const unsigned char f = v.s_tie[s];
-      if (f & 2) { ++undecided; continue; }
+      vd2[s] = bd;  // published either way: lets later samples see that this one can no longer become a node
+      if (mu <= bd) { ++pending; continue; }
+      // (a CREATE entry at a distance above mu cannot have been missed: entries are only skipped when decided otherwise)
       const int i = s / S;
-      const int bn = v.cur_nn[s];
-      const float bd = v.cur_d2[s];
-      if (f & 1) atomicMin(&c->ipop, i);
+      if (tie) atomicMin(&c->ipop, i);
       int nstate;  // state of the nearest node (NodeState: -1 invalid)
       if (bn >= 0) nstate = v.node_state[bn];
       else if (bn <= -2) nstate = (((v.s_pc[-2 - bn] >> 1) & 3) == 0) ? -1 : 0;
@@ -743,20 +738,12 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v, int c_step_ne
         st = ST_CREATE;                                             // trg.cpp:421
         if (((v.s_pc[s] >> 1) & 3) >= 2) atomicMin(&c->ipop, i);    // slope gate too close to call
       }
-      v.st[s] = st;
+      v.cur_nn[s] = bn;  // nearest node: >= 0 existing, <= -2 sample of this step (read after the barrier below)
+      __threadfence();
+      vst[s] = st;
     }
-    const int und_cta = __syncthreads_count(undecided > 0);
-    if (tid == 0) c->und[rounds & 1][rank] = und_cta;
-    ++rounds;
-    cl.sync();
-    if (tid == 0) {
-      int tot = 0;
-      for (int k = 0; k < NC; ++k) tot += ((volatile int*)c->und[(rounds - 1) & 1])[k];
-      s_und = tot;
-    }
-    __syncthreads();
-    if (s_und == 0) break;
   }
+  cl.sync();
   // ---- apply the decisions of the pops before the first one the host must handle --------------------
   const int n_commit = min(((volatile int*)&c->ipop)[0], n_done);
   const int nsc = n_commit * S;
@@ -1170,7 +1157,7 @@ extern "C" int trgb_expander_create(trgb_expander** out, const trgb_map* map, co
     if (top_smem > 200 * 1024) { trgb_expander_destroy(e); set_error("expander: max_pops x window too large for the chain kernel"); return TRGB_E_ARG; }
     e->top_smem = std::max<size_t>(top_smem, 1024);
     TRGB_CUDA(cudaFuncSetAttribute((const void*)k_exp_tables, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)std::max<size_t>(e->top_smem, (size_t)32 * kRow + 8 * 256)));
+                                   (int)std::max<size_t>(e->top_smem, (size_t)32 * kRow + 32 * 256)));
 
   }
   TRGB_CUDA(cudaStreamCreateWithFlags(&e->st2, cudaStreamNonBlocking));
@@ -1282,8 +1269,8 @@ static int launch_step(trgb_expander* e, int c_step) {
   }
   {
     ProfScope ps("k_exp_tables", st, (double)c_step);
-    const size_t smem = std::max<size_t>((size_t)32 * kRow + 8 * 256, (size_t)nblk * (64 * v.norm_words - 32) * 5);
-    k_exp_tables<<<nblk, 256, smem, st>>>(v);
+    const size_t smem = std::max<size_t>((size_t)32 * kRow + 32 * 256, (size_t)nblk * (64 * v.norm_words - 32) * 5);
+    k_exp_tables<<<nblk, 1024, smem, st>>>(v);
   }
   {
     ProfScope ps("k_exp_emit", st, (double)ns);
