@@ -1,23 +1,28 @@
 #!/usr/bin/env python
-"""bench.py — TRG build + risk-aware path batch on synthetic terrain (BASELINE.json configs[1]).
+"""bench.py — TRG build + risk-aware path batch on synthetic terrain.
 
-One "step" = one full pass of the hot path over one map: map-index build (TRG::setGlobalMap),
-graph construction (TRG::initGraph) and a 1k-query planSafePath batch, all through the
-reference-facing C facade (include/trg_b200.h).
+Default workload (--workload c2 = BASELINE.json configs[1]): one "step" = one full pass of the hot path over
+one 10 M-point map: map-index build (TRG::setGlobalMap), graph construction (TRG::initGraph) and a 1k-query
+planSafePath batch, all through the reference-facing C facade (include/trg_b200.h).
 
-  value   points/s of the build with the cloud already resident in HBM (trg_set_global_map_dev);
-          the per-kernel timings behind `roofline` / `kernels` come from one more step of the same
-          workload run with the library's event profiler switched on, right after the timed region
-  e2e     the same through host buffers: pinned-host cloud -> H2D inside the timed region,
-          paths / costs copied back to host
-  N > 1   launched by torchrun: one process per GPU, each rank builds the TRG of its own
-          10 M-point tile of one continuous heightfield and answers its shard of the queries
-          (weak scaling, no data-path collective); boundary nodes are all-gathered over NCCL
-          for stitching, and that exchange step counts as part of the build (build time at
-          N > 1 = tile build + stitching). Times are max over ranks.
+  value   points/s of the build with the cloud already resident in HBM (trg_set_global_map_dev); the
+          per-kernel timings behind `roofline` / `kernels` come from one more step of the same workload run
+          with the library's event profiler switched on, right after the timed region
+  e2e     the same through host buffers: pinned-host cloud -> H2D inside the timed region, paths / costs
+          copied back to host
+  N > 1   torchrun, one process per GPU. c2: every rank builds the TRG of its own 10 M-point tile of one
+          continuous heightfield (weak scaling); c3: ONE 50 M-point map cut into N tiles (strong scaling).
+          Either way the tiles are stitched into ONE graph: boundary nodes and map strips are all-gathered
+          (NCCL), cross-tile edges validated by K4, every rank receives the merged CSR, answers its contiguous
+          share of the query batch on it (paths cross tile borders) and the results are all-gathered.
+          Times are max over ranks.
 
-`--impl reference` times the CPU oracle (restated trg.cpp + the reference's own kdtree.c when
-oracle/_ref was built) on a bounded sample of the same workload.
+Other workloads: --workload c3 | c4 (incremental updates: 200 k-point scans against a 20 M-point map) |
+c5 (200 M-point multi-level terrain, K2 / K4 roofline sweep over the radius). --verify compares the CUDA
+build with the full-size run of the reference itself (profiles/_big/<tag>_ref.npz, scripts/ref_fullsize.py).
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref/libtrg_ref.so = the unmodified
+trg.cpp + kdtree.c; the restated oracle when that library is absent) on a bounded sample of the workload.
 """
 from __future__ import annotations
 
@@ -36,9 +41,13 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 SEED_RNG = 42          # mt19937 seed of TRG::gen_ (the reference seeds from random_device)
-SEED_MAP = 2
-SEED_QUERIES = 7
 CPU_SAMPLE_SIDE = 1000  # bounded CPU sample: 1000 x 1000 lattice = 1 M points of the same generator
+WORKLOADS = {           # tag: (lattice side, map seed, queries, query seed)      SURVEY.md 8d
+    "c2": (3163, 2, 1000, 7),
+    "c3": (7072, 3, 10000, 8),
+    "c4": (4473, 4, 0, 9),
+    "c5": (14143, 5, 0, 10),
+}
 
 
 def env_int(k, d):
@@ -107,42 +116,42 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def tile_map(trg, side, rank, world):
-    """Rank's tile of one continuous world heightfield (tiles laid out along x)."""
-    return trg.terrain.mountain(side, h=0.1, seed=SEED_MAP, tile=(rank, 0), world_tiles=(world, 1))
-
-
 # algorithmic bytes per work unit (DESIGN.md §5 / SURVEY.md §8d); rho = map points per m^2
 def unit_bytes(kernel: str, P, rho: float, cell: float) -> float:
     r = P.robot_size
     k_r = np.pi * r * r * rho
-    if kernel in ("k_sample_window", "k_collision"):
-        return 16.0 * k_r + 8 + 1
-    if kernel == "k_range_count":
-        return 16.0 * k_r + 8 + 4
-    if kernel == "k_nearest_z":
-        return 16.0 * (9.0 * cell * cell * rho) + 12
-    # K4 = segment collision samples (k_edge_collide) + ellipse PCA (k_edge_pca); the two halves of
-    # SURVEY.md's 16*(m*k(r) + k_e) + 32 + 9 figure, each reading the two endpoints (20 B)
     e = P.expand_dist
     m = int(np.ceil(e / (0.5 * r)))
     c = 0.5 * e
     a = np.sqrt(c * c + r * r) if c >= r else r
-    if kernel == "k_edge_collide":
-        return 16.0 * m * k_r + 20 + 1
-    if kernel == "k_edge_pca":
-        return 16.0 * np.pi * a * a * rho + 20 + 9
-    if kernel in ("k_edge_eval", "k_edge_eval_warp"):
-        return 16.0 * (m * k_r + np.pi * a * a * rho) + 32 + 9
-    if kernel in ("k_nodes_nearest",):
-        return 0.0
-    if kernel in ("k_bbox", "k_count"):
-        return 12.0
-    if kernel in ("k_scatter", "k_sort_cell"):
-        return 32.0
-    if kernel == "k_sssp":
-        return 0.0  # reported per relaxed edge elsewhere
-    return 0.0
+    table = {
+        "k_sample_window": 16.0 * k_r + 8 + 1, "k_collision": 16.0 * k_r + 8 + 1, "k_exp_window": 16.0 * k_r + 8 + 1,
+        "k_range_count": 16.0 * k_r + 8 + 4,
+        "k_nearest_z": 16.0 * (9.0 * cell * cell * rho) + 12,
+        # K4 = segment collision samples (k_edge_collide) + ellipse PCA (k_edge_pca); the two halves of
+        # SURVEY.md's 16*(m*k(r) + k_e) + 32 + 9 figure, each reading the two endpoints (20 B)
+        "k_edge_collide": 16.0 * m * k_r + 20 + 1,
+        "k_edge_pca": 16.0 * np.pi * a * a * rho + 20 + 9,
+        "k_edge_eval": 16.0 * (m * k_r + np.pi * a * a * rho) + 32 + 9,
+        "k_edge_eval_warp": 16.0 * (m * k_r + np.pi * a * a * rho) + 32 + 9,
+        "k_bbox": 12.0, "k_count": 12.0, "k_scatter": 32.0, "k_sort_cell": 32.0,
+        # device BFS bookkeeping kernels (latency-bound; bytes of one sample / pop record read + written)
+        "k_exp_commit": 64.0, "k_exp_emit": 52.0, "k_exp_deps": 8.0 + 8.0 * 4, "k_exp_tables": 2.0 * 32 + 224,
+        # K7: 20 B per relaxed edge (12 B edge + 4 B label read + 4 B label write); units = relaxed edges
+        "k_sssp": 20.0,
+    }
+    return float(table.get(kernel, 0.0))
+
+
+def workload_map(trg, tag, side, rank, world, strong):
+    """This rank's cloud: c2 weak = its own side x side tile of a continuous world laid out along x;
+    strong (c3) = its x-slab of ONE side x side map."""
+    seed = WORKLOADS[tag][1]
+    if world == 1:
+        return trg.terrain.mountain(side, h=0.1, seed=seed, tile=(0, 0), world_tiles=(1, 1))
+    if not strong:
+        return trg.terrain.mountain(side, h=0.1, seed=seed, tile=(rank, 0), world_tiles=(world, 1))
+    return trg.terrain.mountain_slab(side, h=0.1, seed=seed, slab=rank, n_slabs=world)
 
 
 def run_product(a):
@@ -167,12 +176,28 @@ def run_product(a):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    tag = a.workload
+    side, _, n_queries, q_seed = WORKLOADS[tag]
+    if a.side:
+        side = a.side
+    if a.queries is not None:
+        n_queries = a.queries
+    strong = tag == "c3"
     P = trg.MOUNTAIN
-    pts = tile_map(trg, a.side, rank, world)
+    pts = workload_map(trg, tag, side, rank, world, strong)
     n = int(pts.shape[0])
     bb = trg.terrain.bbox(pts)
     start = (0.5 * (bb[0][0] + bb[0][1]), 0.5 * (bb[1][0] + bb[1][1]), 0.0)
-    queries = trg.terrain.query_pairs(bb, a.queries, seed=SEED_QUERIES + rank)
+    # queries: N = 1 -> the workload's batch over the map; N > 1 -> ONE global batch over the whole world,
+    # the same on every rank, answered in contiguous shares on the merged graph
+    if world == 1:
+        queries = trg.terrain.query_pairs(bb, n_queries, seed=q_seed)
+    else:
+        lo = torch.tensor([bb[0][0], bb[1][0]], device="cuda", dtype=torch.float64)
+        hi = torch.tensor([bb[0][1], bb[1][1]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        world_bb = ((float(lo[0]), float(hi[0])), (float(lo[1]), float(hi[1])))
+        queries = trg.terrain.query_pairs(world_bb, n_queries * (1 if strong else world), seed=q_seed)
     d_pts = torch.from_numpy(pts).cuda()
     h_pin = torch.from_numpy(pts).pin_memory()
     h_np = h_pin.numpy()
@@ -184,38 +209,13 @@ def run_product(a):
             dist.barrier()
             torch.cuda.synchronize()
 
-    last_stitch = {}
-    resident_leg = [True]
-
-    def exchange_boundary():
-        """N > 1: stitch the per-tile TRGs. NCCL all-gathers of boundary nodes, boundary strips of
-        the map and the stitched edges; cross-tile candidate edges are validated by the K4 kernels
-        on a map of the two strips (trg-planner_b200/sharding.py). Returns bytes gathered."""
-        if dist is None:
-            return 0
-        from trg_planner_b200 import sharding
-        tx = time.perf_counter()
-        g = t.export(edges=False)
-        last_stitch["export_ms"] = round(1e3 * (time.perf_counter() - tx), 2)
-
-        def edge_eval(strip_pts, p1, p2):
-            dm = K.DeviceMap(strip_pts, 0.67 * P.robot_size)
-            r = dm.edge_eval(p1, p2, P.robot_size, P.height_threshold, P.collision_threshold)
-            dm.close()
-            return r["stage"], r["weight"], r["dist"]
-
-        cloud = d_pts if resident_leg[0] else pts   # strips are cut where the step's input lives
-        _, st = sharding.stitch_tiles(dist, torch, torch.device("cuda", local), rank, world, cloud, g.pos, g.ids,
-                                      bb[0][0], bb[0][1], P.expand_dist, P.robot_size, edge_eval)
-        last_stitch.update(st)
-        return st["bytes"]
-
-    STAT_KEYS = ("us_sample", "us_eval", "us_commit", "us_wait", "us_clean", "us_draws", "pops", "window_launches",
-                 "eval_launches", "window_tests", "edge_evals", "us_device_bfs", "us_device_edges", "us_materialize",
-                 "device_steps", "device_rounds", "device_redo_pops", "device_interrupts", "device_builds")
+    STAT_KEYS = ("us_draws", "pops", "window_tests", "edge_evals", "us_device_bfs", "us_device_edges", "us_materialize",
+                 "device_steps", "device_rounds", "device_redo_pops", "device_interrupts", "device_builds",
+                 "us_prep_csr", "us_prep_tree", "us_prep_grid", "sssp_relaxed_edges", "sssp_queries",
+                 "us_commit", "us_clean", "us_wait")
+    merged_stats = {}
 
     def one_step(resident: bool):
-        resident_leg[0] = resident
         t.seed(SEED_RNG)
         s0 = {k: t.stat(k) for k in STAT_KEYS}
         w0 = time.perf_counter()
@@ -226,17 +226,36 @@ def run_product(a):
         rc = t.init_graph(start)
         assert rc == 0
         w1 = time.perf_counter()
-        xb = exchange_boundary()
-        w2 = time.perf_counter()
-        r = t.plan_batch(queries)
+        xb = 0
+        if dist is None:
+            w2 = w1
+            r = t.plan_batch(queries)
+            found = int(r["found"].sum())
+            d2h = int(r["ids"].nbytes + 4 * 4 * len(queries) + 2 * len(queries) + 8 * (len(queries) + 1))
+        else:
+            from trg_planner_b200 import sharding
+            cloud = d_pts if resident else pts   # strips are cut where the step's input lives
+            dev = torch.device("cuda", local)
+            mg = sharding.build_merged_graph(dist, torch, dev, rank, world, t, cloud, bb, P, K)
+            w2 = time.perf_counter()
+            res = sharding.plan_sharded(dist, torch, dev, rank, world, mg, queries, P, K)
+            found = int(res["found"].sum())
+            d2h = int(res["d2h_bytes"])
+            xb = int(mg["stats"]["bytes"] + res["gather_bytes"])
+            merged_stats.clear()
+            merged_stats.update(mg["stats"], cross_tile_paths=int(res["cross_tile_paths"]), merged_nodes=int(mg["n_nodes"]),
+                                merged_edges=int(mg["n_edges"]), result_gather_bytes=int(res["gather_bytes"]))
+            mg["graph"].close()
         w3 = time.perf_counter()
         nn, ne = t.counts()
         host = {k: t.stat(k) - s0[k] for k in STAT_KEYS}
-        host.update(map_ms=round(1e3 * t.seconds("set_global_map"), 2), init_ms=round(1e3 * t.seconds("init_graph"), 2),
-                    snap_ms=round(1e3 * t.seconds("plan_snap"), 2), plan_ms=round(1e3 * t.seconds("plan_batch"), 2))
+        host.update(map_ms=round(1e3 * t.seconds("set_global_map"), 2), init_ms=round(1e3 * t.seconds("init_graph"), 2))
+        if dist is None:
+            host.update(prep_ms=round(1e3 * t.seconds("plan_prep"), 2),
+                        snap_ms=round(1e3 * (t.seconds("plan_snap") - t.seconds("plan_prep")), 2),
+                        plan_ms=round(1e3 * t.seconds("plan_batch"), 2))
         return dict(host=host, build_s=w1 - w0, exch_s=w2 - w1, query_s=w3 - w2, step_s=w3 - w0, nodes=nn, edges=ne,
-                    found=int(r["found"].sum()), d2h=int(r["ids"].nbytes + 4 * 4 * a.queries + 2 * a.queries +
-                                                         8 * (a.queries + 1)), xbytes=xb)
+                    found=found, d2h=d2h, xbytes=xb)
 
     def timed(resident: bool, warmup: int, steps: int):
         # nvidia-smi is started BEFORE the warm-up: its start-up (NVML init) holds driver locks for
@@ -257,7 +276,7 @@ def run_product(a):
         clocks = sampler.stop() if sampler else None
         launches = K.launch_count() - l0
         for r in rows:
-            r["buildx_s"] = r["build_s"] + r["exch_s"]   # N > 1: a tile's TRG is finished when it is stitched
+            r["buildx_s"] = r["build_s"] + r["exch_s"]   # N > 1: the TRG is finished when the tiles are merged
         agg = {k: float(np.mean([r[k] for r in rows])) for k in ("build_s", "buildx_s", "exch_s", "query_s", "step_s")}
         agg.update(total_ms=total_ms, rows=rows, clocks=clocks, launches=launches)
         return agg
@@ -265,22 +284,28 @@ def run_product(a):
     def profiled_steps(n_steps: int):
         """Per-kernel CUDA-event timings (the library's profiler: two events around every launch, on
         the launching stream) of `n_steps` further steps of the same resident workload, run right
-        after the timed region. They are NOT taken inside it: with ~28 k events per step the
-        profiler's bookkeeping stalled the first timed map build by 0.3 - 1.1 s on some boxes (at
-        any N), which is a property of the measurement, not of the path. One profiled step is run
-        and discarded first (event pool, first use)."""
+        after the timed region. They are NOT taken inside it: the profiler replaces the captured CUDA
+        graphs of the device BFS by individual launches and adds ~10 k events per step, which is a
+        property of the measurement, not of the path. One profiled step is run and discarded first."""
         K.prof_enable(True)
         one_step(True)
         K.prof_reset()
+        r0 = t.stat("sssp_relaxed_edges")
         for _ in range(n_steps):
             one_step(True)
         sync_all()
         profd = K.prof_collect()
         K.prof_enable(False)
+        if "k_sssp" in profd:
+            profd["k_sssp"]["units"] = float(t.stat("sssp_relaxed_edges") - r0)
         return profd
 
+    verify = None
+    if a.verify and rank == 0 and world == 1:
+        verify = verify_against_reference(trg, t, tag, one_step, P)
+
     val = timed(True, a.warmup, a.steps)
-    val["prof"] = profiled_steps(1)
+    val["prof"] = profiled_steps(1) if (not a.no_prof and world == 1) else {}
     val["prof_steps"] = 1
     e2e = timed(False, a.warmup, a.steps)
 
@@ -296,8 +321,9 @@ def run_product(a):
     RSUM = dist.ReduceOp.SUM if dist is not None else None
     tot_pts = reduce(float(n), RSUM)
     tot_nodes = reduce(float(val["rows"][-1]["nodes"]), RSUM)
-    tot_q = float(a.queries * world)
+    tot_q = float(len(queries))
     v_build = reduce(val["buildx_s"], RMAX)
+    v_tile = reduce(val["build_s"], RMAX)
     v_query = reduce(val["query_s"], RMAX)
     v_step = reduce(val["total_ms"] / a.steps, RMAX)
     e_build = reduce(e2e["buildx_s"], RMAX)
@@ -308,76 +334,153 @@ def run_product(a):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel inside the timed region -------------------------------
+    # ---- roofline of the dominant kernel (largest share of the profiled step among kernels with a byte model)
     rho = n / ((bb[0][1] - bb[0][0]) * (bb[1][1] - bb[1][0]))
     cell = 0.67 * P.robot_size
     peak, peak_src = measured_peak_gbs()
     prof = {k: v for k, v in val["prof"].items() if v["launches"] > 0}
-    dom = max((k for k in prof if unit_bytes(k, P, rho, cell) > 0), key=lambda k: prof[k]["ms"])
-    d = prof[dom]
-    ub = unit_bytes(dom, P, rho, cell)
-    avg_ms = d["ms"] / d["launches"]
-    bytes_per_launch = ub * d["units"] / d["launches"]
-    achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
-    traffic = None
-    tf = ROOT / "profiles" / "traffic.json"
-    if tf.exists():
-        try:
-            traffic = json.loads(tf.read_text()).get(dom)
-        except Exception:
-            traffic = None
-    psteps = val["prof_steps"]   # steps the kernel profile covers (run right after the timed region)
-    kern = {k: dict(launches=int(v["launches"] / psteps), ms_per_step=round(v["ms"] / psteps, 3),
-                    units_per_step=int(v["units"] / psteps),
-                    achieved_gbs=round(unit_bytes(k, P, rho, cell) * v["units"] / max(v["ms"], 1e-9) / 1e6, 1))
-            for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+    roof = None
+    kern = {}
+    if prof:
+        dom = max((k for k in prof if unit_bytes(k, P, rho, cell) > 0), key=lambda k: prof[k]["ms"])
+        d = prof[dom]
+        ub = unit_bytes(dom, P, rho, cell)
+        avg_ms = d["ms"] / d["launches"]
+        bytes_per_launch = ub * d["units"] / d["launches"]
+        achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
+        traffic = None
+        tf = ROOT / "profiles" / "traffic.json"
+        if tf.exists():
+            try:
+                traffic = json.loads(tf.read_text()).get(dom)
+            except Exception:
+                traffic = None
+        psteps = val["prof_steps"]
+        kern = {k: dict(launches=int(v["launches"] / psteps), ms_per_step=round(v["ms"] / psteps, 3),
+                        units_per_step=int(v["units"] / psteps),
+                        achieved_gbs=round(unit_bytes(k, P, rho, cell) * v["units"] / max(v["ms"], 1e-9) / 1e6, 1))
+                for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "bytes_per_unit": ub, "units_per_launch": d["units"] / d["launches"],
+                "avg_launch_ms": avg_ms, "share_of_profiled_step": d["ms"] / max(sum(v["ms"] for v in prof.values()), 1e-9),
+                "profiled_steps": psteps,
+                "note": "dominant kernel by time of one profiled step (individual launches instead of the captured graphs); "
+                        "k_sssp units = edges relaxed (20 B each); the device-BFS kernels are launch / latency bound "
+                        "(sub-wave batches of one BFS frontier), see kernels_saturated for K2 / K4 at saturating sizes"}
 
     # ---- saturated-batch kernel numbers (config #5 style, isolated) ----------------------------
-    sat = saturated_kernels(trg, K, torch, t, P, bb, rho, cell, peak) if not a.no_sat else None
+    sat = saturated_kernels(trg, K, torch, t, P, bb, rho, cell, peak) if (not a.no_sat and world == 1) else None
 
-    # ---- CPU baseline: oracle on a bounded sample, rank 0, N = 1 only ---------------------------
+    # ---- CPU baseline: the reference on a bounded sample, rank 0, N = 1 only ---------------------
     cpu = None
     if world == 1 and not a.no_cpu:
         cpu = cpu_sample(trg, a.cpu_side, queries_n=100)
 
+    last = val["rows"][-1]
+    hb = last["host"]
     line = {
         "metric": "trg_build_points_per_sec", "value": tot_pts / v_build, "unit": "points/s",
         "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": v_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "higher_is_better": True, "scaling": "strong" if (strong and world > 1) else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"C2 synthetic mountain heightfield {a.side}x{a.side} (h=0.1 m, {n} points per GPU), "
-                               f"config/mountain.yaml params, full TRG build + {a.queries} path queries per GPU",
-                   "points_per_gpu": n, "queries_per_gpu": a.queries, "mt19937_seed": SEED_RNG,
+        "config": {"workload": (f"{tag.upper()} synthetic mountain heightfield, h=0.1 m, {n} points on this GPU "
+                                f"({int(tot_pts)} in all), config/mountain.yaml params, full TRG build + {int(tot_q)} path queries"),
+                   "points_per_gpu": n, "queries": int(tot_q), "mt19937_seed": SEED_RNG,
                    "l2": "inputs larger than L2 (160 MB float4 cloud per build); every step rebuilds from scratch",
-                   "parallelism": f"tiles x{world}" if world > 1 else "single GPU"},
+                   "parallelism": (("one map in " if strong else "") + f"{world} tiles, one merged graph") if world > 1 else "single GPU"},
         "nodes_per_sec": tot_nodes / v_build, "paths_per_sec": tot_q / v_query,
         "build_ms": 1e3 * v_build, "query_ms": 1e3 * v_query,
-        "graph": {"nodes": int(tot_nodes), "edges_rank0": val["rows"][-1]["edges"], "paths_found_rank0": val["rows"][-1]["found"]},
+        "graph": {"nodes": int(tot_nodes), "edges_rank0": last["edges"], "paths_found": last["found"]},
         "e2e": {"value": tot_pts / e_build, "unit": "points/s",
                 "h2d_bytes_per_step": int(n * 12 + queries.nbytes), "d2h_bytes_per_step": e2e["rows"][-1]["d2h"],
                 "build_ms": 1e3 * e_build, "query_ms": 1e3 * e_query, "paths_per_sec": tot_q / e_query,
                 "nodes_per_sec": tot_nodes / e_build},
         "gpu_launches": int(val["launches"]),
+        "device_bfs": {"steps": hb.get("device_steps"), "reservation_sweeps": hb.get("device_rounds"),
+                       "redone_pops": hb.get("device_redo_pops"), "host_handled_pops": hb.get("device_interrupts"),
+                       "useful_over_window_tests": (hb["pops"] * (P.sample_num + 0.2)) / max(hb["window_tests"], 1)},
         "host_breakdown_per_step": {"value_leg": [r["host"] for r in val["rows"]], "e2e_leg": [r["host"] for r in e2e["rows"]]},
         "clocks": val["clocks"],
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "bytes_per_unit": ub, "units_per_launch": d["units"] / d["launches"],
-                     "avg_launch_ms": avg_ms, "share_of_step": d["ms"] / psteps / v_step,
-                     "profiled_steps": psteps,
-                     "profiled": "same workload, extra step(s) right after the timed region (see bench.py: profiled_steps)"},
+        "roofline": roof,
         "kernels": kern,
         "kernels_saturated": sat,
         "cpu_baseline": cpu,
     }
+    if verify is not None:
+        line["verify"] = verify
     if world > 1:
-        line["exchange"] = {"allgather_bytes_per_step": val["rows"][-1]["xbytes"], "ms": 1e3 * val["exch_s"], **last_stitch}
+        line["exchange"] = {"leg": "value (resident cloud), last timed step of rank 0", "bytes_per_step": last["xbytes"],
+                            "tile_build_ms_max": 1e3 * v_tile, "merge_ms_rank0": 1e3 * val["exch_s"], **merged_stats}
     if saved_stdout is not None:
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def verify_against_reference(trg, t, tag, one_step, P):
+    """Full-size parity: the CUDA build of this workload against the reference's own run on the CPU
+    (profiles/_big/<tag>_ref.npz, written by scripts/ref_fullsize.py; git-ignored, travels with gpurun)."""
+    f = ROOT / "profiles" / "_big" / f"{tag}_ref.npz"
+    if not f.exists():
+        return {"skipped": f"{f.relative_to(ROOT)} not present (run scripts/ref_fullsize.py --config {tag})"}
+    ref = np.load(f)
+    one_step(True)
+    g = t.export()
+    out = {"reference_file": str(f.relative_to(ROOT)), "nodes": [int(g.n_nodes), int(len(ref["iter_ids"]))],
+           "edges": [int(g.n_edges), int(len(ref["col"]))], "rng_draws": [int(t.stat("rng_draws")), int(ref["rng_draws"])]}
+    bit = {}
+    for k in ("iter_ids", "pos", "state", "row_ptr", "col", "dist"):
+        x, y = getattr(g, k), ref[k]
+        bit[k] = bool(x.shape == y.shape and np.array_equal(x, y))
+    out["bit_exact"] = bit
+    if g.weight.shape == ref["weight"].shape:
+        rel = np.abs(g.weight - ref["weight"]) / np.maximum(np.abs(ref["weight"]), 1e-12)
+        rel[(g.weight == 0) & (ref["weight"] == 0)] = 0
+        out["edge_risk"] = {"tolerance": 1e-5, "beyond_tolerance": int((rel > 1e-5).sum()), "max_rel": float(rel.max()) if rel.size else 0.0,
+                            "fraction_beyond": float((rel > 1e-5).mean()) if rel.size else 0.0,
+                            "threshold_crossings_at_0.1": int(((g.weight == 0) != (ref["weight"] == 0)).sum())}
+    # paths
+    q = ref["queries"]
+    r = t.plan_batch(q)
+    same = cost_ok = tie = 0
+    sf = np.float32(P.safety_factor)
+
+    def cost_of(ids):
+        c = np.float32(0)
+        for a_, b_ in zip(ids[:-1], ids[1:]):
+            e = ref["row_ptr"][a_] + np.nonzero(ref["col"][ref["row_ptr"][a_]:ref["row_ptr"][a_ + 1]] == b_)[0][0]
+            c = np.float32(c + np.float32(np.float32(np.float32(sf * ref["weight"][e]) + np.float32(1)) * ref["dist"][e]))
+        return float(c)
+    found_equal = bool(np.array_equal(r["found"], ref["path_found"]))
+    known_equal = bool(np.array_equal(r["goal_known"], ref["goal_known"]))
+    ends_equal = 0
+    worst = 0.0
+    for i in range(len(q)):
+        if not ref["path_found"][i]:
+            continue
+        mine = r["ids"][r["offsets"][i]:r["offsets"][i + 1]]
+        theirs = ref["path_ids"][ref["path_off"][i]:ref["path_off"][i + 1]]
+        ends_equal += int(len(mine) > 0 and mine[0] == theirs[0] and mine[-1] == theirs[-1])
+        if np.array_equal(mine, theirs):
+            same += 1
+            cost_ok += 1
+            continue
+        cm, ct = cost_of(mine), cost_of(theirs)
+        rel = abs(cm - ct) / max(ct, 1e-9)
+        worst = max(worst, rel)
+        if rel <= 1e-5:
+            cost_ok += 1
+            tie += 1
+    nf = int(ref["path_found"].sum())
+    out["paths"] = {"queries": int(len(q)), "found_flags_equal": found_equal, "goal_known_equal": known_equal,
+                    "start_goal_nodes_equal": ends_equal, "found": nf, "identical_node_sequences": same,
+                    "different_sequence_equal_cost_within_1e-5": tie, "cost_within_1e-5": cost_ok, "worst_rel_cost_diff": worst}
+    out["pass"] = bool(all(bit.values()) and out["rng_draws"][0] == out["rng_draws"][1] and found_equal and known_equal
+                       and ends_equal == nf and cost_ok == nf and out.get("edge_risk", {}).get("fraction_beyond", 1.0) <= 0.005)
+    return out
 
 
 def saturated_kernels(trg, K, torch, t, P, bb, rho, cell, peak):
@@ -431,31 +534,46 @@ def saturated_kernels(trg, K, torch, t, P, bb, rho, cell, peak):
     return res
 
 
-def cpu_sample(trg, side, queries_n):
-    """Oracle (restated trg.cpp; verbatim reference kdtree.c when oracle/_ref exists) on a bounded
-    sample: one `side` x `side` tile of the same generator, same parameters, same seed."""
+def cpu_sample(trg, side, queries_n, tag="c2"):
+    """The reference's own CPU implementation (oracle/_ref/libtrg_ref.so: unmodified trg.cpp + kdtree.c; the
+    restated oracle when that library is absent) on a bounded sample: one `side` x `side` tile of the same
+    generator, same parameters, same seed. The full-size run of the same code is recorded once in
+    profiles/r02_c2_reference_cpu.json (scripts/ref_fullsize.py)."""
     P = trg.MOUNTAIN
-    pts = trg.terrain.mountain(side, h=0.1, seed=SEED_MAP, tile=(0, 0), world_tiles=(1, 1))
-    refkd = (ROOT / "oracle" / "_ref" / "liboracle_refkd.so").exists()
+    pts = trg.terrain.mountain(side, h=0.1, seed=WORKLOADS[tag][1], tile=(0, 0), world_tiles=(1, 1))
     import _pkg
-    o = _pkg.load_oracle().oracle(P, ref_kdtree=refkd)   # the checker, timed as the CPU baseline
+    F = _pkg.load_oracle()
+    kind = "ref" if F.available("ref") else ("refkd" if F.available("refkd") else "port")
+    o = F.oracle(P, kind=kind)   # the checker, timed as the CPU baseline
     o.seed(SEED_RNG)
     bb = trg.terrain.bbox(pts)
     w0 = time.perf_counter()
     o.set_global_map(pts)
     o.init_graph((0.5 * (bb[0][0] + bb[0][1]), 0.5 * (bb[1][0] + bb[1][1]), 0.0))
     w1 = time.perf_counter()
-    q = trg.terrain.query_pairs(bb, queries_n, seed=SEED_QUERIES)
+    q = trg.terrain.query_pairs(bb, queries_n, seed=WORKLOADS[tag][3])
     for row in q:
         o.plan(row[:2], row[2:5])
     w2 = time.perf_counter()
     nn, ne = o.counts()
-    return {"value": pts.shape[0] / (w1 - w0), "unit": "points/s", "cores": 1, "kind": "port",
-            "sample": f"{side}x{side} tile ({pts.shape[0]} points) of the same generator, full build + {queries_n} queries; "
-                      f"kd-tree = {'verbatim reference kdtree.c' if refkd else 'restated port'}; single thread "
-                      f"(the reference build is single-threaded, serialised by TRG::mtx.graph); host has {os.cpu_count()} cores",
-            "build_s": w1 - w0, "nodes_per_sec": nn / (w1 - w0), "paths_per_sec": queries_n / (w2 - w1),
-            "nodes": nn, "edges": ne}
+    out = {"value": pts.shape[0] / (w1 - w0), "unit": "points/s", "cores": 1,
+           "kind": "reference" if kind == "ref" else "port",
+           "sample": f"{side}x{side} tile ({pts.shape[0]} points) of the same generator, full build + {queries_n} queries; "
+                     + {"ref": "the reference's unmodified trg.cpp + kdtree.c (oracle/_ref/libtrg_ref.so)",
+                        "refkd": "restated trg.cpp on the reference's kdtree.c", "port": "restated oracle"}[kind]
+                     + f"; single thread (the reference build is single-threaded, serialised by TRG::mtx.graph); host has {os.cpu_count()} cores",
+           "build_s": w1 - w0, "nodes_per_sec": nn / (w1 - w0), "paths_per_sec": queries_n / (w2 - w1),
+           "nodes": nn, "edges": ne}
+    full = ROOT / "profiles" / "r02_c2_reference_cpu.json"
+    if full.exists():
+        try:
+            fr = json.loads(full.read_text())
+            out["full_config_record"] = {"file": str(full.relative_to(ROOT)), "points": fr["points"], "build_s": fr["build_s"],
+                                         "points_per_sec": fr["points_per_sec"], "paths_per_sec": fr["paths_per_sec"],
+                                         "host": fr.get("host"), "note": "same code, the whole 10 M-point C2 map, run once in the build container"}
+        except Exception:
+            pass
+    return out
 
 
 def run_reference(a):
@@ -472,13 +590,16 @@ def run_reference(a):
     v = float(np.mean([r["value"] for r in rows]))
     step_ms = 1e3 * float(np.mean([r["build_s"] + 50 / r["paths_per_sec"] for r in rows]))
     cb = dict(rows[-1]); cb["value"] = v
+    side = WORKLOADS["c2"][0]
     line = {"impl": "reference", "metric": "trg_build_points_per_sec", "value": v, "unit": "points/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C2 synthetic mountain heightfield {a.side}x{a.side} (h=0.1 m), config/mountain.yaml params, "
+            "config": {"workload": f"C2 synthetic mountain heightfield {side}x{side} (h=0.1 m), config/mountain.yaml params, "
                                    f"full TRG build + path queries",
-                       "sample": f"each step = the reference's CPU path (oracle: restated trg.cpp + kdtree.c) on a bounded sample: "
-                                 f"one {a.cpu_side}x{a.cpu_side} tile ({a.cpu_side * a.cpu_side} points) of the same generator + 50 queries, 1 thread",
+                       "sample": f"each step = the reference's CPU path ({cb['kind']}) on a BOUNDED sample: one {a.cpu_side}x{a.cpu_side} "
+                                 f"tile ({a.cpu_side * a.cpu_side} points, not the 10 M of the GPU arm) of the same generator + 50 queries, "
+                                 f"1 thread; the CPU's points/s FALLS with map size (unbalanced kd-tree), so the per-point ratio is "
+                                 f"conservative for the GPU: the full 10 M-point run of the same code is in cpu_baseline.full_config_record",
                        "mt19937_seed": SEED_RNG},
             "nodes_per_sec": float(np.mean([r["nodes_per_sec"] for r in rows])),
             "paths_per_sec": float(np.mean([r["paths_per_sec"] for r in rows])),
@@ -493,17 +614,24 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--side", type=int, default=3163, help="lattice side per GPU (3163 -> 10 M points)")
-    ap.add_argument("--queries", type=int, default=1000)
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--side", type=int, default=0, help="override the lattice side per GPU (c2: 3163 -> 10 M points)")
+    ap.add_argument("--queries", type=int, default=None)
     ap.add_argument("--cpu-side", type=int, default=CPU_SAMPLE_SIDE)
+    ap.add_argument("--verify", action="store_true", help="compare with the reference's full-size CPU run (profiles/_big)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sat", action="store_true")
+    ap.add_argument("--no-prof", action="store_true")
     ap.add_argument("--clock-ms", type=int, default=200, help="nvidia-smi sampling period during the timed region (0 = off)")
     a = ap.parse_args()
     if a.warmup < 3 and a.impl == "b200":
         a.warmup = max(a.warmup, 1)
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload in ("c4", "c5"):
+        sys.path.insert(0, str(ROOT / "scripts"))
+        import bench_extra
+        getattr(bench_extra, "run_" + a.workload)(a)
     else:
         run_product(a)
 

@@ -135,6 +135,12 @@ int     trgb_nodes_append_launch(trgb_nodes* g, const float* d_xy, int64_t n, vo
 int     trgb_nodes_nearest_launch(const trgb_nodes* g, const float* d_xy, int64_t n, int32_t* d_idx, float* d_d2,
                                   uint8_t* d_tie, void* stream);
 
+/* The insertion-order 2-D kd-tree n successive kd_insert2 calls build over the graph nodes (trg.cpp:249,
+ * 528-530; kdtree.c:167-194), grown in parallel on the device (one round per tree level). xy: n (x, y) pairs
+ * in insertion order; outputs per node: children (-1 = none), parent (-1 = root), split axis. The tree's
+ * shape is what TRG::setGoal's choice among several in-range nodes and kd_nearest's tie order depend on. */
+int trgb_kdtree_build(const float* xy, int64_t n, int32_t* lo, int32_t* hi, int32_t* parent, uint8_t* axis);
+
 /* ---- K9: device-resident graph expansion — TRG::expandGraph (trg.cpp:372-454) as a BFS that runs on the
  *      GPU including its decisions (trg-planner_b200/csrc/expand.cu). Usable when step 3 of expandGraph
  *      (neighbour wiring, trg.cpp:429) is off, i.e. expand_dist - robot_size >= 0.25 * expand_dist, and
@@ -221,6 +227,10 @@ int trgb_sssp_batch(trgb_graph* g, const int32_t* start_ids, const int32_t* goal
                     float safety_factor, uint8_t* found, float* cost, float* path_length,
                     float* avg_risk, int64_t* path_offsets, int32_t* path_ids,
                     int64_t path_ids_capacity);
+
+/* edges relaxed (atomicMin on a label) and queries answered over the handle's life: the K7 roofline counts
+ * 20 algorithmic bytes per relaxed edge (12 B edge + 4 B label read + 4 B label write) */
+int trgb_graph_stats(const trgb_graph* g, int64_t* relaxed_edges, int64_t* queries);
 
 /* ---- profiling: CUDA-event timing of every kernel launched by this library ------------- */
 int trgb_prof_enable(int on);

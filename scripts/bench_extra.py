@@ -1,0 +1,233 @@
+"""bench.py --workload c4 | c5 (BASELINE.json configs #4 and #5), one JSON line each with the bench contract's keys.
+
+c4  incremental update: 200 k-point scans along a trajectory against a 20 M-point prebuilt map; one step = one
+    scan = TRG::setLocalMap + TRG::updateGraph (trg.cpp:195-231, 456-489; the reference's "Graph update time"
+    timer, src/planner/trg_planner.cpp:185-191). CPU leg: the reference itself on a bounded sample (1 M-point
+    prebuilt map, scans of the same size).
+c5  stress: 200 M-point multi-level terrain (stairs + overhang slabs) generated on the GPU, K2 (cylinder
+    collision test) and K4 (edge evaluation) alone, swept over the search radius. CPU leg: the reference on
+    10^5 sampled queries per radius over a 2 M-point crop of the same cloud.
+"""
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import _pkg  # noqa: E402
+
+
+def _peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    try:
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def _scans(pts, ext, n, half, rng, x0):
+    order = np.argsort(pts[:, 0], kind="stable")
+    xs = pts[order, 0]
+    for k in range(n):
+        cx, cy = x0 + 2.0 * k, ext / 2
+        lo, hi = np.searchsorted(xs, cx - half), np.searchsorted(xs, cx + half)
+        cand = pts[order[lo:hi]]
+        scan = cand[np.abs(cand[:, 1] - cy) < half].copy()
+        scan[:, 2] += rng.normal(0, 0.01, scan.shape[0]).astype(np.float32)
+        yield cx, cy, scan
+
+
+def run_c4(a):
+    import torch
+    trg = _pkg.load()
+    from trg_planner_b200 import kernels as K
+    if K.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU fallback")
+    P = trg.MOUNTAIN
+    side = a.side or 4473
+    half = 22.36   # 44.7 m x 44.7 m window of a 0.1 m map = 200 k points
+    pts = trg.terrain.mountain(side, h=0.1, seed=4)
+    ext = side * 0.1
+    t = trg.product(P)
+    t.seed(42)
+    t.set_global_map(pts)
+    w0 = time.perf_counter(); t.init_graph((ext / 2, ext / 2, 0.0)); w1 = time.perf_counter()
+    nn, ne = t.counts()
+    rng = np.random.default_rng(9)
+    lat, sizes = [], []
+    l0 = None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for k, (cx, cy, scan) in enumerate(_scans(pts, ext, a.warmup + a.steps, half, rng, ext / 2 - 50.0)):
+        if k == a.warmup:
+            torch.cuda.synchronize(); l0 = K.launch_count(); e0.record()
+        s0 = time.perf_counter()
+        t.set_local_map(cx, cy, scan)
+        s1 = time.perf_counter()
+        t.update_graph()
+        s2 = time.perf_counter()
+        if k >= a.warmup:
+            lat.append((s1 - s0, s2 - s1)); sizes.append(int(scan.shape[0]))
+    e1.record(); torch.cuda.synchronize()
+    launches = K.launch_count() - l0
+    L = np.array(lat) * 1e3
+    per_scan_ms = float(L.sum(1).mean())
+    cpu = None
+    if not a.no_cpu:
+        F = _pkg.load_oracle()
+        kind = "ref" if F.available("ref") else "port"
+        cs = 1000
+        cp = trg.terrain.mountain(cs, h=0.1, seed=4)
+        o = F.oracle(P, kind=kind); o.seed(42); o.set_global_map(cp)
+        o.init_graph((cs * 0.05, cs * 0.05, 0.0))
+        crng = np.random.default_rng(9)
+        cl = []
+        for cx, cy, scan in _scans(cp, cs * 0.1, 4, half, crng, cs * 0.05 - 4.0):
+            c0 = time.perf_counter(); o.set_local_map(cx, cy, scan); o.update_graph(); cl.append((time.perf_counter() - c0, scan.shape[0]))
+        cms = 1e3 * float(np.mean([x[0] for x in cl[1:]]))
+        cpu = {"value": float(np.mean([x[1] for x in cl[1:]])) / (cms * 1e-3), "unit": "scan points/s", "cores": 1,
+               "kind": "reference" if kind == "ref" else "port", "per_scan_ms": cms,
+               "sample": f"the reference's setLocalMap + updateGraph ({'libtrg_ref.so' if kind == 'ref' else 'restated oracle'}) on a 1 M-point prebuilt "
+                         f"map ({o.counts()[0]} nodes), 3 scans of {int(np.mean([x[1] for x in cl[1:]]))} points; 1 thread; host has {os.cpu_count()} cores"}
+    line = {"metric": "trg_update_scan_points_per_sec", "value": float(np.mean(sizes)) / (per_scan_ms * 1e-3), "unit": "scan points/s",
+            "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": per_scan_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C4 incremental update: {int(np.mean(sizes))}-point scans (44.7 m windows, 2 m apart) against a "
+                                   f"{pts.shape[0]}-point prebuilt mountain map with a {nn}-node TRG; one step = setLocalMap + updateGraph",
+                       "l2": "every scan is a new 3.2 MB cloud; the 320 MB map index is larger than L2"},
+            "per_scan_ms": {"set_local_map": float(L[:, 0].mean()), "update_graph": float(L[:, 1].mean()),
+                            "p50": float(np.median(L.sum(1))), "max": float(L.sum(1).max())},
+            "prebuilt": {"map_points": int(pts.shape[0]), "graph_nodes": nn, "graph_edges": ne, "build_s": w1 - w0},
+            "e2e": {"value": float(np.mean(sizes)) / (per_scan_ms * 1e-3), "unit": "scan points/s",
+                    "h2d_bytes_per_step": int(np.mean(sizes)) * 12, "d2h_bytes_per_step": 0,
+                    "note": "the scan arrives in host memory (TRG::setLocalMap takes a host cloud): value and e2e coincide"},
+            "gpu_launches": int(launches), "device_ms_total": e0.elapsed_time(e1), "cpu_baseline": cpu,
+            "roofline": None, "clocks": None}
+    print(json.dumps(line), flush=True)
+
+
+def run_c5(a):
+    import torch
+    trg = _pkg.load()
+    from trg_planner_b200 import kernels as K
+    if K.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU fallback")
+    P = trg.MOUNTAIN
+    peak, peak_src = _peak()
+    h = 0.1
+    side = a.side or 14143
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    ext = side * h
+    ix = torch.arange(side, device="cuda", dtype=torch.float32)
+    x = (ix[:, None] * h).expand(side, side).reshape(-1) + (torch.rand(side * side, device="cuda", generator=g) - 0.5) * 0.4 * h
+    y = (ix[None, :] * h).expand(side, side).reshape(-1) + (torch.rand(side * side, device="cuda", generator=g) - 0.5) * 0.4 * h
+    u = torch.remainder(x, 40.0)
+    up = torch.where(u < 20.0, u, 40.0 - u)
+    z = torch.floor(up / 0.3) * 0.10 + torch.randn(side * side, device="cuda", generator=g) * 0.005
+    tiles = int(np.ceil(ext / 4.0)) + 1
+    sel = torch.rand((tiles, tiles), device="cuda", generator=g) < 0.10
+    slab = sel[(x / 4.0).long().clamp(0, tiles - 1), (y / 4.0).long().clamp(0, tiles - 1)]
+    xs, ys, zs = x[slab] + 0.013, y[slab] - 0.017, z[slab] + 2.0
+    pts = torch.stack([torch.cat([x, xs]), torch.cat([y, ys]), torch.cat([z, zs])], 1).contiguous()
+    del x, y, z, u, up, slab, xs, ys, zs
+    n = pts.shape[0]
+    torch.cuda.synchronize()
+    crop_ext = min(140.0, ext)
+    crop = pts[(pts[:, 0] < crop_ext) & (pts[:, 1] < crop_ext)].cpu().numpy() if not a.no_cpu else None
+    t0 = time.perf_counter()
+    dm = K.DeviceMap(None, 0.67 * P.robot_size, dev_ptr=pts.data_ptr(), n=n, stride=3)
+    dm.sync()
+    t_idx = time.perf_counter() - t0
+    del pts
+    rng = np.random.default_rng(10)
+    nq_all, ne_all = 10_000_000, 2_000_000
+    q = rng.uniform(2.0, ext - 2.0, size=(nq_all, 2)).astype(np.float32)
+    key = np.floor(q[:, 1] / 0.6).astype(np.int64) * 1_000_000 + np.floor(q[:, 0] / 0.6).astype(np.int64)
+    q = q[np.argsort(key, kind="stable")]
+    dq = torch.from_numpy(q).cuda()
+    out8 = torch.empty(nq_all, dtype=torch.uint8, device="cuda")
+    ang = rng.uniform(0, 2 * np.pi, ne_all)
+    sub = np.sort(rng.choice(nq_all, ne_all, replace=False))
+    p1 = np.column_stack([q[sub], np.zeros(ne_all, np.float32)]).astype(np.float32)
+    p2 = (q[sub] + P.expand_dist * np.stack([np.cos(ang), np.sin(ang)], 1)).astype(np.float32)
+    dp1, dp2 = torch.from_numpy(p1).cuda(), torch.from_numpy(p2).cuda()
+    st8 = torch.empty(ne_all, dtype=torch.uint8, device="cuda")
+    w = torch.empty(ne_all, dtype=torch.float32, device="cuda")
+    dd = torch.empty(ne_all, dtype=torch.float32, device="cuda")
+    rho = n / (ext * ext)
+    o = None
+    if crop is not None:
+        F = _pkg.load_oracle()
+        o = F.oracle(P, kind="ref" if F.available("ref") else "port")
+        o.set_global_map(crop)
+    rows = []
+    l0 = K.launch_count()
+    for r in (0.15, 0.3, 0.6, 1.2, 2.4):
+        nq = nq_all if r <= 0.6 else nq_all // 8
+        ne = ne_all if r <= 0.6 else ne_all // 8
+        for rep in range(a.warmup + a.steps):
+            if rep == a.warmup:
+                K.prof_reset(); K.prof_enable(True)
+            dm.collision_launch(dq.data_ptr(), nq, r, P.height_threshold, P.collision_threshold, out8.data_ptr())
+            dm.edge_eval_launch(dp1.data_ptr(), dp2.data_ptr(), ne, r, P.height_threshold, P.collision_threshold,
+                                st8.data_ptr(), w.data_ptr(), dd.data_ptr())
+            dm.sync()
+        pr = K.prof_collect(); K.prof_enable(False)
+        k_r = np.pi * r * r * rho
+        row = {"radius": r, "pts_in_cylinder": round(k_r, 1)}
+        k4_ms = 0.0
+        for name, v in pr.items():
+            ups = v["units"] / v["ms"] * 1e3
+            if "collision" in name:
+                per = 16 * k_r + 9
+                row["K2"] = dict(kernel=name, queries_per_s=round(ups), alg_gbs=round(ups * per / 1e9, 1), frac_hbm=round(ups * per / 1e9 / peak, 3))
+            elif "edge" in name:
+                k4_ms += v["ms"] / v["launches"]
+        if k4_ms > 0:
+            e_ = P.expand_dist; m = int(np.ceil(e_ / (0.5 * r))); c = 0.5 * e_
+            aa = np.sqrt(c * c + r * r) if c >= r else r
+            per = 16 * (m * k_r + np.pi * aa * aa * rho) + 41
+            row["K4"] = dict(edges_per_s=round(ne / k4_ms * 1e3), alg_gbs=round(ne / k4_ms * 1e3 * per / 1e9, 1),
+                             frac_hbm=round(ne / k4_ms * 1e3 * per / 1e9 / peak, 3))
+        if o is not None:
+            # parity + CPU time of the reference on 10^5 sampled queries inside the crop
+            inside = np.nonzero((q[:nq, 0] < crop_ext - 3.0) & (q[:nq, 1] < crop_ext - 3.0))[0][:100000]
+            if r <= 0.6 and len(inside):
+                sub_q = q[inside]
+                got = out8[:nq].cpu().numpy()[inside]
+                saved = (P.robot_size,)
+                Pr = trg.TrgParams(False, P.expand_dist, float(r), P.sample_num, P.height_threshold, P.collision_threshold,
+                                   P.update_collision_threshold, P.safety_factor, P.goal_tolerance)
+                F = _pkg.load_oracle()
+                orr = F.oracle(Pr, kind="ref" if F.available("ref") else "port")
+                orr.set_global_map(crop)
+                c0 = time.perf_counter(); want = orr.is_collision(sub_q, P.collision_threshold); c1 = time.perf_counter()
+                row["cpu"] = dict(queries=int(len(inside)), queries_per_s=round(len(inside) / (c1 - c0)), mismatches=int((got != want).sum()))
+        rows.append(row)
+    launches = K.launch_count() - l0
+    best = max(rows, key=lambda rw: rw.get("K2", {}).get("frac_hbm", 0))
+    mid = next(rw for rw in rows if rw["radius"] == 0.3)
+    cpu_rows = [rw["cpu"] for rw in rows if "cpu" in rw]
+    line = {"metric": "collision_queries_per_sec", "value": mid["K2"]["queries_per_s"], "unit": "queries/s (r = 0.3 m)",
+            "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic (generated on the GPU)",
+            "config": {"workload": f"C5 stress: {n}-point multi-level terrain (stairs + overhang slabs), K2 / K4 alone, radius sweep "
+                                   f"0.15 .. 2.4 m, 10 M queries / 2 M edges (1/8 of that above 0.6 m), sorted by 0.6 m tile",
+                       "l2": f"map index {dm.info().device_bytes / 1e9:.1f} GB, queries spread over the whole map: far larger than L2"},
+            "map_index": {"points": int(n), "ms": 1e3 * t_idx, "points_per_s": n / t_idx, "alg_gbs": 32 * n / t_idx / 1e9,
+                          "frac_hbm": 32 * n / t_idx / 1e9 / peak},
+            "sweep": rows,
+            "roofline": {"bound": "hbm", "kernel": "k_collision", "achieved": mid["K2"]["alg_gbs"], "peak": peak, "unit": "GB/s",
+                         "frac": mid["K2"]["frac_hbm"], "traffic": None, "peak_source": peak_src, "best_radius": best["radius"],
+                         "best_frac": best.get("K2", {}).get("frac_hbm")},
+            "e2e": {"value": mid["K2"]["queries_per_s"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "note": "kernel-level workload on device-resident inputs (config #5 is a kernel roofline sweep): no host leg"},
+            "cpu_baseline": ({"value": float(np.mean([c["queries_per_s"] for c in cpu_rows])), "unit": "queries/s", "cores": 1, "kind": "reference",
+                              "sample": "TRG::isCollision of the reference on 10^5 of the same queries per radius (<= 0.6 m) over a 2 M-point crop "
+                                        "of the same cloud; mismatches vs the kernel listed per radius under sweep[].cpu",
+                              "mismatches_total": int(sum(c["mismatches"] for c in cpu_rows))} if cpu_rows else None),
+            "gpu_launches": int(launches), "clocks": None}
+    print(json.dumps(line), flush=True)

@@ -297,3 +297,40 @@ def test_edge_cases_empty_tiny_and_far(pkg, K):
         K.DeviceMap(np.zeros((0, 3), np.float32), 0.2)
     with pytest.raises(RuntimeError):
         K.DeviceMap(np.array([[np.nan, 0, 0]], np.float32), 0.2)
+
+
+def _kd_insert_all(xy):
+    """kd_insert2 in a loop (kdtree.c:167-194): go left iff pos[dir] < node.pos[dir], dir alternating x, y."""
+    n = len(xy)
+    lo, hi, par = np.full(n, -1, np.int32), np.full(n, -1, np.int32), np.full(n, -1, np.int32)
+    ax = np.zeros(n, np.uint8)
+    x = xy.tolist()
+    for i in range(1, n):
+        at, a = 0, 0
+        while True:
+            low = x[i][a] < x[at][a]
+            nxt = lo[at] if low else hi[at]
+            if nxt < 0:
+                if low:
+                    lo[at] = i
+                else:
+                    hi[at] = i
+                par[i], ax[i] = at, a ^ 1
+                break
+            at, a = nxt, a ^ 1
+    return lo, hi, par, ax
+
+
+def test_parallel_kdtree_build_equals_sequential_insertion(pkg, K):
+    """The node kd-tree grown on the device (one level per round) is the tree of n sequential insertions:
+    random points, a lattice full of equal coordinates (ties go right), sorted input (a degenerate list)."""
+    rng = np.random.default_rng(5)
+    cases = [rng.uniform(0, 50, size=(30000, 2)).astype(np.float32),
+             (rng.integers(0, 40, size=(20000, 2)) * 0.25).astype(np.float32),
+             np.stack([np.arange(3000, dtype=np.float32), np.zeros(3000, np.float32)], 1),
+             np.zeros((1, 2), np.float32)]
+    for xy in cases:
+        want = _kd_insert_all(xy)
+        got = K.kdtree_build(xy)
+        for a, b, name in zip(got, want, ("lo", "hi", "parent", "axis")):
+            np.testing.assert_array_equal(a, b, err_msg=name)

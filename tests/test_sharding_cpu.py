@@ -17,8 +17,8 @@ def test_tiles_form_one_continuous_heightfield(pkg):
     # heights on both sides of the shared border x = 12 m agree to the terrain's local slope
     la = a[a[:, 0] > 11.85]
     lb = b[b[:, 0] < 12.05]
-    from scipy.spatial import cKDTree
-    d, j = cKDTree(lb[:, :2]).query(la[:, :2])
+    dd = np.hypot(la[:, None, 0] - lb[None, :, 0], la[:, None, 1] - lb[None, :, 1])
+    j, d = dd.argmin(1), dd.min(1)
     near = d < 0.15
     assert near.sum() > 50
     assert np.abs(la[near, 2] - lb[j[near], 2]).max() < 0.25
@@ -121,7 +121,9 @@ def _stitch_worker(rank, world, port, q):
 
     edges, st = sharding.stitch_tiles(dist, torch, torch.device("cpu"), rank, world, pts, g.pos, g.ids, x_lo, x_hi,
                                       P.expand_dist, P.robot_size, edge_eval)
-    q.put((rank, edges, st, g.pos, g.ids, pts))
+    m = sharding.merge_graphs(dist, torch, torch.device("cpu"), rank, world, g, edges)
+    merged = {k: (v.numpy() if hasattr(v, "numpy") else v) for k, v in m.items()}
+    q.put((rank, edges, st, g.pos, g.ids, pts, merged, (g.row_ptr, g.col, g.weight, g.dist)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -198,3 +200,66 @@ def test_stitch_tiles_gloo_world3_middle_tile_has_two_borders(pkg):
         b = np.array([pr[int(v[3])] for v in sel], np.float32)
         assert (np.hypot(a[:, 0] - b[:, 0], a[:, 1] - b[:, 1]) < pkg.MOUNTAIN.expand_dist + 1e-6).all()
         assert (np.abs(a[:, 0] - border) < 1.0).all() and (np.abs(b[:, 0] - border) < 1.0).all()
+
+
+def test_merged_graph_gloo_world2_paths_cross_the_border(pkg):
+    """ONE graph across the ranks: both ranks assemble the same global CSR (local edges in local order, then
+    the stitched ones, both directions), and a shortest path from tile 0 to tile 1 exists on it."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29300 + (os.getpid() % 150)
+    procs = [ctx.Process(target=_stitch_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(2):
+        r = q.get(timeout=300)
+        res[r[0]] = r
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    m0, m1 = res[0][6], res[1][6]
+    for k in ("pos", "state", "row_ptr", "col", "weight", "dist", "node_off"):
+        np.testing.assert_array_equal(m0[k], m1[k], err_msg=k)
+    n0, n1 = len(res[0][4]), len(res[1][4])
+    st = res[0][1]
+    assert m0["n_nodes"] == n0 + n1 and list(m0["node_off"]) == [0, n0, n0 + n1]
+    assert m0["n_edges"] == len(res[0][7][1]) + len(res[1][7][1]) + 2 * len(st)
+    row, col, w, d = m0["row_ptr"], m0["col"], m0["weight"], m0["dist"]
+    assert row[0] == 0 and row[-1] == len(col) and (np.diff(row) >= 0).all() and col.min() >= 0 and col.max() < m0["n_nodes"]
+    # tile-local adjacency survives as the head of every row (ids shifted by the owner's offset)
+    for rank, off in ((0, 0), (1, n0)):
+        lrow, lcol, lw, ld = res[rank][7]
+        for v in (0, len(lrow) // 3, len(lrow) - 2):
+            a, b = lrow[v], lrow[v + 1]
+            np.testing.assert_array_equal(col[row[v + off]: row[v + off] + (b - a)], lcol[a:b] + off)
+            np.testing.assert_array_equal(w[row[v + off]: row[v + off] + (b - a)], lw[a:b])
+    # every stitched edge is there in both directions with its risk and length
+    for e in st[:50]:
+        ga, gb = int(e[1]), n0 + int(e[3])
+        ia = np.nonzero(col[row[ga]:row[ga + 1]] == gb)[0]
+        ib = np.nonzero(col[row[gb]:row[gb + 1]] == ga)[0]
+        assert len(ia) == 1 and len(ib) == 1
+        assert w[row[ga] + ia[0]] == np.float32(e[4]) and d[row[gb] + ib[0]] == np.float32(e[5])
+    # Dijkstra over the merged CSR from the root of tile 0 reaches the far side of tile 1
+    import heapq
+    cost = (np.float32(pkg.MOUNTAIN.safety_factor) * w + 1) * d
+    dist_ = np.full(m0["n_nodes"], np.inf)
+    src = 0
+    dist_[src] = 0.0
+    pq = [(0.0, src)]
+    while pq:
+        du, u = heapq.heappop(pq)
+        if du > dist_[u]:
+            continue
+        for k in range(row[u], row[u + 1]):
+            v = col[k]
+            if m0["state"][v] == -1:
+                continue
+            nd = du + cost[k]
+            if nd < dist_[v]:
+                dist_[v] = nd
+                heapq.heappush(pq, (nd, v))
+    far = np.nonzero(m0["pos"][:, 0] > 24.0)[0]
+    assert len(far) > 10 and np.isfinite(dist_[far]).mean() > 0.9

@@ -7,6 +7,7 @@
 // flagged and resolved on the host by the insertion-order tree.
 #include <algorithm>
 #include <cmath>
+#include <vector>
 
 #include "common.cuh"
 
@@ -182,5 +183,119 @@ extern "C" int trgb_nodes_nearest_launch(const trgb_nodes* g, const float* d_xy,
   k_nodes_nearest<<<grid, 256, 0, st>>>(reinterpret_cast<const float2*>(d_xy), n, g->x0, g->y0, g->cell, g->inv, g->W,
                                         g->H, g->d_head, g->d_xy, g->d_next, g->count, d_idx, d_d2, d_tie);
   TRGB_CUDA(cudaGetLastError());
+  return TRGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Insertion-order 2-D kd-tree of the graph nodes, built in parallel: the tree the reference grows with one
+// kd_insert2 per node in TRG::cleanGraph / addNode (trg.cpp:249, 528-530; kdtree.c:167-194: go left iff
+// pos[dir] < node.pos[dir], dir alternating x, y). Its SHAPE decides which of several in-range nodes
+// TRG::setGoal picks (head of the result list = last node the traversal visits) and how exact distance ties
+// of kd_nearest resolve, so it has to be the reference's tree, not a balanced one.
+// Every node descends from the root at once; nodes that reach the same empty child slot in a round all share
+// the same root path, and the one inserted first (lowest index) is the slot's occupant in the sequential
+// tree: atomicMin decides, the losers step down into the winner's subtree next round. Rounds = tree depth.
+// ------------------------------------------------------------------------------------------------------
+namespace trgb {
+
+__global__ void __launch_bounds__(256) k_kd_claim(int n, const int* __restrict__ at, const unsigned char* __restrict__ side,
+                                                  const unsigned char* __restrict__ placed, int* __restrict__ claim) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (placed[i]) continue;
+    atomicMin(claim + 2 * (size_t)at[i] + side[i], i);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_kd_place(int n, const float2* __restrict__ xy, int* __restrict__ at,
+                                                  unsigned char* __restrict__ side, unsigned char* __restrict__ placed,
+                                                  const int* __restrict__ claim, int* __restrict__ lo, int* __restrict__ hi,
+                                                  int* __restrict__ parent, unsigned char* __restrict__ axis,
+                                                  int* __restrict__ remaining) {
+  int left = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (placed[i]) continue;
+    const int p = at[i];
+    const int sd = side[i];
+    const int w = claim[2 * (size_t)p + sd];
+    const unsigned char ax = axis[p] ^ 1;
+    if (w == i) {
+      placed[i] = 1;
+      parent[i] = p;
+      axis[i] = ax;
+      if (sd) hi[p] = i; else lo[p] = i;
+    } else {
+      // the slot went to an earlier node: continue below it (its split axis is the parent's, flipped)
+      const float2 me = xy[i], ww = xy[w];
+      const bool low = ax ? (me.y < ww.y) : (me.x < ww.x);
+      at[i] = w;
+      side[i] = low ? 0 : 1;
+      ++left;
+    }
+  }
+  if (left) atomicAdd(remaining, left);
+}
+
+}  // namespace trgb
+
+// xy: n (x, y) pairs in insertion order. Outputs (host, n entries each): children lo / hi (-1 = none), parent
+// (-1 for the root) and split axis of every node — what n successive kd_insert2 calls would have built.
+extern "C" int trgb_kdtree_build(const float* xy, int64_t n, int32_t* lo, int32_t* hi, int32_t* parent, uint8_t* axis) {
+  TRGB_ARG(xy && lo && hi && parent && axis && n > 0 && n < (1ll << 31), "bad argument");
+  trgb::tune_mempool_once();
+  cudaStream_t st = 0;
+  float2* d_xy = nullptr; int *d_at = nullptr, *d_claim = nullptr, *d_lo = nullptr, *d_hi = nullptr, *d_par = nullptr, *d_rem = nullptr;
+  unsigned char *d_side = nullptr, *d_placed = nullptr, *d_axis = nullptr;
+  const size_t N = (size_t)n;
+  TRGB_CUDA(cudaMallocAsync((void**)&d_xy, N * sizeof(float2), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&d_at, N * sizeof(int), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&d_claim, 2 * N * sizeof(int), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&d_lo, N * sizeof(int), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&d_hi, N * sizeof(int), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&d_par, N * sizeof(int), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&d_rem, sizeof(int), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&d_side, N, st));
+  TRGB_CUDA(cudaMallocAsync((void**)&d_placed, N, st));
+  TRGB_CUDA(cudaMallocAsync((void**)&d_axis, N, st));
+  TRGB_CUDA(cudaMemcpyAsync(d_xy, xy, N * sizeof(float2), cudaMemcpyHostToDevice, st));
+  TRGB_CUDA(cudaMemsetAsync(d_claim, 0x7f, 2 * N * sizeof(int), st));
+  TRGB_CUDA(cudaMemsetAsync(d_lo, 0xff, N * sizeof(int), st));
+  TRGB_CUDA(cudaMemsetAsync(d_hi, 0xff, N * sizeof(int), st));
+  TRGB_CUDA(cudaMemsetAsync(d_par, 0xff, N * sizeof(int), st));
+  TRGB_CUDA(cudaMemsetAsync(d_placed, 0, N, st));
+  TRGB_CUDA(cudaMemsetAsync(d_axis, 0, N, st));
+  TRGB_CUDA(cudaMemsetAsync(d_at, 0, N * sizeof(int), st));
+  // the root is node 0; everybody else starts at its low / high slot
+  const unsigned char one = 1;
+  TRGB_CUDA(cudaMemcpyAsync(d_placed, &one, 1, cudaMemcpyHostToDevice, st));
+  {
+    std::vector<unsigned char> side0(N);
+    for (size_t i = 0; i < N; ++i) side0[i] = xy[2 * i] < xy[0] ? 0 : 1;  // axis 0 at the root
+    TRGB_CUDA(cudaMemcpyAsync(d_side, side0.data(), N, cudaMemcpyHostToDevice, st));
+    TRGB_CUDA(cudaStreamSynchronize(st));
+  }
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8));
+  int remaining = (int)n - 1;
+  int rounds = 0;
+  while (remaining > 0) {
+    // a few rounds per host check (the count of the last one decides)
+    for (int k = 0; k < 8; ++k) {
+      TRGB_CUDA(cudaMemsetAsync(d_rem, 0, sizeof(int), st));
+      ProfScope ps("k_kd_round", st, (double)remaining);
+      k_kd_claim<<<grid, 256, 0, st>>>((int)n, d_at, d_side, d_placed, d_claim);
+      k_kd_place<<<grid, 256, 0, st>>>((int)n, d_xy, d_at, d_side, d_placed, d_claim, d_lo, d_hi, d_par, d_axis, d_rem);
+      ++rounds;
+    }
+    TRGB_CUDA(cudaMemcpyAsync(&remaining, d_rem, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TRGB_CUDA(cudaStreamSynchronize(st));
+    if (rounds > 100000) { set_error("kdtree_build: no progress"); return TRGB_E_STATE; }
+  }
+  TRGB_CUDA(cudaMemcpyAsync(lo, d_lo, N * sizeof(int), cudaMemcpyDeviceToHost, st));
+  TRGB_CUDA(cudaMemcpyAsync(hi, d_hi, N * sizeof(int), cudaMemcpyDeviceToHost, st));
+  TRGB_CUDA(cudaMemcpyAsync(parent, d_par, N * sizeof(int), cudaMemcpyDeviceToHost, st));
+  TRGB_CUDA(cudaMemcpyAsync(axis, d_axis, N, cudaMemcpyDeviceToHost, st));
+  TRGB_CUDA(cudaStreamSynchronize(st));
+  for (void* p : {(void*)d_xy, (void*)d_at, (void*)d_claim, (void*)d_lo, (void*)d_hi, (void*)d_par, (void*)d_rem, (void*)d_side,
+                  (void*)d_placed, (void*)d_axis})
+    cudaFreeAsync(p, st);
   return TRGB_OK;
 }

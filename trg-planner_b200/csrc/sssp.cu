@@ -38,6 +38,7 @@ struct trgb_graph {
   size_t label_bytes = 0, queue_bytes = 0, bits_bytes = 0;  // allocated sizes
   int device = 0;
   cudaStream_t stream = nullptr;
+  int64_t relaxed_edges = 0, queries = 0;  // totals over the handle's life (k_sssp roofline: 20 B per relaxed edge)
 };
 
 namespace trgb {
@@ -78,7 +79,7 @@ struct SsspOut {
   int32_t* path_len;   // per query length
   int32_t* path_ids;   // ids, start..goal
   long long capacity;
-  unsigned long long* cursor;  // [0] = path write cursor, [1] = next query
+  unsigned long long* cursor;  // [0] = path write cursor, [1] = next query, [2] = edges relaxed (20 B each)
 };
 
 __global__ void __launch_bounds__(kSsspThreads) k_sssp(
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(kSsspThreads) k_sssp(
   __shared__ int s_plen;
   __shared__ long long s_poff;
   __shared__ float s_stage[2 * kSsspThreads];
+  __shared__ unsigned long long s_relax;
 
   const int tid = threadIdx.x;
   const int grp = tid / kGroup, gl = tid % kGroup;
@@ -119,6 +121,7 @@ __global__ void __launch_bounds__(kSsspThreads) k_sssp(
     __syncthreads();
     int32_t *qcur = q0, *qnxt = q0 + n, *qfar = q0 + 2 * (size_t)n, *qfar2 = q0 + 3 * (size_t)n;
     if (tid == 0) {
+      s_relax = 0ull;
       label[start] = make_label(0.f, start);
       qcur[0] = start;
       s_cnt[0] = 1; s_cnt[1] = 0; s_cnt[2] = 0; s_cnt[3] = 0;
@@ -139,6 +142,7 @@ __global__ void __launch_bounds__(kSsspThreads) k_sssp(
         __syncthreads();
         const float thr = s_thr;
         const float best = label_g(__ldcg(label + goal));
+        unsigned my_relax = 0;
         for (int k = grp; k < ncur; k += ngrp) {
           const int u = qcur[k];
           const float gu = label_g(__ldcg(label + u));
@@ -148,6 +152,7 @@ __global__ void __launch_bounds__(kSsspThreads) k_sssp(
           for (int64_t e = e0 + gl; e < e1; e += kGroup) {
             const int v = __ldg(col + e);
             if (__ldg(state + v) == -1) continue;  // trg.cpp:670 skip Invalid dst
+            ++my_relax;
             const float ng = __fadd_rn(gu, __ldg(cost + e));
             const unsigned long long cand = make_label(ng, u);
             const unsigned long long old = atomicMin(label + v, cand);
@@ -161,6 +166,8 @@ __global__ void __launch_bounds__(kSsspThreads) k_sssp(
             }
           }
         }
+        my_relax = __reduce_add_sync(FULL, my_relax);
+        if ((tid & 31) == 0 && my_relax) atomicAdd(&s_relax, (unsigned long long)my_relax);
         __syncthreads();
         if (tid == 0) { s_cnt[0] = s_cnt[1]; s_cnt[1] = 0; }
         int32_t* t = qcur; qcur = qnxt; qnxt = t;
@@ -254,6 +261,7 @@ __global__ void __launch_bounds__(kSsspThreads) k_sssp(
       out.cost[qi] = ok ? s_best : 0.f;
       out.path_length[qi] = ok ? sum_d : 0.f;
       out.avg_risk[qi] = ok ? __fdiv_rn(sum_w, (float)plen) : 0.f;
+      atomicAdd(out.cursor + 2, s_relax);
       s_poff = (long long)atomicAdd(out.cursor, (unsigned long long)plen);
       out.path_off[qi] = s_poff;
       out.path_len[qi] = plen;
@@ -417,8 +425,8 @@ extern "C" int trgb_sssp_batch(trgb_graph* g, const int32_t* start_ids, const in
   }
   // slots: enough CTAs to fill the machine, bounded by the batch and by ~24 GB of scratch
   const size_t per_slot = (size_t)g->n * (8 + 16) + ((size_t)g->n / 4 + 8);
-  int want = (int)std::min<int64_t>(nq, (int64_t)sm_count() * 4);
-  want = (int)std::min<size_t>((size_t)want, std::max<size_t>(1, ((size_t)24 << 30) / per_slot));
+  int want = (int)std::min<int64_t>(nq, (int64_t)sm_count() * 8);
+  want = (int)std::min<size_t>((size_t)want, std::max<size_t>(1, ((size_t)48 << 30) / per_slot));
   int rc = ensure_slots(g, want);
   if (rc) return rc;
 
@@ -428,11 +436,11 @@ extern "C" int trgb_sssp_batch(trgb_graph* g, const int32_t* start_ids, const in
   DALLOC(d_s, nq * sizeof(int32_t)); DALLOC(d_g, nq * sizeof(int32_t));
   DALLOC(d_found, nq); DALLOC(d_cost, nq * sizeof(float)); DALLOC(d_len, nq * sizeof(float));
   DALLOC(d_risk, nq * sizeof(float)); DALLOC(d_off, nq * sizeof(int64_t)); DALLOC(d_plen, nq * sizeof(int32_t));
-  DALLOC(d_ids, (size_t)path_ids_capacity * sizeof(int32_t)); DALLOC(d_cur, 2 * sizeof(unsigned long long));
+  DALLOC(d_ids, (size_t)path_ids_capacity * sizeof(int32_t)); DALLOC(d_cur, 4 * sizeof(unsigned long long));
 #undef DALLOC
   TRGB_CUDA(cudaMemcpyAsync(d_s.p, start_ids, nq * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   TRGB_CUDA(cudaMemcpyAsync(d_g.p, goal_ids, nq * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  TRGB_CUDA(cudaMemsetAsync(d_cur.p, 0, 2 * sizeof(unsigned long long), st));
+  TRGB_CUDA(cudaMemsetAsync(d_cur.p, 0, 4 * sizeof(unsigned long long), st));
   SsspOut o;
   o.found = (uint8_t*)d_found.p; o.cost = (float*)d_cost.p; o.path_length = (float*)d_len.p;
   o.avg_risk = (float*)d_risk.p; o.path_off = (int64_t*)d_off.p; o.path_len = (int32_t*)d_plen.p;
@@ -448,7 +456,7 @@ extern "C" int trgb_sssp_batch(trgb_graph* g, const int32_t* start_ids, const in
   TRGB_CUDA(cudaGetLastError());
   std::vector<int64_t> off(nq);
   std::vector<int32_t> plen(nq);
-  unsigned long long cursor[2] = {0, 0};
+  unsigned long long cursor[4] = {0, 0, 0, 0};
   TRGB_CUDA(cudaMemcpyAsync(found, d_found.p, nq, cudaMemcpyDeviceToHost, st));
   TRGB_CUDA(cudaMemcpyAsync(cost, d_cost.p, nq * sizeof(float), cudaMemcpyDeviceToHost, st));
   TRGB_CUDA(cudaMemcpyAsync(path_length, d_len.p, nq * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -458,6 +466,8 @@ extern "C" int trgb_sssp_batch(trgb_graph* g, const int32_t* start_ids, const in
   TRGB_CUDA(cudaMemcpyAsync(cursor, d_cur.p, sizeof(cursor), cudaMemcpyDeviceToHost, st));
   TRGB_CUDA(cudaStreamSynchronize(st));
   const int64_t total = (int64_t)cursor[0];
+  g->relaxed_edges += (int64_t)cursor[2];
+  g->queries += nq;
   if (total > path_ids_capacity) {
     path_offsets[nq] = total;
     set_error("sssp_batch: path_ids buffer too small; needed size returned in path_offsets[n]");
@@ -472,5 +482,12 @@ extern "C" int trgb_sssp_batch(trgb_graph* g, const int32_t* start_ids, const in
     w += plen[i];
   }
   path_offsets[nq] = w;
+  return TRGB_OK;
+}
+
+extern "C" int trgb_graph_stats(const trgb_graph* g, int64_t* relaxed_edges, int64_t* queries) {
+  TRGB_ARG(g, "null handle");
+  if (relaxed_edges) *relaxed_edges = g->relaxed_edges;
+  if (queries) *queries = g->queries;
   return TRGB_OK;
 }

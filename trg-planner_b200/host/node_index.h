@@ -101,6 +101,22 @@ class OrderTree2D {
     }
   }
 
+  // Adopt a tree built elsewhere (trgb_kdtree_build: the same insertion-order tree, grown on the device).
+  void adopt(const float* x, const float* y, int n, std::vector<int>&& lo, std::vector<int>&& hi, std::vector<int>&& parent,
+             std::vector<uint8_t>&& axis) {
+    clear();
+    if (n <= 0) return;
+    x_.assign(x, x + n); y_.assign(y, y + n);
+    lo_ = std::move(lo); hi_ = std::move(hi); parent_ = std::move(parent); axis_ = std::move(axis);
+    payload_.resize(n);
+    bmin_[0] = bmax_[0] = x[0]; bmin_[1] = bmax_[1] = y[0]; have_box_ = true;
+    for (int i = 0; i < n; ++i) {
+      payload_[i] = i;
+      bmin_[0] = std::fmin(bmin_[0], x[i]); bmax_[0] = std::fmax(bmax_[0], x[i]);
+      bmin_[1] = std::fmin(bmin_[1], y[i]); bmax_[1] = std::fmax(bmax_[1], y[i]);
+    }
+  }
+
   // Order the given tree nodes (indices = insertion order) the way kd_nearest_range2's result
   // iterator yields them for a query at (qx, qy) whose range contains them all: the traversal
   // (kdtree.c:270-301) is pre-order, query-side child first, and results are PREPENDED, so the

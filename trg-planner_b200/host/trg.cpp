@@ -361,7 +361,17 @@ void TRG::ensureTree(trgStruct& g) {
   if (n >= 256 && (g.tree_built == 0 || pending > 20000)) {
     std::vector<float> xs(n), ys(n);
     for (size_t i = 0; i < n; ++i) { xs[i] = g.node_seq[i]->pos_.x(); ys[i] = g.node_seq[i]->pos_.y(); }
-    g.node_tree.build_bulk(xs.data(), ys.data(), (int)n);
+    if (n >= 20000 && trgb_device_count() > 0) {
+      // large graph: the same tree, grown on the device one level per round (a few ms instead of ~50)
+      std::vector<float> xy(2 * n);
+      for (size_t i = 0; i < n; ++i) { xy[2 * i] = xs[i]; xy[2 * i + 1] = ys[i]; }
+      std::vector<int> lo(n), hi(n), par(n);
+      std::vector<uint8_t> ax(n);
+      K(trgb_kdtree_build(xy.data(), (int64_t)n, lo.data(), hi.data(), par.data(), ax.data()), "trgb_kdtree_build");
+      g.node_tree.adopt(xs.data(), ys.data(), (int)n, std::move(lo), std::move(hi), std::move(par), std::move(ax));
+    } else {
+      g.node_tree.build_bulk(xs.data(), ys.data(), (int)n);
+    }
     g.tree_built = n;
     return;
   }
@@ -1444,6 +1454,7 @@ void TRG::updateGraph() {  // trg.cpp:456-489
 void TRG::invalidateDeviceGraph() {
   if (dev_graph_) trgb_graph_destroy(dev_graph_);
   dev_graph_ = nullptr;
+  dev_graph_relaxed_ = 0;
   dev_graph_nodes_.clear();
 }
 
@@ -1488,55 +1499,62 @@ void TRG::ensureDeviceGraph() {
   K(trgb_graph_upload(&dev_graph_, &desc), "trgb_graph_upload");
 }
 
+// TRG::setGoal (trg.cpp:537-565) without the side effect: the goal node and whether it is "known".
+// Read-only on the graph once the order tree and the hash grid are current (ensureTree /
+// ensureGridBuilt), so a batch of queries snaps on several threads.
+std::pair<TRG::Node*, bool> TRG::snapGoal(trgStruct& g, const Eigen::Vector3f& goal) {
+  static thread_local std::vector<Node*> res;
+  rangeNodesOrdered(g, goal.x(), goal.y(), param_.robot_size, res);
+  if (!res.empty()) return {res[0], true};  // head of the kd result list = last node the traversal visited
+  // Reference (:543-553): linear scan over the node map, strict `<` on dist = sqrt(dx^2+dy^2),
+  // i.e. the first node IN MAP ITERATION ORDER among those whose rounded dist is minimal. The
+  // grid finds the minimal dist^2; every node whose sqrtf equals the minimal dist is a
+  // candidate (several dist^2 values can round to one dist), ranked by iteration order.
+  Node* out = nullptr;
+  auto nn = g.node_grid.nearest(goal.x(), goal.y());
+  if (nn.entry >= 0) {
+    const float min_dist = sqrtf(nn.d2);
+    float d2max = nn.d2;
+    for (int k = 0; k < 8; ++k) {
+      const float up = std::nextafter(d2max, std::numeric_limits<float>::infinity());
+      if (sqrtf(up) != min_dist) break;
+      d2max = up;
+    }
+    int n_cand = 0;
+    Node* only = nullptr;
+    const float reach = min_dist * 1.001f + 1e-4f;
+    g.node_grid.for_each_within_d2(goal.x(), goal.y(), d2max, reach, [&](int e) { ++n_cand; only = g.node_seq[e]; });
+    if (n_cand == 1) {
+      out = only;
+    } else {
+      // rare: rank the candidates by map iteration order (built once per graph state)
+      std::lock_guard<std::mutex> lk(iter_rank_mx_);
+      if (g.iter_rank.size() != g.nodes.size()) {
+        g.iter_rank.clear();
+        g.iter_rank.reserve(g.nodes.size());
+        size_t k = 0;
+        for (auto& node : g.nodes) g.iter_rank[node.second] = k++;
+      }
+      size_t best = std::numeric_limits<size_t>::max();
+      g.node_grid.for_each_within_d2(goal.x(), goal.y(), d2max, reach, [&](int e) {
+        Node* c = g.node_seq[e];
+        const size_t rk = g.iter_rank.at(c);
+        if (rk < best) { best = rk; out = c; }
+      });
+    }
+  }
+  return {out, false};
+}
+
 void TRG::setGoalUnlocked(Eigen::Vector3f& goal) {  // trg.cpp:537-565
   trgStruct& g = *trgMap_["global"];
   goal_.pose3d = goal;
   goal_.pose2d = goal.head(2);
-  static thread_local std::vector<Node*> res;
-  rangeNodesOrdered(g, goal.x(), goal.y(), param_.robot_size, res);
-  if (res.empty()) {
-    // Reference (:543-553): linear scan over the node map, strict `<` on dist = sqrt(dx^2+dy^2),
-    // i.e. the first node IN MAP ITERATION ORDER among those whose rounded dist is minimal. The
-    // grid finds the minimal dist^2; every node whose sqrtf equals the minimal dist is a
-    // candidate (several dist^2 values can round to one dist), ranked by iteration order.
-    goal_.node = nullptr;
-    ensureGridBuilt(g);
-    auto nn = g.node_grid.nearest(goal.x(), goal.y());
-    if (nn.entry >= 0) {
-      const float min_dist = sqrtf(nn.d2);
-      float d2max = nn.d2;
-      for (int k = 0; k < 8; ++k) {
-        const float up = std::nextafter(d2max, std::numeric_limits<float>::infinity());
-        if (sqrtf(up) != min_dist) break;
-        d2max = up;
-      }
-      int n_cand = 0;
-      Node* only = nullptr;
-      const float reach = min_dist * 1.001f + 1e-4f;
-      g.node_grid.for_each_within_d2(goal.x(), goal.y(), d2max, reach, [&](int e) { ++n_cand; only = g.node_seq[e]; });
-      if (n_cand == 1) {
-        goal_.node = only;
-      } else {
-        // rare: rank the candidates by map iteration order (built once per graph state)
-        if (g.iter_rank.size() != g.nodes.size()) {
-          g.iter_rank.clear();
-          g.iter_rank.reserve(g.nodes.size());
-          size_t k = 0;
-          for (auto& node : g.nodes) g.iter_rank[node.second] = k++;
-        }
-        size_t best = std::numeric_limits<size_t>::max();
-        g.node_grid.for_each_within_d2(goal.x(), goal.y(), d2max, reach, [&](int e) {
-          Node* c = g.node_seq[e];
-          const size_t rk = g.iter_rank.at(c);
-          if (rk < best) { best = rk; goal_.node = c; }
-        });
-      }
-    }
-    goal_.isKnown = false;
-  } else {
-    goal_.node    = res[0];  // head of the kd result list = last node the traversal visited
-    goal_.isKnown = true;
-  }
+  ensureTree(g);
+  ensureGridBuilt(g);
+  const auto r = snapGoal(g, goal);
+  goal_.node    = r.first;
+  goal_.isKnown = r.second;
 }
 
 void TRG::setGoal(Eigen::Vector3f& goal) { setGoalUnlocked(goal); }
@@ -1604,8 +1622,10 @@ void TRG::planSafePathBatch(const float* queries, int64_t n, PathBatch& out) {
   {
     // per-graph preparation, three independent pieces side by side: CSR build + upload (this
     // thread), order tree for goal snapping, hash grid for start snapping
-    auto f_tree = std::async(std::launch::async, [&] { ensureTree(g); });
-    auto f_grid = std::async(std::launch::async, [&] { ensureGridBuilt(g); });
+    std::atomic<int64_t> us_tree{0}, us_grid{0};
+    auto f_tree = std::async(std::launch::async, [&] { auto a = Clock::now(); ensureTree(g); us_tree = (int64_t)(1e6 * since(a)); });
+    auto f_grid = std::async(std::launch::async, [&] { auto a = Clock::now(); ensureGridBuilt(g); us_grid = (int64_t)(1e6 * since(a)); });
+    auto tc = Clock::now();
     try {
       ensureDeviceGraph();
     } catch (...) {
@@ -1613,20 +1633,43 @@ void TRG::planSafePathBatch(const float* queries, int64_t n, PathBatch& out) {
       f_grid.wait();
       throw;
     }
+    stat_["us_prep_csr"] += (int64_t)(1e6 * since(tc));
     f_tree.get();
     f_grid.get();
+    stat_["us_prep_tree"] += us_tree.load();
+    stat_["us_prep_grid"] += us_grid.load();
   }
   secs_["plan_prep"] = since(t0);
   std::vector<int32_t> s(n), t(n);
-  for (int64_t i = 0; i < n; ++i) {
-    const float* q = queries + 5 * i;
-    Eigen::Vector3f goal(q[2], q[3], q[4]);
-    setGoalUnlocked(goal);
-    Node* st = nearestNode(g, q[0], q[1]);
-    s[i] = st->id_;
-    t[i] = goal_.node->id_;
-    out.goal_known[i] = goal_.isKnown ? 1 : 0;
-    out.direct_dist[i] = norm2(goal_.node->pos_.x() - st->pos_.x(), goal_.node->pos_.y() - st->pos_.y());
+  {
+    // start / goal snapping (trg.cpp:611-616): independent per query, read-only on the graph -> helper threads
+    std::vector<Node*> gn((size_t)n, nullptr);
+    auto snap = [&](int64_t b, int64_t e) {
+      for (int64_t i = b; i < e; ++i) {
+        const float* q = queries + 5 * i;
+        const auto r = snapGoal(g, Eigen::Vector3f(q[2], q[3], q[4]));
+        Node* st = nearestNode(g, q[0], q[1]);
+        gn[(size_t)i] = r.first;
+        s[i] = st->id_;
+        t[i] = r.first->id_;
+        out.goal_known[i] = r.second ? 1 : 0;
+        out.direct_dist[i] = norm2(r.first->pos_.x() - st->pos_.x(), r.first->pos_.y() - st->pos_.y());
+      }
+    };
+    const int threads = n >= 64 ? trg_b200::thread_budget() : 1;
+    if (threads <= 1) {
+      snap(0, n);
+    } else {
+      std::vector<std::future<void>> jobs;
+      for (int k = 0; k < threads; ++k) jobs.push_back(std::async(std::launch::async, snap, n * k / threads, n * (k + 1) / threads));
+      for (auto& j : jobs) j.get();
+    }
+    // goal_ ends as the reference leaves it after the last query of the batch
+    const float* q = queries + 5 * (n - 1);
+    goal_.pose3d = Eigen::Vector3f(q[2], q[3], q[4]);
+    goal_.pose2d = Eigen::Vector2f(q[2], q[3]);
+    goal_.node = gn[(size_t)n - 1];
+    goal_.isKnown = out.goal_known[n - 1] != 0;
   }
   secs_["plan_snap"] = since(t0);
   size_t cap = std::max<size_t>((size_t)1 << 20, (size_t)n * 1024);
@@ -1641,6 +1684,13 @@ void TRG::planSafePathBatch(const float* queries, int64_t n, PathBatch& out) {
   }
   K(rc, "trgb_sssp_batch");
   out.node_ids.resize((size_t)out.offsets[n]);
+  {
+    int64_t relaxed = 0, nq_total = 0;
+    trgb_graph_stats(dev_graph_, &relaxed, &nq_total);
+    stat_["sssp_relaxed_edges"] += relaxed - dev_graph_relaxed_;
+    stat_["sssp_queries"] += n;
+    dev_graph_relaxed_ = relaxed;
+  }
   secs_["plan_batch"] = since(t0);
 }
 

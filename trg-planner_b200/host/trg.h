@@ -16,6 +16,7 @@
 #ifndef TRG_PLANNER_B200_HOST_TRG_H_
 #define TRG_PLANNER_B200_HOST_TRG_H_
 
+#include <atomic>
 #include <cstdint>
 #include <deque>
 #include <future>
@@ -243,6 +244,8 @@ class TRG {
   void  rewindPools();
   size_t node_used_ = 0, edge_used_ = 0;  // pool cursors
   void setGoalUnlocked(Eigen::Vector3f& goal);
+  std::pair<Node*, bool> snapGoal(trgStruct& g, const Eigen::Vector3f& goal);
+  std::mutex iter_rank_mx_;
   void runExpansion(const std::vector<Node*>& roots, trgStruct& g);
   // initGraph fast path (trg_device_build.cpp): expandGraph(0) as a device-resident BFS (K9) followed
   // by cleanGraph(false), materialised straight into the cleaned containers. false = not applicable
@@ -255,6 +258,7 @@ class TRG {
 
   std::unique_ptr<trg_b200::DeviceSession> dev_;
   trgb_graph* dev_graph_ = nullptr;
+  int64_t dev_graph_relaxed_ = 0;  // edges relaxed by the handle so far (already booked in stat_)
   std::vector<Node*> dev_graph_nodes_;  // row -> node of the uploaded CSR
   std::deque<Node> node_pool_;
   std::deque<Edge> edge_pool_;
@@ -262,7 +266,7 @@ class TRG {
   std::unordered_map<std::string, int64_t> stat_;
   std::vector<int32_t> last_path_ids_;
   double  us_draws_ = 0;
-  int64_t n_node_ties_ = 0;
+  std::atomic<int64_t> n_node_ties_{0};
 
  public:
   // [+] tuning knobs of the wavefront scheduler (defaults are fine; exposed for benchmarks)

@@ -128,6 +128,19 @@ def voxel_filter(xyz: np.ndarray, leaf: float) -> np.ndarray:
     return out[: n.value].copy()
 
 
+def kdtree_build(xy: np.ndarray):
+    """Insertion-order 2-D kd-tree of the graph nodes grown on the device (trg.cpp:249, 528-530):
+    children lo / hi, parent and split axis per node."""
+    a = np.ascontiguousarray(xy, np.float32)
+    n = a.shape[0]
+    lo, hi, par = (np.empty(n, np.int32) for _ in range(3))
+    ax = np.empty(n, np.uint8)
+    L = lib()
+    L.trgb_kdtree_build.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, _vp]
+    _chk(L.trgb_kdtree_build(_p(a), n, _p(lo), _p(hi), _p(par), _p(ax)), "trgb_kdtree_build")
+    return lo, hi, par, ax
+
+
 class DeviceMap:
     """K1: device cell index over one point cloud (replaces the kd_insert2 loop, trg.cpp:185-188)."""
 
@@ -208,6 +221,51 @@ class DeviceMap:
         prm = EdgeParams(robot_size, height_thr, collision_thr)
         _chk(lib().trgb_edge_eval_launch(self.h, _vp(d_p1), _vp(d_p2), n, C.byref(prm), _vp(d_stage), _vp(d_w),
                                          _vp(d_dist), _vp(d_npts) if d_npts else None), "trgb_edge_eval_launch")
+
+
+class DeviceNodeGrid:
+    """K5: device grid over graph nodes; batched exact nearest node (kd_nearest2 on the node tree, trg.cpp:615).
+    `pos`: torch tensor (n, >= 2) on the device, or a numpy array."""
+
+    def __init__(self, pos, robot_size: float):
+        import torch
+        L = lib()
+        L.trgb_nodes_create.argtypes = [C.POINTER(_vp), C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]
+        L.trgb_nodes_destroy.argtypes = [_vp]
+        L.trgb_nodes_destroy.restype = None
+        L.trgb_nodes_append_launch.argtypes = [_vp, _vp, C.c_int64, _vp]
+        L.trgb_nodes_nearest_launch.argtypes = [_vp, _vp, C.c_int64, _vp, _vp, _vp, _vp]
+        p = pos if hasattr(pos, "is_cuda") else torch.from_numpy(np.ascontiguousarray(pos, np.float32))
+        self.xy = p[:, :2].to("cuda", torch.float32).contiguous()
+        lo, hi = self.xy.min(0).values.cpu().numpy(), self.xy.max(0).values.cpu().numpy()
+        self.h = _vp()
+        _chk(L.trgb_nodes_create(C.byref(self.h), float(lo[0]) - 1.0, float(lo[1]) - 1.0, float(hi[0]) + 1.0, float(hi[1]) + 1.0,
+                                 1.5 * float(robot_size)), "trgb_nodes_create")
+        _chk(L.trgb_nodes_append_launch(self.h, _vp(self.xy.data_ptr()), self.xy.shape[0], None), "trgb_nodes_append_launch")
+        torch.cuda.synchronize()
+
+    def nearest(self, xy: np.ndarray) -> np.ndarray:
+        import torch
+        q = torch.from_numpy(np.ascontiguousarray(xy, np.float32)).cuda()
+        n = q.shape[0]
+        idx = torch.empty(n, dtype=torch.int32, device="cuda")
+        d2 = torch.empty(n, dtype=torch.float32, device="cuda")
+        tie = torch.empty(n, dtype=torch.uint8, device="cuda")
+        _chk(lib().trgb_nodes_nearest_launch(self.h, _vp(q.data_ptr()), n, _vp(idx.data_ptr()), _vp(d2.data_ptr()),
+                                             _vp(tie.data_ptr()), None), "trgb_nodes_nearest_launch")
+        torch.cuda.synchronize()
+        return idx.cpu().numpy()
+
+    def close(self):
+        if self.h:
+            lib().trgb_nodes_destroy(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class DeviceGraph:

@@ -55,16 +55,36 @@ def allgather_boundary(dist, torch, pos_sel: np.ndarray, ids_sel: np.ndarray, de
 
 def cross_tile_candidates(mine_pos: np.ndarray, other_pos: np.ndarray, max_dist: float):
     """Pairs (i, j) of boundary nodes from two neighbouring tiles closer than `max_dist` in 2-D:
-    the candidate stitching edges (to be validated with the batched edge kernel)."""
+    the candidate stitching edges (to be validated with the batched edge kernel). Cell hash on a
+    max_dist grid: a node only meets the nodes of the 3 x 3 cells around it."""
     if mine_pos.shape[0] == 0 or other_pos.shape[0] == 0:
         return np.zeros((0, 2), np.int64)
-    from scipy.spatial import cKDTree
-    t = cKDTree(other_pos[:, :2])
-    pairs = []
-    for i, nb in enumerate(t.query_ball_point(mine_pos[:, :2], max_dist)):
-        for j in nb:
-            pairs.append((i, j))
-    return np.asarray(pairs, np.int64).reshape(-1, 2)
+    a, b = np.asarray(mine_pos[:, :2], np.float64), np.asarray(other_pos[:, :2], np.float64)
+    org = np.minimum(a.min(0), b.min(0)) - max_dist
+    ca, cb = np.floor((a - org) / max_dist).astype(np.int64), np.floor((b - org) / max_dist).astype(np.int64)
+    W = int(max(ca[:, 0].max(), cb[:, 0].max())) + 3
+    kb = cb[:, 1] * W + cb[:, 0]
+    order = np.argsort(kb, kind="stable")
+    kb_sorted = kb[order]
+    out_i, out_j = [], []
+    idx_a = np.arange(a.shape[0])
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            key = (ca[:, 1] + dy) * W + (ca[:, 0] + dx)
+            lo, hi = np.searchsorted(kb_sorted, key, "left"), np.searchsorted(kb_sorted, key, "right")
+            cnt = hi - lo
+            if not cnt.any():
+                continue
+            ii = np.repeat(idx_a, cnt)
+            off = np.arange(cnt.sum()) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+            jj = order[np.repeat(lo, cnt) + off]
+            d = a[ii] - b[jj]
+            keep = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) <= max_dist * max_dist
+            out_i.append(ii[keep]); out_j.append(jj[keep])
+    if not out_i:
+        return np.zeros((0, 2), np.int64)
+    pairs = np.stack([np.concatenate(out_i), np.concatenate(out_j)], 1).astype(np.int64)
+    return pairs[np.lexsort((pairs[:, 1], pairs[:, 0]))]
 
 
 def allgather_rows(dist, torch, rows: np.ndarray, device) -> list[np.ndarray]:
@@ -174,12 +194,130 @@ def stitch_tiles(dist, torch, device, rank: int, world: int, tile_pts: np.ndarra
             idb = np.ascontiguousarray(b[:, 3]).view(np.int32)[pairs[ok, 1]]
             mine = np.column_stack([np.full(ok.size, rank), ida, np.full(ok.size, rank + 1), idb,
                                     np.asarray(w)[ok], np.asarray(d)[ok]]).astype(np.float64)
-    # share the stitched edges (float32 payload: ids < 2^24 exact; larger ids would need the bit-cast trick)
-    got = allgather_rows(dist, torch, mine.astype(np.float32), device)
+    # share the stitched edges (float32 payload; the two id columns travel bit-cast)
+    pay = mine.astype(np.float32)
+    if len(pay):
+        pay[:, 1] = mine[:, 1].astype(np.int32).view(np.float32)
+        pay[:, 3] = mine[:, 3].astype(np.int32).view(np.float32)
+    got = allgather_rows(dist, torch, pay, device)
     lap("gather_edges_ms")
-    edges = np.concatenate(got) if got else mine
+    edges = (np.concatenate(got) if got else pay).astype(np.float64)
+    if len(edges):
+        cat = np.concatenate(got).astype(np.float32)
+        edges[:, 1] = np.ascontiguousarray(cat[:, 1]).view(np.int32)
+        edges[:, 3] = np.ascontiguousarray(cat[:, 3]).view(np.int32)
     stats = dict(boundary_nodes=int(sum(len(m) for m in all_nodes)), strip_points=int(sum(len(m) for m in all_strips)),
                  candidate_pairs=int(n_pairs), stitched_edges_total=int(len(edges)),
                  bytes=int(sum(m.nbytes for m in all_nodes) + sum(m.nbytes for m in all_strips) + sum(m.nbytes for m in got)),
                  **{k: round(v, 2) for k, v in tm.items()})
     return edges, stats
+
+
+# ---------------------------------------------------------------------------------------------------
+# ONE graph across the GPUs: merge the per-tile TRGs + the stitched edges, answer a query batch on it
+# ---------------------------------------------------------------------------------------------------
+def allgather_concat(dist, torch, t, device):
+    """All-gather of one tensor per rank with ragged first dimension; returns (concatenation, row counts)."""
+    world = dist.get_world_size()
+    t = t.to(device).contiguous()
+    cnt = torch.tensor([t.shape[0]], dtype=torch.int64, device=device)
+    cnts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(cnts, cnt)
+    counts = [int(c) for c in torch.cat(cnts).cpu()]
+    mx = max(1, max(counts))
+    pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=device)
+    if t.shape[0]:
+        pad[: t.shape[0]] = t
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad)
+    return torch.cat([out[r][: counts[r]] for r in range(world)]), counts
+
+
+def merge_graphs(dist, torch, device, rank, world, local, stitched):
+    """Every rank's tile graph (`local`: GraphSnapshot, CSR by local id) + the stitched cross-tile edges
+    (rows rank_a, id_a, rank_b, id_b, weight, dist) -> ONE global CSR, identical on every rank.
+    Global id = node offset of the owner rank + local id; a node's edge list keeps its local order, the
+    stitched edges follow. Exchange: all-gathers of positions / states and of the edge lists."""
+    pos, counts = allgather_concat(dist, torch, torch.from_numpy(np.ascontiguousarray(local.pos, np.float32)), device)
+    state, _ = allgather_concat(dist, torch, torch.from_numpy(np.ascontiguousarray(local.state, np.int32)), device)
+    node_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    n_local = local.pos.shape[0]
+    deg = np.diff(local.row_ptr).astype(np.int64)
+    src = np.repeat(np.arange(n_local, dtype=np.int64), deg) + node_off[rank]
+    coo = torch.stack([torch.from_numpy(src), torch.from_numpy(local.col.astype(np.int64) + node_off[rank])], 1)
+    wd = torch.stack([torch.from_numpy(np.ascontiguousarray(local.weight, np.float32)),
+                      torch.from_numpy(np.ascontiguousarray(local.dist, np.float32))], 1)
+    coo_all, ecounts = allgather_concat(dist, torch, coo, device)
+    wd_all, _ = allgather_concat(dist, torch, wd, device)
+    nbytes = int(pos.numel() * 4 + state.numel() * 4 + coo_all.numel() * 8 + wd_all.numel() * 4)
+    if len(stitched):
+        st = np.asarray(stitched, np.float64)
+        ga = node_off[st[:, 0].astype(np.int64)] + st[:, 1].astype(np.int64)
+        gb = node_off[st[:, 2].astype(np.int64)] + st[:, 3].astype(np.int64)
+        s_coo = torch.from_numpy(np.concatenate([np.stack([ga, gb], 1), np.stack([gb, ga], 1)])).to(device)
+        s_wd = torch.from_numpy(np.concatenate([st[:, 4:6], st[:, 4:6]]).astype(np.float32)).to(device)
+        coo_all = torch.cat([coo_all, s_coo])
+        wd_all = torch.cat([wd_all, s_wd])
+    n = int(node_off[-1])
+    order = torch.sort(coo_all[:, 0], stable=True).indices   # rows by source id; local edges first, stitched after
+    col = coo_all[order, 1].to(torch.int32)
+    wd_sorted = wd_all[order]
+    row_ptr = torch.zeros(n + 1, dtype=torch.int64, device=coo_all.device)
+    row_ptr[1:] = torch.cumsum(torch.bincount(coo_all[:, 0], minlength=n), 0)
+    return dict(n_nodes=n, n_edges=int(col.shape[0]), node_off=node_off, pos=pos, state=state, row_ptr=row_ptr, col=col,
+                weight=wd_sorted[:, 0].contiguous(), dist=wd_sorted[:, 1].contiguous(), bytes=nbytes, edge_counts=ecounts)
+
+
+def build_merged_graph(dist, torch, device, rank, world, trg_handle, cloud, bb, P, K):
+    """Stitch the tiles (stitch_tiles), merge them (merge_graphs) and upload the merged CSR (K7) on this rank."""
+    import time
+    t0 = time.perf_counter()
+    g = trg_handle.export()
+    t1 = time.perf_counter()
+
+    def edge_eval(strip_pts, p1, p2):
+        dm = K.DeviceMap(strip_pts, 0.67 * P.robot_size)
+        r = dm.edge_eval(p1, p2, P.robot_size, P.height_threshold, P.collision_threshold)
+        dm.close()
+        return r["stage"], r["weight"], r["dist"]
+
+    stitched, st = stitch_tiles(dist, torch, device, rank, world, cloud, g.pos, g.ids, bb[0][0], bb[0][1], P.expand_dist,
+                                P.robot_size, edge_eval)
+    t2 = time.perf_counter()
+    m = merge_graphs(dist, torch, device, rank, world, g, stitched)
+    t3 = time.perf_counter()
+    graph = K.DeviceGraph(m["row_ptr"].cpu().numpy(), m["col"].cpu().numpy(), m["weight"].cpu().numpy(), m["dist"].cpu().numpy(),
+                          m["pos"].cpu().numpy(), m["state"].cpu().numpy())
+    grid = K.DeviceNodeGrid(m["pos"], P.robot_size)   # nearest-node snapping on the merged graph
+    t4 = time.perf_counter()
+    stats = dict(st)
+    stats["bytes"] = int(st["bytes"] + m["bytes"])
+    stats.update(export_ms=round(1e3 * (t1 - t0), 2), stitch_ms=round(1e3 * (t2 - t1), 2), merge_ms=round(1e3 * (t3 - t2), 2),
+                 upload_ms=round(1e3 * (t4 - t3), 2))
+    m.update(graph=graph, grid=grid, stats=stats)
+    return m
+
+
+def plan_sharded(dist, torch, device, rank, world, mg, queries, P, K):
+    """One global query batch on the merged graph: rank r answers the contiguous share query_shard(n, r, world)
+    (start / goal = nearest node of the merged graph), the (found, cost, length, node sequence) records are
+    all-gathered. Returns the full batch on every rank."""
+    sl = query_shard(len(queries), rank, world)
+    q = np.ascontiguousarray(queries[sl], np.float32)
+    s_ids = mg["grid"].nearest(q[:, 0:2])
+    g_ids = mg["grid"].nearest(q[:, 2:4])
+    r = mg["graph"].sssp(s_ids, g_ids, P.safety_factor)
+    lens = np.diff(r["offsets"]).astype(np.int64)
+    rec = torch.from_numpy(np.stack([r["found"].astype(np.float32), r["cost"], r["path_length"], lens.astype(np.float32)], 1))
+    rec_all, _ = allgather_concat(dist, torch, rec, device)
+    ids_all, _ = allgather_concat(dist, torch, torch.from_numpy(r["ids"].astype(np.int32)), device)
+    rec_np, ids_np = rec_all.cpu().numpy(), ids_all.cpu().numpy()
+    offs = np.concatenate([[0], np.cumsum(rec_np[:, 3].astype(np.int64))])
+    owner = np.searchsorted(mg["node_off"], ids_np, side="right") - 1   # tile of every path node
+    cross = 0
+    for i in range(len(rec_np)):
+        seg = owner[offs[i]:offs[i + 1]]
+        cross += int(seg.size > 0 and seg.min() != seg.max())
+    return dict(found=rec_np[:, 0] > 0, cost=rec_np[:, 1], path_length=rec_np[:, 2], offsets=offs, ids=ids_np,
+                cross_tile_paths=cross, gather_bytes=int(rec_all.numel() * 4 + ids_all.numel() * 4),
+                d2h_bytes=int(rec_np.nbytes + ids_np.nbytes))

@@ -47,6 +47,14 @@ def _finish(x, y, z, rng: np.random.Generator, shuffle: bool) -> np.ndarray:
     return np.ascontiguousarray(pts)
 
 
+def mountain_slab(side: int, h: float = 0.1, seed: int = 2, *, slab: int = 0, n_slabs: int = 1, **kw) -> np.ndarray:
+    """ONE side x side mountain map cut into `n_slabs` slabs along x (strong scaling, BASELINE config #3):
+    slab k holds the lattice columns [k * side // n_slabs, (k + 1) * side // n_slabs) of the same
+    continuous height function (side must be divisible by n_slabs, or the remainder columns are dropped)."""
+    nx = side // n_slabs
+    return mountain(nx, side, h=h, seed=seed, tile=(slab, 0), world_tiles=(n_slabs, 1), **kw)
+
+
 def mountain(nx: int, ny: int | None = None, h: float = 0.1, seed: int = 2, *,
              base_wavelength: float = 64.0, amplitude: float = 12.0, octaves: int = 5,
              gain: float = 0.5, noise_sigma: float = 0.01, shuffle: bool = True,
