@@ -5,6 +5,8 @@
 // nodes created inside the batch. Distances use the same float arithmetic as kdtree.c
 // (fl(fl(dx*dx)+fl(dy*dy)), strict `<`), so the minimum is the same number; exact ties are
 // flagged and resolved on the host by the insertion-order tree.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cmath>
 #include <vector>
@@ -19,6 +21,8 @@ struct trgb_nodes {
   float2* d_xy = nullptr;     // cap
   int32_t* d_next = nullptr;  // cap
 };
+
+namespace cg = cooperative_groups;
 
 namespace trgb {
 
@@ -235,6 +239,46 @@ __global__ void __launch_bounds__(256) k_kd_place(int n, const float2* __restric
   if (left) atomicAdd(remaining, left);
 }
 
+// all rounds in one cooperative launch: claim, grid barrier, place, grid barrier, until nobody is left
+__global__ void __launch_bounds__(256) k_kd_build(int n, const float2* __restrict__ xy, int* __restrict__ at,
+                                                  unsigned char* __restrict__ side, unsigned char* __restrict__ placed,
+                                                  int* __restrict__ claim, int* __restrict__ lo, int* __restrict__ hi,
+                                                  int* __restrict__ parent, unsigned char* __restrict__ axis,
+                                                  int* __restrict__ counters /* [2] remaining per round parity, zeroed */) {
+  cg::grid_group grid = cg::this_grid();
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x, GT = gridDim.x * blockDim.x;
+  for (int round = 0;; ++round) {
+    for (int i = gt; i < n; i += GT)
+      if (!placed[i]) atomicMin(claim + 2 * (size_t)at[i] + side[i], i);
+    if (gt == 0) counters[round & 1] = 0;  // (its last readers were two rounds ago: everybody has passed two barriers since)
+    grid.sync();
+    int left = 0;
+    for (int i = gt; i < n; i += GT) {
+      if (placed[i]) continue;
+      const int p = at[i];
+      const int sd = side[i];
+      const int w = ((volatile int*)claim)[2 * (size_t)p + sd];
+      const unsigned char ax = axis[p] ^ 1;
+      if (w == i) {
+        placed[i] = 1;
+        parent[i] = p;
+        axis[i] = ax;
+        if (sd) hi[p] = i; else lo[p] = i;
+      } else {
+        const float2 me = xy[i], ww = xy[w];
+        const bool low = ax ? (me.y < ww.y) : (me.x < ww.x);
+        at[i] = w;
+        side[i] = low ? 0 : 1;
+        ++left;
+      }
+    }
+    left = __reduce_add_sync(0xffffffffu, left);
+    if ((threadIdx.x & 31) == 0 && left) atomicAdd(counters + (round & 1), left);
+    grid.sync();
+    if (((volatile int*)counters)[round & 1] == 0) break;
+  }
+}
+
 }  // namespace trgb
 
 // xy: n (x, y) pairs in insertion order. Outputs (host, n entries each): children lo / hi (-1 = none), parent
@@ -242,7 +286,8 @@ __global__ void __launch_bounds__(256) k_kd_place(int n, const float2* __restric
 extern "C" int trgb_kdtree_build(const float* xy, int64_t n, int32_t* lo, int32_t* hi, int32_t* parent, uint8_t* axis) {
   TRGB_ARG(xy && lo && hi && parent && axis && n > 0 && n < (1ll << 31), "bad argument");
   trgb::tune_mempool_once();
-  cudaStream_t st = 0;
+  cudaStream_t st = nullptr;  // its own non-blocking stream: the legacy default stream would serialise with every other stream
+  TRGB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   float2* d_xy = nullptr; int *d_at = nullptr, *d_claim = nullptr, *d_lo = nullptr, *d_hi = nullptr, *d_par = nullptr, *d_rem = nullptr;
   unsigned char *d_side = nullptr, *d_placed = nullptr, *d_axis = nullptr;
   const size_t N = (size_t)n;
@@ -252,7 +297,7 @@ extern "C" int trgb_kdtree_build(const float* xy, int64_t n, int32_t* lo, int32_
   TRGB_CUDA(cudaMallocAsync((void**)&d_lo, N * sizeof(int), st));
   TRGB_CUDA(cudaMallocAsync((void**)&d_hi, N * sizeof(int), st));
   TRGB_CUDA(cudaMallocAsync((void**)&d_par, N * sizeof(int), st));
-  TRGB_CUDA(cudaMallocAsync((void**)&d_rem, sizeof(int), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&d_rem, 2 * sizeof(int), st));
   TRGB_CUDA(cudaMallocAsync((void**)&d_side, N, st));
   TRGB_CUDA(cudaMallocAsync((void**)&d_placed, N, st));
   TRGB_CUDA(cudaMallocAsync((void**)&d_axis, N, st));
@@ -264,6 +309,7 @@ extern "C" int trgb_kdtree_build(const float* xy, int64_t n, int32_t* lo, int32_
   TRGB_CUDA(cudaMemsetAsync(d_placed, 0, N, st));
   TRGB_CUDA(cudaMemsetAsync(d_axis, 0, N, st));
   TRGB_CUDA(cudaMemsetAsync(d_at, 0, N * sizeof(int), st));
+  TRGB_CUDA(cudaMemsetAsync(d_rem, 0, 2 * sizeof(int), st));
   // the root is node 0; everybody else starts at its low / high slot
   const unsigned char one = 1;
   TRGB_CUDA(cudaMemcpyAsync(d_placed, &one, 1, cudaMemcpyHostToDevice, st));
@@ -273,21 +319,15 @@ extern "C" int trgb_kdtree_build(const float* xy, int64_t n, int32_t* lo, int32_
     TRGB_CUDA(cudaMemcpyAsync(d_side, side0.data(), N, cudaMemcpyHostToDevice, st));
     TRGB_CUDA(cudaStreamSynchronize(st));
   }
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8));
-  int remaining = (int)n - 1;
-  int rounds = 0;
-  while (remaining > 0) {
-    // a few rounds per host check (the count of the last one decides)
-    for (int k = 0; k < 8; ++k) {
-      TRGB_CUDA(cudaMemsetAsync(d_rem, 0, sizeof(int), st));
-      ProfScope ps("k_kd_round", st, (double)remaining);
-      k_kd_claim<<<grid, 256, 0, st>>>((int)n, d_at, d_side, d_placed, d_claim);
-      k_kd_place<<<grid, 256, 0, st>>>((int)n, d_xy, d_at, d_side, d_placed, d_claim, d_lo, d_hi, d_par, d_axis, d_rem);
-      ++rounds;
-    }
-    TRGB_CUDA(cudaMemcpyAsync(&remaining, d_rem, sizeof(int), cudaMemcpyDeviceToHost, st));
-    TRGB_CUDA(cudaStreamSynchronize(st));
-    if (rounds > 100000) { set_error("kdtree_build: no progress"); return TRGB_E_STATE; }
+  if (n > 1) {
+    int per_sm = 0;
+    TRGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k_kd_build, 256, 0));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * std::max(1, std::min(per_sm, 4))));
+    int nn = (int)n;
+    void* args[] = {(void*)&nn, (void*)&d_xy, (void*)&d_at, (void*)&d_side, (void*)&d_placed, (void*)&d_claim, (void*)&d_lo,
+                    (void*)&d_hi, (void*)&d_par, (void*)&d_axis, (void*)&d_rem};
+    ProfScope ps("k_kd_build", st, (double)n);
+    TRGB_CUDA(cudaLaunchCooperativeKernel((const void*)k_kd_build, dim3(grid), dim3(256), args, 0, st));
   }
   TRGB_CUDA(cudaMemcpyAsync(lo, d_lo, N * sizeof(int), cudaMemcpyDeviceToHost, st));
   TRGB_CUDA(cudaMemcpyAsync(hi, d_hi, N * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -297,5 +337,7 @@ extern "C" int trgb_kdtree_build(const float* xy, int64_t n, int32_t* lo, int32_
   for (void* p : {(void*)d_xy, (void*)d_at, (void*)d_claim, (void*)d_lo, (void*)d_hi, (void*)d_par, (void*)d_rem, (void*)d_side,
                   (void*)d_placed, (void*)d_axis})
     cudaFreeAsync(p, st);
+  cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
   return TRGB_OK;
 }

@@ -321,6 +321,7 @@ void TRG::setLocalGraph(bool useMutex) {  // trg.cpp:211-231
 // ================================================================================================
 void TRG::nodeIndexReset(trgStruct& g) {
   g.node_seq.clear();
+  g.seq_xy.clear();
   g.node_grid.clear();
   g.node_tree.clear();
   g.grid_built = 0;
@@ -341,15 +342,15 @@ void TRG::ensureGrid(trgStruct& g) {
 
 void TRG::nodeIndexInsert(trgStruct& g, Node* n) {
   g.node_seq.push_back(n);  // the host grid / order tree catch up lazily (ensureGridBuilt / ensureTree)
+  g.seq_xy.push_back(n->pos_.x());
+  g.seq_xy.push_back(n->pos_.y());
   if (!g.iter_rank.empty()) g.iter_rank.clear();
 }
 
 void TRG::ensureGridBuilt(trgStruct& g) {
   ensureGrid(g);
-  for (; g.grid_built < g.node_seq.size(); ++g.grid_built) {
-    Node* n = g.node_seq[g.grid_built];
-    g.node_grid.insert(n->pos_.x(), n->pos_.y());
-  }
+  for (; g.grid_built < g.node_seq.size(); ++g.grid_built)
+    g.node_grid.insert(g.seq_xy[2 * g.grid_built], g.seq_xy[2 * g.grid_built + 1]);
 }
 
 void TRG::ensureTree(trgStruct& g) {
@@ -360,14 +361,12 @@ void TRG::ensureTree(trgStruct& g) {
   // tree is usually far behind when it is needed) a parallel bulk rebuild of the identical tree wins.
   if (n >= 256 && (g.tree_built == 0 || pending > 20000)) {
     std::vector<float> xs(n), ys(n);
-    for (size_t i = 0; i < n; ++i) { xs[i] = g.node_seq[i]->pos_.x(); ys[i] = g.node_seq[i]->pos_.y(); }
+    for (size_t i = 0; i < n; ++i) { xs[i] = g.seq_xy[2 * i]; ys[i] = g.seq_xy[2 * i + 1]; }
     if (n >= 20000 && trgb_device_count() > 0) {
       // large graph: the same tree, grown on the device one level per round (a few ms instead of ~50)
-      std::vector<float> xy(2 * n);
-      for (size_t i = 0; i < n; ++i) { xy[2 * i] = xs[i]; xy[2 * i + 1] = ys[i]; }
       std::vector<int> lo(n), hi(n), par(n);
       std::vector<uint8_t> ax(n);
-      K(trgb_kdtree_build(xy.data(), (int64_t)n, lo.data(), hi.data(), par.data(), ax.data()), "trgb_kdtree_build");
+      K(trgb_kdtree_build(g.seq_xy.data(), (int64_t)n, lo.data(), hi.data(), par.data(), ax.data()), "trgb_kdtree_build");
       g.node_tree.adopt(xs.data(), ys.data(), (int)n, std::move(lo), std::move(hi), std::move(par), std::move(ax));
     } else {
       g.node_tree.build_bulk(xs.data(), ys.data(), (int)n);
@@ -375,10 +374,8 @@ void TRG::ensureTree(trgStruct& g) {
     g.tree_built = n;
     return;
   }
-  for (; g.tree_built < n; ++g.tree_built) {
-    Node* nd = g.node_seq[g.tree_built];
-    g.node_tree.insert(nd->pos_.x(), nd->pos_.y(), (int)g.tree_built);
-  }
+  for (; g.tree_built < n; ++g.tree_built)
+    g.node_tree.insert(g.seq_xy[2 * g.tree_built], g.seq_xy[2 * g.tree_built + 1], (int)g.tree_built);
 }
 
 // kd_nearest2 on node_tree (kdtree.c:364-417): exact float argmin; exact ties by tree visit order
@@ -1455,12 +1452,23 @@ void TRG::invalidateDeviceGraph() {
   if (dev_graph_) trgb_graph_destroy(dev_graph_);
   dev_graph_ = nullptr;
   dev_graph_relaxed_ = 0;
+  csr_cache_.valid = false;
   dev_graph_nodes_.clear();
 }
 
 void TRG::ensureDeviceGraph() {
   if (dev_graph_) return;
   trgStruct& g = *trgMap_["global"];
+  if (csr_cache_.valid) {
+    // prepared by the device build from its flat arrays: no walk over half a million Node objects
+    CsrCache& c = csr_cache_;
+    const int n = (int)c.state.size();
+    dev_graph_nodes_.resize(n);
+    for (int k = 0; k < n; ++k) dev_graph_nodes_[k] = &node_pool_[(size_t)k];  // the device build numbers nodes by pool slot
+    TrgbGraphDesc desc{n, (int64_t)c.col.size(), c.row.data(), c.col.data(), c.w.data(), c.d.data(), c.pos.data(), c.state.data()};
+    K(trgb_graph_upload(&dev_graph_, &desc), "trgb_graph_upload");
+    return;
+  }
   // rows by node id; every node of the map is in node_seq with id_ == its key (see cleanGraph)
   int max_id = -1;
   for (Node* nd : g.node_seq) max_id = std::max(max_id, nd->id_);

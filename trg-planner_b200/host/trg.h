@@ -163,6 +163,7 @@ class TRG {
 
     // replaces `kdtree* node_tree` (trg.h:106): insertion sequence + grid + lazy order tree
     std::vector<Node*>      node_seq;
+    std::vector<float>      seq_xy;      // (x, y) of node_seq, flat: the index structures are built without chasing Node pointers
     trg_b200::NodeGrid      node_grid;
     trg_b200::OrderTree2D   node_tree;
     size_t                  grid_built = 0;  // prefix of node_seq already in node_grid (filled lazily)
@@ -257,6 +258,13 @@ class TRG {
   const trgb_map* expander_map_ = nullptr;
 
   std::unique_ptr<trg_b200::DeviceSession> dev_;
+  // CSR of the global graph prepared while it was materialised (device build): uploaded as is by ensureDeviceGraph
+  struct CsrCache {
+    bool valid = false;
+    std::vector<int64_t> row;
+    std::vector<int32_t> col, state;
+    std::vector<float> w, d, pos;
+  } csr_cache_;
   trgb_graph* dev_graph_ = nullptr;
   int64_t dev_graph_relaxed_ = 0;  // edges relaxed by the handle so far (already booked in stat_)
   std::vector<Node*> dev_graph_nodes_;  // row -> node of the uploaded CSR

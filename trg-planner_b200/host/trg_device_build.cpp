@@ -347,10 +347,16 @@ bool TRG::buildGraphOnDevice(trgStruct& g) {
   node_used_ = m;
   edge_used_ = e_total;
   const int threads = m > (size_t)tuning_.parallel_min_nodes ? trg_b200::thread_budget() : 1;
+  CsrCache csr;   // the cleaned graph as CSR (rows = new ids): what K7 uploads, prepared in the same pass
+  csr.row.resize(m + 1); csr.col.resize(e_total); csr.w.resize(e_total); csr.d.resize(e_total);
+  csr.pos.resize(3 * m); csr.state.resize(m);
+  for (size_t k = 0; k <= m; ++k) csr.row[k] = (int64_t)e_off[k];
   parallel_for(m, threads, [&](size_t b, size_t en) {
     for (size_t k = b; k < en; ++k) {
       const int old = kept[k];
       Node& nd = node_pool_[k];
+      csr.pos[3 * k] = xyz[3 * (size_t)old]; csr.pos[3 * k + 1] = xyz[3 * (size_t)old + 1]; csr.pos[3 * k + 2] = xyz[3 * (size_t)old + 2];
+      csr.state[k] = (int32_t)state[old];
       nd.id_ = (int)k;
       nd.pos_ = Eigen::Vector3f(xyz[3 * (size_t)old], xyz[3 * (size_t)old + 1], xyz[3 * (size_t)old + 2]);
       nd.state_ = static_cast<NodeState>((int)state[old]);
@@ -359,6 +365,9 @@ bool TRG::buildGraphOnDevice(trgStruct& g) {
       for (int64_t j = row[old]; j < row[old + 1]; ++j) {
         // no edge leads to an Invalid node here (a node is Invalid from birth and never wired, :411), so
         // the del_edges filter of :505-517 keeps everything; ids are remapped (:518)
+        csr.col[eo] = old2new[col[(size_t)j]];
+        csr.w[eo] = ew[(size_t)j];
+        csr.d[eo] = ed[(size_t)j];
         Edge& ed2 = edge_pool_[eo++];
         ed2.dst_id_ = old2new[col[(size_t)j]];
         ed2.weight_ = ew[(size_t)j];
@@ -384,8 +393,14 @@ bool TRG::buildGraphOnDevice(trgStruct& g) {
   g.nodes   = std::move(new_nodes);
   g.node_id = (int)m;
   g.node_seq.resize(m);
+  g.seq_xy.resize(2 * m);
   parallel_for(m, threads, [&](size_t b, size_t en) {
-    for (size_t i = b; i < en; ++i) g.node_seq[i] = &node_pool_[(size_t)order2[i]];
+    for (size_t i = b; i < en; ++i) {
+      const size_t k = (size_t)order2[i];
+      g.node_seq[i] = &node_pool_[k];
+      g.seq_xy[2 * i] = csr.pos[3 * k];
+      g.seq_xy[2 * i + 1] = csr.pos[3 * k + 1];
+    }
   });
 #ifndef NDEBUG
   {
@@ -394,6 +409,8 @@ bool TRG::buildGraphOnDevice(trgStruct& g) {
   }
 #endif
   invalidateDeviceGraph();
+  csr.valid = true;
+  csr_cache_ = std::move(csr);
   const double t_materialize = since(t_mat);
 
   stat_["pops"] += st.pops;
