@@ -202,80 +202,131 @@ extern "C" int trgb_nodes_nearest_launch(const trgb_nodes* g, const float* d_xy,
 // ------------------------------------------------------------------------------------------------------
 namespace trgb {
 
-__global__ void __launch_bounds__(256) k_kd_claim(int n, const int* __restrict__ at, const unsigned char* __restrict__ side,
-                                                  const unsigned char* __restrict__ placed, int* __restrict__ claim) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    if (placed[i]) continue;
-    atomicMin(claim + 2 * (size_t)at[i] + side[i], i);
+// One work item = a node still looking for its place: (node index, slot it competes for = 2 * parent + side).
+// A round: [barrier] read the slot's winner; the winner is placed, every loser steps below the winner, takes
+// part in the atomicMin of its next slot right away (all contenders of a slot arrive in the same round, so the
+// minimum is complete at the next barrier) and appends itself to the next round's list. One barrier per level;
+// the lists shrink with the number of nodes deeper than the level, and once a round fits one CTA the others
+// leave and CTA 0 finishes with __syncthreads alone (BFS insertion order makes the tree deep - several hundred
+// levels for 5e5 nodes - with a long thin tail).
+struct KdCtl {
+  unsigned int bar;      // monotonic arrival counter of the grid barrier
+  int cnt[3];            // items in the list of round r at cnt[r % 3]
+};
+
+__device__ __forceinline__ void kd_barrier(unsigned int* bar, unsigned int target, bool solo) {
+  __syncthreads();
+  if (solo) return;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    while (*(volatile unsigned int*)bar < target) {}
+    __threadfence();
   }
+  __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) k_kd_place(int n, const float2* __restrict__ xy, int* __restrict__ at,
-                                                  unsigned char* __restrict__ side, unsigned char* __restrict__ placed,
-                                                  const int* __restrict__ claim, int* __restrict__ lo, int* __restrict__ hi,
-                                                  int* __restrict__ parent, unsigned char* __restrict__ axis,
-                                                  int* __restrict__ remaining) {
-  int left = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    if (placed[i]) continue;
-    const int p = at[i];
-    const int sd = side[i];
-    const int w = claim[2 * (size_t)p + sd];
-    const unsigned char ax = axis[p] ^ 1;
-    if (w == i) {
-      placed[i] = 1;
-      parent[i] = p;
-      axis[i] = ax;
-      if (sd) hi[p] = i; else lo[p] = i;
-    } else {
-      // the slot went to an earlier node: continue below it (its split axis is the parent's, flipped)
-      const float2 me = xy[i], ww = xy[w];
-      const bool low = ax ? (me.y < ww.y) : (me.x < ww.x);
-      at[i] = w;
-      side[i] = low ? 0 : 1;
-      ++left;
+// Near the root of a tree grown in BFS order almost every node competes for the same few slots, and same-address
+// atomics serialise in L2 (5e5 of them ~ 1 ms per level). So a claim is reduced on the way: lanes of a warp with
+// the same slot merge (match_any + reduce_min), warps merge in a small direct-mapped shared-memory table, and a
+// CTA sends one atomicMin per distinct slot per round. The next round's list is filled a 1024-item chunk at a
+// time with one global atomicAdd per chunk.
+constexpr int kKdTable = 2048;
+
+__global__ void __launch_bounds__(1024, 1) k_kd_build(int n, const float2* __restrict__ xy, int2* listA, int2* listB, int* claim,
+                                                      int* __restrict__ lo, int* __restrict__ hi, int* __restrict__ parent,
+                                                      unsigned char* __restrict__ axis, KdCtl* ctl) {
+  __shared__ int s_key[kKdTable], s_val[kKdTable];
+  __shared__ int s_wcnt[32], s_woff[32], s_base;
+  const int tid = threadIdx.x, gt = blockIdx.x * blockDim.x + tid, GT = gridDim.x * blockDim.x;
+  const unsigned lane = tid & 31, warp = tid >> 5;
+  for (int h = tid; h < kKdTable; h += blockDim.x) { s_key[h] = -1; s_val[h] = 0x7fffffff; }
+  __syncthreads();
+  // merged claim of (slot, idx): through the CTA's table when the slot owns (or can take) its bucket
+  auto claim_slot = [&](int slot, int idx, unsigned peers) {
+    const int mn = __reduce_min_sync(peers, idx);
+    if ((unsigned)(__ffs(peers) - 1) != lane) return;
+    const int h = (int)(((unsigned)slot * 2654435761u) >> 21);  // 11 bits
+    const int old = atomicCAS(&s_key[h], -1, slot);
+    if (old == -1 || old == slot) atomicMin(&s_val[h], mn);
+    else atomicMin(claim + slot, mn);
+  };
+  auto flush_table = [&]() {
+    __syncthreads();
+    for (int h = tid; h < kKdTable; h += blockDim.x) {
+      const int key = s_key[h];
+      if (key >= 0) { atomicMin(claim + key, s_val[h]); s_key[h] = -1; s_val[h] = 0x7fffffff; }
+    }
+  };
+  // round "-1": everybody but the root competes for the root's low / high slot (axis 0 at the root)
+  const float rx = xy[0].x;
+  for (int i0 = gt - (int)lane; i0 < n; i0 += GT) {
+    const int i = i0 + (int)lane;
+    const unsigned act = __ballot_sync(0xffffffffu, i >= 1 && i < n);
+    if (i >= 1 && i < n) {
+      const int slot = xy[i].x < rx ? 0 : 1;
+      listA[i - 1] = make_int2(i, slot);
+      claim_slot(slot, i, __match_any_sync(act, slot));
     }
   }
-  if (left) atomicAdd(remaining, left);
-}
-
-// all rounds in one cooperative launch: claim, grid barrier, place, grid barrier, until nobody is left
-__global__ void __launch_bounds__(256) k_kd_build(int n, const float2* __restrict__ xy, int* __restrict__ at,
-                                                  unsigned char* __restrict__ side, unsigned char* __restrict__ placed,
-                                                  int* __restrict__ claim, int* __restrict__ lo, int* __restrict__ hi,
-                                                  int* __restrict__ parent, unsigned char* __restrict__ axis,
-                                                  int* __restrict__ counters /* [2] remaining per round parity, zeroed */) {
-  cg::grid_group grid = cg::this_grid();
-  const int gt = blockIdx.x * blockDim.x + threadIdx.x, GT = gridDim.x * blockDim.x;
+  flush_table();
+  if (gt == 0) { parent[0] = -1; axis[0] = 0; }
+  bool solo = false;
+  unsigned int epoch = 0;
   for (int round = 0;; ++round) {
-    for (int i = gt; i < n; i += GT)
-      if (!placed[i]) atomicMin(claim + 2 * (size_t)at[i] + side[i], i);
-    if (gt == 0) counters[round & 1] = 0;  // (its last readers were two rounds ago: everybody has passed two barriers since)
-    grid.sync();
-    int left = 0;
-    for (int i = gt; i < n; i += GT) {
-      if (placed[i]) continue;
-      const int p = at[i];
-      const int sd = side[i];
-      const int w = ((volatile int*)claim)[2 * (size_t)p + sd];
-      const unsigned char ax = axis[p] ^ 1;
-      if (w == i) {
-        placed[i] = 1;
-        parent[i] = p;
-        axis[i] = ax;
-        if (sd) hi[p] = i; else lo[p] = i;
-      } else {
-        const float2 me = xy[i], ww = xy[w];
+    epoch += gridDim.x;
+    kd_barrier(&ctl->bar, epoch, solo);
+    const int m = __ldcg(&ctl->cnt[round % 3]);
+    if (m == 0) break;
+    if (!solo && m <= (int)blockDim.x) {
+      if (blockIdx.x != 0) return;
+      solo = true;
+    }
+    if (gt == 0) ctl->cnt[(round + 2) % 3] = 0;  // next round's appends go there; its last readers are two barriers back
+    const int2* cur = (round & 1) ? listB : listA;
+    int2* nxt = (round & 1) ? listA : listB;
+    int* nxt_cnt = &ctl->cnt[(round + 1) % 3];
+    const unsigned char ax = (unsigned char)((round + 1) & 1);  // nodes placed this round sit at depth round + 1
+    const int c_first = solo ? 0 : (int)blockIdx.x * (int)blockDim.x, c_stride = solo ? (int)blockDim.x : GT;
+    for (int c0 = c_first; c0 < m; c0 += c_stride) {  // CTA-uniform
+      const int k = c0 + tid;
+      bool lose = false;
+      int2 it = make_int2(0, 0);
+      int w = 0;
+      if (k < m) {
+        it = __ldcg(cur + k);
+        w = __ldcg(claim + it.y);
+        lose = w != it.x;
+        if (!lose) {
+          const int p = it.y >> 1;
+          parent[it.x] = p;
+          axis[it.x] = ax;
+          if (it.y & 1) hi[p] = it.x; else lo[p] = it.x;
+        }
+      }
+      const unsigned losers = __ballot_sync(0xffffffffu, lose);
+      if (lane == 0) s_wcnt[warp] = __popc(losers);
+      __syncthreads();
+      if (warp == 0) {
+        const int v = s_wcnt[lane];
+        int inc = v;
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, inc, o);
+          if ((int)lane >= o) inc += t;
+        }
+        s_woff[lane] = inc - v;
+        if (lane == 31) s_base = inc ? atomicAdd(nxt_cnt, inc) : 0;
+      }
+      __syncthreads();
+      if (lose) {
+        const float2 me = xy[it.x], ww = xy[w];
         const bool low = ax ? (me.y < ww.y) : (me.x < ww.x);
-        at[i] = w;
-        side[i] = low ? 0 : 1;
-        ++left;
+        const int slot = 2 * w + (low ? 0 : 1);
+        nxt[s_base + s_woff[warp] + __popc(losers & ((1u << lane) - 1u))] = make_int2(it.x, slot);
+        claim_slot(slot, it.x, __match_any_sync(losers, slot));
       }
     }
-    left = __reduce_add_sync(0xffffffffu, left);
-    if ((threadIdx.x & 31) == 0 && left) atomicAdd(counters + (round & 1), left);
-    grid.sync();
-    if (((volatile int*)counters)[round & 1] == 0) break;
+    flush_table();
   }
 }
 
@@ -284,58 +335,43 @@ __global__ void __launch_bounds__(256) k_kd_build(int n, const float2* __restric
 // xy: n (x, y) pairs in insertion order. Outputs (host, n entries each): children lo / hi (-1 = none), parent
 // (-1 for the root) and split axis of every node — what n successive kd_insert2 calls would have built.
 extern "C" int trgb_kdtree_build(const float* xy, int64_t n, int32_t* lo, int32_t* hi, int32_t* parent, uint8_t* axis) {
-  TRGB_ARG(xy && lo && hi && parent && axis && n > 0 && n < (1ll << 31), "bad argument");
+  TRGB_ARG(xy && lo && hi && parent && axis && n > 0 && n < (1ll << 30), "bad argument");
   trgb::tune_mempool_once();
   cudaStream_t st = nullptr;  // its own non-blocking stream: the legacy default stream would serialise with every other stream
   TRGB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  float2* d_xy = nullptr; int *d_at = nullptr, *d_claim = nullptr, *d_lo = nullptr, *d_hi = nullptr, *d_par = nullptr, *d_rem = nullptr;
-  unsigned char *d_side = nullptr, *d_placed = nullptr, *d_axis = nullptr;
+  float2* d_xy = nullptr; int2 *d_la = nullptr, *d_lb = nullptr; int *d_claim = nullptr, *d_lo = nullptr, *d_hi = nullptr, *d_par = nullptr;
+  unsigned char* d_axis = nullptr; KdCtl* d_ctl = nullptr;
   const size_t N = (size_t)n;
   TRGB_CUDA(cudaMallocAsync((void**)&d_xy, N * sizeof(float2), st));
-  TRGB_CUDA(cudaMallocAsync((void**)&d_at, N * sizeof(int), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&d_la, N * sizeof(int2), st));
+  TRGB_CUDA(cudaMallocAsync((void**)&d_lb, N * sizeof(int2), st));
   TRGB_CUDA(cudaMallocAsync((void**)&d_claim, 2 * N * sizeof(int), st));
   TRGB_CUDA(cudaMallocAsync((void**)&d_lo, N * sizeof(int), st));
   TRGB_CUDA(cudaMallocAsync((void**)&d_hi, N * sizeof(int), st));
   TRGB_CUDA(cudaMallocAsync((void**)&d_par, N * sizeof(int), st));
-  TRGB_CUDA(cudaMallocAsync((void**)&d_rem, 2 * sizeof(int), st));
-  TRGB_CUDA(cudaMallocAsync((void**)&d_side, N, st));
-  TRGB_CUDA(cudaMallocAsync((void**)&d_placed, N, st));
   TRGB_CUDA(cudaMallocAsync((void**)&d_axis, N, st));
+  TRGB_CUDA(cudaMallocAsync((void**)&d_ctl, sizeof(KdCtl), st));
   TRGB_CUDA(cudaMemcpyAsync(d_xy, xy, N * sizeof(float2), cudaMemcpyHostToDevice, st));
   TRGB_CUDA(cudaMemsetAsync(d_claim, 0x7f, 2 * N * sizeof(int), st));
   TRGB_CUDA(cudaMemsetAsync(d_lo, 0xff, N * sizeof(int), st));
   TRGB_CUDA(cudaMemsetAsync(d_hi, 0xff, N * sizeof(int), st));
-  TRGB_CUDA(cudaMemsetAsync(d_par, 0xff, N * sizeof(int), st));
-  TRGB_CUDA(cudaMemsetAsync(d_placed, 0, N, st));
-  TRGB_CUDA(cudaMemsetAsync(d_axis, 0, N, st));
-  TRGB_CUDA(cudaMemsetAsync(d_at, 0, N * sizeof(int), st));
-  TRGB_CUDA(cudaMemsetAsync(d_rem, 0, 2 * sizeof(int), st));
-  // the root is node 0; everybody else starts at its low / high slot
-  const unsigned char one = 1;
-  TRGB_CUDA(cudaMemcpyAsync(d_placed, &one, 1, cudaMemcpyHostToDevice, st));
+  const KdCtl ctl0{0u, {(int)n - 1, 0, 0}};
+  TRGB_CUDA(cudaMemcpyAsync(d_ctl, &ctl0, sizeof(KdCtl), cudaMemcpyHostToDevice, st));
   {
-    std::vector<unsigned char> side0(N);
-    for (size_t i = 0; i < N; ++i) side0[i] = xy[2 * i] < xy[0] ? 0 : 1;  // axis 0 at the root
-    TRGB_CUDA(cudaMemcpyAsync(d_side, side0.data(), N, cudaMemcpyHostToDevice, st));
-    TRGB_CUDA(cudaStreamSynchronize(st));
-  }
-  if (n > 1) {
-    int per_sm = 0;
-    TRGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k_kd_build, 256, 0));
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * std::max(1, std::min(per_sm, 4))));
+    // every CTA must be resident for the grid barrier: one per SM, launched cooperatively
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 1023) / 1024, (int64_t)sm_count()));
     int nn = (int)n;
-    void* args[] = {(void*)&nn, (void*)&d_xy, (void*)&d_at, (void*)&d_side, (void*)&d_placed, (void*)&d_claim, (void*)&d_lo,
-                    (void*)&d_hi, (void*)&d_par, (void*)&d_axis, (void*)&d_rem};
+    void* args[] = {(void*)&nn, (void*)&d_xy, (void*)&d_la, (void*)&d_lb, (void*)&d_claim, (void*)&d_lo,
+                    (void*)&d_hi, (void*)&d_par, (void*)&d_axis, (void*)&d_ctl};
     ProfScope ps("k_kd_build", st, (double)n);
-    TRGB_CUDA(cudaLaunchCooperativeKernel((const void*)k_kd_build, dim3(grid), dim3(256), args, 0, st));
+    TRGB_CUDA(cudaLaunchCooperativeKernel((const void*)k_kd_build, dim3(grid), dim3(1024), args, 0, st));
   }
   TRGB_CUDA(cudaMemcpyAsync(lo, d_lo, N * sizeof(int), cudaMemcpyDeviceToHost, st));
   TRGB_CUDA(cudaMemcpyAsync(hi, d_hi, N * sizeof(int), cudaMemcpyDeviceToHost, st));
   TRGB_CUDA(cudaMemcpyAsync(parent, d_par, N * sizeof(int), cudaMemcpyDeviceToHost, st));
   TRGB_CUDA(cudaMemcpyAsync(axis, d_axis, N, cudaMemcpyDeviceToHost, st));
   TRGB_CUDA(cudaStreamSynchronize(st));
-  for (void* p : {(void*)d_xy, (void*)d_at, (void*)d_claim, (void*)d_lo, (void*)d_hi, (void*)d_par, (void*)d_rem, (void*)d_side,
-                  (void*)d_placed, (void*)d_axis})
+  for (void* p : {(void*)d_xy, (void*)d_la, (void*)d_lb, (void*)d_claim, (void*)d_lo, (void*)d_hi, (void*)d_par, (void*)d_axis, (void*)d_ctl})
     cudaFreeAsync(p, st);
   cudaStreamSynchronize(st);
   cudaStreamDestroy(st);

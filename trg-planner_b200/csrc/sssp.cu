@@ -43,7 +43,10 @@ struct trgb_graph {
 
 namespace trgb {
 
-constexpr int kSsspThreads = 256;
+#ifndef TRGB_SSSP_THREADS
+#define TRGB_SSSP_THREADS 256
+#endif
+constexpr int kSsspThreads = TRGB_SSSP_THREADS;
 constexpr unsigned long long kInfLabel = 0x7f800000ffffffffull;
 constexpr int kGroup = 8;  // lanes cooperating on one node's edge list
 
@@ -103,6 +106,7 @@ __global__ void __launch_bounds__(kSsspThreads) k_sssp(
   __shared__ long long s_poff;
   __shared__ float s_stage[2 * kSsspThreads];
   __shared__ unsigned long long s_relax;
+  __shared__ unsigned long long s_dbg[5];  // near passes, threshold steps, far items scanned, nodes expanded, pops pruned
 
   const int tid = threadIdx.x;
   const int grp = tid / kGroup, gl = tid % kGroup;
@@ -122,6 +126,7 @@ __global__ void __launch_bounds__(kSsspThreads) k_sssp(
     int32_t *qcur = q0, *qnxt = q0 + n, *qfar = q0 + 2 * (size_t)n, *qfar2 = q0 + 3 * (size_t)n;
     if (tid == 0) {
       s_relax = 0ull;
+      for (int j = 0; j < 5; ++j) s_dbg[j] = 0ull;
       label[start] = make_label(0.f, start);
       qcur[0] = start;
       s_cnt[0] = 1; s_cnt[1] = 0; s_cnt[2] = 0; s_cnt[3] = 0;
@@ -143,11 +148,13 @@ __global__ void __launch_bounds__(kSsspThreads) k_sssp(
         const float thr = s_thr;
         const float best = label_g(__ldcg(label + goal));
         unsigned my_relax = 0;
+        if (tid == 0) { s_dbg[0] += 1; }
         for (int k = grp; k < ncur; k += ngrp) {
           const int u = qcur[k];
           const float gu = label_g(__ldcg(label + u));
           // goal bound: with a consistent heuristic no path through u beats `best`
-          if (__fadd_rn(gu, heur(pos, u, gpos)) > best * 1.000001f) continue;
+          if (__fadd_rn(gu, heur(pos, u, gpos)) > best * 1.000001f) { if (gl == 0) atomicAdd(&s_dbg[4], 1ull); continue; }
+          if (gl == 0) atomicAdd(&s_dbg[3], 1ull);
           const int64_t e0 = __ldg(row + u), e1 = __ldg(row + u + 1);
           for (int64_t e = e0 + gl; e < e1; e += kGroup) {
             const int v = __ldg(col + e);
@@ -184,6 +191,7 @@ __global__ void __launch_bounds__(kSsspThreads) k_sssp(
       // ---- advance the threshold past the smallest f waiting in the far pile
       const int nfar = s_cnt[2];
       const float best = s_best;
+      if (tid == 0) { s_dbg[1] += 1; s_dbg[2] += (unsigned long long)nfar; }
       float myf = INFINITY;
       for (int k = tid; k < nfar; k += kSsspThreads) {
         const int v = qfar[k];
@@ -262,6 +270,7 @@ __global__ void __launch_bounds__(kSsspThreads) k_sssp(
       out.path_length[qi] = ok ? sum_d : 0.f;
       out.avg_risk[qi] = ok ? __fdiv_rn(sum_w, (float)plen) : 0.f;
       atomicAdd(out.cursor + 2, s_relax);
+      for (int j = 0; j < 5; ++j) atomicAdd(out.cursor + 3 + j, s_dbg[j]);
       s_poff = (long long)atomicAdd(out.cursor, (unsigned long long)plen);
       out.path_off[qi] = s_poff;
       out.path_len[qi] = plen;
@@ -425,7 +434,7 @@ extern "C" int trgb_sssp_batch(trgb_graph* g, const int32_t* start_ids, const in
   }
   // slots: enough CTAs to fill the machine, bounded by the batch and by ~24 GB of scratch
   const size_t per_slot = (size_t)g->n * (8 + 16) + ((size_t)g->n / 4 + 8);
-  int want = (int)std::min<int64_t>(nq, (int64_t)sm_count() * 8);
+  int want = (int)std::min<int64_t>(nq, (int64_t)sm_count() * (2048 / kSsspThreads));
   want = (int)std::min<size_t>((size_t)want, std::max<size_t>(1, ((size_t)48 << 30) / per_slot));
   int rc = ensure_slots(g, want);
   if (rc) return rc;
@@ -436,11 +445,11 @@ extern "C" int trgb_sssp_batch(trgb_graph* g, const int32_t* start_ids, const in
   DALLOC(d_s, nq * sizeof(int32_t)); DALLOC(d_g, nq * sizeof(int32_t));
   DALLOC(d_found, nq); DALLOC(d_cost, nq * sizeof(float)); DALLOC(d_len, nq * sizeof(float));
   DALLOC(d_risk, nq * sizeof(float)); DALLOC(d_off, nq * sizeof(int64_t)); DALLOC(d_plen, nq * sizeof(int32_t));
-  DALLOC(d_ids, (size_t)path_ids_capacity * sizeof(int32_t)); DALLOC(d_cur, 4 * sizeof(unsigned long long));
+  DALLOC(d_ids, (size_t)path_ids_capacity * sizeof(int32_t)); DALLOC(d_cur, 8 * sizeof(unsigned long long));
 #undef DALLOC
   TRGB_CUDA(cudaMemcpyAsync(d_s.p, start_ids, nq * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   TRGB_CUDA(cudaMemcpyAsync(d_g.p, goal_ids, nq * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  TRGB_CUDA(cudaMemsetAsync(d_cur.p, 0, 4 * sizeof(unsigned long long), st));
+  TRGB_CUDA(cudaMemsetAsync(d_cur.p, 0, 8 * sizeof(unsigned long long), st));
   SsspOut o;
   o.found = (uint8_t*)d_found.p; o.cost = (float*)d_cost.p; o.path_length = (float*)d_len.p;
   o.avg_risk = (float*)d_risk.p; o.path_off = (int64_t*)d_off.p; o.path_len = (int32_t*)d_plen.p;
@@ -456,7 +465,7 @@ extern "C" int trgb_sssp_batch(trgb_graph* g, const int32_t* start_ids, const in
   TRGB_CUDA(cudaGetLastError());
   std::vector<int64_t> off(nq);
   std::vector<int32_t> plen(nq);
-  unsigned long long cursor[4] = {0, 0, 0, 0};
+  unsigned long long cursor[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   TRGB_CUDA(cudaMemcpyAsync(found, d_found.p, nq, cudaMemcpyDeviceToHost, st));
   TRGB_CUDA(cudaMemcpyAsync(cost, d_cost.p, nq * sizeof(float), cudaMemcpyDeviceToHost, st));
   TRGB_CUDA(cudaMemcpyAsync(path_length, d_len.p, nq * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -468,6 +477,9 @@ extern "C" int trgb_sssp_batch(trgb_graph* g, const int32_t* start_ids, const in
   const int64_t total = (int64_t)cursor[0];
   g->relaxed_edges += (int64_t)cursor[2];
   g->queries += nq;
+  if (std::getenv("TRGB_SSSP_STATS"))
+    fprintf(stderr, "[k_sssp] nq=%lld relaxed=%llu passes=%llu thr_steps=%llu far_scanned=%llu expanded=%llu pruned=%llu delta=%g\n", (long long)nq,
+            cursor[2], cursor[3], cursor[4], cursor[5], cursor[6], cursor[7], (double)delta);
   if (total > path_ids_capacity) {
     path_offsets[nq] = total;
     set_error("sssp_batch: path_ids buffer too small; needed size returned in path_offsets[n]");

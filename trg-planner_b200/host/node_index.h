@@ -102,19 +102,35 @@ class OrderTree2D {
   }
 
   // Adopt a tree built elsewhere (trgb_kdtree_build: the same insertion-order tree, grown on the device).
-  void adopt(const float* x, const float* y, int n, std::vector<int>&& lo, std::vector<int>&& hi, std::vector<int>&& parent,
+  // xy: n interleaved (x, y) pairs in insertion order.
+  void adopt(const float* xy, int n, std::vector<int>&& lo, std::vector<int>&& hi, std::vector<int>&& parent,
              std::vector<uint8_t>&& axis) {
     clear();
     if (n <= 0) return;
-    x_.assign(x, x + n); y_.assign(y, y + n);
     lo_ = std::move(lo); hi_ = std::move(hi); parent_ = std::move(parent); axis_ = std::move(axis);
-    payload_.resize(n);
-    bmin_[0] = bmax_[0] = x[0]; bmin_[1] = bmax_[1] = y[0]; have_box_ = true;
-    for (int i = 0; i < n; ++i) {
-      payload_[i] = i;
-      bmin_[0] = std::fmin(bmin_[0], x[i]); bmax_[0] = std::fmax(bmax_[0], x[i]);
-      bmin_[1] = std::fmin(bmin_[1], y[i]); bmax_[1] = std::fmax(bmax_[1], y[i]);
+    x_.resize(n); y_.resize(n); payload_.resize(n);
+    const int parts = std::max(1, std::min(thread_budget(), n / 65536));
+    std::vector<float> box(4 * (size_t)parts);
+    auto fill = [&](int part) {
+      const int b = (int)((int64_t)n * part / parts), e = (int)((int64_t)n * (part + 1) / parts);
+      float x0 = xy[2 * b], x1 = x0, y0 = xy[2 * b + 1], y1 = y0;
+      for (int i = b; i < e; ++i) {
+        const float x = xy[2 * i], y = xy[2 * i + 1];
+        x_[i] = x; y_[i] = y; payload_[i] = i;
+        x0 = std::fmin(x0, x); x1 = std::fmax(x1, x); y0 = std::fmin(y0, y); y1 = std::fmax(y1, y);
+      }
+      box[4 * part] = x0; box[4 * part + 1] = x1; box[4 * part + 2] = y0; box[4 * part + 3] = y1;
+    };
+    std::vector<std::future<void>> helpers;
+    for (int k = 1; k < parts; ++k) helpers.push_back(std::async(std::launch::async, fill, k));
+    fill(0);
+    for (auto& h : helpers) h.get();
+    bmin_[0] = box[0]; bmax_[0] = box[1]; bmin_[1] = box[2]; bmax_[1] = box[3];
+    for (int k = 1; k < parts; ++k) {
+      bmin_[0] = std::fmin(bmin_[0], box[4 * k]); bmax_[0] = std::fmax(bmax_[0], box[4 * k + 1]);
+      bmin_[1] = std::fmin(bmin_[1], box[4 * k + 2]); bmax_[1] = std::fmax(bmax_[1], box[4 * k + 3]);
     }
+    have_box_ = true;
   }
 
   // Order the given tree nodes (indices = insertion order) the way kd_nearest_range2's result

@@ -360,15 +360,21 @@ void TRG::ensureTree(trgStruct& g) {
   // thousands of pending nodes (exact-distance ties during a big build are ~1e-7 per query, so the
   // tree is usually far behind when it is needed) a parallel bulk rebuild of the identical tree wins.
   if (n >= 256 && (g.tree_built == 0 || pending > 20000)) {
-    std::vector<float> xs(n), ys(n);
-    for (size_t i = 0; i < n; ++i) { xs[i] = g.seq_xy[2 * i]; ys[i] = g.seq_xy[2 * i + 1]; }
+    auto ta = Clock::now();
     if (n >= 20000 && trgb_device_count() > 0) {
       // large graph: the same tree, grown on the device one level per round (a few ms instead of ~50)
       std::vector<int> lo(n), hi(n), par(n);
       std::vector<uint8_t> ax(n);
+      auto tb = Clock::now();
       K(trgb_kdtree_build(g.seq_xy.data(), (int64_t)n, lo.data(), hi.data(), par.data(), ax.data()), "trgb_kdtree_build");
-      g.node_tree.adopt(xs.data(), ys.data(), (int)n, std::move(lo), std::move(hi), std::move(par), std::move(ax));
+      auto tc = Clock::now();
+      g.node_tree.adopt(g.seq_xy.data(), (int)n, std::move(lo), std::move(hi), std::move(par), std::move(ax));
+      us_tree_parts_[0] += (int64_t)(1e6 * std::chrono::duration<double>(tb - ta).count());
+      us_tree_parts_[1] += (int64_t)(1e6 * std::chrono::duration<double>(tc - tb).count());
+      us_tree_parts_[2] += (int64_t)(1e6 * since(tc));
     } else {
+      std::vector<float> xs(n), ys(n);
+      for (size_t i = 0; i < n; ++i) { xs[i] = g.seq_xy[2 * i]; ys[i] = g.seq_xy[2 * i + 1]; }
       g.node_tree.build_bulk(xs.data(), ys.data(), (int)n);
     }
     g.tree_built = n;
@@ -1757,6 +1763,9 @@ int64_t TRG::stat(const std::string& what) const {
   if (what == "rng_draws") return (int64_t)draw_next_;
   if (what == "us_draws") return (int64_t)us_draws_;
   if (what == "node_ties") return n_node_ties_;
+  if (what == "us_tree_split") return us_tree_parts_[0];
+  if (what == "us_tree_device") return us_tree_parts_[1];
+  if (what == "us_tree_adopt") return us_tree_parts_[2];
   if (what == "batches") return (int64_t)dev_->batches;
   auto it = stat_.find(what);
   return it == stat_.end() ? 0 : it->second;

@@ -232,6 +232,7 @@ class TRG {
   void ensureGrid(trgStruct& g);
   void ensureGridBuilt(trgStruct& g);
   void ensureTree(trgStruct& g);
+  std::atomic<int64_t> us_tree_parts_[3] = {};  // ensureTree: host split / device build / adopt
   Node* nearestNode(trgStruct& g, float x, float y);
   Node* resolveNearestTie(trgStruct& g, float qx, float qy, float d2min);
   void rangeNodesOrdered(trgStruct& g, float x, float y, float r, std::vector<Node*>& out);
