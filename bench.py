@@ -209,7 +209,7 @@ def run_product(a):
             dist.barrier()
             torch.cuda.synchronize()
 
-    STAT_KEYS = ("us_draws", "pops", "window_tests", "edge_evals", "us_device_bfs", "us_device_edges", "us_materialize",
+    STAT_KEYS = ("us_draws", "pops", "window_tests", "edge_evals", "us_device_bfs", "us_device_finalize", "us_device_edges", "us_materialize",
                  "device_steps", "device_rounds", "device_redo_pops", "device_interrupts", "device_builds",
                  "us_prep_csr", "us_prep_tree", "us_prep_grid", "us_tree_split", "us_tree_device", "us_tree_adopt", "sssp_relaxed_edges", "sssp_queries",
                  "us_commit", "us_clean", "us_wait")

@@ -190,6 +190,23 @@ int  trgb_expander_apply_pop(trgb_expander* e, int n_new, const float* nodes_xyz
 int  trgb_expander_finalize(trgb_expander* e, int64_t* n_nodes, int64_t* n_directed_edges);
 int  trgb_expander_download(trgb_expander* e, float* xyz, int8_t* state, int64_t* row_ptr, int32_t* col, float* weight,
                             float* dist);
+/* Same data as trgb_expander_download, in page-locked memory owned by the engine (valid until the next
+ * trgb_expander_finalize / trgb_expander_destroy): xy = 2 floats per node, z, state per node; CSR over engine ids. */
+typedef struct TrgbExpandedGraph {
+  int64_t n_nodes, n_directed_edges;
+  const float* xy;
+  const float* z;
+  const int8_t* state;
+  const int64_t* row_ptr;
+  const int32_t* col;
+  const float* weight;
+  const float* dist;
+} TrgbExpandedGraph;
+int  trgb_expander_download_view(trgb_expander* e, TrgbExpandedGraph* out);
+/* The K7 search graph of the cleaned graph, built on the device from the finalized arrays (nothing crosses
+ * PCIe but old2new): old2new[i] = id of engine node i after TRG::cleanGraph (trg.cpp:491-535) or -1 = dropped;
+ * n_new = number of kept nodes (new ids are 0 .. n_new-1). The handle is used like one from trgb_graph_upload. */
+int trgb_expander_make_graph(trgb_expander* e, const int32_t* old2new, int32_t n_new, trgb_graph** out);
 
 /* ---- K8: voxel-grid centroid filter — the optional down-sampling of the map ingestion,
  *      TRGPlanner::loadPrebuiltMap -> pcl::VoxelGrid (src/planner/trg_planner.cpp:90-94). One output

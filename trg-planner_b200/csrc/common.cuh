@@ -539,6 +539,24 @@ int sort_pairs_u64_u32(const unsigned long long* kin, unsigned long long* kout, 
 int exclusive_sum_u32(const uint32_t* in, uint32_t* out, int n, cudaStream_t st);
 bool prof_enabled();                 // the CUDA-event profiler is recording (core.cu)
 void count_launches(int64_t n);      // kernels launched through a replayed CUDA graph (core.cu)
+// K7 search graph from CSR arrays resident on the device (sssp.cu). Source numbering 0 .. n_src-1; src2ext[i] =
+// the caller's id of source node i or -1 (node dropped), nullptr = identity. Exactly one of xy / xyz and of
+// state8 / state32 is set.
+struct GraphSource {
+  int32_t n_src = 0, n_keep = 0, n_ext = 0;
+  int64_t e_src = 0;
+  const long long* row = nullptr;
+  const int32_t* col = nullptr;
+  const float* w = nullptr;
+  const float* dist = nullptr;
+  const float2* xy = nullptr;
+  const float* xyz = nullptr;
+  const signed char* state8 = nullptr;
+  const int32_t* state32 = nullptr;
+  const int32_t* src2ext = nullptr;
+};
+int graph_from_device(trgb_graph** out, const GraphSource& src, cudaStream_t build_stream);
+
 void tune_mempool_once();  // raise the default mempool's release threshold (map_index.cu)
 int sm_count();
 int grid_for_warps(int64_t n_warps, int ctas_per_sm);

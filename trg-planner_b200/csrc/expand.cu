@@ -1061,6 +1061,9 @@ struct trgb_expander {
   long long* d_row = nullptr; int* d_col = nullptr; float* d_w = nullptr; float* d_d = nullptr;
   int n_dir = 0;
   int n_nodes_final = 0;
+  // pinned host staging of trgb_expander_download_view (grow-only: page-locking 70 MB costs tens of ms)
+  void* h_pin = nullptr;
+  size_t h_pin_bytes = 0;
 };
 
 static void drop_graphs(trgb_expander* e);
@@ -1091,6 +1094,7 @@ extern "C" void trgb_expander_destroy(trgb_expander* e) {
     if (e->h_status[k]) cudaFreeHost(e->h_status[k]);
     if (e->ev[k]) cudaEventDestroy(e->ev[k]);
   }
+  if (e->h_pin) cudaFreeHost(e->h_pin);
   if (e->d_row) cudaFreeAsync(e->d_row, 0);
   if (e->d_col) cudaFreeAsync(e->d_col, 0);
   if (e->d_w) cudaFreeAsync(e->d_w, 0);
@@ -1558,6 +1562,72 @@ extern "C" int trgb_expander_finalize(trgb_expander* e, int64_t* n_nodes, int64_
   *n_nodes = nn;
   *n_dir_edges = n_dir;
   return TRGB_OK;
+}
+
+// The finalized graph in page-locked host memory owned by the engine (valid until the next finalize / destroy):
+// one DMA per array at full PCIe rate into buffers that are locked once, instead of pageable copies into vectors
+// the caller has just allocated (and faults in page by page).
+extern "C" int trgb_expander_download_view(trgb_expander* e, TrgbExpandedGraph* out) {
+  TRGB_ARG(e && e->d_row && out, "finalize first");
+  const size_t nn = (size_t)e->n_nodes_final, nd = (size_t)e->n_dir;
+  auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t o_xy = 0, o_z = o_xy + up(nn * sizeof(float2)), o_state = o_z + up(nn * sizeof(float)),
+               o_row = o_state + up(nn), o_col = o_row + up((nn + 1) * sizeof(long long)), o_w = o_col + up(nd * sizeof(int)),
+               o_d = o_w + up(nd * sizeof(float)), total = o_d + up(nd * sizeof(float));
+  if (total > e->h_pin_bytes) {
+    if (e->h_pin) cudaFreeHost(e->h_pin);
+    e->h_pin = nullptr; e->h_pin_bytes = 0;
+    const size_t want = total + total / 8;
+    TRGB_CUDA(cudaHostAlloc(&e->h_pin, want, cudaHostAllocDefault));
+    e->h_pin_bytes = want;
+  }
+  char* h = static_cast<char*>(e->h_pin);
+  cudaStream_t st = e->st;
+  TRGB_CUDA(cudaMemcpyAsync(h + o_xy, e->v.node_xy, nn * sizeof(float2), cudaMemcpyDeviceToHost, st));
+  TRGB_CUDA(cudaMemcpyAsync(h + o_z, e->v.node_z, nn * sizeof(float), cudaMemcpyDeviceToHost, st));
+  TRGB_CUDA(cudaMemcpyAsync(h + o_state, e->v.node_state, nn, cudaMemcpyDeviceToHost, st));
+  TRGB_CUDA(cudaMemcpyAsync(h + o_row, e->d_row, (nn + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  if (nd) {
+    TRGB_CUDA(cudaMemcpyAsync(h + o_col, e->d_col, nd * sizeof(int), cudaMemcpyDeviceToHost, st));
+    TRGB_CUDA(cudaMemcpyAsync(h + o_w, e->d_w, nd * sizeof(float), cudaMemcpyDeviceToHost, st));
+    TRGB_CUDA(cudaMemcpyAsync(h + o_d, e->d_d, nd * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  TRGB_CUDA(cudaStreamSynchronize(st));
+  out->n_nodes = (int64_t)nn;
+  out->n_directed_edges = (int64_t)nd;
+  out->xy = reinterpret_cast<const float*>(h + o_xy);
+  out->z = reinterpret_cast<const float*>(h + o_z);
+  out->state = reinterpret_cast<const int8_t*>(h + o_state);
+  out->row_ptr = reinterpret_cast<const int64_t*>(h + o_row);
+  out->col = reinterpret_cast<const int32_t*>(h + o_col);
+  out->weight = reinterpret_cast<const float*>(h + o_w);
+  out->dist = reinterpret_cast<const float*>(h + o_d);
+  return TRGB_OK;
+}
+
+// K7 search graph straight from the finalized arrays (no trip through the host): old2new[i] = id of node i in
+// the cleaned graph or -1 (dropped by cleanGraph), n_new = number of kept nodes = id range of the new graph.
+extern "C" int trgb_expander_make_graph(trgb_expander* e, const int32_t* old2new, int32_t n_new, trgb_graph** out) {
+  TRGB_ARG(e && e->d_row && old2new && out, "finalize first");
+  const int nn = e->n_nodes_final;
+  TRGB_ARG(n_new > 0 && n_new <= nn, "bad node count");
+  int kept = 0;
+  for (int i = 0; i < nn; ++i) {
+    TRGB_ARG(old2new[i] >= -1 && old2new[i] < n_new, "old2new out of range");
+    kept += old2new[i] >= 0;
+  }
+  TRGB_ARG(kept == n_new, "old2new does not keep n_new nodes");
+  cudaStream_t st = e->st;
+  int32_t* d_map = nullptr;
+  TRGB_CUDA(cudaMallocAsync((void**)&d_map, (size_t)nn * sizeof(int32_t), st));
+  TRGB_CUDA(cudaMemcpyAsync(d_map, old2new, (size_t)nn * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  GraphSource s;
+  s.n_src = nn; s.n_keep = n_new; s.n_ext = n_new; s.e_src = e->n_dir;
+  s.row = e->d_row; s.col = e->d_col; s.w = e->d_w; s.dist = e->d_d;
+  s.xy = e->v.node_xy; s.state8 = e->v.node_state; s.src2ext = d_map;
+  const int rc = graph_from_device(out, s, st);
+  cudaFreeAsync(d_map, st);
+  return rc;
 }
 
 extern "C" int trgb_expander_download(trgb_expander* e, float* xyz, int8_t* state, int64_t* row_ptr, int32_t* col, float* weight,

@@ -17,6 +17,7 @@
 #include <future>
 #include <thread>
 #include <limits>
+#include <mutex>
 #include <vector>
 
 namespace trg_b200 {
@@ -398,6 +399,7 @@ class NodeGrid {
     cells_.assign(static_cast<size_t>(bw_) * bh * kTile * kTile, Cell{});
     over_.clear();
     count_ = 0;
+    stale_ = false;
   }
   // prefetch the buckets a nearest() query at (qx, qy) will read first
   void prefetch(float qx, float qy) const {
@@ -408,15 +410,55 @@ class NodeGrid {
         if (xx >= 0 && yy >= 0 && xx < w_ && yy < h_) __builtin_prefetch(&cells_[cidx(xx, yy)], 0, 1);
   }
   bool configured() const { return w_ > 0; }
+  // Emptying is deferred: queries on an empty grid return at once, the next insert() wipes the buckets, and
+  // rebuild() wipes them band by band on its helper threads (31 MB for a 300 m map: 3 ms if done serially).
   void clear() {
-    std::fill(cells_.begin(), cells_.end(), Cell{});
-    over_.clear();
+    if (count_ == 0 && over_.empty() && !stale_) return;
+    stale_ = true;
     count_ = 0;
   }
   size_t size() const { return count_; }
 
+  // The grid over n points at once (entry i = point i, as n insert() calls would number them): helper threads
+  // own contiguous bands of bucket tiles, wipe them and insert the points that fall inside.
+  void rebuild(const float* xy, int n, int threads) {
+    over_.clear();
+    const size_t tiles = cells_.size() / (kTile * kTile);
+    threads = static_cast<int>(std::max<size_t>(1, std::min<size_t>(static_cast<size_t>(std::max(1, threads)), tiles)));
+    std::mutex over_mx;
+    auto band = [&](int t) {
+      const size_t c0 = tiles * t / threads * (kTile * kTile), c1 = tiles * (t + 1) / threads * (kTile * kTile);
+      std::fill(cells_.begin() + c0, cells_.begin() + c1, Cell{});
+      for (int i = 0; i < n; ++i) {
+        const float x = xy[2 * i], y = xy[2 * i + 1];
+        const size_t ci = cidx(cx(x), cy(y));
+        if (ci < c0 || ci >= c1) continue;
+        Cell& c = cells_[ci];
+        if (c.n < kInline) {
+          c.x[c.n] = x; c.y[c.n] = y; c.id[c.n] = i;
+          ++c.n;
+        } else {
+          std::lock_guard<std::mutex> lk(over_mx);
+          over_.push_back({x, y, i, c.over});
+          c.over = static_cast<int>(over_.size()) - 1;
+        }
+      }
+    };
+    std::vector<std::future<void>> helpers;
+    for (int t = 1; t < threads; ++t) helpers.push_back(std::async(std::launch::async, band, t));
+    band(0);
+    for (auto& h : helpers) h.get();
+    stale_ = false;
+    count_ = static_cast<size_t>(n);
+  }
+
   // entries are numbered in insertion order (0, 1, 2, ...)
   int insert(float x, float y) {
+    if (stale_) {
+      std::fill(cells_.begin(), cells_.end(), Cell{});
+      over_.clear();
+      stale_ = false;
+    }
     const int id = static_cast<int>(count_++);
     Cell& c = cells_[cidx(cx(x), cy(y))];
     if (c.n < kInline) {
@@ -558,6 +600,7 @@ class NodeGrid {
   float cell_ = 1.f, inv_ = 1.f, x0_ = 0.f, y0_ = 0.f;
   int w_ = 0, h_ = 0, bw_ = 0;
   size_t count_ = 0;
+  bool stale_ = false;  // buckets still hold entries of before the last clear()
   std::vector<Cell> cells_;
   std::vector<Over> over_;
 };

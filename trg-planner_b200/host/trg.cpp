@@ -1458,23 +1458,12 @@ void TRG::invalidateDeviceGraph() {
   if (dev_graph_) trgb_graph_destroy(dev_graph_);
   dev_graph_ = nullptr;
   dev_graph_relaxed_ = 0;
-  csr_cache_.valid = false;
   dev_graph_nodes_.clear();
 }
 
 void TRG::ensureDeviceGraph() {
   if (dev_graph_) return;
   trgStruct& g = *trgMap_["global"];
-  if (csr_cache_.valid) {
-    // prepared by the device build from its flat arrays: no walk over half a million Node objects
-    CsrCache& c = csr_cache_;
-    const int n = (int)c.state.size();
-    dev_graph_nodes_.resize(n);
-    for (int k = 0; k < n; ++k) dev_graph_nodes_[k] = &node_pool_[(size_t)k];  // the device build numbers nodes by pool slot
-    TrgbGraphDesc desc{n, (int64_t)c.col.size(), c.row.data(), c.col.data(), c.w.data(), c.d.data(), c.pos.data(), c.state.data()};
-    K(trgb_graph_upload(&dev_graph_, &desc), "trgb_graph_upload");
-    return;
-  }
   // rows by node id; every node of the map is in node_seq with id_ == its key (see cleanGraph)
   int max_id = -1;
   for (Node* nd : g.node_seq) max_id = std::max(max_id, nd->id_);

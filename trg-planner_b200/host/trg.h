@@ -259,13 +259,7 @@ class TRG {
   const trgb_map* expander_map_ = nullptr;
 
   std::unique_ptr<trg_b200::DeviceSession> dev_;
-  // CSR of the global graph prepared while it was materialised (device build): uploaded as is by ensureDeviceGraph
-  struct CsrCache {
-    bool valid = false;
-    std::vector<int64_t> row;
-    std::vector<int32_t> col, state;
-    std::vector<float> w, d, pos;
-  } csr_cache_;
+  // K7 search graph of the global graph: built on the device by the device build, else uploaded by ensureDeviceGraph
   trgb_graph* dev_graph_ = nullptr;
   int64_t dev_graph_relaxed_ = 0;  // edges relaxed by the handle so far (already booked in stat_)
   std::vector<Node*> dev_graph_nodes_;  // row -> node of the uploaded CSR

@@ -308,11 +308,14 @@ bool TRG::buildGraphOnDevice(trgStruct& g) {
   auto t_fin = Clock::now();
   int64_t n_all = 0, n_dir = 0;
   K(trgb_expander_finalize(e, &n_all, &n_dir), "trgb_expander_finalize");
-  std::vector<float> xyz((size_t)n_all * 3), ew((size_t)n_dir), ed((size_t)n_dir);
-  std::vector<int8_t> state((size_t)n_all);
-  std::vector<int64_t> row((size_t)n_all + 1);
-  std::vector<int32_t> col((size_t)n_dir);
-  K(trgb_expander_download(e, xyz.data(), state.data(), row.data(), col.data(), ew.data(), ed.data()), "trgb_expander_download");
+  const double t_finalize = since(t_fin);
+  TrgbExpandedGraph dl{};
+  K(trgb_expander_download_view(e, &dl), "trgb_expander_download_view");
+  const float *xy = dl.xy, *zz = dl.z, *ew = dl.weight, *ed = dl.dist;
+  const int8_t* state = dl.state;
+  const int64_t* row = dl.row_ptr;
+  const int32_t* col = dl.col;
+  (void)n_dir;
   const double t_edges = since(t_fin);
 
   // ---- cleanGraph(false) (trg.cpp:491-535), straight into the cleaned containers ------------------
@@ -329,6 +332,47 @@ bool TRG::buildGraphOnDevice(trgStruct& g) {
     kept.push_back(id);
   }
   const size_t m = kept.size();
+  // the K7 search graph of the cleaned graph, built by the device from the arrays it still holds
+  struct GraphGuard {
+    trgb_graph* g = nullptr;
+    ~GraphGuard() { if (g) trgb_graph_destroy(g); }
+  } search_graph;
+  if (m > 0) K(trgb_expander_make_graph(e, old2new.data(), (int32_t)m, &search_graph.g), "trgb_expander_make_graph");
+  const int threads = m > (size_t)tuning_.parallel_min_nodes ? trg_b200::thread_budget() : 1;
+
+  // The old containers go first, so that the index structures of the new graph (what the reference's cleanGraph
+  // rebuilds as node_tree, :528-530) can grow on helper threads while the node objects are filled. The renumbered
+  // map's iteration order (the insertion order of that tree) is again that of a sequentially filled fresh map.
+  std::unordered_map<int, Node*> old_nodes;
+  old_nodes.swap(g.nodes);
+  this->resetGraph(g.type);
+  this->resetGraph("local");
+  const std::vector<int> order2 = sequential_map_order(m, 1);
+  g.seq_xy.resize(2 * m);
+  parallel_for(m, threads, [&](size_t b, size_t en) {
+    for (size_t i = b; i < en; ++i) {
+      const size_t old = (size_t)kept[(size_t)order2[i]];
+      g.seq_xy[2 * i] = xy[2 * old];
+      g.seq_xy[2 * i + 1] = xy[2 * old + 1];
+    }
+  });
+  std::future<void> f_grid, f_tree;
+  const bool eager_index = m >= 20000;
+  if (eager_index) {
+    ensureGrid(g);
+    f_grid = std::async(std::launch::async, [&] { g.node_grid.rebuild(g.seq_xy.data(), (int)m, std::max(1, threads / 2)); });
+    f_tree = std::async(std::launch::async, [&] {
+      std::vector<int> lo(m), hi(m), par(m);
+      std::vector<uint8_t> ax(m);
+      K(trgb_kdtree_build(g.seq_xy.data(), (int64_t)m, lo.data(), hi.data(), par.data(), ax.data()), "trgb_kdtree_build");
+      g.node_tree.adopt(g.seq_xy.data(), (int)m, std::move(lo), std::move(hi), std::move(par), std::move(ax));
+    });
+  }
+  struct Joiner {  // the helpers reference this frame: never leave it (exception included) before they are done
+    std::future<void>&a, &b;
+    ~Joiner() { if (a.valid()) a.wait(); if (b.valid()) b.wait(); }
+  } joiner{f_grid, f_tree};
+
   // node / edge objects from the pools (recycled across builds), filled in parallel
   rewindPools();
   while (node_pool_.size() < m) {
@@ -346,28 +390,20 @@ bool TRG::buildGraphOnDevice(trgStruct& g) {
   while (edge_pool_.size() < e_total) edge_pool_.emplace_back(0, 0.f, 0.f);
   node_used_ = m;
   edge_used_ = e_total;
-  const int threads = m > (size_t)tuning_.parallel_min_nodes ? trg_b200::thread_budget() : 1;
-  CsrCache csr;   // the cleaned graph as CSR (rows = new ids): what K7 uploads, prepared in the same pass
-  csr.row.resize(m + 1); csr.col.resize(e_total); csr.w.resize(e_total); csr.d.resize(e_total);
-  csr.pos.resize(3 * m); csr.state.resize(m);
-  for (size_t k = 0; k <= m; ++k) csr.row[k] = (int64_t)e_off[k];
+  dev_graph_nodes_.resize(m);
   parallel_for(m, threads, [&](size_t b, size_t en) {
     for (size_t k = b; k < en; ++k) {
       const int old = kept[k];
       Node& nd = node_pool_[k];
-      csr.pos[3 * k] = xyz[3 * (size_t)old]; csr.pos[3 * k + 1] = xyz[3 * (size_t)old + 1]; csr.pos[3 * k + 2] = xyz[3 * (size_t)old + 2];
-      csr.state[k] = (int32_t)state[old];
+      dev_graph_nodes_[k] = &nd;  // the search graph numbers nodes by pool slot
       nd.id_ = (int)k;
-      nd.pos_ = Eigen::Vector3f(xyz[3 * (size_t)old], xyz[3 * (size_t)old + 1], xyz[3 * (size_t)old + 2]);
+      nd.pos_ = Eigen::Vector3f(xy[2 * (size_t)old], xy[2 * (size_t)old + 1], zz[(size_t)old]);
       nd.state_ = static_cast<NodeState>((int)state[old]);
       nd.edges_.clear();
       size_t eo = e_off[k];
       for (int64_t j = row[old]; j < row[old + 1]; ++j) {
         // no edge leads to an Invalid node here (a node is Invalid from birth and never wired, :411), so
         // the del_edges filter of :505-517 keeps everything; ids are remapped (:518)
-        csr.col[eo] = old2new[col[(size_t)j]];
-        csr.w[eo] = ew[(size_t)j];
-        csr.d[eo] = ed[(size_t)j];
         Edge& ed2 = edge_pool_[eo++];
         ed2.dst_id_ = old2new[col[(size_t)j]];
         ed2.weight_ = ew[(size_t)j];
@@ -381,26 +417,14 @@ bool TRG::buildGraphOnDevice(trgStruct& g) {
   map_stop.store(true, std::memory_order_release);
   map_builder.join();
   if (new_nodes.size() != m) throw std::logic_error("trg_b200: renumbered map out of step with the survivors");
-  // its iteration order (needed for node_tree, :528-530) is again that of a sequentially filled fresh map
-  const std::vector<int> order2 = sequential_map_order(m, 1);
   parallel_for(m, threads, [&](size_t b, size_t en) {
     for (size_t k = b; k < en; ++k) new_nodes.find((int)k)->second = &node_pool_[k];
   });
-  std::unordered_map<int, Node*> old_nodes;
-  old_nodes.swap(g.nodes);
-  this->resetGraph(g.type);
-  this->resetGraph("local");
   g.nodes   = std::move(new_nodes);
   g.node_id = (int)m;
   g.node_seq.resize(m);
-  g.seq_xy.resize(2 * m);
   parallel_for(m, threads, [&](size_t b, size_t en) {
-    for (size_t i = b; i < en; ++i) {
-      const size_t k = (size_t)order2[i];
-      g.node_seq[i] = &node_pool_[k];
-      g.seq_xy[2 * i] = csr.pos[3 * k];
-      g.seq_xy[2 * i + 1] = csr.pos[3 * k + 1];
-    }
+    for (size_t i = b; i < en; ++i) g.node_seq[i] = &node_pool_[(size_t)order2[i]];
   });
 #ifndef NDEBUG
   {
@@ -408,9 +432,12 @@ bool TRG::buildGraphOnDevice(trgStruct& g) {
     for (auto& node : g.nodes) assert(node.second == g.node_seq[i++]);
   }
 #endif
-  invalidateDeviceGraph();
-  csr.valid = true;
-  csr_cache_ = std::move(csr);
+  if (f_grid.valid()) f_grid.get();
+  if (f_tree.valid()) f_tree.get();
+  if (eager_index) g.grid_built = g.tree_built = m;
+  dev_graph_ = search_graph.g;  // (resetGraph above dropped the previous one)
+  search_graph.g = nullptr;
+  dev_graph_relaxed_ = 0;
   const double t_materialize = since(t_mat);
 
   stat_["pops"] += st.pops;
@@ -429,6 +456,7 @@ bool TRG::buildGraphOnDevice(trgStruct& g) {
   stat_["edge_evals"] += st.n_req;
   stat_["us_device_bfs"] += (int64_t)(1e6 * t_bfs);
   stat_["us_device_edges"] += (int64_t)(1e6 * t_edges);
+  stat_["us_device_finalize"] += (int64_t)(1e6 * t_finalize);
   stat_["us_materialize"] += (int64_t)(1e6 * t_materialize);
   return true;
 }
