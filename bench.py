@@ -255,7 +255,7 @@ def run_product(a):
                         snap_ms=round(1e3 * (t.seconds("plan_snap") - t.seconds("plan_prep")), 2),
                         plan_ms=round(1e3 * t.seconds("plan_batch"), 2))
         return dict(host=host, build_s=w1 - w0, exch_s=w2 - w1, query_s=w3 - w2, step_s=w3 - w0, nodes=nn, edges=ne,
-                    found=found, d2h=d2h, xbytes=xb)
+                    found=found, d2h=d2h, xbytes=xb, merged=dict(merged_stats))
 
     def timed(resident: bool, warmup: int, steps: int):
         # nvidia-smi is started BEFORE the warm-up: its start-up (NVML init) holds driver locks for
@@ -411,7 +411,7 @@ def run_product(a):
         line["verify"] = verify
     if world > 1:
         line["exchange"] = {"leg": "value (resident cloud), last timed step of rank 0", "bytes_per_step": last["xbytes"],
-                            "tile_build_ms_max": 1e3 * v_tile, "merge_ms_rank0": 1e3 * val["exch_s"], **merged_stats}
+                            "tile_build_ms_max": 1e3 * v_tile, "merge_ms_rank0": 1e3 * val["exch_s"], **val["rows"][-1]["merged"]}
     if saved_stdout is not None:
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)

@@ -233,6 +233,8 @@ typedef struct TrgbGraphDesc {
 } TrgbGraphDesc;
 
 int  trgb_graph_upload(trgb_graph** out, const TrgbGraphDesc* g);
+/* the same with every array of the descriptor resident on the device (stream = where they were produced) */
+int  trgb_graph_upload_device(trgb_graph** out, const TrgbGraphDesc* g_on_device, void* stream);
 void trgb_graph_destroy(trgb_graph* g);
 /* n (start, goal) node-id pairs. Outputs per query: found; cost = float-accumulated
  * g(goal) = sum (sf*w+1)*dist in the reference's evaluation order (trg.cpp:674);

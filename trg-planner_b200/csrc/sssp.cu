@@ -171,6 +171,17 @@ __global__ void __launch_bounds__(256) k_g_fill(int n, const uint32_t* __restric
   }
 }
 
+// a CSR that does not describe n rows over e columns would be read out of bounds: flag it
+__global__ void __launch_bounds__(256) k_g_validate(int n, long long e, const long long* __restrict__ row,
+                                                    const int32_t* __restrict__ col, int* __restrict__ bad) {
+  const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x, GT = (long long)gridDim.x * blockDim.x;
+  if (gt == 0 && (row[0] != 0 || row[n] != e)) atomicOr(bad, 1);
+  for (long long i = gt; i < n; i += GT)
+    if (row[i] > row[i + 1]) atomicOr(bad, 2);
+  for (long long j = gt; j < e; j += GT)
+    if (col[j] < 0 || col[j] >= n) atomicOr(bad, 4);
+}
+
 __global__ void __launch_bounds__(256) k_g_sum(const float* __restrict__ dist, const int4* __restrict__ sentinel,
                                                double* __restrict__ partial) {
   __shared__ double s[256];
@@ -643,6 +654,33 @@ extern "C" int trgb_graph_upload(trgb_graph** out, const TrgbGraphDesc* d) {
     if (p) cudaFreeAsync(p, st);
   cudaStreamSynchronize(st);  // the host arrays may go away after return
   cudaStreamDestroy(st);
+  return rc;
+}
+
+// Same as trgb_graph_upload with every array of the descriptor already resident on the device (e.g. a graph
+// merged from several tiles by torch ops): nothing crosses PCIe. `stream` = the stream the arrays were produced on.
+extern "C" int trgb_graph_upload_device(trgb_graph** out, const TrgbGraphDesc* d, void* stream) {
+  TRGB_ARG(out && d, "null pointer");
+  TRGB_ARG(d->n_nodes > 0 && d->row_ptr && d->pos_xyz && d->state, "empty graph");
+  TRGB_ARG(d->n_edges >= 0 && (d->n_edges == 0 || (d->col && d->weight && d->dist)), "null edge arrays");
+  trgb::tune_mempool_once();
+  cudaStream_t st = (cudaStream_t)stream;
+  int* d_bad = nullptr;
+  TRGB_CUDA(cudaMallocAsync((void**)&d_bad, sizeof(int), st));
+  TRGB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+  k_g_validate<<<sm_count() * 4, 256, 0, st>>>(d->n_nodes, (long long)d->n_edges, (const long long*)d->row_ptr, d->col, d_bad);
+  int bad = 0;
+  TRGB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+  TRGB_CUDA(cudaStreamSynchronize(st));
+  cudaFreeAsync(d_bad, st);
+  TRGB_ARG(!(bad & 1), "row_ptr does not span the edge arrays");
+  TRGB_ARG(!(bad & 2), "row_ptr is not monotonic");
+  TRGB_ARG(!(bad & 4), "edge to a node id outside the graph");
+  GraphSource s;
+  s.n_src = d->n_nodes; s.n_keep = d->n_nodes; s.n_ext = d->n_nodes; s.e_src = d->n_edges;
+  s.row = (const long long*)d->row_ptr; s.col = d->col; s.w = d->weight; s.dist = d->dist; s.xyz = d->pos_xyz; s.state32 = d->state;
+  const int rc = graph_from_device(out, s, st);
+  if (!rc) TRGB_CUDA(cudaStreamSynchronize(st));  // the caller's arrays may go away after return
   return rc;
 }
 

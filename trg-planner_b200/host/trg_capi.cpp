@@ -107,28 +107,55 @@ int trg_graph_export(void* h, const char* type, int32_t* iter_ids, int32_t* ids_
     std::vector<std::pair<int, TRG::Node*>> ids;
     ids.reserve(g.size());
     int64_t k = 0;
+    bool dense = true;  // keys are exactly 0 .. n-1 (every cleaned graph): rows are placed by key instead of sorted
+    const int64_t n = (int64_t)g.size();
     for (auto& kv : g) {
       if (iter_ids) iter_ids[k] = kv.first;
       ids.emplace_back(kv.first, kv.second);
+      dense = dense && kv.first >= 0 && kv.first < n;
       ++k;
     }
-    std::sort(ids.begin(), ids.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
-    const bool want_edges = row_ptr || col || weight || dist;
-    int64_t e = 0;
-    for (size_t i = 0; i < ids.size(); ++i) {
-      TRG::Node* n = ids[i].second;
-      if (ids_sorted) ids_sorted[i] = ids[i].first;
-      if (pos_xyz) { pos_xyz[3 * i] = n->pos_.x(); pos_xyz[3 * i + 1] = n->pos_.y(); pos_xyz[3 * i + 2] = n->pos_.z(); }
-      if (state) state[i] = (int32_t)n->state_;
-      if (row_ptr) row_ptr[i] = e;
-      if (!want_edges) continue;
-      for (auto* ed : n->edges_) {
-        if (col) col[e] = ed->dst_id_;
-        if (weight) weight[e] = ed->weight_;
-        if (dist) dist[e] = ed->dist_;
-        ++e;
+    if (dense) {
+      std::vector<std::pair<int, TRG::Node*>> by_key((size_t)n, {-1, nullptr});
+      for (auto& p : ids) {
+        if (by_key[(size_t)p.first].second) { dense = false; break; }
+        by_key[(size_t)p.first] = p;
       }
+      if (dense) ids.swap(by_key);
     }
+    if (!dense) std::sort(ids.begin(), ids.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    const bool want_edges = row_ptr || col || weight || dist;
+    // rows are independent once their first edge slot is known: offsets first, then helper threads fill
+    std::vector<int64_t> first(ids.size() + 1, 0);
+    if (want_edges)
+      for (size_t i = 0; i < ids.size(); ++i) first[i + 1] = first[i] + (int64_t)ids[i].second->edges_.size();
+    auto fill = [&](size_t b0, size_t e0) {
+      for (size_t i = b0; i < e0; ++i) {
+        TRG::Node* nd = ids[i].second;
+        if (ids_sorted) ids_sorted[i] = ids[i].first;
+        if (pos_xyz) { pos_xyz[3 * i] = nd->pos_.x(); pos_xyz[3 * i + 1] = nd->pos_.y(); pos_xyz[3 * i + 2] = nd->pos_.z(); }
+        if (state) state[i] = (int32_t)nd->state_;
+        if (row_ptr) row_ptr[i] = first[i];
+        if (!want_edges) continue;
+        int64_t e = first[i];
+        for (auto* ed : nd->edges_) {
+          if (col) col[e] = ed->dst_id_;
+          if (weight) weight[e] = ed->weight_;
+          if (dist) dist[e] = ed->dist_;
+          ++e;
+        }
+      }
+    };
+    const int threads = ids.size() >= 65536 ? trg_b200::thread_budget() : 1;
+    if (threads <= 1) {
+      fill(0, ids.size());
+    } else {
+      std::vector<std::future<void>> jobs;
+      for (int t = 0; t < threads; ++t)
+        jobs.push_back(std::async(std::launch::async, fill, ids.size() * t / threads, ids.size() * (t + 1) / threads));
+      for (auto& j : jobs) j.get();
+    }
+    const int64_t e = first[ids.size()];
     if (row_ptr) row_ptr[ids.size()] = e;
     return 0;
   });

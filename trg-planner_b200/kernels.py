@@ -70,6 +70,7 @@ def lib():
         L.trgb_sample_window_launch.argtypes = [_vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_float,
                                                 C.c_float, C.c_float, _vp]
         L.trgb_graph_upload.argtypes = [C.POINTER(_vp), C.POINTER(GraphDesc)]
+        L.trgb_graph_upload_device.argtypes = [C.POINTER(_vp), C.POINTER(GraphDesc), _vp]
         L.trgb_graph_destroy.argtypes = [_vp]
         L.trgb_graph_destroy.restype = None
         L.trgb_sssp_batch.argtypes = [_vp, _vp, _vp, C.c_int64, C.c_float] + [_vp] * 6 + [C.c_int64]
@@ -282,6 +283,23 @@ class DeviceGraph:
                       _p(self.dist), _p(self.pos), _p(self.state))
         self.h = _vp()
         _chk(lib().trgb_graph_upload(C.byref(self.h), C.byref(d)), "trgb_graph_upload")
+
+    @classmethod
+    def from_device(cls, row_ptr, col, weight, dist, pos_xyz, state):
+        """The same graph from torch CUDA tensors (int64 row_ptr, int32 col / state, float32 rest): no PCIe trip."""
+        import torch
+        self = cls.__new__(cls)
+        t = dict(row_ptr=row_ptr.to(torch.int64).contiguous(), col=col.to(torch.int32).contiguous(),
+                 weight=weight.to(torch.float32).contiguous(), dist=dist.to(torch.float32).contiguous(),
+                 pos=pos_xyz.to(torch.float32).contiguous(), state=state.to(torch.int32).contiguous())
+        assert all(v.is_cuda for v in t.values())
+        vp = lambda x: C.c_void_p(x.data_ptr())
+        d = GraphDesc(int(t["state"].shape[0]), int(t["col"].shape[0]), vp(t["row_ptr"]), vp(t["col"]), vp(t["weight"]),
+                      vp(t["dist"]), vp(t["pos"]), vp(t["state"]))
+        self.h = _vp()
+        stream = torch.cuda.current_stream().cuda_stream
+        _chk(lib().trgb_graph_upload_device(C.byref(self.h), C.byref(d), C.c_void_p(stream)), "trgb_graph_upload_device")
+        return self
 
     def close(self):
         if self.h:

@@ -145,15 +145,18 @@ def stitch_tiles(dist, torch, device, rank: int, world: int, tile_pts: np.ndarra
     side = np.concatenate([np.zeros(left.size), np.ones(right.size)]).astype(np.float32)
     ids_f = np.ascontiguousarray(node_ids[sel], np.int32).view(np.float32)   # ids travel bit-cast
     nodes_rows = np.column_stack([node_pos[sel], ids_f, side]).astype(np.float32) if sel.size else np.zeros((0, 5), np.float32)
+    lap("select_nodes_ms")
     if hasattr(tile_pts, "is_cuda"):
         # the tile's cloud as a torch tensor (resident in HBM on the GPU box): select the strips there
         px = tile_pts[:, 0]
         parts = []
         if rank > 0:
-            pl = tile_pts[px < x_lo + strip][:, :3]
+            ml = px < float(x_lo + strip)
+            pl = tile_pts[ml][:, :3]
             parts.append(torch.cat([pl, torch.zeros((pl.shape[0], 1), dtype=pl.dtype, device=pl.device)], 1))
         if rank < world - 1:
-            pr = tile_pts[px > x_hi - strip][:, :3]
+            mr = px > float(x_hi - strip)
+            pr = tile_pts[mr][:, :3]
             parts.append(torch.cat([pr, torch.ones((pr.shape[0], 1), dtype=pr.dtype, device=pr.device)], 1))
         strip_rows = torch.cat(parts).to(torch.float32) if parts else torch.zeros((0, 4), dtype=torch.float32, device=device)
     else:
@@ -170,7 +173,7 @@ def stitch_tiles(dist, torch, device, rank: int, world: int, tile_pts: np.ndarra
             pl, pr = sub[is_left], sub[~is_left]
         strip_rows = np.concatenate([np.column_stack([pl, np.zeros(len(pl), np.float32)]),
                                      np.column_stack([pr, np.ones(len(pr), np.float32)])]).astype(np.float32)
-    lap("select_ms")
+    lap("select_strips_ms")
     all_nodes = allgather_rows(dist, torch, nodes_rows, device)
     lap("gather_nodes_ms")   # first collective of the step: includes waiting for the slowest rank's build
     all_strips = allgather_rows(dist, torch, strip_rows, device)
@@ -238,24 +241,28 @@ def merge_graphs(dist, torch, device, rank, world, local, stitched):
     (rows rank_a, id_a, rank_b, id_b, weight, dist) -> ONE global CSR, identical on every rank.
     Global id = node offset of the owner rank + local id; a node's edge list keeps its local order, the
     stitched edges follow. Exchange: all-gathers of positions / states and of the edge lists."""
-    pos, counts = allgather_concat(dist, torch, torch.from_numpy(np.ascontiguousarray(local.pos, np.float32)), device)
-    state, _ = allgather_concat(dist, torch, torch.from_numpy(np.ascontiguousarray(local.state, np.int32)), device)
+    T = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dt))
+    pos, counts = allgather_concat(dist, torch, T(local.pos, np.float32), device)
+    state, _ = allgather_concat(dist, torch, T(local.state, np.int32), device)
+    # the tile graphs travel as they are (CSR, local ids, 12 bytes per edge); global ids are put on after the gather
+    deg, _ = allgather_concat(dist, torch, T(np.diff(local.row_ptr), np.int32), device)
+    col_all, ecounts = allgather_concat(dist, torch, T(local.col, np.int32), device)
+    w_all, _ = allgather_concat(dist, torch, T(local.weight, np.float32), device)
+    d_all, _ = allgather_concat(dist, torch, T(local.dist, np.float32), device)
     node_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
-    n_local = local.pos.shape[0]
-    deg = np.diff(local.row_ptr).astype(np.int64)
-    src = np.repeat(np.arange(n_local, dtype=np.int64), deg) + node_off[rank]
-    coo = torch.stack([torch.from_numpy(src), torch.from_numpy(local.col.astype(np.int64) + node_off[rank])], 1)
-    wd = torch.stack([torch.from_numpy(np.ascontiguousarray(local.weight, np.float32)),
-                      torch.from_numpy(np.ascontiguousarray(local.dist, np.float32))], 1)
-    coo_all, ecounts = allgather_concat(dist, torch, coo, device)
-    wd_all, _ = allgather_concat(dist, torch, wd, device)
-    nbytes = int(pos.numel() * 4 + state.numel() * 4 + coo_all.numel() * 8 + wd_all.numel() * 4)
+    dev = pos.device
+    owner_off = torch.repeat_interleave(torch.from_numpy(node_off[:-1]).to(dev), torch.tensor(ecounts, dtype=torch.int64, device=dev))
+    dst = col_all.to(torch.int64) + owner_off
+    src = torch.repeat_interleave(torch.arange(int(node_off[-1]), dtype=torch.int64, device=dev), deg.to(torch.int64))
+    coo_all = torch.stack([src, dst], 1)
+    wd_all = torch.stack([w_all, d_all], 1)
+    nbytes = int(pos.numel() * 4 + state.numel() * 4 + deg.numel() * 4 + col_all.numel() * 4 + wd_all.numel() * 4)
     if len(stitched):
         st = np.asarray(stitched, np.float64)
         ga = node_off[st[:, 0].astype(np.int64)] + st[:, 1].astype(np.int64)
         gb = node_off[st[:, 2].astype(np.int64)] + st[:, 3].astype(np.int64)
-        s_coo = torch.from_numpy(np.concatenate([np.stack([ga, gb], 1), np.stack([gb, ga], 1)])).to(device)
-        s_wd = torch.from_numpy(np.concatenate([st[:, 4:6], st[:, 4:6]]).astype(np.float32)).to(device)
+        s_coo = torch.from_numpy(np.concatenate([np.stack([ga, gb], 1), np.stack([gb, ga], 1)])).to(dev)
+        s_wd = torch.from_numpy(np.concatenate([st[:, 4:6], st[:, 4:6]]).astype(np.float32)).to(dev)
         coo_all = torch.cat([coo_all, s_coo])
         wd_all = torch.cat([wd_all, s_wd])
     n = int(node_off[-1])
@@ -286,8 +293,11 @@ def build_merged_graph(dist, torch, device, rank, world, trg_handle, cloud, bb, 
     t2 = time.perf_counter()
     m = merge_graphs(dist, torch, device, rank, world, g, stitched)
     t3 = time.perf_counter()
-    graph = K.DeviceGraph(m["row_ptr"].cpu().numpy(), m["col"].cpu().numpy(), m["weight"].cpu().numpy(), m["dist"].cpu().numpy(),
-                          m["pos"].cpu().numpy(), m["state"].cpu().numpy())
+    if m["pos"].is_cuda:   # merged on the device: the search graph is built from those tensors where they are
+        graph = K.DeviceGraph.from_device(m["row_ptr"], m["col"], m["weight"], m["dist"], m["pos"], m["state"])
+    else:
+        graph = K.DeviceGraph(m["row_ptr"].numpy(), m["col"].numpy(), m["weight"].numpy(), m["dist"].numpy(),
+                              m["pos"].numpy(), m["state"].numpy())
     grid = K.DeviceNodeGrid(m["pos"], P.robot_size)   # nearest-node snapping on the merged graph
     t4 = time.perf_counter()
     stats = dict(st)
