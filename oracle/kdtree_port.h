@@ -10,7 +10,8 @@
 //   single nearest    kdtree.c:303-417  (strict `<`; nearer subtree, node, farther subtree;
 //                                        bounding-box pruning; initial best = root)
 // It is validated against the verbatim reference kdtree.c (oracle/_ref) by
-// tests/test_oracle_kdtree.py and can be swapped for it with -DORACLE_USE_REF_KDTREE.
+// tests/test_oracle_cpu.py (the "refkd" and "ref" builds of oracle/Makefile against the golden fixtures, plus
+// restatement == reference on fresh maps) and can be swapped for it with -DORACLE_USE_REF_KDTREE.
 #ifndef ORACLE_KDTREE_PORT_H_
 #define ORACLE_KDTREE_PORT_H_
 

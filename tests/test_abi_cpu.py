@@ -43,6 +43,25 @@ def test_host_node_index_against_kdtree_port(built, tmp_path):
     assert r.returncode == 0, r.stdout[-2000:]
 
 
+def build_consumer(tmp_path):
+    """tests/host/consumer_check.cpp: class TRG used the way TRGPlanner, the ROS nodes and the pybind module use it."""
+    exe = tmp_path / "consumer_check"
+    lib = ROOT / "trg-planner_b200" / "lib"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-pthread", f"-I{ROOT/'trg-planner_b200'/'host'}",
+                    f"-I{ROOT/'include'}", str(ROOT / "tests" / "host" / "consumer_check.cpp"), "-o", str(exe), f"-L{lib}",
+                    "-ltrg_b200", "-ltrgb_kernels", f"-Wl,-rpath,{lib}"], check=True)
+    return exe
+
+
+def test_cpp_consumer_of_trg_h_compiles_and_fails_loudly_without_gpu(built, tmp_path):
+    from trg_planner_b200 import kernels as K
+    exe = build_consumer(tmp_path)
+    if K.device_count() > 0:
+        pytest.skip("a CUDA device is present (the run is covered by the GPU test)")
+    r = subprocess.run([str(exe), "40", str(tmp_path / "g.json")], capture_output=True, text=True)
+    assert r.returncode != 0 and "CUDA" in r.stderr   # no CPU fallback behind the reference's API
+
+
 def test_facade_without_map_fails_loudly(pkg, built):
     t = pkg.product(pkg.MOUNTAIN)
     with pytest.raises(RuntimeError, match="no global map"):

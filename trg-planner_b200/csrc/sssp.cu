@@ -767,8 +767,8 @@ extern "C" int trgb_sssp_batch(trgb_graph* g, const int32_t* start_ids, const in
   o.found = (uint8_t*)d_found.p; o.cost = (float*)d_cost.p; o.path_length = (float*)d_len.p;
   o.avg_risk = (float*)d_risk.p; o.path_off = (int64_t*)d_off.p; o.path_len = (int32_t*)d_plen.p;
   o.path_ids = (int32_t*)d_ids.p; o.capacity = path_ids_capacity; o.cursor = (unsigned long long*)d_cur.p;
-  // threshold step: 0.5..32 x the mean edge length measured; 1..2 is the flat optimum (profiles/README.md)
-  float delta = 1.5f * std::max(g->mean_cost, 1e-3f);
+  // threshold step: 0.75..6 x the mean edge length measured at C2 (scripts/sssp_sweep.py): flat between 0.75 and 1.5
+  float delta = 1.0f * std::max(g->mean_cost, 1e-3f);
   if (const char* ev = std::getenv("TRGB_SSSP_DELTA")) delta = (float)std::atof(ev) * std::max(g->mean_cost, 1e-3f);
   {
     ProfScope ps("k_sssp", st, (double)nq);

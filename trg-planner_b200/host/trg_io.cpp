@@ -193,7 +193,13 @@ void TRG::loadPrebuiltGraph(const std::string& filepath) {  // trg.cpp:66-128
   rewindPools();
   std::unordered_map<int, Node*> id_to_node;
   for (const JValue& nj : root.at("nodes").arr()) {
-    const int id = (int)nj.at("id").num();
+    const double id_d = nj.at("id").num();
+    // ids index the CSR rows of the search graph (ensureDeviceGraph): a negative, fractional or repeated id
+    // has no row; the reference would silently build a map it cannot plan on
+    if (!(id_d >= 0.0 && id_d < 2147483647.0) || id_d != (double)(int)id_d)
+      throw std::runtime_error("trg_b200: node id is not a non-negative 32-bit integer");
+    const int id = (int)id_d;
+    if (id_to_node.count(id)) throw std::runtime_error("trg_b200: node id appears twice");
     const JArray& p = nj.at("pos").arr();
     Eigen::Vector2f pos2d((float)p.at(0).num(), (float)p.at(1).num());
     NodeState state = static_cast<NodeState>((int)nj.at("state").num());
@@ -208,6 +214,7 @@ void TRG::loadPrebuiltGraph(const std::string& filepath) {  // trg.cpp:66-128
     const int dst = (int)ej.at("target").num();
     auto it = id_to_node.find(src);
     if (it == id_to_node.end()) throw std::runtime_error("trg_b200: edge source id not among nodes");
+    if (!id_to_node.count(dst)) throw std::runtime_error("trg_b200: edge target id not among nodes");
     it->second->edges_.push_back(newEdge(dst, (float)ej.at("weight").num(), (float)ej.at("dist").num()));
   }
   invalidateDeviceGraph();
