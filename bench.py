@@ -507,7 +507,11 @@ def saturated_kernels(trg, K, torch, t, P, bb, rho, cell, peak):
     tl.trg_device_map.restype = C.c_void_p
     tl.trg_device_map.argtypes = [C.c_void_p, C.c_char_p]
     m = C.c_void_p(tl.trg_device_map(t.h, b"global"))
-    prm = K.EdgeParams(P.robot_size, P.height_threshold, P.collision_threshold, 0)
+    # sample slots per edge = what edges of length expand_dist need (trg.cpp:279-289 steps by robot_size / 2), plus
+    # one for the edges whose float length lands just above it (the device build passes the same count,
+    # expand.cu launch_step); the last slot's thread walks any further sample, so the setting changes the thread
+    # layout, never the result
+    prm = K.EdgeParams(P.robot_size, P.height_threshold, P.collision_threshold, int(np.ceil(P.expand_dist / (0.5 * P.robot_size))) + 1)
     res = {}
     for rep in range(4):
         if rep == 1:

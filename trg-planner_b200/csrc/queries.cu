@@ -787,6 +787,154 @@ __global__ void __launch_bounds__(256) k_edge_pca(MapView m, const float* __rest
   }
 }
 
+#ifndef PCA_VARIANT
+#define PCA_VARIANT 0  // ellipse gather of k_edge_pca_t: 0 = row by row, 1 = flattened over rows, 2 = row by row in 256-bit groups
+#endif
+#ifndef PCA_MINBLK
+#define PCA_MINBLK 8  // 63 registers: measured best at saturation (0.38 ms per 1e6 edges; 0.43 with ptxas' own 72)
+#endif
+constexpr int kPcaRows = 7;  // cell rows the flattened ellipse gather holds in registers
+
+// (b') k_edge_pca_t: one THREAD per edge. Every lane walks the cell rows of its own ellipse — a contiguous run of
+// points per row, streamed through L1 (neighbouring edges of a spatially coherent batch share the lines) — so no
+// lane idles on a short row, nothing is combined across lanes and the Jacobi SVD runs in every lane at once.
+__global__ void __launch_bounds__(128, PCA_MINBLK) k_edge_pca_t(MapView m, const float* __restrict__ p1_xyz,
+                                                    const float2* __restrict__ p2_xy, int64_t n, float rs,
+                                                    uint8_t* __restrict__ stage_io, float* __restrict__ w_out,
+                                                    float* __restrict__ dist_out, int32_t* __restrict__ npts_out,
+                                                    const float* __restrict__ skip_d2, int64_t n_skip,
+                                                    float skip_below) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float p1x = __ldg(p1_xyz + 3 * i), p1y = __ldg(p1_xyz + 3 * i + 1), p1z = __ldg(p1_xyz + 3 * i + 2);
+    const float2 p2 = __ldg(p2_xy + i);
+    int st = stage_io[i];
+    if (i < n_skip && __fsqrt_rn(__ldg(skip_d2 + i)) < skip_below) st = TRGB_EDGE_SKIPPED;
+    const EdgeGeom g = edge_geom(p1x, p1y, p2.x, p2.y);
+    const float dist = g.dist, dirx = g.dirx, diry = g.diry;
+    int nrange = 0, npts = 0;
+    double sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
+    if (st != TRGB_EDGE_COLLISION && st != TRGB_EDGE_SKIPPED) {
+      // :291-297 ellipse with foci at the two nodes (circle when the nodes are close)
+      const float c = 0.5f * dist;
+      const float b = rs;
+      float a = b;
+      if (c >= b) a = __fsqrt_rn(__fadd_rn(__fmul_rn(c, c), __fmul_rn(b, b)));
+      const bool circle = (a == b);
+      const float cx = __fadd_rn(p1x, __fmul_rn(c, dirx)), cy = __fadd_rn(p1y, __fmul_rn(c, diry));
+      const float a2 = __fmul_rn(a, a), b2 = __fmul_rn(b, b);
+      const float rhs = __fmul_rn(__fmul_rn(a2, b), b);  // a*a*b*b, left to right
+      const float ndiry = -diry;
+      const float rr = inflate(a, cx, cy);
+      const int cx0 = cell_coord(cx - rr, m.x0, m.inv_cell, m.W), cx1 = cell_coord(cx + rr, m.x0, m.inv_cell, m.W);
+      const int cy0 = cell_coord(cy - rr, m.y0, m.inv_cell, m.H), cy1 = cell_coord(cy + rr, m.y0, m.inv_cell, m.H);
+#define PCA_POINT(P, OK)                                                                                           \
+      {                                                                                                            \
+        const float qx = __fsub_rn(P.x, cx), qy = __fsub_rn(P.y, cy);                                              \
+        const float d2 = __fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy));                                          \
+        if ((OK) && d2 <= a2) { /* kd_nearest_range2(center, a) */                                                 \
+          ++nrange;                                                                                                \
+          /* :312-316 p2d = R * (pt - center), R = [dir.x -dir.y; dir.y dir.x] */                                  \
+          const float px = __fadd_rn(__fmul_rn(dirx, qx), __fmul_rn(ndiry, qy));                                   \
+          const float py = __fadd_rn(__fmul_rn(diry, qx), __fmul_rn(dirx, qy));                                    \
+          if (circle || __fadd_rn(__fmul_rn(__fmul_rn(px, px), b2), __fmul_rn(__fmul_rn(py, py), a2)) < rhs) {     \
+            /* covariance sums in double about the pivot z = p1.z (see warp_edge_eval) */                          \
+            const double X = px, Y = py, Z = (double)P.z - (double)p1z;                                            \
+            ++npts;                                                                                                \
+            sx += X; sy += Y; sz += Z;                                                                             \
+            sxx += X * X; sxy += X * Y; sxz += X * Z; syy += Y * Y; syz += Y * Z; szz += Z * Z;                    \
+          }                                                                                                        \
+        }                                                                                                          \
+      }
+      if (PCA_VARIANT == 1 && cy1 - cy0 < kPcaRows) {
+        // flattened gather (see thread_is_collision): the rows' runs are located first, then walked as one loop
+        // over groups of four points fetched with two 256-bit loads - lanes differ in how their candidates split
+        // over rows, hardly in the total
+        uint32_t gb[kPcaRows], gs[kPcaRows], ge[kPcaRows], gc[kPcaRows];
+        uint32_t totg = 0;
+        const float slack = 1e-3f * m.cell + 4e-6f * (fabsf(cy) + fabsf(m.y0));
+#pragma unroll
+        for (int k = 0; k < kPcaRows; ++k) {
+          const int row = cy0 + k;
+          const float ylo = m.y0 + (float)row * m.cell - slack;
+          const float yhi = m.y0 + (float)(row + 1) * m.cell + slack;
+          const float dy = fmaxf(0.f, fmaxf(ylo - cy, cy - yhi));
+          const float h2 = rr * rr - dy * dy;
+          float half;
+          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(half) : "f"(fmaxf(h2, 0.f)));
+          half = half * 1.0001f + 1e-6f;
+          const int ca = max(cx0, min(m.W - 1, __float2int_rd(__fmul_rn(__fsub_rn(cx - half, m.x0), m.inv_cell))));
+          const int cb = min(cx1, max(0, __float2int_rd(__fmul_rn(__fsub_rn(cx + half, m.x0), m.inv_cell))));
+          const bool any = row <= cy1 && h2 > 0.f && ca <= cb;
+          const uint32_t* cs = m.cell_start + (size_t)min(row, cy1) * (size_t)m.W;
+          const uint32_t s0 = any ? __ldg(cs + ca) : 0u;
+          const uint32_t e0 = any ? __ldg(cs + cb + 1) : 0u;
+          const uint32_t sa = s0 & ~1u;  // groups start at even indices: 32-byte aligned
+          gb[k] = sa - 4u * totg;
+          gs[k] = s0;
+          ge[k] = e0;
+          totg += e0 > s0 ? (e0 - sa + 3u) >> 2 : 0u;
+          gc[k] = totg;
+        }
+#pragma unroll 2
+        for (uint32_t gi = 0; gi < totg; ++gi) {
+          uint32_t bb = gb[0], lo = gs[0], en = ge[0];
+#pragma unroll
+          for (int k = 1; k < kPcaRows; ++k) {
+            const bool in = gi >= gc[k - 1];
+            bb = in ? gb[k] : bb;
+            lo = in ? gs[k] : lo;
+            en = in ? ge[k] : en;
+          }
+          const uint32_t i0 = bb + 4u * gi;  // >= lo - 1; only slot 0 can lie before the run, slots 1..3 behind it
+          float4 q0, q1, q2, q3;
+          ld_pt2(m.pts + i0, q0, q1);
+          ld_pt2(m.pts + i0 + 2, q2, q3);
+          PCA_POINT(q0, i0 >= lo) PCA_POINT(q1, i0 + 1 < en) PCA_POINT(q2, i0 + 2 < en) PCA_POINT(q3, i0 + 3 < en)
+        }
+      } else {
+        for (int row = cy0; row <= cy1; ++row) {
+          int ca, cb;
+          row_chord(m, cx, cy, rr, row, cx0, cx1, &ca, &cb);  // chord of the radius-a disc in this row
+          if (ca > cb) continue;
+          const size_t rb = (size_t)row * (size_t)m.W;
+          const uint32_t s0 = __ldg(m.cell_start + rb + ca), e0 = __ldg(m.cell_start + rb + cb + 1);
+          if (PCA_VARIANT == 2) {
+            // groups of four points from an even index: two 256-bit loads each (the point array is padded)
+#pragma unroll 2
+            for (uint32_t i0 = s0 & ~1u; i0 < e0; i0 += 4) {
+              float4 q0, q1, q2, q3;
+              ld_pt2(m.pts + i0, q0, q1);
+              ld_pt2(m.pts + i0 + 2, q2, q3);
+              PCA_POINT(q0, i0 >= s0) PCA_POINT(q1, i0 + 1 < e0) PCA_POINT(q2, i0 + 2 < e0) PCA_POINT(q3, i0 + 3 < e0)
+            }
+          } else {
+#pragma unroll 4
+            for (uint32_t k = s0; k < e0; ++k) {
+              const float4 q0 = ld_pt(m.pts + k);
+              PCA_POINT(q0, true)
+            }
+          }
+        }
+      }
+#undef PCA_POINT
+    }
+    float weight = 0.f;
+    if (st == TRGB_EDGE_COLLISION || st == TRGB_EDGE_SKIPPED) {
+      npts = 0;
+    } else if (nrange == 0) {
+      st = TRGB_EDGE_EMPTY;   // :305
+    } else if (npts < 3) {
+      st = TRGB_EDGE_FEWPTS;  // :327
+    } else {
+      weight = weight_from_sums(npts, sx, sy, sz, sxx, sxy, sxz, syy, syz, szz);
+    }
+    stage_io[i] = (uint8_t)st;
+    w_out[i] = weight;
+    dist_out[i] = dist;
+    if (npts_out) npts_out[i] = npts;
+  }
+}
+
 // per-warp shared z-buffer capacity for a radius-r cylinder on this map
 static double map_density(const trgb_map* m) {
   const double area = (double)m->view.W * m->view.H * (double)m->view.cell * m->view.cell;
@@ -969,6 +1117,15 @@ extern "C" int trgb_edge_eval_launch_skip(const trgb_map* m, const float* d_p1_x
       ProfScope ps("k_edge_pca", m->stream, (double)n);
       // lanes per edge: 8 for the small, latency-bound batches of the graph build (shorter gather
       // chain per lane), 4 at saturation (fewer idle lanes): 17 vs 22 ms per build, 1.75 vs 1.19 G edges/s
+      static const int pca_mode = [] { const char* e = std::getenv("TRGB_PCA_MODE"); return e ? std::atoi(e) : 0; }();
+      if (pca_mode == 1 || (pca_mode == 0 && n >= 200000)) {
+        const int g3 = (int)std::max<int64_t>(1, std::min<int64_t>((n + 127) / 128, (int64_t)sm_count() * 16));
+        k_edge_pca_t<<<g3, 128, 0, m->stream>>>(m->view, d_p1_xyz, reinterpret_cast<const float2*>(d_p2_xy), n,
+                                                prm->robot_size, d_stage, d_weight, d_dist, d_npts, d_skip_d2, n_skip,
+                                                skip_below);
+        TRGB_CUDA(cudaGetLastError());
+        return TRGB_OK;
+      }
       const int lanes = n < 200000 ? 8 : 4;
       const int64_t need = (n + (256 / lanes) - 1) / (256 / lanes);
       const int g2 = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)sm_count() * 8));

@@ -236,7 +236,7 @@ def allgather_concat(dist, torch, t, device):
     return torch.cat([out[r][: counts[r]] for r in range(world)]), counts
 
 
-def merge_graphs(dist, torch, device, rank, world, local, stitched):
+def merge_graphs(dist, torch, device, rank, world, local, stitched, compute_device=None):
     """Every rank's tile graph (`local`: GraphSnapshot, CSR by local id) + the stitched cross-tile edges
     (rows rank_a, id_a, rank_b, id_b, weight, dist) -> ONE global CSR, identical on every rank.
     Global id = node offset of the owner rank + local id; a node's edge list keeps its local order, the
@@ -250,6 +250,8 @@ def merge_graphs(dist, torch, device, rank, world, local, stitched):
     w_all, _ = allgather_concat(dist, torch, T(local.weight, np.float32), device)
     d_all, _ = allgather_concat(dist, torch, T(local.dist, np.float32), device)
     node_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    if compute_device is not None:   # collectives on `device` (gloo: the host), the merge itself where the graph will live
+        pos, state, deg, col_all, w_all, d_all = (x.to(compute_device) for x in (pos, state, deg, col_all, w_all, d_all))
     dev = pos.device
     owner_off = torch.repeat_interleave(torch.from_numpy(node_off[:-1]).to(dev), torch.tensor(ecounts, dtype=torch.int64, device=dev))
     dst = col_all.to(torch.int64) + owner_off
@@ -275,7 +277,7 @@ def merge_graphs(dist, torch, device, rank, world, local, stitched):
                 weight=wd_sorted[:, 0].contiguous(), dist=wd_sorted[:, 1].contiguous(), bytes=nbytes, edge_counts=ecounts)
 
 
-def build_merged_graph(dist, torch, device, rank, world, trg_handle, cloud, bb, P, K):
+def build_merged_graph(dist, torch, device, rank, world, trg_handle, cloud, bb, P, K, compute_device=None):
     """Stitch the tiles (stitch_tiles), merge them (merge_graphs) and upload the merged CSR (K7) on this rank."""
     import time
     t0 = time.perf_counter()
@@ -291,7 +293,7 @@ def build_merged_graph(dist, torch, device, rank, world, trg_handle, cloud, bb, 
     stitched, st = stitch_tiles(dist, torch, device, rank, world, cloud, g.pos, g.ids, bb[0][0], bb[0][1], P.expand_dist,
                                 P.robot_size, edge_eval)
     t2 = time.perf_counter()
-    m = merge_graphs(dist, torch, device, rank, world, g, stitched)
+    m = merge_graphs(dist, torch, device, rank, world, g, stitched, compute_device)
     t3 = time.perf_counter()
     if m["pos"].is_cuda:   # merged on the device: the search graph is built from those tensors where they are
         graph = K.DeviceGraph.from_device(m["row_ptr"], m["col"], m["weight"], m["dist"], m["pos"], m["state"])
