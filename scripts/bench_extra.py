@@ -41,6 +41,9 @@ def _scans(pts, ext, n, half, rng, x0):
         yield cx, cy, scan
 
 
+C4_STATS = ("pops", "us_sample", "us_eval", "us_commit", "us_wait", "us_clean", "us_local_graph", "us_update_tests", "window_tests", "edge_evals", "batches")
+
+
 def run_c4(a):
     import torch
     trg = _pkg.load()
@@ -64,6 +67,7 @@ def run_c4(a):
     for k, (cx, cy, scan) in enumerate(_scans(pts, ext, a.warmup + a.steps, half, rng, ext / 2 - 50.0)):
         if k == a.warmup:
             torch.cuda.synchronize(); l0 = K.launch_count(); e0.record()
+            st0 = {kk: t.stat(kk) for kk in C4_STATS}
         s0 = time.perf_counter()
         t.set_local_map(cx, cy, scan)
         s1 = time.perf_counter()
@@ -73,6 +77,7 @@ def run_c4(a):
             lat.append((s1 - s0, s2 - s1)); sizes.append(int(scan.shape[0]))
     e1.record(); torch.cuda.synchronize()
     launches = K.launch_count() - l0
+    host = {kk: (t.stat(kk) - st0[kk]) / max(1, a.steps) for kk in C4_STATS}
     L = np.array(lat) * 1e3
     per_scan_ms = float(L.sum(1).mean())
     cpu = None
@@ -100,6 +105,7 @@ def run_c4(a):
                        "l2": "every scan is a new 3.2 MB cloud; the 320 MB map index is larger than L2"},
             "per_scan_ms": {"set_local_map": float(L[:, 0].mean()), "update_graph": float(L[:, 1].mean()),
                             "p50": float(np.median(L.sum(1))), "max": float(L.sum(1).max())},
+            "host_breakdown_per_scan": host,
             "prebuilt": {"map_points": int(pts.shape[0]), "graph_nodes": nn, "graph_edges": ne, "build_s": w1 - w0},
             "e2e": {"value": float(np.mean(sizes)) / (per_scan_ms * 1e-3), "unit": "scan points/s",
                     "h2d_bytes_per_step": int(np.mean(sizes)) * 12, "d2h_bytes_per_step": 0,

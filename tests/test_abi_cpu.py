@@ -43,6 +43,16 @@ def test_host_node_index_against_kdtree_port(built, tmp_path):
     assert r.returncode == 0, r.stdout[-2000:]
 
 
+def test_analytic_unordered_map_order_matches_libstdcxx(tmp_path):
+    """host/map_order.h (the iteration order the device build computes instead of walking the maps) against the
+    real std::unordered_map, fresh and re-used, across every rehash point up to the C2 graph size."""
+    exe = tmp_path / "map_order_check"
+    subprocess.run(["g++", "-O2", "-std=c++17", f"-I{ROOT/'trg-planner_b200'/'host'}",
+                    str(ROOT / "tests" / "host" / "map_order_check.cpp"), "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+
+
 def build_consumer(tmp_path):
     """tests/host/consumer_check.cpp: class TRG used the way TRGPlanner, the ROS nodes and the pybind module use it."""
     exe = tmp_path / "consumer_check"

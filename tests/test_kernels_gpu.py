@@ -83,6 +83,41 @@ def test_nearest_z_parity(pkg, K, small_mountain, small_indoor):
         assert ok.mean() > 0.999
 
 
+def test_nearest_z_tie_rule_on_a_duplicate_bearing_cloud(pkg, K, small_mountain):
+    """K3 deviation, quantified (deviations): among map points at the IDENTICAL float distance the
+    kernel returns the lowest index, the reference whichever its insertion-order kd-tree visits first
+    (kdtree.c:303-362). The tie FLAG is exact, so an affected query is never silent. Jittered clouds (every
+    generator of terrain.py, any voxel-filtered PCD) hold no such ties; a cloud with repeated (x, y) columns -
+    two returns at different heights - ties on every query that lands on a repeated column."""
+    P = pkg.MOUNTAIN
+    rng = np.random.default_rng(21)
+    base = small_mountain[:: 2].copy()
+    for frac in (0.0, 0.05):
+        n_dup = int(frac * len(base))
+        dup = base[rng.choice(len(base), n_dup, replace=False)].copy()
+        dup[:, 2] += rng.uniform(0.3, 1.5, n_dup).astype(np.float32)       # same (x, y), another height
+        pts = np.concatenate([base, dup]).astype(np.float32)
+        pts = pts[rng.permutation(len(pts))]
+        o = pkg.oracle(P)
+        o.set_global_map(pts)
+        dm = K.DeviceMap(pts, P.robot_size)
+        q = _queries(pts, 60_000, 15, margin=0.0)
+        z, idx, tie = dm.nearest_z(q)
+        oz, oidx, otie = o.nearest_z(q)
+        np.testing.assert_array_equal(tie, otie)                 # the flag itself is exact
+        differ = z != oz
+        assert not (differ & (tie == 0)).any()                   # no disagreement without the flag
+        tied = tie != 0
+        # a flagged query returns the z of ONE of the tied points (here: of the repeated column)
+        print(f"duplicate fraction {frac}: {tied.mean():.4f} of the queries tie, {differ.mean():.4f} return another z than the reference"
+              f" ({(differ.sum() / max(1, tied.sum())):.2f} of the tied ones)")
+        if frac == 0.0:
+            assert tied.sum() == 0
+        else:
+            assert 0.5 * frac < tied.mean() < 2.5 * frac          # ~ the share of repeated columns
+            assert differ.sum() <= tied.sum()
+
+
 def _edge_pairs(pts, o, n, seed, e):
     rng = np.random.default_rng(seed)
     a = _queries(pts, n, seed, margin=-1.0)

@@ -294,25 +294,41 @@ void TRG::setLocalGraph(bool useMutex) {  // trg.cpp:211-231
   trgStruct& l = *trgMap_["local"];
   this->resetGraph("local");
   if (g.nodes.empty()) return;
-  // one batched range-count over every global node, in the map's iteration order
+  // The reference range-counts the local map around EVERY global node, in the map's iteration order (:215-229).
+  // Only nodes within robot_size / 2 of the local cloud's bounding box can count a point, and right after
+  // cleanGraph the iteration order is node_seq's: candidates come from one pass over the flat position array
+  // instead of a walk over a million hash nodes, and only they go to the device.
+  const float reach = (float)(param_.robot_size * 0.5) * 1.01f + 1e-3f;
+  const bool boxed = l.map_index && l.bbox[2] >= l.bbox[0] && l.bbox[3] >= l.bbox[1];
+  const float bx0 = l.bbox[0] - reach, by0 = l.bbox[1] - reach, bx1 = l.bbox[2] + reach, by1 = l.bbox[3] + reach;
   std::vector<Node*> order;
-  order.reserve(g.nodes.size());
   std::vector<float> xy;
-  xy.reserve(2 * g.nodes.size());
-  for (auto& node : g.nodes) {
-    order.push_back(node.second);
-    xy.push_back(node.second->pos_.x());
-    xy.push_back(node.second->pos_.y());
+  if (g.seq_in_iter_order && g.node_seq.size() == g.nodes.size()) {
+    const size_t n = g.node_seq.size();
+    for (size_t i = 0; i < n; ++i) {
+      const float x = g.seq_xy[2 * i], y = g.seq_xy[2 * i + 1];
+      if (boxed && !(x >= bx0 && x <= bx1 && y >= by0 && y <= by1)) continue;
+      order.push_back(g.node_seq[i]);
+      xy.push_back(x);
+      xy.push_back(y);
+    }
+  } else {
+    for (auto& node : g.nodes) {
+      const float x = node.second->pos_.x(), y = node.second->pos_.y();
+      if (boxed && !(x >= bx0 && x <= bx1 && y >= by0 && y <= by1)) continue;
+      order.push_back(node.second);
+      xy.push_back(x);
+      xy.push_back(y);
+    }
   }
   std::vector<int32_t> cnt(order.size(), 0);
-  if (l.map_index)
+  if (l.map_index && !order.empty())
     K(trgb_range_count_batch(l.map_index, xy.data(), (int64_t)order.size(), (float)(param_.robot_size * 0.5), cnt.data()),
       "trgb_range_count_batch");
-  size_t k = 0;
-  for (auto& node : g.nodes) {
-    if (cnt[k++] == 0) continue;
-    l.nodes[node.first] = node.second;
-    nodeIndexInsert(l, node.second);
+  for (size_t k = 0; k < order.size(); ++k) {
+    if (cnt[k] == 0) continue;
+    l.nodes[order[k]->id_] = order[k];   // (key == id_ for every node of the global map)
+    nodeIndexInsert(l, order[k]);
   }
 }
 
@@ -327,6 +343,7 @@ void TRG::nodeIndexReset(trgStruct& g) {
   g.grid_built = 0;
   g.tree_built = 0;
   g.iter_rank.clear();
+  g.seq_in_iter_order = true;  // (empty)
   if (dev_ && dev_->nodes_owner == &g) dev_->nodes_owner = nullptr;  // device copy is stale
 }
 
@@ -344,11 +361,17 @@ void TRG::nodeIndexInsert(trgStruct& g, Node* n) {
   g.node_seq.push_back(n);  // the host grid / order tree catch up lazily (ensureGridBuilt / ensureTree)
   g.seq_xy.push_back(n->pos_.x());
   g.seq_xy.push_back(n->pos_.y());
+  g.seq_in_iter_order = false;  // a hash map does not iterate in insertion order; cleanGraph re-establishes it
   if (!g.iter_rank.empty()) g.iter_rank.clear();
 }
 
 void TRG::ensureGridBuilt(trgStruct& g) {
   ensureGrid(g);
+  if (g.grid_built == 0 && g.node_seq.size() >= 65536) {  // a whole graph at once (after cleanGraph): banded, on helper threads
+    g.node_grid.rebuild(g.seq_xy.data(), (int)g.node_seq.size(), trg_b200::thread_budget());
+    g.grid_built = g.node_seq.size();
+    return;
+  }
   for (; g.grid_built < g.node_seq.size(); ++g.grid_built)
     g.node_grid.insert(g.seq_xy[2 * g.grid_built], g.seq_xy[2 * g.grid_built + 1]);
 }
@@ -1392,9 +1415,14 @@ void TRG::cleanGraph(bool updateLocal) {  // trg.cpp:491-535
   g.node_id = new_id;
   g.node_seq.reserve(g.nodes.size());
   for (auto& node : g.nodes) nodeIndexInsert(g, node.second);  // node_tree order = new map's iteration order (:528-530)
+  g.seq_in_iter_order = true;
   if (piped) disposal.get();
   invalidateDeviceGraph();
-  if (updateLocal) this->setLocalGraph(false);
+  if (updateLocal) {
+    auto tl = Clock::now();
+    this->setLocalGraph(false);
+    stat_["us_local_graph"] += (int64_t)(1e6 * since(tl));
+  }
 }
 
 void TRG::updateGraph() {  // trg.cpp:456-489
@@ -1446,8 +1474,11 @@ void TRG::updateGraph() {  // trg.cpp:456-489
     expand_queue.push_back(node);
     node->state_ = NodeState::Valid;
   }
+  stat_["us_update_tests"] += (int64_t)(1e6 * since(t0));
   runExpansion(expand_queue, g);  // == expandGraph(node->id_, "global") for each, in order
+  auto tc = Clock::now();
   this->cleanGraph(true);
+  stat_["us_clean"] += (int64_t)(1e6 * since(tc));
   secs_["update_graph"] = since(t0);
 }
 

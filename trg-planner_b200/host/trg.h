@@ -168,6 +168,7 @@ class TRG {
     trg_b200::OrderTree2D   node_tree;
     size_t                  grid_built = 0;  // prefix of node_seq already in node_grid (filled lazily)
     size_t                  tree_built = 0;  // prefix of node_seq already in node_tree
+    bool                    seq_in_iter_order = true;  // node_seq is also the iteration order of `nodes` (true right after cleanGraph)
     std::unordered_map<const Node*, size_t> iter_rank;  // lazily: position in `nodes` iteration order
     // replaces `kdtree* map_tree` (trg.h:110): device cell index
     trgb_map*               map_index = nullptr;

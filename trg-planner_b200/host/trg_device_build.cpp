@@ -25,6 +25,7 @@
 #include <thread>
 
 #include "device_session.h"
+#include "map_order.h"
 #include "trg.h"
 #include "trgb_kernels.h"
 
@@ -36,34 +37,7 @@ inline void K(int rc, const char* what) {
   if (rc != TRGB_OK) fail(what);
 }
 
-// Iteration order of a std::unordered_map<int, T> (libstdc++, identity hash, max load factor 1) into
-// which the keys 0 .. n-1 are inserted in ascending order, starting from `bucket_count` buckets
-// (1 = never used; otherwise what clear() left behind). A key whose bucket is empty becomes the new
-// head of the element list (hashtable.h _M_insert_bucket_begin), and keys below the bucket count all
-// have their own bucket; a rehash re-links the elements in list order, each again at the head
-// (_M_rehash_aux), i.e. reverses the list. Rehash points come from libstdc++'s own policy object.
-// Keys >= bucket count cannot occur before a rehash (the policy grows first), so no chain is shared.
-std::vector<int> sequential_map_order(size_t n, size_t bucket_count) {
-  std::__detail::_Prime_rehash_policy pol(1.0f);
-  size_t bkt = bucket_count;
-  pol._M_next_resize = bkt <= 1 ? 0 : (size_t)__builtin_floor((double)bkt * 1.0);
-  // deque with a direction flag: push at the logical front, reverse = flip
-  std::vector<int> buf(2 * n + 2);
-  size_t lo = n + 1, hi = n + 1;  // elements in [lo, hi)
-  bool flipped = false;           // logical front is at hi when flipped
-  for (size_t k = 0; k < n; ++k) {
-    const auto r = pol._M_need_rehash(bkt, k, 1);
-    if (r.first) {
-      bkt = r.second;
-      flipped = !flipped;
-    }
-    if (!flipped) buf[--lo] = (int)k; else buf[hi++] = (int)k;
-  }
-  std::vector<int> out(n);
-  if (!flipped) std::copy(buf.begin() + lo, buf.begin() + hi, out.begin());
-  else std::reverse_copy(buf.begin() + lo, buf.begin() + hi, out.begin());
-  return out;
-}
+using trg_b200::sequential_map_order;
 
 template <class F>
 void parallel_for(size_t n, int threads, F&& f) {
