@@ -557,6 +557,8 @@ struct GraphSource {
 };
 int graph_from_device(trgb_graph** out, const GraphSource& src, cudaStream_t build_stream);
 
+int nearest_z_launch_on(const trgb_map* m, const float* d_xy, int64_t n, float* d_z, int64_t* d_idx, uint8_t* d_tie,
+                        const float* d_skip_d2, float skip_below, cudaStream_t st);  // K3 on a stream of the caller's (queries.cu)
 void tune_mempool_once();  // raise the default mempool's release threshold (map_index.cu)
 int sm_count();
 int grid_for_warps(int64_t n_warps, int ctas_per_sm);

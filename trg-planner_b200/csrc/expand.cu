@@ -671,27 +671,54 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v, int c_step_ne
   int rounds = 0;
   volatile int* vst = v.st;
   volatile float* vd2 = v.cur_d2;
+  // A blocked sample polls only the earlier sample that blocked it (one round trip) until that one is decided or
+  // can no longer become a node, and walks its whole list again only then: a chain of k dependent samples costs
+  // k polls instead of k list walks. (Kept for the thread's first sample: a step rarely has more samples than
+  // the cluster has threads.)
+  int blocker0 = -1;
   for (int pending = 1; pending;) {
     pending = 0;
     ++rounds;
     for (int s = gtid; s < ns; s += GT) {
       if (vst[s] != ST_UNDECIDED) continue;
+      if (s == gtid && blocker0 >= 0) {
+        const int sb = vst[blocker0];
+        const float db = vd2[blocker0];
+        if (sb == ST_UNDECIDED && __fsqrt_rn(db) >= r) { ++pending; continue; }
+        blocker0 = -1;
+      }
       float bd = __ldg(v.s_d2 + s);
       int bn = __ldg(v.s_nn + s);
       int tie = 0;
       float mu = INFINITY;  // closest earlier undecided potential creator
+      int mu_q = -1;
       const int nd = __ldg(v.dep_n + s);
       if (nd <= kDepMax) {
-        for (int u = 0; u < nd; ++u) {
-          const int q = __ldg(v.dep_j + (size_t)s * kDepMax + u);
-          const int sq = vst[q];
-          if (sq != ST_CREATE && sq != ST_UNDECIDED) continue;
-          const float d2 = __ldg(v.dep_d2 + (size_t)s * kDepMax + u);
-          if (sq == ST_CREATE) {
-            if (d2 < bd) { bd = d2; bn = -2 - q; tie = 0; }
-            else if (d2 == bd && bn != -2 - q) tie = 1;
-          } else if (__fsqrt_rn(vd2[q]) >= r) {
-            mu = fminf(mu, d2);
+        // the list in chunks of four: indices, states and distances of a chunk are fetched together (independent
+        // loads in flight at once) instead of one dependent round trip after the other
+#pragma unroll
+        for (int u0 = 0; u0 < kDepMax; u0 += 4) {
+          if (u0 >= nd) break;
+          int qs[4], sq[4];
+          float dd[4], vq[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const bool in = u0 + u < nd;
+            qs[u] = in ? __ldg(v.dep_j + (size_t)s * kDepMax + u0 + u) : -1;
+            dd[u] = in ? __ldg(v.dep_d2 + (size_t)s * kDepMax + u0 + u) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) sq[u] = qs[u] >= 0 ? vst[qs[u]] : ST_VOID;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) vq[u] = sq[u] == ST_UNDECIDED ? vd2[qs[u]] : 0.f;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (sq[u] == ST_CREATE) {
+              if (dd[u] < bd) { bd = dd[u]; bn = -2 - qs[u]; tie = 0; }
+              else if (dd[u] == bd && bn != -2 - qs[u]) tie = 1;
+            } else if (sq[u] == ST_UNDECIDED && __fsqrt_rn(vq[u]) >= r) {
+              if (dd[u] < mu) { mu = dd[u]; mu_q = qs[u]; }
+            }
           }
         }
       } else {
@@ -723,7 +750,11 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v, int c_step_ne
           }
       }
       vd2[s] = bd;  // published either way: lets later samples see that this one can no longer become a node
-      if (mu <= bd) { ++pending; continue; }
+      if (mu <= bd) {
+        if (s == gtid) blocker0 = mu_q;  // (-1 after the hash walk: no single blocker recorded there)
+        ++pending;
+        continue;
+      }
       // (a CREATE entry at a distance above mu cannot have been missed: entries are only skipped when decided otherwise)
       const int i = s / S;
       if (tie) atomicMin(&c->ipop, i);
@@ -1255,8 +1286,7 @@ extern "C" int trgb_expander_push_draws(trgb_expander* e, const float* xy, int64
   return TRGB_OK;
 }
 
-// the kernels of one step, in stream order on e->st (the dependency lists are built on a side stream,
-// beside the K3 / K4 launches they do not depend on)
+// the kernels of one step, in stream order on e->st (K3 and the dependency lists run on a side stream beside K4)
 static int launch_step(trgb_expander* e, int c_step) {
   ExpView& v = e->v;
   cudaStream_t st = e->st;
@@ -1282,13 +1312,15 @@ static int launch_step(trgb_expander* e, int c_step) {
   }
   TRGB_CUDA(cudaEventRecord(e->ev_fork, st));
   TRGB_CUDA(cudaStreamWaitEvent(e->st2, e->ev_fork, 0));
+  // side stream: heights of the would-be nodes (K3) and the dependency lists; main stream: their parent edges (K4,
+  // which reads the parent's height, not the sample's). The commit needs all three.
+  int rc = nearest_z_launch_on(m, reinterpret_cast<const float*>(v.s_xy), ns, v.s_z, nullptr, v.s_ztie, v.s_d2, v.r, e->st2);
+  if (rc) return rc;
   {
     ProfScope ps("k_exp_deps", e->st2, (double)ns);
     k_exp_deps<<<(int)((ns + 255) / 256), 256, 0, e->st2>>>(v);
   }
   TRGB_CUDA(cudaEventRecord(e->ev_join, e->st2));
-  int rc = trgb_nearest_z_launch_skip(m, reinterpret_cast<const float*>(v.s_xy), ns, v.s_z, nullptr, v.s_ztie, v.s_d2, v.r);
-  if (rc) return rc;
   rc = trgb_edge_eval_launch_skip(m, v.s_p1, reinterpret_cast<const float*>(v.s_xy), ns, &ep, v.s_stage, v.s_w, v.s_d, nullptr,
                                   v.s_d2, ns, v.r);
   if (rc) return rc;

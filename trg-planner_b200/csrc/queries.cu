@@ -1070,15 +1070,22 @@ extern "C" int trgb_sample_window_launch2(const trgb_map* m, const float* d_node
   return TRGB_OK;
 }
 
-extern "C" int trgb_nearest_z_launch_skip(const trgb_map* m, const float* d_xy, int64_t n, float* d_z,
-                                          int64_t* d_idx, uint8_t* d_tie, const float* d_skip_d2, float skip_below) {
+// (the device BFS runs K3 beside K4 on a side stream: neither needs the other's output)
+int trgb::nearest_z_launch_on(const trgb_map* m, const float* d_xy, int64_t n, float* d_z, int64_t* d_idx, uint8_t* d_tie,
+                              const float* d_skip_d2, float skip_below, cudaStream_t st) {
   TRGB_ARG(m && d_xy, "null pointer");
   if (n <= 0) return TRGB_OK;
-  ProfScope ps("k_nearest_z", m->stream, (double)n);
-  k_nearest_z<<<grid_for_warps(n, 8), kThreads, 0, m->stream>>>(m->view, reinterpret_cast<const float2*>(d_xy), n,
-                                                                 d_z, d_idx, d_tie, d_skip_d2, skip_below);
+  ProfScope ps("k_nearest_z", st, (double)n);
+  k_nearest_z<<<grid_for_warps(n, 8), kThreads, 0, st>>>(m->view, reinterpret_cast<const float2*>(d_xy), n, d_z, d_idx,
+                                                         d_tie, d_skip_d2, skip_below);
   TRGB_CUDA(cudaGetLastError());
   return TRGB_OK;
+}
+
+extern "C" int trgb_nearest_z_launch_skip(const trgb_map* m, const float* d_xy, int64_t n, float* d_z,
+                                          int64_t* d_idx, uint8_t* d_tie, const float* d_skip_d2, float skip_below) {
+  TRGB_ARG(m, "null pointer");
+  return nearest_z_launch_on(m, d_xy, n, d_z, d_idx, d_tie, d_skip_d2, skip_below, m->stream);
 }
 
 extern "C" int trgb_nearest_z_launch(const trgb_map* m, const float* d_xy, int64_t n, float* d_z,
