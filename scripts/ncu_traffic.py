@@ -14,7 +14,7 @@ for rep in sys.argv[1:]:
     hdr, units, body = rows[0], rows[1], rows[2:]
     ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
     for r in body:
-        name = r[ik].split("(")[0].split("<")[0].split("::")[-1]
+        name = r[ik].split("(")[0].split("<")[0].split("::")[-1].replace("void ", "").strip()
         b = float(r[ir].replace(",", "")) * UNIT.get(units[ir], 1.0) + float(r[iw].replace(",", "")) * UNIT.get(units[iw], 1.0)
         acc[ALIAS.get(name, name)].append(b)
 out = {k: round(sum(v) / len(v), 1) for k, v in sorted(acc.items())}

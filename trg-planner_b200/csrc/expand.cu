@@ -113,14 +113,15 @@ __device__ __forceinline__ int exp_ncell(float v, float origin, float inv, int d
 // ------------------------------------------------------------------------------------------
 // Plan of the next step, executed by one whole thread block (any size): pops taken, window geometry,
 // guessed stream positions, zeroed masks.
-__device__ void exp_plan_block(const ExpView& v, int c_step) {
+__device__ void exp_plan_block(const ExpView& v, int c_step, const ExpCtl* current = nullptr) {
   ExpCtl* c = v.ctl;
   __shared__ int s_m, s_words, s_D, s_fit;
   __shared__ float s_mean, s_var;
   __shared__ long long s_room;
   __syncthreads();
+  ExpCtl k;  // thread 0's copy: one read (or the caller's shared copy, `current`), one write-back at the very end
   if (threadIdx.x == 0) {
-    ExpCtl k = *c;  // (one read, one write-back)
+    k = current ? *current : *c;
     int m = 0;
     k.slow = 0;
     k.n_done = 0;
@@ -149,8 +150,6 @@ __device__ void exp_plan_block(const ExpView& v, int c_step) {
     s_m = m; s_words = words; s_D = k.D; s_fit = m;
     s_mean = k.mean; s_var = k.var;
     s_room = k.draws_end - k.pos;  // draws available from pos0 on
-    k.m = m;
-    *c = k;
   }
   __syncthreads();
   // guesses (relative to pos0): exact for pop 0, extrapolated with the running mean minus a lead that
@@ -170,8 +169,9 @@ __device__ void exp_plan_block(const ExpView& v, int c_step) {
   __syncthreads();
   const int m = s_fit;  // 0: the host must push draws first (it sees pos / draws_end in the status block)
   if (threadIdx.x == 0) {
-    c->m = m;
-    if (m > 0) c->steps_active++;
+    k.m = m;
+    if (m > 0) k.steps_active++;
+    *c = k;
   }
   const int n = m * s_words;
   for (int k = threadIdx.x; k < n; k += blockDim.x) v.mask[k] = 0ull;
@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v, int c_step_ne
     return;
   }
   __shared__ int s_any;
-  __shared__ unsigned long long s_part[1024];
+  __shared__ unsigned long long s_part[64];  // warp totals, then exclusive warp bases
   __shared__ unsigned long long s_base;
   const int S = v.S;
   const float r = v.r;
@@ -791,19 +791,27 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v, int c_step_ne
       mine += 1ull << 42;
     }
   }
-  s_part[tid] = mine;
-  __syncthreads();
-  if (tid < 32) {  // exclusive scan of this CTA's 1024 partials (32 values per lane)
-    unsigned long long sum = 0;
-    for (int k = 0; k < 32; ++k) { const unsigned long long x = s_part[tid * 32 + k]; s_part[tid * 32 + k] = sum; sum += x; }
-    unsigned long long inc = sum;
+  {  // exclusive scan of this CTA's 1024 partials: shuffles inside each warp, then over the 32 warp totals
+    unsigned long long inc = mine;
+    const int lane = tid & 31, wid = tid >> 5;
     for (int d = 1; d < 32; d <<= 1) {
       const unsigned long long t = __shfl_up_sync(FULL, inc, d);
-      if (tid >= d) inc += t;
+      if (lane >= d) inc += t;
     }
-    const unsigned long long exc = inc - sum;
-    for (int k = 0; k < 32; ++k) s_part[tid * 32 + k] += exc;
-    if (tid == 31) c->cta_tot[rank] = inc;
+    if (lane == 31) s_part[wid] = inc;   // warp totals in the first 32 slots
+    __syncthreads();
+    if (wid == 0) {
+      const unsigned long long wt = s_part[lane];
+      unsigned long long winc = wt;
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(FULL, winc, d);
+        if (lane >= d) winc += t;
+      }
+      s_part[32 + lane] = winc - wt;      // exclusive warp bases
+      if (lane == 31) c->cta_tot[rank] = winc;
+    }
+    __syncthreads();
+    mine = s_part[32 + wid] + inc - mine;  // exclusive prefix of this thread inside the CTA
   }
   cl.sync();
   if (tid == 0) {
@@ -832,7 +840,7 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v, int c_step_ne
     }
     return;
   }
-  const unsigned long long run0 = s_base + s_part[tid];
+  const unsigned long long run0 = s_base + mine;
   {
     unsigned long long run = run0;
     for (int s = a0; s < a1; ++s) {
@@ -884,10 +892,11 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v, int c_step_ne
       }
     }
   }
-  cl.sync();
+  // (no cluster barrier here: what CTA 0 does below reads nothing the other CTAs are still writing)
   if (rank != 0) return;
   // ---- CTA 0: control block, statistics, plan of the next step -----------------------------------------
   __shared__ unsigned long long s_sum, s_sq;
+  __shared__ ExpCtl s_ctl;
   if (tid == 0) { s_sum = 0; s_sq = 0; }
   __syncthreads();
   {  // draws / pop statistics of the committed pops
@@ -934,10 +943,10 @@ __global__ void __launch_bounds__(1024, 1) k_exp_commit(ExpView v, int c_step_ne
       k.var += w * ((float)var - k.var);
       if (k.var < 0.05f) k.var = 0.05f;
     }
-    *c = k;
+    s_ctl = k;  // handed to the plan below in shared memory; written back to the device copy once, there
   }
   // ---- plan the next step --------------------------------------------------------------------------
-  exp_plan_block(v, c_step_next);
+  exp_plan_block(v, c_step_next, &s_ctl);
 }
 
 // a pop handled by the host (interrupt): append its nodes, queue entries and requests

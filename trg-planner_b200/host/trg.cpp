@@ -1490,6 +1490,7 @@ void TRG::invalidateDeviceGraph() {
   dev_graph_ = nullptr;
   dev_graph_relaxed_ = 0;
   dev_graph_nodes_.clear();
+  built_row_.clear();  // (every change of the global graph comes through here)
 }
 
 void TRG::ensureDeviceGraph() {

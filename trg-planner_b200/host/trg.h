@@ -145,6 +145,11 @@ class TRG {
   void isCollisionBatch(const float* xy, int64_t n, const std::string& type, float threshold,
                         uint8_t* out);
   // wall-clock seconds of the last call at the reference's timer sites (planner.cpp:185-270)
+  // [+] The global graph as flat arrays without walking the node map, when it still is what the device build
+  // materialised (ids == pool slots, edges of a node consecutive in the edge pool): rows by id. Returns false when
+  // the graph has changed since (the caller then walks the map). Any output may be null. The caller holds lockGraph().
+  bool exportBuiltGraph(int32_t* iter_ids, int32_t* ids_sorted, float* pos_xyz, int32_t* state, int64_t* row_ptr,
+                        int32_t* col, float* weight, float* dist);
   double lastSeconds(const std::string& what) const;
   int64_t stat(const std::string& what) const;
   trgb_map* deviceMap(const std::string& type);
@@ -264,6 +269,7 @@ class TRG {
   trgb_graph* dev_graph_ = nullptr;
   int64_t dev_graph_relaxed_ = 0;  // edges relaxed by the handle so far (already booked in stat_)
   std::vector<Node*> dev_graph_nodes_;  // row -> node of the uploaded CSR
+  std::vector<int64_t> built_row_;      // first edge-pool slot of every node of the last device build (+ total); empty = graph changed since
   std::deque<Node> node_pool_;
   std::deque<Edge> edge_pool_;
   std::unordered_map<std::string, double>  secs_;

@@ -103,6 +103,8 @@ int trg_graph_export(void* h, const char* type, int32_t* iter_ids, int32_t* ids_
   return guard([&] {
     check_type(type);
     GraphLock lock(T(h));
+    if (std::string(type) == "global" && T(h)->exportBuiltGraph(iter_ids, ids_sorted, pos_xyz, state, row_ptr, col, weight, dist))
+      return 0;  // straight from the pools of the last device build
     const auto& g = T(h)->getGraphRef(type);
     std::vector<std::pair<int, TRG::Node*>> ids;
     ids.reserve(g.size());

@@ -412,6 +412,7 @@ bool TRG::buildGraphOnDevice(trgStruct& g) {
   dev_graph_ = search_graph.g;  // (resetGraph above dropped the previous one)
   search_graph.g = nullptr;
   dev_graph_relaxed_ = 0;
+  built_row_.assign(e_off.begin(), e_off.end());
   const double t_materialize = since(t_mat);
 
   stat_["pops"] += st.pops;
@@ -432,5 +433,33 @@ bool TRG::buildGraphOnDevice(trgStruct& g) {
   stat_["us_device_edges"] += (int64_t)(1e6 * t_edges);
   stat_["us_device_finalize"] += (int64_t)(1e6 * t_finalize);
   stat_["us_materialize"] += (int64_t)(1e6 * t_materialize);
+  return true;
+}
+
+bool TRG::exportBuiltGraph(int32_t* iter_ids, int32_t* ids_sorted, float* pos_xyz, int32_t* state, int64_t* row_ptr,
+                           int32_t* col, float* weight, float* dist) {
+  trgStruct& g = *trgMap_["global"];
+  const size_t m = g.nodes.size();
+  if (built_row_.size() != m + 1 || g.node_seq.size() != m || !g.seq_in_iter_order || node_used_ != m) return false;
+  const int threads = m > (size_t)tuning_.parallel_min_nodes ? trg_b200::thread_budget() : 1;
+  parallel_for(m, threads, [&](size_t b, size_t en) {
+    for (size_t k = b; k < en; ++k) {
+      const Node& nd = node_pool_[k];
+      if (iter_ids) iter_ids[k] = g.node_seq[k]->id_;
+      if (ids_sorted) ids_sorted[k] = (int32_t)k;
+      if (pos_xyz) { pos_xyz[3 * k] = nd.pos_.x(); pos_xyz[3 * k + 1] = nd.pos_.y(); pos_xyz[3 * k + 2] = nd.pos_.z(); }
+      if (state) state[k] = (int32_t)nd.state_;
+      if (row_ptr) row_ptr[k] = built_row_[k];
+      if (!col && !weight && !dist) continue;
+      int64_t e = built_row_[k];
+      for (const Edge* ed : nd.edges_) {
+        if (col) col[e] = ed->dst_id_;
+        if (weight) weight[e] = ed->weight_;
+        if (dist) dist[e] = ed->dist_;
+        ++e;
+      }
+    }
+  });
+  if (row_ptr) row_ptr[m] = built_row_[m];
   return true;
 }
