@@ -234,7 +234,9 @@ def run_product(a):
             d2h = int(r["ids"].nbytes + 4 * 4 * len(queries) + 2 * len(queries) + 8 * (len(queries) + 1))
         else:
             from trg_planner_b200 import sharding
-            cloud = d_pts if resident else pts   # strips are cut where the step's input lives
+            # boundary strips are cut on the device: from the resident input, or (host-buffer leg) from the cloud
+            # as the product's map index holds it in HBM after the upload - no second trip over PCIe
+            cloud = d_pts if resident else K.map_points_view(device_map_of(t))
             dev = torch.device("cuda", local)
             mg = sharding.build_merged_graph(dist, torch, dev, rank, world, t, cloud, bb, P, K)
             w2 = time.perf_counter()
@@ -256,6 +258,13 @@ def run_product(a):
                         plan_ms=round(1e3 * t.seconds("plan_batch"), 2))
         return dict(host=host, build_s=w1 - w0, exch_s=w2 - w1, query_s=w3 - w2, step_s=w3 - w0, nodes=nn, edges=ne,
                     found=found, d2h=d2h, xbytes=xb, merged=dict(merged_stats))
+
+    def device_map_of(handle):
+        import ctypes as C
+        tl = C.CDLL(str(ROOT / "trg-planner_b200" / "lib" / "libtrg_b200.so"), mode=C.RTLD_GLOBAL)
+        tl.trg_device_map.restype = C.c_void_p
+        tl.trg_device_map.argtypes = [C.c_void_p, C.c_char_p]
+        return C.c_void_p(tl.trg_device_map(handle.h, b"global"))
 
     def timed(resident: bool, warmup: int, steps: int):
         # nvidia-smi is started BEFORE the warm-up: its start-up (NVML init) holds driver locks for

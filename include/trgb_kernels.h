@@ -64,6 +64,8 @@ int  trgb_map_create(trgb_map** out, const float* host_pts, int64_t n, int strid
 int  trgb_map_create_dev(trgb_map** out, const float* dev_pts, int64_t n, int stride_floats, float cell_size);
 void trgb_map_destroy(trgb_map* m);
 int  trgb_map_info(const trgb_map* m, TrgbMapInfo* info);
+/* the indexed cloud in HBM: n records of 4 floats (x, y, z, bit-cast original index), sorted by cell (valid after trgb_map_sync) */
+int  trgb_map_points(const trgb_map* m, const float** d_xyzi, int64_t* n);
 void* trgb_map_stream(const trgb_map* m); /* cudaStream_t */
 int  trgb_map_sync(const trgb_map* m);
 /* options: "force_warp_path" (0/1) routes every query launch through the warp-per-item kernels

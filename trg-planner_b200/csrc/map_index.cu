@@ -398,6 +398,15 @@ extern "C" int trgb_map_info(const trgb_map* m, TrgbMapInfo* info) {
   return TRGB_OK;
 }
 
+// the indexed points where they lie in HBM: n records (x, y, z, bit-cast original index), sorted by cell; complete
+// once the handle's stream has been synchronised (trgb_map_sync)
+extern "C" int trgb_map_points(const trgb_map* m, const float** d_xyzi, int64_t* n) {
+  TRGB_ARG(m && d_xyzi && n, "null pointer");
+  *d_xyzi = reinterpret_cast<const float*>(m->view.pts);
+  *n = m->n;
+  return TRGB_OK;
+}
+
 extern "C" void* trgb_map_stream(const trgb_map* m) { return m ? (void*)m->stream : nullptr; }
 
 extern "C" int trgb_map_set_option(trgb_map* m, const char* key, int value) {

@@ -1658,7 +1658,14 @@ void TRG::planSafePathBatch(const float* queries, int64_t n, PathBatch& out) {
     // per-graph preparation, three independent pieces side by side: CSR build + upload (this
     // thread), order tree for goal snapping, hash grid for start snapping
     std::atomic<int64_t> us_tree{0}, us_grid{0};
-    auto f_tree = std::async(std::launch::async, [&] { auto a = Clock::now(); ensureTree(g); us_tree = (int64_t)(1e6 * since(a)); });
+    int device = 0;
+    cudaGetDevice(&device);
+    auto f_tree = std::async(std::launch::async, [&, device] {
+      cudaSetDevice(device);  // (per-thread state: the tree may be grown by trgb_kdtree_build)
+      auto a = Clock::now();
+      ensureTree(g);
+      us_tree = (int64_t)(1e6 * since(a));
+    });
     auto f_grid = std::async(std::launch::async, [&] { auto a = Clock::now(); ensureGridBuilt(g); us_grid = (int64_t)(1e6 * since(a)); });
     auto tc = Clock::now();
     try {

@@ -24,6 +24,8 @@
 #include <stdexcept>
 #include <thread>
 
+#include <cuda_runtime.h>
+
 #include "device_session.h"
 #include "map_order.h"
 #include "trg.h"
@@ -335,7 +337,10 @@ bool TRG::buildGraphOnDevice(trgStruct& g) {
   if (eager_index) {
     ensureGrid(g);
     f_grid = std::async(std::launch::async, [&] { g.node_grid.rebuild(g.seq_xy.data(), (int)m, std::max(1, threads / 2)); });
-    f_tree = std::async(std::launch::async, [&] {
+    int device = 0;
+    cudaGetDevice(&device);
+    f_tree = std::async(std::launch::async, [&, device] {
+      cudaSetDevice(device);  // the current device is per thread: a helper would otherwise build the tree on GPU 0
       std::vector<int> lo(m), hi(m), par(m);
       std::vector<uint8_t> ax(m);
       K(trgb_kdtree_build(g.seq_xy.data(), (int64_t)m, lo.data(), hi.data(), par.data(), ax.data()), "trgb_kdtree_build");

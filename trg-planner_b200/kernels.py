@@ -224,6 +224,26 @@ class DeviceMap:
                                          _vp(d_dist), _vp(d_npts) if d_npts else None), "trgb_edge_eval_launch")
 
 
+class _DevArray:
+    """Minimal __cuda_array_interface__ carrier: lets torch view device memory owned by the library."""
+
+    def __init__(self, ptr: int, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}   # (torch refuses the read-only flag; callers only read)
+
+
+def map_points_view(map_handle):
+    """torch view (n, 4) float32 of the indexed cloud of a trgb_map (x, y, z, bit-cast original index): the points
+    as the product holds them in HBM, e.g. to cut boundary strips without a second upload of the cloud."""
+    import torch
+    L = lib()
+    L.trgb_map_points.argtypes = [_vp, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    L.trgb_map_sync.argtypes = [_vp]
+    p, n = C.c_void_p(), C.c_int64()
+    _chk(L.trgb_map_points(map_handle, C.byref(p), C.byref(n)), "trgb_map_points")
+    _chk(L.trgb_map_sync(map_handle), "trgb_map_sync")
+    return torch.as_tensor(_DevArray(p.value, (n.value, 4)), device="cuda")
+
+
 class DeviceNodeGrid:
     """K5: device grid over graph nodes; batched exact nearest node (kd_nearest2 on the node tree, trg.cpp:615).
     `pos`: torch tensor (n, >= 2) on the device, or a numpy array."""
