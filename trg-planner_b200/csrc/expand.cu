@@ -1101,6 +1101,11 @@ struct trgb_expander {
   long long* d_row = nullptr; int* d_col = nullptr; float* d_w = nullptr; float* d_d = nullptr;
   int n_dir = 0;
   int n_nodes_final = 0;
+  // finalize arena: every temporary and output array of trgb_expander_finalize, carved from one grow-only block
+  // (a 50 M-point build needs 2 GB of them; taking and returning them from the pool each build fragmented it:
+  // 190 - 570 ms stalls in a rebuild loop)
+  char* fin_arena = nullptr;
+  size_t fin_bytes = 0;
   // pinned host staging of trgb_expander_download_view (grow-only: page-locking 70 MB costs tens of ms)
   void* h_pin = nullptr;
   size_t h_pin_bytes = 0;
@@ -1135,10 +1140,7 @@ extern "C" void trgb_expander_destroy(trgb_expander* e) {
     if (e->ev[k]) cudaEventDestroy(e->ev[k]);
   }
   if (e->h_pin) cudaFreeHost(e->h_pin);
-  if (e->d_row) cudaFreeAsync(e->d_row, 0);
-  if (e->d_col) cudaFreeAsync(e->d_col, 0);
-  if (e->d_w) cudaFreeAsync(e->d_w, 0);
-  if (e->d_d) cudaFreeAsync(e->d_d, 0);
+  if (e->fin_arena) cudaFree(e->fin_arena);  // (d_row / d_col / d_w / d_d live inside it)
   cudaStreamSynchronize(0);
   delete e;
 }
@@ -1489,12 +1491,32 @@ extern "C" int trgb_expander_finalize(trgb_expander* e, int64_t* n_nodes, int64_
   const long long nr = c.n_req;
   const int nn = c.n_nodes;
   e->n_nodes_final = nn;
-  // (stream-ordered pool: cudaMalloc / cudaFree stall for tens of ms once the pool holds GBs)
-  if (e->d_row) { cudaFreeAsync(e->d_row, st); e->d_row = nullptr; }
-  if (e->d_col) { cudaFreeAsync(e->d_col, st); e->d_col = nullptr; }
-  if (e->d_w) { cudaFreeAsync(e->d_w, st); e->d_w = nullptr; }
-  if (e->d_d) { cudaFreeAsync(e->d_d, st); e->d_d = nullptr; }
-  TRGB_CUDA(cudaMallocAsync((void**)&e->d_row, ((size_t)nn + 1) * sizeof(long long), st));
+  // one grow-only block for everything below (sizes are bounded by the request count: at most nr requests
+  // succeed, each giving two directed entries)
+  auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t NR = (size_t)std::max<long long>(nr, 1);
+  const int unc_cap = 1 << 16;
+  size_t need = 0;
+  auto take = [&](size_t bytes) { const size_t o = need; need += up(bytes); return o; };
+  const size_t o_row = take(((size_t)nn + 1) * sizeof(long long)), o_col = take(2 * NR * sizeof(int)), o_ow = take(2 * NR * sizeof(float)),
+               o_od = take(2 * NR * sizeof(float)), o_p1 = take(NR * 3 * sizeof(float)), o_p2 = take(NR * sizeof(float2)),
+               o_skip = take(NR * sizeof(float)), o_stage = take(NR), o_w = take(NR * sizeof(float)), o_d = take(NR * sizeof(float)),
+               o_ok = take(NR), o_cnt = take(4 * sizeof(int)), o_unc = take((size_t)unc_cap * sizeof(int)),
+               o_key = take(NR * 8), o_key2 = take(NR * 8), o_val = take(NR * 4), o_val2 = take(NR * 4),
+               o_dkey = take(2 * NR * 8), o_dkey2 = take(2 * NR * 8), o_dval = take(2 * NR * 4), o_dval2 = take(2 * NR * 4);
+  if (need > e->fin_bytes) {
+    if (e->fin_arena) cudaFree(e->fin_arena);
+    e->fin_arena = nullptr; e->fin_bytes = 0;
+    e->d_row = nullptr; e->d_col = nullptr; e->d_w = nullptr; e->d_d = nullptr;
+    const size_t want = need + need / 8;
+    TRGB_CUDA(cudaMalloc((void**)&e->fin_arena, want));
+    e->fin_bytes = want;
+  }
+  char* A = e->fin_arena;
+  e->d_row = reinterpret_cast<long long*>(A + o_row);
+  e->d_col = reinterpret_cast<int*>(A + o_col);
+  e->d_w = reinterpret_cast<float*>(A + o_ow);
+  e->d_d = reinterpret_cast<float*>(A + o_od);
   if (nr == 0) {
     TRGB_CUDA(cudaMemsetAsync(e->d_row, 0, ((size_t)nn + 1) * sizeof(long long), st));
     TRGB_CUDA(cudaStreamSynchronize(st));
@@ -1503,18 +1525,11 @@ extern "C" int trgb_expander_finalize(trgb_expander* e, int64_t* n_nodes, int64_
     return TRGB_OK;
   }
   const int grid = sm_count() * 8;
-  float* p1 = nullptr; float2* p2 = nullptr; float* skip = nullptr; unsigned char* stage = nullptr; float* w = nullptr; float* d = nullptr;
-  unsigned char* ok = nullptr; int* cnt = nullptr; int* unc = nullptr;
-  const int unc_cap = 1 << 16;
-  TRGB_CUDA(cudaMallocAsync((void**)&p1, (size_t)nr * 3 * sizeof(float), st));
-  TRGB_CUDA(cudaMallocAsync((void**)&p2, (size_t)nr * sizeof(float2), st));
-  TRGB_CUDA(cudaMallocAsync((void**)&skip, (size_t)nr * sizeof(float), st));
-  TRGB_CUDA(cudaMallocAsync((void**)&stage, (size_t)nr, st));
-  TRGB_CUDA(cudaMallocAsync((void**)&w, (size_t)nr * sizeof(float), st));
-  TRGB_CUDA(cudaMallocAsync((void**)&d, (size_t)nr * sizeof(float), st));
-  TRGB_CUDA(cudaMallocAsync((void**)&ok, (size_t)nr, st));
-  TRGB_CUDA(cudaMallocAsync((void**)&cnt, 4 * sizeof(int), st));
-  TRGB_CUDA(cudaMallocAsync((void**)&unc, (size_t)unc_cap * sizeof(int), st));
+  float* p1 = reinterpret_cast<float*>(A + o_p1); float2* p2 = reinterpret_cast<float2*>(A + o_p2);
+  float* skip = reinterpret_cast<float*>(A + o_skip); unsigned char* stage = reinterpret_cast<unsigned char*>(A + o_stage);
+  float* w = reinterpret_cast<float*>(A + o_w); float* d = reinterpret_cast<float*>(A + o_d);
+  unsigned char* ok = reinterpret_cast<unsigned char*>(A + o_ok); int* cnt = reinterpret_cast<int*>(A + o_cnt);
+  int* unc = reinterpret_cast<int*>(A + o_unc);
   TRGB_CUDA(cudaMemsetAsync(cnt, 0, 4 * sizeof(int), st));
   k_fin_prepare<<<grid, 256, 0, st>>>(v, nr, p1, p2, skip);
   // wire requests reach expand_dist + robot_size (a node created robot_size from the sample's parent circle)
@@ -1555,11 +1570,8 @@ extern "C" int trgb_expander_finalize(trgb_expander* e, int64_t* n_nodes, int64_
     }
   }
   // (pair, request index) of every request that would succeed, in request order per pair
-  unsigned long long *key = nullptr, *key2 = nullptr; unsigned int *val = nullptr, *val2 = nullptr;
-  TRGB_CUDA(cudaMallocAsync((void**)&key, (size_t)nr * sizeof(unsigned long long), st));
-  TRGB_CUDA(cudaMallocAsync((void**)&key2, (size_t)nr * sizeof(unsigned long long), st));
-  TRGB_CUDA(cudaMallocAsync((void**)&val, (size_t)nr * sizeof(unsigned int), st));
-  TRGB_CUDA(cudaMallocAsync((void**)&val2, (size_t)nr * sizeof(unsigned int), st));
+  unsigned long long *key = reinterpret_cast<unsigned long long*>(A + o_key), *key2 = reinterpret_cast<unsigned long long*>(A + o_key2);
+  unsigned int *val = reinterpret_cast<unsigned int*>(A + o_val), *val2 = reinterpret_cast<unsigned int*>(A + o_val2);
   // compaction by atomics loses the request order inside a pair: sort by (pair, index) instead, in
   // two stable passes (index first — it is the value —, then pair)
   k_fin_keys<<<grid, 256, 0, st>>>(v, nr, ok, key, val, cnt);
@@ -1575,12 +1587,8 @@ extern "C" int trgb_expander_finalize(trgb_expander* e, int64_t* n_nodes, int64_
     if (rc2) return rc2;
   }
   // first of each pair -> two directed entries keyed (source node, request index)
-  unsigned long long *dkey = nullptr, *dkey2 = nullptr; unsigned int *dval = nullptr, *dval2 = nullptr;
-  const size_t nd_cap = (size_t)2 * std::max(n_ok, 1);
-  TRGB_CUDA(cudaMallocAsync((void**)&dkey, nd_cap * sizeof(unsigned long long), st));
-  TRGB_CUDA(cudaMallocAsync((void**)&dkey2, nd_cap * sizeof(unsigned long long), st));
-  TRGB_CUDA(cudaMallocAsync((void**)&dval, nd_cap * sizeof(unsigned int), st));
-  TRGB_CUDA(cudaMallocAsync((void**)&dval2, nd_cap * sizeof(unsigned int), st));
+  unsigned long long *dkey = reinterpret_cast<unsigned long long*>(A + o_dkey), *dkey2 = reinterpret_cast<unsigned long long*>(A + o_dkey2);
+  unsigned int *dval = reinterpret_cast<unsigned int*>(A + o_dval), *dval2 = reinterpret_cast<unsigned int*>(A + o_dval2);
   k_fin_edges<<<grid, 256, 0, st>>>(v, n_ok, key, val, dkey, dval, cnt + 2);
   int n_dir = 0;
   TRGB_CUDA(cudaMemcpyAsync(&n_dir, cnt + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1590,14 +1598,8 @@ extern "C" int trgb_expander_finalize(trgb_expander* e, int64_t* n_nodes, int64_
     const int rc3 = sort_pairs_u64_u32(dkey, dkey2, dval, dval2, n_dir, 64, st);
     if (rc3) return rc3;
   }
-  TRGB_CUDA(cudaMallocAsync((void**)&e->d_col, std::max<size_t>(n_dir, 1) * sizeof(int), st));
-  TRGB_CUDA(cudaMallocAsync((void**)&e->d_w, std::max<size_t>(n_dir, 1) * sizeof(float), st));
-  TRGB_CUDA(cudaMallocAsync((void**)&e->d_d, std::max<size_t>(n_dir, 1) * sizeof(float), st));
   k_fin_csr<<<grid, 256, 0, st>>>(v, n_dir, nn, dkey2, dval2, e->d_row, e->d_col, e->d_w, e->d_d);
   TRGB_CUDA(cudaGetLastError());
-  for (void* p : {(void*)p1, (void*)p2, (void*)skip, (void*)stage, (void*)w, (void*)d, (void*)ok, (void*)cnt, (void*)unc, (void*)key,
-                  (void*)key2, (void*)val, (void*)val2, (void*)dkey, (void*)dkey2, (void*)dval, (void*)dval2})
-    cudaFreeAsync(p, st);
   TRGB_CUDA(cudaStreamSynchronize(st));
   e->n_dir = n_dir;
   *n_nodes = nn;

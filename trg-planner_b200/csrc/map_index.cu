@@ -18,6 +18,8 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace trgb {
@@ -352,22 +354,57 @@ extern "C" int trgb_map_create_dev(trgb_map** out, const float* dev_pts, int64_t
   return TRGB_OK;
 }
 
+// The device-side landing buffer of a host cloud is parked between calls (one per process, grow-only): a 50 M-point
+// cloud is 600 MB, and taking / returning a block of that size from the pool on every map rebuild, next to the
+// 800 MB index it is sorted into, sent every few allocations to the driver for fresh memory (140 - 570 ms stalls
+// measured in a rebuild loop). A second thread that finds the buffer busy falls back to a pool allocation.
+namespace {
+struct LandingBuffer {
+  std::mutex mx;
+  float* p = nullptr;
+  size_t bytes = 0;
+  int device = -1;
+} g_landing;
+}  // namespace
+
 extern "C" int trgb_map_create(trgb_map** out, const float* host_pts, int64_t n, int stride_floats,
                                float cell_size) {
   TRGB_ARG(host_pts != nullptr && n > 0, "empty point cloud");
   TRGB_ARG(stride_floats == 3 || stride_floats == 4, "stride_floats must be 3 or 4");
   tune_mempool_once();
-  float* d_in = nullptr;
   const size_t bytes = (size_t)n * stride_floats * sizeof(float);
-  TRGB_CUDA(cudaMallocAsync((void**)&d_in, bytes, 0));
+  int dev = 0;
+  TRGB_CUDA(cudaGetDevice(&dev));
+  std::unique_lock<std::mutex> parked(g_landing.mx, std::try_to_lock);
+  float* d_in = nullptr;
+  bool own = false;
+  if (parked.owns_lock()) {
+    if (g_landing.device != dev || g_landing.bytes < bytes) {
+      if (g_landing.p) {
+        if (g_landing.device >= 0 && g_landing.device != dev) { cudaSetDevice(g_landing.device); cudaFree(g_landing.p); cudaSetDevice(dev); }
+        else cudaFree(g_landing.p);
+      }
+      g_landing.p = nullptr; g_landing.bytes = 0; g_landing.device = dev;
+      const size_t want = bytes + bytes / 8;
+      cudaError_t ea = cudaMalloc((void**)&g_landing.p, want);
+      if (ea != cudaSuccess) return cuda_fail(ea, "cudaMalloc (landing buffer of the cloud)", __FILE__, __LINE__);
+      g_landing.bytes = want;
+    }
+    d_in = g_landing.p;
+  } else {
+    TRGB_CUDA(cudaMallocAsync((void**)&d_in, bytes, 0));
+    own = true;
+  }
   cudaError_t e = cudaMemcpyAsync(d_in, host_pts, bytes, cudaMemcpyHostToDevice, 0);
   if (e == cudaSuccess) e = cudaStreamSynchronize(0);
   if (e != cudaSuccess) {
-    cudaFreeAsync(d_in, 0);
+    if (own) cudaFreeAsync(d_in, 0);
     return cuda_fail(e, "cudaMemcpy H2D (map points)", __FILE__, __LINE__);
   }
   int rc = trgb_map_create_dev(out, d_in, n, stride_floats, cell_size);
-  cudaFreeAsync(d_in, 0);
+  // (the index build reads d_in on the new handle's stream: finish it before the buffer can be handed out again)
+  if (rc == TRGB_OK && !own) rc = trgb_map_sync(*out);
+  if (own) cudaFreeAsync(d_in, 0);
   return rc;
 }
 
