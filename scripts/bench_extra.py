@@ -143,6 +143,11 @@ def run_c5(a):
     torch.cuda.synchronize()
     crop_ext = min(140.0, ext)
     crop = pts[(pts[:, 0] < crop_ext) & (pts[:, 1] < crop_ext)].cpu().numpy() if not a.no_cpu else None
+    # built twice: the first build also pays the pool's first 4 GB of physical memory (a one-time cost of the
+    # process, ~0.18 s); the second is the K1 kernels
+    dm = K.DeviceMap(None, 0.67 * P.robot_size, dev_ptr=pts.data_ptr(), n=n, stride=3)
+    dm.sync()
+    dm.close()
     t0 = time.perf_counter()
     dm = K.DeviceMap(None, 0.67 * P.robot_size, dev_ptr=pts.data_ptr(), n=n, stride=3)
     dm.sync()
