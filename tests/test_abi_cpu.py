@@ -53,6 +53,25 @@ def test_analytic_unordered_map_order_matches_libstdcxx(tmp_path):
     assert r.returncode == 0, r.stdout[-2000:]
 
 
+def test_save_graph_numbers_are_laid_out_like_nlohmann(built, tmp_path):
+    """TRG::saveGraph writes floats the way nlohmann::json::dump(4) does in the reference (fixed / scientific switch,
+    '.0' suffix, two-digit exponents): tests/host/json_number_check.cpp against the real json.hpp of the image."""
+    import sysconfig
+    inc = None
+    for d in ("/usr/include", "/usr/local/include", sysconfig.get_paths()["purelib"] + "/include/cudnn_frontend/thirdparty"):
+        if (Path(d) / "nlohmann" / "json.hpp").exists():
+            inc = d
+            break
+    if inc is None:
+        pytest.skip("nlohmann/json.hpp not in this image")
+    exe = tmp_path / "json_number_check"
+    lib = ROOT / "trg-planner_b200" / "lib"
+    subprocess.run(["g++", "-O2", "-std=c++17", f"-I{inc}", str(ROOT / "tests" / "host" / "json_number_check.cpp"), "-o", str(exe),
+                    f"-L{lib}", "-ltrg_b200", "-ltrgb_kernels", f"-Wl,-rpath,{lib}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+
+
 def build_consumer(tmp_path):
     """tests/host/consumer_check.cpp: class TRG used the way TRGPlanner, the ROS nodes and the pybind module use it."""
     exe = tmp_path / "consumer_check"

@@ -118,6 +118,41 @@ def test_nearest_z_tie_rule_on_a_duplicate_bearing_cloud(pkg, K, small_mountain)
             assert differ.sum() <= tied.sum()
 
 
+def test_map_index_with_crowded_cells(pkg, K, small_mountain):
+    """K1 on a cloud whose cells hold thousands of points (raw, un-voxelised scans; duplicates): the per-cell ordering
+    by original index switches to a heap sort beyond 48 points, the layout stays deterministic and every query
+    agrees with the reference."""
+    P = pkg.MOUNTAIN
+    rng = np.random.default_rng(33)
+    base = small_mountain[:: 3]
+    blobs = []
+    for cx, cy, k in ((5.03, 7.01, 6000), (12.4, 3.3, 900), (20.0, 20.0, 60)):
+        b = np.column_stack([rng.normal(cx, 0.02, k), rng.normal(cy, 0.02, k), rng.normal(0.5, 0.3, k)])
+        blobs.append(b.astype(np.float32))
+    pts = np.concatenate([base] + blobs).astype(np.float32)
+    pts = pts[rng.permutation(len(pts))]
+    o = pkg.oracle(P)
+    o.set_global_map(pts)
+    q = np.concatenate([_queries(pts, 4000, 3, margin=0.0),
+                        np.column_stack([rng.normal(5.03, 0.3, 500), rng.normal(7.01, 0.3, 500)]).astype(np.float32)])
+    outs = []
+    for rep in range(2):
+        dm = K.DeviceMap(pts, P.robot_size)
+        z, idx, tie = dm.nearest_z(q)
+        cnt = dm.range_count(q, P.robot_size)
+        coll = dm.collision(q, P.robot_size, P.height_threshold, P.collision_threshold)
+        outs.append((z, idx, cnt, coll))
+        dm.close()
+    for a, b in zip(outs[0], outs[1]):
+        np.testing.assert_array_equal(a, b)          # two builds, one layout
+    oz, oidx, otie = o.nearest_z(q)
+    ok = otie == 0
+    np.testing.assert_array_equal(outs[0][1][ok], oidx[ok])
+    np.testing.assert_array_equal(outs[0][0][ok], oz[ok])
+    np.testing.assert_array_equal(outs[0][2], o.range_count(q, P.robot_size))
+    np.testing.assert_array_equal(outs[0][3].astype(bool), o.is_collision(q, P.collision_threshold).astype(bool))
+
+
 def _edge_pairs(pts, o, n, seed, e):
     rng = np.random.default_rng(seed)
     a = _queries(pts, n, seed, margin=-1.0)

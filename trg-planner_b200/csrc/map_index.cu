@@ -190,12 +190,38 @@ __global__ void __launch_bounds__(256) k_scatter(const float* __restrict__ pts, 
   }
 }
 
-// one thread per cell: insertion sort by original index (cells hold a handful of points)
+// one thread per cell: insertion sort by original index (cells hold a handful of points). A cell of an
+// un-voxelised or duplicate-laden cloud can hold thousands: beyond 48 points the thread switches to an in-place
+// heap sort (O(k log k): 1e4 points cost 1e5 steps instead of the 1e8 of the insertion sort).
+__device__ __forceinline__ void cell_sift_down(float4* a, uint32_t root, uint32_t n) {
+  const float4 x = a[root];
+  const int kx = __float_as_int(x.w);
+  for (;;) {
+    uint32_t child = 2 * root + 1;
+    if (child >= n) break;
+    if (child + 1 < n && __float_as_int(a[child + 1].w) > __float_as_int(a[child].w)) ++child;
+    if (__float_as_int(a[child].w) <= kx) break;
+    a[root] = a[child];
+    root = child;
+  }
+  a[root] = x;
+}
+
 __global__ void __launch_bounds__(256) k_sort_cell(const uint32_t* __restrict__ cell_start,
                                                    int64_t ncells, float4* __restrict__ pts) {
   for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < ncells;
        c += (int64_t)gridDim.x * blockDim.x) {
     const uint32_t s = cell_start[c], e = cell_start[c + 1];
+    if (e - s > 48u) {
+      float4* a = pts + s;
+      const uint32_t n = e - s;
+      for (uint32_t i = n / 2; i-- > 0;) cell_sift_down(a, i, n);
+      for (uint32_t m = n - 1; m > 0; --m) {
+        const float4 t = a[0]; a[0] = a[m]; a[m] = t;
+        cell_sift_down(a, 0, m);
+      }
+      continue;
+    }
     for (uint32_t i = s + 1; i < e; ++i) {
       const float4 key = pts[i];
       const int ki = __float_as_int(key.w);

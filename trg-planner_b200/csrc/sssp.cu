@@ -65,6 +65,10 @@ constexpr int kSsspThreads = TRGB_SSSP_THREADS;
 constexpr unsigned long long kInfLabel = 0x7f800000ffffffffull;
 constexpr int kGroup = 8;  // lanes cooperating on one node's edge list
 constexpr int kPartials = 256;
+// goal bound: a node is dropped when g + h exceeds the best goal label by more than the parity tolerance (1e-5
+// relative): float sums over several hundred edges carry ~sqrt(hops) ulp of rounding, a few ulp of slack could
+// prune a node of the true optimum on zero-risk, near-straight stretches where h is tight
+constexpr float kGoalSlack = 1.00001f;
 
 // ------------------------------------------------------------------------------------------------------
 // search-graph construction
@@ -351,7 +355,7 @@ __global__ void __launch_bounds__(kSsspThreads, 1024 / kSsspThreads) k_sssp(
           const int4 ru = __ldg(node + u);
           const int e1 = __ldg(&node[u + 1].x);
           // goal bound: with a consistent heuristic no path through u beats `best`
-          if (__fadd_rn(gu, dist2d(__int_as_float(ru.z), __int_as_float(ru.w), gpos)) > best * 1.000001f) {
+          if (__fadd_rn(gu, dist2d(__int_as_float(ru.z), __int_as_float(ru.w), gpos)) > best * kGoalSlack) {
             if (gl == 0) atomicAdd(&s_dbg[4], 1ull);
             continue;
           }
@@ -408,7 +412,7 @@ __global__ void __launch_bounds__(kSsspThreads, 1024 / kSsspThreads) k_sssp(
       for (int k = tid; k < nfar; k += kSsspThreads) {
         const int v = qfar[k];
         const float f = __fadd_rn(label_g(__ldcg(label + v)), heur(node, v, gpos));
-        if (f > best * 1.000001f) { clear_bit(far_bits, v); continue; }  // can never matter
+        if (f > best * kGoalSlack) { clear_bit(far_bits, v); continue; }  // can never matter
         if (f < thr) {
           clear_bit(far_bits, v);
           if (set_bit(cur_bits, v)) qcur[atomicAdd(cur_cnt, 1)] = v;

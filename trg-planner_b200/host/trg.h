@@ -39,6 +39,7 @@ struct trgb_expander;
 namespace trg_b200 {
 class DeviceSession;
 class Expander;
+std::string json_number(float f);  // a float as nlohmann::json::dump writes it (trg_io.cpp; saveGraph)
 }  // namespace trg_b200
 
 class TRG {

@@ -5,6 +5,7 @@
 // shortest-round-trip); this file writes the same layout and reads any JSON with that schema, so
 // graphs built here load in an unmodified reference and vice versa.
 #include <charconv>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <filesystem>
@@ -116,15 +117,48 @@ class JReader {
   size_t i_ = 0;
 };
 
-// nlohmann stores a float as double and prints the shortest string that round-trips the double
-std::string fnum(float f) {
+}  // namespace
+
+// nlohmann stores a float as double and prints a digit string that round-trips the double, laid out by its
+// format_buffer (json.hpp, detail::to_chars): fixed notation while the decimal point lies within [-4, 15) digits of
+// the first digit ("100000.0", "0.0001"), otherwise d[.ddd]e[+-]XX with at least two exponent digits. Same layout
+// here; the digits are the SHORTEST round-trip string (std::to_chars), where nlohmann's Grisu2 now and then emits a
+// 17th digit or rounds it the other way (2 % of random floats; both parse to the same double:
+// tests/host/json_number_check.cpp).
+std::string trg_b200::json_number(float f) {
+  const double v = (double)f;
+  if (v == 0.0) return std::signbit(v) ? "-0.0" : "0.0";
+  if (!std::isfinite(v)) return "null";  // (nlohmann dumps non-finite numbers as null)
   char buf[64];
-  auto r = std::to_chars(buf, buf + sizeof(buf), (double)f);
-  std::string s(buf, r.ptr);
-  if (s.find_first_of(".eEni") == std::string::npos) s += ".0";
-  return s;
+  auto r = std::to_chars(buf, buf + sizeof(buf), std::fabs(v), std::chars_format::scientific);  // d[.ddd]e[+-]XX, shortest
+  std::string sci(buf, r.ptr);
+  const size_t epos = sci.find('e');
+  std::string digits;
+  for (size_t i = 0; i < epos; ++i)
+    if (sci[i] != '.') digits += sci[i];
+  const int k = (int)digits.size();
+  const int n = std::atoi(sci.c_str() + epos + 1) + 1;  // the decimal point sits after n digits
+  std::string out = std::signbit(v) ? "-" : "";
+  if (k <= n && n <= 15) {
+    out += digits + std::string((size_t)(n - k), '0') + ".0";
+  } else if (0 < n && n <= 15) {
+    out += digits.substr(0, (size_t)n) + "." + digits.substr((size_t)n);
+  } else if (-4 < n && n <= 0) {
+    out += "0." + std::string((size_t)(-n), '0') + digits;
+  } else {
+    out += digits.substr(0, 1);
+    if (k > 1) out += "." + digits.substr(1);
+    const int e = n - 1;
+    out += e < 0 ? "e-" : "e+";
+    const int ae = e < 0 ? -e : e;
+    if (ae < 10) out += "0";
+    out += std::to_string(ae);
+  }
+  return out;
 }
 
+namespace {
+inline std::string fnum(float f) { return trg_b200::json_number(f); }
 }  // namespace
 
 void TRG::saveGraph(const std::string& filepath) {  // trg.cpp:130-177
