@@ -263,3 +263,74 @@ def test_merged_graph_gloo_world2_paths_cross_the_border(pkg):
                 heapq.heappush(pq, (nd, v))
     far = np.nonzero(m0["pos"][:, 0] > 24.0)[0]
     assert len(far) > 10 and np.isfinite(dist_[far]).mean() > 0.9
+
+
+def _qlist_worker(rank, world, port, q):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    import _pkg
+    trg = _pkg.load()
+    from trg_planner_b200 import sharding
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    P = trg.MOUNTAIN
+    pts = trg.terrain.stairs(160, h=0.1, seed=5)
+    rng = np.random.default_rng(3)
+    qxy = rng.uniform(pts[:, :2].min(0) - 0.5, pts[:, :2].max(0) + 0.5, size=(3000, 2)).astype(np.float32)
+    oracle = _pkg.load_oracle().oracle
+
+    def k2_k3(part, idx):   # CPU tests: the oracle stands in for the K2 / K3 kernels
+        o = oracle(P)
+        o.set_global_map(part)
+        coll = o.is_collision(qxy[idx], P.collision_threshold).astype(np.float32)
+        cnt = o.range_count(qxy[idx], P.robot_size).astype(np.int32).view(np.float32)
+        z, _, tie = o.nearest_z(qxy[idx])
+        return np.column_stack([coll, cnt, z, tie.astype(np.float32)])
+
+    # K3 looks at the nearest point wherever it is: on this dense map it is closer than 0.3 m from every query
+    rows, st = sharding.sharded_query_list(dist, torch, torch.device("cpu"), rank, world, pts, qxy, max(P.robot_size, 0.3) + 0.05, k2_k3)
+    q.put((rank, rows, st, qxy, pts))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_query_list_morton_partition_gloo_world4_equals_unsharded(pkg):
+    """SURVEY 8(e), pure kernels on a fixed query list: Morton partition of the queries, every rank holds only the map
+    points within the halo of its run, all-gather of the outputs — and the answers are those of the whole map."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world = 4
+    port = 29450 + (os.getpid() % 100)
+    procs = [ctx.Process(target=_qlist_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(world):
+        r = q.get(timeout=400)
+        res[r[0]] = r
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rows, qxy, pts = res[0][1], res[0][3], res[0][4]
+    for r in range(1, world):
+        np.testing.assert_array_equal(rows, res[r][1])
+    assert sum(res[r][2]["mine"] for r in range(world)) == len(qxy)
+    # a quarter of a Z-curve is a quadrant: every rank holds about a quarter of the map plus the halo
+    assert all(res[r][2]["map_points_mine"] < 0.4 * len(pts) for r in range(world))
+    P = pkg.MOUNTAIN
+    o = pkg.oracle(P)
+    o.set_global_map(pts)
+    np.testing.assert_array_equal(rows[:, 0] > 0, o.is_collision(qxy, P.collision_threshold).astype(bool))
+    np.testing.assert_array_equal(np.ascontiguousarray(rows[:, 1]).view(np.int32), o.range_count(qxy, P.robot_size))
+    z, _, tie = o.nearest_z(qxy)
+    inside = (qxy[:, 0] > pts[:, 0].min()) & (qxy[:, 0] < pts[:, 0].max()) & (qxy[:, 1] > pts[:, 1].min()) & (qxy[:, 1] < pts[:, 1].max())
+    ok = inside & (tie == 0)
+    np.testing.assert_array_equal(rows[ok, 2], z[ok])
+    # the Morton order itself: a permutation, and spatially coherent (consecutive queries are close)
+    from trg_planner_b200 import sharding
+    order = sharding.morton_order(qxy, qxy.min(0), qxy.max(0))
+    assert sorted(order.tolist()) == list(range(len(qxy)))
+    step = np.hypot(*(qxy[order][1:] - qxy[order][:-1]).T)
+    assert np.median(step) < 0.1 * np.hypot(*(qxy.max(0) - qxy.min(0)))

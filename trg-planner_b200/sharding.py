@@ -361,3 +361,88 @@ def plan_sharded(dist, torch, device, rank, world, mg, queries, P, K):
     return dict(found=rec_np[:, 0] > 0, cost=rec_np[:, 1], path_length=rec_np[:, 2], offsets=offs, ids=ids_np,
                 cross_tile_paths=cross, gather_bytes=int(rec_all.numel() * 4 + ids_all.numel() * 4),
                 d2h_bytes=int(rec_np.nbytes + ids_np.nbytes))
+
+
+# ---------------------------------------------------------------------------------------------------
+# Pure query kernels (K2 / K3 / K4) over a fixed query list: Morton partition of the queries, each rank
+# holds only the map points its queries can reach
+# ---------------------------------------------------------------------------------------------------
+def morton_order(xy: np.ndarray, lo, hi) -> np.ndarray:
+    """Indices that sort 2-D points along a Morton (Z-order) curve over the box [lo, hi] (16 bits per axis);
+    ties keep the input order. Identical on every rank for identical input."""
+    xy = np.asarray(xy, np.float64)
+    span = np.maximum(np.asarray(hi, np.float64) - np.asarray(lo, np.float64), 1e-9)
+    q = np.clip((xy - np.asarray(lo, np.float64)) / span * 65535.0, 0, 65535).astype(np.uint32)
+
+    def spread(v):
+        v = v & np.uint32(0xFFFF)
+        v = (v | (v << np.uint32(8))) & np.uint32(0x00FF00FF)
+        v = (v | (v << np.uint32(4))) & np.uint32(0x0F0F0F0F)
+        v = (v | (v << np.uint32(2))) & np.uint32(0x33333333)
+        v = (v | (v << np.uint32(1))) & np.uint32(0x55555555)
+        return v
+
+    code = spread(q[:, 0]) | (spread(q[:, 1]) << np.uint32(1))
+    return np.argsort(code, kind="stable")
+
+
+def sharded_query_list(dist, torch, device, rank: int, world: int, cloud: np.ndarray, anchors: np.ndarray, halo: float,
+                       evaluate):
+    """One batch of independent map queries split over the ranks, no communication while they run.
+
+    anchors (n, 2): the point that locates query i (the query point for K2 / K3, the first end point for K4).
+    The queries are ordered along a Morton curve and cut into `world` contiguous runs; rank r keeps only the map
+    points within `halo` of the bounding box of its run (halo >= the largest radius a query of the run reads:
+    robot_size for K2, the search ring for K3, edge length + ellipse semi-axis for K4), so every query sees exactly
+    the points it would see on the whole map and the answers are bit-identical to the unsharded ones.
+    evaluate(map_points (m, 3) float32, indices of my queries) -> float32 array (len(indices), k); integers
+    travel bit-cast. The rows are all-gathered (one ragged collective) and put back in the caller's order.
+    Returns (rows (n, k) float32 in query order, stats)."""
+    anchors = np.ascontiguousarray(anchors, np.float32)
+    n = anchors.shape[0]
+    lo, hi = anchors.min(0), anchors.max(0)
+    order = morton_order(anchors, lo, hi)
+    sl = query_shard(n, rank, world)
+    mine = order[sl]
+    if mine.size:
+        # the map cells my queries can reach: coarse tiles (>= the halo wide) that hold a query of mine, grown by one
+        # tile. (A bounding box would not do: a run of a Z-curve that spills a few queries into the next quadrant
+        # has a box twice its area.)
+        ext = np.maximum(hi - lo, 1e-6)
+        T = float(max(halo, float(ext.max()) / 256.0))
+        org = lo - T
+        W, H = int(np.floor((ext[0] + 2 * T) / T)) + 2, int(np.floor((ext[1] + 2 * T) / T)) + 2
+        tq = np.floor((anchors[mine] - org) / T).astype(np.int64)
+        grid = np.zeros((H, W), bool)
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                grid[np.clip(tq[:, 1] + dy, 0, H - 1), np.clip(tq[:, 0] + dx, 0, W - 1)] = True
+        if hasattr(cloud, "is_cuda"):
+            g = torch.from_numpy(grid).to(cloud.device)
+            tx = torch.floor((cloud[:, 0] - float(org[0])) / T).long()
+            ty = torch.floor((cloud[:, 1] - float(org[1])) / T).long()
+            inside = (tx >= 0) & (tx < W) & (ty >= 0) & (ty < H)
+            m = inside & g[ty.clamp(0, H - 1), tx.clamp(0, W - 1)]
+            part = cloud[m][:, :3].contiguous()
+        else:
+            tx = np.floor((cloud[:, 0] - org[0]) / T).astype(np.int64)
+            ty = np.floor((cloud[:, 1] - org[1]) / T).astype(np.int64)
+            inside = (tx >= 0) & (tx < W) & (ty >= 0) & (ty < H)
+            m = inside & grid[np.clip(ty, 0, H - 1), np.clip(tx, 0, W - 1)]
+            part = np.ascontiguousarray(cloud[m][:, :3], np.float32)
+        rows = np.ascontiguousarray(evaluate(part, mine), np.float32)
+        n_part = int(part.shape[0])
+    else:
+        rows, n_part = None, 0
+    k = rows.shape[1] if rows is not None else 0
+    kk = torch.tensor([k], dtype=torch.int64, device=device)
+    dist.all_reduce(kk, op=dist.ReduceOp.MAX)   # ranks with an empty share learn the row width
+    k = int(kk.item())
+    if rows is None:
+        rows = np.zeros((0, k), np.float32)
+    got = allgather_rows(dist, torch, rows, device)
+    out = np.empty((n, k), np.float32)
+    for r in range(world):
+        out[order[query_shard(n, r, world)]] = got[r]
+    return out, dict(queries=n, mine=int(mine.size), map_points_mine=n_part, map_points_all=int(cloud.shape[0]),
+                     gathered_bytes=int(sum(g.nbytes for g in got)))
