@@ -306,6 +306,12 @@ def run_product(a):
         K.prof_enable(False)
         if "k_sssp" in profd:
             profd["k_sssp"]["units"] = float(t.stat("sssp_relaxed_edges") - r0)
+        # the per-sample kernels of the device BFS are launched for the step's capacity (a power of two of pops);
+        # their work units are the samples the steps actually held
+        samples = float(sum(r["host"]["pops"] for r in rows)) * P.sample_num
+        for kname in ("k_exp_commit", "k_exp_emit", "k_exp_deps"):
+            if kname in profd and samples > 0:
+                profd[kname]["units"] = samples
         profd["_wall"] = {"build_ms": 1e3 * float(np.mean([r["build_s"] for r in rows])),
                           "query_ms": 1e3 * float(np.mean([r["query_s"] for r in rows]))}
         return profd
@@ -369,7 +375,8 @@ def run_product(a):
         psteps = val["prof_steps"]
         kern = {k: dict(launches=int(v["launches"] / psteps), ms_per_step=round(v["ms"] / psteps, 3),
                         units_per_step=int(v["units"] / psteps),
-                        achieved_gbs=round(unit_bytes(k, P, rho, cell) * v["units"] / max(v["ms"], 1e-9) / 1e6, 1))
+                        achieved_gbs=round(unit_bytes(k, P, rho, cell) * v["units"] / max(v["ms"], 1e-9) / 1e6, 1),
+                        frac_of_peak=round(unit_bytes(k, P, rho, cell) * v["units"] / max(v["ms"], 1e-9) / 1e6 / peak, 4))
                 for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
