@@ -236,47 +236,22 @@ def allgather_concat(dist, torch, t, device):
     return torch.cat([out[r][: counts[r]] for r in range(world)]), counts
 
 
-def allgather_ragged(dist, torch, t, device):
-    """All-gather of one 1-D tensor per rank with ragged length; returns the list of the ranks' tensors."""
-    world = dist.get_world_size()
-    t = t.to(device).contiguous()
-    cnt = torch.tensor([t.shape[0]], dtype=torch.int64, device=device)
-    cnts = [torch.zeros_like(cnt) for _ in range(world)]
-    dist.all_gather(cnts, cnt)
-    counts = [int(c) for c in torch.cat(cnts).cpu()]
-    mx = max(1, max(counts))
-    pad = torch.zeros((mx,), dtype=t.dtype, device=device)
-    if t.shape[0]:
-        pad[: t.shape[0]] = t
-    out = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(out, pad)
-    return [out[r][: counts[r]] for r in range(world)]
-
-
 def merge_graphs(dist, torch, device, rank, world, local, stitched, compute_device=None):
     """Every rank's tile graph (`local`: GraphSnapshot, CSR by local id) + the stitched cross-tile edges
     (rows rank_a, id_a, rank_b, id_b, weight, dist) -> ONE global CSR, identical on every rank.
     Global id = node offset of the owner rank + local id; a node's edge list keeps its local order, the
     stitched edges follow. Exchange: all-gathers of positions / states and of the edge lists."""
-    # the tile graphs travel as they are (CSR, local ids) in TWO ragged all-gathers of flat float32 buffers:
-    # [positions | states | degrees] (20 bytes per node) and [targets | risks | lengths] (12 bytes per edge);
-    # integers ride bit-cast; global ids are put on after the gather
-    n_local, e_local = local.pos.shape[0], local.col.shape[0]
-    node_buf = np.concatenate([np.ascontiguousarray(local.pos, np.float32).ravel(),
-                               np.ascontiguousarray(local.state, np.int32).view(np.float32),
-                               np.diff(local.row_ptr).astype(np.int32).view(np.float32)])
-    edge_buf = np.concatenate([np.ascontiguousarray(local.col, np.int32).view(np.float32),
-                               np.ascontiguousarray(local.weight, np.float32), np.ascontiguousarray(local.dist, np.float32)])
-    nodes_r = allgather_ragged(dist, torch, torch.from_numpy(node_buf), device)
-    edges_r = allgather_ragged(dist, torch, torch.from_numpy(edge_buf), device)
-    counts = [int(t.shape[0]) // 5 for t in nodes_r]
-    ecounts = [int(t.shape[0]) // 3 for t in edges_r]
-    pos = torch.cat([t[: 3 * c].view(c, 3) for t, c in zip(nodes_r, counts)])
-    state = torch.cat([t[3 * c: 4 * c] for t, c in zip(nodes_r, counts)]).view(torch.int32)
-    deg = torch.cat([t[4 * c: 5 * c] for t, c in zip(nodes_r, counts)]).view(torch.int32)
-    col_all = torch.cat([t[:c] for t, c in zip(edges_r, ecounts)]).view(torch.int32)
-    w_all = torch.cat([t[c: 2 * c] for t, c in zip(edges_r, ecounts)])
-    d_all = torch.cat([t[2 * c: 3 * c] for t, c in zip(edges_r, ecounts)])
+    # the tile graphs travel as they are (CSR, local ids, 12 bytes per edge), one ragged all-gather per array
+    # (packing them into one or two buffers was measured slower: the host-side packing and the slicing on the
+    # device cost more than the four extra collectives; merge 12 -> 22 ms at N = 2, 16 -> 36 ms at N = 4);
+    # global ids are put on after the gather
+    T = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dt))
+    pos, counts = allgather_concat(dist, torch, T(local.pos, np.float32), device)
+    state, _ = allgather_concat(dist, torch, T(local.state, np.int32), device)
+    deg, _ = allgather_concat(dist, torch, T(np.diff(local.row_ptr), np.int32), device)
+    col_all, ecounts = allgather_concat(dist, torch, T(local.col, np.int32), device)
+    w_all, _ = allgather_concat(dist, torch, T(local.weight, np.float32), device)
+    d_all, _ = allgather_concat(dist, torch, T(local.dist, np.float32), device)
     node_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
     if compute_device is not None:   # collectives on `device` (gloo: the host), the merge itself where the graph will live
         pos, state, deg, col_all, w_all, d_all = (x.to(compute_device) for x in (pos, state, deg, col_all, w_all, d_all))
