@@ -81,6 +81,27 @@ int main() {
     }
     bulk.build_bulk(xs.data(), ys.data(), n);
     CHECK(bulk.low() == seq.low() && bulk.high() == seq.high() && bulk.axis() == seq.axis(), "bulk != sequential (n=%d)", n);
+    // a tree grown elsewhere and adopted (the device build hands over lo / hi / parent / axis of k_kd_build)
+    trg_b200::OrderTree2D adopted;
+    std::vector<float> xy2(2 * (size_t)n);
+    for (int i = 0; i < n; ++i) { xy2[2 * i] = xs[i]; xy2[2 * i + 1] = ys[i]; }
+    {
+      std::vector<int> lo = seq.low(), hi = seq.high(), par = seq.parent();
+      std::vector<uint8_t> ax = seq.axis();
+      adopted.adopt(xy2.data(), n, std::move(lo), std::move(hi), std::move(par), std::move(ax));
+    }
+    // the hash grid filled in one go by banded helper threads (after a build), and re-used after clear()
+    trg_b200::NodeGrid grid2;
+    grid2.configure(0.f, 0.f, ext, ext, 0.6f);
+    for (int i = 0; i < std::min(n, 50); ++i) grid2.insert(xs[n - 1 - i], ys[n - 1 - i]);  // stale content
+    grid2.clear();
+    CHECK(grid2.nearest(1.f, 1.f).entry == -1 && grid2.count_in_range(1.f, 1.f, 5.f) == 0, "cleared grid still answers");
+    grid2.rebuild(xy2.data(), n, 5);
+    trg_b200::NodeGrid grid3;
+    grid3.configure(0.f, 0.f, ext, ext, 0.6f);
+    for (int i = 0; i < 7 && i < n; ++i) grid3.insert(ys[i], xs[i]);
+    grid3.clear();
+    for (int i = 0; i < n; ++i) grid3.insert(xs[i], ys[i]);   // the lazy clear happens on this first insert
     std::vector<int64_t> want;
     std::vector<int> got, got2;
     std::uniform_real_distribution<float> Q(-1.f, ext + 1.f);
@@ -91,7 +112,13 @@ int main() {
       const int64_t wn = ref.nearest(qx, qy);
       CHECK(seq.nearest(qx, qy) == (int)wn, "tree nearest");
       CHECK(bulk.nearest(qx, qy) == (int)wn, "bulk tree nearest");
+      CHECK(adopted.nearest(qx, qy) == (int)wn, "adopted tree nearest");
       auto g = grid.nearest(qx, qy);
+      for (const trg_b200::NodeGrid* gg : {&grid2, &grid3}) {
+        const auto g2 = gg->nearest(qx, qy);
+        CHECK(g2.d2 == g.d2 && g2.tie == g.tie && (g.tie || g2.entry == g.entry), "rebuilt / re-used grid nearest");
+        CHECK(gg->count_in_range(qx, qy, 0.6f) == grid.count_in_range(qx, qy, 0.6f), "rebuilt / re-used grid range count");
+      }
       const float dxw = xs[wn] - qx, dyw = ys[wn] - qy;
       float d2w = 0.f; d2w += dxw * dxw; d2w += dyw * dyw;
       CHECK(g.entry >= 0 && g.d2 == d2w, "grid nearest distance %g vs %g", g.d2, d2w);
@@ -123,6 +150,10 @@ int main() {
           std::reverse(c3.begin(), c3.end());
           bulk.order_like_range(c3, qx, qy);
           CHECK(c3 == got, "order_like_range on the bulk-built tree");
+          std::vector<int> c4;
+          grid2.for_each_in_range(qx, qy, r, [&](int e) { c4.push_back(e); });
+          adopted.order_like_range(c4, qx, qy);
+          CHECK(c4 == got, "order_like_range: rebuilt grid + adopted tree");
         }
         CHECK(grid.count_in_range(qx, qy, r) == (int)want.size(), "grid range count round=%d n=%d q=(%g,%g) r=%g got=%d want=%d", round, n, qx, qy, r, grid.count_in_range(qx, qy, r), (int)want.size());
       }

@@ -313,6 +313,7 @@ class OrderTree2D {
   const std::vector<int>& high() const { return hi_; }
   const std::vector<uint8_t>& axis() const { return axis_; }
   const std::vector<int>& payload() const { return payload_; }
+  const std::vector<int>& parent() const { return parent_; }
 
  private:
   struct Step { int node; float delta; bool second_half; };
