@@ -452,6 +452,36 @@ def run_product(a):
         dist.destroy_process_group()
 
 
+def pos_rows_report(t, mine, theirs):
+    """Node positions that differ from the reference's, row by row: x / y must still be bit-identical, and every
+    differing z must sit on a query K3 itself flags as an exact tie (two map points at the same float distance:
+    the reference returns whichever its kd-tree visits first, kdtree.c:303-350; K3 the lowest index)."""
+    import ctypes as C
+    from trg_planner_b200 import kernels as K   # (_pkg.load() ran in run_product)
+    bad = np.nonzero((mine.view(np.uint32) != theirs.view(np.uint32)).any(axis=1))[0]
+    xy_bad = int((mine[bad, :2].view(np.uint32) != theirs[bad, :2].view(np.uint32)).any(axis=1).sum())
+    rep = {"rows": int(len(mine)), "rows_differing": int(len(bad)), "rows_with_xy_differing": xy_bad,
+           "max_abs_z_diff": float(np.abs(mine[bad, 2] - theirs[bad, 2]).max()) if len(bad) else 0.0,
+           "build_z_ties_stat": int(t.stat("z_ties"))}
+    flagged = other = 0
+    if len(bad):
+        L = K.lib()
+        tl = C.CDLL(str(ROOT / "trg-planner_b200" / "lib" / "libtrg_b200.so"), mode=C.RTLD_GLOBAL)
+        tl.trg_device_map.restype = C.c_void_p
+        tl.trg_device_map.argtypes = [C.c_void_p, C.c_char_p]
+        m = C.c_void_p(tl.trg_device_map(t.h, b"global"))
+        xy = np.ascontiguousarray(mine[bad, :2], np.float32)
+        z, idx, tie = np.empty(len(bad), np.float32), np.empty(len(bad), np.int64), np.empty(len(bad), np.uint8)
+        rc = L.trgb_nearest_z_batch(m, K._p(xy), len(bad), K._p(z), K._p(idx), K._p(tie))
+        assert rc == 0, "trgb_nearest_z_batch"
+        flagged = int((tie != 0).sum())
+        rep["first_rows"] = [{"node_row": int(b), "xy": [float(v) for v in mine[b, :2]], "z_product": float(mine[b, 2]),
+                              "z_reference": float(theirs[b, 2]), "k3_tie_flag": int(tie[j])} for j, b in enumerate(bad[:8])]
+    rep["differing_rows_flagged_as_ties_by_k3"] = flagged
+    rep["every_differing_row_is_a_flagged_z_tie"] = bool(xy_bad == 0 and flagged == len(bad))
+    return rep
+
+
 def verify_against_reference(trg, t, tag, one_step, P):
     """Full-size parity: the CUDA build of this workload against the reference's own run on the CPU
     (profiles/_big/<tag>_ref.npz, written by scripts/ref_fullsize.py; git-ignored, travels with gpurun)."""
@@ -461,13 +491,35 @@ def verify_against_reference(trg, t, tag, one_step, P):
     ref = np.load(f)
     one_step(True)
     g = t.export()
-    out = {"reference_file": str(f.relative_to(ROOT)), "nodes": [int(g.n_nodes), int(len(ref["iter_ids"]))],
-           "edges": [int(g.n_edges), int(len(ref["col"]))], "rng_draws": [int(t.stat("rng_draws")), int(ref["rng_draws"])]}
+    slim = "slim" in ref.files   # big graphs: the arrays that must match bit for bit travel as SHA-256 digests
+    if slim:
+        import hashlib
+        want = dict(zip([str(x) for x in ref["digest_names"]], [str(x) for x in ref["digest_values"]]))
+        n_ref, e_ref = int(ref["n_nodes"]), int(ref["n_edges"])
+    else:
+        n_ref, e_ref = int(len(ref["iter_ids"])), int(len(ref["col"]))
+    out = {"reference_file": str(f.relative_to(ROOT)), "nodes": [int(g.n_nodes), n_ref],
+           "edges": [int(g.n_edges), e_ref], "rng_draws": [int(t.stat("rng_draws")), int(ref["rng_draws"])]}
     bit = {}
     for k in ("iter_ids", "pos", "state", "row_ptr", "col", "dist"):
-        x, y = getattr(g, k), ref[k]
-        bit[k] = bool(x.shape == y.shape and np.array_equal(x, y))
+        x = getattr(g, k)
+        if slim:
+            bit[k] = hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest()[:32] == want[k]
+        else:
+            y = ref[k]
+            bit[k] = bool(x.shape == y.shape and np.array_equal(x, y))
     out["bit_exact"] = bit
+    if slim:
+        out["bit_exact_by"] = "SHA-256 digests of the reference's arrays (scripts/ref_fullsize.py --slim)"
+        # the CSR is the reference's once its digests match: the path checks below walk the product's copy
+        csr = ({"row_ptr": g.row_ptr, "col": g.col, "dist": g.dist, "weight": ref["weight"]}
+               if bit["row_ptr"] and bit["col"] and bit["dist"] else None)
+    else:
+        csr = {"row_ptr": ref["row_ptr"], "col": ref["col"], "dist": ref["dist"], "weight": ref["weight"]}
+    z_tie_only = False
+    if not bit["pos"] and "pos" in ref.files and ref["pos"].shape == g.pos.shape:
+        out["pos_rows"] = pos_rows_report(t, g.pos, ref["pos"])
+        z_tie_only = out["pos_rows"]["every_differing_row_is_a_flagged_z_tie"]
     if g.weight.shape == ref["weight"].shape:
         rel = np.abs(g.weight - ref["weight"]) / np.maximum(np.abs(ref["weight"]), 1e-12)
         rel[(g.weight == 0) & (ref["weight"] == 0)] = 0
@@ -483,9 +535,12 @@ def verify_against_reference(trg, t, tag, one_step, P):
     def cost_of(ids):
         c = np.float32(0)
         for a_, b_ in zip(ids[:-1], ids[1:]):
-            e = ref["row_ptr"][a_] + np.nonzero(ref["col"][ref["row_ptr"][a_]:ref["row_ptr"][a_ + 1]] == b_)[0][0]
-            c = np.float32(c + np.float32(np.float32(np.float32(sf * ref["weight"][e]) + np.float32(1)) * ref["dist"][e]))
+            e = csr["row_ptr"][a_] + np.nonzero(csr["col"][csr["row_ptr"][a_]:csr["row_ptr"][a_ + 1]] == b_)[0][0]
+            c = np.float32(c + np.float32(np.float32(np.float32(sf * csr["weight"][e]) + np.float32(1)) * csr["dist"][e]))
         return float(c)
+    if csr is None:
+        out["pass"] = False
+        return out
     found_equal = bool(np.array_equal(r["found"], ref["path_found"]))
     known_equal = bool(np.array_equal(r["goal_known"], ref["goal_known"]))
     ends_equal = 0
@@ -510,7 +565,11 @@ def verify_against_reference(trg, t, tag, one_step, P):
     out["paths"] = {"queries": int(len(q)), "found_flags_equal": found_equal, "goal_known_equal": known_equal,
                     "start_goal_nodes_equal": ends_equal, "found": nf, "identical_node_sequences": same,
                     "different_sequence_equal_cost_within_1e-5": tie, "cost_within_1e-5": cost_ok, "worst_rel_cost_diff": worst}
-    out["pass"] = bool(all(bit.values()) and out["rng_draws"][0] == out["rng_draws"][1] and found_equal and known_equal
+    # node z: bit-exact, or differing only where K3 flagged an exact float-distance tie between two map points
+    # (DESIGN.md "Known deviations"; the reference's answer there depends on its kd-tree's visit order)
+    out["pos_ok_by"] = "bit-exact" if bit["pos"] else ("bit-exact but for flagged nearest-map-point ties" if z_tie_only else "MISMATCH")
+    bit_ok = all(v for k, v in bit.items() if k != "pos") and (bit["pos"] or z_tie_only)
+    out["pass"] = bool(bit_ok and out["rng_draws"][0] == out["rng_draws"][1] and found_equal and known_equal
                        and ends_equal == nf and cost_ok == nf and out.get("edge_risk", {}).get("fraction_beyond", 1.0) <= 0.005)
     return out
 

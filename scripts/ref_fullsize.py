@@ -28,6 +28,7 @@ CONFIGS = {  # tag: (side, map seed, n queries, query seed)  — SURVEY.md §8d
     "c2": (3163, 2, 1000, 7),
     "c2s": (1000, 2, 100, 7),     # the 1 M-point sample bench.py's default CPU leg uses
     "c3t": (3536, 3, 1000, 8),    # one 12.5 M-point tile of C3's generator
+    "c3": (7072, 3, 200, 8),      # the whole 50 M-point C3 map (the first 200 of its 10 000 queries); written --slim
 }
 
 
@@ -40,6 +41,8 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--round", default="r02")
     ap.add_argument("--kind", default="ref", choices=["ref", "refkd", "port"])
+    ap.add_argument("--slim", action="store_true",
+                    help="keep only what cannot be compared by digest (edge risks, queries, paths) + the digests of the rest")
     a = ap.parse_args()
     side, map_seed, nq, q_seed = CONFIGS[a.config]
     trg = _pkg.load()
@@ -73,8 +76,18 @@ def main():
                   goal_known=np.array([p["goal_known"] for p in plans]))
     big = ROOT / "profiles" / "_big"
     big.mkdir(parents=True, exist_ok=True)
-    np.savez(big / f"{a.config}_ref.npz", seed=42, start=np.asarray(start, np.float32), side=side, map_seed=map_seed,
-             rng_draws=o.stat("rng_draws"), **arrays)
+    digests = {k: digest(v) for k, v in arrays.items()}
+    if a.slim or a.config == "c3":
+        # a 50 M-point graph is 0.4 GB: the arrays that must match bit for bit travel as SHA-256 digests, only the
+        # edge risks (compared within 1e-5), the paths and the node positions (so that a nearest-map-point tie, the one
+        # documented deviation, can be counted row by row) travel as data
+        keep = {k: arrays[k] for k in ("pos", "weight", "queries", "path_ids", "path_off", "path_found", "path_len", "path_risk", "direct", "goal_known")}
+        np.savez_compressed(big / f"{a.config}_ref.npz", seed=42, start=np.asarray(start, np.float32), side=side, map_seed=map_seed,
+                            rng_draws=o.stat("rng_draws"), n_nodes=g.n_nodes, n_edges=g.n_edges, slim=1,
+                            digest_names=np.array(sorted(digests)), digest_values=np.array([digests[k] for k in sorted(digests)]), **keep)
+    else:
+        np.savez(big / f"{a.config}_ref.npz", seed=42, start=np.asarray(start, np.float32), side=side, map_seed=map_seed,
+                 rng_draws=o.stat("rng_draws"), **arrays)
     rec = {
         "what": "the reference's own unmodified trg.cpp + kdtree.c (oracle/_ref/libtrg_ref.so) on the full configuration"
                 if a.kind == "ref" else f"oracle kind {a.kind}",
@@ -86,7 +99,7 @@ def main():
         "nodes": g.n_nodes, "edges": g.n_edges, "rng_draws": o.stat("rng_draws"),
         "paths_found": int(sum(p["found"] for p in plans)),
         "mean_path_nodes": float(np.mean([len(p["ids"]) for p in plans if p["found"]] or [0])),
-        "digests": {k: digest(v) for k, v in arrays.items()},
+        "digests": digests,
     }
     out = ROOT / "profiles" / f"{a.round}_{a.config}_reference_cpu.json"
     out.write_text(json.dumps(rec, indent=1))
