@@ -60,6 +60,9 @@ def run_c4(a):
     t.set_global_map(pts)
     w0 = time.perf_counter(); t.init_graph((ext / 2, ext / 2, 0.0)); w1 = time.perf_counter()
     nn, ne = t.counts()
+    ver = _C4Verify(t) if getattr(a, "verify", False) else None
+    if ver:
+        ver.check(-1)
     rng = np.random.default_rng(9)
     lat, sizes = [], []
     l0 = None
@@ -75,6 +78,8 @@ def run_c4(a):
         s2 = time.perf_counter()
         if k >= a.warmup:
             lat.append((s1 - s0, s2 - s1)); sizes.append(int(scan.shape[0]))
+        if ver:
+            ver.check(k)   # (between the timed calls of two scans: exports the whole global graph)
     e1.record(); torch.cuda.synchronize()
     launches = K.launch_count() - l0
     host = {kk: (t.stat(kk) - st0[kk]) / max(1, a.steps) for kk in C4_STATS}
@@ -112,7 +117,79 @@ def run_c4(a):
                     "note": "the scan arrives in host memory (TRG::setLocalMap takes a host cloud): value and e2e coincide"},
             "gpu_launches": int(launches), "device_ms_total": e0.elapsed_time(e1), "cpu_baseline": cpu,
             "roofline": None, "clocks": None}
+    if ver:
+        line["verify"] = ver.report()
     print(json.dumps(line), flush=True)
+
+
+class _C4Verify:
+    """--verify: the global graph after the build and after every scan against the reference's own full-size run of
+    the same scans (profiles/_big/c4_ref.npz + profiles/r02_c4_reference_cpu.json, scripts/ref_fullsize.py --config c4):
+    SHA-256 digests of ids, positions, states, CSR and edge lengths, draw counts; node positions and edge risks of
+    the last scan as data."""
+    KEYS = ("iter_ids", "pos", "state", "row_ptr", "col", "dist")
+
+    def __init__(self, t):
+        import hashlib
+        self.h = hashlib
+        self.t = t
+        f = ROOT / "profiles" / "_big" / "c4_ref.npz"
+        self.ref = np.load(f) if f.exists() else None
+        self.scans = {int(r["scan"]): r for r in json.loads(str(self.ref["scans"]))} if self.ref is not None else {}
+        self.rows = []
+        self.last = None
+
+    def check(self, k):
+        if k not in self.scans:
+            return
+        try:
+            r = self.scans[k]
+            g = self.t.export()
+            row = {"scan": k, "nodes": [int(g.n_nodes), int(r["nodes"])], "edges": [int(g.n_edges), int(r["edges"])],
+                   "rng_draws": [int(self.t.stat("rng_draws")), int(r["rng_draws"])]}
+            for key in self.KEYS:
+                d = self.h.sha256(np.ascontiguousarray(getattr(g, key)).tobytes()).hexdigest()[:32]
+                row[key] = bool(d == r["digests"][key])
+            self.rows.append(row)
+            self.last = (k, g)
+        except Exception as ex:   # a verification bug must not cost the run
+            self.rows.append({"scan": k, "error": repr(ex)})
+
+    def report(self):
+        if self.ref is None:
+            return {"skipped": "profiles/_big/c4_ref.npz not present (run scripts/ref_fullsize.py --config c4)"}
+        out = {"reference_file": "profiles/_big/c4_ref.npz", "per_scan": self.rows}
+        ok_rows = [r for r in self.rows if "error" not in r]
+        exact = [all(r[k] for k in self.KEYS if k != "pos") and r["nodes"][0] == r["nodes"][1] and r["edges"][0] == r["edges"][1]
+                 and r["rng_draws"][0] == r["rng_draws"][1] for r in ok_rows]
+        out["scans_compared"] = len(ok_rows)
+        out["scans_bit_exact_but_pos"] = int(sum(exact))
+        out["scans_pos_bit_exact"] = int(sum(bool(r["pos"]) for r in ok_rows))
+        pos_ok = all(bool(r["pos"]) for r in ok_rows)
+        try:
+            k, g = self.last
+            if k == max(self.scans):   # the reference kept the arrays of its last scan
+                rp, rw = self.ref["pos"], self.ref["weight"]
+                if rp.shape == g.pos.shape:
+                    bad = np.nonzero((g.pos.view(np.uint32) != rp.view(np.uint32)).any(axis=1))[0]
+                    xy_bad = int((g.pos[bad, :2].view(np.uint32) != rp[bad, :2].view(np.uint32)).any(axis=1).sum())
+                    zt = max(0, int(self.t.stat("z_ties")))
+                    out["pos_rows_last_scan"] = {"rows": int(len(rp)), "rows_differing": int(len(bad)), "rows_with_xy_differing": xy_bad,
+                                                 "max_abs_z_diff": float(np.abs(g.pos[bad, 2] - rp[bad, 2]).max()) if len(bad) else 0.0,
+                                                 "z_ties_flagged_since_the_build": zt}
+                    pos_ok = pos_ok or (xy_bad == 0 and len(bad) <= zt)
+                if rw.shape == g.weight.shape:
+                    rel = np.abs(g.weight - rw) / np.maximum(np.abs(rw), 1e-12)
+                    rel[(g.weight == 0) & (rw == 0)] = 0
+                    out["edge_risk_last_scan"] = {"tolerance": 1e-5, "edges": int(rel.size), "beyond_tolerance": int((rel > 1e-5).sum()),
+                                                  "max_rel": float(rel.max()) if rel.size else 0.0,
+                                                  "fraction_beyond": float((rel > 1e-5).mean()) if rel.size else 0.0,
+                                                  "threshold_crossings_at_0.1": int(((g.weight == 0) != (rw == 0)).sum())}
+        except Exception as ex:
+            out["last_scan_error"] = repr(ex)
+        out["pass"] = bool(len(ok_rows) == len(self.rows) and len(ok_rows) > 0 and all(exact) and pos_ok
+                           and out.get("edge_risk_last_scan", {}).get("fraction_beyond", 1.0) <= 0.005)
+        return out
 
 
 def run_c5(a):

@@ -36,14 +36,73 @@ def digest(a: np.ndarray) -> str:
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:32]
 
 
+C4 = dict(side=4473, map_seed=4, scan_seed=9, half=22.36, scans=7)   # = scripts/bench_extra.py run_c4 (2 warm-up + 5 timed scans)
+C4_KEYS = ("iter_ids", "pos", "state", "row_ptr", "col", "dist")
+
+
+def run_c4(a):
+    """Config #4 at full size: the reference builds the TRG of the 20 M-point map, then takes the 200 k-point scans of
+    bench.py --workload c4 one by one (setLocalMap + updateGraph, trg.cpp:195-231, 456-489). The global graph after
+    every scan is recorded as SHA-256 digests; the last one also keeps its node positions and edge risks as data."""
+    sys.path.insert(0, str(ROOT / "scripts"))
+    from bench_extra import _scans
+    trg = _pkg.load()
+    P = trg.MOUNTAIN
+    side = C4["side"]
+    pts = trg.terrain.mountain(side, h=0.1, seed=C4["map_seed"])
+    ext = side * 0.1
+    o = _pkg.load_oracle().oracle(P, kind=a.kind)
+    o.seed(42)
+    t0 = time.perf_counter()
+    o.set_global_map(pts)
+    t1 = time.perf_counter()
+    assert o.init_graph((ext / 2, ext / 2, 0.0)) == 0
+    t2 = time.perf_counter()
+    rng = np.random.default_rng(C4["scan_seed"])
+    per_scan = []
+    g = o.export()
+    rec_scans = [{"scan": -1, "nodes": g.n_nodes, "edges": g.n_edges, "rng_draws": o.stat("rng_draws"),
+                  "digests": {k: digest(getattr(g, k)) for k in C4_KEYS}}]
+    for k, (cx, cy, scan) in enumerate(_scans(pts, ext, C4["scans"], C4["half"], rng, ext / 2 - 50.0)):
+        s0 = time.perf_counter()
+        o.set_local_map(cx, cy, scan)
+        s1 = time.perf_counter()
+        o.update_graph()
+        s2 = time.perf_counter()
+        g = o.export()
+        ln, le = o.counts("local")
+        per_scan.append((s1 - s0, s2 - s1))
+        rec_scans.append({"scan": k, "scan_points": int(scan.shape[0]), "set_local_map_s": s1 - s0, "update_graph_s": s2 - s1,
+                          "nodes": g.n_nodes, "edges": g.n_edges, "local_nodes": ln, "local_edges": le,
+                          "rng_draws": o.stat("rng_draws"), "digests": {k: digest(getattr(g, k)) for k in C4_KEYS}})
+        print(json.dumps(rec_scans[-1]), flush=True)
+    big = ROOT / "profiles" / "_big"
+    big.mkdir(parents=True, exist_ok=True)
+    np.savez_compressed(big / "c4_ref.npz", slim=1, side=side, scans=json.dumps(rec_scans), pos=g.pos, weight=g.weight)
+    L = np.array(per_scan)
+    T = L[2:] if len(L) > 2 else L
+    rec = {"what": "the reference's own unmodified trg.cpp + kdtree.c (oracle/_ref/libtrg_ref.so) on config #4 at full size"
+                   if a.kind == "ref" else f"oracle kind {a.kind}",
+           "config": "c4", "side": side, "points": int(pts.shape[0]), "mt19937_seed": 42, "cores_used": 1,
+           "host_cores": os.cpu_count(), "set_global_map_s": round(t1 - t0, 3), "init_graph_s": round(t2 - t1, 3),
+           "per_scan_ms": {"set_local_map": float(1e3 * T[:, 0].mean()), "update_graph": float(1e3 * T[:, 1].mean()),
+                           "note": "mean of scans 2..6 (the five the GPU arm times)"},
+           "scans": rec_scans}
+    out = ROOT / "profiles" / f"{a.round}_c4_reference_cpu.json"
+    out.write_text(json.dumps(rec, indent=1))
+    print(json.dumps({k: v for k, v in rec.items() if k != "scans"}))
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS) + ["c4"])
     ap.add_argument("--round", default="r02")
     ap.add_argument("--kind", default="ref", choices=["ref", "refkd", "port"])
     ap.add_argument("--slim", action="store_true",
                     help="keep only what cannot be compared by digest (edge risks, queries, paths) + the digests of the rest")
     a = ap.parse_args()
+    if a.config == "c4":
+        return run_c4(a)
     side, map_seed, nq, q_seed = CONFIGS[a.config]
     trg = _pkg.load()
     P = trg.MOUNTAIN
