@@ -181,10 +181,14 @@ class _C4Verify:
                 if rw.shape == g.weight.shape:
                     rel = np.abs(g.weight - rw) / np.maximum(np.abs(rw), 1e-12)
                     rel[(g.weight == 0) & (rw == 0)] = 0
+                    # `if (weight < 0.1) weight = 0` (trg.cpp:360-362) is a step: a risk within rounding of 0.1 lands on either side
+                    cross = (g.weight == 0) != (rw == 0)
                     out["edge_risk_last_scan"] = {"tolerance": 1e-5, "edges": int(rel.size), "beyond_tolerance": int((rel > 1e-5).sum()),
-                                                  "max_rel": float(rel.max()) if rel.size else 0.0,
+                                                  "max_rel": float(rel[~cross].max()) if (~cross).any() else 0.0,
+                                                  "max_rel_note": "over the edges on the same side of the 0.1 step",
                                                   "fraction_beyond": float((rel > 1e-5).mean()) if rel.size else 0.0,
-                                                  "threshold_crossings_at_0.1": int(((g.weight == 0) != (rw == 0)).sum())}
+                                                  "threshold_crossings_at_0.1": int(cross.sum()),
+                                                  "nonzero_side_of_the_crossings": [float(x) for x in np.maximum(g.weight[cross], rw[cross])[:16]]}
         except Exception as ex:
             out["last_scan_error"] = repr(ex)
         out["pass"] = bool(len(ok_rows) == len(self.rows) and len(ok_rows) > 0 and all(exact) and pos_ok
