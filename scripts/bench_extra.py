@@ -102,6 +102,16 @@ def run_c4(a):
                "kind": "reference" if kind == "ref" else "port", "per_scan_ms": cms,
                "sample": f"the reference's setLocalMap + updateGraph ({'libtrg_ref.so' if kind == 'ref' else 'restated oracle'}) on a 1 M-point prebuilt "
                          f"map ({o.counts()[0]} nodes), 3 scans of {int(np.mean([x[1] for x in cl[1:]]))} points; 1 thread; host has {os.cpu_count()} cores"}
+    full = ROOT / "profiles" / "r02_c4_reference_cpu.json"
+    if cpu is not None and full.exists():
+        try:
+            fr = json.loads(full.read_text())
+            ms = fr["per_scan_ms"]["set_local_map"] + fr["per_scan_ms"]["update_graph"]
+            cpu["full_config_record"] = {"file": str(full.relative_to(ROOT)), "map_points": fr["points"], "per_scan_ms": ms,
+                                         "scan_points_per_sec": float(np.mean([s_["scan_points"] for s_ in fr["scans"][3:]])) / (ms * 1e-3),
+                                         "note": "same code on the whole 20 M-point map and the same scans, run once in the build container"}
+        except Exception:
+            pass
     line = {"metric": "trg_update_scan_points_per_sec", "value": float(np.mean(sizes)) / (per_scan_ms * 1e-3), "unit": "scan points/s",
             "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": per_scan_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
